@@ -1,0 +1,166 @@
+/*
+ * b200env.h -- C ABI of the B200-native batched environment engine.
+ *
+ * This is the drop-in boundary for the environment-step hot path of
+ * HKPolyU-UAV/ReinforcementLearningPlatform.  The reference has no FFI of its
+ * own: its boundary is the duck-typed Python object contract of
+ * `algorithm/rl_base.py:4-162` (attributes + reset/step_update/get_state/
+ * get_reward/is_Terminal).  Each entry point below names the reference
+ * method(s) it replaces; the Python classes in
+ * `reinforcementlearningplatform_b200/` re-expose the rl_base attribute names
+ * on top of these calls.
+ *
+ * Conventions
+ *   - every pointer inside b200env_io is a DEVICE pointer; `params` is a HOST
+ *     pointer to one of the POD structs below (copied into kernel-argument
+ *     space at launch);
+ *   - all per-instance arrays are struct-of-arrays, field-major: element
+ *     (field f, instance i) of an array with F fields lives at [f * n + i];
+ *   - `dtype` selects the arithmetic/storage type of state, action, dis, obs
+ *     and reward (B200ENV_F64 or B200ENV_F32).  `time` is always float64 and
+ *     is accumulated with plain IEEE additions exactly as the reference does
+ *     (`self.time += h`), so time-out flags are bit-exact in both modes;
+ *   - no call blocks: work is enqueued on `stream` (a cudaStream_t, may be 0);
+ *   - return value: 0 on success, a negative B200ENV_E* code otherwise.  No
+ *     CPU fallback exists: without a CUDA device every launch returns
+ *     B200ENV_ECUDA.
+ */
+#ifndef B200ENV_H
+#define B200ENV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ enums */
+
+enum b200env_id {
+    B200ENV_CARTPOLE      = 0, /* environment/CartPole/CartPole.py, CartPoleAngleOnly.py (+ PPO2 demo copy) */
+    B200ENV_FAS           = 1, /* environment/FlightAttitudeSimulator/FlightAttitudeSimulator.py */
+    B200ENV_SOI           = 2, /* environment/SecondOrderIntegration/SecondOrderIntegration.py */
+    B200ENV_BALLBALANCER  = 3, /* environment/BallBalancer/BallBalancer1D.py */
+    B200ENV_TWOLINK       = 4, /* environment/RobotManipulator/TwoLinkManipulator.py */
+    B200ENV_UGV           = 5, /* environment/UGV/UGVForward.py, UGVBidirectional.py */
+    B200ENV_UGVO          = 6, /* environment/UGVForwardObstacleAvoidance/UGVForwardObstacleAvoidance.py */
+    B200ENV_UAV_ATT       = 7, /* environment/UavFntsmcParam/uav_att_ctrl_RL.py (+ uav.py, FNTSMC.py, ref_cmd.py) */
+    B200ENV_UAV_POS       = 8, /* environment/UavFntsmcParam/uav_pos_ctrl_RL.py (+ uav.py, FNTSMC.py, ref_cmd.py) */
+    B200ENV_UAVROBUST     = 9, /* environment/UavRobust/Uav{Hover,HoverOuterLoop,InnerLoop,TrackingOuterLoop}.py */
+    B200ENV_COUNT         = 10
+};
+
+enum b200env_dtype { B200ENV_F64 = 0, B200ENV_F32 = 1 };
+
+enum b200env_err {
+    B200ENV_OK      =  0,
+    B200ENV_EENV    = -1, /* unknown env id / variant */
+    B200ENV_EDTYPE  = -2,
+    B200ENV_EPARAMS = -3, /* params_bytes does not match the struct of this env */
+    B200ENV_ENULL   = -4, /* a required pointer is NULL */
+    B200ENV_ECUDA   = -5, /* CUDA error at launch; see b200env_last_cuda_error() */
+    B200ENV_ESIZE   = -6  /* n_envs <= 0 or too large */
+};
+
+/* step flags */
+#define B200ENV_AUTO_RESET 1u /* re-initialise an instance in the same call that sets its `done`
+                                 (in-kernel Philox draw with the reference's reset distribution);
+                                 replaces the `if env.is_terminal: env.reset(True)` branch of the
+                                 train.py loops (e.g. demonstration/PPO2/PPO2-4-CartPoleAngleOnly/train.py:187-191) */
+
+/* ------------------------------------------------------------- I/O bundle */
+
+typedef struct b200env_io {
+    void          *state;      /* [state_fields][n]  dtype   persistent per-instance state              */
+    double        *time;       /* [n]                f64     `self.time`                                */
+    uint32_t      *episode;    /* [n]                u32     episode counter = Philox counter for reset */
+    const void    *action;     /* [action_dim][n]    dtype   (step only)                                */
+    const void    *dis;        /* [dis_dim][n]       dtype   injected disturbance, may be NULL          */
+    void          *obs;        /* [obs_dim][n]       dtype   `current_state` (pre-step obs), may be NULL*/
+    void          *next_obs;   /* [obs_dim][n]       dtype   `next_state`  (s' of the transition)       */
+    void          *reward;     /* [n]                dtype   `reward`                                   */
+    uint8_t       *done;       /* [n]                u8      `is_terminal`                              */
+    int32_t       *flag;       /* [n]                i32     `terminal_flag`                            */
+    void          *reset_obs;  /* [obs_dim][n]       dtype   obs the policy sees next: s' or, where an
+                                                             auto-reset happened, the reset obs; may be NULL */
+} b200env_io;
+
+/* ------------------------------------------------------ per-env parameters */
+/* All parameter structs are plain doubles/ints.  The host mirror fills them
+ * from the attribute names of the reference classes; thresholds that the
+ * reference computes from constants (e.g. `theta_max + deg2rad(1)`) are
+ * evaluated on the host with the same expression so comparisons are
+ * bit-identical. */
+
+/* CartPole family.  variant 0: CartPole.py (obs 4); 1: CartPoleAngleOnly.py (obs 2, time-loop);
+ * 2: demonstration/PPO2/PPO2-4-CartPoleAngleOnly/cartpole_angleonly.py (obs 2, single RK4 step). */
+typedef struct b200_cartpole_params {
+    double M, m, g, ell, kf;            /* CartPole.py:34-38 */
+    double dt, time_max;                /* CartPole.py:41-42 */
+    double theta_max, dtheta_max, x_max, dx_max; /* obs normalisers, CartPole.py:26-29 */
+    double static_gain;                 /* CartPole.py:31 */
+    double norm_boundless;              /* CartPoleAngleOnly.py:28 (dtheta normaliser = 4) */
+    double theta_term_hi;               /* theta_max + deg2rad(1)                       CartPole.py:167 */
+    double theta_term_lo;               /* -dtheta_max - deg2rad(1) (sic, N2) or -thetaMax - deg2rad(1) */
+    double reset_theta_lo, reset_theta_hi; /* U(lo,hi) for theta0, CartPole.py:272 */
+    double reset_x_lo, reset_x_hi;         /* U(lo,hi) for x0,     CartPole.py:273 (0,0 for AngleOnly) */
+    int32_t variant;
+    int32_t pad_;
+} b200_cartpole_params;
+
+/* state fields of the CartPole family: theta, dtheta, x, dx */
+#define B200_CARTPOLE_STATE_FIELDS 4
+
+/* ---------------------------------------------------------------- queries */
+
+/* sizes of the SoA arrays of one env family/variant; any out pointer may be NULL */
+B200_API int b200env_dims(int env_id, int variant, int *state_fields, int *obs_dim, int *action_dim, int *dis_dim);
+
+/* sizeof() of the params struct the library was compiled with (ABI check) */
+B200_API size_t b200env_params_bytes(int env_id);
+
+/* last cudaError_t seen by a failed launch in this thread (0 if none) */
+B200_API int b200env_last_cuda_error(void);
+B200_API const char *b200env_version(void);
+
+/* ------------------------------------------------------------- hot path */
+
+/* One control period for n instances: replaces `env.step_update(action)` of every
+ * environment (algorithm/rl_base.py:126; e.g. CartPole.py:257-264) -- obs = get_state(),
+ * rk44(action), is_Terminal(), next_obs = get_state(), get_reward() -- and, with
+ * B200ENV_AUTO_RESET, the following `env.reset(True)`.
+ * For the UavFntsmcParam envs the default action is the 8 controller gains and the call
+ * fuses `get_param_from_actor(a)` + `generate_action_4_uav()`/`att_control()` +
+ * `step_update()` (train.py:292-297 of PPO2-4-UavFntsmcParamPos). */
+B200_API int b200env_step(int env_id, int dtype, int64_t n_envs,
+                 const void *params, size_t params_bytes,
+                 const b200env_io *io, uint32_t flags,
+                 uint64_t seed, int64_t env_index_offset, void *cuda_stream);
+
+/* Replaces `env.reset(random=True)` (rl_base.py:161; e.g. CartPole.py:266-295) for the
+ * instances whose mask byte is non-zero (mask == NULL: all).  Draws the reference's
+ * reset distribution from Philox4x32-10 keyed by (seed, env_index_offset + i, episode[i]),
+ * increments episode[i], zeroes time[i] and writes the initial observation to
+ * io->next_obs (if not NULL). */
+B200_API int b200env_reset(int env_id, int dtype, int64_t n_envs,
+                  const void *params, size_t params_bytes,
+                  const b200env_io *io, const uint8_t *mask,
+                  uint64_t seed, int64_t env_index_offset, void *cuda_stream);
+
+/* Replaces `env.get_state()` (rl_base.py:158): observation of the current state into
+ * io->next_obs without stepping.  Used after the caller injected a state. */
+B200_API int b200env_observe(int env_id, int dtype, int64_t n_envs,
+                    const void *params, size_t params_bytes,
+                    const b200env_io *io, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ENV_H */

@@ -1,0 +1,96 @@
+"""ctypes binding of libb200env.so (C ABI declared in include/b200env.h).
+
+The library is the product: there is no Python/torch fallback.  If the shared
+object is missing this module raises, and every env class fails with it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200env.so")
+
+# enum b200env_id
+CARTPOLE, FAS, SOI, BALLBALANCER, TWOLINK, UGV, UGVO, UAV_ATT, UAV_POS, UAVROBUST = range(10)
+F64, F32 = 0, 1
+AUTO_RESET = 1
+
+ERRORS = {
+    0: "ok",
+    -1: "B200ENV_EENV: unknown env id / variant",
+    -2: "B200ENV_EDTYPE: bad dtype",
+    -3: "B200ENV_EPARAMS: params struct size mismatch (ABI drift between Python mirror and library)",
+    -4: "B200ENV_ENULL: required pointer is NULL",
+    -5: "B200ENV_ECUDA: CUDA launch failed",
+    -6: "B200ENV_ESIZE: bad n_envs",
+}
+
+
+class B200EnvError(RuntimeError):
+    pass
+
+
+class IO(C.Structure):
+    """struct b200env_io"""
+    _fields_ = [(k, C.c_void_p) for k in (
+        "state", "time", "episode", "action", "dis", "obs", "next_obs", "reward", "done", "flag", "reset_obs")]
+
+
+class CartPoleParams(C.Structure):
+    """struct b200_cartpole_params"""
+    _fields_ = [(k, C.c_double) for k in (
+        "M", "m", "g", "ell", "kf", "dt", "time_max", "theta_max", "dtheta_max", "x_max", "dx_max",
+        "static_gain", "norm_boundless", "theta_term_hi", "theta_term_lo",
+        "reset_theta_lo", "reset_theta_hi", "reset_x_lo", "reset_x_hi")] + [
+        ("variant", C.c_int32), ("pad_", C.c_int32)]
+
+
+PARAMS_OF = {CARTPOLE: CartPoleParams}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libb200env.so once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200EnvError(
+            f"{LIB_PATH} not found: the CUDA engine is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C "
+            "reinforcementlearningplatform_b200/csrc`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, u64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_uint64, C.c_size_t
+    ip = C.POINTER(C.c_int)
+    lib.b200env_version.restype = C.c_char_p
+    lib.b200env_version.argtypes = []
+    lib.b200env_last_cuda_error.restype = i32
+    lib.b200env_last_cuda_error.argtypes = []
+    lib.b200env_params_bytes.restype = sz
+    lib.b200env_params_bytes.argtypes = [i32]
+    lib.b200env_dims.restype = i32
+    lib.b200env_dims.argtypes = [i32, i32, ip, ip, ip, ip]
+    lib.b200env_step.restype = i32
+    lib.b200env_step.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), u32, u64, i64, vp]
+    lib.b200env_reset.restype = i32
+    lib.b200env_reset.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), vp, u64, i64, vp]
+    lib.b200env_observe.restype = i32
+    lib.b200env_observe.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        extra = ""
+        if rc == -5:
+            extra = f" (cudaError {load().b200env_last_cuda_error()})"
+        raise B200EnvError(f"{what}: {ERRORS.get(rc, rc)}{extra}")
+
+
+def dims(env_id: int, variant: int = 0):
+    sf, od, ad, dd = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    check(load().b200env_dims(env_id, variant, C.byref(sf), C.byref(od), C.byref(ad), C.byref(dd)), "b200env_dims")
+    return sf.value, od.value, ad.value, dd.value

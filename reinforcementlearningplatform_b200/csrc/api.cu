@@ -1,0 +1,78 @@
+// api.cu -- extern "C" surface of libb200env.so (see include/b200env.h).
+// Dispatches on env id to the family launchers; no torch types, no state.
+#include "common.cuh"
+
+thread_local int g_b200_last_cuda_error = 0;
+
+namespace {
+struct Family {
+    size_t params_bytes;
+    int (*dims)(int, int *, int *, int *, int *);
+    int (*step)(int, int64_t, const void *, const b200env_io *, uint32_t, uint64_t, int64_t, cudaStream_t);
+    int (*reset)(int, int64_t, const void *, const b200env_io *, const uint8_t *, uint64_t, int64_t, cudaStream_t);
+    int (*observe)(int, int64_t, const void *, const b200env_io *, cudaStream_t);
+};
+
+#define FAM(name, P) {sizeof(P), name##_dims, name##_step, name##_reset, name##_observe}
+const Family *family(int env_id) {
+    static const Family table[B200ENV_COUNT] = {
+        FAM(cartpole, b200_cartpole_params),
+    };
+    if (env_id < 0 || env_id >= B200ENV_COUNT) return nullptr;
+    const Family *f = &table[env_id];
+    return f->step ? f : nullptr;
+}
+
+int check_common(const Family *f, int dtype, int64_t n, const void *params, size_t bytes, const b200env_io *io) {
+    if (!f) return B200ENV_EENV;
+    if (dtype != B200ENV_F64 && dtype != B200ENV_F32) return B200ENV_EDTYPE;
+    if (n <= 0 || n > ((int64_t)1 << 40)) return B200ENV_ESIZE;
+    if (!params || !io) return B200ENV_ENULL;
+    if (bytes != f->params_bytes) return B200ENV_EPARAMS;
+    return B200ENV_OK;
+}
+} // namespace
+
+extern "C" {
+
+const char *b200env_version(void) { return "b200env 0.1 (sm_100a)"; }
+
+int b200env_last_cuda_error(void) { return g_b200_last_cuda_error; }
+
+size_t b200env_params_bytes(int env_id) {
+    const Family *f = family(env_id);
+    return f ? f->params_bytes : 0;
+}
+
+int b200env_dims(int env_id, int variant, int *state_fields, int *obs_dim, int *action_dim, int *dis_dim) {
+    const Family *f = family(env_id);
+    if (!f) return B200ENV_EENV;
+    return f->dims(variant, state_fields, obs_dim, action_dim, dis_dim);
+}
+
+int b200env_step(int env_id, int dtype, int64_t n_envs, const void *params, size_t params_bytes,
+                 const b200env_io *io, uint32_t flags, uint64_t seed, int64_t env_index_offset, void *cuda_stream) {
+    const Family *f = family(env_id);
+    int rc = check_common(f, dtype, n_envs, params, params_bytes, io);
+    if (rc) return rc;
+    return f->step(dtype, n_envs, params, io, flags, seed, env_index_offset, (cudaStream_t)cuda_stream);
+}
+
+int b200env_reset(int env_id, int dtype, int64_t n_envs, const void *params, size_t params_bytes,
+                  const b200env_io *io, const uint8_t *mask, uint64_t seed, int64_t env_index_offset,
+                  void *cuda_stream) {
+    const Family *f = family(env_id);
+    int rc = check_common(f, dtype, n_envs, params, params_bytes, io);
+    if (rc) return rc;
+    return f->reset(dtype, n_envs, params, io, mask, seed, env_index_offset, (cudaStream_t)cuda_stream);
+}
+
+int b200env_observe(int env_id, int dtype, int64_t n_envs, const void *params, size_t params_bytes,
+                    const b200env_io *io, void *cuda_stream) {
+    const Family *f = family(env_id);
+    int rc = check_common(f, dtype, n_envs, params, params_bytes, io);
+    if (rc) return rc;
+    return f->observe(dtype, n_envs, params, io, (cudaStream_t)cuda_stream);
+}
+
+} // extern "C"

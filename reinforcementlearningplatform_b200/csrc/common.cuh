@@ -1,0 +1,133 @@
+// common.cuh -- shared device helpers of the batched environment kernels.
+//
+// One thread owns one environment instance; all per-instance arrays are
+// field-major SoA ([field][n]) so that consecutive threads touch consecutive
+// addresses (fully coalesced 8 B / 4 B accesses).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/b200env.h"
+
+#define B200_BLOCK 128
+
+// ---------------------------------------------------------------------------
+// Math traits: the fp64 path uses the libdevice double routines (1-2 ulp), the
+// fp32 path the float ones.  No fast-math intrinsics: the fp32 tolerance is
+// stated per env in the tests.
+// ---------------------------------------------------------------------------
+template <typename T> struct Mth;
+
+template <> struct Mth<double> {
+    static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
+    static __device__ __forceinline__ double cos(double x) { return ::cos(x); }
+    static __device__ __forceinline__ void sincos(double x, double *s, double *c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ double tan(double x) { return ::tan(x); }
+    static __device__ __forceinline__ double tanh(double x) { return ::tanh(x); }
+    static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
+    static __device__ __forceinline__ double acos(double x) { return ::acos(x); }
+    static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+    static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+    static __device__ __forceinline__ double min(double a, double b) { return ::fmin(a, b); }
+    static __device__ __forceinline__ double max(double a, double b) { return ::fmax(a, b); }
+};
+
+template <> struct Mth<float> {
+    static __device__ __forceinline__ float sin(float x) { return ::sinf(x); }
+    static __device__ __forceinline__ float cos(float x) { return ::cosf(x); }
+    static __device__ __forceinline__ void sincos(float x, float *s, float *c) { ::sincosf(x, s, c); }
+    static __device__ __forceinline__ float tan(float x) { return ::tanf(x); }
+    static __device__ __forceinline__ float tanh(float x) { return ::tanhf(x); }
+    static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }
+    static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
+    static __device__ __forceinline__ float asin(float x) { return ::asinf(x); }
+    static __device__ __forceinline__ float acos(float x) { return ::acosf(x); }
+    static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
+    static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
+    static __device__ __forceinline__ float min(float a, float b) { return ::fminf(a, b); }
+    static __device__ __forceinline__ float max(float a, float b) { return ::fmaxf(a, b); }
+};
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Counter = (env index lo, env index hi,
+// episode, block); key = 64-bit seed.  Results are therefore independent of
+// the launch geometry and of how instances are sharded over GPUs.
+// ---------------------------------------------------------------------------
+struct Philox {
+    uint32_t c0, c1, c2, c3; // counter
+    uint32_t k0, k1;         // key
+    uint32_t r[4];           // last block
+    int have;                // unread words in r
+
+    __device__ __forceinline__ Philox(uint64_t seed, uint64_t env, uint32_t episode)
+        : c0((uint32_t)env), c1((uint32_t)(env >> 32)), c2(episode), c3(0u),
+          k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), have(0) {}
+
+    __device__ __forceinline__ void block() {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, ka = k0, kb = k1;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+            const uint32_t y0 = hi1 ^ x1 ^ ka, y1 = lo1, y2 = hi0 ^ x3 ^ kb, y3 = lo0;
+            x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+        }
+        r[0] = x0; r[1] = x1; r[2] = x2; r[3] = x3;
+        ++c3;
+        have = 4;
+    }
+
+    // uniform double in [0,1) with 53 random bits (two 32-bit words)
+    __device__ __forceinline__ double u01() {
+        if (have < 2) block();
+        const uint32_t a = r[4 - have], b = r[5 - have];
+        have -= 2;
+        return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+    }
+
+    // U(lo, hi) = fma(hi - lo, u, lo): one rounding, reproducible on the CPU with fma()
+    __device__ __forceinline__ double uniform(double lo, double hi) { return ::fma(hi - lo, u01(), lo); }
+};
+
+// ---------------------------------------------------------------------------
+// SoA accessors
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T ld(const void *base, int64_t n, int field, int64_t i) {
+    return static_cast<const T *>(base)[(int64_t)field * n + i];
+}
+template <typename T>
+__device__ __forceinline__ void st(void *base, int64_t n, int field, int64_t i, T v) {
+    static_cast<T *>(base)[(int64_t)field * n + i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// host-side launch helpers
+// ---------------------------------------------------------------------------
+extern thread_local int g_b200_last_cuda_error;
+
+static inline int b200_check_launch() {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        g_b200_last_cuda_error = (int)e;
+        cudaGetLastError(); // clear the non-sticky error
+        return B200ENV_ECUDA;
+    }
+    return B200ENV_OK;
+}
+
+static inline unsigned b200_grid(int64_t n, int block = B200_BLOCK) { return (unsigned)((n + block - 1) / block); }
+
+// per-family entry points (defined in the family's .cu file)
+#define B200_FAMILY_DECL(name)                                                                                  \
+    int name##_dims(int variant, int *sf, int *od, int *ad, int *dd);                                           \
+    int name##_step(int dtype, int64_t n, const void *params, const b200env_io *io, uint32_t flags,              \
+                    uint64_t seed, int64_t off, cudaStream_t s);                                                \
+    int name##_reset(int dtype, int64_t n, const void *params, const b200env_io *io, const uint8_t *mask,        \
+                     uint64_t seed, int64_t off, cudaStream_t s);                                               \
+    int name##_observe(int dtype, int64_t n, const void *params, const b200env_io *io, cudaStream_t s);
+
+B200_FAMILY_DECL(cartpole)

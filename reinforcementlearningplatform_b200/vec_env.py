@@ -1,0 +1,206 @@
+"""Vector mirror of the reference env contract ``algorithm/rl_base.py:4-162``.
+
+The reference exposes one instance per Python object; its ``train.py`` loops
+read ``state_dim / action_dim / action_range / name / dt / timeMax|time_max``
+and, every step, ``current_state, next_state, reward, is_terminal,
+terminal_flag, time`` after calling ``step_update(action)`` (e.g.
+``demonstration/PPO2/PPO2-4-CartPoleAngleOnly/train.py:138-215``).
+
+``VecEnvBase`` keeps exactly those names but with a leading instance axis
+(torch CUDA tensors, owned by the env and overwritten in place each step --
+``.clone()`` replaces the reference's ``.copy()``).  All arithmetic happens in
+``libb200env.so`` (hand-written sm_100a kernels); this file only owns buffers
+and fills the parameter struct from the reference attribute names.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class VecEnvBase:
+    ENV_ID: int = -1
+    VARIANT: int = 0
+    STATE_FIELDS: tuple = ()  # names of the SoA state fields, in storage order
+
+    def __init__(self, n_envs: int = 1, device="cuda", dtype=torch.float64, seed: int = 0,
+                 env_index_offset: int = 0, auto_reset: bool = False, host_only: bool = False):
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError("dtype must be torch.float64 or torch.float32")
+        self._params = self.make_params()
+        self.host_only = bool(host_only)
+        if host_only:  # parameter/attribute mirror only (CPU tests, oracle drivers): no buffers, no launches
+            self.n_envs, self.dtype = int(n_envs), dtype
+            return
+        self._lib = _lib.load()  # raises if the CUDA engine is not built
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.B200EnvError("the engine has no CPU path: device must be a CUDA device")
+        self.n_envs = int(n_envs)
+        self.dtype = dtype
+        self._dt_code = _lib.F64 if dtype == torch.float64 else _lib.F32
+        self.seed = int(seed)
+        self.env_index_offset = int(env_index_offset)
+        self.auto_reset = bool(auto_reset)
+
+        sf, od, ad, dd = _lib.dims(self.ENV_ID, self.VARIANT)
+        assert sf == len(self.STATE_FIELDS), (sf, self.STATE_FIELDS)
+        self._sf, self._od, self._ad, self._dd = sf, od, ad, dd
+        N, dev = self.n_envs, self.device
+        z = lambda *shape, dt=dtype: torch.zeros(*shape, dtype=dt, device=dev)
+        self._state = z(sf, N)
+        self._time = z(N, dt=torch.float64)
+        self._episode = z(N, dt=torch.int32)  # bit pattern of the u32 episode counter
+        self._obs = z(od, N)
+        self._next_obs = z(od, N)
+        self._reset_obs = z(od, N)
+        self._reward = z(N)
+        self._done = z(N, dt=torch.uint8)
+        self._flag = z(N, dt=torch.int32)
+        self._action = z(ad, N)
+
+        '''rl_base'''
+        self.state_dim = od
+        self.action_dim = ad
+        self.current_action = self._action.t()
+        self.is_terminal = self._done.view(torch.bool)
+        self.terminal_flag = self._flag
+        self.reward = self._reward
+        self.time = self._time
+        '''rl_base'''
+
+    # ------------------------------------------------------------------ params
+    def make_params(self) -> C.Structure:
+        raise NotImplementedError
+
+    # ----------------------------------------------------------------- helpers
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _io(self, action=None, dis=None, obs=True, reset_obs=True) -> _lib.IO:
+        io = _lib.IO()
+        io.state = self._state.data_ptr()
+        io.time = self._time.data_ptr()
+        io.episode = self._episode.data_ptr()
+        io.action = None if action is None else action.data_ptr()
+        io.dis = None if dis is None else dis.data_ptr()
+        io.obs = self._obs.data_ptr() if obs else None
+        io.next_obs = self._next_obs.data_ptr()
+        io.reward = self._reward.data_ptr()
+        io.done = self._done.data_ptr()
+        io.flag = self._flag.data_ptr()
+        io.reset_obs = self._reset_obs.data_ptr() if reset_obs else None
+        return io
+
+    def _as_soa(self, x, rows: int) -> torch.Tensor:
+        """Accept [N, rows] (reference orientation) or [rows, N] (engine SoA) tensors/arrays."""
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(np.asarray(x), dtype=self.dtype)
+        x = x.to(device=self.device, dtype=self.dtype)
+        if x.dim() == 1:
+            x = x.view(1, -1) if rows == 1 and x.numel() == self.n_envs else x.view(-1, 1).expand(rows, self.n_envs)
+        if x.shape == (rows, self.n_envs):
+            return x.contiguous()
+        if x.shape == (self.n_envs, rows):
+            return x.t().contiguous()
+        raise ValueError(f"expected [{self.n_envs},{rows}] or [{rows},{self.n_envs}], got {tuple(x.shape)}")
+
+    # ------------------------------------------------------------- rl_base API
+    @property
+    def current_state(self) -> torch.Tensor:
+        """[N, state_dim] view of the pre-step observation (rl_base.py:22)."""
+        return self._obs.t()
+
+    @property
+    def next_state(self) -> torch.Tensor:
+        """[N, state_dim] view of s' (rl_base.py:23)."""
+        return self._next_obs.t()
+
+    @property
+    def policy_state(self) -> torch.Tensor:
+        """[N, state_dim] observation to act on next: s' or the reset observation after an auto-reset."""
+        return self._reset_obs.t()
+
+    def reset(self, random: bool = True, mask: Optional[torch.Tensor] = None) -> None:
+        """``env.reset(random)`` (rl_base.py:161) for all instances or those in ``mask``."""
+        if random:
+            with torch.cuda.device(self.device):
+                io = self._io(obs=False, reset_obs=False)
+                m = None
+                if mask is not None:
+                    m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+                _lib.check(self._lib.b200env_reset(self.ENV_ID, self._dt_code, self.n_envs, C.byref(self._params),
+                                                   C.sizeof(self._params), C.byref(io), self._ptr(m), self.seed,
+                                                   self.env_index_offset, self._stream()), "b200env_reset")
+        else:
+            self._reset_default(mask)
+            self.observe()
+        sel = slice(None) if mask is None else mask.to(self.device).bool()
+        self._obs[:, sel] = self._next_obs[:, sel]
+        self._reset_obs[:, sel] = self._next_obs[:, sel]
+        self._reward[sel] = 0
+        self._done[sel] = 0
+        self._flag[sel] = 0
+
+    def _reset_default(self, mask) -> None:
+        raise NotImplementedError
+
+    def observe(self) -> torch.Tensor:
+        """``env.get_state()`` (rl_base.py:158) of the current state, into ``next_state``."""
+        with torch.cuda.device(self.device):
+            io = self._io(obs=False, reset_obs=False)
+            _lib.check(self._lib.b200env_observe(self.ENV_ID, self._dt_code, self.n_envs, C.byref(self._params),
+                                                 C.sizeof(self._params), C.byref(io), self._stream()),
+                       "b200env_observe")
+        return self.next_state
+
+    get_state = observe
+
+    def step_update(self, action, dis=None) -> None:
+        """``env.step_update(action)`` (rl_base.py:126) for every instance; results land in
+        ``current_state, next_state, reward, is_terminal, terminal_flag`` like the reference."""
+        a = self._as_soa(action, self._ad)
+        self._action = a
+        self.current_action = a.t()
+        d = None if dis is None else self._as_soa(dis, self._dd)
+        self.step_soa(a, d)
+
+    def step_soa(self, action_soa: torch.Tensor, dis_soa: Optional[torch.Tensor] = None) -> None:
+        """Hot call: ``action_soa`` is ``[action_dim, N]`` contiguous in the env dtype (no copies made)."""
+        with torch.cuda.device(self.device):
+            io = self._io(action_soa, dis_soa)
+            flags = _lib.AUTO_RESET if self.auto_reset else 0
+            _lib.check(self._lib.b200env_step(self.ENV_ID, self._dt_code, self.n_envs, C.byref(self._params),
+                                              C.sizeof(self._params), C.byref(io), flags, self.seed,
+                                              self.env_index_offset, self._stream()), "b200env_step")
+
+    def get_reward(self) -> torch.Tensor:
+        return self._reward
+
+    def is_Terminal(self) -> torch.Tensor:
+        return self.is_terminal
+
+    # ------------------------------------------------------- state injection
+    def get_state_buffers(self) -> dict:
+        return {"state": self._state.clone(), "time": self._time.clone(), "episode": self._episode.clone()}
+
+    def set_state_buffers(self, state=None, time=None, episode=None) -> None:
+        """Inject SoA state ([fields, N]), time ([N]) -- parity re-sync and checkpoint restore."""
+        if state is not None:
+            self._state.copy_(torch.as_tensor(state).to(self.device, self.dtype))
+        if time is not None:
+            self._time.copy_(torch.as_tensor(time).to(self.device, torch.float64))
+        if episode is not None:
+            self._episode.copy_(torch.as_tensor(episode).to(self.device, torch.int32))
+
+    def field(self, name: str) -> torch.Tensor:
+        return self._state[self.STATE_FIELDS.index(name)]

@@ -1,0 +1,182 @@
+"""Shared parity machinery: replay a golden fixture (recorded from the live reference by
+oracle/gen_golden.py) through a backend -- the C oracle on the CPU or the CUDA engine -- and
+report the worst deviation.  Metric: |a-b| <= tol * max(1, |b|)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def mixed_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+
+
+def env_specs():
+    """golden fixture name -> (env class, constructor kwargs)."""
+    import reinforcementlearningplatform_b200 as rlp
+    return {
+        "cartpole": (rlp.CartPole, {}),
+        "cartpole_gentle": (rlp.CartPole, {}),
+        "cartpole_angleonly_env": (rlp.CartPoleAngleOnly, {"variant": "env"}),
+        "cartpole_angleonly_ppo2": (rlp.CartPoleAngleOnly, {"variant": "ppo2"}),
+    }
+
+
+class OracleBackend:
+    """C restatement (oracle/liboracle.so) behind the replay interface."""
+
+    def __init__(self, name, lanes):
+        from oracle import oracle
+        from reinforcementlearningplatform_b200 import _lib
+        cls, kw = env_specs()[name]
+        host = cls(n_envs=lanes, host_only=True, **kw)
+        sf, od, ad, dd = _lib.dims(cls.ENV_ID, host.VARIANT)
+        self.env = oracle.OracleEnv(cls.ENV_ID, host._params, lanes, sf, od, ad, dd)
+
+    def set_state(self, state, time, lanes=None):
+        sel = slice(None) if lanes is None else lanes
+        self.env.state[:, sel] = np.asarray(state).T
+        self.env.time[sel] = time
+
+    def step(self, actions, dis=None):
+        e = self.env
+        e.step(np.ascontiguousarray(actions.T), None if dis is None else np.ascontiguousarray(dis.T))
+        return dict(obs=e.obs.T.copy(), next_obs=e.next_obs.T.copy(), reward=e.reward.copy(), done=e.done.copy(),
+                    flag=e.flag.copy(), state=e.state.T.copy(), time=e.time.copy())
+
+
+class EngineBackend:
+    """CUDA engine (libb200env.so through the VecEnv mirror) behind the replay interface."""
+
+    def __init__(self, name, lanes, dtype=None):
+        import torch
+        cls, kw = env_specs()[name]
+        self.torch = torch
+        self.env = cls(n_envs=lanes, device="cuda", dtype=dtype or torch.float64, **kw)
+
+    def set_state(self, state, time, lanes=None):
+        t = self.torch
+        e = self.env
+        st = e._state.cpu().numpy().astype(np.float64)
+        tm = e._time.cpu().numpy()
+        sel = slice(None) if lanes is None else lanes
+        st[:, sel] = np.asarray(state).T
+        tm[sel] = time
+        e.set_state_buffers(t.from_numpy(st), t.from_numpy(tm))
+
+    def step(self, actions, dis=None):
+        t = self.torch
+        e = self.env
+        e.step_update(t.from_numpy(np.ascontiguousarray(actions)), None if dis is None else t.from_numpy(np.ascontiguousarray(dis)))
+        t.cuda.synchronize()
+        f = lambda x: x.detach().cpu().numpy().astype(np.float64)
+        return dict(obs=f(e.current_state), next_obs=f(e.next_state), reward=f(e.reward),
+                    done=e._done.cpu().numpy().copy(), flag=e._flag.cpu().numpy().copy(),
+                    state=f(e._state.t()), time=e._time.cpu().numpy().copy())
+
+
+def replay(g, backend, resync=False, steps=None):
+    """Run the fixture's actions through `backend`.  Free-running: state carried by the backend, re-injected
+    only after the reference's resets.  resync=True: the fixture's state is injected before every step."""
+    T, L = g["reward"].shape
+    if steps:
+        T = min(T, steps)
+    has_dis = "dis" in g
+    backend.set_state(g["state0"], g["time0"])
+    worst = dict(obs=0.0, next_obs=0.0, reward=0.0, state=0.0, time=0.0)
+    flag_mismatch = 0
+    done_mismatch = 0
+    first_bad = None
+    for t in range(T):
+        if resync and t > 0:
+            st = np.where(np.isnan(g["reset_state"][t - 1]), g["state"][t - 1], g["reset_state"][t - 1])
+            tm = np.where(np.isnan(g["reset_time"][t - 1]), g["time"][t - 1], g["reset_time"][t - 1])
+            backend.set_state(st, tm)
+        out = backend.step(g["actions"][t], g["dis"][t] if has_dis else None)
+        for k in ("obs", "next_obs", "reward", "state"):
+            worst[k] = max(worst[k], mixed_err(out[k], g[k][t]))
+        worst["time"] = max(worst["time"], float(np.max(np.abs(out["time"] - g["time"][t]))))
+        fm = int(np.sum(out["flag"] != g["flag"][t]))
+        dm = int(np.sum(out["done"] != g["done"][t]))
+        if (fm or dm) and first_bad is None:
+            first_bad = (t, out["flag"].tolist(), g["flag"][t].tolist())
+        flag_mismatch += fm
+        done_mismatch += dm
+        lanes = np.nonzero(g["done"][t])[0]
+        if len(lanes) and not resync:
+            backend.set_state(g["reset_state"][t][lanes], g["reset_time"][t][lanes], lanes)
+    return dict(worst=worst, flag_mismatch=flag_mismatch, done_mismatch=done_mismatch, first_bad=first_bad, steps=T)
+
+
+# ---------------------------------------------------------------------------------------------
+# engine vs oracle on seeded random inputs, both with the in-kernel Philox auto-reset
+# ---------------------------------------------------------------------------------------------
+def action_bounds(name, env):
+    ar = np.asarray(env.action_range, dtype=np.float64)
+    return ar[:, 0], ar[:, 1]
+
+
+def smoke_cases():
+    return ["cartpole"]
+
+
+# fp64 tolerance of the free-running engine-vs-oracle comparison (mixed metric), per fixture family
+ENGINE_TOL = {
+    "cartpole": 1e-9, "cartpole_gentle": 1e-9, "cartpole_angleonly_env": 1e-9, "cartpole_angleonly_ppo2": 1e-9,
+}
+
+
+def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None):
+    """Step the CUDA engine and the C oracle side by side from the same Philox reset with the same random actions.
+    Auto-reset uses the same counter-based draws on both sides, so trajectories stay comparable across episodes.
+    Returns the worst mixed error over obs/next_obs/reward/state and the number of flag mismatches."""
+    import torch
+    from oracle import oracle
+    from reinforcementlearningplatform_b200 import _lib
+    cls, kw = env_specs()[name]
+    dtype = dtype or torch.float64
+    env = cls(n_envs=n, device="cuda", dtype=dtype, seed=seed, auto_reset=auto_reset, **kw)
+    sf, od, ad, dd = _lib.dims(cls.ENV_ID, env.VARIANT)
+    orc = oracle.OracleEnv(cls.ENV_ID, env._params, n, sf, od, ad, dd, seed=seed, auto_reset=auto_reset, nthreads=8)
+    env.reset(True)
+    orc.reset()
+    torch.cuda.synchronize()
+    f = lambda x: x.detach().cpu().numpy().astype(np.float64)
+    worst = mixed_err(f(env._state), orc.state)
+    lo, hi = action_bounds(name, env)
+    rng = np.random.default_rng(seed)
+    flag_mismatch = 0
+    n_done = 0
+    for t in range(steps):
+        a = rng.uniform(lo[:, None], hi[:, None], size=(ad, n))
+        d = rng.normal(0, 0.5, size=(dd, n)) if dd else None
+        a_dev = torch.from_numpy(a).to("cuda", dtype)
+        d_dev = None if d is None else torch.from_numpy(d).to("cuda", dtype)
+        a_cpu = f(a_dev)  # the oracle sees exactly the values the engine sees (matters in fp32 mode)
+        env.step_soa(a_dev, d_dev)
+        orc.step(a_cpu, None if d is None else f(d_dev))
+        torch.cuda.synchronize()
+        fm = int(np.sum(env._flag.cpu().numpy() != orc.flag) + np.sum(env._done.cpu().numpy() != orc.done))
+        flag_mismatch += fm
+        n_done += int(orc.done.sum())
+        for got, ref in ((env._obs, orc.obs), (env._next_obs, orc.next_obs), (env._reward, orc.reward),
+                         (env._state, orc.state), (env._reset_obs, orc.reset_obs)):
+            worst = max(worst, mixed_err(f(got), ref))
+        worst = max(worst, float(np.max(np.abs(env._time.cpu().numpy() - orc.time))))
+        if fm:  # trajectories diverge after a flag mismatch: re-sync the engine from the oracle
+            env.set_state_buffers(torch.from_numpy(orc.state), torch.from_numpy(orc.time),
+                                  torch.from_numpy(orc.episode.astype(np.int32)))
+    return dict(worst=worst, flag_mismatch=flag_mismatch, terminals=n_done,
+                tol=tol if tol is not None else ENGINE_TOL[name])

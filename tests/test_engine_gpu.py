@@ -1,0 +1,41 @@
+"""GPU: the CUDA engine (through the C ABI) against (1) the fixtures recorded from the live reference and
+(2) the C oracle on seeded random inputs at larger sizes.  fp64 bar: 1e-12 mixed error per step in one-step
+re-sync mode; free-running tolerances are stated per env in helpers.ENGINE_TOL."""
+import numpy as np
+import pytest
+
+from helpers import ENGINE_TOL, EngineBackend, engine_vs_oracle, env_specs, load_golden, replay
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_CASES = sorted(ENGINE_TOL)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_engine_matches_reference_fixture_resync(name):
+    """one-step mode: inject the reference state before every step; every output within 1e-12, flags exact."""
+    g = load_golden(name)
+    res = replay(g, EngineBackend(name, g["reward"].shape[1]), resync=True)
+    assert res["flag_mismatch"] == 0 and res["done_mismatch"] == 0, res
+    assert res["worst"]["time"] == 0.0, res
+    for k, v in res["worst"].items():
+        assert v <= 1e-12, (k, res)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_engine_matches_reference_fixture_free_running(name):
+    """free-running over the whole fixture (1000 steps), state re-injected only after the reference's resets."""
+    g = load_golden(name)
+    res = replay(g, EngineBackend(name, g["reward"].shape[1]), resync=False)
+    assert res["flag_mismatch"] == 0 and res["done_mismatch"] == 0, res
+    assert res["worst"]["time"] == 0.0, res
+    for k, v in res["worst"].items():
+        assert v <= ENGINE_TOL[name], (k, res)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_engine_vs_oracle_random(name, oracle_lib):
+    res = engine_vs_oracle(name, n=8192, steps=60, seed=7)
+    assert res["flag_mismatch"] == 0, res
+    assert res["worst"] <= res["tol"], res
+    assert res["terminals"] > 0 or name == "cartpole_gentle", res
