@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched environment engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload uav_pos|uav_att|cartpole] [--impl reference]
+
+Default workload = config #4 of BASELINE.json: UavFntsmcParam position tracking (quadrotor RK4 + FNTSMC outer and
+inner loops), 1,048,576 instances per GPU, fp64, 8 fresh gains per instance per step, auto-reset on.  One "step" is
+one launch of the fused step kernel over all instances of this rank.  Instances shard independently over ranks (weak
+scaling, no data-path collective); the timed region is bracketed by barrier + synchronize and the reported time is
+the max over ranks.
+
+The JSON line carries, besides the contract keys: `roofline` (algorithmic HBM bytes of the step kernel / measured
+HBM peak, plus the fp64-pipe view), `cpu_baseline` (the C port of the reference timed on the host cores on a bounded
+sample), `e2e` (same metric through the public VecEnv API with host buffers: pinned H2D of the actions and D2H of
+next_state/reward/done every step), `clocks`, `gpu_launches`, and `also` (the other single-GPU workloads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# algorithmic HBM bytes per env-step (fp64), derived in DESIGN.md section 4 from the kernel's loads/stores:
+#   uav_pos: state 21 fields R+W (12 ODE, 3 sigma_o1, 3 s1, 3 att_ref) + 12 gains W + 12 trajectory R + 8 action R
+#            + time R+W + 6 next_obs + reward W (8 B each) + done (1) + flag (4)
+ALGO_BYTES = {
+    "uav_pos": (21 * 2 + 12 + 12 + 8 + 2 + 6 + 1) * 8 + 5,
+    "uav_att": (9 * 2 + 12 + 9 + 8 + 2 + 6 + 1) * 8 + 5,
+    "cartpole": (4 * 2 + 1 + 2 + 4 + 1) * 8 + 5,
+}
+# algorithmic fp64 work per env-step (weighted flops, SURVEY.md section 8d convention), used for the fp64-pipe view
+ALGO_FLOPS = {"uav_pos": 5100.0, "uav_att": 3300.0, "cartpole": 3100.0}
+
+WORKLOADS = {
+    "uav_pos": dict(n=1 << 20, desc="UavFntsmcParam position tracking, dt=0.02, time_max=10, 8 gains~U(0,5)/step"),
+    "uav_att": dict(n=1 << 20, desc="UavFntsmcParam attitude tracking, dt=0.02, time_max=10, 8 gains~U(0,3)/step"),
+    "cartpole": dict(n=65536, desc="CartPole (angle+position) RK4 time-loop step, force~U(-8,8)"),
+}
+
+
+def make_env(workload, n, device, offset, dtype=torch.float64, host_only=False):
+    import reinforcementlearningplatform_b200 as rlp
+    kw = dict(n_envs=n, device=device, dtype=dtype, seed=2024, env_index_offset=offset, auto_reset=True,
+              host_only=host_only)
+    if workload == "uav_pos":
+        return rlp.UavPosCtrlRL(random_trajectory=True, **kw)
+    if workload == "uav_att":
+        return rlp.UavAttCtrlRL(random_trajectory=True, **kw)
+    if workload == "cartpole":
+        return rlp.CartPole(**kw)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+def action_pool(env, n, pool, device, dtype, seed):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    ar = torch.as_tensor(np.asarray(env.action_range, dtype=np.float64), device=device)
+    lo, hi = ar[:, 0].view(1, -1, 1), ar[:, 1].view(1, -1, 1)
+    u = torch.rand((pool, ar.shape[0], n), generator=g, device=device, dtype=torch.float64)
+    return (lo + (hi - lo) * u).to(dtype).contiguous()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def timed_steps(env, pool, steps, warmup, dist_on):
+    import torch.distributed as dist
+    P = pool.shape[0]
+    for k in range(warmup):
+        env.step_soa(pool[k % P])
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        env.step_soa(pool[(warmup + k) % P])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+def timed_e2e(env, n, steps, warmup, dist_on, seed):
+    """Same metric through the public API with HOST buffers: every step copies the actions from pinned host memory,
+    launches the step, and reads next_state / reward / is_terminal back to pinned host memory."""
+    import torch.distributed as dist
+    A, S = env.action_dim, env.state_dim
+    rng = np.random.default_rng(seed)
+    ar = np.asarray(env.action_range, dtype=np.float64)
+    host_a = [torch.from_numpy(rng.uniform(ar[:, :1], ar[:, 1:], size=(A, n))).to(env.dtype).pin_memory() for _ in range(2)]
+    dev_a = [torch.empty((A, n), dtype=env.dtype, device=env.device) for _ in range(2)]
+    h_obs = torch.empty((S, n), dtype=env.dtype).pin_memory()
+    h_rew = torch.empty((n,), dtype=env.dtype).pin_memory()
+    h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+
+    def one(k):
+        b = k & 1
+        dev_a[b].copy_(host_a[b], non_blocking=True)
+        env.step_soa(dev_a[b])
+        h_obs.copy_(env._reset_obs, non_blocking=True)
+        h_rew.copy_(env._reward, non_blocking=True)
+        h_done.copy_(env._done, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the host-side policy needs the result before the next action
+
+    for k in range(warmup):
+        one(k)
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        one(k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    if dist_on:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    el = torch.tensor([], dtype=env.dtype).element_size()
+    return ms, A * n * el, (S * n + n) * el + n
+
+
+def cpu_port(workload, n, steps, threads, seed=2024):
+    """The C restatement of the reference (oracle/, kind "port") on the host cores: bounded sample."""
+    from oracle import oracle
+    from reinforcementlearningplatform_b200 import _lib
+    host = make_env(workload, n, "cuda", 0, host_only=True)
+    sf, od, ad, dd = _lib.dims(host.ENV_ID, host.VARIANT)
+    orc = oracle.OracleEnv(host.ENV_ID, host._params, n, sf, od, ad, dd, seed=seed, auto_reset=True, nthreads=threads)
+    orc.reset()
+    rng = np.random.default_rng(seed)
+    ar = np.asarray(host.action_range, dtype=np.float64)
+    acts = [rng.uniform(ar[:, :1], ar[:, 1:], size=(ad, n)) for _ in range(4)]
+    orc.step(acts[0])  # warm-up (page faults, thread pool)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        orc.step(acts[k % 4])
+    dt = time.perf_counter() - t0
+    return n * steps / dt, dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The reference is pure
+    Python and cannot travel to the GPU box, so this arm times its C restatement (oracle/, kind "port") with all host
+    threads on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = min(WORKLOADS[args.workload]["n"], 1 << 17)
+    total_steps = args.steps
+    for _ in range(max(args.warmup, 1)):
+        cpu_port(args.workload, n, 1, threads)
+    val, dt = cpu_port(args.workload, n, total_steps, threads)
+    line = {
+        "impl": "reference", "metric": "env-steps/sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / total_steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "envs": n, "desc": WORKLOADS[args.workload]["desc"]},
+        "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} instances x {total_steps} steps, OpenMP over instances"},
+        "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="uav_pos", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="instances per GPU (default: the config's)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / e2e / also (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist_on = world > 1
+    torch.cuda.set_device(local)
+    if dist_on:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    n = args.envs or WORKLOADS[args.workload]["n"]
+    dev = torch.device("cuda", local)
+
+    env = make_env(args.workload, n, dev, rank * n, dtype)
+    env.reset(True)
+    pool = action_pool(env, n, 4, dev, dtype, seed=rank + 1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed_steps(env, pool, args.steps, args.warmup, dist_on)
+    clocks = sampler.result()
+    value = world * n * args.steps / (ms * 1e-3)
+    per_launch_s = ms * 1e-3 / args.steps
+    el = 8 if dtype == torch.float64 else 4
+    algo_bytes = ALGO_BYTES[args.workload] * el / 8.0 * n
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    achieved = algo_bytes / per_launch_s / 1e9
+    line = {
+        "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": args.workload, "envs_per_gpu": n, "desc": WORKLOADS[args.workload]["desc"],
+                   "auto_reset": True, "parallelism": f"env-shard x{world}",
+                   "l2": "per-step working set (state + action + outputs) exceeds the 126 MB L2; 4 rotating action buffers"
+                   if n >= (1 << 19) else "working set fits L2 (config size); launch-bound"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+                     "kernel": f"{args.workload}_step_kernel<{'double' if el == 8 else 'float'}>",
+                     "fp64_pipe": {"achieved_tflops_weighted": ALGO_FLOPS[args.workload] * n / per_launch_s / 1e12,
+                                   "note": "weighted algorithmic flops (SURVEY 8d convention); see profiles/ for the measured DFMA peak"}},
+        "clocks": clocks, "gpu_launches": args.steps,
+    }
+    if not args.no_extras:
+        sampler2 = ClockSampler(local)
+        e_ms, h2d, d2h = timed_e2e(env, n, max(10, args.steps // 4), 3, dist_on, seed=rank + 11)
+        e_steps = max(10, args.steps // 4)
+        line["e2e"] = {"value": world * n * e_steps / (e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "api": "VecEnv.step_soa with pinned host action / result buffers"}
+        del sampler2
+        if rank == 0 and world == 1:
+            threads = os.cpu_count() or 1
+            cn = min(n, 1 << 16)
+            cval, cdt = cpu_port(args.workload, cn, 40, threads)
+            line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                                    "sample": f"{cn} instances x 40 steps ({cdt:.1f} s), C restatement of the reference, OpenMP"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist_on:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

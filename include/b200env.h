@@ -118,6 +118,44 @@ typedef struct b200_cartpole_params {
 /* state fields of the CartPole family: theta, dtheta, x, dx */
 #define B200_CARTPOLE_STATE_FIELDS 4
 
+
+/* UavFntsmcParam attitude / position tracking envs (B200ENV_UAV_ATT, B200ENV_UAV_POS).
+ * Quadrotor: environment/UavFntsmcParam/uav.py:7-25,93-148; controllers: FNTSMC.py:4-14,47-69,112-137;
+ * wrappers: uav_att_ctrl.py, uav_att_ctrl_RL.py, uav_pos_ctrl.py, uav_pos_ctrl_RL.py; references: ref_cmd.py.
+ * The per-instance learnable gains, FNTSMC integrators and trajectory parameters live in `state`;
+ * everything here is shared by all instances. */
+typedef struct b200_uav_params {
+    double m, g, J[3], kr, kt;          /* uav.py:9-17 */
+    double dt, time_max;                /* uav.py:22-23 (train.py sets 0.02 / 10) */
+    double pos_lo[3], pos_hi[3];        /* pos_zone[i][0] - max_admissible_error, pos_zone[i][1] + ...   uav.py:182-193 */
+    double att_lo[3], att_hi[3];        /* att_zone[i][0] + deg2rad(1), att_zone[i][1] - deg2rad(1)      uav.py:195-206 */
+    double att_zone_min[3], att_zone_max[3]; /* raw zone, used by the att reward penalty uav_att_ctrl_RL.py:96-102 */
+    double t_term;                      /* time_max - dt / 2                                             uav.py:216 */
+    double init_state[12];              /* concat(pos0, vel0, angle0, pos0) (sic, N5)                    uav.py:64 */
+    /* inner-loop (attitude) FNTSMC: fixed in the position env, reset values of the learnable gains in the attitude env */
+    double att_k1[3], att_k2[3], att_alpha[3], att_beta[3], att_gamma[3], att_lmd[3];
+    /* outer-loop (position) FNTSMC: alpha/beta fixed; k1,k2,gamma,lmd are the reset values of the learnable gains */
+    double pos_k1[3], pos_k2[3], pos_alpha[3], pos_beta[3], pos_gamma[3], pos_lmd[3];
+    double Q_e[3], Q_de[3], R[3];       /* reward weights: (Q_att,Q_pqr,R) uav_att_ctrl_RL.py:44-46 or (Q_pos,Q_vel,R) uav_pos_ctrl_RL.py:51-53 */
+    double ref_amplitude[4], ref_period[4], ref_bias_a[4], ref_bias_phase[4]; /* deterministic trajectory (random_trajectory=False) */
+    double dot_att_ref_limit;           /* 60 * pi / 180                                                 uav_pos_ctrl.py:25 */
+    double att_limit;                   /* pi / 4                                                        uav_pos_ctrl.py:314 */
+    double traj_A_hi[4];                /* random trajectory: A ~ U(0, hi)   uav_att_ctrl.py:157-159 / uav_pos_ctrl.py:405-406 */
+    double traj_T_lo, traj_T_hi;        /* random trajectory: T ~ U(lo, hi)  uav_att_ctrl.py:160 / uav_pos_ctrl.py:407 */
+    double traj_phase_hi;               /* att: phi0 ~ U(0, pi/2) uav_att_ctrl.py:161; pos: unused (phi0 fixed) */
+    int32_t random_trajectory;          /* reset_..._tracking(random_trajectory=...) */
+    int32_t yaw_fixed;
+} b200_uav_params;
+
+/* state fields, attitude env: phi theta psi p q r | s1[3] | k1[3] k2[3] gamma[3] lmd[3] | A[3] T[3] phase[3] | ref[3] dot_ref[3] */
+#define B200_UAV_ATT_STATE_FIELDS 36
+/* state fields, position env: x y z vx vy vz phi theta psi p q r | sigma_o1[3] | s1[3] | att_ref[3] |
+ *                             k1[3] k2[3] gamma[3] lmd[3] | A[4] T[4] phase[4] | pos_ref[3] dot_pos_ref[3] */
+#define B200_UAV_POS_STATE_FIELDS 51
+/* `ref/dot_ref` (att) and `pos_ref/dot_pos_ref` (pos) are only stored on a terminal step without auto-reset and read by
+ * b200env_reset / b200env_observe: the reference's reset does not clear them, so the first observation of the next
+ * episode is taken against the previous episode's last reference (uav_att_ctrl.py:187-216, uav_pos_ctrl.py:488-533). */
+
 /* ---------------------------------------------------------------- queries */
 
 /* sizes of the SoA arrays of one env family/variant; any out pointer may be NULL */

@@ -12,16 +12,22 @@ typedef void (*reset_one_fn)(const void *, const oracle_io *, int64_t, int64_t, 
     void orc_##name##_step_one(const void *, const oracle_io *, int64_t, int64_t, uint32_t, uint64_t, int64_t); \
     void orc_##name##_reset_one(const void *, const oracle_io *, int64_t, int64_t, uint64_t, int64_t, int);
 DECL(cartpole)
+DECL(uav_att)
+DECL(uav_pos)
 
 static step_one_fn step_of(int env_id) {
     switch (env_id) {
     case B200ENV_CARTPOLE: return orc_cartpole_step_one;
+    case B200ENV_UAV_ATT: return orc_uav_att_step_one;
+    case B200ENV_UAV_POS: return orc_uav_pos_step_one;
     default: return 0;
     }
 }
 static reset_one_fn reset_of(int env_id) {
     switch (env_id) {
     case B200ENV_CARTPOLE: return orc_cartpole_reset_one;
+    case B200ENV_UAV_ATT: return orc_uav_att_reset_one;
+    case B200ENV_UAV_POS: return orc_uav_pos_reset_one;
     default: return 0;
     }
 }

@@ -15,6 +15,10 @@ L independent lanes and T steps,
     state [T,L,F], time [T,L]        internal state after the step (before any reset)
     reset_state [T,L,F]              state after the reference's own reset(True) that follows
                                      a terminal step (NaN rows elsewhere), reset_time likewise
+    twin_err [T,L]                   self-sensitivity of the reference: mixed error of next_obs between the recorded run and
+                                     a twin reference instance whose state is nudged by ~1e-16 after the reset and after
+                                     every step (what any re-implementation with different rounding does).  Free-running
+                                     tolerances are expressed as a multiple of its running maximum.
     meta                             numpy version, cpu flags, reference call sites
 
 The checkers (C restatement in oracle/, CUDA engine) start from state0, apply the same
@@ -48,6 +52,7 @@ def record(adapter: "A.Adapter", lanes: int, steps: int, seed: int) -> dict:
         "done": np.zeros((steps, lanes), np.uint8), "flag": np.zeros((steps, lanes), np.int32),
         "state": np.zeros((steps, lanes, F)), "time": np.zeros((steps, lanes)),
         "reset_state": np.full((steps, lanes, F), np.nan), "reset_time": np.full((steps, lanes), np.nan),
+        "twin_err": np.zeros((steps, lanes)),
     }
     if D:
         out["dis"] = np.zeros((steps, lanes, D))
@@ -55,13 +60,21 @@ def record(adapter: "A.Adapter", lanes: int, steps: int, seed: int) -> dict:
         np.random.seed(seed * 1000 + l)  # the reference's resets use the global numpy RNG
         with R.quiet():
             env = adapter.make()
+            twin = adapter.make()
+            rs = np.random.get_state()
             adapter.reset(env)
+            np.random.set_state(rs)
+            adapter.reset(twin)
+            adapter.perturb(twin, 0)
         out["state0"][l], out["time0"][l] = adapter.internal(env)
         for t in range(steps):
             a = adapter.sample_action(rng, t, l, env)
-            d = adapter.sample_dis(rng, t, l) if D else None
+            d = adapter.sample_dis(rng, t, l, env) if D else None
             with R.quiet():
                 o, o2, r, done, flag = adapter.step(env, a, d)
+                _, t2, _, tdone, _ = adapter.step(twin, a, d)
+            out["twin_err"][t, l] = float(np.max(np.abs(t2 - o2) / np.maximum(1.0, np.abs(o2))))
+            adapter.perturb(twin, t + 1)
             out["actions"][t, l] = a
             if D:
                 out["dis"][t, l] = d
@@ -73,7 +86,11 @@ def record(adapter: "A.Adapter", lanes: int, steps: int, seed: int) -> dict:
             out["state"][t, l], out["time"][t, l] = adapter.internal(env)
             if done:
                 with R.quiet():
+                    rs = np.random.get_state()
                     adapter.reset(env)
+                    np.random.set_state(rs)
+                    adapter.reset(twin)
+                    adapter.perturb(twin, 0)
                 out["reset_state"][t, l], out["reset_time"][t, l] = adapter.internal(env)
     meta = {
         "adapter": adapter.name, "reference": adapter.cites, "lanes": lanes, "steps": steps, "seed": seed,

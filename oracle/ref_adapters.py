@@ -29,7 +29,7 @@ class Adapter:
     def sample_action(self, rng, t, l, env=None):
         return rng.uniform(self.action_lo, self.action_hi)
 
-    def sample_dis(self, rng, t, l):
+    def sample_dis(self, rng, t, l, env=None):
         return np.zeros(self.D)
 
     def step(self, env, a, d):
@@ -40,6 +40,14 @@ class Adapter:
     def params_json(self):
         return {}
 
+    #: attributes nudged by +-1e-16 * max(1, |v|) in the twin instance (self-sensitivity measurement)
+    perturb_attrs = ()
+
+    def perturb(self, env, k):
+        for j, name in enumerate(self.perturb_attrs):
+            v = float(getattr(env, name))
+            setattr(env, name, v + (1e-16 if (k + j) % 2 == 0 else -1e-16) * max(1.0, abs(v)))
+
 
 # --------------------------------------------------------------------- CartPole
 class CartPoleA(Adapter):
@@ -47,6 +55,7 @@ class CartPoleA(Adapter):
     cites = "environment/CartPole/CartPole.py:145-295"
     F, S, A, D = 4, 4, 1, 0
     action_lo, action_hi = np.array([-8.]), np.array([8.])
+    perturb_attrs = ("theta", "dtheta", "dx")
 
     def make(self):
         return R.load("environment.CartPole.CartPole").CartPole(0., 0.)
@@ -70,6 +79,7 @@ class CartPoleAngleOnlyEnvA(Adapter):
     cites = "environment/CartPole/CartPoleAngleOnly.py:139-299"
     F, S, A, D = 4, 2, 1, 0
     action_lo, action_hi = np.array([-8.]), np.array([8.])
+    perturb_attrs = ("theta", "dtheta", "dx")
 
     def make(self):
         return R.load("environment.CartPole.CartPoleAngleOnly").CartPoleAngleOnly(0.)
@@ -95,3 +105,199 @@ REGISTRY = {
     "cartpole_angleonly_env": (CartPoleAngleOnlyEnvA, 4, 1000, 2),
     "cartpole_angleonly_ppo2": (CartPoleAngleOnlyPPO2A, 4, 1000, 3),
 }
+
+
+# ------------------------------------------------------------- UavFntsmcParam
+def _uav_train_params(kind):
+    """Parameter objects exactly as the PPO2 training scripts build them
+    (PPO2-4-UavFntsmcParamAtt/train.py:29-62, PPO2-4-UavFntsmcParamPos/train.py:29-76)."""
+    R.use_family("UavFntsmcParam")
+    uav = R.load("uav")
+    fn = R.load("FNTSMC")
+    F = R.load("utils.functions")
+    up = uav.uav_param()
+    up.dt, up.time_max = 0.02, 10
+    if kind == "att":
+        up.pos_zone = np.atleast_2d([[-np.inf, np.inf], [-np.inf, np.inf], [-np.inf, np.inf]])
+        up.att_zone = np.atleast_2d([[F.deg2rad(-90), F.deg2rad(90)], [F.deg2rad(-90), F.deg2rad(90)], [F.deg2rad(-180), F.deg2rad(180)]])
+    else:
+        up.pos_zone = np.atleast_2d([[-3, 3], [-3, 3], [0, 3]])
+        up.att_zone = np.atleast_2d([[F.deg2rad(-90), F.deg2rad(90)], [F.deg2rad(-90), F.deg2rad(90)], [F.deg2rad(-120), F.deg2rad(120)]])
+    att = fn.fntsmc_param()
+    att.k1 = np.array([25., 25., 40.]); att.k2 = np.array([0.1, 0.1, 0.2]); att.alpha = np.array([2.5, 2.5, 2.5])
+    att.beta = np.array([0.99, 0.99, 0.99]); att.gamma = np.array([1.5, 1.5, 1.2]); att.lmd = np.array([2.0, 2.0, 2.0])
+    att.dim, att.dt, att.ctrl0 = 3, 0.02, np.array([0., 0., 0.])
+    pos = fn.fntsmc_param()
+    pos.k1 = np.array([1.2, 0.8, 0.5]); pos.k2 = np.array([0.2, 0.6, 0.5]); pos.alpha = np.array([1.2, 1.5, 1.2])
+    pos.beta = np.array([0.3, 0.3, 0.5]); pos.gamma = np.array([0.2, 0.2, 0.2]); pos.lmd = np.array([2.0, 2.0, 2.0])
+    pos.dim, pos.dt, pos.ctrl0 = 3, 0.02, np.array([0., 0., 0.])
+    return up, att, pos
+
+
+def _zero(p):
+    p.k1 = 0.01 * np.ones(3); p.k2 = 0.01 * np.ones(3); p.gamma = 0.01 * np.ones(3); p.lmd = 0.01 * np.ones(3)
+
+
+class UavPosA(Adapter):
+    """Loop body of PPO2-4-UavFntsmcParamPos/train.py:273-297 around uav_pos_ctrl_RL."""
+    name = "uav_pos"
+    cites = ("environment/UavFntsmcParam/uav_pos_ctrl_RL.py:59-173, uav_pos_ctrl.py:302-376,467-533, uav.py:93-219, "
+             "FNTSMC.py:47-69,112-137, ref_cmd.py:25-43")
+    F, S, A, D = 51, 6, 8, 3
+    perturb_attrs = ("vx", "vy", "vz", "p", "q", "r")
+    random_trajectory = True
+    with_dis = False
+
+    def make(self):
+        self.up, self.att, self.pos = _uav_train_params("pos")
+        _zero(self.pos)
+        m = R.load("uav_pos_ctrl_RL")
+        self.ref_cmd = R.load("ref_cmd")
+        return m.uav_pos_ctrl_RL(self.up, self.att, self.pos)
+
+    def reset(self, env):
+        _zero(self.pos)  # reset_pos_ctrl_param('zero'), train.py:84-89,275
+        env.reset_uav_pos_ctrl_RL_tracking(random_trajectroy=self.random_trajectory, random_pos0=False,
+                                           new_att_ctrl_param=None, new_pos_ctrl_parma=self.pos, outer_param=None)
+
+    def internal(self, env):
+        s = np.concatenate((env.uav_state_call_back(), env.pos_ctrl.sigma_o1, env.att_ctrl.s1, env.att_ref,
+                            env.pos_ctrl.k1, env.pos_ctrl.k2, env.pos_ctrl.gamma, env.pos_ctrl.lmd,
+                            env.ref_amplitude, env.ref_period, env.ref_bias_phase, env.pos_ref, env.dot_pos_ref))
+        return np.array(s, dtype=float), float(env.time)
+
+    def sample_action(self, rng, t, l, env=None):
+        kind = l % 3
+        if kind == 0:      # fresh gains over the whole action range every step
+            return rng.uniform(0., 5., 8)
+        if kind == 1:      # near the hand-tuned gains: long episodes that reach the time-out flag
+            base = np.array([1.2, 0.8, 0.5, 0.2, 0.6, 0.5, 0.2, 2.0])
+            return base * rng.uniform(0.8, 1.2, 8)
+        a = rng.uniform(0., 3., 8)  # some entries <= 0: those gains keep their previous value (note N6)
+        a[rng.random(8) < 0.3] = 0.
+        return a
+
+    def sample_dis(self, rng, t, l, env=None):
+        if not self.with_dis:
+            return np.zeros(3)
+        tt = 0.02 * t  # UavRobust/ref_cmd.py:46-61 style sinusoids + noise
+        return np.array([0.5 * np.sin(1.3 * tt) + 0.2, 0.4 * np.cos(0.9 * tt), 0.3 * np.sin(2.1 * tt + 1.0)]) + rng.normal(0, 0.05, 3)
+
+    def step(self, env, a, d):
+        a = np.array(a, dtype=float)
+        env.dis = np.array(d, dtype=float)
+        env.get_param_from_actor(a)
+        action_4_uav = env.generate_action_4_uav()
+        env.step_update(action_4_uav)
+        return (np.array(env.current_state, dtype=float), np.array(env.next_state, dtype=float),
+                float(env.reward), bool(env.is_terminal), int(env.terminal_flag))
+
+
+class UavPosDisA(UavPosA):
+    name = "uav_pos_dis"
+    with_dis = True
+
+
+class UavAttA(Adapter):
+    """Loop body of PPO2-4-UavFntsmcParamAtt/train.py:254-276 around uav_att_ctrl_RL."""
+    name = "uav_att"
+    cites = ("environment/UavFntsmcParam/uav_att_ctrl_RL.py:59-178, uav_att_ctrl.py:91-216, uav.py:93-219,285-360, "
+             "FNTSMC.py:112-137, ref_cmd.py:4-22")
+    F, S, A, D = 36, 6, 8, 0
+    perturb_attrs = ("p", "q", "r")
+    random_trajectory = False
+
+    def make(self):
+        self.up, self.att, _ = _uav_train_params("att")
+        _zero(self.att)
+        m = R.load("uav_att_ctrl_RL")
+        self.ref_cmd = R.load("ref_cmd")
+        return m.uav_att_ctrl_RL(self.up, self.att)
+
+    def reset(self, env):
+        _zero(self.att)  # reset_att_ctrl_param('zero'), train.py:69-74,256
+        env.reset_uav_att_ctrl_RL_tracking(random_trajectory=self.random_trajectory, yaw_fixed=False,
+                                           new_att_ctrl_param=self.att)
+
+    def internal(self, env):
+        s = np.concatenate((env.uav_att_pqr_call_back(), env.att_ctrl.s1, env.att_ctrl.k1, env.att_ctrl.k2,
+                            env.att_ctrl.gamma, env.att_ctrl.lmd, env.ref_att_amplitude, env.ref_att_period,
+                            env.ref_att_bias_phase, env.ref, env.dot_ref))
+        return np.array(s, dtype=float), float(env.time)
+
+    def sample_action(self, rng, t, l, env=None):
+        kind = l % 3
+        if kind == 0:
+            return rng.uniform(0., 3., 8)
+        if kind == 1:      # near the hand-tuned inner-loop gains (k1 = 10 a, k2 = a / 10)
+            base = np.array([2.5, 2.5, 4.0, 1.0, 1.0, 2.0, 1.5, 2.0])
+            return np.clip(base * rng.uniform(0.8, 1.2, 8), 0, 3)
+        a = rng.uniform(0., 3., 8)
+        a[rng.random(8) < 0.3] = 0.
+        return a
+
+    def step(self, env, a, d):
+        a = np.array(a, dtype=float)
+        env.get_param_from_actor(a)
+        rhod, dot_rhod, _, _ = self.ref_cmd.ref_inner(env.time, env.ref_att_amplitude, env.ref_att_period,
+                                                      env.ref_att_bias_a, env.ref_att_bias_phase)
+        torque = env.att_control(rhod, dot_rhod, None)
+        env.step_update([torque[0], torque[1], torque[2]])
+        return (np.array(env.current_state, dtype=float), np.array(env.next_state, dtype=float),
+                float(env.reward), bool(env.is_terminal), int(env.terminal_flag))
+
+
+class UavAttRandA(UavAttA):
+    name = "uav_att_rand"
+    random_trajectory = True
+
+
+REGISTRY.update({
+    "uav_pos": (UavPosA, 6, 1000, 21),
+    "uav_pos_dis": (UavPosDisA, 3, 1000, 22),
+    "uav_att": (UavAttA, 6, 1000, 23),
+    "uav_att_rand": (UavAttRandA, 3, 1000, 24),
+})
+
+
+class UavPosCrashA(UavPosDisA):
+    """Weak gains + a strong constant disturbance: episodes end with the position-out flag (2)."""
+    name = "uav_pos_crash"
+
+    def sample_action(self, rng, t, l, env=None):
+        return rng.uniform(0., 0.3, 8)
+
+    def sample_dis(self, rng, t, l, env=None):
+        return np.array([4.0, -3.0, 2.0]) * (1 + 0.5 * l) + rng.normal(0, 0.05, 3)
+
+
+class UavPosEdgeA(UavPosA):
+    """Reset followed by an injected near-edge attitude and a body-rate kick: attitude-out flag (3)."""
+    name = "uav_pos_edge"
+
+    def reset(self, env):
+        super().reset(env)
+        env.theta = 1.40 + 0.02 * (getattr(self, "_k", 0) % 3)
+        env.q = 8.0
+        env.phi = -0.3
+        self._k = getattr(self, "_k", 0) + 1
+
+
+class UavAttEdgeA(UavAttRandA):
+    name = "uav_att_edge"
+
+    def reset(self, env):
+        super().reset(env)
+        k = getattr(self, "_k", 0)
+        if k % 2 == 0:
+            env.phi, env.p = 1.45, 6.0
+        else:
+            env.psi, env.r, env.theta = 3.1235, (1.0 if k % 4 == 1 else 2.0), -0.4   # psi wraps past pi and leaves the zone; theta near its edge
+        self._k = k + 1
+
+
+REGISTRY.update({
+    "uav_pos_crash": (UavPosCrashA, 2, 400, 25),
+    "uav_pos_edge": (UavPosEdgeA, 2, 200, 26),
+    "uav_att_edge": (UavAttEdgeA, 2, 200, 27),
+})

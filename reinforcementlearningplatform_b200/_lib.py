@@ -46,7 +46,25 @@ class CartPoleParams(C.Structure):
         ("variant", C.c_int32), ("pad_", C.c_int32)]
 
 
-PARAMS_OF = {CARTPOLE: CartPoleParams}
+def _d(name, n=1):
+    return (name, C.c_double if n == 1 else C.c_double * n)
+
+
+class UavParams(C.Structure):
+    """struct b200_uav_params"""
+    _fields_ = [
+        _d("m"), _d("g"), _d("J", 3), _d("kr"), _d("kt"), _d("dt"), _d("time_max"),
+        _d("pos_lo", 3), _d("pos_hi", 3), _d("att_lo", 3), _d("att_hi", 3),
+        _d("att_zone_min", 3), _d("att_zone_max", 3), _d("t_term"), _d("init_state", 12),
+        _d("att_k1", 3), _d("att_k2", 3), _d("att_alpha", 3), _d("att_beta", 3), _d("att_gamma", 3), _d("att_lmd", 3),
+        _d("pos_k1", 3), _d("pos_k2", 3), _d("pos_alpha", 3), _d("pos_beta", 3), _d("pos_gamma", 3), _d("pos_lmd", 3),
+        _d("Q_e", 3), _d("Q_de", 3), _d("R", 3),
+        _d("ref_amplitude", 4), _d("ref_period", 4), _d("ref_bias_a", 4), _d("ref_bias_phase", 4),
+        _d("dot_att_ref_limit"), _d("att_limit"), _d("traj_A_hi", 4), _d("traj_T_lo"), _d("traj_T_hi"),
+        _d("traj_phase_hi"), ("random_trajectory", C.c_int32), ("yaw_fixed", C.c_int32)]
+
+
+PARAMS_OF = {CARTPOLE: CartPoleParams, UAV_ATT: UavParams, UAV_POS: UavParams}
 
 _lib = None
 

@@ -13,11 +13,16 @@ struct Family {
     int (*observe)(int, int64_t, const void *, const b200env_io *, cudaStream_t);
 };
 
-#define FAM(name, P) {sizeof(P), name##_dims, name##_step, name##_reset, name##_observe}
+#define FAM(name, P) Family{sizeof(P), name##_dims, name##_step, name##_reset, name##_observe}
 const Family *family(int env_id) {
-    static const Family table[B200ENV_COUNT] = {
-        FAM(cartpole, b200_cartpole_params),
-    };
+    static Family table[B200ENV_COUNT] = {};
+    static bool init = false;
+    if (!init) {
+        table[B200ENV_CARTPOLE] = FAM(cartpole, b200_cartpole_params);
+        table[B200ENV_UAV_ATT] = FAM(uav_att, b200_uav_params);
+        table[B200ENV_UAV_POS] = FAM(uav_pos, b200_uav_params);
+        init = true;
+    }
     if (env_id < 0 || env_id >= B200ENV_COUNT) return nullptr;
     const Family *f = &table[env_id];
     return f->step ? f : nullptr;

@@ -131,3 +131,5 @@ static inline unsigned b200_grid(int64_t n, int block = B200_BLOCK) { return (un
     int name##_observe(int dtype, int64_t n, const void *params, const b200env_io *io, cudaStream_t s);
 
 B200_FAMILY_DECL(cartpole)
+B200_FAMILY_DECL(uav_att)
+B200_FAMILY_DECL(uav_pos)

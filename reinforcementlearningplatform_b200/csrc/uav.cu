@@ -1,0 +1,654 @@
+// uav.cu -- K-UAVA / K-UAVP: batched UavFntsmcParam attitude and position tracking steps (sm_100a).
+//
+// One thread = one quadrotor.  A launch performs, for every instance, the whole loop body of the reference's
+// train.py: get_param_from_actor(a) -> [ref_uav -> pos FNTSMC -> throttle/angle mapping ->] ref -> attitude FNTSMC
+// -> step_update (RK4 of the 12-state ODE, terminal flag, observation, reward) and, optionally, the auto-reset.
+//   quadrotor ODE / RK4 / zones      environment/UavFntsmcParam/uav.py:93-148,182-219
+//   attitude kinematics f1,f2,F,h    uav.py:285-360
+//   controllers                      FNTSMC.py:47-69 (pos), 112-137 (att, with np.linalg.inv)
+//   references                       ref_cmd.py:4-43
+//   wrappers                         uav_att_ctrl.py:91-128, uav_att_ctrl_RL.py:59-156,
+//                                    uav_pos_ctrl.py:302-376,467-486, uav_pos_ctrl_RL.py:59-173
+//
+// Register-resident design: the 12 ODE states, the RK4 accumulators, both sliding-mode integrators and the gains
+// stay in registers for the whole step; sin/cos of (phi, theta, psi) are evaluated once per RK stage and the
+// stage-1 values are shared with the controllers (the reference evaluates f1() four times and sin/cos ~60 times).
+// HBM traffic is one coalesced read and one coalesced write of each SoA field.
+#include "common.cuh"
+
+namespace {
+
+typedef b200_uav_params P;
+
+template <typename T>
+struct Trig {
+    T sphi, cphi, sth, cth, spsi, cpsi, tth;
+    __device__ __forceinline__ void eval(T phi, T th, T psi, bool need_psi) {
+        Mth<T>::sincos(phi, &sphi, &cphi);
+        Mth<T>::sincos(th, &sth, &cth);
+        tth = sth / cth;
+        if (need_psi) Mth<T>::sincos(psi, &spsi, &cpsi);
+        else { spsi = (T)0; cpsi = (T)1; }
+    }
+};
+
+template <typename T>
+struct Consts {
+    T m, g, kr, kt, J0, J1, J2, J21, J02, J10, dt;
+    __device__ __forceinline__ Consts(const P &p)
+        : m((T)p.m), g((T)p.g), kr((T)p.kr), kt((T)p.kt), J0((T)p.J[0]), J1((T)p.J[1]), J2((T)p.J[2]),
+          J21((T)(p.J[2] - p.J[1])), J02((T)(p.J[0] - p.J[2])), J10((T)(p.J[1] - p.J[0])), dt((T)p.dt) {}
+};
+
+// uav.py:93-124.  x = (x y z vx vy vz phi th psi p q r); only the derivative entries that the caller needs.
+template <typename T, bool ATT_ONLY>
+__device__ __forceinline__ void uav_ode(const Consts<T> &c, const T *x, const Trig<T> &t, T throttle, const T *tq,
+                                        const T *dis, T *d) {
+    const T p = x[9], q = x[10], r = x[11];
+    d[9] = (-c.kr * p - q * r * c.J21 + tq[0]) / c.J0;
+    d[10] = (-c.kr * q - p * r * c.J02 + tq[1]) / c.J1;
+    d[11] = (-c.kr * r - p * q * c.J10 + tq[2]) / c.J2;
+    d[6] = p + (t.tth * t.sphi) * q + (t.tth * t.cphi) * r;
+    d[7] = t.cphi * q - t.sphi * r;
+    d[8] = (t.sphi / t.cth) * q + (t.cphi / t.cth) * r;
+    if (!ATT_ONLY) {
+        d[0] = x[3]; d[1] = x[4]; d[2] = x[5];
+        d[3] = (throttle * (t.cpsi * t.sth * t.cphi + t.spsi * t.sphi) - c.kt * x[3] + dis[0]) / c.m;
+        d[4] = (throttle * (t.spsi * t.sth * t.cphi - t.cpsi * t.sphi) - c.kt * x[4] + dis[1]) / c.m;
+        d[5] = -c.g + (throttle * t.cphi * t.cth - c.kt * x[5] + dis[2]) / c.m;
+    }
+}
+
+// uav.py:126-148 with n = 1: x <- x + (K1 + 2 K2 + 2 K3 + K4) / 6, time += dt, psi wrapped to (-pi, pi].
+// `t1` holds sin/cos of the current attitude (already computed for the controllers).
+template <typename T, bool ATT_ONLY>
+__device__ __forceinline__ void uav_rk44(const Consts<T> &c, T *x, const Trig<T> &t1, T throttle, const T *tq,
+                                         const T *dis) {
+    constexpr int LO = ATT_ONLY ? 6 : 0;
+    const T h = c.dt, half = (T)0.5;
+    T acc[12], xs[12], d[12];
+    Trig<T> t;
+    uav_ode<T, ATT_ONLY>(c, x, t1, throttle, tq, dis, d);
+#pragma unroll
+    for (int i = LO; i < 12; ++i) { const T k = h * d[i]; acc[i] = k; xs[i] = x[i] + k * half; }
+    t.eval(xs[6], xs[7], xs[8], !ATT_ONLY);
+    uav_ode<T, ATT_ONLY>(c, xs, t, throttle, tq, dis, d);
+#pragma unroll
+    for (int i = LO; i < 12; ++i) { const T k = h * d[i]; acc[i] = acc[i] + (T)2 * k; xs[i] = x[i] + k * half; }
+    t.eval(xs[6], xs[7], xs[8], !ATT_ONLY);
+    uav_ode<T, ATT_ONLY>(c, xs, t, throttle, tq, dis, d);
+#pragma unroll
+    for (int i = LO; i < 12; ++i) { const T k = h * d[i]; acc[i] = acc[i] + (T)2 * k; xs[i] = x[i] + k; }
+    t.eval(xs[6], xs[7], xs[8], !ATT_ONLY);
+    uav_ode<T, ATT_ONLY>(c, xs, t, throttle, tq, dis, d);
+#pragma unroll
+    for (int i = LO; i < 12; ++i) { const T k = h * d[i]; x[i] = x[i] + (acc[i] + k) / (T)6; }
+    if (x[8] > (T)M_PI) x[8] -= (T)(2 * M_PI);
+    if (x[8] < (T)-M_PI) x[8] += (T)(2 * M_PI);
+}
+
+// FNTSMC sliding surface pieces shared by both loops (FNTSMC.py:61-66 / 128-134), one axis.
+template <typename T>
+__device__ __forceinline__ void smc_axis(T e, T de, T k1, T gamma, T alpha, T beta, T lmd, T dt, T &integ,
+                                         T &s_out, T &dot_s1, T &pa1_de) {
+    const T ae = Mth<T>::abs(e);
+    const T pa = Mth<T>::pow(ae, alpha);
+    const T pa1 = Mth<T>::pow(ae, alpha - (T)1);
+    const T s = de + k1 * e + gamma * pa * Mth<T>::tanh((T)5 * e);
+    dot_s1 = Mth<T>::pow(Mth<T>::abs(s), beta) * Mth<T>::tanh((T)5 * s);
+    integ += dot_s1 * dt;
+    s_out = s + lmd * integ;           // sigma (att) / so (pos)
+    pa1_de = gamma * alpha * pa1 * de; // gamma * alpha * |e|^(alpha-1) * de
+}
+
+// -inv(B) . v with B = f1 . diag(1/J) (uav.py:359-360) and inv = LAPACK dgesv(B, I) semantics: LU with partial
+// pivoting, then forward/back substitution per unit column, then the 3x3 . 3 product (FNTSMC.py:137).
+// Column 0 of B is (1/J0, 0, 0): its multipliers are exactly 0, so only rows 1,2 can be swapped.
+template <typename T>
+__device__ __forceinline__ void neg_inv_apply(T b00, T b01, T b02, T b11, T b12, T b21, T b22, const T *v, T *out) {
+    const bool swap = Mth<T>::abs(b21) > Mth<T>::abs(b11);
+    const T u11 = swap ? b21 : b11, u12 = swap ? b22 : b12;
+    const T r21 = swap ? b11 : b21, r22 = swap ? b12 : b22;
+    const T l = r21 * ((T)1 / u11);
+    const T u22 = r22 - l * u12;
+    T inv[3][3];
+#pragma unroll
+    for (int cidx = 0; cidx < 3; ++cidx) {
+        // P e_c: rows 1 and 2 exchanged when swap
+        T y0 = cidx == 0 ? (T)1 : (T)0;
+        T y1 = (cidx == (swap ? 2 : 1)) ? (T)1 : (T)0;
+        T y2 = (cidx == (swap ? 1 : 2)) ? (T)1 : (T)0;
+        y2 = y2 - l * y1;
+        const T x2 = y2 / u22;
+        const T x1 = (y1 - u12 * x2) / u11;
+        const T x0 = ((y0 - b01 * x1) - b02 * x2) / b00;
+        inv[0][cidx] = x0; inv[1][cidx] = x1; inv[2][cidx] = x2;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] = -(inv[i][0] * v[0] + inv[i][1] * v[1] + inv[i][2] * v[2]);
+}
+
+// Attitude loop: uav_att_ctrl.py:91-108 / uav_pos_ctrl.py:317-337 + FNTSMC.py:112-137 (dd_ref = 0).
+// x: full state, t: trig of the current attitude.  Returns torque; also d1 = f1 . pqr (Euler rates).
+template <typename T>
+__device__ __forceinline__ void att_control(const Consts<T> &c, const T *x, const Trig<T> &t, const T *k1, const T *k2,
+                                            const T *gamma, const T *lmd, const T *alpha, const T *beta, T *s1,
+                                            const T *ref, const T *dref, T *torque, T *d1) {
+    const T p = x[9], q = x[10], r = x[11];
+    const T f01 = t.sphi * t.tth, f02 = t.cphi * t.tth, f11 = t.cphi, f12 = -t.sphi;
+    const T f21 = t.sphi / t.cth, f22 = t.cphi / t.cth;
+    d1[0] = p + f01 * q + f02 * r;
+    d1[1] = f11 * q + f12 * r;
+    d1[2] = f21 * q + f22 * r;
+    // F() (uav.py:340-354) . rho2
+    const T c2 = t.cth * t.cth;
+    const T F01 = d1[0] * t.tth * t.cphi + d1[1] * t.sphi / c2;
+    const T F02 = -d1[0] * t.tth * t.sphi + d1[1] * t.cphi / c2;
+    const T F11 = -d1[0] * t.sphi, F12 = -d1[0] * t.cphi;
+    const T F21 = (d1[0] * t.cphi * t.cth + d1[1] * t.sphi * t.sth) / c2;
+    const T F22 = (-d1[0] * t.sphi * t.cth + d1[1] * t.cphi * t.sth) / c2;
+    // f2() (uav.py:302-313)
+    const T g0 = (c.kr * p + q * r * (c.J1 - c.J2)) / c.J0;
+    const T g1 = (c.kr * q + p * r * (c.J2 - c.J0)) / c.J1;
+    const T g2 = (c.kr * r + p * q * (c.J0 - c.J1)) / c.J2;
+    T sec[3];
+    sec[0] = (F01 * q + F02 * r) + (g0 + f01 * g1 + f02 * g2);
+    sec[1] = (F11 * q + F12 * r) + (f11 * g1 + f12 * g2);
+    sec[2] = (F21 * q + F22 * r) + (f21 * g1 + f22 * g2);
+    T v[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const T e = x[6 + i] - ref[i], de = d1[i] - dref[i];
+        T sigma, dot_s1, pa1_de;
+        smc_axis<T>(e, de, k1[i], gamma[i], alpha[i], beta[i], lmd[i], c.dt, s1[i], sigma, dot_s1, pa1_de);
+        const T u1 = sec[i] + k1[i] * de + pa1_de + lmd[i] * dot_s1;
+        const T u2 = -k2[i] * Mth<T>::tanh((T)10 * sigma);
+        v[i] = u1 + u2;
+    }
+    const T h0 = (T)1 / c.J0, h1 = (T)1 / c.J1, h2 = (T)1 / c.J2;
+    neg_inv_apply<T>(h0, f01 * h1, f02 * h2, f11 * h1, f12 * h2, f21 * h1, f22 * h2, v, torque);
+}
+
+// uav.py:182-219: 2 position out, 3 attitude out, 1 time out -- evaluated in this order, the last true wins
+template <typename T>
+__device__ __forceinline__ int terminal_flag(const P &p, const T *x, double time) {
+    int flag = 0;
+    bool out = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out = out || (x[i] < (T)p.pos_lo[i]) || (x[i] > (T)p.pos_hi[i]);
+    if (out) flag = 2;
+    out = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out = out || (x[6 + i] < (T)p.att_lo[i]) || (x[6 + i] > (T)p.att_hi[i]);
+    if (out) flag = 3;
+    if (time > p.t_term) flag = 1;
+    return flag;
+}
+
+// ref_cmd.py:4-43, one channel
+template <typename T>
+__device__ __forceinline__ void ref_channel(T time, T A, T period, T bias, T phase, T &r, T &dr, T &ddr) {
+    const T w = (T)(2 * M_PI) / period;
+    T s, co;
+    Mth<T>::sincos(w * time + phase, &s, &co);
+    r = A * s + bias;
+    dr = A * w * co;
+    ddr = -A * (w * w) * s;
+}
+
+// ------------------------------------------------------------------------------------------ attitude env
+enum { A_S1 = 6, A_K1 = 9, A_K2 = 12, A_GAM = 15, A_LMD = 18, A_AMP = 21, A_PER = 24, A_PHS = 27, A_REF = 30, A_DREF = 33 };
+
+template <typename T>
+__device__ __forceinline__ void att_reset_state(const P &p, const b200env_io &io, int64_t n, int64_t i, uint64_t seed,
+                                                int64_t off, T *x /* out: 12 states */) {
+    const uint32_t ep = io.episode[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = (T)p.init_state[6 + k]; st<T>(io.state, n, k, i, x[6 + k]); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        st<T>(io.state, n, A_S1 + k, i, (T)0);
+        st<T>(io.state, n, A_K1 + k, i, (T)p.att_k1[k]);
+        st<T>(io.state, n, A_K2 + k, i, (T)p.att_k2[k]);
+        st<T>(io.state, n, A_GAM + k, i, (T)p.att_gamma[k]);
+        st<T>(io.state, n, A_LMD + k, i, (T)p.att_lmd[k]);
+    }
+    double A[3], Tp[3], ph[3];
+    if (p.random_trajectory) { // uav_att_ctrl.py:156-161
+        Philox rng(seed, (uint64_t)(off + i), ep);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) A[k] = rng.uniform(0., p.traj_A_hi[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Tp[k] = rng.uniform(p.traj_T_lo, p.traj_T_hi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ph[k] = rng.uniform(0., p.traj_phase_hi);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { A[k] = p.ref_amplitude[k]; Tp[k] = p.ref_period[k]; ph[k] = p.ref_bias_phase[k]; }
+    }
+    if (p.yaw_fixed) { A[2] = 0.; ph[2] = 0.; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        st<T>(io.state, n, A_AMP + k, i, (T)A[k]);
+        st<T>(io.state, n, A_PER + k, i, (T)Tp[k]);
+        st<T>(io.state, n, A_PHS + k, i, (T)ph[k]);
+    }
+    io.time[i] = 0.0;
+    io.episode[i] = ep + 1u;
+}
+
+// uav_att_ctrl_RL.py:59-68 (use_norm = False)
+template <typename T>
+__device__ __forceinline__ void att_observe(const T *x, const Trig<T> &t, const T *ref, const T *dref, T *o) {
+    const T q = x[10], r = x[11];
+    o[0] = x[6] - ref[0]; o[1] = x[7] - ref[1]; o[2] = x[8] - ref[2];
+    o[3] = (x[9] + (t.sphi * t.tth) * q + (t.cphi * t.tth) * r) - dref[0];
+    o[4] = (t.cphi * q - t.sphi * r) - dref[1];
+    o[5] = ((t.sphi / t.cth) * q + (t.cphi / t.cth) * r) - dref[2];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B200_BLOCK)
+uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
+                    uint64_t seed, int64_t off) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Consts<T> c(p);
+    T x[12];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = ld<T>(io.state, n, k, i); }
+    double time = io.time[i];
+    T s1[3], k1[3], k2[3], gam[3], lmd[3], alpha[3], beta[3], ref[3], dref[3];
+    T a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = ld<T>(io.action, n, k, i);
+    // get_param_from_actor, uav_att_ctrl_RL.py:141-156: a gain is overwritten only where the actor output is > 0 (N6)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s1[k] = ld<T>(io.state, n, A_S1 + k, i);
+        k1[k] = a[k] > (T)0 ? (T)10 * a[k] : ld<T>(io.state, n, A_K1 + k, i);
+        k2[k] = a[k + 3] > (T)0 ? a[k + 3] / (T)10 : ld<T>(io.state, n, A_K2 + k, i);
+        gam[k] = a[6] > (T)0 ? a[6] : ld<T>(io.state, n, A_GAM + k, i);
+        lmd[k] = a[7] > (T)0 ? a[7] : ld<T>(io.state, n, A_LMD + k, i);
+        alpha[k] = (T)p.att_alpha[k];
+        beta[k] = (T)p.att_beta[k];
+    }
+    // ref_inner(time, A, T, 0, phase), ref_cmd.py:4-22
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        T dd;
+        ref_channel<T>((T)time, ld<T>(io.state, n, A_AMP + k, i), ld<T>(io.state, n, A_PER + k, i), (T)0,
+                       ld<T>(io.state, n, A_PHS + k, i), ref[k], dref[k], dd);
+    }
+    Trig<T> t1;
+    t1.eval(x[6], x[7], x[8], false);
+    T torque[3], d1[3];
+    att_control<T>(c, x, t1, k1, k2, gam, lmd, alpha, beta, s1, ref, dref, torque, d1);
+    if (io.obs) { // current_state = get_state()
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            st<T>(io.obs, n, k, i, x[6 + k] - ref[k]);
+            st<T>(io.obs, n, 3 + k, i, d1[k] - dref[k]);
+        }
+    }
+    // update(): throttle only drives the (zeroed) translational states in att_only mode, uav_att_ctrl.py:110-128
+    const T zero3[3] = {(T)0, (T)0, (T)0};
+    uav_rk44<T, true>(c, x, t1, (T)0, torque, zero3);
+    time += p.dt;
+    const int flag = terminal_flag<T>(p, x, time);
+    const bool done = (flag == 1) || (flag == 3); // uav_att_ctrl_RL.py:118-127
+    Trig<T> t2;
+    t2.eval(x[6], x[7], x[8], false);
+    T nxt[6];
+    att_observe<T>(x, t2, ref, dref, nxt);
+    // get_reward, uav_att_ctrl_RL.py:70-106
+    const T u_att = -(nxt[0] * nxt[0] * (T)p.Q_e[0] + nxt[1] * nxt[1] * (T)p.Q_e[1] + nxt[2] * nxt[2] * (T)p.Q_e[2]);
+    const T u_pqr = -(nxt[3] * nxt[3] * (T)p.Q_de[0] + nxt[4] * nxt[4] * (T)p.Q_de[1] + nxt[5] * nxt[5] * (T)p.Q_de[2]);
+    const T u_acc = -(torque[0] * torque[0] * (T)p.R[0] + torque[1] * torque[1] * (T)p.R[1] + torque[2] * torque[2] * (T)p.R[2]);
+    T u_extra = (T)0;
+    if (flag == 3) {
+        const T nn = (T)((p.time_max - time) / p.dt);
+        const T pi2 = (T)(M_PI * M_PI);
+        T u_phi = (T)0, u_theta = (T)0;
+        if (x[6] > (T)p.att_zone_max[0] || x[6] < (T)p.att_zone_min[0]) u_phi = -pi2 * (T)p.Q_e[0];
+        if (x[7] > (T)p.att_zone_max[1] || x[7] < (T)p.att_zone_min[1]) u_theta = -pi2 * (T)p.Q_e[1];
+        if (x[8] > (T)p.att_zone_max[2] || x[8] < (T)p.att_zone_min[2]) u_theta = (T)-4 * pi2 * (T)p.Q_e[2]; // sic (N7)
+        u_extra = nn * (u_phi + u_theta + u_pqr + u_acc);
+    }
+    const T reward = u_att + u_pqr + u_acc + u_extra;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) st<T>(io.next_obs, n, k, i, nxt[k]);
+    st<T>(io.reward, n, 0, i, reward);
+    io.done[i] = done ? 1 : 0;
+    io.flag[i] = flag;
+    if (done && (flags & B200ENV_AUTO_RESET)) {
+        T xr[12];
+        att_reset_state<T>(p, io, n, i, seed, off, xr);
+        Trig<T> tr;
+        tr.eval(xr[6], xr[7], xr[8], false);
+        att_observe<T>(xr, tr, ref, dref, nxt); // first obs of the next episode against the stale ref (reference quirk)
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st<T>(io.state, n, k, i, x[6 + k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            st<T>(io.state, n, A_S1 + k, i, s1[k]);
+            st<T>(io.state, n, A_K1 + k, i, k1[k]);
+            st<T>(io.state, n, A_K2 + k, i, k2[k]);
+            st<T>(io.state, n, A_GAM + k, i, gam[k]);
+            st<T>(io.state, n, A_LMD + k, i, lmd[k]);
+        }
+        io.time[i] = time;
+        if (done) { // keep the last reference for a later explicit reset()/observe()
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { st<T>(io.state, n, A_REF + k, i, ref[k]); st<T>(io.state, n, A_DREF + k, i, dref[k]); }
+        }
+    }
+    if (io.reset_obs) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st<T>(io.reset_obs, n, k, i, nxt[k]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B200_BLOCK)
+uav_att_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n,
+                     const uint8_t *mask, uint64_t seed, int64_t off, int observe_only) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!observe_only && mask && !mask[i]) return;
+    T x[12];
+    if (observe_only) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = ld<T>(io.state, n, k, i); }
+    } else {
+        att_reset_state<T>(p, io, n, i, seed, off, x);
+    }
+    if (io.next_obs) {
+        T ref[3], dref[3], o[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { ref[k] = ld<T>(io.state, n, A_REF + k, i); dref[k] = ld<T>(io.state, n, A_DREF + k, i); }
+        Trig<T> t;
+        t.eval(x[6], x[7], x[8], false);
+        att_observe<T>(x, t, ref, dref, o);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st<T>(io.next_obs, n, k, i, o[k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ position env
+enum { P_SIG = 12, P_S1 = 15, P_AREF = 18, P_K1 = 21, P_K2 = 24, P_GAM = 27, P_LMD = 30, P_AMP = 33, P_PER = 37,
+       P_PHS = 41, P_PREF = 45, P_DPREF = 48 };
+
+template <typename T>
+__device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io, int64_t n, int64_t i, uint64_t seed,
+                                                int64_t off, T *x) {
+    const uint32_t ep = io.episode[i];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { x[k] = (T)p.init_state[k]; st<T>(io.state, n, k, i, x[k]); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        st<T>(io.state, n, P_SIG + k, i, (T)0);
+        st<T>(io.state, n, P_S1 + k, i, (T)0);
+        st<T>(io.state, n, P_K1 + k, i, (T)p.pos_k1[k]);
+        st<T>(io.state, n, P_K2 + k, i, (T)p.pos_k2[k]);
+        st<T>(io.state, n, P_GAM + k, i, (T)p.pos_gamma[k]);
+        st<T>(io.state, n, P_LMD + k, i, (T)p.pos_lmd[k]);
+    }
+    double A[4], Tp[4], ph[4];
+    if (p.random_trajectory) { // uav_pos_ctrl.py:404-408
+        Philox rng(seed, (uint64_t)(off + i), ep);
+        const double a = rng.uniform(0., p.traj_A_hi[0]);
+        const double tt = rng.uniform(p.traj_T_lo, p.traj_T_hi);
+        A[0] = A[1] = A[2] = a; A[3] = 0.;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { Tp[k] = tt; ph[k] = p.ref_bias_phase[k]; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { A[k] = p.ref_amplitude[k]; Tp[k] = p.ref_period[k]; ph[k] = p.ref_bias_phase[k]; }
+    }
+    if (p.yaw_fixed) { A[3] = 0.; ph[3] = 0.; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        st<T>(io.state, n, P_AMP + k, i, (T)A[k]);
+        st<T>(io.state, n, P_PER + k, i, (T)Tp[k]);
+        st<T>(io.state, n, P_PHS + k, i, (T)ph[k]);
+    }
+    // att_ref is not reset by the reference (uav_pos_ctrl.py:488-533): left as stored
+    io.time[i] = 0.0;
+    io.episode[i] = ep + 1u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B200_BLOCK)
+uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
+                    uint64_t seed, int64_t off) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Consts<T> c(p);
+    T x[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) x[k] = ld<T>(io.state, n, k, i);
+    double time = io.time[i];
+    T a[8], dis[3] = {(T)0, (T)0, (T)0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = ld<T>(io.action, n, k, i);
+    if (io.dis) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dis[k] = ld<T>(io.dis, n, k, i);
+    }
+    // get_param_from_actor, uav_pos_ctrl_RL.py:158-173 (N6)
+    T sig[3], s1[3], aref[3], k1[3], k2[3], gam[3], lmd[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        sig[k] = ld<T>(io.state, n, P_SIG + k, i);
+        s1[k] = ld<T>(io.state, n, P_S1 + k, i);
+        aref[k] = ld<T>(io.state, n, P_AREF + k, i);
+        k1[k] = a[k] > (T)0 ? a[k] : ld<T>(io.state, n, P_K1 + k, i);
+        k2[k] = a[k + 3] > (T)0 ? a[k + 3] : ld<T>(io.state, n, P_K2 + k, i);
+        gam[k] = a[6] > (T)0 ? a[6] : ld<T>(io.state, n, P_GAM + k, i);
+        lmd[k] = a[7] > (T)0 ? a[7] : ld<T>(io.state, n, P_LMD + k, i);
+    }
+    // ref_uav(time, A, T, bias, phase), ref_cmd.py:25-43
+    T ref[4], dref[4], ddref[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        ref_channel<T>((T)time, ld<T>(io.state, n, P_AMP + k, i), ld<T>(io.state, n, P_PER + k, i), (T)p.ref_bias_a[k],
+                       ld<T>(io.state, n, P_PHS + k, i), ref[k], dref[k], ddref[k]);
+    // pos_control, uav_pos_ctrl.py:302-315 + FNTSMC.py:47-69 (obs = 0)
+    T ctrl[3];
+    const T kt_m = c.kt / c.m;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T e = x[k] - ref[k], de = x[3 + k] - dref[k];
+        T so, dso1, pa1_de;
+        smc_axis<T>(e, de, k1[k], gam[k], (T)p.pos_alpha[k], (T)p.pos_beta[k], lmd[k], c.dt, sig[k], so, dso1, pa1_de);
+        const T uo1 = kt_m * x[3 + k] + ddref[k] - k1[k] * de - pa1_de - lmd[k] * dso1;
+        const T uo2 = -k2[k] * so;
+        ctrl[k] = uo1 + uo2;
+    }
+    Trig<T> t1;
+    t1.eval(x[6], x[7], x[8], true);
+    // uo_2_ref_angle_throttle(limit = pi/4), uav_pos_ctrl.py:339-357
+    const T uf = (ctrl[2] + c.g) * c.m / (t1.cphi * t1.cth);
+    const T asin_phi_d = Mth<T>::min(Mth<T>::max((ctrl[0] * t1.spsi - ctrl[1] * t1.cpsi) * c.m / uf, (T)-1), (T)1);
+    T phi_d = Mth<T>::asin(asin_phi_d);
+    const T asin_theta_d = Mth<T>::min(
+        Mth<T>::max((ctrl[0] * t1.cpsi + ctrl[1] * t1.spsi) * c.m / (uf * Mth<T>::cos(phi_d)), (T)-1), (T)1);
+    T theta_d = Mth<T>::asin(asin_theta_d);
+    const T lim = (T)p.att_limit;
+    phi_d = Mth<T>::max(Mth<T>::min(phi_d, lim), -lim);
+    theta_d = Mth<T>::max(Mth<T>::min(theta_d, lim), -lim);
+    // generate_action_4_uav, uav_pos_ctrl.py:470-481: finite-difference reference rates, clipped, then integrated back
+    T rho_d[3] = {phi_d, theta_d, ref[3]};
+    T drho_d[3] = {(phi_d - aref[0]) / c.dt, (theta_d - aref[1]) / c.dt, dref[3]};
+    const T rl = (T)p.dot_att_ref_limit;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        drho_d[k] = Mth<T>::min(Mth<T>::max(drho_d[k], -rl), rl);
+        rho_d[k] = rho_d[k] + drho_d[k] * c.dt;
+        aref[k] = rho_d[k];
+    }
+    T torque[3], d1[3], ak1[3], ak2[3], agam[3], almd[3], aalpha[3], abeta[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        ak1[k] = (T)p.att_k1[k]; ak2[k] = (T)p.att_k2[k]; agam[k] = (T)p.att_gamma[k]; almd[k] = (T)p.att_lmd[k];
+        aalpha[k] = (T)p.att_alpha[k]; abeta[k] = (T)p.att_beta[k];
+    }
+    att_control<T>(c, x, t1, ak1, ak2, agam, almd, aalpha, abeta, s1, rho_d, drho_d, torque, d1);
+    if (io.obs) { // current_state = get_state(), uav_pos_ctrl_RL.py:59-68
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            st<T>(io.obs, n, k, i, x[k] - ref[k]);
+            st<T>(io.obs, n, 3 + k, i, x[3 + k] - dref[k]);
+        }
+    }
+    uav_rk44<T, false>(c, x, t1, uf, torque, dis);
+    time += p.dt;
+    const int flag = terminal_flag<T>(p, x, time);
+    const bool done = flag != 0; // uav_pos_ctrl_RL.py:132-143
+    T nxt[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { nxt[k] = x[k] - ref[k]; nxt[3 + k] = x[3 + k] - dref[k]; }
+    // get_reward, uav_pos_ctrl_RL.py:82-120
+    const T u_pos = -(nxt[0] * nxt[0] * (T)p.Q_e[0] + nxt[1] * nxt[1] * (T)p.Q_e[1] + nxt[2] * nxt[2] * (T)p.Q_e[2]);
+    const T u_vel = -(nxt[3] * nxt[3] * (T)p.Q_de[0] + nxt[4] * nxt[4] * (T)p.Q_de[1] + nxt[5] * nxt[5] * (T)p.Q_de[2]);
+    const T u_acc = -(ctrl[0] * ctrl[0] * (T)p.R[0] + ctrl[1] * ctrl[1] * (T)p.R[1] + ctrl[2] * ctrl[2] * (T)p.R[2]);
+    T u_extra = (T)0;
+    if (flag == 2 || flag == 3) {
+        const T nn = (T)((p.time_max - time) / p.dt);
+        u_extra = nn * (u_pos + u_vel + u_acc);
+    }
+    const T reward = u_pos + u_vel + u_acc + u_extra;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) st<T>(io.next_obs, n, k, i, nxt[k]);
+    st<T>(io.reward, n, 0, i, reward);
+    io.done[i] = done ? 1 : 0;
+    io.flag[i] = flag;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) st<T>(io.state, n, P_AREF + k, i, aref[k]);
+    if (done && (flags & B200ENV_AUTO_RESET)) {
+        T xr[12];
+        pos_reset_state<T>(p, io, n, i, seed, off, xr);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { nxt[k] = xr[k] - ref[k]; nxt[3 + k] = xr[3 + k] - dref[k]; } // stale pos_ref (quirk)
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) st<T>(io.state, n, k, i, x[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            st<T>(io.state, n, P_SIG + k, i, sig[k]);
+            st<T>(io.state, n, P_S1 + k, i, s1[k]);
+            st<T>(io.state, n, P_K1 + k, i, k1[k]);
+            st<T>(io.state, n, P_K2 + k, i, k2[k]);
+            st<T>(io.state, n, P_GAM + k, i, gam[k]);
+            st<T>(io.state, n, P_LMD + k, i, lmd[k]);
+        }
+        io.time[i] = time;
+        if (done) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { st<T>(io.state, n, P_PREF + k, i, ref[k]); st<T>(io.state, n, P_DPREF + k, i, dref[k]); }
+        }
+    }
+    if (io.reset_obs) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st<T>(io.reset_obs, n, k, i, nxt[k]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B200_BLOCK)
+uav_pos_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n,
+                     const uint8_t *mask, uint64_t seed, int64_t off, int observe_only) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!observe_only && mask && !mask[i]) return;
+    T x[12];
+    if (observe_only) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) x[k] = ld<T>(io.state, n, k, i);
+    } else {
+        pos_reset_state<T>(p, io, n, i, seed, off, x);
+    }
+    if (io.next_obs) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            st<T>(io.next_obs, n, k, i, x[k] - ld<T>(io.state, n, P_PREF + k, i));
+            st<T>(io.next_obs, n, 3 + k, i, x[3 + k] - ld<T>(io.state, n, P_DPREF + k, i));
+        }
+    }
+}
+
+} // namespace
+
+#define UAV_LAUNCH(kern, ...)                                                                      \
+    do {                                                                                           \
+        if (dtype == B200ENV_F64) kern<double><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);   \
+        else kern<float><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                         \
+    } while (0)
+
+int uav_att_dims(int variant, int *sf, int *od, int *ad, int *dd) {
+    if (variant != 0) return B200ENV_EENV;
+    if (sf) *sf = B200_UAV_ATT_STATE_FIELDS;
+    if (od) *od = 6;
+    if (ad) *ad = 8;
+    if (dd) *dd = 0;
+    return B200ENV_OK;
+}
+int uav_pos_dims(int variant, int *sf, int *od, int *ad, int *dd) {
+    if (variant != 0) return B200ENV_EENV;
+    if (sf) *sf = B200_UAV_POS_STATE_FIELDS;
+    if (od) *od = 6;
+    if (ad) *ad = 8;
+    if (dd) *dd = 3;
+    return B200ENV_OK;
+}
+
+static int uav_check_step(const b200env_io *io, uint32_t flags) {
+    if (!io->state || !io->time || !io->action || !io->next_obs || !io->reward || !io->done || !io->flag) return B200ENV_ENULL;
+    if ((flags & B200ENV_AUTO_RESET) && !io->episode) return B200ENV_ENULL;
+    return B200ENV_OK;
+}
+
+int uav_att_step(int dtype, int64_t n, const void *params, const b200env_io *io, uint32_t flags, uint64_t seed,
+                 int64_t off, cudaStream_t s) {
+    int rc = uav_check_step(io, flags);
+    if (rc) return rc;
+    const P &p = *static_cast<const P *>(params);
+    UAV_LAUNCH(uav_att_step_kernel, p, *io, n, flags, seed, off);
+    return b200_check_launch();
+}
+int uav_pos_step(int dtype, int64_t n, const void *params, const b200env_io *io, uint32_t flags, uint64_t seed,
+                 int64_t off, cudaStream_t s) {
+    int rc = uav_check_step(io, flags);
+    if (rc) return rc;
+    const P &p = *static_cast<const P *>(params);
+    UAV_LAUNCH(uav_pos_step_kernel, p, *io, n, flags, seed, off);
+    return b200_check_launch();
+}
+int uav_att_reset(int dtype, int64_t n, const void *params, const b200env_io *io, const uint8_t *mask, uint64_t seed,
+                  int64_t off, cudaStream_t s) {
+    if (!io->state || !io->time || !io->episode) return B200ENV_ENULL;
+    const P &p = *static_cast<const P *>(params);
+    UAV_LAUNCH(uav_att_reset_kernel, p, *io, n, mask, seed, off, 0);
+    return b200_check_launch();
+}
+int uav_pos_reset(int dtype, int64_t n, const void *params, const b200env_io *io, const uint8_t *mask, uint64_t seed,
+                  int64_t off, cudaStream_t s) {
+    if (!io->state || !io->time || !io->episode) return B200ENV_ENULL;
+    const P &p = *static_cast<const P *>(params);
+    UAV_LAUNCH(uav_pos_reset_kernel, p, *io, n, mask, seed, off, 0);
+    return b200_check_launch();
+}
+int uav_att_observe(int dtype, int64_t n, const void *params, const b200env_io *io, cudaStream_t s) {
+    if (!io->state || !io->time || !io->next_obs) return B200ENV_ENULL;
+    const P &p = *static_cast<const P *>(params);
+    UAV_LAUNCH(uav_att_reset_kernel, p, *io, n, nullptr, 0, 0, 1);
+    return b200_check_launch();
+}
+int uav_pos_observe(int dtype, int64_t n, const void *params, const b200env_io *io, cudaStream_t s) {
+    if (!io->state || !io->time || !io->next_obs) return B200ENV_ENULL;
+    const P &p = *static_cast<const P *>(params);
+    UAV_LAUNCH(uav_pos_reset_kernel, p, *io, n, nullptr, 0, 0, 1);
+    return b200_check_launch();
+}

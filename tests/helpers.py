@@ -31,6 +31,13 @@ def env_specs():
         "cartpole_gentle": (rlp.CartPole, {}),
         "cartpole_angleonly_env": (rlp.CartPoleAngleOnly, {"variant": "env"}),
         "cartpole_angleonly_ppo2": (rlp.CartPoleAngleOnly, {"variant": "ppo2"}),
+        "uav_pos": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
+        "uav_pos_dis": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
+        "uav_pos_crash": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
+        "uav_pos_edge": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
+        "uav_att": (rlp.UavAttCtrlRL, {"random_trajectory": False}),
+        "uav_att_rand": (rlp.UavAttCtrlRL, {"random_trajectory": True}),
+        "uav_att_edge": (rlp.UavAttCtrlRL, {"random_trajectory": True}),
     }
 
 
@@ -87,26 +94,54 @@ class EngineBackend:
                     state=f(e._state.t()), time=e._time.cpu().numpy().copy())
 
 
-def replay(g, backend, resync=False, steps=None):
+# leading state fields that are compared; the trailing ones are "lazy" (only written on terminal steps, see
+# include/b200env.h: ref/dot_ref of the attitude env, pos_ref/dot_pos_ref of the position env)
+STATE_CMP = {"uav_pos": 45, "uav_att": 30}
+
+
+def _cmp_fields(name):
+    for k, v in STATE_CMP.items():
+        if name.startswith(k):
+            return v
+    return None
+
+
+def replay(g, backend, resync=False, steps=None, name="", sens_k=1000.0, floor=1e-12):
     """Run the fixture's actions through `backend`.  Free-running: state carried by the backend, re-injected
-    only after the reference's resets.  resync=True: the fixture's state is injected before every step."""
+    only after the reference's resets.  resync=True: the fixture's state is injected before every step.
+
+    Besides the raw worst mixed errors the result carries `worst_ratio`: the worst error divided by the per-lane
+    tolerance max(floor, sens_k * running max of the fixture's twin_err), i.e. relative to how far the reference
+    drifts from ITSELF when nudged by 1e-16 per step (its own sensitivity to rounding)."""
     T, L = g["reward"].shape
     if steps:
         T = min(T, steps)
     has_dis = "dis" in g
+    nf = _cmp_fields(name)
     backend.set_state(g["state0"], g["time0"])
     worst = dict(obs=0.0, next_obs=0.0, reward=0.0, state=0.0, time=0.0)
     flag_mismatch = 0
     done_mismatch = 0
     first_bad = None
+    run_sens = np.zeros(L)
+    worst_ratio = 0.0
+    lane_err = lambda a, b: np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)), axis=1) if a.ndim == 2 else np.abs(a - b) / np.maximum(1.0, np.abs(b))
     for t in range(T):
         if resync and t > 0:
             st = np.where(np.isnan(g["reset_state"][t - 1]), g["state"][t - 1], g["reset_state"][t - 1])
             tm = np.where(np.isnan(g["reset_time"][t - 1]), g["time"][t - 1], g["reset_time"][t - 1])
             backend.set_state(st, tm)
         out = backend.step(g["actions"][t], g["dis"][t] if has_dis else None)
+        if "twin_err" in g:
+            run_sens = np.maximum(run_sens, g["twin_err"][t])
+        tol = np.maximum(floor, sens_k * run_sens)
         for k in ("obs", "next_obs", "reward", "state"):
-            worst[k] = max(worst[k], mixed_err(out[k], g[k][t]))
+            a, b = out[k], g[k][t]
+            if k == "state" and nf:
+                a, b = a[:, :nf], b[:, :nf]
+            worst[k] = max(worst[k], mixed_err(a, b))
+            if k != "obs":
+                worst_ratio = max(worst_ratio, float(np.max(lane_err(np.asarray(a, np.float64), b) / tol)))
         worst["time"] = max(worst["time"], float(np.max(np.abs(out["time"] - g["time"][t]))))
         fm = int(np.sum(out["flag"] != g["flag"][t]))
         dm = int(np.sum(out["done"] != g["done"][t]))
@@ -115,9 +150,12 @@ def replay(g, backend, resync=False, steps=None):
         flag_mismatch += fm
         done_mismatch += dm
         lanes = np.nonzero(g["done"][t])[0]
-        if len(lanes) and not resync:
-            backend.set_state(g["reset_state"][t][lanes], g["reset_time"][t][lanes], lanes)
-    return dict(worst=worst, flag_mismatch=flag_mismatch, done_mismatch=done_mismatch, first_bad=first_bad, steps=T)
+        if len(lanes):
+            run_sens[lanes] = 0.0
+            if not resync:
+                backend.set_state(g["reset_state"][t][lanes], g["reset_time"][t][lanes], lanes)
+    return dict(worst=worst, worst_ratio=worst_ratio, flag_mismatch=flag_mismatch, done_mismatch=done_mismatch,
+                first_bad=first_bad, steps=T)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -129,12 +167,14 @@ def action_bounds(name, env):
 
 
 def smoke_cases():
-    return ["cartpole"]
+    return ["cartpole", "uav_att", "uav_pos"]
 
 
 # fp64 tolerance of the free-running engine-vs-oracle comparison (mixed metric), per fixture family
 ENGINE_TOL = {
     "cartpole": 1e-9, "cartpole_gentle": 1e-9, "cartpole_angleonly_env": 1e-9, "cartpole_angleonly_ppo2": 1e-9,
+    "uav_pos": 1e-9, "uav_pos_dis": 1e-9, "uav_pos_crash": 1e-9, "uav_pos_edge": 1e-9,
+    "uav_att": 1e-9, "uav_att_rand": 1e-9, "uav_att_edge": 1e-9,
 }
 
 
@@ -154,7 +194,9 @@ def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None
     orc.reset()
     torch.cuda.synchronize()
     f = lambda x: x.detach().cpu().numpy().astype(np.float64)
-    worst = mixed_err(f(env._state), orc.state)
+    nf = _cmp_fields(name)
+    cs = (lambda a: a[:nf]) if nf else (lambda a: a)
+    worst = mixed_err(cs(f(env._state)), cs(orc.state))
     lo, hi = action_bounds(name, env)
     rng = np.random.default_rng(seed)
     flag_mismatch = 0
@@ -172,7 +214,7 @@ def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None
         flag_mismatch += fm
         n_done += int(orc.done.sum())
         for got, ref in ((env._obs, orc.obs), (env._next_obs, orc.next_obs), (env._reward, orc.reward),
-                         (env._state, orc.state), (env._reset_obs, orc.reset_obs)):
+                         (cs(env._state), cs(orc.state)), (env._reset_obs, orc.reset_obs)):
             worst = max(worst, mixed_err(f(got), ref))
         worst = max(worst, float(np.max(np.abs(env._time.cpu().numpy() - orc.time))))
         if fm:  # trajectories diverge after a flag mismatch: re-sync the engine from the oracle

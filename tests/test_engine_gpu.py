@@ -10,12 +10,17 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN_CASES = sorted(ENGINE_TOL)
 
+# Fixtures whose actions were recorded from a closed loop around an open-loop-unstable plant: replaying them
+# open loop amplifies a 1-ulp difference by e^(lambda*t) (inverted pendulum: lambda ~ 6/s, 5 s episodes -> 1e13),
+# so only the one-step (re-sync) comparison is meaningful.  The C oracle still matches them bit-exactly.
+OPEN_LOOP_UNSTABLE = {"cartpole_gentle": "open-loop replay of closed-loop actions on an unstable plant (e^30 gain)"}
+
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_engine_matches_reference_fixture_resync(name):
     """one-step mode: inject the reference state before every step; every output within 1e-12, flags exact."""
     g = load_golden(name)
-    res = replay(g, EngineBackend(name, g["reward"].shape[1]), resync=True)
+    res = replay(g, EngineBackend(name, g["reward"].shape[1]), resync=True, name=name)
     assert res["flag_mismatch"] == 0 and res["done_mismatch"] == 0, res
     assert res["worst"]["time"] == 0.0, res
     for k, v in res["worst"].items():
@@ -25,10 +30,14 @@ def test_engine_matches_reference_fixture_resync(name):
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_engine_matches_reference_fixture_free_running(name):
     """free-running over the whole fixture (1000 steps), state re-injected only after the reference's resets."""
+    if name in OPEN_LOOP_UNSTABLE:
+        pytest.skip(OPEN_LOOP_UNSTABLE[name])
     g = load_golden(name)
-    res = replay(g, EngineBackend(name, g["reward"].shape[1]), resync=False)
+    res = replay(g, EngineBackend(name, g["reward"].shape[1]), resync=False, name=name)
     assert res["flag_mismatch"] == 0 and res["done_mismatch"] == 0, res
     assert res["worst"]["time"] == 0.0, res
+    # within 1000x the reference's own drift under 1e-16 nudges (floor 1e-12), and an absolute ceiling
+    assert res["worst_ratio"] <= 1.0, res
     for k, v in res["worst"].items():
         assert v <= ENGINE_TOL[name], (k, res)
 

@@ -6,11 +6,15 @@ import pytest
 from helpers import OracleBackend, load_golden, replay
 
 # name -> tolerance of the mixed metric.  0.0 = bit-exact (same glibc sin/cos as numpy, same operation order).
+# The UAV envs cannot be bit-exact: numpy evaluates the vector pow/tanh of FNTSMC.py with AVX-512 SIMD kernels that
+# differ from glibc by 1-3 ulp and np.dot/np.linalg.inv go through OpenBLAS.  One-step bar: 1e-12 (observed <= 1e-14).
 CASES = {
     "cartpole": 0.0,
     "cartpole_gentle": 0.0,
     "cartpole_angleonly_env": 0.0,
     "cartpole_angleonly_ppo2": 0.0,
+    "uav_pos": 1e-12, "uav_pos_dis": 1e-12, "uav_pos_crash": 1e-12, "uav_pos_edge": 1e-12,
+    "uav_att": 1e-12, "uav_att_rand": 1e-12, "uav_att_edge": 1e-12,
 }
 
 
@@ -18,8 +22,12 @@ CASES = {
 @pytest.mark.parametrize("resync", [False, True])
 def test_oracle_matches_reference_fixture(name, resync, oracle_lib):
     g = load_golden(name)
-    res = replay(g, OracleBackend(name, g["reward"].shape[1]), resync=resync)
+    res = replay(g, OracleBackend(name, g["reward"].shape[1]), resync=resync, name=name)
     assert res["flag_mismatch"] == 0 and res["done_mismatch"] == 0, res
     assert res["worst"]["time"] == 0.0, res
-    for k, v in res["worst"].items():
-        assert v <= CASES[name], (k, res)
+    if resync or CASES[name] == 0.0:
+        for k, v in res["worst"].items():
+            assert v <= CASES[name], (k, res)
+    else:
+        # free-running: within 1000x the reference's own sensitivity to 1e-16 nudges (floor 1e-12)
+        assert res["worst_ratio"] <= 1.0, res
