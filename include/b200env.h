@@ -198,6 +198,13 @@ B200_API int b200env_observe(int env_id, int dtype, int64_t n_envs,
                     const void *params, size_t params_bytes,
                     const b200env_io *io, void *cuda_stream);
 
+/* ------------------------------------------------------------- diagnostics */
+
+/* Measures the FP64 (dtype = B200ENV_F64) or FP32 vector FMA peak of the current device in TFLOP/s (2 flops per
+ * FMA) with an 8-way independent FMA chain per thread: the roofline denominator of the compute-bound env kernels,
+ * which MEASURED_PEAKS.json does not carry.  Blocks until done.  Not on the hot path. */
+B200_API int b200_measure_fma_peak(int dtype, int iters, double *tflops, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,8 +96,17 @@ def load() -> C.CDLL:
     lib.b200env_reset.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), vp, u64, i64, vp]
     lib.b200env_observe.restype = i32
     lib.b200env_observe.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), vp]
+    lib.b200_measure_fma_peak.restype = i32
+    lib.b200_measure_fma_peak.argtypes = [i32, i32, C.POINTER(C.c_double), vp]
     _lib = lib
     return lib
+
+
+def measure_fma_peak(dtype_code: int = F64, iters: int = 20000) -> float:
+    """TFLOP/s of the FP64/FP32 vector FMA pipe of the current CUDA device (diagnostic, include/b200env.h)."""
+    out = C.c_double()
+    check(load().b200_measure_fma_peak(dtype_code, iters, C.byref(out), None), "b200_measure_fma_peak")
+    return out.value
 
 
 def check(rc: int, what: str) -> None:

@@ -25,6 +25,8 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double tan(double x) { return ::tan(x); }
     static __device__ __forceinline__ double tanh(double x) { return ::tanh(x); }
     static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
+    static __device__ __forceinline__ double log(double x) { return ::log(x); }
+    static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
     static __device__ __forceinline__ double acos(double x) { return ::acos(x); }
@@ -41,6 +43,8 @@ template <> struct Mth<float> {
     static __device__ __forceinline__ float tan(float x) { return ::tanf(x); }
     static __device__ __forceinline__ float tanh(float x) { return ::tanhf(x); }
     static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }
+    static __device__ __forceinline__ float log(float x) { return ::logf(x); }
+    static __device__ __forceinline__ float exp(float x) { return ::expf(x); }
     static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
     static __device__ __forceinline__ float asin(float x) { return ::asinf(x); }
     static __device__ __forceinline__ float acos(float x) { return ::acosf(x); }
@@ -49,6 +53,14 @@ template <> struct Mth<float> {
     static __device__ __forceinline__ float min(float a, float b) { return ::fminf(a, b); }
     static __device__ __forceinline__ float max(float a, float b) { return ::fmaxf(a, b); }
 };
+
+// x^a for x >= 0 given L = log(x): exp(a * L), with pow()'s conventions x^0 = 1 and 0^a = 0 (a > 0), inf (a < 0).
+// Sharing L between |e|^alpha and |e|^(alpha-1) replaces two libdevice pow() calls (165 instructions each, measured
+// with ncu) by one log and two exp.  Relative error <= (|a L| + 1) ulp, i.e. ~4e-15 for |a L| <= 35.
+template <typename T>
+__device__ __forceinline__ T pow_from_log(T L, T a) {
+    return a == (T)0 ? (T)1 : Mth<T>::exp(a * L);
+}
 
 // ---------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter = (env index lo, env index hi,

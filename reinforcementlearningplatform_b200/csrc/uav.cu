@@ -22,11 +22,12 @@ typedef b200_uav_params P;
 
 template <typename T>
 struct Trig {
-    T sphi, cphi, sth, cth, spsi, cpsi, tth;
+    T sphi, cphi, sth, cth, spsi, cpsi, tth, rcth;
     __device__ __forceinline__ void eval(T phi, T th, T psi, bool need_psi) {
         Mth<T>::sincos(phi, &sphi, &cphi);
         Mth<T>::sincos(th, &sth, &cth);
-        tth = sth / cth;
+        rcth = (T)1 / cth;
+        tth = sth * rcth;
         if (need_psi) Mth<T>::sincos(psi, &spsi, &cpsi);
         else { spsi = (T)0; cpsi = (T)1; }
     }
@@ -34,10 +35,11 @@ struct Trig {
 
 template <typename T>
 struct Consts {
-    T m, g, kr, kt, J0, J1, J2, J21, J02, J10, dt;
+    T m, g, kr, kt, J0, J1, J2, J21, J02, J10, dt, rJ0, rJ1, rJ2, rm;
     __device__ __forceinline__ Consts(const P &p)
         : m((T)p.m), g((T)p.g), kr((T)p.kr), kt((T)p.kt), J0((T)p.J[0]), J1((T)p.J[1]), J2((T)p.J[2]),
-          J21((T)(p.J[2] - p.J[1])), J02((T)(p.J[0] - p.J[2])), J10((T)(p.J[1] - p.J[0])), dt((T)p.dt) {}
+          J21((T)(p.J[2] - p.J[1])), J02((T)(p.J[0] - p.J[2])), J10((T)(p.J[1] - p.J[0])), dt((T)p.dt),
+          rJ0((T)(1.0 / p.J[0])), rJ1((T)(1.0 / p.J[1])), rJ2((T)(1.0 / p.J[2])), rm((T)(1.0 / p.m)) {}
 };
 
 // uav.py:93-124.  x = (x y z vx vy vz phi th psi p q r); only the derivative entries that the caller needs.
@@ -45,17 +47,18 @@ template <typename T, bool ATT_ONLY>
 __device__ __forceinline__ void uav_ode(const Consts<T> &c, const T *x, const Trig<T> &t, T throttle, const T *tq,
                                         const T *dis, T *d) {
     const T p = x[9], q = x[10], r = x[11];
-    d[9] = (-c.kr * p - q * r * c.J21 + tq[0]) / c.J0;
-    d[10] = (-c.kr * q - p * r * c.J02 + tq[1]) / c.J1;
-    d[11] = (-c.kr * r - p * q * c.J10 + tq[2]) / c.J2;
+    // divisions by the constants J, m are multiplications by their reciprocals (<= 1 ulp from the reference's x / J)
+    d[9] = (-c.kr * p - q * r * c.J21 + tq[0]) * c.rJ0;
+    d[10] = (-c.kr * q - p * r * c.J02 + tq[1]) * c.rJ1;
+    d[11] = (-c.kr * r - p * q * c.J10 + tq[2]) * c.rJ2;
     d[6] = p + (t.tth * t.sphi) * q + (t.tth * t.cphi) * r;
     d[7] = t.cphi * q - t.sphi * r;
-    d[8] = (t.sphi / t.cth) * q + (t.cphi / t.cth) * r;
+    d[8] = (t.sphi * t.rcth) * q + (t.cphi * t.rcth) * r;
     if (!ATT_ONLY) {
         d[0] = x[3]; d[1] = x[4]; d[2] = x[5];
-        d[3] = (throttle * (t.cpsi * t.sth * t.cphi + t.spsi * t.sphi) - c.kt * x[3] + dis[0]) / c.m;
-        d[4] = (throttle * (t.spsi * t.sth * t.cphi - t.cpsi * t.sphi) - c.kt * x[4] + dis[1]) / c.m;
-        d[5] = -c.g + (throttle * t.cphi * t.cth - c.kt * x[5] + dis[2]) / c.m;
+        d[3] = (throttle * (t.cpsi * t.sth * t.cphi + t.spsi * t.sphi) - c.kt * x[3] + dis[0]) * c.rm;
+        d[4] = (throttle * (t.spsi * t.sth * t.cphi - t.cpsi * t.sphi) - c.kt * x[4] + dis[1]) * c.rm;
+        d[5] = -c.g + (throttle * t.cphi * t.cth - c.kt * x[5] + dis[2]) * c.rm;
     }
 }
 
@@ -82,7 +85,7 @@ __device__ __forceinline__ void uav_rk44(const Consts<T> &c, T *x, const Trig<T>
     t.eval(xs[6], xs[7], xs[8], !ATT_ONLY);
     uav_ode<T, ATT_ONLY>(c, xs, t, throttle, tq, dis, d);
 #pragma unroll
-    for (int i = LO; i < 12; ++i) { const T k = h * d[i]; x[i] = x[i] + (acc[i] + k) / (T)6; }
+    for (int i = LO; i < 12; ++i) { const T k = h * d[i]; x[i] = x[i] + (acc[i] + k) * (T)(1.0 / 6.0); }
     if (x[8] > (T)M_PI) x[8] -= (T)(2 * M_PI);
     if (x[8] < (T)-M_PI) x[8] += (T)(2 * M_PI);
 }
@@ -91,11 +94,11 @@ __device__ __forceinline__ void uav_rk44(const Consts<T> &c, T *x, const Trig<T>
 template <typename T>
 __device__ __forceinline__ void smc_axis(T e, T de, T k1, T gamma, T alpha, T beta, T lmd, T dt, T &integ,
                                          T &s_out, T &dot_s1, T &pa1_de) {
-    const T ae = Mth<T>::abs(e);
-    const T pa = Mth<T>::pow(ae, alpha);
-    const T pa1 = Mth<T>::pow(ae, alpha - (T)1);
+    const T L = Mth<T>::log(Mth<T>::abs(e)); // shared by |e|^alpha and |e|^(alpha-1)
+    const T pa = pow_from_log<T>(L, alpha);
+    const T pa1 = pow_from_log<T>(L, alpha - (T)1);
     const T s = de + k1 * e + gamma * pa * Mth<T>::tanh((T)5 * e);
-    dot_s1 = Mth<T>::pow(Mth<T>::abs(s), beta) * Mth<T>::tanh((T)5 * s);
+    dot_s1 = pow_from_log<T>(Mth<T>::log(Mth<T>::abs(s)), beta) * Mth<T>::tanh((T)5 * s);
     integ += dot_s1 * dt;
     s_out = s + lmd * integ;           // sigma (att) / so (pos)
     pa1_de = gamma * alpha * pa1 * de; // gamma * alpha * |e|^(alpha-1) * de
@@ -136,21 +139,21 @@ __device__ __forceinline__ void att_control(const Consts<T> &c, const T *x, cons
                                             const T *ref, const T *dref, T *torque, T *d1) {
     const T p = x[9], q = x[10], r = x[11];
     const T f01 = t.sphi * t.tth, f02 = t.cphi * t.tth, f11 = t.cphi, f12 = -t.sphi;
-    const T f21 = t.sphi / t.cth, f22 = t.cphi / t.cth;
+    const T f21 = t.sphi * t.rcth, f22 = t.cphi * t.rcth;
     d1[0] = p + f01 * q + f02 * r;
     d1[1] = f11 * q + f12 * r;
     d1[2] = f21 * q + f22 * r;
     // F() (uav.py:340-354) . rho2
-    const T c2 = t.cth * t.cth;
-    const T F01 = d1[0] * t.tth * t.cphi + d1[1] * t.sphi / c2;
-    const T F02 = -d1[0] * t.tth * t.sphi + d1[1] * t.cphi / c2;
+    const T rc2 = t.rcth * t.rcth;
+    const T F01 = d1[0] * t.tth * t.cphi + d1[1] * t.sphi * rc2;
+    const T F02 = -d1[0] * t.tth * t.sphi + d1[1] * t.cphi * rc2;
     const T F11 = -d1[0] * t.sphi, F12 = -d1[0] * t.cphi;
-    const T F21 = (d1[0] * t.cphi * t.cth + d1[1] * t.sphi * t.sth) / c2;
-    const T F22 = (-d1[0] * t.sphi * t.cth + d1[1] * t.cphi * t.sth) / c2;
+    const T F21 = (d1[0] * t.cphi * t.cth + d1[1] * t.sphi * t.sth) * rc2;
+    const T F22 = (-d1[0] * t.sphi * t.cth + d1[1] * t.cphi * t.sth) * rc2;
     // f2() (uav.py:302-313)
-    const T g0 = (c.kr * p + q * r * (c.J1 - c.J2)) / c.J0;
-    const T g1 = (c.kr * q + p * r * (c.J2 - c.J0)) / c.J1;
-    const T g2 = (c.kr * r + p * q * (c.J0 - c.J1)) / c.J2;
+    const T g0 = (c.kr * p + q * r * (c.J1 - c.J2)) * c.rJ0;
+    const T g1 = (c.kr * q + p * r * (c.J2 - c.J0)) * c.rJ1;
+    const T g2 = (c.kr * r + p * q * (c.J0 - c.J1)) * c.rJ2;
     T sec[3];
     sec[0] = (F01 * q + F02 * r) + (g0 + f01 * g1 + f02 * g2);
     sec[1] = (F11 * q + F12 * r) + (f11 * g1 + f12 * g2);
@@ -165,8 +168,17 @@ __device__ __forceinline__ void att_control(const Consts<T> &c, const T *x, cons
         const T u2 = -k2[i] * Mth<T>::tanh((T)10 * sigma);
         v[i] = u1 + u2;
     }
-    const T h0 = (T)1 / c.J0, h1 = (T)1 / c.J1, h2 = (T)1 / c.J2;
-    neg_inv_apply<T>(h0, f01 * h1, f02 * h2, f11 * h1, f12 * h2, f21 * h1, f22 * h2, v, torque);
+#ifdef B200_UAV_LAPACK_INV
+    neg_inv_apply<T>(c.rJ0, f01 * c.rJ1, f02 * c.rJ2, f11 * c.rJ1, f12 * c.rJ2, f21 * c.rJ1, f22 * c.rJ2, v, torque);
+#else
+    // B = f1 . diag(1/J)  =>  B^-1 = diag(J) . f1^-1 with the closed form
+    //   f1^-1 = [[1, 0, -sin th], [0, cos phi, sin phi cos th], [0, -sin phi, cos phi cos th]].
+    // The reference calls np.linalg.inv (LU, FNTSMC.py:137); the closed form differs from it only by LAPACK's own
+    // rounding (cond(f1) * eps) -- measured in tests/parity_report.py, incl. the near-singular fixtures.
+    torque[0] = -c.J0 * (v[0] - t.sth * v[2]);
+    torque[1] = -c.J1 * (t.cphi * v[1] + t.sphi * t.cth * v[2]);
+    torque[2] = -c.J2 * (t.cphi * t.cth * v[2] - t.sphi * v[1]);
+#endif
 }
 
 // uav.py:182-219: 2 position out, 3 attitude out, 1 time out -- evaluated in this order, the last true wins

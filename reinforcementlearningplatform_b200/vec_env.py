@@ -102,16 +102,16 @@ class VecEnvBase:
         return io
 
     def _as_soa(self, x, rows: int) -> torch.Tensor:
-        """Accept [N, rows] (reference orientation) or [rows, N] (engine SoA) tensors/arrays."""
+        """Accept [N, rows] (reference orientation, preferred when ambiguous) or [rows, N] (engine SoA)."""
         if not torch.is_tensor(x):
             x = torch.as_tensor(np.asarray(x), dtype=self.dtype)
         x = x.to(device=self.device, dtype=self.dtype)
         if x.dim() == 1:
             x = x.view(1, -1) if rows == 1 and x.numel() == self.n_envs else x.view(-1, 1).expand(rows, self.n_envs)
+        if x.shape == (self.n_envs, rows):  # reference orientation wins when n_envs == rows
+            return x.t().contiguous()
         if x.shape == (rows, self.n_envs):
             return x.contiguous()
-        if x.shape == (self.n_envs, rows):
-            return x.t().contiguous()
         raise ValueError(f"expected [{self.n_envs},{rows}] or [{rows},{self.n_envs}], got {tuple(x.shape)}")
 
     # ------------------------------------------------------------- rl_base API

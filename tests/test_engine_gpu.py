@@ -47,4 +47,5 @@ def test_engine_vs_oracle_random(name, oracle_lib):
     res = engine_vs_oracle(name, n=8192, steps=60, seed=7)
     assert res["flag_mismatch"] == 0, res
     assert res["worst"] <= res["tol"], res
-    assert res["terminals"] > 0 or name == "cartpole_gentle", res
+    if name.startswith("cartpole") and name != "cartpole_gentle":
+        assert res["terminals"] > 0, res  # episodes are short: the Philox auto-reset path is exercised
