@@ -205,6 +205,10 @@ B200_API int b200env_observe(int env_id, int dtype, int64_t n_envs,
  * which MEASURED_PEAKS.json does not carry.  Blocks until done.  Not on the hot path. */
 B200_API int b200_measure_fma_peak(int dtype, int iters, double *tflops, void *cuda_stream);
 
+/* Element-wise evaluation of the in-house fp64 math used by the kernels (csrc/fastmath64.cuh), for accuracy tests:
+ * func 0 sincos (out0 = sin, out1 = cos), 1 exp, 2 log, 3 tanh, 4 x^a with a read from out1.  Device pointers. */
+B200_API int b200_fastmath_eval(int func, int64_t n, const double *x, double *out0, double *out1, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

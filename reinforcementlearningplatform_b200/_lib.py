@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200env.so")
+# B200ENV_LIB selects an alternative build of the same library (A/B experiments with compile-time options)
+LIB_PATH = os.environ.get("B200ENV_LIB") or os.path.join(_HERE, "libb200env.so")
 
 # enum b200env_id
 CARTPOLE, FAS, SOI, BALLBALANCER, TWOLINK, UGV, UGVO, UAV_ATT, UAV_POS, UAVROBUST = range(10)
@@ -96,6 +97,8 @@ def load() -> C.CDLL:
     lib.b200env_reset.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), vp, u64, i64, vp]
     lib.b200env_observe.restype = i32
     lib.b200env_observe.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), vp]
+    lib.b200_fastmath_eval.restype = i32
+    lib.b200_fastmath_eval.argtypes = [i32, i64, vp, vp, vp, vp]
     lib.b200_measure_fma_peak.restype = i32
     lib.b200_measure_fma_peak.argtypes = [i32, i32, C.POINTER(C.c_double), vp]
     _lib = lib

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <math.h>
 #include "../../include/b200env.h"
+#include "fastmath64.cuh"
 
 #define B200_BLOCK 128
 
@@ -19,14 +20,21 @@
 template <typename T> struct Mth;
 
 template <> struct Mth<double> {
-    static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
-    static __device__ __forceinline__ double cos(double x) { return ::cos(x); }
+#ifdef B200_LIBDEVICE_MATH // A/B switch: libdevice everywhere
     static __device__ __forceinline__ void sincos(double x, double *s, double *c) { ::sincos(x, s, c); }
-    static __device__ __forceinline__ double tan(double x) { return ::tan(x); }
     static __device__ __forceinline__ double tanh(double x) { return ::tanh(x); }
-    static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+#else // fastmath64.cuh: constant-bank coefficients, no special-case ladders, ~1 ulp
+    static __device__ __forceinline__ void sincos(double x, double *s, double *c) { fm64::sincos(x, s, c); }
+    static __device__ __forceinline__ double tanh(double x) { return fm64::tanh(x); }
+    static __device__ __forceinline__ double log(double x) { return fm64::log(x); }
+    static __device__ __forceinline__ double exp(double x) { return fm64::exp(x); }
+#endif
+    static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
+    static __device__ __forceinline__ double cos(double x) { return ::cos(x); }
+    static __device__ __forceinline__ double tan(double x) { return ::tan(x); }
+    static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
     static __device__ __forceinline__ double acos(double x) { return ::acos(x); }

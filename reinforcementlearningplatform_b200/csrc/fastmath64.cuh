@@ -1,0 +1,119 @@
+// fastmath64.cuh -- lean double-precision sincos / exp / log / tanh for the environment kernels (sm_100a).
+//
+// Why: ncu on the UAV step kernel (profiles/) showed 71 % of all executed instructions inside libdevice's
+// sincos/tanh/log/exp/pow, and 27 % of ALL instructions being UMOV pairs that materialise fp64 polynomial
+// coefficients as immediates (DFMA has no fp64-immediate form on sm_100a).  These versions
+//   * keep the coefficients in __constant__ memory, which the compiler fetches with LDCU.128 (two doubles per
+//     instruction instead of two UMOVs per double),
+//   * drop the special-case ladders the env kernels never need (huge arguments, denormal results), keeping cheap
+//     guards so that 0, inf and NaN still behave as in IEEE libm,
+//   * stay within ~1-1.5 ulp (coefficients: tools/gen_fastmath_coeffs.py, near-minimax fits made with mpmath;
+//     accuracy is re-measured on the GPU by tests/test_fastmath_gpu.py).
+// Accuracy note: tanh() is accurate to ~2e-16 ABSOLUTE (not relative) for |x| -> 0, which is what the controllers
+// need (it always multiplies an O(1) gain).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace fm64 {
+
+// S: sin(r) = r + r z S(z);  C: cos(r) = 1 - z/2 + z^2 C(z);  z = r^2, |r| <= pi/4
+static __constant__ double kS[6] = {-0x1.5555555555555p-3, 0x1.1111111110b23p-7, -0x1.a01a019e623afp-13,
+                                    0x1.71de376b9c575p-19, -0x1.ae5fdeb852566p-26, 0x1.5dfb4dfaf15abp-33};
+static __constant__ double kC[6] = {0x1.5555555555555p-5, -0x1.6c16c16c1691fp-10, 0x1.a01a019f3df42p-16,
+                                    -0x1.27e4fa025e03dp-22, 0x1.1eeb52bea9072p-29, -0x1.906dd38cb66a1p-37};
+// E: exp(r) = 1 + r + r^2 E(r), |r| <= ln2/2
+static __constant__ double kE[10] = {0x1.0000000000001p-1, 0x1.5555555555556p-3, 0x1.5555555553b6cp-5,
+                                     0x1.1111111110918p-7, 0x1.6c16c1794e1dcp-10, 0x1.a01a01a83ba17p-13,
+                                     0x1.a019b621f9d08p-16, 0x1.71de0be2b5e96p-19, 0x1.2894f52583578p-22,
+                                     0x1.af3ce42b12b24p-26};
+// L: log(m) = 2s + s z L(z), s = (m-1)/(m+1), z = s^2, m in [sqrt(1/2), sqrt(2))
+static __constant__ double kL[7] = {0x1.5555555555558p-1, 0x1.99999999949c3p-2, 0x1.2492492ef134dp-2,
+                                    0x1.c71c61a265960p-3, 0x1.74630fb47b087p-3, 0x1.39f2ac8e848c3p-3,
+                                    0x1.2be78035f90e7p-3};
+// reduction constants: pi/2 in three pieces, 2/pi, ln2 in two pieces, log2(e), 1.5 * 2^52 (round-to-nearest magic)
+static __constant__ double kR[8] = {0x1.921fb54442d18p+0, 0x1.1a62633145c07p-54, -0x1.f1976b7ed8fbcp-110,
+                                    0x1.45f306dc9c883p-1, 0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56,
+                                    0x1.71547652b82fep+0, 6755399441055744.0};
+
+__device__ __forceinline__ void sincos(double x, double *sn, double *cs) {
+    if (!(fabs(x) < 1.0e5)) { // huge / inf / NaN: not on the env kernels' paths
+        ::sincos(x, sn, cs);
+        return;
+    }
+    const double t = fma(x, kR[3], kR[7]); // x * 2/pi rounded to the nearest integer in the low mantissa bits
+    const int n = __double2loint(t);
+    const double fn = t - kR[7];
+    double r = fma(-fn, kR[0], x);
+    r = fma(-fn, kR[1], r);
+    r = fma(-fn, kR[2], r);
+    const double z = r * r;
+    double ps = kS[5];
+    ps = fma(ps, z, kS[4]); ps = fma(ps, z, kS[3]); ps = fma(ps, z, kS[2]); ps = fma(ps, z, kS[1]); ps = fma(ps, z, kS[0]);
+    ps = fma(r * z, ps, r);
+    double pc = kC[5];
+    pc = fma(pc, z, kC[4]); pc = fma(pc, z, kC[3]); pc = fma(pc, z, kC[2]); pc = fma(pc, z, kC[1]); pc = fma(pc, z, kC[0]);
+    pc = fma(z, fma(z, pc, -0.5), 1.0);
+    double s = (n & 1) ? pc : ps;
+    double c = (n & 1) ? ps : pc;
+    if (n & 2) s = -s;
+    if ((n + 1) & 2) c = -c;
+    *sn = s;
+    *cs = c;
+}
+
+__device__ __forceinline__ double exp(double x) {
+    const double t = fma(x, kR[6], kR[7]);
+    const int n = __double2loint(t);
+    const double fn = t - kR[7];
+    double r = fma(-fn, kR[4], x);
+    r = fma(-fn, kR[5], r);
+    double p = kE[9];
+    p = fma(p, r, kE[8]); p = fma(p, r, kE[7]); p = fma(p, r, kE[6]); p = fma(p, r, kE[5]); p = fma(p, r, kE[4]);
+    p = fma(p, r, kE[3]); p = fma(p, r, kE[2]); p = fma(p, r, kE[1]); p = fma(p, r, kE[0]);
+    double y = fma(r * r, p, r) + 1.0;
+    y *= __hiloint2double((n + 1023) << 20, 0); // 2^n, valid for the clamped range below
+    if (x < -708.0) y = 0.0;                    // (denormal results flush to 0)
+    if (x > 709.0) y = CUDART_INF;
+    return y;                                   // NaN in -> NaN out (the comparisons are false, the polynomial is NaN)
+}
+
+__device__ __forceinline__ double log(double x) {
+    int hi = __double2hiint(x);
+    int k = 0;
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) { // zero, subnormal, negative, inf, NaN
+        if (x == 0.0) return -CUDART_INF;
+        if (!(x > 0.0)) return CUDART_NAN;
+        if (hi >= 0x7ff00000) return x;
+        x *= 18014398509481984.0; // 2^54
+        k = -54;
+        hi = __double2hiint(x);
+    }
+    const int lo = __double2loint(x);
+    k += (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int i = (hi + 0x95f64) & 0x100000; // m >= sqrt(2): halve it and bump the exponent
+    k += i >> 20;
+    const double m = __hiloint2double(hi | (i ^ 0x3ff00000), lo);
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    double R = kL[6];
+    R = fma(R, z, kL[5]); R = fma(R, z, kL[4]); R = fma(R, z, kL[3]); R = fma(R, z, kL[2]); R = fma(R, z, kL[1]);
+    R = fma(R, z, kL[0]);
+    R *= z;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    return dk * kR[4] - ((hfsq - (s * (hfsq + R) + dk * kR[5])) - f);
+}
+
+__device__ __forceinline__ double tanh(double x) {
+    const double ax = fabs(x);
+    const double t = fm64::exp(2.0 * ax); // inf for ax > 354.5 -> y = 1
+    const double y = 1.0 - 2.0 / (t + 1.0);
+    return copysign(y, x);
+}
+
+} // namespace fm64

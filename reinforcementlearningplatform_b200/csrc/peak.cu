@@ -54,3 +54,31 @@ extern "C" B200_API int b200_measure_fma_peak(int dtype, int iters, double *tflo
     return dtype == B200ENV_F64 ? measure<double>(tflops, iters, (cudaStream_t)cuda_stream)
                                 : measure<float>(tflops, iters, (cudaStream_t)cuda_stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// element-wise evaluation of the fastmath64.cuh functions (accuracy tests only)
+namespace {
+__global__ void fastmath_eval_kernel(int func, int64_t n, const double *x, double *o0, double *o1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double a = 0, b = 0;
+    switch (func) {
+    case 0: fm64::sincos(v, &a, &b); break;
+    case 1: a = fm64::exp(v); break;
+    case 2: a = fm64::log(v); break;
+    case 3: a = fm64::tanh(v); break;
+    case 4: a = pow_from_log<double>(fm64::log(v), o1[i]); b = o1[i]; break; // exponent passed in o1
+    default: break;
+    }
+    o0[i] = a;
+    if (o1) o1[i] = b;
+}
+} // namespace
+
+extern "C" B200_API int b200_fastmath_eval(int func, int64_t n, const double *x, double *out0, double *out1,
+                                           void *cuda_stream) {
+    if (!x || !out0 || n <= 0) return B200ENV_ENULL;
+    fastmath_eval_kernel<<<b200_grid(n, 256), 256, 0, (cudaStream_t)cuda_stream>>>(func, n, x, out0, out1);
+    return b200_check_launch();
+}

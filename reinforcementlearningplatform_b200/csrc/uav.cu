@@ -16,6 +16,12 @@
 // HBM traffic is one coalesced read and one coalesced write of each SoA field.
 #include "common.cuh"
 
+#ifndef UAV_POS_MINBLOCKS
+#define UAV_POS_MINBLOCKS 4
+#endif
+#ifndef UAV_ATT_MINBLOCKS
+#define UAV_ATT_MINBLOCKS 4
+#endif
 namespace {
 
 typedef b200_uav_params P;
@@ -260,7 +266,7 @@ __device__ __forceinline__ void att_observe(const T *x, const Trig<T> &t, const 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(B200_BLOCK)
+__global__ void __launch_bounds__(B200_BLOCK, UAV_ATT_MINBLOCKS)
 uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
                     uint64_t seed, int64_t off) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -432,7 +438,7 @@ __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io
 }
 
 template <typename T>
-__global__ void __launch_bounds__(B200_BLOCK)
+__global__ void __launch_bounds__(B200_BLOCK, UAV_POS_MINBLOCKS)
 uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
                     uint64_t seed, int64_t off) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
