@@ -22,11 +22,27 @@ template <typename T> struct Mth;
 template <> struct Mth<double> {
 #ifdef B200_LIBDEVICE_MATH // A/B switch: libdevice everywhere
     static __device__ __forceinline__ void sincos(double x, double *s, double *c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ void sincos3(double a, double b, double c, double *sa, double *ca, double *sb,
+                                                   double *cb, double *sc, double *cc) {
+        ::sincos(a, sa, ca); ::sincos(b, sb, cb); ::sincos(c, sc, cc);
+    }
+    static __device__ __forceinline__ void sincos2(double a, double b, double *sa, double *ca, double *sb, double *cb) {
+        ::sincos(a, sa, ca); ::sincos(b, sb, cb);
+    }
+    static __device__ __forceinline__ double rcp(double y) { return 1.0 / y; }
     static __device__ __forceinline__ double tanh(double x) { return ::tanh(x); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
 #else // fastmath64.cuh: constant-bank coefficients, no special-case ladders, ~1 ulp
     static __device__ __forceinline__ void sincos(double x, double *s, double *c) { fm64::sincos(x, s, c); }
+    static __device__ __forceinline__ void sincos3(double a, double b, double c, double *sa, double *ca, double *sb,
+                                                   double *cb, double *sc, double *cc) {
+        fm64::sincos3(a, b, c, sa, ca, sb, cb, sc, cc);
+    }
+    static __device__ __forceinline__ void sincos2(double a, double b, double *sa, double *ca, double *sb, double *cb) {
+        fm64::sincos2(a, b, sa, ca, sb, cb);
+    }
+    static __device__ __forceinline__ double rcp(double y) { return fm64::rcp(y); }
     static __device__ __forceinline__ double tanh(double x) { return fm64::tanh(x); }
     static __device__ __forceinline__ double log(double x) { return fm64::log(x); }
     static __device__ __forceinline__ double exp(double x) { return fm64::exp(x); }
@@ -48,6 +64,14 @@ template <> struct Mth<float> {
     static __device__ __forceinline__ float sin(float x) { return ::sinf(x); }
     static __device__ __forceinline__ float cos(float x) { return ::cosf(x); }
     static __device__ __forceinline__ void sincos(float x, float *s, float *c) { ::sincosf(x, s, c); }
+    static __device__ __forceinline__ void sincos3(float a, float b, float c, float *sa, float *ca, float *sb, float *cb,
+                                                   float *sc, float *cc) {
+        ::sincosf(a, sa, ca); ::sincosf(b, sb, cb); ::sincosf(c, sc, cc);
+    }
+    static __device__ __forceinline__ void sincos2(float a, float b, float *sa, float *ca, float *sb, float *cb) {
+        ::sincosf(a, sa, ca); ::sincosf(b, sb, cb);
+    }
+    static __device__ __forceinline__ float rcp(float y) { return 1.0f / y; }
     static __device__ __forceinline__ float tan(float x) { return ::tanf(x); }
     static __device__ __forceinline__ float tanh(float x) { return ::tanhf(x); }
     static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }

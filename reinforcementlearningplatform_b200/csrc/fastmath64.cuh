@@ -38,11 +38,28 @@ static __constant__ double kR[8] = {0x1.921fb54442d18p+0, 0x1.1a62633145c07p-54,
                                     0x1.45f306dc9c883p-1, 0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56,
                                     0x1.71547652b82fep+0, 6755399441055744.0};
 
-__device__ __forceinline__ void sincos(double x, double *sn, double *cs) {
-    if (!(fabs(x) < 1.0e5)) { // huge / inf / NaN: not on the env kernels' paths
-        ::sincos(x, sn, cs);
-        return;
-    }
+// 1/y and x/y without the slow-path branches of the compiler's IEEE division: MUFU.RCP64H seed (>= 20 bits), two
+// Newton steps, one correction step for the quotient.  Valid for normal, finite y (every call site guarantees it);
+// <= 1 ulp.  Branch-free code keeps consecutive function evaluations in ONE basic block, so the scheduler can
+// interleave their dependent DFMA chains (the kernels are latency-bound: ncu "stall_wait").
+__device__ __forceinline__ double rcp(double y) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    double e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double div(double x, double y) {
+    const double r = rcp(y);
+    const double q = x * r;
+    return fma(fma(-y, q, x), r, q);
+}
+
+// sin and cos of x for |x| < 1e5 (three-term Cody-Waite reduction by pi/2, two degree-5 kernels in z = r^2).
+// No argument check: callers go through sincos() / sincos3() below.
+__device__ __forceinline__ void sincos_core(double x, double *sn, double *cs) {
     const double t = fma(x, kR[3], kR[7]); // x * 2/pi rounded to the nearest integer in the low mantissa bits
     const int n = __double2loint(t);
     const double fn = t - kR[7];
@@ -64,41 +81,69 @@ __device__ __forceinline__ void sincos(double x, double *sn, double *cs) {
     *cs = c;
 }
 
+__device__ __forceinline__ void sincos(double x, double *sn, double *cs) {
+    if (!(fabs(x) < 1.0e5)) { // huge / inf / NaN: not on the env kernels' paths
+        ::sincos(x, sn, cs);
+        return;
+    }
+    sincos_core(x, sn, cs);
+}
+
+// three angles behind ONE range check, so that the six polynomial chains share a basic block
+__device__ __forceinline__ void sincos3(double a, double b, double c, double *sa, double *ca, double *sb, double *cb,
+                                        double *sc, double *cc) {
+    if (!(fmax(fmax(fabs(a), fabs(b)), fabs(c)) < 1.0e5) || a != a || b != b || c != c) {
+        ::sincos(a, sa, ca);
+        ::sincos(b, sb, cb);
+        ::sincos(c, sc, cc);
+        return;
+    }
+    sincos_core(a, sa, ca);
+    sincos_core(b, sb, cb);
+    sincos_core(c, sc, cc);
+}
+__device__ __forceinline__ void sincos2(double a, double b, double *sa, double *ca, double *sb, double *cb) {
+    if (!(fmax(fabs(a), fabs(b)) < 1.0e5) || a != a || b != b) {
+        ::sincos(a, sa, ca);
+        ::sincos(b, sb, cb);
+        return;
+    }
+    sincos_core(a, sa, ca);
+    sincos_core(b, sb, cb);
+}
+
 __device__ __forceinline__ double exp(double x) {
     const double t = fma(x, kR[6], kR[7]);
     const int n = __double2loint(t);
     const double fn = t - kR[7];
     double r = fma(-fn, kR[4], x);
     r = fma(-fn, kR[5], r);
-    double p = kE[9];
-    p = fma(p, r, kE[8]); p = fma(p, r, kE[7]); p = fma(p, r, kE[6]); p = fma(p, r, kE[5]); p = fma(p, r, kE[4]);
-    p = fma(p, r, kE[3]); p = fma(p, r, kE[2]); p = fma(p, r, kE[1]); p = fma(p, r, kE[0]);
-    double y = fma(r * r, p, r) + 1.0;
+    // even/odd split Horner: two chains of depth 5 instead of one of depth 9
+    const double r2 = r * r;
+    double pe = kE[8], po = kE[9];
+    pe = fma(pe, r2, kE[6]); po = fma(po, r2, kE[7]);
+    pe = fma(pe, r2, kE[4]); po = fma(po, r2, kE[5]);
+    pe = fma(pe, r2, kE[2]); po = fma(po, r2, kE[3]);
+    pe = fma(pe, r2, kE[0]); po = fma(po, r2, kE[1]);
+    const double p = fma(po, r, pe);
+    double y = fma(r2, p, r) + 1.0;
     y *= __hiloint2double((n + 1023) << 20, 0); // 2^n, valid for the clamped range below
     if (x < -708.0) y = 0.0;                    // (denormal results flush to 0)
     if (x > 709.0) y = CUDART_INF;
     return y;                                   // NaN in -> NaN out (the comparisons are false, the polynomial is NaN)
 }
 
+// natural log, branch-free.  x = 0 (and subnormal x, treated as 0) -> -inf, x < 0 or NaN -> NaN, +inf -> +inf.
 __device__ __forceinline__ double log(double x) {
     int hi = __double2hiint(x);
-    int k = 0;
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) { // zero, subnormal, negative, inf, NaN
-        if (x == 0.0) return -CUDART_INF;
-        if (!(x > 0.0)) return CUDART_NAN;
-        if (hi >= 0x7ff00000) return x;
-        x *= 18014398509481984.0; // 2^54
-        k = -54;
-        hi = __double2hiint(x);
-    }
     const int lo = __double2loint(x);
-    k += (hi >> 20) - 1023;
+    int k = (hi >> 20) - 1023;
     hi &= 0x000fffff;
     const int i = (hi + 0x95f64) & 0x100000; // m >= sqrt(2): halve it and bump the exponent
     k += i >> 20;
     const double m = __hiloint2double(hi | (i ^ 0x3ff00000), lo);
     const double f = m - 1.0;
-    const double s = f / (2.0 + f);
+    const double s = div(f, 2.0 + f);
     const double z = s * s;
     double R = kL[6];
     R = fma(R, z, kL[5]); R = fma(R, z, kL[4]); R = fma(R, z, kL[3]); R = fma(R, z, kL[2]); R = fma(R, z, kL[1]);
@@ -106,14 +151,20 @@ __device__ __forceinline__ double log(double x) {
     R *= z;
     const double hfsq = 0.5 * f * f;
     const double dk = (double)k;
-    return dk * kR[4] - ((hfsq - (s * (hfsq + R) + dk * kR[5])) - f);
+    double y = dk * kR[4] - ((hfsq - (s * (hfsq + R) + dk * kR[5])) - f);
+    if (x < 2.2250738585072014e-308) y = -CUDART_INF; // zero / subnormal
+    if (!(x >= 0.0)) y = CUDART_NAN;                   // negative / NaN
+    if (x == CUDART_INF) y = x;
+    return y;
 }
 
+// tanh, branch-free; ~2e-16 absolute accuracy
 __device__ __forceinline__ double tanh(double x) {
-    const double ax = fabs(x);
-    const double t = fm64::exp(2.0 * ax); // inf for ax > 354.5 -> y = 1
-    const double y = 1.0 - 2.0 / (t + 1.0);
-    return copysign(y, x);
+    const double ax = fmin(fabs(x), 20.0); // tanh(20) rounds to 1
+    const double t = fm64::exp(2.0 * ax);
+    double y = fma(-2.0, rcp(t + 1.0), 1.0);
+    y = copysign(y, x);
+    return x != x ? x : y;
 }
 
 } // namespace fm64

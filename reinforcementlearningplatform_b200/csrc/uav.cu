@@ -29,13 +29,16 @@ typedef b200_uav_params P;
 template <typename T>
 struct Trig {
     T sphi, cphi, sth, cth, spsi, cpsi, tth, rcth;
+    // one range check for all angles (fastmath64.cuh): the polynomial chains of the 2-3 sincos share a basic block
     __device__ __forceinline__ void eval(T phi, T th, T psi, bool need_psi) {
-        Mth<T>::sincos(phi, &sphi, &cphi);
-        Mth<T>::sincos(th, &sth, &cth);
-        rcth = (T)1 / cth;
+        if (need_psi) {
+            Mth<T>::sincos3(phi, th, psi, &sphi, &cphi, &sth, &cth, &spsi, &cpsi);
+        } else {
+            Mth<T>::sincos2(phi, th, &sphi, &cphi, &sth, &cth);
+            spsi = (T)0; cpsi = (T)1;
+        }
+        rcth = Mth<T>::rcp(cth);
         tth = sth * rcth;
-        if (need_psi) Mth<T>::sincos(psi, &spsi, &cpsi);
-        else { spsi = (T)0; cpsi = (T)1; }
     }
 };
 
@@ -68,30 +71,34 @@ __device__ __forceinline__ void uav_ode(const Consts<T> &c, const T *x, const Tr
     }
 }
 
-// uav.py:126-148 with n = 1: x <- x + (K1 + 2 K2 + 2 K3 + K4) / 6, time += dt, psi wrapped to (-pi, pi].
-// `t1` holds sin/cos of the current attitude (already computed for the controllers).
+// uav.py:126-148 with n = 1: x <- x + (K1 + 2 K2 + 2 K3 + K4) / 6, psi wrapped to (-pi, pi] (time is advanced by
+// the caller).  `t` enters with sin/cos of the current attitude (already computed for the controllers).  The four
+// stages run as a rolled loop (one copy of the ODE + trig code instead of four: the fully unrolled kernel was
+// 128 KB of SASS and stalled on instruction fetch); weights (1,2,2,1) and stage offsets (1/2,1/2,1) are selected by
+// the stage index, and acc starts at 0 so acc + 1*K1 == K1 exactly -- the summation order of the reference is kept.
 template <typename T, bool ATT_ONLY>
-__device__ __forceinline__ void uav_rk44(const Consts<T> &c, T *x, const Trig<T> &t1, T throttle, const T *tq,
-                                         const T *dis) {
+__device__ __forceinline__ void uav_rk44(const Consts<T> &c, T *x, Trig<T> t, T throttle, const T *tq, const T *dis) {
     constexpr int LO = ATT_ONLY ? 6 : 0;
-    const T h = c.dt, half = (T)0.5;
-    T acc[12], xs[12], d[12];
-    Trig<T> t;
-    uav_ode<T, ATT_ONLY>(c, x, t1, throttle, tq, dis, d);
+    const T h = c.dt;
+    T acc[12], xs[12];
 #pragma unroll
-    for (int i = LO; i < 12; ++i) { const T k = h * d[i]; acc[i] = k; xs[i] = x[i] + k * half; }
-    t.eval(xs[6], xs[7], xs[8], !ATT_ONLY);
-    uav_ode<T, ATT_ONLY>(c, xs, t, throttle, tq, dis, d);
+    for (int i = LO; i < 12; ++i) { acc[i] = (T)0; xs[i] = x[i]; }
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+        T d[12];
+        uav_ode<T, ATT_ONLY>(c, xs, t, throttle, tq, dis, d);
+        const T w = (s == 0 || s == 3) ? (T)1 : (T)2;
+        const T cs = (s == 2) ? (T)1 : (T)0.5;
 #pragma unroll
-    for (int i = LO; i < 12; ++i) { const T k = h * d[i]; acc[i] = acc[i] + (T)2 * k; xs[i] = x[i] + k * half; }
-    t.eval(xs[6], xs[7], xs[8], !ATT_ONLY);
-    uav_ode<T, ATT_ONLY>(c, xs, t, throttle, tq, dis, d);
+        for (int i = LO; i < 12; ++i) {
+            const T k = h * d[i];
+            acc[i] = acc[i] + w * k;
+            xs[i] = x[i] + k * cs;
+        }
+        if (s < 3) t.eval(xs[6], xs[7], xs[8], !ATT_ONLY);
+    }
 #pragma unroll
-    for (int i = LO; i < 12; ++i) { const T k = h * d[i]; acc[i] = acc[i] + (T)2 * k; xs[i] = x[i] + k; }
-    t.eval(xs[6], xs[7], xs[8], !ATT_ONLY);
-    uav_ode<T, ATT_ONLY>(c, xs, t, throttle, tq, dis, d);
-#pragma unroll
-    for (int i = LO; i < 12; ++i) { const T k = h * d[i]; x[i] = x[i] + (acc[i] + k) * (T)(1.0 / 6.0); }
+    for (int i = LO; i < 12; ++i) x[i] = x[i] + acc[i] * (T)(1.0 / 6.0);
     if (x[8] > (T)M_PI) x[8] -= (T)(2 * M_PI);
     if (x[8] < (T)-M_PI) x[8] += (T)(2 * M_PI);
 }
@@ -455,39 +462,45 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
 #pragma unroll
         for (int k = 0; k < 3; ++k) dis[k] = ld<T>(io.dis, n, k, i);
     }
-    // get_param_from_actor, uav_pos_ctrl_RL.py:158-173 (N6)
-    T sig[3], s1[3], aref[3], k1[3], k2[3], gam[3], lmd[3];
+    // Every persistent field is written back as soon as its new value is known (short register live ranges; a later
+    // auto-reset simply overwrites what it redefines).
+    // ---- get_param_from_actor, uav_pos_ctrl_RL.py:158-173: a gain changes only where the actor output is > 0 (N6)
+    T k1[3], k2[3], gam[3], lmd[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        sig[k] = ld<T>(io.state, n, P_SIG + k, i);
-        s1[k] = ld<T>(io.state, n, P_S1 + k, i);
-        aref[k] = ld<T>(io.state, n, P_AREF + k, i);
         k1[k] = a[k] > (T)0 ? a[k] : ld<T>(io.state, n, P_K1 + k, i);
         k2[k] = a[k + 3] > (T)0 ? a[k + 3] : ld<T>(io.state, n, P_K2 + k, i);
         gam[k] = a[6] > (T)0 ? a[6] : ld<T>(io.state, n, P_GAM + k, i);
         lmd[k] = a[7] > (T)0 ? a[7] : ld<T>(io.state, n, P_LMD + k, i);
+        st<T>(io.state, n, P_K1 + k, i, k1[k]);
+        st<T>(io.state, n, P_K2 + k, i, k2[k]);
+        st<T>(io.state, n, P_GAM + k, i, gam[k]);
+        st<T>(io.state, n, P_LMD + k, i, lmd[k]);
     }
-    // ref_uav(time, A, T, bias, phase), ref_cmd.py:25-43
+    // ---- ref_uav(time, A, T, bias, phase), ref_cmd.py:25-43
     T ref[4], dref[4], ddref[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         ref_channel<T>((T)time, ld<T>(io.state, n, P_AMP + k, i), ld<T>(io.state, n, P_PER + k, i), (T)p.ref_bias_a[k],
                        ld<T>(io.state, n, P_PHS + k, i), ref[k], dref[k], ddref[k]);
-    // pos_control, uav_pos_ctrl.py:302-315 + FNTSMC.py:47-69 (obs = 0)
+    // ---- pos_control, uav_pos_ctrl.py:302-315 + FNTSMC.py:47-69 (obs = 0)
     T ctrl[3];
     const T kt_m = c.kt / c.m;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const T e = x[k] - ref[k], de = x[3 + k] - dref[k];
+        T sig = ld<T>(io.state, n, P_SIG + k, i);
         T so, dso1, pa1_de;
-        smc_axis<T>(e, de, k1[k], gam[k], (T)p.pos_alpha[k], (T)p.pos_beta[k], lmd[k], c.dt, sig[k], so, dso1, pa1_de);
+        smc_axis<T>(e, de, k1[k], gam[k], (T)p.pos_alpha[k], (T)p.pos_beta[k], lmd[k], c.dt, sig, so, dso1, pa1_de);
+        st<T>(io.state, n, P_SIG + k, i, sig);
         const T uo1 = kt_m * x[3 + k] + ddref[k] - k1[k] * de - pa1_de - lmd[k] * dso1;
         const T uo2 = -k2[k] * so;
         ctrl[k] = uo1 + uo2;
     }
+    const T u_acc = -(ctrl[0] * ctrl[0] * (T)p.R[0] + ctrl[1] * ctrl[1] * (T)p.R[1] + ctrl[2] * ctrl[2] * (T)p.R[2]);
     Trig<T> t1;
     t1.eval(x[6], x[7], x[8], true);
-    // uo_2_ref_angle_throttle(limit = pi/4), uav_pos_ctrl.py:339-357
+    // ---- uo_2_ref_angle_throttle(limit = pi/4), uav_pos_ctrl.py:339-357
     const T uf = (ctrl[2] + c.g) * c.m / (t1.cphi * t1.cth);
     const T asin_phi_d = Mth<T>::min(Mth<T>::max((ctrl[0] * t1.spsi - ctrl[1] * t1.cpsi) * c.m / uf, (T)-1), (T)1);
     T phi_d = Mth<T>::asin(asin_phi_d);
@@ -497,23 +510,28 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     const T lim = (T)p.att_limit;
     phi_d = Mth<T>::max(Mth<T>::min(phi_d, lim), -lim);
     theta_d = Mth<T>::max(Mth<T>::min(theta_d, lim), -lim);
-    // generate_action_4_uav, uav_pos_ctrl.py:470-481: finite-difference reference rates, clipped, then integrated back
+    // ---- generate_action_4_uav, uav_pos_ctrl.py:470-481: finite-difference reference rates, clipped, integrated back
     T rho_d[3] = {phi_d, theta_d, ref[3]};
-    T drho_d[3] = {(phi_d - aref[0]) / c.dt, (theta_d - aref[1]) / c.dt, dref[3]};
+    T drho_d[3] = {(phi_d - ld<T>(io.state, n, P_AREF + 0, i)) / c.dt, (theta_d - ld<T>(io.state, n, P_AREF + 1, i)) / c.dt,
+                   dref[3]};
     const T rl = (T)p.dot_att_ref_limit;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         drho_d[k] = Mth<T>::min(Mth<T>::max(drho_d[k], -rl), rl);
         rho_d[k] = rho_d[k] + drho_d[k] * c.dt;
-        aref[k] = rho_d[k];
+        st<T>(io.state, n, P_AREF + k, i, rho_d[k]); // att_ref = rho_d (persists across resets, uav_pos_ctrl.py:329)
     }
-    T torque[3], d1[3], ak1[3], ak2[3], agam[3], almd[3], aalpha[3], abeta[3];
+    // ---- att_control, uav_pos_ctrl.py:317-337
+    T torque[3], d1[3], s1[3], ak1[3], ak2[3], agam[3], almd[3], aalpha[3], abeta[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
+        s1[k] = ld<T>(io.state, n, P_S1 + k, i);
         ak1[k] = (T)p.att_k1[k]; ak2[k] = (T)p.att_k2[k]; agam[k] = (T)p.att_gamma[k]; almd[k] = (T)p.att_lmd[k];
         aalpha[k] = (T)p.att_alpha[k]; abeta[k] = (T)p.att_beta[k];
     }
     att_control<T>(c, x, t1, ak1, ak2, agam, almd, aalpha, abeta, s1, rho_d, drho_d, torque, d1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) st<T>(io.state, n, P_S1 + k, i, s1[k]);
     if (io.obs) { // current_state = get_state(), uav_pos_ctrl_RL.py:59-68
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -521,6 +539,7 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
             st<T>(io.obs, n, 3 + k, i, x[3 + k] - dref[k]);
         }
     }
+    // ---- update(): rk44(action, dis, n = 1), uav_pos_ctrl.py:359-376
     uav_rk44<T, false>(c, x, t1, uf, torque, dis);
     time += p.dt;
     const int flag = terminal_flag<T>(p, x, time);
@@ -528,10 +547,9 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     T nxt[6];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { nxt[k] = x[k] - ref[k]; nxt[3 + k] = x[3 + k] - dref[k]; }
-    // get_reward, uav_pos_ctrl_RL.py:82-120
+    // ---- get_reward, uav_pos_ctrl_RL.py:82-120
     const T u_pos = -(nxt[0] * nxt[0] * (T)p.Q_e[0] + nxt[1] * nxt[1] * (T)p.Q_e[1] + nxt[2] * nxt[2] * (T)p.Q_e[2]);
     const T u_vel = -(nxt[3] * nxt[3] * (T)p.Q_de[0] + nxt[4] * nxt[4] * (T)p.Q_de[1] + nxt[5] * nxt[5] * (T)p.Q_de[2]);
-    const T u_acc = -(ctrl[0] * ctrl[0] * (T)p.R[0] + ctrl[1] * ctrl[1] * (T)p.R[1] + ctrl[2] * ctrl[2] * (T)p.R[2]);
     T u_extra = (T)0;
     if (flag == 2 || flag == 3) {
         const T nn = (T)((p.time_max - time) / p.dt);
@@ -543,8 +561,6 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     st<T>(io.reward, n, 0, i, reward);
     io.done[i] = done ? 1 : 0;
     io.flag[i] = flag;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) st<T>(io.state, n, P_AREF + k, i, aref[k]);
     if (done && (flags & B200ENV_AUTO_RESET)) {
         T xr[12];
         pos_reset_state<T>(p, io, n, i, seed, off, xr);
@@ -553,17 +569,8 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     } else {
 #pragma unroll
         for (int k = 0; k < 12; ++k) st<T>(io.state, n, k, i, x[k]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            st<T>(io.state, n, P_SIG + k, i, sig[k]);
-            st<T>(io.state, n, P_S1 + k, i, s1[k]);
-            st<T>(io.state, n, P_K1 + k, i, k1[k]);
-            st<T>(io.state, n, P_K2 + k, i, k2[k]);
-            st<T>(io.state, n, P_GAM + k, i, gam[k]);
-            st<T>(io.state, n, P_LMD + k, i, lmd[k]);
-        }
         io.time[i] = time;
-        if (done) {
+        if (done) { // keep the last reference for a later explicit reset()/observe()
 #pragma unroll
             for (int k = 0; k < 3; ++k) { st<T>(io.state, n, P_PREF + k, i, ref[k]); st<T>(io.state, n, P_DPREF + k, i, dref[k]); }
         }
