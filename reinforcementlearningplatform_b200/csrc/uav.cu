@@ -284,13 +284,18 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = ld<T>(io.state, n, k, i); }
     double time = io.time[i];
     T s1[3], k1[3], k2[3], gam[3], lmd[3], alpha[3], beta[3], ref[3], dref[3];
-    T a[8];
+    T a[8], rA[3], rT[3], rP[3];
 #pragma unroll
     for (int k = 0; k < 8; ++k) a[k] = ld<T>(io.action, n, k, i);
-    // get_param_from_actor, uav_att_ctrl_RL.py:141-156: a gain is overwritten only where the actor output is > 0 (N6)
+    // all loads before the first store (see uav_pos_step_kernel)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         s1[k] = ld<T>(io.state, n, A_S1 + k, i);
+        rA[k] = ld<T>(io.state, n, A_AMP + k, i); rT[k] = ld<T>(io.state, n, A_PER + k, i); rP[k] = ld<T>(io.state, n, A_PHS + k, i);
+    }
+    // get_param_from_actor, uav_att_ctrl_RL.py:141-156: a gain is overwritten only where the actor output is > 0 (N6)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
         k1[k] = a[k] > (T)0 ? (T)10 * a[k] : ld<T>(io.state, n, A_K1 + k, i);
         k2[k] = a[k + 3] > (T)0 ? a[k + 3] / (T)10 : ld<T>(io.state, n, A_K2 + k, i);
         gam[k] = a[6] > (T)0 ? a[6] : ld<T>(io.state, n, A_GAM + k, i);
@@ -298,17 +303,26 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
         alpha[k] = (T)p.att_alpha[k];
         beta[k] = (T)p.att_beta[k];
     }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { // early write-back
+        st<T>(io.state, n, A_K1 + k, i, k1[k]);
+        st<T>(io.state, n, A_K2 + k, i, k2[k]);
+        st<T>(io.state, n, A_GAM + k, i, gam[k]);
+        st<T>(io.state, n, A_LMD + k, i, lmd[k]);
+    }
     // ref_inner(time, A, T, 0, phase), ref_cmd.py:4-22
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         T dd;
-        ref_channel<T>((T)time, ld<T>(io.state, n, A_AMP + k, i), ld<T>(io.state, n, A_PER + k, i), (T)0,
-                       ld<T>(io.state, n, A_PHS + k, i), ref[k], dref[k], dd);
+        ref_channel<T>((T)time, rA[k], rT[k], (T)0, rP[k], ref[k], dref[k], dd);
     }
     Trig<T> t1;
     t1.eval(x[6], x[7], x[8], false);
     T torque[3], d1[3];
     att_control<T>(c, x, t1, k1, k2, gam, lmd, alpha, beta, s1, ref, dref, torque, d1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) st<T>(io.state, n, A_S1 + k, i, s1[k]);
+    const T u_acc = -(torque[0] * torque[0] * (T)p.R[0] + torque[1] * torque[1] * (T)p.R[1] + torque[2] * torque[2] * (T)p.R[2]);
     if (io.obs) { // current_state = get_state()
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -329,7 +343,6 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     // get_reward, uav_att_ctrl_RL.py:70-106
     const T u_att = -(nxt[0] * nxt[0] * (T)p.Q_e[0] + nxt[1] * nxt[1] * (T)p.Q_e[1] + nxt[2] * nxt[2] * (T)p.Q_e[2]);
     const T u_pqr = -(nxt[3] * nxt[3] * (T)p.Q_de[0] + nxt[4] * nxt[4] * (T)p.Q_de[1] + nxt[5] * nxt[5] * (T)p.Q_de[2]);
-    const T u_acc = -(torque[0] * torque[0] * (T)p.R[0] + torque[1] * torque[1] * (T)p.R[1] + torque[2] * torque[2] * (T)p.R[2]);
     T u_extra = (T)0;
     if (flag == 3) {
         const T nn = (T)((p.time_max - time) / p.dt);
@@ -355,14 +368,6 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     } else {
 #pragma unroll
         for (int k = 0; k < 6; ++k) st<T>(io.state, n, k, i, x[6 + k]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            st<T>(io.state, n, A_S1 + k, i, s1[k]);
-            st<T>(io.state, n, A_K1 + k, i, k1[k]);
-            st<T>(io.state, n, A_K2 + k, i, k2[k]);
-            st<T>(io.state, n, A_GAM + k, i, gam[k]);
-            st<T>(io.state, n, A_LMD + k, i, lmd[k]);
-        }
         io.time[i] = time;
         if (done) { // keep the last reference for a later explicit reset()/observe()
 #pragma unroll
@@ -462,6 +467,17 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
 #pragma unroll
         for (int k = 0; k < 3; ++k) dis[k] = ld<T>(io.dis, n, k, i);
     }
+    // All loads are issued here, before the first store: the compiler cannot move a load above a store to the same
+    // buffer (possible aliasing), and a mid-kernel DRAM load is not hidden by the 4 resident warps per scheduler.
+    T sig[3], s1[3], aref0, aref1, rA[4], rT[4], rP[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { sig[k] = ld<T>(io.state, n, P_SIG + k, i); s1[k] = ld<T>(io.state, n, P_S1 + k, i); }
+    aref0 = ld<T>(io.state, n, P_AREF + 0, i);
+    aref1 = ld<T>(io.state, n, P_AREF + 1, i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        rA[k] = ld<T>(io.state, n, P_AMP + k, i); rT[k] = ld<T>(io.state, n, P_PER + k, i); rP[k] = ld<T>(io.state, n, P_PHS + k, i);
+    }
     // Every persistent field is written back as soon as its new value is known (short register live ranges; a later
     // auto-reset simply overwrites what it redefines).
     // ---- get_param_from_actor, uav_pos_ctrl_RL.py:158-173: a gain changes only where the actor output is > 0 (N6)
@@ -481,18 +497,16 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     T ref[4], dref[4], ddref[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        ref_channel<T>((T)time, ld<T>(io.state, n, P_AMP + k, i), ld<T>(io.state, n, P_PER + k, i), (T)p.ref_bias_a[k],
-                       ld<T>(io.state, n, P_PHS + k, i), ref[k], dref[k], ddref[k]);
+        ref_channel<T>((T)time, rA[k], rT[k], (T)p.ref_bias_a[k], rP[k], ref[k], dref[k], ddref[k]);
     // ---- pos_control, uav_pos_ctrl.py:302-315 + FNTSMC.py:47-69 (obs = 0)
     T ctrl[3];
     const T kt_m = c.kt / c.m;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const T e = x[k] - ref[k], de = x[3 + k] - dref[k];
-        T sig = ld<T>(io.state, n, P_SIG + k, i);
         T so, dso1, pa1_de;
-        smc_axis<T>(e, de, k1[k], gam[k], (T)p.pos_alpha[k], (T)p.pos_beta[k], lmd[k], c.dt, sig, so, dso1, pa1_de);
-        st<T>(io.state, n, P_SIG + k, i, sig);
+        smc_axis<T>(e, de, k1[k], gam[k], (T)p.pos_alpha[k], (T)p.pos_beta[k], lmd[k], c.dt, sig[k], so, dso1, pa1_de);
+        st<T>(io.state, n, P_SIG + k, i, sig[k]);
         const T uo1 = kt_m * x[3 + k] + ddref[k] - k1[k] * de - pa1_de - lmd[k] * dso1;
         const T uo2 = -k2[k] * so;
         ctrl[k] = uo1 + uo2;
@@ -512,8 +526,7 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     theta_d = Mth<T>::max(Mth<T>::min(theta_d, lim), -lim);
     // ---- generate_action_4_uav, uav_pos_ctrl.py:470-481: finite-difference reference rates, clipped, integrated back
     T rho_d[3] = {phi_d, theta_d, ref[3]};
-    T drho_d[3] = {(phi_d - ld<T>(io.state, n, P_AREF + 0, i)) / c.dt, (theta_d - ld<T>(io.state, n, P_AREF + 1, i)) / c.dt,
-                   dref[3]};
+    T drho_d[3] = {(phi_d - aref0) / c.dt, (theta_d - aref1) / c.dt, dref[3]};
     const T rl = (T)p.dot_att_ref_limit;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -522,10 +535,9 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
         st<T>(io.state, n, P_AREF + k, i, rho_d[k]); // att_ref = rho_d (persists across resets, uav_pos_ctrl.py:329)
     }
     // ---- att_control, uav_pos_ctrl.py:317-337
-    T torque[3], d1[3], s1[3], ak1[3], ak2[3], agam[3], almd[3], aalpha[3], abeta[3];
+    T torque[3], d1[3], ak1[3], ak2[3], agam[3], almd[3], aalpha[3], abeta[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        s1[k] = ld<T>(io.state, n, P_S1 + k, i);
         ak1[k] = (T)p.att_k1[k]; ak2[k] = (T)p.att_k2[k]; agam[k] = (T)p.att_gamma[k]; almd[k] = (T)p.att_lmd[k];
         aalpha[k] = (T)p.att_alpha[k]; abeta[k] = (T)p.att_beta[k];
     }
