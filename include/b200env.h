@@ -156,6 +156,65 @@ typedef struct b200_uav_params {
  * b200env_reset / b200env_observe: the reference's reset does not clear them, so the first observation of the next
  * episode is taken against the previous episode's last reference (uav_att_ctrl.py:187-216, uav_pos_ctrl.py:488-533). */
 
+/* Flight_Attitude_Simulator (B200ENV_FAS): environment/FlightAttitudeSimulator/FlightAttitudeSimulator.py:9-287;
+ * PPO2/DPPO2 demo copy = same code with timeMax = 10, Q = 1, R = 0.05 (flight_attitude_simulator.py:42,211-224). */
+typedef struct b200_fas_params {
+    double L, k, mgd, denom;            /* L; k; m*g*dis; J + m*dis**2          :232-236 (host-evaluated) */
+    double dt, time_max;                /* :38, :42 */
+    double min_theta, max_theta, min_omega, max_omega, static_gain; /* obs normalisation :173-185 */
+    double theta_term_hi, theta_term_lo; /* maxTheta + deg2rad(1), minTheta - deg2rad(1)   :199-206 */
+    double Q, R;                        /* reward weights :218-219 */
+    double reset_lo, reset_hi;          /* theta0 ~ U(minTheta, maxTheta) :270-271 */
+} b200_fas_params;
+#define B200_FAS_STATE_FIELDS 2         /* theta, dTheta */
+
+/* SecondOrderIntegration (B200ENV_SOI): environment/SecondOrderIntegration/SecondOrderIntegration.py:13-352;
+ * DPPO2 demo copy: obs multiplied by static_gain, success terminal disabled, Q_vel = Q_acc = 0. */
+typedef struct b200_soi_params {
+    double map_x, map_y, target_x, target_y; /* :16-17 */
+    double mass, k, vmax, dt, time_max, admissible_error; /* :31-42 */
+    double obs_gain;                    /* 1 (ENV) or static_gain (DPPO2 copy :213) */
+    double Q_pos, Q_vel, Q_acc;         /* :262-264 */
+    double reset_margin;                /* pos0 ~ U(0 + 0.1, map - 0.1) :329-331 */
+    int32_t success_terminal;           /* 1 (ENV :246-249) / 0 (DPPO2 copy) */
+    int32_t pad_;
+} b200_soi_params;
+#define B200_SOI_STATE_FIELDS 4         /* x, y, vx, vy */
+
+/* BallBalancer1D (B200ENV_BALLBALANCER): environment/BallBalancer/BallBalancer1D.py:14-322 */
+typedef struct b200_ballbalancer_params {
+    double K, L;                        /* :62-63, :58 */
+    double omega_min, omega_max, theta_min, theta_max, v_min, v_max; /* :34-39 */
+    double dt, time_max, static_gain, target; /* :47-51, :70 */
+    double deg1;                        /* deg2rad(1) :214 */
+    double reset_theta_lo, reset_theta_hi, reset_pos_lo, reset_pos_hi, init_vel; /* :294-296 */
+} b200_ballbalancer_params;
+#define B200_BALLBALANCER_STATE_FIELDS 4 /* pos, vel, theta, error (error lags one step inside is_Terminal, :279-281) */
+
+/* TwoLinkManipulator (B200ENV_TWOLINK): environment/RobotManipulator/TwoLinkManipulator.py:8-312 */
+typedef struct b200_twolink_params {
+    double l, m, g, J;                  /* :33-36 */
+    double dt, time_max;                /* :37-39 */
+    double base_x, base_y;              /* :32 */
+    double theta_max, miss, omega_ok;   /* pi; 0.01; deg2rad(5)  :42-48,194-197 */
+    double init_end_x, init_end_y;      /* init_endPos :19 (error after reset = target - init_endPos, :300) */
+    double r2_lo, r2_hi;                /* target radius^2 ~ U(0.3^2, (2l)^2) :286 */
+    double Q_pos, Q_omega, Q_acc;       /* :212-214 */
+} b200_twolink_params;
+#define B200_TWOLINK_STATE_FIELDS 8     /* theta1 theta2 omega1 omega2 err_x err_y target_x target_y */
+
+/* UGVForward / UGVBidirectional (B200ENV_UGV): environment/UGV/UGVForward.py:10-362, UGVBidirectional.py:10-367 */
+typedef struct b200_ugv_params {
+    double map_x, map_y, target_x, target_y;
+    double dt, time_max, kf, kt;        /* :43-48 */
+    double e_max, v_max, e_phi_max, omega_max, static_gain; /* :53-58,66 */
+    double Q_pos, Q_vel, Q_phi, Q_omega; /* :264-267 */
+    double reset_d0;                    /* pos0 ~ U(d0, map - d0) :336-338 */
+    int32_t bidirectional;              /* 0 UGVForward, 1 UGVBidirectional */
+    int32_t pad_;
+} b200_ugv_params;
+#define B200_UGV_STATE_FIELDS 5         /* x, y, vel, phi, omega */
+
 /* ---------------------------------------------------------------- queries */
 
 /* sizes of the SoA arrays of one env family/variant; any out pointer may be NULL */
@@ -197,6 +256,25 @@ B200_API int b200env_reset(int env_id, int dtype, int64_t n_envs,
 B200_API int b200env_observe(int env_id, int dtype, int64_t n_envs,
                     const void *params, size_t params_bytes,
                     const b200env_io *io, void *cuda_stream);
+
+/* ------------------------------------------------------------- GAE */
+
+/* Replaces the reverse loop of Proximal_Policy_Optimization2.learn (algorithm/policy_base/
+ * Proximal_Policy_Optimization2.py:88-98) and Worker.learn (Distributed_PPO2.py:59-69) for N env columns at once.
+ * All arrays are device float32, time-major [T][N] (element (t, n) at t * N + n); `done`/`success` hold 0.0/1.0 like
+ * the reference's RolloutBuffer (utils/classes.py:250-301).
+ *   delta = r + gamma * (1 - success) * vs_next - vs;  gae_t = delta_t + gamma * lmd * gae_{t+1} * (1 - done_t)
+ *   adv = gae;  v_target = adv + vs
+ * acc_mode 0: float32 sequential, bit-identical to the reference loop under numpy >= 2; 1: float64 carry (numpy 1.x).
+ * stats (device double[3], may be NULL) is INCREMENTED by (sum adv, sum adv^2, T * N): zero it first; all-reduce it
+ * over ranks for a global advantage normalisation. */
+B200_API int b200_gae(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next, const float *done,
+                      const float *success, double gamma, double lmd, int acc_mode, float *adv, float *v_target,
+                      double *stats, void *cuda_stream);
+
+/* adv <- (adv - mean) / (std + eps) with the unbiased std (torch.Tensor.std) derived from stats = (sum, sum of
+ * squares, count): Proximal_Policy_Optimization2.py:99-100 (eps = 1e-5). */
+B200_API int b200_adv_normalize(int64_t count, float *adv, const double *stats, double eps, void *cuda_stream);
 
 /* ------------------------------------------------------------- diagnostics */
 

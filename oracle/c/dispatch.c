@@ -14,12 +14,22 @@ typedef void (*reset_one_fn)(const void *, const oracle_io *, int64_t, int64_t, 
 DECL(cartpole)
 DECL(uav_att)
 DECL(uav_pos)
+DECL(fas)
+DECL(soi)
+DECL(ballbalancer)
+DECL(twolink)
+DECL(ugv)
 
 static step_one_fn step_of(int env_id) {
     switch (env_id) {
     case B200ENV_CARTPOLE: return orc_cartpole_step_one;
     case B200ENV_UAV_ATT: return orc_uav_att_step_one;
     case B200ENV_UAV_POS: return orc_uav_pos_step_one;
+    case B200ENV_FAS: return orc_fas_step_one;
+    case B200ENV_SOI: return orc_soi_step_one;
+    case B200ENV_BALLBALANCER: return orc_ballbalancer_step_one;
+    case B200ENV_TWOLINK: return orc_twolink_step_one;
+    case B200ENV_UGV: return orc_ugv_step_one;
     default: return 0;
     }
 }
@@ -28,6 +38,11 @@ static reset_one_fn reset_of(int env_id) {
     case B200ENV_CARTPOLE: return orc_cartpole_reset_one;
     case B200ENV_UAV_ATT: return orc_uav_att_reset_one;
     case B200ENV_UAV_POS: return orc_uav_pos_reset_one;
+    case B200ENV_FAS: return orc_fas_reset_one;
+    case B200ENV_SOI: return orc_soi_reset_one;
+    case B200ENV_BALLBALANCER: return orc_ballbalancer_reset_one;
+    case B200ENV_TWOLINK: return orc_twolink_reset_one;
+    case B200ENV_UGV: return orc_ugv_reset_one;
     default: return 0;
     }
 }

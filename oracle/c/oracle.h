@@ -49,7 +49,8 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 /* GAE reverse scan, float32 sequential exactly like the Python loop under numpy >= 2
  * (algorithm/policy_base/Proximal_Policy_Optimization2.py:88-98) */
 void oracle_gae(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next, const float *done,
-                const float *success, float gamma, float lambda, float *adv, float *v_target, double *stats);
+                const float *success, float gamma, float lambda_gamma /* float32(gamma * lmd) */, float *adv,
+                float *v_target, double *stats /* += (sum adv, sum adv^2, T*N), may be NULL */);
 
 #ifdef __cplusplus
 }

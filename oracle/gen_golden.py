@@ -16,7 +16,7 @@ L independent lanes and T steps,
     reset_state [T,L,F]              state after the reference's own reset(True) that follows
                                      a terminal step (NaN rows elsewhere), reset_time likewise
     twin_err [T,L]                   self-sensitivity of the reference: mixed error of next_obs between the recorded run and
-                                     a twin reference instance whose state is nudged by ~1e-16 after the reset and after
+                                     a twin reference instance whose state is nudged by about one ulp after the reset and after
                                      every step (what any re-implementation with different rounding does).  Free-running
                                      tolerances are expressed as a multiple of its running maximum.
     meta                             numpy version, cpu flags, reference call sites

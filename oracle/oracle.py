@@ -41,6 +41,8 @@ def load() -> C.CDLL:
         lib.oracle_reset.argtypes = [i32, i64, vp, C.POINTER(OracleIO), vp, u64, i64]
         lib.oracle_observe.restype = i32
         lib.oracle_observe.argtypes = [i32, i64, vp, C.POINTER(OracleIO)]
+        lib.oracle_gae.restype = None
+        lib.oracle_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp]
         lib.oracle_philox4x32_10.restype = None
         lib.oracle_philox4x32_10.argtypes = [vp, vp, vp]
         _lib = lib
@@ -106,3 +108,15 @@ class OracleEnv:
         rc = self.lib.oracle_observe(self.env_id, self.n, C.byref(self.params), C.byref(io))
         assert rc == 0, rc
         return self.next_obs
+
+
+def gae(r, vs, vs_next, done, success, gamma, lmd):
+    """C restatement of the reference GAE loop on time-major [T, N] float32 arrays -> (adv, v_target, stats)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (r, vs, vs_next, done, success)]
+    T, N = arrs[0].shape
+    adv = np.zeros((T, N), np.float32)
+    vt = np.zeros((T, N), np.float32)
+    stats = np.zeros(3, np.float64)
+    load().oracle_gae(T, N, *[a.ctypes.data for a in arrs], np.float32(gamma), np.float32(gamma * lmd),
+                      adv.ctypes.data, vt.ctypes.data, stats.ctypes.data)
+    return adv, vt, stats

@@ -40,13 +40,14 @@ class Adapter:
     def params_json(self):
         return {}
 
-    #: attributes nudged by +-1e-16 * max(1, |v|) in the twin instance (self-sensitivity measurement)
+    #: attributes nudged by about one ulp (+-2.3e-16 * max(1, |v|)) in the twin instance (self-sensitivity measurement)
     perturb_attrs = ()
+    EPS = 2.3e-16
 
     def perturb(self, env, k):
         for j, name in enumerate(self.perturb_attrs):
             v = float(getattr(env, name))
-            setattr(env, name, v + (1e-16 if (k + j) % 2 == 0 else -1e-16) * max(1.0, abs(v)))
+            setattr(env, name, v + (self.EPS if (k + j) % 2 == 0 else -self.EPS) * max(1.0, abs(v)))
 
 
 # --------------------------------------------------------------------- CartPole
@@ -300,4 +301,161 @@ REGISTRY.update({
     "uav_pos_crash": (UavPosCrashA, 2, 400, 25),
     "uav_pos_edge": (UavPosEdgeA, 2, 200, 26),
     "uav_att_edge": (UavAttEdgeA, 2, 200, 27),
+})
+
+
+# ------------------------------------------------------------- small envs
+class FasA(Adapter):
+    name = "fas"
+    cites = "environment/FlightAttitudeSimulator/FlightAttitudeSimulator.py:173-287"
+    F, S, A, D = 2, 2, 1, 0
+    action_lo, action_hi = np.array([-1.5]), np.array([4.])
+    perturb_attrs = ("theta", "dTheta")
+
+    def make(self):
+        return R.load("environment.FlightAttitudeSimulator.FlightAttitudeSimulator").Flight_Attitude_Simulator(0.)
+
+    def internal(self, env):
+        return np.array([env.theta, env.dTheta], dtype=float), float(env.time)
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 4 == 0:
+            return rng.uniform(self.action_lo, self.action_hi)
+        if l % 4 == 2:
+            return rng.uniform(3.0, 4.0, 1)  # pushes up: upper-bound flag (1)
+        hover = env.m * env.g * env.dis / env.L  # keeps the rod near level: episodes reach the time-out flag
+        return np.clip(np.array([hover - 3.0 * env.theta - 0.8 * env.dTheta]) + rng.uniform(-0.3, 0.3, 1), -1.5, 4)
+
+
+class FasPPO2A(FasA):
+    name = "fas_ppo2"
+    cites = "demonstration/PPO2/PPO2-4-FlightAttitudeSimulator/flight_attitude_simulator.py:170-280"
+
+    def make(self):
+        m = R.load_file("demonstration/PPO2/PPO2-4-FlightAttitudeSimulator/flight_attitude_simulator.py", "ref_fas_ppo2")
+        return m.Flight_Attitude_Simulator(0.)
+
+
+class SoiA(Adapter):
+    name = "soi"
+    cites = "environment/SecondOrderIntegration/SecondOrderIntegration.py:211-352"
+    F, S, A, D = 4, 4, 2, 0
+    action_lo, action_hi = np.array([-3., -3.]), np.array([3., 3.])
+    perturb_attrs = ()
+
+    def make(self):
+        return R.load("environment.SecondOrderIntegration.SecondOrderIntegration").SecondOrderIntegration()
+
+    def internal(self, env):
+        return np.array([env.pos[0], env.pos[1], env.vel[0], env.vel[1]], dtype=float), float(env.time)
+
+    def perturb(self, env, k):
+        env.vel[0] += (self.EPS if k % 2 == 0 else -self.EPS) * max(1.0, abs(env.vel[0]))
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 2 == 0:
+            return rng.uniform(self.action_lo, self.action_hi)
+        e = env.target - env.pos  # PD towards the target: reaches the success flag
+        return np.clip(4.0 * e - 2.5 * env.vel + rng.uniform(-0.05, 0.05, 2), -3, 3)
+
+
+class SoiDPPO2A(SoiA):
+    name = "soi_dppo2"
+    cites = "demonstration/DPPO2/DPPO2-4-SecondOrderIntegration/SecondOrderIntegration.py:208-340"
+
+    def make(self):
+        m = R.load_file("demonstration/DPPO2/DPPO2-4-SecondOrderIntegration/SecondOrderIntegration.py", "ref_soi_dppo2")
+        return m.SecondOrderIntegration()
+
+
+class BallBalancerA(Adapter):
+    name = "ballbalancer"
+    cites = "environment/BallBalancer/BallBalancer1D.py:200-322"
+    F, S, A, D = 4, 3, 1, 0
+    action_lo, action_hi = np.array([-np.pi]), np.array([np.pi])
+    perturb_attrs = ("vel", "theta")
+
+    def make(self):
+        return R.load("environment.BallBalancer.BallBalancer1D").BallBalancer1D()
+
+    def internal(self, env):
+        return np.array([env.pos, env.vel, env.theta, env.error], dtype=float), float(env.time)
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 2 == 0:
+            return rng.uniform(-4.0, 4.0, 1)  # beyond +-pi: exercises the np.clip of the action
+        goal = env.target + (0.04 if l % 4 == 3 else 0.0)  # lane 3 holds the ball off-target: time-out flag (2)
+        u = -(25.0 * (env.pos - goal) + 12.0 * env.vel) - 6.0 * env.theta  # stabilising: success flag (3)
+        return np.clip(np.array([u]) + rng.uniform(-0.02, 0.02, 1), -np.pi, np.pi)
+
+
+class TwoLinkA(Adapter):
+    name = "twolink"
+    cites = "environment/RobotManipulator/TwoLinkManipulator.py:186-312"
+    F, S, A, D = 8, 6, 2, 0
+    action_lo, action_hi = np.array([-5., -5.]), np.array([5., 5.])
+
+    def make(self):
+        return R.load("environment.RobotManipulator.TwoLinkManipulator").TwoLinkManipulator()
+
+    def perturb(self, env, k):
+        env.omega[0] += (self.EPS if k % 2 == 0 else -self.EPS) * max(1.0, abs(env.omega[0]))
+
+    def internal(self, env):
+        return np.array([env.theta[0], env.theta[1], env.omega[0], env.omega[1], env.error[0], env.error[1],
+                         env.target[0], env.target[1]], dtype=float), float(env.time)
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 2 == 0:
+            return rng.uniform(self.action_lo, self.action_hi)
+        return np.clip(-3.0 * env.omega + rng.uniform(-0.5, 0.5, 2), -5, 5)  # damped: long episodes (time-out flag)
+
+
+class UgvForwardA(Adapter):
+    name = "ugv_forward"
+    cites = "environment/UGV/UGVForward.py:217-362"
+    F, S, A, D = 5, 4, 2, 0
+    action_lo, action_hi = np.array([-3., -2 * np.pi]), np.array([3., 2 * np.pi])
+    perturb_attrs = ("vel", "phi", "omega")
+    mod, cls = "environment.UGV.UGVForward", "UGVForward"
+
+    def make(self):
+        return getattr(R.load(self.mod), self.cls)()
+
+    def internal(self, env):
+        return np.array([env.pos[0], env.pos[1], env.vel, env.phi, env.omega], dtype=float), float(env.time)
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 2 == 0:
+            return rng.uniform(self.action_lo, self.action_hi)
+        # go-to-goal: heads for the target and brakes there (success flag), some noise
+        e, ephi = env.get_e(), env.get_e_phi()
+        a_lin = 2.0 * abs(e) * np.cos(ephi) - 2.5 * env.vel
+        a_ang = 6.0 * ephi - 4.0 * env.omega
+        return np.clip(np.array([a_lin, a_ang]) + rng.uniform(-0.02, 0.02, 2), self.action_lo, self.action_hi)
+
+
+class UgvBidirectionalA(UgvForwardA):
+    name = "ugv_bidirectional"
+    cites = "environment/UGV/UGVBidirectional.py:217-367"
+    mod, cls = "environment.UGV.UGVBidirectional", "UGVBidirectional"
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 2 == 0:
+            return rng.uniform(self.action_lo, self.action_hi)
+        e, ephi = env.get_e(), env.get_e_phi()
+        a_lin = 2.0 * e - 2.5 * env.vel
+        a_ang = 6.0 * ephi - 4.0 * env.omega
+        return np.clip(np.array([a_lin, a_ang]) + rng.uniform(-0.02, 0.02, 2), self.action_lo, self.action_hi)
+
+
+REGISTRY.update({
+    "fas": (FasA, 4, 800, 31),
+    "fas_ppo2": (FasPPO2A, 2, 1200, 32),
+    "soi": (SoiA, 4, 800, 33),
+    "soi_dppo2": (SoiDPPO2A, 2, 600, 34),
+    "ballbalancer": (BallBalancerA, 4, 1000, 35),
+    "twolink": (TwoLinkA, 4, 900, 36),
+    "ugv_forward": (UgvForwardA, 4, 1100, 37),
+    "ugv_bidirectional": (UgvBidirectionalA, 4, 1100, 38),
 })

@@ -65,7 +65,29 @@ class UavParams(C.Structure):
         _d("traj_phase_hi"), ("random_trajectory", C.c_int32), ("yaw_fixed", C.c_int32)]
 
 
-PARAMS_OF = {CARTPOLE: CartPoleParams, UAV_ATT: UavParams, UAV_POS: UavParams}
+def _struct(name, doc, doubles, ints=()):
+    fields = [(k, C.c_double) for k in doubles] + [(k, C.c_int32) for k in ints]
+    return type(name, (C.Structure,), {"_fields_": fields, "__doc__": doc})
+
+
+FasParams = _struct("FasParams", "struct b200_fas_params", (
+    "L", "k", "mgd", "denom", "dt", "time_max", "min_theta", "max_theta", "min_omega", "max_omega", "static_gain",
+    "theta_term_hi", "theta_term_lo", "Q", "R", "reset_lo", "reset_hi"))
+SoiParams = _struct("SoiParams", "struct b200_soi_params", (
+    "map_x", "map_y", "target_x", "target_y", "mass", "k", "vmax", "dt", "time_max", "admissible_error", "obs_gain",
+    "Q_pos", "Q_vel", "Q_acc", "reset_margin"), ("success_terminal", "pad_"))
+BallBalancerParams = _struct("BallBalancerParams", "struct b200_ballbalancer_params", (
+    "K", "L", "omega_min", "omega_max", "theta_min", "theta_max", "v_min", "v_max", "dt", "time_max", "static_gain",
+    "target", "deg1", "reset_theta_lo", "reset_theta_hi", "reset_pos_lo", "reset_pos_hi", "init_vel"))
+TwoLinkParams = _struct("TwoLinkParams", "struct b200_twolink_params", (
+    "l", "m", "g", "J", "dt", "time_max", "base_x", "base_y", "theta_max", "miss", "omega_ok", "init_end_x",
+    "init_end_y", "r2_lo", "r2_hi", "Q_pos", "Q_omega", "Q_acc"))
+UgvParams = _struct("UgvParams", "struct b200_ugv_params", (
+    "map_x", "map_y", "target_x", "target_y", "dt", "time_max", "kf", "kt", "e_max", "v_max", "e_phi_max", "omega_max",
+    "static_gain", "Q_pos", "Q_vel", "Q_phi", "Q_omega", "reset_d0"), ("bidirectional", "pad_"))
+
+PARAMS_OF = {CARTPOLE: CartPoleParams, UAV_ATT: UavParams, UAV_POS: UavParams, FAS: FasParams, SOI: SoiParams,
+             BALLBALANCER: BallBalancerParams, TWOLINK: TwoLinkParams, UGV: UgvParams}
 
 _lib = None
 
@@ -97,6 +119,11 @@ def load() -> C.CDLL:
     lib.b200env_reset.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), vp, u64, i64, vp]
     lib.b200env_observe.restype = i32
     lib.b200env_observe.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), vp]
+    f64 = C.c_double
+    lib.b200_gae.restype = i32
+    lib.b200_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, f64, f64, i32, vp, vp, vp, vp]
+    lib.b200_adv_normalize.restype = i32
+    lib.b200_adv_normalize.argtypes = [i64, vp, vp, f64, vp]
     lib.b200_fastmath_eval.restype = i32
     lib.b200_fastmath_eval.argtypes = [i32, i64, vp, vp, vp, vp]
     lib.b200_measure_fma_peak.restype = i32

@@ -21,6 +21,11 @@ const Family *family(int env_id) {
         table[B200ENV_CARTPOLE] = FAM(cartpole, b200_cartpole_params);
         table[B200ENV_UAV_ATT] = FAM(uav_att, b200_uav_params);
         table[B200ENV_UAV_POS] = FAM(uav_pos, b200_uav_params);
+        table[B200ENV_FAS] = FAM(fas, b200_fas_params);
+        table[B200ENV_SOI] = FAM(soi, b200_soi_params);
+        table[B200ENV_BALLBALANCER] = FAM(ballbalancer, b200_ballbalancer_params);
+        table[B200ENV_TWOLINK] = FAM(twolink, b200_twolink_params);
+        table[B200ENV_UGV] = FAM(ugv, b200_ugv_params);
         init = true;
     }
     if (env_id < 0 || env_id >= B200ENV_COUNT) return nullptr;

@@ -177,3 +177,8 @@ static inline unsigned b200_grid(int64_t n, int block = B200_BLOCK) { return (un
 B200_FAMILY_DECL(cartpole)
 B200_FAMILY_DECL(uav_att)
 B200_FAMILY_DECL(uav_pos)
+B200_FAMILY_DECL(fas)
+B200_FAMILY_DECL(soi)
+B200_FAMILY_DECL(ballbalancer)
+B200_FAMILY_DECL(twolink)
+B200_FAMILY_DECL(ugv)

@@ -1,0 +1,127 @@
+// env_kernel.cuh -- generic one-thread-per-instance step / reset / observe kernels for the small env families.
+//
+// An env family provides a struct E<T> with
+//     using P = <params struct>;  static constexpr int SF, OD, AD;       (state fields, obs dim, action dim)
+//     load(io, n, i) / store(io, n, i)           SoA state <-> registers (time included)
+//     observe(p, o[OD])                          get_state()
+//     step(p, act[AD], cur[OD], flag, done, reward)   rk44 + is_Terminal + get_reward (next obs is taken afterwards)
+//     reset(p, rng)                              reset(random=True) with Philox draws in the reference's draw order
+// and the kernels below add the common data movement: all loads first, outputs, optional auto-reset.
+#pragma once
+#include "common.cuh"
+
+template <typename T, class E>
+__global__ void __launch_bounds__(B200_BLOCK)
+env_step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ b200env_io io, int64_t n,
+                uint32_t flags, uint64_t seed, int64_t off) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    E e;
+    e.load(io, n, i);
+    T act[E::AD];
+#pragma unroll
+    for (int k = 0; k < E::AD; ++k) act[k] = ld<T>(io.action, n, k, i);
+    T cur[E::OD], nxt[E::OD];
+    e.observe(p, cur); // self.current_state = self.get_state()
+    if (io.obs) {
+#pragma unroll
+        for (int k = 0; k < E::OD; ++k) st<T>(io.obs, n, k, i, cur[k]);
+    }
+    int flag = 0;
+    bool done = false;
+    T reward = (T)0;
+    e.step(p, act, cur, flag, done, reward, nxt);
+#pragma unroll
+    for (int k = 0; k < E::OD; ++k) st<T>(io.next_obs, n, k, i, nxt[k]);
+    st<T>(io.reward, n, 0, i, reward);
+    io.done[i] = done ? 1 : 0;
+    io.flag[i] = flag;
+    if (done && (flags & B200ENV_AUTO_RESET)) {
+        const uint32_t ep = io.episode[i];
+        Philox rng(seed, (uint64_t)(off + i), ep);
+        e.reset(p, rng);
+        io.episode[i] = ep + 1u;
+        e.observe(p, nxt);
+    }
+    if (io.reset_obs) {
+#pragma unroll
+        for (int k = 0; k < E::OD; ++k) st<T>(io.reset_obs, n, k, i, nxt[k]);
+    }
+    e.store(io, n, i);
+}
+
+template <typename T, class E>
+__global__ void __launch_bounds__(B200_BLOCK)
+env_reset_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ b200env_io io, int64_t n,
+                 const uint8_t *mask, uint64_t seed, int64_t off, int observe_only) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!observe_only && mask && !mask[i]) return;
+    E e;
+    e.load(io, n, i);
+    if (!observe_only) {
+        const uint32_t ep = io.episode[i];
+        Philox rng(seed, (uint64_t)(off + i), ep);
+        e.reset(p, rng);
+        io.episode[i] = ep + 1u;
+        e.store(io, n, i);
+    }
+    if (io.next_obs) {
+        T o[E::OD];
+        e.observe(p, o);
+#pragma unroll
+        for (int k = 0; k < E::OD; ++k) st<T>(io.next_obs, n, k, i, o[k]);
+    }
+}
+
+// host-side launchers: EnvT is the family template, instantiated for double and float
+template <template <typename> class EnvT>
+int env_launch_step(int dtype, int64_t n, const void *params, const b200env_io *io, uint32_t flags, uint64_t seed,
+                    int64_t off, cudaStream_t s) {
+    typedef typename EnvT<double>::P P;
+    if (!io->state || !io->time || !io->action || !io->next_obs || !io->reward || !io->done || !io->flag)
+        return B200ENV_ENULL;
+    if ((flags & B200ENV_AUTO_RESET) && !io->episode) return B200ENV_ENULL;
+    const P &p = *static_cast<const P *>(params);
+    if (dtype == B200ENV_F64)
+        env_step_kernel<double, EnvT<double>><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
+    else
+        env_step_kernel<float, EnvT<float>><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
+    return b200_check_launch();
+}
+
+template <template <typename> class EnvT>
+int env_launch_reset(int dtype, int64_t n, const void *params, const b200env_io *io, const uint8_t *mask,
+                     uint64_t seed, int64_t off, cudaStream_t s, int observe_only) {
+    typedef typename EnvT<double>::P P;
+    if (!io->state || !io->time) return B200ENV_ENULL;
+    if (!observe_only && !io->episode) return B200ENV_ENULL;
+    if (observe_only && !io->next_obs) return B200ENV_ENULL;
+    const P &p = *static_cast<const P *>(params);
+    if (dtype == B200ENV_F64)
+        env_reset_kernel<double, EnvT<double>><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, mask, seed, off, observe_only);
+    else
+        env_reset_kernel<float, EnvT<float>><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, mask, seed, off, observe_only);
+    return b200_check_launch();
+}
+
+#define B200_FAMILY_IMPL(name, EnvT, sf, od, ad, dd)                                                                  \
+    int name##_dims(int variant, int *psf, int *pod, int *pad, int *pdd) {                                            \
+        if (variant != 0) return B200ENV_EENV;                                                                        \
+        if (psf) *psf = sf;                                                                                           \
+        if (pod) *pod = od;                                                                                           \
+        if (pad) *pad = ad;                                                                                           \
+        if (pdd) *pdd = dd;                                                                                           \
+        return B200ENV_OK;                                                                                            \
+    }                                                                                                                 \
+    int name##_step(int dtype, int64_t n, const void *params, const b200env_io *io, uint32_t flags, uint64_t seed,    \
+                    int64_t off, cudaStream_t s) {                                                                    \
+        return env_launch_step<EnvT>(dtype, n, params, io, flags, seed, off, s);                                      \
+    }                                                                                                                 \
+    int name##_reset(int dtype, int64_t n, const void *params, const b200env_io *io, const uint8_t *mask,             \
+                     uint64_t seed, int64_t off, cudaStream_t s) {                                                    \
+        return env_launch_reset<EnvT>(dtype, n, params, io, mask, seed, off, s, 0);                                   \
+    }                                                                                                                 \
+    int name##_observe(int dtype, int64_t n, const void *params, const b200env_io *io, cudaStream_t s) {              \
+        return env_launch_reset<EnvT>(dtype, n, params, io, nullptr, 0, 0, s, 1);                                     \
+    }

@@ -1,0 +1,145 @@
+// gae.cu -- K-GAE: PPO2 / DPPO2 generalised-advantage reverse scan over a time-major [T, N] rollout (sm_100a).
+//
+// Replaces the Python loop of algorithm/policy_base/Proximal_Policy_Optimization2.py:88-100 (and the identical
+// Worker.learn lines of Distributed_PPO2.py:59-71):
+//     deltas   = r + gamma * (1 - success) * V(s') - V(s)                   float32 tensors
+//     gae_t    = delta_t + gamma * lmd * gae_{t+1} * (1 - done_t)           reverse loop, gae_T = 0
+//     v_target = adv + V(s);   adv <- (adv - mean) / (std_unbiased + 1e-5)
+// The reference holds one env (N = 1, T = buffer size); here every column n of the [T, N] arrays is one env instance,
+// one thread walks its column backwards, and consecutive threads read consecutive addresses (28 B of HBM traffic per
+// element: 5 float loads + 2 float stores).
+//
+// Exactness: with acc_mode 0 every operation is a separately rounded float32 multiply/add (__fmul_rn/__fadd_rn, no
+// FMA contraction) in the reference's evaluation order, i.e. bit-identical to the loop under numpy >= 2 (NEP 50:
+// python floats are weak, the scan runs in float32).  acc_mode 1 carries gae in float64 (the numpy 1.x behaviour).
+// The per-launch (sum adv, sum adv^2, count) are accumulated in float64 and added atomically to stats[3], ready for a
+// 3-double all-reduce when the rollout is sharded over GPUs (global advantage normalisation).
+#include "common.cuh"
+
+namespace {
+
+constexpr int GAE_BLOCK = 128;
+constexpr int GAE_UNROLL = 4;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <bool F64_ACC>
+__global__ void __launch_bounds__(GAE_BLOCK)
+gae_kernel(int64_t T, int64_t N, const float *__restrict__ r, const float *__restrict__ vs,
+           const float *__restrict__ vsn, const float *__restrict__ done, const float *__restrict__ succ, float g32,
+           float gl32, double gl64, float *__restrict__ adv, float *__restrict__ vt, double *stats) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    if (n < N) {
+        float gae = 0.0f;
+        double gae64 = 0.0;
+        int64_t t = T - 1;
+        // main loop: GAE_UNROLL time steps per trip, all loads of a trip issued before the dependent scan
+        for (; t >= GAE_UNROLL - 1; t -= GAE_UNROLL) {
+            float rr[GAE_UNROLL], v0[GAE_UNROLL], v1[GAE_UNROLL], dd[GAE_UNROLL], ss[GAE_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GAE_UNROLL; ++u) {
+                const int64_t idx = (t - u) * N + n;
+                rr[u] = __ldcs(r + idx); v0[u] = __ldcs(vs + idx); v1[u] = __ldcs(vsn + idx);
+                dd[u] = __ldcs(done + idx); ss[u] = __ldcs(succ + idx);
+            }
+#pragma unroll
+            for (int u = 0; u < GAE_UNROLL; ++u) {
+                const int64_t idx = (t - u) * N + n;
+                // deltas = r + gamma * (1.0 - success) * vs_ - vs
+                const float delta = __fsub_rn(__fadd_rn(rr[u], __fmul_rn(__fmul_rn(g32, __fsub_rn(1.0f, ss[u])), v1[u])), v0[u]);
+                float a;
+                if (F64_ACC) {
+                    gae64 = (double)delta + gl64 * gae64 * (1.0 - (double)dd[u]);
+                    a = (float)gae64;
+                } else {
+                    // gae = delta + gamma * lmd * gae * (1.0 - d)
+                    gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl32, gae), __fsub_rn(1.0f, dd[u])));
+                    a = gae;
+                }
+                __stcs(adv + idx, a);
+                __stcs(vt + idx, __fadd_rn(a, v0[u]));
+                s1 += (double)a;
+                s2 += (double)a * (double)a;
+            }
+        }
+        for (; t >= 0; --t) {
+            const int64_t idx = t * N + n;
+            const float v0 = vs[idx];
+            const float delta = __fsub_rn(__fadd_rn(r[idx], __fmul_rn(__fmul_rn(g32, __fsub_rn(1.0f, succ[idx])), vsn[idx])), v0);
+            float a;
+            if (F64_ACC) {
+                gae64 = (double)delta + gl64 * gae64 * (1.0 - (double)done[idx]);
+                a = (float)gae64;
+            } else {
+                gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl32, gae), __fsub_rn(1.0f, done[idx])));
+                a = gae;
+            }
+            adv[idx] = a;
+            vt[idx] = __fadd_rn(a, v0);
+            s1 += (double)a;
+            s2 += (double)a * (double)a;
+        }
+    }
+    if (stats) {
+        __shared__ double sh1[GAE_BLOCK / 32], sh2[GAE_BLOCK / 32];
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) { sh1[w] = s1; sh2[w] = s2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0, b = 0;
+#pragma unroll
+            for (int k = 0; k < GAE_BLOCK / 32; ++k) { a += sh1[k]; b += sh2[k]; }
+            atomicAdd(stats + 0, a);
+            atomicAdd(stats + 1, b);
+            if (blockIdx.x == 0) atomicAdd(stats + 2, (double)T * (double)N);
+        }
+    }
+}
+
+// adv <- (adv - mean) / (std + eps), mean/std from (sum, sum of squares, count); unbiased std like torch.Tensor.std()
+__global__ void __launch_bounds__(256)
+adv_normalize_kernel(int64_t count, float *__restrict__ adv, const double *__restrict__ stats, double eps) {
+    const double cnt = stats[2];
+    const double mean = stats[0] / cnt;
+    const double var = fmax((stats[1] - cnt * mean * mean) / (cnt - 1.0), 0.0);
+    const float m = (float)mean, inv = (float)(1.0 / (sqrt(var) + eps));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        adv[i] = (adv[i] - m) * inv;
+}
+
+} // namespace
+
+extern "C" B200_API int b200_gae(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next,
+                                 const float *done, const float *success, double gamma, double lmd, int acc_mode,
+                                 float *adv, float *v_target, double *stats, void *cuda_stream) {
+    if (T <= 0 || N <= 0) return B200ENV_ESIZE;
+    if (!r || !vs || !vs_next || !done || !success || !adv || !v_target) return B200ENV_ENULL;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const unsigned grid = (unsigned)((N + GAE_BLOCK - 1) / GAE_BLOCK);
+    const float g32 = (float)gamma, gl32 = (float)(gamma * lmd);
+    if (acc_mode == 0)
+        gae_kernel<false><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, done, success, g32, gl32, gamma * lmd, adv, v_target, stats);
+    else
+        gae_kernel<true><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, done, success, g32, gl32, gamma * lmd, adv, v_target, stats);
+    return b200_check_launch();
+}
+
+extern "C" B200_API int b200_adv_normalize(int64_t count, float *adv, const double *stats, double eps,
+                                           void *cuda_stream) {
+    if (count <= 0) return B200ENV_ESIZE;
+    if (!adv || !stats) return B200ENV_ENULL;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t blocks = (count + 255) / 256;
+    if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+    adv_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(count, adv, stats, eps);
+    return b200_check_launch();
+}

@@ -1,0 +1,51 @@
+"""GAE reverse scan + advantage normalisation on device (kernel K-GAE, csrc/gae.cu).
+
+Replaces ``Proximal_Policy_Optimization2.learn`` lines 88-100 (and ``Distributed_PPO2.Worker.learn`` 59-71) for a
+time-major ``[T, N]`` rollout: every column is one env instance.  With ``torch.distributed`` initialised the
+normalisation statistics ``(sum adv, sum adv^2, count)`` are all-reduced (3 doubles over NCCL) so that every rank
+normalises with the GLOBAL mean / unbiased std, the multi-GPU analogue of ``adv.mean()`` / ``adv.std()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def gae(r, vs, vs_next, done, success, gamma: float, lmd: float, acc_mode: int = 0, stats: torch.Tensor = None):
+    """adv, v_target, stats = gae(...).  All inputs: CUDA float32 ``[T, N]`` contiguous (done / success as 0.0 / 1.0).
+    acc_mode 0 = float32 sequential (bit-identical to the reference loop under numpy >= 2), 1 = float64 carry."""
+    lib = _lib.load()
+    ts = [r, vs, vs_next, done, success]
+    for t in ts:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == r.shape and t.dim() == 2):
+            raise ValueError("gae: inputs must be contiguous CUDA float32 tensors of one [T, N] shape")
+    T, N = r.shape
+    adv = torch.empty_like(r)
+    vt = torch.empty_like(r)
+    if stats is None:
+        stats = torch.zeros(3, dtype=torch.float64, device=r.device)
+    with torch.cuda.device(r.device):
+        stream = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
+        _lib.check(lib.b200_gae(T, N, *[_p(t) for t in ts], float(gamma), float(lmd), int(acc_mode), _p(adv), _p(vt),
+                                _p(stats), stream), "b200_gae")
+    return adv, vt, stats
+
+
+def normalize_advantage(adv: torch.Tensor, stats: torch.Tensor, eps: float = 1e-5, group=None) -> torch.Tensor:
+    """In place ``adv <- (adv - mean) / (std + eps)`` (PPO2.py:99-100); ``stats`` from :func:`gae`.  If a process group
+    is initialised the 3 statistics are summed over ranks first (global normalisation)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    lib = _lib.load()
+    with torch.cuda.device(adv.device):
+        stream = C.c_void_p(torch.cuda.current_stream(adv.device).cuda_stream)
+        _lib.check(lib.b200_adv_normalize(adv.numel(), _p(adv), _p(stats), float(eps), stream), "b200_adv_normalize")
+    return adv

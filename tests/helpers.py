@@ -31,6 +31,14 @@ def env_specs():
         "cartpole_gentle": (rlp.CartPole, {}),
         "cartpole_angleonly_env": (rlp.CartPoleAngleOnly, {"variant": "env"}),
         "cartpole_angleonly_ppo2": (rlp.CartPoleAngleOnly, {"variant": "ppo2"}),
+        "fas": (rlp.Flight_Attitude_Simulator, {}),
+        "fas_ppo2": (rlp.Flight_Attitude_Simulator, {"variant": "ppo2"}),
+        "soi": (rlp.SecondOrderIntegration, {}),
+        "soi_dppo2": (rlp.SecondOrderIntegration, {"variant": "dppo2"}),
+        "ballbalancer": (rlp.BallBalancer1D, {}),
+        "twolink": (rlp.TwoLinkManipulator, {}),
+        "ugv_forward": (rlp.UGVForward, {}),
+        "ugv_bidirectional": (rlp.UGVBidirectional, {}),
         "uav_pos": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
         "uav_pos_dis": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
         "uav_pos_crash": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
@@ -106,13 +114,15 @@ def _cmp_fields(name):
     return None
 
 
-def replay(g, backend, resync=False, steps=None, name="", sens_k=1000.0, floor=1e-12):
+def replay(g, backend, resync=False, steps=None, name="", sens_k=1.0e4, floor=1e-12, chaos_cut=1e-10):
     """Run the fixture's actions through `backend`.  Free-running: state carried by the backend, re-injected
     only after the reference's resets.  resync=True: the fixture's state is injected before every step.
 
     Besides the raw worst mixed errors the result carries `worst_ratio`: the worst error divided by the per-lane
     tolerance max(floor, sens_k * running max of the fixture's twin_err), i.e. relative to how far the reference
-    drifts from ITSELF when nudged by 1e-16 per step (its own sensitivity to rounding)."""
+    drifts from ITSELF when nudged by one ulp per step (its own sensitivity to rounding).  Once that self-drift of a
+    lane exceeds `chaos_cut` the episode is no longer reproducible even by the reference (chaotic two-link arm,
+    open-loop-unstable cart-pole): the lane is skipped until its next reset, where the state is re-injected."""
     T, L = g["reward"].shape
     if steps:
         T = min(T, steps)
@@ -135,16 +145,18 @@ def replay(g, backend, resync=False, steps=None, name="", sens_k=1000.0, floor=1
         if "twin_err" in g:
             run_sens = np.maximum(run_sens, g["twin_err"][t])
         tol = np.maximum(floor, sens_k * run_sens)
+        live = (run_sens <= chaos_cut) | resync
         for k in ("obs", "next_obs", "reward", "state"):
             a, b = out[k], g[k][t]
             if k == "state" and nf:
                 a, b = a[:, :nf], b[:, :nf]
-            worst[k] = max(worst[k], mixed_err(a, b))
-            if k != "obs":
-                worst_ratio = max(worst_ratio, float(np.max(lane_err(np.asarray(a, np.float64), b) / tol)))
+            if live.any():
+                worst[k] = max(worst[k], mixed_err(np.asarray(a)[live], np.asarray(b)[live]))
+                if k != "obs":
+                    worst_ratio = max(worst_ratio, float(np.max((lane_err(np.asarray(a, np.float64), b) / tol)[live])))
         worst["time"] = max(worst["time"], float(np.max(np.abs(out["time"] - g["time"][t]))))
-        fm = int(np.sum(out["flag"] != g["flag"][t]))
-        dm = int(np.sum(out["done"] != g["done"][t]))
+        fm = int(np.sum((out["flag"] != g["flag"][t])[live]))
+        dm = int(np.sum((out["done"] != g["done"][t])[live]))
         if (fm or dm) and first_bad is None:
             first_bad = (t, out["flag"].tolist(), g["flag"][t].tolist())
         flag_mismatch += fm
@@ -175,6 +187,8 @@ ENGINE_TOL = {
     "cartpole": 1e-9, "cartpole_gentle": 1e-9, "cartpole_angleonly_env": 1e-9, "cartpole_angleonly_ppo2": 1e-9,
     "uav_pos": 1e-9, "uav_pos_dis": 1e-9, "uav_pos_crash": 1e-9, "uav_pos_edge": 1e-9,
     "uav_att": 1e-9, "uav_att_rand": 1e-9, "uav_att_edge": 1e-9,
+    "fas": 1e-9, "fas_ppo2": 1e-9, "soi": 1e-9, "soi_dppo2": 1e-9, "ballbalancer": 1e-9, "twolink": 1e-7,
+    "ugv_forward": 1e-9, "ugv_bidirectional": 1e-9,
 }
 
 
