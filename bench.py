@@ -36,14 +36,21 @@ ALGO_BYTES = {
     "uav_pos": (21 * 2 + 12 + 12 + 8 + 2 + 6 + 1) * 8 + 5,
     "uav_att": (9 * 2 + 12 + 9 + 8 + 2 + 6 + 1) * 8 + 5,
     "cartpole": (4 * 2 + 1 + 2 + 4 + 1) * 8 + 5,
+    # ugvo: 5 kinematic states R+W, target + n_obs + 16 obstacles R, 2 actions, time R+W, obs 41 + next_obs 41 + reward W
+    "ugvo": (5 * 2 + 3 + 48 + 2 + 2 + 41 + 41 + 1) * 8 + 5,
+    "soi": (4 * 2 + 2 + 2 + 4 + 4 + 1) * 8 + 5,
+    "fas": (2 * 2 + 1 + 2 + 2 + 2 + 1) * 8 + 5,
 }
 # algorithmic fp64 work per env-step (weighted flops, SURVEY.md section 8d convention), used for the fp64-pipe view
-ALGO_FLOPS = {"uav_pos": 5100.0, "uav_att": 3300.0, "cartpole": 3100.0}
+ALGO_FLOPS = {"uav_pos": 5100.0, "uav_att": 3300.0, "cartpole": 3100.0, "ugvo": 54000.0, "soi": 125.0, "fas": 570.0}
 
 WORKLOADS = {
     "uav_pos": dict(n=1 << 20, desc="UavFntsmcParam position tracking, dt=0.02, time_max=10, 8 gains~U(0,5)/step"),
     "uav_att": dict(n=1 << 20, desc="UavFntsmcParam attitude tracking, dt=0.02, time_max=10, 8 gains~U(0,3)/step"),
     "cartpole": dict(n=65536, desc="CartPole (angle+position) RK4 time-loop step, force~U(-8,8)"),
+    "ugvo": dict(n=262144, desc="UGVForwardObstacleAvoidance DPPO2 variant, dt=0.05, 15 circles, 37-ray laser x2 scans/step"),
+    "soi": dict(n=1 << 20, desc="SecondOrderIntegration (ENV), RK4 step"),
+    "fas": dict(n=1 << 20, desc="Flight_Attitude_Simulator (PPO2 variant), RK4 time-loop step"),
 }
 
 
@@ -57,6 +64,12 @@ def make_env(workload, n, device, offset, dtype=torch.float64, host_only=False):
         return rlp.UavAttCtrlRL(random_trajectory=True, **kw)
     if workload == "cartpole":
         return rlp.CartPole(**kw)
+    if workload == "ugvo":
+        return rlp.UGVForwardObstacleAvoidance(variant="dppo2", **kw)
+    if workload == "soi":
+        return rlp.SecondOrderIntegration(**kw)
+    if workload == "fas":
+        return rlp.Flight_Attitude_Simulator(variant="ppo2", **kw)
     raise SystemExit(f"unknown workload {workload}")
 
 

@@ -215,6 +215,33 @@ typedef struct b200_ugv_params {
 } b200_ugv_params;
 #define B200_UGV_STATE_FIELDS 5         /* x, y, vel, phi, omega */
 
+/* UGVForwardObstacleAvoidance (B200ENV_UGVO): environment/UGVForwardObstacleAvoidance/UGVForwardObstacleAvoidance.py:11-557
+ * + map.py:65-80,120-174.  variant 0 = that file; variant 1 = the PPO2/DPPO2 demo copies
+ * (demonstration/DPPO2/DPPO2-4-UGVForwardObstacleAvoidance/UGVForwardObstacleAvoidance.py: dt = 0.05, progress reward
+ * :449-473, is_success ignores omega :421-427, rk44 freezes the pose when the PREVIOUS vel < 0 :488-509). */
+typedef struct b200_ugvo_params {
+    double map_x, map_y;
+    double dt, time_max, kf, kt;                 /* :42-47 */
+    double e_max, v_max, e_phi_max, omega_max, static_gain; /* :58-63,71 */
+    double r_vehicle;                            /* :38 */
+    double laser_dis, laser_blind, laser_range;  /* :49-51 */
+    double Q_pos, Q_vel, Q_phi, Q_omega;         /* :452-455 (variant 0) */
+    double safety_dis_obs, safety_dis_st, r_min, r_max, st_margin; /* reset: :529-537, map.py:67 */
+    int32_t n_rays;                              /* laserState = int(2 * range / step) + 1 = 37   :53 */
+    int32_t obs_num;                             /* obstacles drawn at reset (10 ENV/PPO2, 15 DPPO2), <= B200_UGVO_MAX_OBS */
+    int32_t variant;
+    int32_t pad_;
+} b200_ugvo_params;
+#define B200_UGVO_MAX_OBS 16
+#define B200_UGVO_MAX_RAYS 37
+/* state fields: x y vel phi omega | target_x target_y | n_obs | (cx, cy, r) x B200_UGVO_MAX_OBS */
+#define B200_UGVO_STATE_FIELDS (8 + 3 * B200_UGVO_MAX_OBS)
+/* Reset draws (Philox4x32-10 block index = counter word 3; two doubles per block):
+ *   block 0: start;  blocks 1..64: target candidates (first with |t - s| >= safety_dis_st);  block 100: phi0;
+ *   obstacle k, candidate c: blocks 1000 + 2 * (2048 k + c) (centre) and + 1 (radius).  Candidates are tried in index
+ *   order, at most 2048 per obstacle (the reference retries without bound, map.py:171-172); if none is legal the map
+ *   keeps the obstacles placed so far. */
+
 /* ---------------------------------------------------------------- queries */
 
 /* sizes of the SoA arrays of one env family/variant; any out pointer may be NULL */

@@ -19,6 +19,7 @@ DECL(soi)
 DECL(ballbalancer)
 DECL(twolink)
 DECL(ugv)
+DECL(ugvo)
 
 static step_one_fn step_of(int env_id) {
     switch (env_id) {
@@ -30,6 +31,7 @@ static step_one_fn step_of(int env_id) {
     case B200ENV_BALLBALANCER: return orc_ballbalancer_step_one;
     case B200ENV_TWOLINK: return orc_twolink_step_one;
     case B200ENV_UGV: return orc_ugv_step_one;
+    case B200ENV_UGVO: return orc_ugvo_step_one;
     default: return 0;
     }
 }
@@ -43,6 +45,7 @@ static reset_one_fn reset_of(int env_id) {
     case B200ENV_BALLBALANCER: return orc_ballbalancer_reset_one;
     case B200ENV_TWOLINK: return orc_twolink_reset_one;
     case B200ENV_UGV: return orc_ugv_reset_one;
+    case B200ENV_UGVO: return orc_ugvo_reset_one;
     default: return 0;
     }
 }

@@ -459,3 +459,57 @@ REGISTRY.update({
     "ugv_forward": (UgvForwardA, 4, 1100, 37),
     "ugv_bidirectional": (UgvBidirectionalA, 4, 1100, 38),
 })
+
+
+# ------------------------------------------------------------- UGVForwardObstacleAvoidance
+class UgvoA(Adapter):
+    name = "ugvo"
+    cites = "environment/UGVForwardObstacleAvoidance/UGVForwardObstacleAvoidance.py:261-557, map.py:65-174"
+    F, S, A, D = 56, 41, 2, 0
+    action_lo, action_hi = np.array([-3., -2 * np.pi]), np.array([3., 2 * np.pi])
+    perturb_attrs = ("vel", "phi", "omega")
+
+    def make(self):
+        R.use_family("UGVForwardObstacleAvoidance")
+        return R.load("UGVForwardObstacleAvoidance").UGVForwardObstacleAvoidance()
+
+    def internal(self, env):
+        s = [env.pos[0], env.pos[1], env.vel, env.phi, env.omega, env.target[0], env.target[1], float(len(env.obs))]
+        for k in range(16):
+            if k < len(env.obs):
+                s += [env.obs[k][1][0], env.obs[k][1][1], env.obs[k][2][0]]
+            else:
+                s += [0., 0., 0.]
+        return np.array(s, dtype=float), float(env.time)
+
+    def reset(self, env):
+        env.reset(True)
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 2 == 0:
+            return np.array([rng.uniform(0.0, 3.0), rng.uniform(-2.0, 2.0)])  # drives around: collisions, out of map
+        e, ephi = env.get_e(), env.get_e_phi()  # go-to-goal (may hit obstacles on the way)
+        a_lin = 2.0 * abs(e) * np.cos(ephi) - 2.5 * env.vel
+        a_ang = 6.0 * ephi - 4.0 * env.omega
+        return np.clip(np.array([a_lin, a_ang]) + rng.uniform(-0.02, 0.02, 2), self.action_lo, self.action_hi)
+
+
+class UgvoDPPO2A(UgvoA):
+    name = "ugvo_dppo2"
+    cites = "demonstration/DPPO2/DPPO2-4-UGVForwardObstacleAvoidance/UGVForwardObstacleAvoidance.py:259-555"
+
+    def make(self):
+        R.use_family("UGVForwardObstacleAvoidance")
+        m = R.load_file("demonstration/DPPO2/DPPO2-4-UGVForwardObstacleAvoidance/UGVForwardObstacleAvoidance.py", "ref_ugvo_dppo2")
+        return m.UGVForwardObstacleAvoidance()
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 2 == 0:  # includes braking below zero: exercises the pre-update `vel < 0` freeze (note N9)
+            return np.array([rng.uniform(-3.0, 3.0), rng.uniform(-2.0, 2.0)])
+        return super().sample_action(rng, t, 1, env)
+
+
+REGISTRY.update({
+    "ugvo": (UgvoA, 4, 300, 41),
+    "ugvo_dppo2": (UgvoDPPO2A, 4, 400, 42),
+})

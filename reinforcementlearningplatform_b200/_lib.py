@@ -86,7 +86,12 @@ UgvParams = _struct("UgvParams", "struct b200_ugv_params", (
     "map_x", "map_y", "target_x", "target_y", "dt", "time_max", "kf", "kt", "e_max", "v_max", "e_phi_max", "omega_max",
     "static_gain", "Q_pos", "Q_vel", "Q_phi", "Q_omega", "reset_d0"), ("bidirectional", "pad_"))
 
-PARAMS_OF = {CARTPOLE: CartPoleParams, UAV_ATT: UavParams, UAV_POS: UavParams, FAS: FasParams, SOI: SoiParams,
+UgvoParams = _struct("UgvoParams", "struct b200_ugvo_params", (
+    "map_x", "map_y", "dt", "time_max", "kf", "kt", "e_max", "v_max", "e_phi_max", "omega_max", "static_gain",
+    "r_vehicle", "laser_dis", "laser_blind", "laser_range", "Q_pos", "Q_vel", "Q_phi", "Q_omega", "safety_dis_obs",
+    "safety_dis_st", "r_min", "r_max", "st_margin"), ("n_rays", "obs_num", "variant", "pad_"))
+
+PARAMS_OF = {UGVO: UgvoParams, CARTPOLE: CartPoleParams, UAV_ATT: UavParams, UAV_POS: UavParams, FAS: FasParams, SOI: SoiParams,
              BALLBALANCER: BallBalancerParams, TWOLINK: TwoLinkParams, UGV: UgvParams}
 
 _lib = None

@@ -182,3 +182,4 @@ B200_FAMILY_DECL(soi)
 B200_FAMILY_DECL(ballbalancer)
 B200_FAMILY_DECL(twolink)
 B200_FAMILY_DECL(ugv)
+B200_FAMILY_DECL(ugvo)

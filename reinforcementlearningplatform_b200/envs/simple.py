@@ -185,3 +185,51 @@ class UGVForward(_Simple):
 class UGVBidirectional(UGVForward):
     """environment/UGV/UGVBidirectional.py:10-367 (signed position error, folded heading error, no v >= 0 clamp)."""
     BIDIRECTIONAL = 1
+
+
+class UGVForwardObstacleAvoidance(_Simple):
+    """environment/UGVForwardObstacleAvoidance/UGVForwardObstacleAvoidance.py:11-557 (``variant='env'``: dt = 0.1, 10
+    circles) or the PPO2 / DPPO2 demo copies (``variant='ppo2'``: dt = 0.05, 10 circles; ``'dppo2'``: 15 circles;
+    progress reward, success ignores omega, pose frozen when the previous velocity was negative).  Observation =
+    4 kinematic terms + 37 fake-laser ranges (kernel K-UGVO: one warp per instance, lanes = rays)."""
+    ENV_ID = _lib.UGVO
+    MAX_OBS = 16
+    STATE_FIELDS = tuple(["x", "y", "vel", "phi", "omega", "target_x", "target_y", "n_obs"] +
+                         [f"{c}_{k}" for k in range(16) for c in ("cx", "cy", "r")])
+
+    def __init__(self, n_envs: int = 1, map_size=(5.0, 5.0), variant: str = 'env', obsNum: int = None, **kw):
+        if variant not in ('env', 'ppo2', 'dppo2'):
+            raise ValueError("variant must be 'env', 'ppo2' or 'dppo2'")
+        self.name = 'UGVForwardObstacleAvoidance'
+        self._variant = variant
+        self.map_size = np.array(map_size, dtype=float)
+        self.r_vehicle = 0.15                                  # :38
+        self.dt = 0.1 if variant == 'env' else 0.05            # :42 / demo copy :40
+        self.time_max, self.kf, self.kt = 15.0, 0.1, 0.1       # :44-47
+        self.laserDis, self.laserBlind = 2.0, 0.0              # :49-50
+        self.laserRange, self.laserStep = deg2rad(90), deg2rad(5)   # :51-52
+        self.laserState = int(2 * self.laserRange / self.laserStep) + 1   # :53  (= 37)
+        self.e_max = np.linalg.norm(self.map_size) / 2         # :58
+        self.v_max, self.e_phi_max, self.omega_max = 3, np.pi, 2 * np.pi
+        self.a_linear_max, self.a_angular_max = 3, 2 * np.pi
+        self.static_gain = 1.
+        self.obsNum = obsNum if obsNum is not None else (15 if variant == 'dppo2' else 10)   # reset() :535 / demo :543
+        if not 0 < self.obsNum <= self.MAX_OBS:
+            raise ValueError("obsNum must be in 1..16")
+        super().__init__(n_envs, **kw)
+        self.action_range = np.array([[-self.a_linear_max, self.a_linear_max], [-self.a_angular_max, self.a_angular_max]])
+        self.use_norm = True
+
+    def make_params(self):
+        p = _lib.UgvoParams()
+        p.map_x, p.map_y = self.map_size
+        p.dt, p.time_max, p.kf, p.kt = self.dt, self.time_max, self.kf, self.kt
+        p.e_max, p.v_max, p.e_phi_max, p.omega_max = float(self.e_max), self.v_max, self.e_phi_max, self.omega_max
+        p.static_gain, p.r_vehicle = self.static_gain, self.r_vehicle
+        p.laser_dis, p.laser_blind, p.laser_range = self.laserDis, self.laserBlind, self.laserRange
+        p.Q_pos, p.Q_vel, p.Q_phi, p.Q_omega = 2., 0.0, 2., 1.0            # :452-455
+        p.safety_dis_obs = p.safety_dis_st = 4 * self.r_vehicle             # :531-532
+        p.r_min, p.r_max, p.st_margin = 0.2, 0.5, 0.3                       # :533-534, map.py:67
+        p.n_rays, p.obs_num = self.laserState, self.obsNum
+        p.variant = 0 if self._variant == 'env' else 1
+        return p

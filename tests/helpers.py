@@ -39,6 +39,8 @@ def env_specs():
         "twolink": (rlp.TwoLinkManipulator, {}),
         "ugv_forward": (rlp.UGVForward, {}),
         "ugv_bidirectional": (rlp.UGVBidirectional, {}),
+        "ugvo": (rlp.UGVForwardObstacleAvoidance, {}),
+        "ugvo_dppo2": (rlp.UGVForwardObstacleAvoidance, {"variant": "dppo2"}),
         "uav_pos": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
         "uav_pos_dis": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
         "uav_pos_crash": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
@@ -105,6 +107,8 @@ class EngineBackend:
 # leading state fields that are compared; the trailing ones are "lazy" (only written on terminal steps, see
 # include/b200env.h: ref/dot_ref of the attitude env, pos_ref/dot_pos_ref of the position env)
 STATE_CMP = {"uav_pos": 45, "uav_att": 30}
+# chaotic plants (random torques on a double pendulum): compare one step at a time, re-syncing the engine from the oracle
+RESYNC_EVERY_STEP = {"twolink"}
 
 
 def _cmp_fields(name):
@@ -114,7 +118,7 @@ def _cmp_fields(name):
     return None
 
 
-def replay(g, backend, resync=False, steps=None, name="", sens_k=1.0e4, floor=1e-12, chaos_cut=1e-11):
+def replay(g, backend, resync=False, steps=None, name="", sens_k=None, floor=1e-12, chaos_cut=1e-11):
     """Run the fixture's actions through `backend`.  Free-running: state carried by the backend, re-injected
     only after the reference's resets.  resync=True: the fixture's state is injected before every step.
 
@@ -126,6 +130,7 @@ def replay(g, backend, resync=False, steps=None, name="", sens_k=1.0e4, floor=1e
     T, L = g["reward"].shape
     if steps:
         T = min(T, steps)
+    sens_k = sens_k or (1.0e6 if name in RESYNC_EVERY_STEP else 1.0e4)  # chaotic plants: errors grow like e^(lambda t)
     has_dis = "dis" in g
     nf = _cmp_fields(name)
     backend.set_state(g["state0"], g["time0"])
@@ -188,12 +193,8 @@ ENGINE_TOL = {
     "uav_pos": 1e-7, "uav_pos_dis": 1e-9, "uav_pos_crash": 1e-9, "uav_pos_edge": 1e-9,
     "uav_att": 1e-9, "uav_att_rand": 1e-9, "uav_att_edge": 1e-9,
     "fas": 1e-9, "fas_ppo2": 1e-9, "soi": 1e-9, "soi_dppo2": 1e-9, "ballbalancer": 1e-9, "twolink": 1e-5,
-    "ugv_forward": 1e-9, "ugv_bidirectional": 1e-9,
+    "ugv_forward": 1e-9, "ugv_bidirectional": 1e-9, "ugvo": 1e-9, "ugvo_dppo2": 1e-9,
 }
-
-
-# chaotic plants (random torques on a double pendulum): compare one step at a time, re-syncing the engine from the oracle
-RESYNC_EVERY_STEP = {"twolink"}
 
 
 def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None):

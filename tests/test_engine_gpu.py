@@ -10,6 +10,12 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN_CASES = sorted(ENGINE_TOL)
 
+# One-step bar is 1e-12 except for the fake laser: the reference's line/circle intersection
+# (UGVForwardObstacleAvoidance.py:360-364) works with the slope m = tan(phi), |m| up to 1e16 on near-vertical rays, and
+# loses ~eps * m^2 there, so a 1-ulp difference between numpy's and CUDA's tan() moves a range by up to ~1e-10 (the
+# reference itself moves as much under a 1-ulp nudge: fixture twin_err).  Kinematic state, reward and flags stay exact.
+ONE_STEP_TOL = {"ugvo": 1e-9, "ugvo_dppo2": 1e-9}
+
 # Fixtures whose actions were recorded from a closed loop around an open-loop-unstable plant: replaying them
 # open loop amplifies a 1-ulp difference by e^(lambda*t) (inverted pendulum: lambda ~ 6/s, 5 s episodes -> 1e13),
 # so only the one-step (re-sync) comparison is meaningful.  The C oracle still matches them bit-exactly.
@@ -24,7 +30,7 @@ def test_engine_matches_reference_fixture_resync(name):
     assert res["flag_mismatch"] == 0 and res["done_mismatch"] == 0, res
     assert res["worst"]["time"] == 0.0, res
     for k, v in res["worst"].items():
-        assert v <= 1e-12, (k, res)
+        assert v <= ONE_STEP_TOL.get(name, 1e-12), (k, res)
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
