@@ -197,7 +197,7 @@ ENGINE_TOL = {
 }
 
 
-def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None):
+def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None, offset=0):
     """Step the CUDA engine and the C oracle side by side from the same Philox reset with the same random actions.
     Auto-reset uses the same counter-based draws on both sides, so trajectories stay comparable across episodes.
     Returns the worst mixed error over obs/next_obs/reward/state and the number of flag mismatches."""
@@ -206,9 +206,10 @@ def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None
     from reinforcementlearningplatform_b200 import _lib
     cls, kw = env_specs()[name]
     dtype = dtype or torch.float64
-    env = cls(n_envs=n, device="cuda", dtype=dtype, seed=seed, auto_reset=auto_reset, **kw)
+    env = cls(n_envs=n, device="cuda", dtype=dtype, seed=seed, auto_reset=auto_reset, env_index_offset=offset, **kw)
     sf, od, ad, dd = _lib.dims(cls.ENV_ID, env.VARIANT)
-    orc = oracle.OracleEnv(cls.ENV_ID, env._params, n, sf, od, ad, dd, seed=seed, auto_reset=auto_reset, nthreads=8)
+    orc = oracle.OracleEnv(cls.ENV_ID, env._params, n, sf, od, ad, dd, seed=seed, auto_reset=auto_reset, nthreads=8,
+                           env_index_offset=offset)
     env.reset(True)
     orc.reset()
     torch.cuda.synchronize()

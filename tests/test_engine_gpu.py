@@ -55,3 +55,11 @@ def test_engine_vs_oracle_random(name, oracle_lib):
     assert res["worst"] <= res["tol"], res
     if name.startswith("cartpole") and name != "cartpole_gentle":
         assert res["terminals"] > 0, res  # episodes are short: the Philox auto-reset path is exercised
+
+
+@pytest.mark.parametrize("name", ["cartpole", "uav_pos", "ugvo_dppo2"])
+def test_engine_vs_oracle_sharded_offset(name, oracle_lib):
+    """a shard that starts at a non-zero global instance index draws the resets of THOSE instances (multi-GPU contract)"""
+    res = engine_vs_oracle(name, n=1000, steps=40, seed=11, offset=(1 << 33) + 12345)
+    assert res["flag_mismatch"] == 0, res
+    assert res["worst"] <= res["tol"], res
