@@ -1,6 +1,7 @@
 """B200-native batched environment engine for the environment-step hot path of
 HKPolyU-UAV/ReinforcementLearningPlatform (include/b200env.h)."""
 from . import _lib  # noqa: F401
+from . import dist, gae  # noqa: F401
 from .vec_env import VecEnvBase  # noqa: F401
 from .envs.cartpole import CartPole, CartPoleAngleOnly  # noqa: F401
 from .envs.simple import (BallBalancer1D, Flight_Attitude_Simulator, SecondOrderIntegration,  # noqa: F401
