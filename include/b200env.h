@@ -242,6 +242,37 @@ typedef struct b200_ugvo_params {
  *   order, at most 2048 per obstacle (the reference retries without bound, map.py:171-172); if none is legal the map
  *   keeps the obstacles placed so far. */
 
+/* UavRobust (B200ENV_UAVROBUST): the same quadrotor (environment/UavRobust/uav.py:429-560) wrapped as four RL envs.
+ * variant 0 uav_hover_outer_loop   UavHoverOuterLoop.py:81-196    obs 6, action = virtual acceleration (3), inner loop by FNTSMC
+ * variant 1 uav_hover              UavHover.py:101-226            obs 12, action = acceleration (3) + torque (3)
+ * variant 2 uav_inner_loop         UavInnerLoop.py:88-210         obs 6, action = torque (3), attitude only
+ * variant 3 uav_tracking_outer_loop UavTrackingOuterLoop.py:90-255 obs 6, action = virtual acceleration (3), sinusoidal reference
+ * Inner-loop FNTSMC with torque saturation: UavRobust/FNTSMC.py:80-106. */
+typedef struct b200_uavrobust_params {
+    double m, g, J[3], kr, kt;
+    double dt, time_max, t_term;            /* t_term = time_max - dt / 2                   uav.py:545 */
+    double pos_zone_min[3], pos_zone_max[3];/* no margins here                              uav.py:511-525 */
+    double att_zone_min[3], att_zone_max[3];/*                                              uav.py:527-541 */
+    double pos0[3], vel0[3], angle0[3], pqr0[3]; /* reset state (here pqr0 IS used)         UavHover.py:178-189 */
+    double att_k1[3], att_k2[3], att_alpha[3], att_beta[3], att_gamma[3], att_lmd[3], att_saturation[3];
+    double e_pos_span[3];                   /* e_pos_max - e_pos_min                        UavHover.py:38-39 */
+    double vel_span[3];                     /* vel_max - vel_min  (e_vel_max - e_vel_min)   UavHover.py:40-41 */
+    double e_att_span[3];                   /* e_att_max - e_att_min                        UavHover.py:47-48 */
+    double e_dot_att_span_neg[3];           /* e_dot_att_min - e_dot_att_max  (sic, N10)    UavHover.py:109, UavInnerLoop.py:94 */
+    double dot_att_min[3], dot_att_max[3];  /* reference-rate limits                        UavHover.py:42-43 */
+    double static_gain;
+    double Qx, Qv, R;                       /* reward weights (get_reward locals) */
+    double ref_bias_a[3];                   /* tracking: centre of pos_zone; inner loop: zeros */
+    double target_lo[3], target_hi[3];      /* hover: pos_ref ~ U(zone_min + 1, zone_max - 1)   UavHover.py:224-226 */
+    double sig_A_hi[3];                     /* random reference amplitude upper bounds (variants 2, 3) */
+    double sig_T_lo, sig_T_hi, sig_phase_hi;/* U(3,6) / U(5,10); U(0, pi/2) */
+    double init_pos_r;                      /* tracking: initial position within +-0.3 of the trajectory start */
+    int32_t variant;
+    int32_t pad_;
+} b200_uavrobust_params;
+/* state fields: x y z vx vy vz phi theta psi p q r | s1[3] | att_ref[3] | dot_att_ref[3] | pos_ref[3] | A[3] T[3] phase[3] */
+#define B200_UAVROBUST_STATE_FIELDS 33
+
 /* ---------------------------------------------------------------- queries */
 
 /* sizes of the SoA arrays of one env family/variant; any out pointer may be NULL */

@@ -20,6 +20,7 @@ DECL(ballbalancer)
 DECL(twolink)
 DECL(ugv)
 DECL(ugvo)
+DECL(uavrobust)
 
 static step_one_fn step_of(int env_id) {
     switch (env_id) {
@@ -32,6 +33,7 @@ static step_one_fn step_of(int env_id) {
     case B200ENV_TWOLINK: return orc_twolink_step_one;
     case B200ENV_UGV: return orc_ugv_step_one;
     case B200ENV_UGVO: return orc_ugvo_step_one;
+    case B200ENV_UAVROBUST: return orc_uavrobust_step_one;
     default: return 0;
     }
 }
@@ -46,6 +48,7 @@ static reset_one_fn reset_of(int env_id) {
     case B200ENV_TWOLINK: return orc_twolink_reset_one;
     case B200ENV_UGV: return orc_ugv_reset_one;
     case B200ENV_UGVO: return orc_ugvo_reset_one;
+    case B200ENV_UAVROBUST: return orc_uavrobust_reset_one;
     default: return 0;
     }
 }

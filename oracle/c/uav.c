@@ -478,3 +478,222 @@ void orc_uav_pos_reset_one(const void *params, const oracle_io *io, int64_t n, i
         for (int k = 0; k < 6; ++k) io->next_obs[(int64_t)k * n + i] = o[k];
     }
 }
+
+/* ==================================================================================================================
+ * UavRobust: environment/UavRobust/{uav.py:429-560, FNTSMC.py:80-106, uav_pos_ctrl.py:41-76, uav_att_ctrl.py:19-46,
+ * UavHoverOuterLoop.py, UavHover.py, UavInnerLoop.py, UavTrackingOuterLoop.py}.  The quadrotor ODE / RK4 / f1 / f2 / F
+ * are the same code as UavFntsmcParam's, so the static helpers above are reused through a b200_uav_params shim.
+ * ================================================================================================================== */
+typedef b200_uavrobust_params RP;
+enum { R_S1 = 12, R_AREF = 15, R_DAREF = 18, R_PREF = 21, R_AMP = 24, R_PER = 27, R_PHS = 30 };
+
+static void rp_shim(const RP *r, P *p) {
+    memset(p, 0, sizeof(*p));
+    p->m = r->m; p->g = r->g; p->kr = r->kr; p->kt = r->kt; p->dt = r->dt; p->time_max = r->time_max;
+    for (int k = 0; k < 3; ++k) p->J[k] = r->J[k];
+}
+
+static int rob_pos_out(const RP *r, const uav_t *u) { /* uav.py:511-525 */
+    int f = 0;
+    for (int k = 0; k < 3; ++k) if (u->x[k] < r->pos_zone_min[k] || u->x[k] > r->pos_zone_max[k]) f = 1;
+    return f;
+}
+static int rob_att_out(const RP *r, const uav_t *u) { /* uav.py:527-541 */
+    int f = 0;
+    for (int k = 0; k < 3; ++k) if (u->x[6 + k] < r->att_zone_min[k] || u->x[6 + k] > r->att_zone_max[k]) f = 1;
+    return f;
+}
+static double sqn(const double *v, int n) { /* np.linalg.norm(v) ** 2 */
+    double s = 0;
+    for (int k = 0; k < n; ++k) s += v[k] * v[k];
+    return pow(sqrt(s), 2.0);
+}
+static double sqn_tanh10(const double *v, int n) { /* np.linalg.norm(np.tanh(10 * v)) ** 2 */
+    double t[6];
+    for (int k = 0; k < n; ++k) t[k] = tanh(10 * v[k]);
+    return sqn(t, n);
+}
+
+static void rob_observe(const RP *r, const P *p, const uav_t *u, const oracle_io *io, int64_t n, int64_t i, double *o) {
+    double f1[3][3], d1[3];
+    uav_f1(u, f1);
+    mat3_vec(f1, u->x + 9, d1); /* dot_rho1 */
+    const double g = r->static_gain;
+    if (r->variant == 0 || r->variant == 1) { /* UavHoverOuterLoop.py:81-92, UavHover.py:101-114 */
+        for (int k = 0; k < 3; ++k) {
+            o[k] = (u->x[k] - SF(R_PREF + k)) / r->e_pos_span[k] * g;
+            o[3 + k] = 2 * u->x[3 + k] / r->vel_span[k] * g;
+        }
+        if (r->variant == 1)
+            for (int k = 0; k < 3; ++k) {
+                o[6 + k] = (u->x[6 + k] - SF(R_AREF + k)) / r->e_att_span[k] * g;
+                o[9 + k] = (d1[k] - SF(R_DAREF + k)) / r->e_dot_att_span_neg[k] * g;
+            }
+    } else if (r->variant == 2) { /* UavInnerLoop.py:88-99 */
+        double A[3], T[3], ph[3], z3[3] = {0, 0, 0}, ref[3], dref[3], ddref[3];
+        for (int k = 0; k < 3; ++k) { A[k] = SF(R_AMP + k); T[k] = SF(R_PER + k); ph[k] = SF(R_PHS + k); }
+        ref_cmd(3, u->time, A, T, z3, ph, ref, dref, ddref);
+        for (int k = 0; k < 3; ++k) {
+            o[k] = (u->x[6 + k] - ref[k]) / r->e_att_span[k] * g;
+            o[3 + k] = (d1[k] - dref[k]) / r->e_dot_att_span_neg[k] * g;
+        }
+    } else { /* UavTrackingOuterLoop.py:90-101 */
+        double A[3], T[3], ph[3], ref[3], dref[3], ddref[3];
+        for (int k = 0; k < 3; ++k) { A[k] = SF(R_AMP + k); T[k] = SF(R_PER + k); ph[k] = SF(R_PHS + k); }
+        ref_cmd(3, u->time, A, T, r->ref_bias_a, ph, ref, dref, ddref);
+        for (int k = 0; k < 3; ++k) {
+            o[k] = (u->x[k] - ref[k]) / r->e_pos_span[k] * g;
+            o[3 + k] = (u->x[3 + k] - dref[k]) / r->vel_span[k] * g;
+        }
+    }
+}
+
+static void rob_reset(const RP *r, const oracle_io *io, int64_t n, int64_t i, uint64_t seed, int64_t off) {
+    uint32_t ep = io->episode[i];
+    orc_rng g;
+    orc_rng_init(&g, seed, (uint64_t)(off + i), ep);
+    for (int k = 0; k < 3; ++k) { SF(k) = r->pos0[k]; SF(3 + k) = r->vel0[k]; SF(6 + k) = r->angle0[k]; SF(9 + k) = r->pqr0[k]; }
+    if (r->variant == 0 || r->variant == 1) { /* generate_random_point(offset = 1.0) */
+        for (int k = 0; k < 3; ++k) SF(R_PREF + k) = orc_uniform(&g, r->target_lo[k], r->target_hi[k]);
+        if (r->variant == 1) for (int k = 0; k < 3; ++k) SF(R_AREF + k) = 0.; /* UavHover.py:209 */
+    } else { /* generate_random_signal UavInnerLoop.py:197-210 / generate_random_trajectory UavTrackingOuterLoop.py:222-250 */
+        for (int k = 0; k < 3; ++k) SF(R_AMP + k) = orc_uniform(&g, 0., r->sig_A_hi[k]);
+        for (int k = 0; k < 3; ++k) SF(R_PER + k) = orc_uniform(&g, r->sig_T_lo, r->sig_T_hi);
+        for (int k = 0; k < 3; ++k) SF(R_PHS + k) = orc_uniform(&g, 0., r->sig_phase_hi);
+        if (r->variant == 3) /* set_random_init_pos(trajectory[0], 0.3): trajectory[0] = bias + A sin(phase) */
+            for (int k = 0; k < 3; ++k) {
+                double t0 = r->ref_bias_a[k] + SF(R_AMP + k) * sin(2 * M_PI / SF(R_PER + k) * 0. + SF(R_PHS + k));
+                SF(k) = orc_uniform(&g, t0 - fabs(r->init_pos_r), t0 + fabs(r->init_pos_r));
+            }
+    }
+    /* the FNTSMC integrator s1 (and att_ref / dot_att_ref except where noted) survive the reference's reset() */
+    io->time[i] = 0.;
+    io->episode[i] = ep + 1u;
+}
+
+void orc_uavrobust_step_one(const void *params, const oracle_io *io, int64_t n, int64_t i, uint32_t flags, uint64_t seed, int64_t off) {
+    const RP *r = (const RP *)params;
+    P p;
+    rp_shim(r, &p);
+    const int V = r->variant, S = V == 1 ? 12 : 6, AD = V == 1 ? 6 : 3;
+    uav_t u;
+    for (int k = 0; k < 12; ++k) u.x[k] = SF(k);
+    u.time = io->time[i];
+    double a[6], dis[3] = {0, 0, 0};
+    for (int k = 0; k < AD; ++k) a[k] = io->action[(int64_t)k * n + i];
+    if (io->dis) for (int k = 0; k < 3; ++k) dis[k] = io->dis[(int64_t)k * n + i];
+    double cur[12], nxt[12];
+    rob_observe(r, &p, &u, io, n, i, cur);
+    if (V == 2) { /* UavInnerLoop.py:127-142 + uav_att_ctrl.py:33-46 */
+        double act4[4] = {0, a[0], a[1], a[2]}, z3[3] = {0, 0, 0};
+        for (int k = 0; k < 6; ++k) u.x[k] = SF(k);
+        uav_rk44(&p, &u, act4, z3, 1);
+    } else {
+        /* uo_2_ref_angle_throttle, uav_pos_ctrl.py:67-76 */
+        const double phi = u.x[6], theta = u.x[7], psi = u.x[8];
+        double uf = (a[2] + p.g) * p.m / (cos(phi) * cos(theta));
+        double asin_phi_d = fmin(fmax((a[0] * sin(psi) - a[1] * cos(psi)) * p.m / uf, -1), 1);
+        double phi_d = asin(asin_phi_d);
+        double asin_theta_d = fmin(fmax((a[0] * cos(psi) + a[1] * sin(psi)) * p.m / (uf * cos(phi_d)), -1), 1);
+        double theta_d = asin(asin_theta_d);
+        phi_d = fmin(fmax(phi_d, r->att_zone_min[0]), r->att_zone_max[0]); /* np.clip */
+        theta_d = fmin(fmax(theta_d, r->att_zone_min[1]), r->att_zone_max[1]);
+        double att_new[3] = {phi_d, theta_d, 0.0}, att_ref[3], dot_att_ref[3];
+        for (int k = 0; k < 3; ++k) {
+            const double old = SF(R_AREF + k);
+            double d = (att_new[k] - old) / p.dt;
+            d = fmin(fmax(d, r->dot_att_min[k]), r->dot_att_max[k]);
+            dot_att_ref[k] = d;
+            att_ref[k] = d * p.dt + old;
+        }
+        double torque[3];
+        if (V == 1) {
+            for (int k = 0; k < 3; ++k) torque[k] = a[3 + k];
+        } else { /* att_control + FNTSMC with saturation, uav_pos_ctrl.py:41-65, FNTSMC.py:80-106 */
+            gains_t ga;
+            double s1[3];
+            for (int k = 0; k < 3; ++k) {
+                ga.k1[k] = r->att_k1[k]; ga.k2[k] = r->att_k2[k]; ga.alpha[k] = r->att_alpha[k]; ga.beta[k] = r->att_beta[k];
+                ga.gamma[k] = r->att_gamma[k]; ga.lmd[k] = r->att_lmd[k];
+                s1[k] = SF(R_S1 + k);
+            }
+            att_control(&p, &u, &ga, s1, att_ref, dot_att_ref, torque);
+            for (int k = 0; k < 3; ++k) {
+                torque[k] = fmin(fmax(torque[k], -r->att_saturation[k]), r->att_saturation[k]);
+                SF(R_S1 + k) = s1[k];
+            }
+        }
+        for (int k = 0; k < 3; ++k) { SF(R_AREF + k) = att_ref[k]; SF(R_DAREF + k) = dot_att_ref[k]; }
+        double act4[4] = {uf, torque[0], torque[1], torque[2]};
+        uav_rk44(&p, &u, act4, dis, 0);
+    }
+    for (int k = 0; k < 12; ++k) SF(k) = u.x[k];
+    io->time[i] = u.time;
+    /* is_episode_Terminal uav.py:543-560 */
+    int flag = 0, done = 0;
+    if (u.time > r->t_term) { flag = 1; done = 1; }
+    const int pout = rob_pos_out(r, &u), aout = rob_att_out(r, &u);
+    if (pout) { flag = 2; done = 1; }
+    if (aout) { flag = 3; done = 1; }
+    rob_observe(r, &p, &u, io, n, i, nxt);
+    /* rewards */
+    double reward;
+    const double Qx = r->Qx, Qv = r->Qv, R = r->R;
+    if (V == 0 || V == 1) { /* UavHoverOuterLoop.py:94-109 / UavHover.py:116-131 */
+        double e[3], v[3] = {u.x[3], u.x[4], u.x[5]};
+        for (int k = 0; k < 3; ++k) e[k] = u.x[k] - SF(R_PREF + k);
+        double r1 = -sqn_tanh10(e, 3) * 0.5 * Qx - sqn(e, 3) * 0.5 * Qx;
+        double r2 = -sqn_tanh10(v, 3) * 0.5 * Qx - sqn(v, 3) * 0.5 * Qv;
+        double r3 = -sqn(a, AD) * R, r4 = 0;
+        if (pout || aout) r4 = -(r->time_max - u.time) / p.dt * (Qx * sqn(e, 3) + Qv * sqn(v, 3) + R * sqn(a, AD));
+        reward = r1 + r2 + r3 + r4;
+    } else { /* UavInnerLoop.py:101-120 / UavTrackingOuterLoop.py:103-120 */
+        double e[3], de[3];
+        const double sc_e = V == 2 ? 1.0 : 1.0;
+        (void)sc_e;
+        /* error / dot_error = un-normalised observation terms */
+        double f1[3][3], d1[3];
+        uav_f1(&u, f1);
+        mat3_vec(f1, u.x + 9, d1);
+        double A[3], T[3], ph[3], z3[3] = {0, 0, 0}, ref[3], dref[3], ddref[3];
+        for (int k = 0; k < 3; ++k) { A[k] = SF(R_AMP + k); T[k] = SF(R_PER + k); ph[k] = SF(R_PHS + k); }
+        ref_cmd(3, u.time, A, T, V == 2 ? z3 : r->ref_bias_a, ph, ref, dref, ddref);
+        for (int k = 0; k < 3; ++k) {
+            e[k] = (V == 2 ? u.x[6 + k] : u.x[k]) - ref[k];
+            de[k] = (V == 2 ? d1[k] : u.x[3 + k]) - dref[k];
+        }
+        double r1 = -sqn(e, 3) * Qx, r2 = -sqn(de, 3) * Qv;
+        r1 -= sqn_tanh10(e, 3) * Qx;
+        r2 -= sqn_tanh10(de, 3) * Qv;
+        double r3 = -sqn(a, 3) * R, r4 = 0;
+        if ((V == 2) ? aout : (pout || aout)) r4 = (r->time_max - u.time) / p.dt * (r1 + r2 + r3);
+        reward = r1 + r2 + r3 + r4;
+    }
+    for (int k = 0; k < S; ++k) {
+        if (io->obs) io->obs[(int64_t)k * n + i] = cur[k];
+        io->next_obs[(int64_t)k * n + i] = nxt[k];
+    }
+    io->reward[i] = reward; io->done[i] = (uint8_t)done; io->flag[i] = flag;
+    if (done && (flags & B200ENV_AUTO_RESET)) {
+        rob_reset(r, io, n, i, seed, off);
+        for (int k = 0; k < 12; ++k) u.x[k] = SF(k);
+        u.time = 0.;
+        rob_observe(r, &p, &u, io, n, i, nxt);
+    }
+    if (io->reset_obs) for (int k = 0; k < S; ++k) io->reset_obs[(int64_t)k * n + i] = nxt[k];
+}
+
+void orc_uavrobust_reset_one(const void *params, const oracle_io *io, int64_t n, int64_t i, uint64_t seed, int64_t off, int observe_only) {
+    const RP *r = (const RP *)params;
+    P p;
+    rp_shim(r, &p);
+    if (!observe_only) rob_reset(r, io, n, i, seed, off);
+    if (io->next_obs) {
+        uav_t u;
+        for (int k = 0; k < 12; ++k) u.x[k] = SF(k);
+        u.time = io->time[i];
+        double o[12];
+        rob_observe(r, &p, &u, io, n, i, o);
+        for (int k = 0; k < (r->variant == 1 ? 12 : 6); ++k) io->next_obs[(int64_t)k * n + i] = o[k];
+    }
+}

@@ -513,3 +513,141 @@ REGISTRY.update({
     "ugvo": (UgvoA, 4, 300, 41),
     "ugvo_dppo2": (UgvoDPPO2A, 4, 400, 42),
 })
+
+
+# ------------------------------------------------------------- UavRobust (own interpreter state: clashing module names)
+def _robust_params():
+    R.use_family("UavRobust")
+    uav = R.load("environment.UavRobust.uav")
+    fn = R.load("environment.UavRobust.FNTSMC")
+    up = uav.uav_param()
+    up.dt, up.time_max = 0.01, 10
+    up.pos_zone = np.atleast_2d([[-5, 5], [-5, 5], [0, 5]])
+    att = fn.fntsmc_param()
+    att.k1 = np.array([25., 25., 40.]); att.k2 = np.array([0.1, 0.1, 0.2]); att.alpha = np.array([2.5, 2.5, 2.5])
+    att.beta = np.array([0.99, 0.99, 0.99]); att.gamma = np.array([1.5, 1.5, 1.2]); att.lmd = np.array([2.0, 2.0, 2.0])
+    att.dim, att.dt, att.ctrl0 = 3, 0.01, np.array([0., 0., 0.])
+    att.saturation = np.array([0.3, 0.3, 0.3])
+    return up, att, fn.fntsmc_param()
+
+
+class _RobustBase(Adapter):
+    F, D = 33, 3
+    perturb_attrs = ("p", "q", "r")
+
+    def reset(self, env):
+        env.reset(random=True)
+
+    def _common(self, env):
+        s1 = env.att_ctrl.s1 if hasattr(env, "att_ctrl") else np.zeros(3)
+        aref = getattr(env, "att_ref", np.zeros(3))
+        daref = getattr(env, "dot_att_ref", np.zeros(3))
+        return env.uav_state_call_back(), s1, aref, daref
+
+    def step(self, env, a, d):
+        if self.D and d is not None and hasattr(env, "dis"):
+            env.dis = np.array(d, dtype=float)
+        env.step_update(np.array(a, dtype=float))
+        return (np.array(env.current_state, dtype=float), np.array(env.next_state, dtype=float),
+                float(env.reward), bool(env.is_terminal), int(env.terminal_flag))
+
+    def sample_dis(self, rng, t, l, env=None):
+        if l % 2 == 0:
+            return np.zeros(3)
+        tt = 0.01 * t  # generate_uncertainty(time, is_ideal=False), UavRobust/ref_cmd.py:46-61
+        w = 2 * np.pi / 4
+        return np.array([0.8 * np.cos(w * tt) + 0.6 * np.sin(w * tt), 0.8 * np.sin(w * tt) + 0.6 * np.cos(w * tt),
+                         0.8 * np.cos(w * tt) + 0.6 * np.sin(w * tt)])
+
+
+class HoverOuterA(_RobustBase):
+    name = "uavr_hover_outer"
+    cites = "environment/UavRobust/UavHoverOuterLoop.py:81-196 (+ uav.py:429-560, FNTSMC.py:80-106, uav_pos_ctrl.py:41-76)"
+    S, A = 6, 3
+
+    def make(self):
+        up, att, pos = _robust_params()
+        m = R.load("environment.UavRobust.UavHoverOuterLoop")
+        return m.uav_hover_outer_loop(up, pos, att, np.array([1.0, -1.0, 2.0]))
+
+    def internal(self, env):
+        x, s1, aref, daref = self._common(env)
+        return np.concatenate((x, s1, aref, daref, env.pos_ref, np.zeros(9))).astype(float), float(env.time)
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 3 == 0:
+            return rng.uniform(-8, 8, 3)  # wild accelerations: position / attitude out
+        e = env.uav_pos() - env.pos_ref    # PD hover controller + noise: reaches the time-out flag
+        return np.clip(-2.0 * e - 2.5 * env.uav_vel() + rng.uniform(-0.3, 0.3, 3), -8, 8)
+
+
+class HoverA(HoverOuterA):
+    name = "uavr_hover"
+    cites = "environment/UavRobust/UavHover.py:101-226"
+    S, A = 12, 6
+
+    def make(self):
+        up, att, pos = _robust_params()
+        m = R.load("environment.UavRobust.UavHover")
+        return m.uav_hover(up, pos, att, np.array([1.0, -1.0, 2.0]))
+
+    def sample_action(self, rng, t, l, env=None):
+        acc = super().sample_action(rng, t, l, env)
+        if l % 3 == 0:
+            tq = rng.uniform(-0.3, 0.3, 3)
+        else:  # PD attitude torque towards the shaped reference
+            e_att = env.uav_att() - env.att_ref
+            tq = np.clip(-0.15 * e_att - 0.03 * env.uav_pqr() + rng.uniform(-0.005, 0.005, 3), -0.3, 0.3)
+        return np.concatenate((acc, tq))
+
+
+class InnerLoopA(_RobustBase):
+    name = "uavr_inner"
+    cites = "environment/UavRobust/UavInnerLoop.py:88-210 (+ uav_att_ctrl.py:33-46)"
+    S, A, D = 6, 3, 0
+
+    def make(self):
+        up, att, _ = _robust_params()
+        m = R.load("environment.UavRobust.UavInnerLoop")
+        return m.uav_inner_loop(up, att, np.array([0.3, 0.3, 0.3]), np.array([5., 5., 5.]), np.zeros(3), np.array([np.pi / 2, 0., 0.]))
+
+    def internal(self, env):
+        x = env.uav_state_call_back()
+        return np.concatenate((x, np.zeros(12), env.ref_amplitude, env.ref_period, env.ref_bias_phase)).astype(float), float(env.time)
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 3 == 0:
+            return rng.uniform(-0.3, 0.3, 3)
+        e = env.uav_att() - env.ref
+        return np.clip(-0.2 * e - 0.03 * (env.dot_rho1() - env.dot_ref) + rng.uniform(-0.005, 0.005, 3), -0.3, 0.3)
+
+
+class TrackingOuterA(_RobustBase):
+    name = "uavr_tracking"
+    cites = "environment/UavRobust/UavTrackingOuterLoop.py:90-255"
+    S, A = 6, 3
+
+    def make(self):
+        up, att, pos = _robust_params()
+        m = R.load("environment.UavRobust.UavTrackingOuterLoop")
+        return m.uav_tracking_outer_loop(up, pos, att, np.array([1.5, 1.5, 0.3]), np.array([6., 6., 10.]),
+                                         np.array([0., 0., 2.5]), np.array([np.pi / 2, 0., 0.]))
+
+    def internal(self, env):
+        x, s1, aref, daref = self._common(env)
+        return np.concatenate((x, s1, aref, daref, np.zeros(3), env.ref_amplitude, env.ref_period, env.ref_bias_phase)).astype(float), float(env.time)
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 3 == 0:
+            return rng.uniform(-8, 8, 3)
+        e = env.uav_pos() - env.pos_ref
+        de = env.uav_vel() - env.dot_pos_ref
+        return np.clip(-2.0 * e - 2.5 * de + rng.uniform(-0.3, 0.3, 3), -8, 8)
+
+
+REGISTRY.update({
+    "uavr_hover_outer": (HoverOuterA, 3, 1500, 51),
+    "uavr_hover": (HoverA, 3, 1500, 52),
+    "uavr_inner": (InnerLoopA, 3, 1500, 53),
+    "uavr_tracking": (TrackingOuterA, 3, 1500, 54),
+})

@@ -6,8 +6,10 @@ from .vec_env import VecEnvBase  # noqa: F401
 from .envs.cartpole import CartPole, CartPoleAngleOnly  # noqa: F401
 from .envs.simple import (BallBalancer1D, Flight_Attitude_Simulator, SecondOrderIntegration,  # noqa: F401
                           TwoLinkManipulator, UGVBidirectional, UGVForward, UGVForwardObstacleAvoidance)
+from .envs.uavrobust import uav_hover, uav_hover_outer_loop, uav_inner_loop, uav_tracking_outer_loop  # noqa: F401
 from .envs.uav import UavAttCtrlRL, UavPosCtrlRL, uav_param, fntsmc_param  # noqa: F401
 
 __all__ = ["VecEnvBase", "CartPole", "CartPoleAngleOnly", "UavAttCtrlRL", "UavPosCtrlRL", "uav_param", "fntsmc_param",
            "Flight_Attitude_Simulator", "SecondOrderIntegration", "BallBalancer1D", "TwoLinkManipulator", "UGVForward",
-           "UGVBidirectional", "UGVForwardObstacleAvoidance"]
+           "UGVBidirectional", "UGVForwardObstacleAvoidance", "uav_hover", "uav_hover_outer_loop",
+           "uav_inner_loop", "uav_tracking_outer_loop"]

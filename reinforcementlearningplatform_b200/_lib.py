@@ -91,7 +91,20 @@ UgvoParams = _struct("UgvoParams", "struct b200_ugvo_params", (
     "r_vehicle", "laser_dis", "laser_blind", "laser_range", "Q_pos", "Q_vel", "Q_phi", "Q_omega", "safety_dis_obs",
     "safety_dis_st", "r_min", "r_max", "st_margin"), ("n_rays", "obs_num", "variant", "pad_"))
 
-PARAMS_OF = {UGVO: UgvoParams, CARTPOLE: CartPoleParams, UAV_ATT: UavParams, UAV_POS: UavParams, FAS: FasParams, SOI: SoiParams,
+class UavRobustParams(C.Structure):
+    """struct b200_uavrobust_params"""
+    _fields_ = [
+        _d("m"), _d("g"), _d("J", 3), _d("kr"), _d("kt"), _d("dt"), _d("time_max"), _d("t_term"),
+        _d("pos_zone_min", 3), _d("pos_zone_max", 3), _d("att_zone_min", 3), _d("att_zone_max", 3),
+        _d("pos0", 3), _d("vel0", 3), _d("angle0", 3), _d("pqr0", 3),
+        _d("att_k1", 3), _d("att_k2", 3), _d("att_alpha", 3), _d("att_beta", 3), _d("att_gamma", 3), _d("att_lmd", 3),
+        _d("att_saturation", 3), _d("e_pos_span", 3), _d("vel_span", 3), _d("e_att_span", 3), _d("e_dot_att_span_neg", 3),
+        _d("dot_att_min", 3), _d("dot_att_max", 3), _d("static_gain"), _d("Qx"), _d("Qv"), _d("R"),
+        _d("ref_bias_a", 3), _d("target_lo", 3), _d("target_hi", 3), _d("sig_A_hi", 3), _d("sig_T_lo"), _d("sig_T_hi"),
+        _d("sig_phase_hi"), _d("init_pos_r"), ("variant", C.c_int32), ("pad_", C.c_int32)]
+
+
+PARAMS_OF = {UAVROBUST: UavRobustParams, UGVO: UgvoParams, CARTPOLE: CartPoleParams, UAV_ATT: UavParams, UAV_POS: UavParams, FAS: FasParams, SOI: SoiParams,
              BALLBALANCER: BallBalancerParams, TWOLINK: TwoLinkParams, UGV: UgvParams}
 
 _lib = None

@@ -183,3 +183,4 @@ B200_FAMILY_DECL(ballbalancer)
 B200_FAMILY_DECL(twolink)
 B200_FAMILY_DECL(ugv)
 B200_FAMILY_DECL(ugvo)
+B200_FAMILY_DECL(uavrobust)

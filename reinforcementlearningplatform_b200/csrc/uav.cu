@@ -15,184 +15,16 @@
 // stage-1 values are shared with the controllers (the reference evaluates f1() four times and sin/cos ~60 times).
 // HBM traffic is one coalesced read and one coalesced write of each SoA field.
 #include "common.cuh"
-
 #ifndef UAV_POS_MINBLOCKS
 #define UAV_POS_MINBLOCKS 4
 #endif
 #ifndef UAV_ATT_MINBLOCKS
 #define UAV_ATT_MINBLOCKS 4
 #endif
+#include "uav_common.cuh"
+
 namespace {
-
-typedef b200_uav_params P;
-
-template <typename T>
-struct Trig {
-    T sphi, cphi, sth, cth, spsi, cpsi, tth, rcth;
-    // one range check for all angles (fastmath64.cuh): the polynomial chains of the 2-3 sincos share a basic block
-    __device__ __forceinline__ void eval(T phi, T th, T psi, bool need_psi) {
-        if (need_psi) {
-            Mth<T>::sincos3(phi, th, psi, &sphi, &cphi, &sth, &cth, &spsi, &cpsi);
-        } else {
-            Mth<T>::sincos2(phi, th, &sphi, &cphi, &sth, &cth);
-            spsi = (T)0; cpsi = (T)1;
-        }
-        rcth = Mth<T>::rcp(cth);
-        tth = sth * rcth;
-    }
-};
-
-template <typename T>
-struct Consts {
-    T m, g, kr, kt, J0, J1, J2, J21, J02, J10, dt, rJ0, rJ1, rJ2, rm;
-    __device__ __forceinline__ Consts(const P &p)
-        : m((T)p.m), g((T)p.g), kr((T)p.kr), kt((T)p.kt), J0((T)p.J[0]), J1((T)p.J[1]), J2((T)p.J[2]),
-          J21((T)(p.J[2] - p.J[1])), J02((T)(p.J[0] - p.J[2])), J10((T)(p.J[1] - p.J[0])), dt((T)p.dt),
-          rJ0((T)(1.0 / p.J[0])), rJ1((T)(1.0 / p.J[1])), rJ2((T)(1.0 / p.J[2])), rm((T)(1.0 / p.m)) {}
-};
-
-// uav.py:93-124.  x = (x y z vx vy vz phi th psi p q r); only the derivative entries that the caller needs.
-template <typename T, bool ATT_ONLY>
-__device__ __forceinline__ void uav_ode(const Consts<T> &c, const T *x, const Trig<T> &t, T throttle, const T *tq,
-                                        const T *dis, T *d) {
-    const T p = x[9], q = x[10], r = x[11];
-    // divisions by the constants J, m are multiplications by their reciprocals (<= 1 ulp from the reference's x / J)
-    d[9] = (-c.kr * p - q * r * c.J21 + tq[0]) * c.rJ0;
-    d[10] = (-c.kr * q - p * r * c.J02 + tq[1]) * c.rJ1;
-    d[11] = (-c.kr * r - p * q * c.J10 + tq[2]) * c.rJ2;
-    d[6] = p + (t.tth * t.sphi) * q + (t.tth * t.cphi) * r;
-    d[7] = t.cphi * q - t.sphi * r;
-    d[8] = (t.sphi * t.rcth) * q + (t.cphi * t.rcth) * r;
-    if (!ATT_ONLY) {
-        d[0] = x[3]; d[1] = x[4]; d[2] = x[5];
-        d[3] = (throttle * (t.cpsi * t.sth * t.cphi + t.spsi * t.sphi) - c.kt * x[3] + dis[0]) * c.rm;
-        d[4] = (throttle * (t.spsi * t.sth * t.cphi - t.cpsi * t.sphi) - c.kt * x[4] + dis[1]) * c.rm;
-        d[5] = -c.g + (throttle * t.cphi * t.cth - c.kt * x[5] + dis[2]) * c.rm;
-    }
-}
-
-// uav.py:126-148 with n = 1: x <- x + (K1 + 2 K2 + 2 K3 + K4) / 6, psi wrapped to (-pi, pi] (time is advanced by
-// the caller).  `t` enters with sin/cos of the current attitude (already computed for the controllers).  The four
-// stages run as a rolled loop (one copy of the ODE + trig code instead of four: the fully unrolled kernel was
-// 128 KB of SASS and stalled on instruction fetch); weights (1,2,2,1) and stage offsets (1/2,1/2,1) are selected by
-// the stage index, and acc starts at 0 so acc + 1*K1 == K1 exactly -- the summation order of the reference is kept.
-template <typename T, bool ATT_ONLY>
-__device__ __forceinline__ void uav_rk44(const Consts<T> &c, T *x, Trig<T> t, T throttle, const T *tq, const T *dis) {
-    constexpr int LO = ATT_ONLY ? 6 : 0;
-    const T h = c.dt;
-    T acc[12], xs[12];
-#pragma unroll
-    for (int i = LO; i < 12; ++i) { acc[i] = (T)0; xs[i] = x[i]; }
-#pragma unroll 1
-    for (int s = 0; s < 4; ++s) {
-        T d[12];
-        uav_ode<T, ATT_ONLY>(c, xs, t, throttle, tq, dis, d);
-        const T w = (s == 0 || s == 3) ? (T)1 : (T)2;
-        const T cs = (s == 2) ? (T)1 : (T)0.5;
-#pragma unroll
-        for (int i = LO; i < 12; ++i) {
-            const T k = h * d[i];
-            acc[i] = acc[i] + w * k;
-            xs[i] = x[i] + k * cs;
-        }
-        if (s < 3) t.eval(xs[6], xs[7], xs[8], !ATT_ONLY);
-    }
-#pragma unroll
-    for (int i = LO; i < 12; ++i) x[i] = x[i] + acc[i] * (T)(1.0 / 6.0);
-    if (x[8] > (T)M_PI) x[8] -= (T)(2 * M_PI);
-    if (x[8] < (T)-M_PI) x[8] += (T)(2 * M_PI);
-}
-
-// FNTSMC sliding surface pieces shared by both loops (FNTSMC.py:61-66 / 128-134), one axis.
-template <typename T>
-__device__ __forceinline__ void smc_axis(T e, T de, T k1, T gamma, T alpha, T beta, T lmd, T dt, T &integ,
-                                         T &s_out, T &dot_s1, T &pa1_de) {
-    const T L = Mth<T>::log(Mth<T>::abs(e)); // shared by |e|^alpha and |e|^(alpha-1)
-    const T pa = pow_from_log<T>(L, alpha);
-    const T pa1 = pow_from_log<T>(L, alpha - (T)1);
-    const T s = de + k1 * e + gamma * pa * Mth<T>::tanh((T)5 * e);
-    dot_s1 = pow_from_log<T>(Mth<T>::log(Mth<T>::abs(s)), beta) * Mth<T>::tanh((T)5 * s);
-    integ += dot_s1 * dt;
-    s_out = s + lmd * integ;           // sigma (att) / so (pos)
-    pa1_de = gamma * alpha * pa1 * de; // gamma * alpha * |e|^(alpha-1) * de
-}
-
-// -inv(B) . v with B = f1 . diag(1/J) (uav.py:359-360) and inv = LAPACK dgesv(B, I) semantics: LU with partial
-// pivoting, then forward/back substitution per unit column, then the 3x3 . 3 product (FNTSMC.py:137).
-// Column 0 of B is (1/J0, 0, 0): its multipliers are exactly 0, so only rows 1,2 can be swapped.
-template <typename T>
-__device__ __forceinline__ void neg_inv_apply(T b00, T b01, T b02, T b11, T b12, T b21, T b22, const T *v, T *out) {
-    const bool swap = Mth<T>::abs(b21) > Mth<T>::abs(b11);
-    const T u11 = swap ? b21 : b11, u12 = swap ? b22 : b12;
-    const T r21 = swap ? b11 : b21, r22 = swap ? b12 : b22;
-    const T l = r21 * ((T)1 / u11);
-    const T u22 = r22 - l * u12;
-    T inv[3][3];
-#pragma unroll
-    for (int cidx = 0; cidx < 3; ++cidx) {
-        // P e_c: rows 1 and 2 exchanged when swap
-        T y0 = cidx == 0 ? (T)1 : (T)0;
-        T y1 = (cidx == (swap ? 2 : 1)) ? (T)1 : (T)0;
-        T y2 = (cidx == (swap ? 1 : 2)) ? (T)1 : (T)0;
-        y2 = y2 - l * y1;
-        const T x2 = y2 / u22;
-        const T x1 = (y1 - u12 * x2) / u11;
-        const T x0 = ((y0 - b01 * x1) - b02 * x2) / b00;
-        inv[0][cidx] = x0; inv[1][cidx] = x1; inv[2][cidx] = x2;
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) out[i] = -(inv[i][0] * v[0] + inv[i][1] * v[1] + inv[i][2] * v[2]);
-}
-
-// Attitude loop: uav_att_ctrl.py:91-108 / uav_pos_ctrl.py:317-337 + FNTSMC.py:112-137 (dd_ref = 0).
-// x: full state, t: trig of the current attitude.  Returns torque; also d1 = f1 . pqr (Euler rates).
-template <typename T>
-__device__ __forceinline__ void att_control(const Consts<T> &c, const T *x, const Trig<T> &t, const T *k1, const T *k2,
-                                            const T *gamma, const T *lmd, const T *alpha, const T *beta, T *s1,
-                                            const T *ref, const T *dref, T *torque, T *d1) {
-    const T p = x[9], q = x[10], r = x[11];
-    const T f01 = t.sphi * t.tth, f02 = t.cphi * t.tth, f11 = t.cphi, f12 = -t.sphi;
-    const T f21 = t.sphi * t.rcth, f22 = t.cphi * t.rcth;
-    d1[0] = p + f01 * q + f02 * r;
-    d1[1] = f11 * q + f12 * r;
-    d1[2] = f21 * q + f22 * r;
-    // F() (uav.py:340-354) . rho2
-    const T rc2 = t.rcth * t.rcth;
-    const T F01 = d1[0] * t.tth * t.cphi + d1[1] * t.sphi * rc2;
-    const T F02 = -d1[0] * t.tth * t.sphi + d1[1] * t.cphi * rc2;
-    const T F11 = -d1[0] * t.sphi, F12 = -d1[0] * t.cphi;
-    const T F21 = (d1[0] * t.cphi * t.cth + d1[1] * t.sphi * t.sth) * rc2;
-    const T F22 = (-d1[0] * t.sphi * t.cth + d1[1] * t.cphi * t.sth) * rc2;
-    // f2() (uav.py:302-313)
-    const T g0 = (c.kr * p + q * r * (c.J1 - c.J2)) * c.rJ0;
-    const T g1 = (c.kr * q + p * r * (c.J2 - c.J0)) * c.rJ1;
-    const T g2 = (c.kr * r + p * q * (c.J0 - c.J1)) * c.rJ2;
-    T sec[3];
-    sec[0] = (F01 * q + F02 * r) + (g0 + f01 * g1 + f02 * g2);
-    sec[1] = (F11 * q + F12 * r) + (f11 * g1 + f12 * g2);
-    sec[2] = (F21 * q + F22 * r) + (f21 * g1 + f22 * g2);
-    T v[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const T e = x[6 + i] - ref[i], de = d1[i] - dref[i];
-        T sigma, dot_s1, pa1_de;
-        smc_axis<T>(e, de, k1[i], gamma[i], alpha[i], beta[i], lmd[i], c.dt, s1[i], sigma, dot_s1, pa1_de);
-        const T u1 = sec[i] + k1[i] * de + pa1_de + lmd[i] * dot_s1;
-        const T u2 = -k2[i] * Mth<T>::tanh((T)10 * sigma);
-        v[i] = u1 + u2;
-    }
-#ifdef B200_UAV_LAPACK_INV
-    neg_inv_apply<T>(c.rJ0, f01 * c.rJ1, f02 * c.rJ2, f11 * c.rJ1, f12 * c.rJ2, f21 * c.rJ1, f22 * c.rJ2, v, torque);
-#else
-    // B = f1 . diag(1/J)  =>  B^-1 = diag(J) . f1^-1 with the closed form
-    //   f1^-1 = [[1, 0, -sin th], [0, cos phi, sin phi cos th], [0, -sin phi, cos phi cos th]].
-    // The reference calls np.linalg.inv (LU, FNTSMC.py:137); the closed form differs from it only by LAPACK's own
-    // rounding (cond(f1) * eps) -- measured in tests/parity_report.py, incl. the near-singular fixtures.
-    torque[0] = -c.J0 * (v[0] - t.sth * v[2]);
-    torque[1] = -c.J1 * (t.cphi * v[1] + t.sphi * t.cth * v[2]);
-    torque[2] = -c.J2 * (t.cphi * t.cth * v[2] - t.sphi * v[1]);
-#endif
-}
+using namespace uavk;
 
 // uav.py:182-219: 2 position out, 3 attitude out, 1 time out -- evaluated in this order, the last true wins
 template <typename T>
@@ -208,17 +40,6 @@ __device__ __forceinline__ int terminal_flag(const P &p, const T *x, double time
     if (out) flag = 3;
     if (time > p.t_term) flag = 1;
     return flag;
-}
-
-// ref_cmd.py:4-43, one channel
-template <typename T>
-__device__ __forceinline__ void ref_channel(T time, T A, T period, T bias, T phase, T &r, T &dr, T &ddr) {
-    const T w = (T)(2 * M_PI) / period;
-    T s, co;
-    Mth<T>::sincos(w * time + phase, &s, &co);
-    r = A * s + bias;
-    dr = A * w * co;
-    ddr = -A * (w * w) * s;
 }
 
 // ------------------------------------------------------------------------------------------ attitude env

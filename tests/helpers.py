@@ -39,6 +39,10 @@ def env_specs():
         "twolink": (rlp.TwoLinkManipulator, {}),
         "ugv_forward": (rlp.UGVForward, {}),
         "ugv_bidirectional": (rlp.UGVBidirectional, {}),
+        "uavr_hover_outer": (rlp.uav_hover_outer_loop, {}),
+        "uavr_hover": (rlp.uav_hover, {}),
+        "uavr_inner": (rlp.uav_inner_loop, {}),
+        "uavr_tracking": (rlp.uav_tracking_outer_loop, {}),
         "ugvo": (rlp.UGVForwardObstacleAvoidance, {}),
         "ugvo_dppo2": (rlp.UGVForwardObstacleAvoidance, {"variant": "dppo2"}),
         "uav_pos": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
@@ -194,6 +198,7 @@ ENGINE_TOL = {
     "uav_att": 1e-9, "uav_att_rand": 1e-9, "uav_att_edge": 1e-9,
     "fas": 1e-9, "fas_ppo2": 1e-9, "soi": 1e-9, "soi_dppo2": 1e-9, "ballbalancer": 1e-9, "twolink": 1e-5,
     "ugv_forward": 1e-9, "ugv_bidirectional": 1e-9, "ugvo": 1e-9, "ugvo_dppo2": 1e-9,
+    "uavr_hover_outer": 1e-7, "uavr_hover": 1e-7, "uavr_inner": 1e-7, "uavr_tracking": 1e-7,
 }
 
 
