@@ -149,47 +149,60 @@ def timed_steps(env, pool, steps, warmup, dist_on):
     return ms
 
 
-def timed_e2e(env, n, steps, warmup, dist_on, seed):
-    """Same metric through the public API with HOST buffers: every step copies the actions from pinned host memory,
-    launches the step, and reads next_state / reward / is_terminal back to pinned host memory."""
+def timed_e2e(workload, n, steps, warmup, dist_on, seed, device, offset, dtype, chunks=4):
+    """Same metric through the public API with HOST buffers.  Every step, for every instance: the actions are copied
+    from pinned host memory, the step kernel runs, and policy_state / reward / is_terminal are read back to pinned host
+    memory, where the host waits for them before it issues that instance's next action.  The batch is split into
+    `chunks` independent VecEnv shards on their own CUDA streams so that shard c's copies overlap shard c+1's kernel
+    (PCIe is full duplex); the dependency action(t+1) <- result(t) is kept per shard."""
     import torch.distributed as dist
-    A, S = env.action_dim, env.state_dim
+    nc = n // chunks
+    envs, streams = [], []
+    for c in range(chunks):
+        e = make_env(workload, nc, device, offset + c * nc, dtype)
+        e.reset(True)
+        envs.append(e)
+        streams.append(torch.cuda.Stream(device=device))
+    A, S = envs[0].action_dim, envs[0].state_dim
     rng = np.random.default_rng(seed)
-    ar = np.asarray(env.action_range, dtype=np.float64)
-    host_a = [torch.from_numpy(rng.uniform(ar[:, :1], ar[:, 1:], size=(A, n))).to(env.dtype).pin_memory() for _ in range(2)]
-    dev_a = [torch.empty((A, n), dtype=env.dtype, device=env.device) for _ in range(2)]
-    h_obs = torch.empty((S, n), dtype=env.dtype).pin_memory()
-    h_rew = torch.empty((n,), dtype=env.dtype).pin_memory()
-    h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    ar = np.asarray(envs[0].action_range, dtype=np.float64)
+    host_a = [[torch.from_numpy(rng.uniform(ar[:, :1], ar[:, 1:], size=(A, nc))).to(dtype).pin_memory() for _ in range(2)]
+              for _ in range(chunks)]
+    dev_a = [torch.empty((A, nc), dtype=dtype, device=device) for _ in range(chunks)]
+    h_obs = [torch.empty((S, nc), dtype=dtype).pin_memory() for _ in range(chunks)]
+    h_rew = [torch.empty((nc,), dtype=dtype).pin_memory() for _ in range(chunks)]
+    h_done = [torch.empty((nc,), dtype=torch.uint8).pin_memory() for _ in range(chunks)]
+    ready = [torch.cuda.Event() for _ in range(chunks)]
+    torch.cuda.synchronize()
 
     def one(k):
-        b = k & 1
-        dev_a[b].copy_(host_a[b], non_blocking=True)
-        env.step_soa(dev_a[b])
-        h_obs.copy_(env._reset_obs, non_blocking=True)
-        h_rew.copy_(env._reward, non_blocking=True)
-        h_done.copy_(env._done, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the host-side policy needs the result before the next action
+        for c in range(chunks):
+            if k > 0:
+                ready[c].synchronize()  # the host-side policy needs shard c's previous result before acting on it
+            with torch.cuda.stream(streams[c]):
+                dev_a[c].copy_(host_a[c][k & 1], non_blocking=True)
+                envs[c].step_soa(dev_a[c])
+                h_obs[c].copy_(envs[c]._reset_obs, non_blocking=True)
+                h_rew[c].copy_(envs[c]._reward, non_blocking=True)
+                h_done[c].copy_(envs[c]._done, non_blocking=True)
+                ready[c].record(streams[c])
 
     for k in range(warmup):
         one(k)
+    torch.cuda.synchronize()
     if dist_on:
         dist.barrier()
-    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     for k in range(steps):
-        one(k)
-    e1.record()
+        one(warmup + k)
     torch.cuda.synchronize()
-    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    ms = (time.perf_counter() - t0) * 1e3  # host clock around fully synchronised work (copies on several streams)
     if dist_on:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    el = torch.tensor([], dtype=env.dtype).element_size()
-    return ms, A * n * el, (S * n + n) * el + n
+    el = torch.tensor([], dtype=dtype).element_size()
+    return ms, chunks * nc, A * chunks * nc * el, (S * nc + nc) * chunks * el + chunks * nc
 
 
 def cpu_port(workload, n, steps, threads, seed=2024):
@@ -235,6 +248,50 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def also_workloads(args, dev, dtype, peaks):
+    """Short device-resident measurements of the other single-GPU configs (same timing rules, fewer steps)."""
+    out = []
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    for w in ("uav_att", "cartpole", "soi", "fas", "ugvo"):
+        if w == args.workload:
+            continue
+        n = WORKLOADS[w]["n"]
+        env = make_env(w, n, dev, 0, dtype)
+        env.reset(True)
+        pool = action_pool(env, n, 4, dev, dtype, seed=7)
+        steps = 20 if w == "ugvo" else 100
+        ms = timed_steps(env, pool, steps, 5, False)
+        per = ms * 1e-3 / steps
+        out.append({"workload": w, "envs": n, "value": n / per, "unit": "env-steps/s", "ms_per_step": ms / steps,
+                    "hbm_frac": ALGO_BYTES[w] * n / per / 1e9 / hbm, "desc": WORKLOADS[w]["desc"]})
+        del env, pool
+        torch.cuda.empty_cache()
+    # config #3: GAE over a 2048-step rollout, 131072 env columns per GPU
+    from reinforcementlearningplatform_b200 import gae as G
+    T, N = 2048, 131072
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    mk = lambda: torch.randn((T, N), generator=g, device=dev, dtype=torch.float32)
+    r, vs, vsn = mk(), mk(), mk()
+    done = (torch.rand((T, N), generator=g, device=dev) < 0.002).float()
+    succ = done * (torch.rand((T, N), generator=g, device=dev) < 0.5).float()
+    for _ in range(3):
+        adv, vt, st = G.gae(r, vs, vsn, done, succ, 0.99, 0.95)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 10
+    for _ in range(reps):
+        adv, vt, st = G.gae(r, vs, vsn, done, succ, 0.99, 0.95)
+    e1.record()
+    torch.cuda.synchronize()
+    per = e0.elapsed_time(e1) * 1e-3 / reps
+    out.append({"workload": "gae", "T": T, "N": N, "value": T * N / per, "unit": "elements/s", "ms_per_step": per * 1e3,
+                "hbm_frac": 28.0 * T * N / per / 1e9 / hbm,
+                "desc": "PPO2 GAE reverse scan + (sum, sum^2, n) statistics, float32, time-major [T, N]"})
+    return out
 
 
 def main():
@@ -298,18 +355,28 @@ def main():
         "clocks": clocks, "gpu_launches": args.steps,
     }
     if not args.no_extras:
-        sampler2 = ClockSampler(local)
-        e_ms, h2d, d2h = timed_e2e(env, n, max(10, args.steps // 4), 3, dist_on, seed=rank + 11)
+        del env, pool
+        torch.cuda.empty_cache()
         e_steps = max(10, args.steps // 4)
-        line["e2e"] = {"value": world * n * e_steps / (e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": d2h, "api": "VecEnv.step_soa with pinned host action / result buffers"}
-        del sampler2
+        e_ms, e_n, h2d, d2h = timed_e2e(args.workload, n, e_steps, 3, dist_on, rank + 11, dev, rank * n, dtype)
+        line["e2e"] = {"value": world * e_n * e_steps / (e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h,
+                       "api": "VecEnv.step_soa on 4 shards / 4 streams: pinned host actions in, policy_state + reward + "
+                              "is_terminal out every step; the host waits for a shard's result before its next action"}
+        if rank == 0 and world == 1:
+            line["also"] = also_workloads(args, dev, dtype, peaks)
         if rank == 0 and world == 1:
             threads = os.cpu_count() or 1
-            cn = min(n, 1 << 16)
-            cval, cdt = cpu_port(args.workload, cn, 40, threads)
+            cn = min(n, 1 << 17)
+            csteps = 40
+            cval, cdt = cpu_port(args.workload, cn, csteps, threads)
+            csteps = int(min(max(csteps * 12.0 / max(cdt, 1e-3), 40), 4000))  # ~12 s of CPU work
+            cval, cdt = cpu_port(args.workload, cn, csteps, threads)
             line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{cn} instances x 40 steps ({cdt:.1f} s), C restatement of the reference, OpenMP"}
+                                    "sample": f"{cn} instances x {csteps} steps ({cdt:.1f} s), C restatement of the "
+                                              "reference (oracle/), OpenMP over instances",
+                                    "reference_python_loop": "1.36e3 env-steps/s per core measured in the build container "
+                                                             "(BASELINE.md section 2); pure Python, cannot travel to the GPU box"}
     if rank == 0:
         print(json.dumps(line))
     if dist_on:
