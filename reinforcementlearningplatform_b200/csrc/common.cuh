@@ -33,6 +33,7 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double tanh(double x) { return ::tanh(x); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+    static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
 #else // fastmath64.cuh: constant-bank coefficients, no special-case ladders, ~1 ulp
     static __device__ __forceinline__ void sincos(double x, double *s, double *c) { fm64::sincos(x, s, c); }
     static __device__ __forceinline__ void sincos3(double a, double b, double c, double *sa, double *ca, double *sb,
@@ -46,13 +47,13 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double tanh(double x) { return fm64::tanh(x); }
     static __device__ __forceinline__ double log(double x) { return fm64::log(x); }
     static __device__ __forceinline__ double exp(double x) { return fm64::exp(x); }
+    static __device__ __forceinline__ double asin(double x) { return fm64::asin(x); }
 #endif
     static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
     static __device__ __forceinline__ double cos(double x) { return ::cos(x); }
     static __device__ __forceinline__ double tan(double x) { return ::tan(x); }
     static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
-    static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
     static __device__ __forceinline__ double acos(double x) { return ::acos(x); }
     static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
     static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
@@ -91,7 +92,8 @@ template <> struct Mth<float> {
 // with ncu) by one log and two exp.  Relative error <= (|a L| + 1) ulp, i.e. ~4e-15 for |a L| <= 35.
 template <typename T>
 __device__ __forceinline__ T pow_from_log(T L, T a) {
-    return a == (T)0 ? (T)1 : Mth<T>::exp(a * L);
+    const T r = Mth<T>::exp(a * L); // evaluated unconditionally: a select instead of a branch
+    return a == (T)0 ? (T)1 : r;
 }
 
 // ---------------------------------------------------------------------------
@@ -139,13 +141,16 @@ struct Philox {
 // ---------------------------------------------------------------------------
 // SoA accessors
 // ---------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ T ld(const void *base, int64_t n, int field, int64_t i) {
-    return static_cast<const T *>(base)[(int64_t)field * n + i];
+// The index type I is int64_t in general; the hot UAV kernels are also instantiated with uint32_t (chosen by the
+// launcher when fields * n < 2^32), which turns ~5 instructions of 64-bit address arithmetic per access into
+// IMAD + IMAD.WIDE.U32 (8 % of the executed instructions of the UAV-pos step, ncu).
+template <typename T, typename I>
+__device__ __forceinline__ T ld(const void *base, I n, int field, I i) {
+    return static_cast<const T *>(base)[(I)field * n + i];
 }
-template <typename T>
-__device__ __forceinline__ void st(void *base, int64_t n, int field, int64_t i, T v) {
-    static_cast<T *>(base)[(int64_t)field * n + i] = v;
+template <typename T, typename I>
+__device__ __forceinline__ void st(void *base, I n, int field, I i, T v) {
+    static_cast<T *>(base)[(I)field * n + i] = v;
 }
 
 // ---------------------------------------------------------------------------

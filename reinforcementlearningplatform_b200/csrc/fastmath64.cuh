@@ -33,6 +33,11 @@ static __constant__ double kE[10] = {0x1.0000000000001p-1, 0x1.5555555555556p-3,
 static __constant__ double kL[7] = {0x1.5555555555558p-1, 0x1.99999999949c3p-2, 0x1.2492492ef134dp-2,
                                     0x1.c71c61a265960p-3, 0x1.74630fb47b087p-3, 0x1.39f2ac8e848c3p-3,
                                     0x1.2be78035f90e7p-3};
+// A: asin(t) = t + t z A(z), z = t^2 <= 1/4 (degree 11; |x| > 1/2 goes through pi/2 - 2 asin(sqrt((1 - |x|) / 2)))
+static __constant__ double kA[12] = {0x1.555555555554fp-3, 0x1.3333333336f25p-4, 0x1.6db6db682abf8p-5,
+                                     0x1.f1c71fa66977fp-6, 0x1.6e8b28e7f8608p-6, 0x1.1c596afc9d8acp-6,
+                                     0x1.c86de3215c77bp-7, 0x1.8546aebb901aap-7, 0x1.fdf3b5f7fbfb1p-8,
+                                     0x1.07d821fcdce60p-6, -0x1.64309bd35e9c9p-7, 0x1.cf09bf99f54b7p-6};
 // reduction constants: pi/2 in three pieces, 2/pi, ln2 in two pieces, log2(e), 1.5 * 2^52 (round-to-nearest magic)
 static __constant__ double kR[8] = {0x1.921fb54442d18p+0, 0x1.1a62633145c07p-54, -0x1.f1976b7ed8fbcp-110,
                                     0x1.45f306dc9c883p-1, 0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56,
@@ -112,7 +117,8 @@ __device__ __forceinline__ void sincos2(double a, double b, double *sa, double *
     sincos_core(b, sb, cb);
 }
 
-__device__ __forceinline__ double exp(double x) {
+// exp without the range guards: valid for -708 < x < 709 (tanh calls it on [0, 40])
+__device__ __forceinline__ double exp_core(double x) {
     const double t = fma(x, kR[6], kR[7]);
     const int n = __double2loint(t);
     const double fn = t - kR[7];
@@ -126,11 +132,15 @@ __device__ __forceinline__ double exp(double x) {
     pe = fma(pe, r2, kE[2]); po = fma(po, r2, kE[3]);
     pe = fma(pe, r2, kE[0]); po = fma(po, r2, kE[1]);
     const double p = fma(po, r, pe);
-    double y = fma(r2, p, r) + 1.0;
-    y *= __hiloint2double((n + 1023) << 20, 0); // 2^n, valid for the clamped range below
-    if (x < -708.0) y = 0.0;                    // (denormal results flush to 0)
+    const double y = fma(r2, p, r) + 1.0;
+    return y * __hiloint2double((n + 1023) << 20, 0); // 2^n by exponent construction
+}
+
+__device__ __forceinline__ double exp(double x) {
+    double y = exp_core(x);
+    if (x < -708.0) y = 0.0;       // (denormal results flush to 0)
     if (x > 709.0) y = CUDART_INF;
-    return y;                                   // NaN in -> NaN out (the comparisons are false, the polynomial is NaN)
+    return y;                      // NaN in -> NaN out (the comparisons are false, the polynomial is NaN)
 }
 
 // natural log, branch-free.  x = 0 (and subnormal x, treated as 0) -> -inf, x < 0 or NaN -> NaN, +inf -> +inf.
@@ -160,11 +170,27 @@ __device__ __forceinline__ double log(double x) {
 
 // tanh, branch-free; ~2e-16 absolute accuracy
 __device__ __forceinline__ double tanh(double x) {
-    const double ax = fmin(fabs(x), 20.0); // tanh(20) rounds to 1
-    const double t = fm64::exp(2.0 * ax);
-    double y = fma(-2.0, rcp(t + 1.0), 1.0);
-    y = copysign(y, x);
-    return x != x ? x : y;
+    const double ax = (fabs(x) > 20.0) ? 20.0 : fabs(x); // tanh(20) rounds to 1; NaN stays NaN (comparison false)
+    const double t = exp_core(2.0 * ax);
+    const double y = fma(-2.0, rcp(t + 1.0), 1.0);
+    return copysign(y, x);
+}
+
+// asin for |x| <= 1 (NaN outside), branch-free: one degree-11 kernel on t <= 1/2, the upper half folded by
+// asin(x) = pi/2 - 2 asin(sqrt((1 - |x|) / 2)).  <= 1.5 ulp.
+__device__ __forceinline__ double asin(double x) {
+    const double ax = fabs(x);
+    const bool big = ax > 0.5;
+    const double w = big ? 0.5 * (1.0 - ax) : ax * ax; // z = t^2
+    const double t = big ? ::sqrt(w) : ax;
+    double p = kA[11];
+    p = fma(p, w, kA[10]); p = fma(p, w, kA[9]); p = fma(p, w, kA[8]); p = fma(p, w, kA[7]); p = fma(p, w, kA[6]);
+    p = fma(p, w, kA[5]); p = fma(p, w, kA[4]); p = fma(p, w, kA[3]); p = fma(p, w, kA[2]); p = fma(p, w, kA[1]);
+    p = fma(p, w, kA[0]);
+    const double a = fma(t * w, p, t);
+    // pi/2 - 2a with the low part of pi/2 folded in
+    const double r = big ? (kR[0] - 2.0 * a) + kR[1] : a;
+    return copysign(r, x);
 }
 
 } // namespace fm64

@@ -69,6 +69,7 @@ __global__ void fastmath_eval_kernel(int func, int64_t n, const double *x, doubl
     case 2: a = fm64::log(v); break;
     case 3: a = fm64::tanh(v); break;
     case 4: a = pow_from_log<double>(fm64::log(v), o1[i]); b = o1[i]; break; // exponent passed in o1
+    case 5: a = fm64::asin(v); break;
     default: break;
     }
     o0[i] = a;

@@ -45,8 +45,8 @@ __device__ __forceinline__ int terminal_flag(const P &p, const T *x, double time
 // ------------------------------------------------------------------------------------------ attitude env
 enum { A_S1 = 6, A_K1 = 9, A_K2 = 12, A_GAM = 15, A_LMD = 18, A_AMP = 21, A_PER = 24, A_PHS = 27, A_REF = 30, A_DREF = 33 };
 
-template <typename T>
-__device__ __forceinline__ void att_reset_state(const P &p, const b200env_io &io, int64_t n, int64_t i, uint64_t seed,
+template <typename T, typename I>
+__device__ __forceinline__ void att_reset_state(const P &p, const b200env_io &io, I n, I i, uint64_t seed,
                                                 int64_t off, T *x /* out: 12 states */) {
     const uint32_t ep = io.episode[i];
 #pragma unroll
@@ -61,7 +61,7 @@ __device__ __forceinline__ void att_reset_state(const P &p, const b200env_io &io
     }
     double A[3], Tp[3], ph[3];
     if (p.random_trajectory) { // uav_att_ctrl.py:156-161
-        Philox rng(seed, (uint64_t)(off + i), ep);
+        Philox rng(seed, (uint64_t)(off + (int64_t)i), ep);
 #pragma unroll
         for (int k = 0; k < 3; ++k) A[k] = rng.uniform(0., p.traj_A_hi[k]);
 #pragma unroll
@@ -93,12 +93,13 @@ __device__ __forceinline__ void att_observe(const T *x, const Trig<T> &t, const 
     o[5] = ((t.sphi / t.cth) * q + (t.cphi / t.cth) * r) - dref[2];
 }
 
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(B200_BLOCK, UAV_ATT_MINBLOCKS)
-uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
+uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n_, uint32_t flags,
                     uint64_t seed, int64_t off) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_) return;
+    const I n = (I)n_, i = (I)gi;
     const Consts<T> c(p);
     T x[12];
 #pragma unroll
@@ -182,7 +183,7 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     io.flag[i] = flag;
     if (done && (flags & B200ENV_AUTO_RESET)) {
         T xr[12];
-        att_reset_state<T>(p, io, n, i, seed, off, xr);
+        att_reset_state<T, I>(p, io, n, i, seed, off, xr);
         Trig<T> tr;
         tr.eval(xr[6], xr[7], xr[8], false);
         att_observe<T>(xr, tr, ref, dref, nxt); // first obs of the next episode against the stale ref (reference quirk)
@@ -213,7 +214,7 @@ uav_att_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200en
 #pragma unroll
         for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = ld<T>(io.state, n, k, i); }
     } else {
-        att_reset_state<T>(p, io, n, i, seed, off, x);
+        att_reset_state<T, int64_t>(p, io, n, i, seed, off, x);
     }
     if (io.next_obs) {
         T ref[3], dref[3], o[6];
@@ -231,8 +232,8 @@ uav_att_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200en
 enum { P_SIG = 12, P_S1 = 15, P_AREF = 18, P_K1 = 21, P_K2 = 24, P_GAM = 27, P_LMD = 30, P_AMP = 33, P_PER = 37,
        P_PHS = 41, P_PREF = 45, P_DPREF = 48 };
 
-template <typename T>
-__device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io, int64_t n, int64_t i, uint64_t seed,
+template <typename T, typename I>
+__device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io, I n, I i, uint64_t seed,
                                                 int64_t off, T *x) {
     const uint32_t ep = io.episode[i];
 #pragma unroll
@@ -248,7 +249,7 @@ __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io
     }
     double A[4], Tp[4], ph[4];
     if (p.random_trajectory) { // uav_pos_ctrl.py:404-408
-        Philox rng(seed, (uint64_t)(off + i), ep);
+        Philox rng(seed, (uint64_t)(off + (int64_t)i), ep);
         const double a = rng.uniform(0., p.traj_A_hi[0]);
         const double tt = rng.uniform(p.traj_T_lo, p.traj_T_hi);
         A[0] = A[1] = A[2] = a; A[3] = 0.;
@@ -270,12 +271,13 @@ __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io
     io.episode[i] = ep + 1u;
 }
 
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(B200_BLOCK, UAV_POS_MINBLOCKS)
-uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
+uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n_, uint32_t flags,
                     uint64_t seed, int64_t off) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_) return;
+    const I n = (I)n_, i = (I)gi;
     const Consts<T> c(p);
     T x[12];
 #pragma unroll
@@ -396,7 +398,7 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     io.flag[i] = flag;
     if (done && (flags & B200ENV_AUTO_RESET)) {
         T xr[12];
-        pos_reset_state<T>(p, io, n, i, seed, off, xr);
+        pos_reset_state<T, I>(p, io, n, i, seed, off, xr);
 #pragma unroll
         for (int k = 0; k < 3; ++k) { nxt[k] = xr[k] - ref[k]; nxt[3 + k] = xr[3 + k] - dref[k]; } // stale pos_ref (quirk)
     } else {
@@ -426,7 +428,7 @@ uav_pos_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200en
 #pragma unroll
         for (int k = 0; k < 12; ++k) x[k] = ld<T>(io.state, n, k, i);
     } else {
-        pos_reset_state<T>(p, io, n, i, seed, off, x);
+        pos_reset_state<T, int64_t>(p, io, n, i, seed, off, x);
     }
     if (io.next_obs) {
 #pragma unroll
@@ -443,6 +445,19 @@ uav_pos_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200en
     do {                                                                                           \
         if (dtype == B200ENV_F64) kern<double><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);   \
         else kern<float><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                         \
+    } while (0)
+
+// step kernels: 32-bit SoA index arithmetic whenever every [field][n] offset fits in 32 bits
+#define UAV_LAUNCH_STEP(kern, fields, ...)                                                                         \
+    do {                                                                                                           \
+        const bool i32 = (int64_t)(fields) * n < ((int64_t)1 << 32);                                               \
+        if (dtype == B200ENV_F64) {                                                                                \
+            if (i32) kern<double, uint32_t><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                      \
+            else kern<double, int64_t><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                           \
+        } else {                                                                                                   \
+            if (i32) kern<float, uint32_t><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                       \
+            else kern<float, int64_t><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                            \
+        }                                                                                                          \
     } while (0)
 
 int uav_att_dims(int variant, int *sf, int *od, int *ad, int *dd) {
@@ -473,7 +488,7 @@ int uav_att_step(int dtype, int64_t n, const void *params, const b200env_io *io,
     int rc = uav_check_step(io, flags);
     if (rc) return rc;
     const P &p = *static_cast<const P *>(params);
-    UAV_LAUNCH(uav_att_step_kernel, p, *io, n, flags, seed, off);
+    UAV_LAUNCH_STEP(uav_att_step_kernel, B200_UAV_ATT_STATE_FIELDS, p, *io, n, flags, seed, off);
     return b200_check_launch();
 }
 int uav_pos_step(int dtype, int64_t n, const void *params, const b200env_io *io, uint32_t flags, uint64_t seed,
@@ -481,7 +496,7 @@ int uav_pos_step(int dtype, int64_t n, const void *params, const b200env_io *io,
     int rc = uav_check_step(io, flags);
     if (rc) return rc;
     const P &p = *static_cast<const P *>(params);
-    UAV_LAUNCH(uav_pos_step_kernel, p, *io, n, flags, seed, off);
+    UAV_LAUNCH_STEP(uav_pos_step_kernel, B200_UAV_POS_STATE_FIELDS, p, *io, n, flags, seed, off);
     return b200_check_launch();
 }
 int uav_att_reset(int dtype, int64_t n, const void *params, const b200env_io *io, const uint8_t *mask, uint64_t seed,
