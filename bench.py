@@ -43,6 +43,12 @@ ALGO_BYTES = {
 }
 # algorithmic fp64 work per env-step (weighted flops, SURVEY.md section 8d convention), used for the fp64-pipe view
 ALGO_FLOPS = {"uav_pos": 5100.0, "uav_att": 3300.0, "cartpole": 3100.0, "ugvo": 54000.0, "soi": 125.0, "fas": 570.0}
+# what the kernel really executes per env-step, counted from the ncu SASS page of the profiled launch
+# (profiles/r1/uav_pos_step_ncu_v4_ophist.txt): fp64-pipe instructions (DFMA + DMUL + DADD + DSETP) and flops (DFMA = 2)
+EXEC_F64 = {"uav_pos": {"pipe_inst": 2342.0, "flops": 3530.0, "src": "profiles/r1/uav_pos_step_ncu_v4_ophist.txt"}}
+# DRAM bytes per launch of the dominant kernel from the `ncu --set full` capture (dram__bytes_read + write), at the
+# profiled size; None where no capture is committed
+NCU_TRAFFIC = {("uav_pos", "f64", 1 << 20): {"bytes": 344107520 + 426992640, "src": "profiles/r1/uav_pos_step_ncu_v4_keys.txt"}}
 
 WORKLOADS = {
     "uav_pos": dict(n=1 << 20, desc="UavFntsmcParam position tracking, dt=0.02, time_max=10, 8 gains~U(0,5)/step"),
@@ -54,10 +60,10 @@ WORKLOADS = {
 }
 
 
-def make_env(workload, n, device, offset, dtype=torch.float64, host_only=False):
+def make_env(workload, n, device, offset, dtype=torch.float64, host_only=False, io_dtype=None):
     import reinforcementlearningplatform_b200 as rlp
     kw = dict(n_envs=n, device=device, dtype=dtype, seed=2024, env_index_offset=offset, auto_reset=True,
-              host_only=host_only)
+              host_only=host_only, io_dtype=io_dtype)
     if workload == "uav_pos":
         return rlp.UavPosCtrlRL(random_trajectory=True, **kw)
     if workload == "uav_att":
@@ -149,7 +155,7 @@ def timed_steps(env, pool, steps, warmup, dist_on):
     return ms
 
 
-def timed_e2e(workload, n, steps, warmup, dist_on, seed, device, offset, dtype, chunks=4):
+def timed_e2e(workload, n, steps, warmup, dist_on, seed, device, offset, dtype, chunks=4, io_dtype=None):
     """Same metric through the public API with HOST buffers.  Every step, for every instance: the actions are copied
     from pinned host memory, the step kernel runs, and policy_state / reward / is_terminal are read back to pinned host
     memory, where the host waits for them before it issues that instance's next action.  The batch is split into
@@ -159,11 +165,12 @@ def timed_e2e(workload, n, steps, warmup, dist_on, seed, device, offset, dtype, 
     nc = n // chunks
     envs, streams = [], []
     for c in range(chunks):
-        e = make_env(workload, nc, device, offset + c * nc, dtype)
+        e = make_env(workload, nc, device, offset + c * nc, dtype, io_dtype=io_dtype)
         e.reset(True)
         envs.append(e)
         streams.append(torch.cuda.Stream(device=device))
     A, S = envs[0].action_dim, envs[0].state_dim
+    dtype = io_dtype or dtype  # element type of every host <-> device buffer below
     rng = np.random.default_rng(seed)
     ar = np.asarray(envs[0].action_range, dtype=np.float64)
     host_a = [[torch.from_numpy(rng.uniform(ar[:, :1], ar[:, 1:], size=(A, nc))).to(dtype).pin_memory() for _ in range(2)]
@@ -339,6 +346,18 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     achieved = algo_bytes / per_launch_s / 1e9
+    from reinforcementlearningplatform_b200 import _lib
+    fma_peak = _lib.measure_fma_peak(_lib.F64 if el == 8 else _lib.F32)  # TFLOP/s, live, this GPU
+    pipe = {"achieved_tflops_weighted": ALGO_FLOPS[args.workload] * n / per_launch_s / 1e12,
+            "peak_tflops_fma": fma_peak, "peak_source": "b200_measure_fma_peak, live (8 independent FMA chains/thread)",
+            "note": "weighted = algorithmic flops in the SURVEY 8d convention (transcendentals at fixed weights)"}
+    if args.workload in EXEC_F64 and el == 8:
+        ex = EXEC_F64[args.workload]
+        pipe.update({"executed_tflops": ex["flops"] * n / per_launch_s / 1e12,
+                     "frac_flops": ex["flops"] * n / per_launch_s / 1e12 / fma_peak,
+                     "frac_pipe_slots": ex["pipe_inst"] * n / per_launch_s / 1e12 / (fma_peak / 2.0),
+                     "executed_per_step": ex})
+    tr = NCU_TRAFFIC.get((args.workload, args.dtype, n))
     line = {
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -348,21 +367,29 @@ def main():
                    "l2": "per-step working set (state + action + outputs) exceeds the 126 MB L2; 4 rotating action buffers"
                    if n >= (1 << 19) else "working set fits L2 (config size); launch-bound"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+                     "traffic": tr["bytes"] if tr else None, "traffic_source": tr["src"] if tr else None,
+                     "algorithmic_bytes": algo_bytes,
+                     "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                      "kernel": f"{args.workload}_step_kernel<{'double' if el == 8 else 'float'}>",
-                     "fp64_pipe": {"achieved_tflops_weighted": ALGO_FLOPS[args.workload] * n / per_launch_s / 1e12,
-                                   "note": "weighted algorithmic flops (SURVEY 8d convention); see profiles/ for the measured DFMA peak"}},
+                     "binding": "fp64 pipe / issue (not HBM): see fp64_pipe", "fp64_pipe": pipe},
         "clocks": clocks, "gpu_launches": args.steps,
     }
     if not args.no_extras:
         del env, pool
         torch.cuda.empty_cache()
         e_steps = max(10, args.steps // 4)
-        e_ms, e_n, h2d, d2h = timed_e2e(args.workload, n, e_steps, 3, dist_on, rank + 11, dev, rank * n, dtype)
+        e_ms, e_n, h2d, d2h = timed_e2e(args.workload, n, e_steps, 3, dist_on, rank + 11, dev, rank * n, dtype,
+                                        io_dtype=torch.float32)
         line["e2e"] = {"value": world * e_n * e_steps / (e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": d2h,
-                       "api": "VecEnv.step_soa on 4 shards / 4 streams: pinned host actions in, policy_state + reward + "
-                              "is_terminal out every step; the host waits for a shard's result before its next action"}
+                       "d2h_bytes_per_step": d2h, "io_dtype": "f32", "state_and_arithmetic": args.dtype,
+                       "api": "VecEnv.step_soa on 4 shards / 4 streams: pinned host float32 actions in (the reference's "
+                              "actor emits float32), float32 policy_state + reward and u8 is_terminal out every step; "
+                              "state and arithmetic stay in the env dtype; the host waits for a shard's result before "
+                              "its next action"}
+        if dtype == torch.float64:
+            f_ms, f_n, fh, fd = timed_e2e(args.workload, n, e_steps, 3, dist_on, rank + 11, dev, rank * n, dtype)
+            line["e2e_f64_io"] = {"value": world * f_n * e_steps / (f_ms * 1e-3), "unit": "env-steps/s",
+                                  "h2d_bytes_per_step": fh, "d2h_bytes_per_step": fd, "io_dtype": "f64"}
         if rank == 0 and world == 1:
             line["also"] = also_workloads(args, dev, dtype, peaks)
         if rank == 0 and world == 1:

@@ -90,6 +90,13 @@ typedef struct b200env_io {
     int32_t       *flag;       /* [n]                i32     `terminal_flag`                            */
     void          *reset_obs;  /* [obs_dim][n]       dtype   obs the policy sees next: s' or, where an
                                                              auto-reset happened, the reset obs; may be NULL */
+    int32_t        io_dtype;   /* element type of the RL-facing buffers action, dis, obs, next_obs, reward and
+                                  reset_obs: B200ENV_F64 (0) = same as `dtype` (default), B200ENV_F32 = float32 even
+                                  when dtype is F64.  The RL side of the reference is float32 (actor output
+                                  Proximal_Policy_Optimization2.py:69-76, RolloutBuffer.to_tensor
+                                  utils/classes.py:292-301), so float32 I/O with float64 state and arithmetic keeps the
+                                  fp64 trajectory and halves the interface bytes (PCIe, rollout buffer). */
+    int32_t        pad_;
 } b200env_io;
 
 /* ------------------------------------------------------ per-env parameters */

@@ -102,7 +102,7 @@ __device__ __forceinline__ void store_state(const CartPole<T> &e, const b200env_
     io.time[i] = e.time;
 }
 
-template <typename T>
+template <typename T, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK)
 cartpole_step_kernel(const __grid_constant__ b200_cartpole_params p, const __grid_constant__ b200env_io io,
                      int64_t n, uint32_t flags, uint64_t seed, int64_t off) {
@@ -113,12 +113,12 @@ cartpole_step_kernel(const __grid_constant__ b200_cartpole_params p, const __gri
     CartPole<T> e;
     e.init_consts(p);
     load_state(e, io, n, i);
-    e.force = ld<T>(io.action, n, 0, i);
+    e.force = ldio<T, IO32>(io.action, n, 0, i);
 
     T cur[4];
     e.observe(p, cur); // self.current_state = self.get_state()
     if (io.obs) {
-        for (int k = 0; k < obs_dim; ++k) st<T>(io.obs, n, k, i, cur[k]);
+        for (int k = 0; k < obs_dim; ++k) stio<T, IO32>(io.obs, n, k, i, cur[k]);
     }
 
     // ---- rk44
@@ -190,8 +190,8 @@ cartpole_step_kernel(const __grid_constant__ b200_cartpole_params p, const __gri
         reward = r1 + r4;
     }
 
-    for (int k = 0; k < obs_dim; ++k) st<T>(io.next_obs, n, k, i, nxt[k]);
-    st<T>(io.reward, n, 0, i, reward);
+    for (int k = 0; k < obs_dim; ++k) stio<T, IO32>(io.next_obs, n, k, i, nxt[k]);
+    stio<T, IO32>(io.reward, n, 0, i, reward);
     io.done[i] = done ? 1 : 0;
     io.flag[i] = flag;
 
@@ -202,12 +202,12 @@ cartpole_step_kernel(const __grid_constant__ b200_cartpole_params p, const __gri
         e.observe(p, nxt);
     }
     if (io.reset_obs) {
-        for (int k = 0; k < obs_dim; ++k) st<T>(io.reset_obs, n, k, i, nxt[k]);
+        for (int k = 0; k < obs_dim; ++k) stio<T, IO32>(io.reset_obs, n, k, i, nxt[k]);
     }
     store_state(e, io, n, i);
 }
 
-template <typename T>
+template <typename T, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK)
 cartpole_reset_kernel(const __grid_constant__ b200_cartpole_params p, const __grid_constant__ b200env_io io,
                       int64_t n, const uint8_t *mask, uint64_t seed, int64_t off, int observe_only) {
@@ -227,7 +227,7 @@ cartpole_reset_kernel(const __grid_constant__ b200_cartpole_params p, const __gr
         T o[4];
         e.observe(p, o);
         const int obs_dim = p.variant == 0 ? 4 : 2;
-        for (int k = 0; k < obs_dim; ++k) st<T>(io.next_obs, n, k, i, o[k]);
+        for (int k = 0; k < obs_dim; ++k) stio<T, IO32>(io.next_obs, n, k, i, o[k]);
     }
 }
 
@@ -249,10 +249,7 @@ int cartpole_step(int dtype, int64_t n, const void *params, const b200env_io *io
     if (!io->state || !io->time || !io->action || !io->next_obs || !io->reward || !io->done || !io->flag)
         return B200ENV_ENULL;
     if ((flags & B200ENV_AUTO_RESET) && !io->episode) return B200ENV_ENULL;
-    if (dtype == B200ENV_F64)
-        cartpole_step_kernel<double><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
-    else
-        cartpole_step_kernel<float><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
+    B200_LAUNCH_TIO(cartpole_step_kernel, b200_grid(n), B200_BLOCK, s, p, *io, n, flags, seed, off);
     return b200_check_launch();
 }
 
@@ -261,10 +258,7 @@ int cartpole_reset(int dtype, int64_t n, const void *params, const b200env_io *i
     const b200_cartpole_params &p = *static_cast<const b200_cartpole_params *>(params);
     if (p.variant < 0 || p.variant > 2) return B200ENV_EENV;
     if (!io->state || !io->time || !io->episode) return B200ENV_ENULL;
-    if (dtype == B200ENV_F64)
-        cartpole_reset_kernel<double><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, mask, seed, off, 0);
-    else
-        cartpole_reset_kernel<float><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, mask, seed, off, 0);
+    B200_LAUNCH_TIO(cartpole_reset_kernel, b200_grid(n), B200_BLOCK, s, p, *io, n, mask, seed, off, 0);
     return b200_check_launch();
 }
 
@@ -272,9 +266,6 @@ int cartpole_observe(int dtype, int64_t n, const void *params, const b200env_io 
     const b200_cartpole_params &p = *static_cast<const b200_cartpole_params *>(params);
     if (p.variant < 0 || p.variant > 2) return B200ENV_EENV;
     if (!io->state || !io->time || !io->next_obs) return B200ENV_ENULL;
-    if (dtype == B200ENV_F64)
-        cartpole_reset_kernel<double><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, nullptr, 0, 0, 1);
-    else
-        cartpole_reset_kernel<float><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, nullptr, 0, 0, 1);
+    B200_LAUNCH_TIO(cartpole_reset_kernel, b200_grid(n), B200_BLOCK, s, p, *io, n, nullptr, 0, 0, 1);
     return b200_check_launch();
 }

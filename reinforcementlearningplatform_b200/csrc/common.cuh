@@ -96,6 +96,21 @@ __device__ __forceinline__ T pow_from_log(T L, T a) {
     return a == (T)0 ? (T)1 : r;
 }
 
+// I/O-side accessors (action, dis in; obs, next_obs, reward, reset_obs out).  IO32 = the buffers hold float32 although
+// the kernel computes in T = double (b200env_io::io_dtype == B200ENV_F32): the RL side of the reference is float32
+// (actor output, RolloutBuffer.to_tensor utils/classes.py:292-301), so float32 I/O halves the PCIe / HBM bytes of the
+// interface without touching the fp64 trajectory.  float -> double is exact; outputs are rounded once on store.
+template <typename T, bool IO32, typename I>
+__device__ __forceinline__ T ldio(const void *base, I n, int field, I i) {
+    if (IO32) return (T) static_cast<const float *>(base)[(I)field * n + i];
+    return static_cast<const T *>(base)[(I)field * n + i];
+}
+template <typename T, bool IO32, typename I>
+__device__ __forceinline__ void stio(void *base, I n, int field, I i, T v) {
+    if (IO32) static_cast<float *>(base)[(I)field * n + i] = (float)v;
+    else static_cast<T *>(base)[(I)field * n + i] = v;
+}
+
 // ---------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter = (env index lo, env index hi,
 // episode, block); key = 64-bit seed.  Results are therefore independent of
@@ -168,6 +183,15 @@ static inline int b200_check_launch() {
     return B200ENV_OK;
 }
 
+// float32 I/O buffers with fp64 arithmetic (b200env_io::io_dtype); in F32 mode everything is float anyway
+static inline bool b200_io32(const b200env_io *io) { return io->io_dtype == B200ENV_F32; }
+// launches KERN<T, IO32> for (double, io32) / (double, native) / float; expects `dtype` and `io` in scope
+#define B200_LAUNCH_TIO(KERN, grid, block, s, ...)                                                                   \
+    do {                                                                                                             \
+        if (dtype == B200ENV_F64 && b200_io32(io)) KERN<double, true><<<grid, block, 0, s>>>(__VA_ARGS__);           \
+        else if (dtype == B200ENV_F64) KERN<double, false><<<grid, block, 0, s>>>(__VA_ARGS__);                      \
+        else KERN<float, false><<<grid, block, 0, s>>>(__VA_ARGS__);                                                 \
+    } while (0)
 static inline unsigned b200_grid(int64_t n, int block = B200_BLOCK) { return (unsigned)((n + block - 1) / block); }
 
 // per-family entry points (defined in the family's .cu file)

@@ -10,7 +10,7 @@
 #pragma once
 #include "common.cuh"
 
-template <typename T, class E>
+template <typename T, class E, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK)
 env_step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ b200env_io io, int64_t n,
                 uint32_t flags, uint64_t seed, int64_t off) {
@@ -20,20 +20,20 @@ env_step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__
     e.load(io, n, i);
     T act[E::AD];
 #pragma unroll
-    for (int k = 0; k < E::AD; ++k) act[k] = ld<T>(io.action, n, k, i);
+    for (int k = 0; k < E::AD; ++k) act[k] = ldio<T, IO32>(io.action, n, k, i);
     T cur[E::OD], nxt[E::OD];
     e.observe(p, cur); // self.current_state = self.get_state()
     if (io.obs) {
 #pragma unroll
-        for (int k = 0; k < E::OD; ++k) st<T>(io.obs, n, k, i, cur[k]);
+        for (int k = 0; k < E::OD; ++k) stio<T, IO32>(io.obs, n, k, i, cur[k]);
     }
     int flag = 0;
     bool done = false;
     T reward = (T)0;
     e.step(p, act, cur, flag, done, reward, nxt);
 #pragma unroll
-    for (int k = 0; k < E::OD; ++k) st<T>(io.next_obs, n, k, i, nxt[k]);
-    st<T>(io.reward, n, 0, i, reward);
+    for (int k = 0; k < E::OD; ++k) stio<T, IO32>(io.next_obs, n, k, i, nxt[k]);
+    stio<T, IO32>(io.reward, n, 0, i, reward);
     io.done[i] = done ? 1 : 0;
     io.flag[i] = flag;
     if (done && (flags & B200ENV_AUTO_RESET)) {
@@ -45,12 +45,12 @@ env_step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__
     }
     if (io.reset_obs) {
 #pragma unroll
-        for (int k = 0; k < E::OD; ++k) st<T>(io.reset_obs, n, k, i, nxt[k]);
+        for (int k = 0; k < E::OD; ++k) stio<T, IO32>(io.reset_obs, n, k, i, nxt[k]);
     }
     e.store(io, n, i);
 }
 
-template <typename T, class E>
+template <typename T, class E, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK)
 env_reset_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ b200env_io io, int64_t n,
                  const uint8_t *mask, uint64_t seed, int64_t off, int observe_only) {
@@ -70,7 +70,7 @@ env_reset_kernel(const __grid_constant__ typename E::P p, const __grid_constant_
         T o[E::OD];
         e.observe(p, o);
 #pragma unroll
-        for (int k = 0; k < E::OD; ++k) st<T>(io.next_obs, n, k, i, o[k]);
+        for (int k = 0; k < E::OD; ++k) stio<T, IO32>(io.next_obs, n, k, i, o[k]);
     }
 }
 
@@ -83,10 +83,12 @@ int env_launch_step(int dtype, int64_t n, const void *params, const b200env_io *
         return B200ENV_ENULL;
     if ((flags & B200ENV_AUTO_RESET) && !io->episode) return B200ENV_ENULL;
     const P &p = *static_cast<const P *>(params);
-    if (dtype == B200ENV_F64)
-        env_step_kernel<double, EnvT<double>><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
+    if (dtype == B200ENV_F64 && b200_io32(io))
+        env_step_kernel<double, EnvT<double>, true><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
+    else if (dtype == B200ENV_F64)
+        env_step_kernel<double, EnvT<double>, false><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
     else
-        env_step_kernel<float, EnvT<float>><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
+        env_step_kernel<float, EnvT<float>, false><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
     return b200_check_launch();
 }
 
@@ -98,10 +100,12 @@ int env_launch_reset(int dtype, int64_t n, const void *params, const b200env_io 
     if (!observe_only && !io->episode) return B200ENV_ENULL;
     if (observe_only && !io->next_obs) return B200ENV_ENULL;
     const P &p = *static_cast<const P *>(params);
-    if (dtype == B200ENV_F64)
-        env_reset_kernel<double, EnvT<double>><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, mask, seed, off, observe_only);
+    if (dtype == B200ENV_F64 && b200_io32(io))
+        env_reset_kernel<double, EnvT<double>, true><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, mask, seed, off, observe_only);
+    else if (dtype == B200ENV_F64)
+        env_reset_kernel<double, EnvT<double>, false><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, mask, seed, off, observe_only);
     else
-        env_reset_kernel<float, EnvT<float>><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, mask, seed, off, observe_only);
+        env_reset_kernel<float, EnvT<float>, false><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, mask, seed, off, observe_only);
     return b200_check_launch();
 }
 

@@ -93,7 +93,7 @@ __device__ __forceinline__ void att_observe(const T *x, const Trig<T> &t, const 
     o[5] = ((t.sphi / t.cth) * q + (t.cphi / t.cth) * r) - dref[2];
 }
 
-template <typename T, typename I>
+template <typename T, typename I, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK, UAV_ATT_MINBLOCKS)
 uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n_, uint32_t flags,
                     uint64_t seed, int64_t off) {
@@ -108,7 +108,7 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     T s1[3], k1[3], k2[3], gam[3], lmd[3], alpha[3], beta[3], ref[3], dref[3];
     T a[8], rA[3], rT[3], rP[3];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] = ld<T>(io.action, n, k, i);
+    for (int k = 0; k < 8; ++k) a[k] = ldio<T, IO32>(io.action, n, k, i);
     // all loads before the first store (see uav_pos_step_kernel)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -148,8 +148,8 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     if (io.obs) { // current_state = get_state()
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            st<T>(io.obs, n, k, i, x[6 + k] - ref[k]);
-            st<T>(io.obs, n, 3 + k, i, d1[k] - dref[k]);
+            stio<T, IO32>(io.obs, n, k, i, x[6 + k] - ref[k]);
+            stio<T, IO32>(io.obs, n, 3 + k, i, d1[k] - dref[k]);
         }
     }
     // update(): throttle only drives the (zeroed) translational states in att_only mode, uav_att_ctrl.py:110-128
@@ -177,8 +177,8 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     }
     const T reward = u_att + u_pqr + u_acc + u_extra;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) st<T>(io.next_obs, n, k, i, nxt[k]);
-    st<T>(io.reward, n, 0, i, reward);
+    for (int k = 0; k < 6; ++k) stio<T, IO32>(io.next_obs, n, k, i, nxt[k]);
+    stio<T, IO32>(io.reward, n, 0, i, reward);
     io.done[i] = done ? 1 : 0;
     io.flag[i] = flag;
     if (done && (flags & B200ENV_AUTO_RESET)) {
@@ -198,11 +198,11 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     }
     if (io.reset_obs) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) st<T>(io.reset_obs, n, k, i, nxt[k]);
+        for (int k = 0; k < 6; ++k) stio<T, IO32>(io.reset_obs, n, k, i, nxt[k]);
     }
 }
 
-template <typename T>
+template <typename T, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK)
 uav_att_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n,
                      const uint8_t *mask, uint64_t seed, int64_t off, int observe_only) {
@@ -224,7 +224,7 @@ uav_att_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200en
         t.eval(x[6], x[7], x[8], false);
         att_observe<T>(x, t, ref, dref, o);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) st<T>(io.next_obs, n, k, i, o[k]);
+        for (int k = 0; k < 6; ++k) stio<T, IO32>(io.next_obs, n, k, i, o[k]);
     }
 }
 
@@ -271,7 +271,7 @@ __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io
     io.episode[i] = ep + 1u;
 }
 
-template <typename T, typename I>
+template <typename T, typename I, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK, UAV_POS_MINBLOCKS)
 uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n_, uint32_t flags,
                     uint64_t seed, int64_t off) {
@@ -285,10 +285,10 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     double time = io.time[i];
     T a[8], dis[3] = {(T)0, (T)0, (T)0};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] = ld<T>(io.action, n, k, i);
+    for (int k = 0; k < 8; ++k) a[k] = ldio<T, IO32>(io.action, n, k, i);
     if (io.dis) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) dis[k] = ld<T>(io.dis, n, k, i);
+        for (int k = 0; k < 3; ++k) dis[k] = ldio<T, IO32>(io.dis, n, k, i);
     }
     // All loads are issued here, before the first store: the compiler cannot move a load above a store to the same
     // buffer (possible aliasing), and a mid-kernel DRAM load is not hidden by the 4 resident warps per scheduler.
@@ -370,8 +370,8 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     if (io.obs) { // current_state = get_state(), uav_pos_ctrl_RL.py:59-68
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            st<T>(io.obs, n, k, i, x[k] - ref[k]);
-            st<T>(io.obs, n, 3 + k, i, x[3 + k] - dref[k]);
+            stio<T, IO32>(io.obs, n, k, i, x[k] - ref[k]);
+            stio<T, IO32>(io.obs, n, 3 + k, i, x[3 + k] - dref[k]);
         }
     }
     // ---- update(): rk44(action, dis, n = 1), uav_pos_ctrl.py:359-376
@@ -392,8 +392,8 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     }
     const T reward = u_pos + u_vel + u_acc + u_extra;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) st<T>(io.next_obs, n, k, i, nxt[k]);
-    st<T>(io.reward, n, 0, i, reward);
+    for (int k = 0; k < 6; ++k) stio<T, IO32>(io.next_obs, n, k, i, nxt[k]);
+    stio<T, IO32>(io.reward, n, 0, i, reward);
     io.done[i] = done ? 1 : 0;
     io.flag[i] = flag;
     if (done && (flags & B200ENV_AUTO_RESET)) {
@@ -412,11 +412,11 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     }
     if (io.reset_obs) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) st<T>(io.reset_obs, n, k, i, nxt[k]);
+        for (int k = 0; k < 6; ++k) stio<T, IO32>(io.reset_obs, n, k, i, nxt[k]);
     }
 }
 
-template <typename T>
+template <typename T, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK)
 uav_pos_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n,
                      const uint8_t *mask, uint64_t seed, int64_t off, int observe_only) {
@@ -433,30 +433,30 @@ uav_pos_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200en
     if (io.next_obs) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            st<T>(io.next_obs, n, k, i, x[k] - ld<T>(io.state, n, P_PREF + k, i));
-            st<T>(io.next_obs, n, 3 + k, i, x[3 + k] - ld<T>(io.state, n, P_DPREF + k, i));
+            stio<T, IO32>(io.next_obs, n, k, i, x[k] - ld<T>(io.state, n, P_PREF + k, i));
+            stio<T, IO32>(io.next_obs, n, 3 + k, i, x[3 + k] - ld<T>(io.state, n, P_DPREF + k, i));
         }
     }
 }
 
 } // namespace
 
-#define UAV_LAUNCH(kern, ...)                                                                      \
-    do {                                                                                           \
-        if (dtype == B200ENV_F64) kern<double><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);   \
-        else kern<float><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                         \
-    } while (0)
+#define UAV_LAUNCH(kern, ...) B200_LAUNCH_TIO(kern, b200_grid(n), B200_BLOCK, s, __VA_ARGS__)
 
 // step kernels: 32-bit SoA index arithmetic whenever every [field][n] offset fits in 32 bits
 #define UAV_LAUNCH_STEP(kern, fields, ...)                                                                         \
     do {                                                                                                           \
         const bool i32 = (int64_t)(fields) * n < ((int64_t)1 << 32);                                               \
+        const bool o32 = b200_io32(io);                                                                            \
+        const unsigned g = b200_grid(n);                                                                           \
         if (dtype == B200ENV_F64) {                                                                                \
-            if (i32) kern<double, uint32_t><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                      \
-            else kern<double, int64_t><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                           \
+            if (i32 && o32) kern<double, uint32_t, true><<<g, B200_BLOCK, 0, s>>>(__VA_ARGS__);                    \
+            else if (i32) kern<double, uint32_t, false><<<g, B200_BLOCK, 0, s>>>(__VA_ARGS__);                     \
+            else if (o32) kern<double, int64_t, true><<<g, B200_BLOCK, 0, s>>>(__VA_ARGS__);                       \
+            else kern<double, int64_t, false><<<g, B200_BLOCK, 0, s>>>(__VA_ARGS__);                               \
         } else {                                                                                                   \
-            if (i32) kern<float, uint32_t><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                       \
-            else kern<float, int64_t><<<b200_grid(n), B200_BLOCK, 0, s>>>(__VA_ARGS__);                            \
+            if (i32) kern<float, uint32_t, false><<<g, B200_BLOCK, 0, s>>>(__VA_ARGS__);                           \
+            else kern<float, int64_t, false><<<g, B200_BLOCK, 0, s>>>(__VA_ARGS__);                                \
         }                                                                                                          \
     } while (0)
 

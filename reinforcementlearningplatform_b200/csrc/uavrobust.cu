@@ -108,7 +108,7 @@ __device__ __forceinline__ void reset_state(const RP &r, const b200env_io &io, i
     io.episode[i] = ep + 1u;
 }
 
-template <typename T, int V>
+template <typename T, int V, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK, 4)
 uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
                       uint64_t seed, int64_t off) {
@@ -122,10 +122,10 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ b200
     double time = io.time[i];
     T a[AD], dis[3] = {(T)0, (T)0, (T)0};
 #pragma unroll
-    for (int k = 0; k < AD; ++k) a[k] = ld<T>(io.action, n, k, i);
+    for (int k = 0; k < AD; ++k) a[k] = ldio<T, IO32>(io.action, n, k, i);
     if (V != 2 && io.dis) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) dis[k] = ld<T>(io.dis, n, k, i);
+        for (int k = 0; k < 3; ++k) dis[k] = ldio<T, IO32>(io.dis, n, k, i);
     }
     T s1[3], aref_old[3];
 #pragma unroll
@@ -139,7 +139,7 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ b200
     observe<T, V>(r, io, n, i, x, t1, time, cur, e, de); // current_state = get_state()
     if (io.obs) {
 #pragma unroll
-        for (int k = 0; k < S; ++k) st<T>(io.obs, n, k, i, cur[k]);
+        for (int k = 0; k < S; ++k) stio<T, IO32>(io.obs, n, k, i, cur[k]);
     }
     T torque[3], uf = (T)0;
     if (V == 2) { // UavInnerLoop.py:127-133: the action is the torque; throttle 0, attitude only
@@ -238,8 +238,8 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ b200
         reward = r1 + r2 + r3 + r4;
     }
 #pragma unroll
-    for (int k = 0; k < S; ++k) st<T>(io.next_obs, n, k, i, nxt[k]);
-    st<T>(io.reward, n, 0, i, reward);
+    for (int k = 0; k < S; ++k) stio<T, IO32>(io.next_obs, n, k, i, nxt[k]);
+    stio<T, IO32>(io.reward, n, 0, i, reward);
     io.done[i] = done ? 1 : 0;
     io.flag[i] = flag;
     if (done && (flags & B200ENV_AUTO_RESET)) {
@@ -251,11 +251,11 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ b200
     }
     if (io.reset_obs) {
 #pragma unroll
-        for (int k = 0; k < S; ++k) st<T>(io.reset_obs, n, k, i, nxt[k]);
+        for (int k = 0; k < S; ++k) stio<T, IO32>(io.reset_obs, n, k, i, nxt[k]);
     }
 }
 
-template <typename T, int V>
+template <typename T, int V, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK)
 uavrobust_reset_kernel(const __grid_constant__ RP r, const __grid_constant__ b200env_io io, int64_t n,
                        const uint8_t *mask, uint64_t seed, int64_t off, int observe_only) {
@@ -276,31 +276,31 @@ uavrobust_reset_kernel(const __grid_constant__ RP r, const __grid_constant__ b20
         t.eval(x[6], x[7], x[8], false);
         observe<T, V>(r, io, n, i, x, t, io.time[i], o, e, de);
 #pragma unroll
-        for (int k = 0; k < S; ++k) st<T>(io.next_obs, n, k, i, o[k]);
+        for (int k = 0; k < S; ++k) stio<T, IO32>(io.next_obs, n, k, i, o[k]);
     }
 }
 
-template <typename T>
+template <typename T, bool IO32>
 int launch_step(int V, const RP &r, const b200env_io &io, int64_t n, uint32_t flags, uint64_t seed, int64_t off, cudaStream_t s) {
     const unsigned g = b200_grid(n);
     switch (V) {
-    case 0: uavrobust_step_kernel<T, 0><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
-    case 1: uavrobust_step_kernel<T, 1><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
-    case 2: uavrobust_step_kernel<T, 2><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
-    case 3: uavrobust_step_kernel<T, 3><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
+    case 0: uavrobust_step_kernel<T, 0, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
+    case 1: uavrobust_step_kernel<T, 1, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
+    case 2: uavrobust_step_kernel<T, 2, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
+    case 3: uavrobust_step_kernel<T, 3, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
     default: return B200ENV_EENV;
     }
     return b200_check_launch();
 }
-template <typename T>
+template <typename T, bool IO32>
 int launch_reset(int V, const RP &r, const b200env_io &io, int64_t n, const uint8_t *mask, uint64_t seed, int64_t off,
                  int observe_only, cudaStream_t s) {
     const unsigned g = b200_grid(n);
     switch (V) {
-    case 0: uavrobust_reset_kernel<T, 0><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
-    case 1: uavrobust_reset_kernel<T, 1><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
-    case 2: uavrobust_reset_kernel<T, 2><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
-    case 3: uavrobust_reset_kernel<T, 3><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
+    case 0: uavrobust_reset_kernel<T, 0, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
+    case 1: uavrobust_reset_kernel<T, 1, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
+    case 2: uavrobust_reset_kernel<T, 2, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
+    case 3: uavrobust_reset_kernel<T, 3, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
     default: return B200ENV_EENV;
     }
     return b200_check_launch();
@@ -321,19 +321,19 @@ int uavrobust_step(int dtype, int64_t n, const void *params, const b200env_io *i
     if (!io->state || !io->time || !io->action || !io->next_obs || !io->reward || !io->done || !io->flag) return B200ENV_ENULL;
     if ((flags & B200ENV_AUTO_RESET) && !io->episode) return B200ENV_ENULL;
     const RP &r = *static_cast<const RP *>(params);
-    return dtype == B200ENV_F64 ? launch_step<double>(r.variant, r, *io, n, flags, seed, off, s)
-                                : launch_step<float>(r.variant, r, *io, n, flags, seed, off, s);
+    if (dtype == B200ENV_F64 && b200_io32(io)) return launch_step<double, true>(r.variant, r, *io, n, flags, seed, off, s);
+    return dtype == B200ENV_F64 ? launch_step<double, false>(r.variant, r, *io, n, flags, seed, off, s) : launch_step<float, false>(r.variant, r, *io, n, flags, seed, off, s);
 }
 int uavrobust_reset(int dtype, int64_t n, const void *params, const b200env_io *io, const uint8_t *mask, uint64_t seed,
                     int64_t off, cudaStream_t s) {
     if (!io->state || !io->time || !io->episode) return B200ENV_ENULL;
     const RP &r = *static_cast<const RP *>(params);
-    return dtype == B200ENV_F64 ? launch_reset<double>(r.variant, r, *io, n, mask, seed, off, 0, s)
-                                : launch_reset<float>(r.variant, r, *io, n, mask, seed, off, 0, s);
+    if (dtype == B200ENV_F64 && b200_io32(io)) return launch_reset<double, true>(r.variant, r, *io, n, mask, seed, off, 0, s);
+    return dtype == B200ENV_F64 ? launch_reset<double, false>(r.variant, r, *io, n, mask, seed, off, 0, s) : launch_reset<float, false>(r.variant, r, *io, n, mask, seed, off, 0, s);
 }
 int uavrobust_observe(int dtype, int64_t n, const void *params, const b200env_io *io, cudaStream_t s) {
     if (!io->state || !io->time || !io->next_obs) return B200ENV_ENULL;
     const RP &r = *static_cast<const RP *>(params);
-    return dtype == B200ENV_F64 ? launch_reset<double>(r.variant, r, *io, n, nullptr, 0, 0, 1, s)
-                                : launch_reset<float>(r.variant, r, *io, n, nullptr, 0, 0, 1, s);
+    if (dtype == B200ENV_F64 && b200_io32(io)) return launch_reset<double, true>(r.variant, r, *io, n, nullptr, 0, 0, 1, s);
+    return dtype == B200ENV_F64 ? launch_reset<double, false>(r.variant, r, *io, n, nullptr, 0, 0, 1, s) : launch_reset<float, false>(r.variant, r, *io, n, nullptr, 0, 0, 1, s);
 }

@@ -244,7 +244,7 @@ __device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gi
 enum { F_X = 0, F_Y, F_VEL, F_PHI, F_OMEGA, F_TX, F_TY, F_NOBS, F_OBS };
 
 // shared body of step / reset / observe.  mode 0 = step, 1 = reset (masked), 2 = observe only
-template <typename T>
+template <typename T, bool IO32>
 __global__ void __launch_bounds__(WARPS * 32)
 ugvo_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
             uint64_t seed, int64_t off, const uint8_t *mask, int mode) {
@@ -290,16 +290,16 @@ ugvo_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, 
         for (int pass = 0; pass * 32 < NR; ++pass) {
             const int ray = pass * 32 + lane;
             const T l = cast_ray<T>(p, q, ray < NR ? ray : 0, nobs, s_obs[w][slot], ray < NR);
-            if (ray < NR && dst) st<T>(dst, n, 4 + ray, i, ((T)2 * l / (T)p.laser_dis - (T)1) * g);
+            if (ray < NR && dst) stio<T, IO32>(dst, n, 4 + ray, i, ((T)2 * l / (T)p.laser_dis - (T)1) * g);
         }
         if (lane == 0 && dst) {
             T s, c;
             Mth<T>::sincos(phi, &s, &c);
             const T e = norm2(tgx - x, tgy - y), ephi = vector_rad_oriented<T>(c, s, tgx - x, tgy - y);
-            st<T>(dst, n, 0, i, ((T)(2 / p.e_max) * e - (T)1) * g);
-            st<T>(dst, n, 1, i, ((T)(2 / p.v_max) * vel - (T)1) * g);
-            st<T>(dst, n, 2, i, ephi / (T)p.e_phi_max * g);
-            st<T>(dst, n, 3, i, omega / (T)p.omega_max * g);
+            stio<T, IO32>(dst, n, 0, i, ((T)(2 / p.e_max) * e - (T)1) * g);
+            stio<T, IO32>(dst, n, 1, i, ((T)(2 / p.v_max) * vel - (T)1) * g);
+            stio<T, IO32>(dst, n, 2, i, ephi / (T)p.e_phi_max * g);
+            stio<T, IO32>(dst, n, 3, i, omega / (T)p.omega_max * g);
         }
         __syncwarp();
     };
@@ -327,7 +327,7 @@ ugvo_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, 
 
     // ---- step_update :510-520
     T al = (T)0;
-    if (lane < 2) al = ld<T>(io.action, n, lane, i);
+    if (lane < 2) al = ldio<T, IO32>(io.action, n, lane, i);
     const T a_lin = shfl<T>(al, 0), a_ang = shfl<T>(al, 1);
     Pose<T> qa, qb;
     qa.x = x; qa.y = y; qa.phi = phi;
@@ -341,10 +341,10 @@ ugvo_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, 
         T s, c;
         Mth<T>::sincos(phi, &s, &c);
         const T g = (T)p.static_gain;
-        st<T>(io.obs, n, 0, i, cur_e);
-        st<T>(io.obs, n, 1, i, ((T)(2 / p.v_max) * vel - (T)1) * g);
-        st<T>(io.obs, n, 2, i, vector_rad_oriented<T>(c, s, tgx - x, tgy - y) / (T)p.e_phi_max * g);
-        st<T>(io.obs, n, 3, i, omega / (T)p.omega_max * g);
+        stio<T, IO32>(io.obs, n, 0, i, cur_e);
+        stio<T, IO32>(io.obs, n, 1, i, ((T)(2 / p.v_max) * vel - (T)1) * g);
+        stio<T, IO32>(io.obs, n, 2, i, vector_rad_oriented<T>(c, s, tgx - x, tgy - y) / (T)p.e_phi_max * g);
+        stio<T, IO32>(io.obs, n, 3, i, omega / (T)p.omega_max * g);
     }
     // rk44 :482-501 / demo copy :488-509 (all lanes, redundantly)
     {
@@ -414,8 +414,8 @@ ugvo_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, 
             const T l = cast_ray<T>(p, q, ray, nobs, s_obs[w][is_b ? 1 : 0], active);
             if (active) {
                 const T v = ((T)2 * l / (T)p.laser_dis - (T)1) * g;
-                st<T>(is_b ? io.next_obs : io.obs, n, 4 + ray, i, v);
-                if (is_b && mirror) st<T>(mirror, n, 4 + ray, i, v);
+                stio<T, IO32>(is_b ? io.next_obs : io.obs, n, 4 + ray, i, v);
+                if (is_b && mirror) stio<T, IO32>(mirror, n, 4 + ray, i, v);
             }
         }
     }
@@ -440,12 +440,12 @@ ugvo_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, 
     }
     if (lane == 0) {
         const T o2 = ephi / (T)p.e_phi_max * g, o3 = omega / (T)p.omega_max * g;
-        st<T>(io.next_obs, n, 0, i, nxt0);
-        st<T>(io.next_obs, n, 1, i, nxt1);
-        st<T>(io.next_obs, n, 2, i, o2);
-        st<T>(io.next_obs, n, 3, i, o3);
-        if (mirror) { st<T>(mirror, n, 0, i, nxt0); st<T>(mirror, n, 1, i, nxt1); st<T>(mirror, n, 2, i, o2); st<T>(mirror, n, 3, i, o3); }
-        st<T>(io.reward, n, 0, i, reward);
+        stio<T, IO32>(io.next_obs, n, 0, i, nxt0);
+        stio<T, IO32>(io.next_obs, n, 1, i, nxt1);
+        stio<T, IO32>(io.next_obs, n, 2, i, o2);
+        stio<T, IO32>(io.next_obs, n, 3, i, o3);
+        if (mirror) { stio<T, IO32>(mirror, n, 0, i, nxt0); stio<T, IO32>(mirror, n, 1, i, nxt1); stio<T, IO32>(mirror, n, 2, i, o2); stio<T, IO32>(mirror, n, 3, i, o3); }
+        stio<T, IO32>(io.reward, n, 0, i, reward);
         io.done[i] = done ? 1 : 0;
         io.flag[i] = flag;
     }
@@ -462,8 +462,7 @@ int launch(int dtype, int64_t n, const void *params, const b200env_io *io, uint3
     const P &p = *static_cast<const P *>(params);
     if (p.n_rays < 2 || p.n_rays > B200_UGVO_MAX_RAYS || p.obs_num < 0 || p.obs_num > MAXO) return B200ENV_EPARAMS;
     const unsigned grid = (unsigned)((n + WARPS - 1) / WARPS);
-    if (dtype == B200ENV_F64) ugvo_kernel<double><<<grid, WARPS * 32, 0, s>>>(p, *io, n, flags, seed, off, mask, mode);
-    else ugvo_kernel<float><<<grid, WARPS * 32, 0, s>>>(p, *io, n, flags, seed, off, mask, mode);
+    B200_LAUNCH_TIO(ugvo_kernel, grid, WARPS * 32, s, p, *io, n, flags, seed, off, mask, mode);
     return b200_check_launch();
 }
 

@@ -27,6 +27,7 @@ class Flight_Attitude_Simulator(_Simple):
     """environment/FlightAttitudeSimulator/FlightAttitudeSimulator.py:9-287.  ``variant='ppo2'`` selects the
     PPO2/DPPO2 demo copy (timeMax = 10, reward Q = 1, R = 0.05; flight_attitude_simulator.py:42,211-224)."""
     ENV_ID = _lib.FAS
+    OBS_IS_PURE = True
     STATE_FIELDS = ("theta", "dTheta")
 
     def __init__(self, n_envs: int = 1, variant: str = 'env', **kw):
@@ -62,6 +63,7 @@ class SecondOrderIntegration(_Simple):
     """environment/SecondOrderIntegration/SecondOrderIntegration.py:13-352.  ``variant='dppo2'``: the DPPO2 demo copy
     (obs * static_gain :213, success terminal disabled :243-246, Q_vel = Q_acc = 0 :260-261)."""
     ENV_ID = _lib.SOI
+    OBS_IS_PURE = True
     STATE_FIELDS = ("x", "y", "vx", "vy")
 
     def __init__(self, n_envs: int = 1, map_size=(5.0, 5.0), target=None, variant: str = 'env', **kw):
@@ -93,6 +95,7 @@ class SecondOrderIntegration(_Simple):
 class BallBalancer1D(_Simple):
     """environment/BallBalancer/BallBalancer1D.py:14-322."""
     ENV_ID = _lib.BALLBALANCER
+    OBS_IS_PURE = True
     STATE_FIELDS = ("pos", "vel", "theta", "error")
 
     def __init__(self, n_envs: int = 1, initVel: float = 0.0, target: float = 0.0, **kw):
@@ -153,6 +156,7 @@ class TwoLinkManipulator(_Simple):
 class UGVForward(_Simple):
     """environment/UGV/UGVForward.py:10-362."""
     ENV_ID = _lib.UGV
+    OBS_IS_PURE = True
     STATE_FIELDS = ("x", "y", "vel", "phi", "omega")
     BIDIRECTIONAL = 0
 
@@ -193,6 +197,7 @@ class UGVForwardObstacleAvoidance(_Simple):
     progress reward, success ignores omega, pose frozen when the previous velocity was negative).  Observation =
     4 kinematic terms + 37 fake-laser ranges (kernel K-UGVO: one warp per instance, lanes = rays)."""
     ENV_ID = _lib.UGVO
+    OBS_IS_PURE = True
     MAX_OBS = 16
     STATE_FIELDS = tuple(["x", "y", "vel", "phi", "omega", "target_x", "target_y", "n_obs"] +
                          [f"{c}_{k}" for k in range(16) for c in ("cx", "cy", "r")])

@@ -27,11 +27,26 @@ class VecEnvBase:
     ENV_ID: int = -1
     VARIANT: int = 0
     STATE_FIELDS: tuple = ()  # names of the SoA state fields, in storage order
+    # True where get_state() is a pure function of the persistent state, so that the pre-step `current_state` of step
+    # t+1 is bit-identical to the policy-facing observation written by step t (s' or the reset observation).  Such envs
+    # do not recompute it: the two buffers swap roles and the kernel is launched with io.obs = NULL (for the fake laser
+    # of UGVForwardObstacleAvoidance this removes one of the two 37-ray scans per step).  Not true for the
+    # UAV envs (the reset observation is taken against the stale reference) nor the two-link arm (pre-wrap error).
+    OBS_IS_PURE: bool = False
 
     def __init__(self, n_envs: int = 1, device="cuda", dtype=torch.float64, seed: int = 0,
-                 env_index_offset: int = 0, auto_reset: bool = False, host_only: bool = False):
+                 env_index_offset: int = 0, auto_reset: bool = False, host_only: bool = False, io_dtype=None,
+                 reuse_obs: Optional[bool] = None):
+        """``dtype``: type of the persistent state and of all arithmetic.  ``io_dtype``: type of the RL-facing buffers
+        (action, dis, current/next/policy state, reward); default = ``dtype``.  ``dtype=float64, io_dtype=float32`` keeps
+        the reference's fp64 trajectories while exchanging float32 with the (float32) policy and rollout buffer, as the
+        reference does at ``RolloutBuffer.to_tensor`` (utils/classes.py:292-301)."""
         if dtype not in (torch.float64, torch.float32):
             raise ValueError("dtype must be torch.float64 or torch.float32")
+        io_dtype = dtype if io_dtype is None else io_dtype
+        if io_dtype not in (dtype, torch.float32):
+            raise ValueError("io_dtype must equal dtype or be torch.float32")
+        self.io_dtype = io_dtype
         self._params = self.make_params()
         self.host_only = bool(host_only)
         if host_only:  # parameter/attribute mirror only (CPU tests, oracle drivers): no buffers, no launches
@@ -47,13 +62,15 @@ class VecEnvBase:
         self.seed = int(seed)
         self.env_index_offset = int(env_index_offset)
         self.auto_reset = bool(auto_reset)
+        self.reuse_obs = self.OBS_IS_PURE if reuse_obs is None else (bool(reuse_obs) and self.OBS_IS_PURE)
+        self._policy_obs_valid = False  # _reset_obs holds get_state() of the current persistent state for every lane
 
         sf, od, ad, dd = _lib.dims(self.ENV_ID, self.VARIANT)
         assert sf == len(self.STATE_FIELDS), (sf, self.STATE_FIELDS)
         self._sf, self._od, self._ad, self._dd = sf, od, ad, dd
         N, dev = self.n_envs, self.device
-        z = lambda *shape, dt=dtype: torch.zeros(*shape, dtype=dt, device=dev)
-        self._state = z(sf, N)
+        z = lambda *shape, dt=io_dtype: torch.zeros(*shape, dtype=dt, device=dev)
+        self._state = z(sf, N, dt=dtype)
         self._time = z(N, dt=torch.float64)
         self._episode = z(N, dt=torch.int32)  # bit pattern of the u32 episode counter
         self._obs = z(od, N)
@@ -99,13 +116,14 @@ class VecEnvBase:
         io.done = self._done.data_ptr()
         io.flag = self._flag.data_ptr()
         io.reset_obs = self._reset_obs.data_ptr() if reset_obs else None
+        io.io_dtype = _lib.F32 if (self.io_dtype == torch.float32 and self.dtype == torch.float64) else _lib.F64
         return io
 
     def _as_soa(self, x, rows: int) -> torch.Tensor:
         """Accept [N, rows] (reference orientation, preferred when ambiguous) or [rows, N] (engine SoA)."""
         if not torch.is_tensor(x):
-            x = torch.as_tensor(np.asarray(x), dtype=self.dtype)
-        x = x.to(device=self.device, dtype=self.dtype)
+            x = torch.as_tensor(np.asarray(x), dtype=self.io_dtype)
+        x = x.to(device=self.device, dtype=self.io_dtype)
         if x.dim() == 1:
             x = x.view(1, -1) if rows == 1 and x.numel() == self.n_envs else x.view(-1, 1).expand(rows, self.n_envs)
         if x.shape == (self.n_envs, rows):  # reference orientation wins when n_envs == rows
@@ -150,6 +168,8 @@ class VecEnvBase:
         self._reward[sel] = 0
         self._done[sel] = 0
         self._flag[sel] = 0
+        if mask is None:
+            self._policy_obs_valid = True
 
     def _reset_default(self, mask) -> None:
         raise NotImplementedError
@@ -175,9 +195,15 @@ class VecEnvBase:
         self.step_soa(a, d)
 
     def step_soa(self, action_soa: torch.Tensor, dis_soa: Optional[torch.Tensor] = None) -> None:
-        """Hot call: ``action_soa`` is ``[action_dim, N]`` contiguous in the env dtype (no copies made)."""
+        """Hot call: ``action_soa`` is ``[action_dim, N]`` contiguous in ``io_dtype`` (no copies made)."""
+        if action_soa.dtype != self.io_dtype or (dis_soa is not None and dis_soa.dtype != self.io_dtype):
+            raise _lib.B200EnvError(f"step_soa: action/dis must be {self.io_dtype}")
         with torch.cuda.device(self.device):
-            io = self._io(action_soa, dis_soa)
+            reuse = self.reuse_obs and self._policy_obs_valid
+            if reuse:  # current_state(t+1) == policy_state(t): swap the buffers instead of recomputing get_state()
+                self._obs, self._reset_obs = self._reset_obs, self._obs
+            io = self._io(action_soa, dis_soa, obs=not reuse)
+            self._policy_obs_valid = True
             flags = _lib.AUTO_RESET if self.auto_reset else 0
             _lib.check(self._lib.b200env_step(self.ENV_ID, self._dt_code, self.n_envs, C.byref(self._params),
                                               C.sizeof(self._params), C.byref(io), flags, self.seed,
@@ -195,6 +221,7 @@ class VecEnvBase:
 
     def set_state_buffers(self, state=None, time=None, episode=None) -> None:
         """Inject SoA state ([fields, N]), time ([N]) -- parity re-sync and checkpoint restore."""
+        self._policy_obs_valid = False  # the next step recomputes current_state in-kernel
         if state is not None:
             self._state.copy_(torch.as_tensor(state).to(self.device, self.dtype))
         if time is not None:

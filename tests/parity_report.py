@@ -11,15 +11,21 @@ from helpers import ENGINE_TOL, EngineBackend, OracleBackend, load_golden, repla
 
 
 def main():
-    backend = sys.argv[1] if len(sys.argv) > 1 else "engine"
+    backend = sys.argv[1] if len(sys.argv) > 1 else "engine"  # engine | engine_f32 | oracle
     names = sys.argv[2:] or sorted(ENGINE_TOL)
+    f32 = backend == "engine_f32"
+    if f32:
+        import torch
     rows = {}
     for name in names:
         g = load_golden(name)
         L = g["reward"].shape[1]
         for mode in ("resync", "free"):
-            b = EngineBackend(name, L) if backend == "engine" else OracleBackend(name, L)
-            r = replay(g, b, resync=(mode == "resync"), name=name)
+            b = (EngineBackend(name, L, dtype=torch.float32) if f32 else EngineBackend(name, L)) \
+                if backend.startswith("engine") else OracleBackend(name, L)
+            # fp32: short horizon (100 steps), compared without the chaos cut-off so the raw drift is visible
+            r = replay(g, b, resync=(mode == "resync"), name=name, steps=100 if f32 else None,
+                       chaos_cut=1e300 if f32 else 1e-11)
             rows[f"{name}:{mode}"] = r
             w = r["worst"]
             print(f"{name:26s} {mode:6s} obs {w['obs']:.1e} next {w['next_obs']:.1e} rew {w['reward']:.1e} "

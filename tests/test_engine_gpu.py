@@ -63,3 +63,16 @@ def test_engine_vs_oracle_sharded_offset(name, oracle_lib):
     res = engine_vs_oracle(name, n=1000, steps=40, seed=11, offset=(1 << 33) + 12345)
     assert res["flag_mismatch"] == 0, res
     assert res["worst"] <= res["tol"], res
+
+
+@pytest.mark.parametrize("name", ["cartpole", "soi", "fas_ppo2", "ugv_forward", "ugvo_dppo2", "uav_att_rand", "uav_pos",
+                                  "uavr_hover", "twolink", "ballbalancer"])
+def test_engine_f32_io_keeps_fp64_trajectory(name, oracle_lib):
+    """b200env_io.io_dtype = F32 with dtype = F64: float32 actions in, float32 obs/reward out, state and arithmetic in
+    fp64.  The state must meet the same fp64 tolerance as the all-fp64 engine; the float32 outputs are the oracle's fp64
+    values rounded once (2^-24 relative + the fp64 tolerance)."""
+    import torch
+    res = engine_vs_oracle(name, n=4096, steps=40, seed=5, io_dtype=torch.float32)
+    assert res["flag_mismatch"] == 0, res
+    assert res["worst"] <= res["tol"], res
+    assert 0.0 < res["worst_io"] <= 2.0 ** -24 + res["tol"], res
