@@ -59,6 +59,7 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
     static __device__ __forceinline__ double min(double a, double b) { return ::fmin(a, b); }
     static __device__ __forceinline__ double max(double a, double b) { return ::fmax(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
 };
 
 template <> struct Mth<float> {
@@ -85,6 +86,7 @@ template <> struct Mth<float> {
     static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
     static __device__ __forceinline__ float min(float a, float b) { return ::fminf(a, b); }
     static __device__ __forceinline__ float max(float a, float b) { return ::fmaxf(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return ::fmaf(a, b, c); }
 };
 
 // x^a for x >= 0 given L = log(x): exp(a * L), with pow()'s conventions x^0 = 1 and 0^a = 0 (a > 0), inf (a < 0).

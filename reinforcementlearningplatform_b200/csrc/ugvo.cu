@@ -5,13 +5,14 @@
 // generation), plus the PPO2/DPPO2 demo copies (variant 1).  97 % of the reference's step time is the ray cast, run
 // twice per step (before and after the RK4 update).
 //
-// ONE WARP = ONE INSTANCE.  The unicycle RK4 is computed redundantly by all lanes (it is tiny and independent of the
-// laser), so both poses are known up front and the 2 x 37 rays of the two scans are cast together in 3 passes of 32
-// lanes (74/96 lanes busy instead of 74/128 with a pass pair per scan).  Per pose the obstacles are ranked by centre
-// distance with a lane-parallel counting sort (lane k = obstacle k, 16 shuffles) and written in rank order to shared
-// memory; every ray lane then walks that list and stops at the FIRST obstacle it accepts -- the reference's
-// selection rule (note N8: first accepted obstacle in centre-distance order, not the nearest crossing).  Warp votes
-// (__any_sync / __all_sync / __ballot_sync) implement the collision test, the early exit and, at reset, the
+// Step kernel: block-cooperative, 64 instances per 128-thread block.  The scalar part of the step (unicycle RK4,
+// collision test, centre-distance ordering of the obstacles, terminal flag, reward) runs one THREAD per instance; the
+// rays of all instances of the block are then dealt to all threads, so every lane casts a ray (the first version ran
+// one warp per instance: 37 of 64 lanes busy in the scan and all scalar work repeated by 32 lanes -- 3400 warp
+// instructions per step, ncu profiles/r1/ugvo_kernel_ncu_v1_keys.txt).  Per pose only the obstacles within laser
+// range are kept, in np.argsort(centre distance) order; a ray walks that list and stops at the FIRST obstacle it
+// accepts -- the reference's selection rule (note N8: first accepted obstacle in centre-distance order, not the
+// nearest crossing).  Reset / observe and the in-step auto-reset run one warp per instance: warp votes implement the
 // lane-parallel rejection sampling of the obstacle map (32 candidates per round, lowest legal index wins, so the
 // result is identical to trying the candidates one by one).
 #include "common.cuh"
@@ -60,44 +61,44 @@ struct Pose {
     bool collided;        // collision_check() :261-272 -> every ray returns laserBlind
 };
 
-// sorted obstacle list of one pose in shared memory
+// In-range obstacle list of one pose.  `dis > laserDis + r0` (:349-351) is the same for every ray of a pose, so it is
+// evaluated once per obstacle and the rays walk the compacted list (typically 3-5 of the 15 circles), kept in
+// centre-distance order (np.argsort :301; ties: lower index first).  Element j lives at ptr[j * stride]: stride 1 for
+// the warp-cooperative path (reset / observe), stride G for the block-cooperative step kernel ([slot][instance]).
 template <typename T>
-struct SortedObs {
-    T x0[MAXO], y0[MAXO], r0[MAXO], d[MAXO];
+struct ObsList {
+    const T *x0, *y0, *r0, *d;
+    int stride, count;
 };
 
-// Prepares one pose: collision flag, corner bearings, obstacles ranked by centre distance into `so`.
-// lane k < nobs owns obstacle k (cx, cy, r).
+// a / d with d fixed per ray: one IEEE reciprocal, then per quotient a product and one FMA-corrected Newton step
+// (Markstein: with r = RN(1/d) and q within 1 ulp, q + (a - q d) r rounds to the IEEE quotient) -- 3 instructions instead
+// of the ~25 of a fp64 division, same result as the reference's `/`.  NaN numerators stay NaN.
 template <typename T>
-__device__ __forceinline__ void prepare_pose(const P &p, Pose<T> &q, int lane, int nobs, T cx, T cy, T r, SortedObs<T> &so) {
-    const bool mine = lane < nobs;
-    const T d = mine ? norm2(q.x - cx, q.y - cy) : (T)1e300;
-    q.collided = __any_sync(FULL, mine && d <= r + (T)p.r_vehicle);
-    // rank = number of obstacles strictly closer (ties: lower index first) -- np.argsort order
-    int rank = 0;
-#pragma unroll
-    for (int j = 0; j < MAXO; ++j) {
-        const T dj = shfl<T>(d, j);
-        rank += (j < nobs) && (dj < d || (dj == d && j < lane));
+struct Divisor {
+    T d, r;
+    __device__ __forceinline__ explicit Divisor(T d_) : d(d_), r((T)1 / d_) {}
+    __device__ __forceinline__ T div(T a) const {
+        const T q = a * r;
+        return Mth<T>::fma(Mth<T>::fma(-q, d, a), r, q);
     }
-    if (mine) { so.x0[rank] = cx; so.y0[rank] = cy; so.r0[rank] = r; so.d[rank] = d; }
-    // corner bearings: lanes 0..3 evaluate one acos each
-    const T xm = (T)p.map_x, ym = (T)p.map_y;
-    const T vx = (lane == 0 || lane == 3) ? xm - q.x : (T)0 - q.x;
-    const T vy = (lane == 0 || lane == 1) ? ym - q.y : (T)0 - q.y;
-    T th = (T)0;
-    if (lane < 4) th = vector_rad<T>((T)1, (T)0, vx, vy);
-    q.th1 = shfl<T>(th, 0);
-    q.th2 = shfl<T>(th, 1);
-    q.th3 = -shfl<T>(th, 2);
-    q.th4 = -shfl<T>(th, 3);
-    __syncwarp();
+};
+
+// bearings of the four map corners seen from (x, y), :304-309
+template <typename T>
+__device__ __forceinline__ T corner_bearing(const P &p, T x, T y, int k) {
+    const T vx = (k == 0 || k == 3) ? (T)p.map_x - x : (T)0 - x;
+    const T vy = (k == 0 || k == 1) ? (T)p.map_y - y : (T)0 - y;
+    const T th = vector_rad<T>((T)1, (T)0, vx, vy);
+    return k < 2 ? th : -th;
 }
 
-// One ray of get_fake_laser (:302-395) for pose q; ray index in [0, n_rays).
+// One ray of get_fake_laser (:302-395) for pose q; ray index in [0, n_rays).  No warp-level operations: lanes of one
+// warp may belong to different instances.
 template <typename T>
-__device__ __forceinline__ T cast_ray(const P &p, const Pose<T> &q, int ray, int nobs, const SortedObs<T> &so, bool active) {
+__device__ __forceinline__ T cast_ray(const P &p, const Pose<T> &q, int ray, const ObsList<T> &so) {
     const T LD = (T)p.laser_dis, LB = (T)p.laser_blind;
+    if (q.collided) return LB; // collision_check() :261-272 -> every ray returns laserBlind
     const T x = q.x, y = q.y, xm = (T)p.map_x, ym = (T)p.map_y;
     // np.linspace(phi - R, phi + R, n): arange * step + start, last element = stop
     const T a0 = q.phi - (T)p.laser_range, a1 = q.phi + (T)p.laser_range;
@@ -105,68 +106,93 @@ __device__ __forceinline__ T cast_ray(const P &p, const Pose<T> &q, int ray, int
     T phi = (ray == p.n_rays - 1) ? a1 : (T)ray * step + a0;
     if (phi > (T)M_PI) phi -= (T)(2 * M_PI);
     if (phi < (T)-M_PI) phi += (T)(2 * M_PI);
-    const T m = Mth<T>::tan(phi);
+    T sphi, cphi;
+    Mth<T>::sincos(phi, &sphi, &cphi);
+    const T m = sphi / cphi; // np.tan(phi) :311 (constant-bank sincos + one IEEE division, <= 2.5 ulp)
     const T b = y - m * x;
     const T m2p1 = m * m + (T)1;
     const T sq = Mth<T>::sqrt(m2p1);
-    const T cosT = Mth<T>::abs(m) / sq, sinT = (T)1 / sq;
-    T tx, ty;
+    const Divisor<T> dsq(sq), dm2(m2p1);
+    const T am = Mth<T>::abs(m);
+    const T cosT = dsq.div(am), sinT = dsq.r; // |m| / sqrt(m^2 + 1), 1 / sqrt(m^2 + 1)
+    const T ld_sq = dsq.div(LD);               // laserDis / sqrt(m^2 + 1)
+    const bool mpos = m >= (T)0;
+    T tx, ty; // end point of the ray on the map border or at laserDis (:313-343)
     if (q.th4 < phi && phi <= q.th1) { // right wall
         tx = xm; ty = m * xm + b;
-        const T t = x + LD / sq;
-        if (t < xm) { tx = t; ty = (m >= (T)0) ? y + cosT * LD : y - cosT * LD; }
+        const T t = x + ld_sq;
+        if (t < xm) { tx = t; ty = mpos ? y + cosT * LD : y - cosT * LD; }
     } else if (q.th1 < phi && phi <= q.th2) { // top wall
-        if (Mth<T>::abs(m) < (T)1e8) { tx = (ym - b) / m; ty = ym; } else { tx = x; ty = ym; }
-        const T t = y + Mth<T>::abs(m) * LD / sq;
-        if (t < ym) { ty = t; tx = (m >= (T)0) ? x + LD * sinT : x - LD * sinT; }
+        if (am < (T)1e8) { tx = (ym - b) / m; ty = ym; } else { tx = x; ty = ym; }
+        const T t = y + dsq.div(am * LD);
+        if (t < ym) { ty = t; tx = mpos ? x + LD * sinT : x - LD * sinT; }
     } else if (q.th3 < phi && phi <= q.th4) { // bottom wall
-        if (Mth<T>::abs(m) < (T)1e8) { tx = -b / m; ty = (T)0; } else { tx = x; ty = (T)0; }
-        const T t = y - Mth<T>::abs(m) * LD / sq;
-        if (t > (T)0) { ty = t; tx = (m >= (T)0) ? x - LD * sinT : x + LD * sinT; }
+        if (am < (T)1e8) { tx = -b / m; ty = (T)0; } else { tx = x; ty = (T)0; }
+        const T t = y - dsq.div(am * LD);
+        if (t > (T)0) { ty = t; tx = mpos ? x - LD * sinT : x + LD * sinT; }
     } else { // left wall
         tx = (T)0; ty = b;
-        const T t = x - LD / sq;
-        if (t > (T)0) { tx = t; ty = (m >= (T)0) ? y - cosT * LD : y + cosT * LD; }
+        const T t = x - ld_sq;
+        if (t > (T)0) { tx = t; ty = mpos ? y - cosT * LD : y + cosT * LD; }
     }
-    const T dxs = tx - x;
-    const T sg = dxs > (T)0 ? (T)1 : (dxs < (T)0 ? (T)-1 : (T)0);
-    const T lo = Mth<T>::min(x, tx), hi = Mth<T>::max(x, tx);
     const T rdx = tx - x, rdy = ty - y;
-    const bool ray_ok = !(norm2(rdx, rdy) < (T)1e-4); // cal_vector_rad returns 0 for a degenerate ray (never > pi/2)
-    bool found = !active;
-    T out = (T)0;
-    for (int j = 0; j < nobs; ++j) { // obstacles in centre-distance order, first accepted wins (N8)
-        if (__all_sync(FULL, found)) break;
-        if (!found) {
-            const T x0 = so.x0[j], y0 = so.y0[j], r0 = so.r0[j];
-            const T dj = so.d[j]; // = |centre - start|, the second norm of cal_vector_rad
-            bool rej = dj > LD + r0;                                         // out of range
-            rej = rej || (Mth<T>::abs(m * x0 - y0 + b) / sq > r0);           // the line misses the circle
-            // cal_vector_rad(ray, centre - start) > pi / 2  <=>  both vectors non-degenerate and their dot product < 0
-            // (dividing by the positive norms and taking acos cannot change the sign; see vector_rad_obtuse)
-            rej = rej || (ray_ok && !(dj < (T)1e-4) && (rdx * (x0 - x) + rdy * (y0 - y) < (T)0)); // behind the ray
-            if (!rej) {
-                const T fx = (x0 + m * y0 - m * b) / m2p1;
-                const T fy = (m * x0 + m * m * y0 + b) / m2p1;
-                const T rd = norm2(fx - x0, fy - y0);
-                const T cross = fx - sg * Mth<T>::sqrt(r0 * r0 - rd * rd) / sq; // NaN (no crossing) fails the test below
-                if (lo <= cross && cross <= hi) {
-                    found = true;
-                    const T dis = Mth<T>::abs(cross - x) * sq;
-                    out = dis < LB ? LB : dis;
-                }
+    const T sg = rdx > (T)0 ? (T)1 : (rdx < (T)0 ? (T)-1 : (T)0);
+    const T lo = Mth<T>::min(x, tx), hi = Mth<T>::max(x, tx);
+    const T ray_len = norm2(rdx, rdy);
+    const bool ray_ok = !(ray_len < (T)1e-4); // cal_vector_rad returns 0 for a degenerate ray (never > pi/2)
+    for (int j = 0; j < so.count; ++j) { // in-range obstacles in centre-distance order, first accepted wins (N8)
+        const int o = j * so.stride;
+        const T x0 = so.x0[o], y0 = so.y0[o], r0 = so.r0[o];
+        const T dj = so.d[o]; // = |centre - start|, the second norm of cal_vector_rad
+        // `abs(m x0 - y0 + b) / sqrt(m^2 + 1) > r0` (:353): decided on the product form; the exact quotient is only
+        // evaluated when the two sides are within a few ulp of each other (same decision as the reference, no division)
+        const T num = Mth<T>::abs(m * x0 - y0 + b), rhs = r0 * sq;
+        bool miss = num > rhs;
+        if (Mth<T>::abs(num - rhs) <= (T)(sizeof(T) == 8 ? 1e-15 : 1e-6) * rhs) miss = num / sq > r0;
+        // cal_vector_rad(ray, centre - start) > pi / 2  <=>  both vectors non-degenerate and their dot product < 0
+        // (dividing by the positive norms and taking acos cannot change the sign; see vector_rad_obtuse)
+        const bool behind = ray_ok && !(dj < (T)1e-4) && (rdx * (x0 - x) + rdy * (y0 - y) < (T)0);
+        if (!miss && !behind) {
+            const T fx = dm2.div(x0 + m * y0 - m * b);
+            const T fy = dm2.div(m * x0 + m * m * y0 + b);
+            const T rd = norm2(fx - x0, fy - y0);
+            const T cross = fx - dsq.div(sg * Mth<T>::sqrt(r0 * r0 - rd * rd)); // NaN (no crossing) fails the test below
+            if (lo <= cross && cross <= hi) {
+                const T dis = Mth<T>::abs(cross - x) * sq;
+                return dis < LB ? LB : dis;
             }
         }
     }
-    if (active && !found) { // :382-395
-        const T dis = norm2(x - tx, y - ty);
-        if (dis > LD) out = LD;
-        else if (LB < dis && dis <= LD) out = dis;
-        else out = LB;
-    } else if (!active) {
-        out = (T)0;
+    // no obstacle hit (:382-395): ray_len = norm2(x - tx, y - ty) (the squares are sign-symmetric)
+    if (ray_len > LD) return LD;
+    if (LB < ray_len && ray_len <= LD) return ray_len;
+    return LB;
+}
+
+// ---- warp-cooperative pose preparation (reset / observe path): lane k < nobs owns obstacle k (cx, cy, r)
+// (sx0, sy0, sr0, sd: MAXO elements each in shared memory, owned by this warp)
+template <typename T>
+__device__ __forceinline__ ObsList<T> prepare_pose_warp(const P &p, Pose<T> &q, int lane, int nobs, T cx, T cy, T r,
+                                                        T *sx0, T *sy0, T *sr0, T *sd) {
+    const bool mine = lane < nobs;
+    const T d = mine ? norm2(q.x - cx, q.y - cy) : (T)1e300;
+    q.collided = __any_sync(FULL, mine && d <= r + (T)p.r_vehicle);
+    const bool inr = mine && !(d > (T)p.laser_dis + r); // :349 `if dis > self.laserDis + _r: continue`
+    const unsigned in_mask = __ballot_sync(FULL, inr);
+    int rank = 0; // number of in-range obstacles strictly closer (ties: lower index first) -- np.argsort order
+    for (unsigned mm = in_mask; mm; mm &= mm - 1) {
+        const int j = __ffs(mm) - 1;
+        const T dj = shfl<T>(d, j);
+        rank += (dj < d || (dj == d && j < lane));
     }
-    return q.collided ? LB : out;
+    if (inr) { sx0[rank] = cx; sy0[rank] = cy; sr0[rank] = r; sd[rank] = d; }
+    T th = (T)0;
+    if (lane < 4) th = corner_bearing<T>(p, q.x, q.y, lane);
+    q.th1 = shfl<T>(th, 0); q.th2 = shfl<T>(th, 1); q.th3 = shfl<T>(th, 2); q.th4 = shfl<T>(th, 3);
+    __syncwarp();
+    ObsList<T> l;
+    l.x0 = sx0; l.y0 = sy0; l.r0 = sr0; l.d = sd; l.stride = 1; l.count = __popc(in_mask);
+    return l;
 }
 
 struct Draw2 { double u0, u1; };
@@ -243,111 +269,163 @@ __device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gi
 
 enum { F_X = 0, F_Y, F_VEL, F_PHI, F_OMEGA, F_TX, F_TY, F_NOBS, F_OBS };
 
-// shared body of step / reset / observe.  mode 0 = step, 1 = reset (masked), 2 = observe only
+// get_state :399-411, kinematic part (4 terms) of pose (x, y, phi) with velocity / rate (vel, omega)
+template <typename T>
+__device__ __forceinline__ void kin_obs(const P &p, T x, T y, T vel, T phi, T omega, T tgx, T tgy, T *o, T *err_out,
+                                        T *ephi_out) {
+    T s, c;
+    Mth<T>::sincos(phi, &s, &c);
+    const T g = (T)p.static_gain;
+    const T e = norm2(tgx - x, tgy - y), ephi = vector_rad_oriented<T>(c, s, tgx - x, tgy - y);
+    o[0] = ((T)(2 / p.e_max) * e - (T)1) * g;
+    o[1] = ((T)(2 / p.v_max) * vel - (T)1) * g;
+    o[2] = ephi / (T)p.e_phi_max * g;
+    o[3] = omega / (T)p.omega_max * g;
+    if (err_out) *err_out = e;
+    if (ephi_out) *ephi_out = ephi;
+}
+
+// ---- warp view of one instance (reset / observe path): scalars are warp-uniform, lane k holds obstacle k
+template <typename T>
+struct WarpInst {
+    T x, y, vel, phi, omega, tgx, tgy, ocx, ocy, orr;
+    int nobs;
+    double time;
+};
+
+template <typename T>
+__device__ __forceinline__ void warp_load(const b200env_io &io, int64_t n, int64_t i, int lane, WarpInst<T> &e) {
+    T sc = (T)0; // lanes 0..7 fetch the scalar fields, lane k the k-th obstacle; scalars are broadcast
+    if (lane < F_OBS) sc = ld<T>(io.state, n, lane, i);
+    e.x = shfl<T>(sc, F_X); e.y = shfl<T>(sc, F_Y); e.vel = shfl<T>(sc, F_VEL); e.phi = shfl<T>(sc, F_PHI);
+    e.omega = shfl<T>(sc, F_OMEGA); e.tgx = shfl<T>(sc, F_TX); e.tgy = shfl<T>(sc, F_TY);
+    e.nobs = (int)shfl<T>(sc, F_NOBS);
+    e.ocx = e.ocy = e.orr = (T)0;
+    if (lane < MAXO) {
+        e.ocx = ld<T>(io.state, n, F_OBS + 3 * lane + 0, i);
+        e.ocy = ld<T>(io.state, n, F_OBS + 3 * lane + 1, i);
+        e.orr = ld<T>(io.state, n, F_OBS + 3 * lane + 2, i);
+    }
+    e.time = io.time[i];
+}
+
+// reset(random=True) :527-557 of instance i by one warp; writes the whole persistent state
+template <typename T>
+__device__ __forceinline__ void warp_reset(const P &p, const b200env_io &io, int64_t n, int64_t i, uint64_t seed,
+                                           int64_t off, int lane, WarpInst<T> &e) {
+    const uint32_t ep = io.episode[i];
+    double sx, sy, ttx, tty, phi0, cx, cy, rr;
+    int no;
+    reset_map(p, seed, (uint64_t)(off + i), ep, lane, sx, sy, ttx, tty, phi0, cx, cy, rr, no);
+    e.x = (T)sx; e.y = (T)sy; e.tgx = (T)ttx; e.tgy = (T)tty; e.phi = (T)phi0; e.vel = (T)0; e.omega = (T)0;
+    e.ocx = (T)cx; e.ocy = (T)cy; e.orr = (T)rr; e.nobs = no;
+    e.time = 0.0;
+    __syncwarp();
+    if (lane == 0) {
+        io.episode[i] = ep + 1u;
+        st<T>(io.state, n, F_X, i, e.x); st<T>(io.state, n, F_Y, i, e.y); st<T>(io.state, n, F_VEL, i, e.vel);
+        st<T>(io.state, n, F_PHI, i, e.phi); st<T>(io.state, n, F_OMEGA, i, e.omega);
+        st<T>(io.state, n, F_TX, i, e.tgx); st<T>(io.state, n, F_TY, i, e.tgy); st<T>(io.state, n, F_NOBS, i, (T)e.nobs);
+        io.time[i] = 0.0;
+    }
+    if (lane < MAXO) {
+        st<T>(io.state, n, F_OBS + 3 * lane + 0, i, e.ocx);
+        st<T>(io.state, n, F_OBS + 3 * lane + 1, i, e.ocy);
+        st<T>(io.state, n, F_OBS + 3 * lane + 2, i, e.orr);
+    }
+}
+
+// get_state :399-411 of instance i by one warp (lanes = rays) into dst[41][n]
+template <typename T, bool IO32>
+__device__ __forceinline__ void warp_observe(const P &p, int64_t n, int64_t i, int lane, const WarpInst<T> &e, void *dst,
+                                             T *sx0, T *sy0, T *sr0, T *sd) {
+    Pose<T> q;
+    q.x = e.x; q.y = e.y; q.phi = e.phi;
+    __syncwarp();
+    const ObsList<T> l = prepare_pose_warp<T>(p, q, lane, e.nobs, e.ocx, e.ocy, e.orr, sx0, sy0, sr0, sd);
+    const T g = (T)p.static_gain;
+    for (int ray = lane; ray < p.n_rays; ray += 32)
+        stio<T, IO32>(dst, n, 4 + ray, i, ((T)2 * cast_ray<T>(p, q, ray, l) / (T)p.laser_dis - (T)1) * g);
+    if (lane == 0) {
+        T o[4];
+        kin_obs<T>(p, e.x, e.y, e.vel, e.phi, e.omega, e.tgx, e.tgy, o, nullptr, nullptr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) stio<T, IO32>(dst, n, k, i, o[k]);
+    }
+    __syncwarp();
+}
+
+// reset (mode 1, masked) / observe (mode 2): one warp per instance
 template <typename T, bool IO32>
 __global__ void __launch_bounds__(WARPS * 32)
-ugvo_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
-            uint64_t seed, int64_t off, const uint8_t *mask, int mode) {
-    __shared__ SortedObs<T> s_obs[WARPS][2];
+ugvo_aux_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint64_t seed,
+                int64_t off, const uint8_t *mask, int mode) {
+    __shared__ T s_o[WARPS][4][MAXO];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * WARPS + w;
     if (i >= n) return; // whole warp exits together
     if (mode == 1 && mask && !mask[i]) return;
+    WarpInst<T> e;
+    warp_load<T>(io, n, i, lane, e);
+    if (mode == 1) warp_reset<T>(p, io, n, i, seed, off, lane, e);
+    if (io.next_obs) warp_observe<T, IO32>(p, n, i, lane, e, io.next_obs, s_o[w][0], s_o[w][1], s_o[w][2], s_o[w][3]);
+}
+
+// ---- step: block-cooperative.  G instances per block.
+//   phase 1  thread t = instance t: unicycle RK4 (rk44 :482-501), collision test, in-range obstacle list of the pose
+//            (insertion sort by centre distance into shared memory, [slot][instance] so thread t stays in bank t),
+//            corner bearings, terminal flag, reward, kinematic observation terms -- all scalar work of the step is done
+//            once per instance with every lane busy, and its loads / stores are coalesced over instances;
+//   phase 2  the G x n_rays rays are dealt round-robin to all threads of the block (a warp covers at most two
+//            instances, so the obstacle lists are shared-memory broadcasts) -- every lane casts a ray;
+//   phase 3  instances that terminated with auto-reset on: one warp each draws the new map (rejection sampling by
+//            ballot) and casts the reset observation.
+// With io.obs == NULL (observation reuse, vec_env.py) only the post-update scan is cast (one scan per step).
+constexpr int G = 64;
+constexpr int TPB = 128;
+
+template <typename T, bool IO32>
+__global__ void __launch_bounds__(TPB)
+ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
+                 uint64_t seed, int64_t off) {
+    __shared__ T s_o[4][MAXO][G];                 // x0, y0, r0, d of the in-range obstacles, [slot][instance]
+    __shared__ T s_pose[7][G];                    // x, y, phi, th1..th4
+    __shared__ int s_cnt[G], s_reset[G], s_nreset;
+    __shared__ unsigned char s_col[G], s_mirror[G];
+    const int t = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * G;
+    const int gv = (int)((n - base) < (int64_t)G ? (n - base) : (int64_t)G);
     const int NR = p.n_rays;
+    const bool own = t < gv;
+    const int64_t i = base + t;
+    const bool scan_a = io.obs != nullptr;
+    const T g = (T)p.static_gain;
+    if (t == 0) s_nreset = 0;
+    __syncthreads();
 
-    // ---- load: lanes 0..7 fetch the scalar fields, lane k the k-th obstacle; scalars are broadcast
-    T sc = (T)0;
-    if (lane < F_OBS) sc = ld<T>(io.state, n, lane, i);
-    T x = shfl<T>(sc, F_X), y = shfl<T>(sc, F_Y), vel = shfl<T>(sc, F_VEL), phi = shfl<T>(sc, F_PHI);
-    T omega = shfl<T>(sc, F_OMEGA), tgx = shfl<T>(sc, F_TX), tgy = shfl<T>(sc, F_TY);
-    int nobs = (int)shfl<T>(sc, F_NOBS);
-    T ocx = (T)0, ocy = (T)0, orr = (T)0;
-    if (lane < MAXO) {
-        ocx = ld<T>(io.state, n, F_OBS + 3 * lane + 0, i);
-        ocy = ld<T>(io.state, n, F_OBS + 3 * lane + 1, i);
-        orr = ld<T>(io.state, n, F_OBS + 3 * lane + 2, i);
-    }
-    double time = io.time[i];
-    bool store_map = false;
-
-    auto do_reset = [&]() {
-        const uint32_t ep = io.episode[i];
-        double sx, sy, ttx, tty, phi0, cx, cy, rr;
-        int no;
-        reset_map(p, seed, (uint64_t)(off + i), ep, lane, sx, sy, ttx, tty, phi0, cx, cy, rr, no);
-        x = (T)sx; y = (T)sy; tgx = (T)ttx; tgy = (T)tty; phi = (T)phi0; vel = (T)0; omega = (T)0;
-        ocx = (T)cx; ocy = (T)cy; orr = (T)rr; nobs = no;
-        time = 0.0;
-        if (lane == 0) io.episode[i] = ep + 1u;
-        store_map = true;
-    };
-    // observation of the current (x, y, vel, phi, omega): get_state :399-411; uses pose slot `slot`
-    auto observe_into = [&](void *dst, int slot) {
-        Pose<T> q;
-        q.x = x; q.y = y; q.phi = phi;
-        prepare_pose<T>(p, q, lane, nobs, ocx, ocy, orr, s_obs[w][slot]);
-        const T g = (T)p.static_gain;
-        for (int pass = 0; pass * 32 < NR; ++pass) {
-            const int ray = pass * 32 + lane;
-            const T l = cast_ray<T>(p, q, ray < NR ? ray : 0, nobs, s_obs[w][slot], ray < NR);
-            if (ray < NR && dst) stio<T, IO32>(dst, n, 4 + ray, i, ((T)2 * l / (T)p.laser_dis - (T)1) * g);
+    T x = (T)0, y = (T)0, vel = (T)0, phi = (T)0, omega = (T)0, tgx = (T)0, tgy = (T)0;
+    T xa = (T)0, ya = (T)0, phia = (T)0, cur_e = (T)0, cur_vel = (T)0;
+    int nobs = 0;
+    double time = 0.0;
+    if (own) {
+        x = ld<T>(io.state, n, F_X, i); y = ld<T>(io.state, n, F_Y, i); vel = ld<T>(io.state, n, F_VEL, i);
+        phi = ld<T>(io.state, n, F_PHI, i); omega = ld<T>(io.state, n, F_OMEGA, i);
+        tgx = ld<T>(io.state, n, F_TX, i); tgy = ld<T>(io.state, n, F_TY, i);
+        nobs = (int)ld<T>(io.state, n, F_NOBS, i);
+        time = io.time[i];
+        const T a_lin = ldio<T, IO32>(io.action, n, 0, i), a_ang = ldio<T, IO32>(io.action, n, 1, i);
+        xa = x; ya = y; phia = phi; cur_vel = vel;
+        // ---- step_update :510-520: current_state = get_state() (kinematic part; the laser part is scan A)
+        if (scan_a) {
+            T o[4];
+            kin_obs<T>(p, x, y, vel, phi, omega, tgx, tgy, o, nullptr, nullptr);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) stio<T, IO32>(io.obs, n, k, i, o[k]);
+            cur_e = o[0];
+        } else {
+            cur_e = ((T)(2 / p.e_max) * norm2(tgx - x, tgy - y) - (T)1) * g; // current_state[0] (demo-copy reward)
         }
-        if (lane == 0 && dst) {
-            T s, c;
-            Mth<T>::sincos(phi, &s, &c);
-            const T e = norm2(tgx - x, tgy - y), ephi = vector_rad_oriented<T>(c, s, tgx - x, tgy - y);
-            stio<T, IO32>(dst, n, 0, i, ((T)(2 / p.e_max) * e - (T)1) * g);
-            stio<T, IO32>(dst, n, 1, i, ((T)(2 / p.v_max) * vel - (T)1) * g);
-            stio<T, IO32>(dst, n, 2, i, ephi / (T)p.e_phi_max * g);
-            stio<T, IO32>(dst, n, 3, i, omega / (T)p.omega_max * g);
-        }
-        __syncwarp();
-    };
-    auto store_state = [&]() {
-        if (lane == 0) {
-            st<T>(io.state, n, F_X, i, x); st<T>(io.state, n, F_Y, i, y); st<T>(io.state, n, F_VEL, i, vel);
-            st<T>(io.state, n, F_PHI, i, phi); st<T>(io.state, n, F_OMEGA, i, omega);
-            io.time[i] = time;
-            if (store_map) {
-                st<T>(io.state, n, F_TX, i, tgx); st<T>(io.state, n, F_TY, i, tgy); st<T>(io.state, n, F_NOBS, i, (T)nobs);
-            }
-        }
-        if (store_map && lane < MAXO) {
-            st<T>(io.state, n, F_OBS + 3 * lane + 0, i, ocx);
-            st<T>(io.state, n, F_OBS + 3 * lane + 1, i, ocy);
-            st<T>(io.state, n, F_OBS + 3 * lane + 2, i, orr);
-        }
-    };
-
-    if (mode != 0) { // reset / observe
-        if (mode == 1) { do_reset(); store_state(); }
-        if (io.next_obs) observe_into(io.next_obs, 0);
-        return;
-    }
-
-    // ---- step_update :510-520
-    T al = (T)0;
-    if (lane < 2) al = ldio<T, IO32>(io.action, n, lane, i);
-    const T a_lin = shfl<T>(al, 0), a_ang = shfl<T>(al, 1);
-    Pose<T> qa, qb;
-    qa.x = x; qa.y = y; qa.phi = phi;
-    const T cur_vel = vel;
-    T cur_e;
-    {
-        const T e0 = norm2(tgx - x, tgy - y);
-        cur_e = ((T)(2 / p.e_max) * e0 - (T)1) * (T)p.static_gain; // current_state[0], used by the demo-copy reward
-    }
-    if (io.obs && lane == 0) { // kinematic part of current_state
-        T s, c;
-        Mth<T>::sincos(phi, &s, &c);
-        const T g = (T)p.static_gain;
-        stio<T, IO32>(io.obs, n, 0, i, cur_e);
-        stio<T, IO32>(io.obs, n, 1, i, ((T)(2 / p.v_max) * vel - (T)1) * g);
-        stio<T, IO32>(io.obs, n, 2, i, vector_rad_oriented<T>(c, s, tgx - x, tgy - y) / (T)p.e_phi_max * g);
-        stio<T, IO32>(io.obs, n, 3, i, omega / (T)p.omega_max * g);
-    }
-    // rk44 :482-501 / demo copy :488-509 (all lanes, redundantly)
-    {
+        // ---- rk44 :482-501 / demo copy :488-509
         const T h = (T)p.dt, half = (T)0.5, kf = (T)p.kf, kt = (T)p.kt;
         T s, c;
         Mth<T>::sincos(phi, &s, &c);
@@ -378,91 +456,126 @@ ugvo_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, 
         if (phi > (T)M_PI) phi -= (T)(2 * M_PI);
         if (phi < (T)-M_PI) phi += (T)(2 * M_PI);
     }
-    qb.x = x; qb.y = y; qb.phi = phi;
-    // ---- is_Terminal :431-449 (uniform over the warp; needs only the new pose and its collision flag)
-    const bool scan_a = io.obs != nullptr;
-    if (scan_a) prepare_pose<T>(p, qa, lane, nobs, ocx, ocy, orr, s_obs[w][0]);
-    prepare_pose<T>(p, qb, lane, nobs, ocx, ocy, orr, s_obs[w][1]);
-    T s, c;
-    Mth<T>::sincos(phi, &s, &c);
-    const T err = norm2(tgx - x, tgy - y), ephi = vector_rad_oriented<T>(c, s, tgx - x, tgy - y);
-    const bool succ = Mth<T>::abs(err) <= (T)0.05 && (p.variant != 0 || Mth<T>::abs(omega) < (T)0.01) &&
-                      Mth<T>::abs(vel) < (T)0.01;
-    int flag = 0;
-    if (x > (T)p.map_x || x < (T)0 || y > (T)p.map_y || y < (T)0) flag = 1;
-    if (time > p.time_max) flag = 2;
-    if (succ) flag = 3;
-    if (qb.collided) flag = 4;
-    const bool done = flag != 0;
-    const bool will_reset = done && (flags & B200ENV_AUTO_RESET);
-    void *mirror = (!will_reset && io.reset_obs) ? io.reset_obs : nullptr; // policy-facing obs = next_obs unless reset
-    const T g = (T)p.static_gain;
-    // ---- both laser scans together: rays 0..NR-1 from pose A (into obs), NR..2NR-1 from pose B (into next_obs)
-    {
-        const int first = scan_a ? 0 : NR, total = 2 * NR;
-        for (int base = first; base < total; base += 32) {
-            const int r = base + lane;
-            const bool active = r < total;
-            const bool is_b = r >= NR;
-            const int ray = active ? (is_b ? r - NR : r) : 0;
-            // the two poses differ per lane: select the pose data, then one common cast
-            Pose<T> q;
-            q.x = is_b ? qb.x : qa.x; q.y = is_b ? qb.y : qa.y; q.phi = is_b ? qb.phi : qa.phi;
-            q.th1 = is_b ? qb.th1 : qa.th1; q.th2 = is_b ? qb.th2 : qa.th2;
-            q.th3 = is_b ? qb.th3 : qa.th3; q.th4 = is_b ? qb.th4 : qa.th4;
-            q.collided = is_b ? qb.collided : qa.collided;
-            const T l = cast_ray<T>(p, q, ray, nobs, s_obs[w][is_b ? 1 : 0], active);
-            if (active) {
-                const T v = ((T)2 * l / (T)p.laser_dis - (T)1) * g;
-                stio<T, IO32>(is_b ? io.next_obs : io.obs, n, 4 + ray, i, v);
-                if (is_b && mirror) stio<T, IO32>(mirror, n, 4 + ray, i, v);
+
+    for (int scan = scan_a ? 0 : 1; scan < 2; ++scan) {
+        if (own) {
+            const T px = scan ? x : xa, py = scan ? y : ya, pphi = scan ? phi : phia;
+            // collision_check :261-272 + in-range list in np.argsort(centre distance) order (stable insertion)
+            bool collided = false;
+            int cnt = 0;
+            for (int k = 0; k < nobs; ++k) {
+                const T cx = ld<T>(io.state, n, F_OBS + 3 * k + 0, i), cy = ld<T>(io.state, n, F_OBS + 3 * k + 1, i);
+                const T r = ld<T>(io.state, n, F_OBS + 3 * k + 2, i);
+                const T d = norm2(px - cx, py - cy);
+                collided = collided || d <= r + (T)p.r_vehicle;
+                if (!(d > (T)p.laser_dis + r)) { // :349 `if dis > self.laserDis + _r: continue`
+                    int pos = cnt;
+                    while (pos > 0 && s_o[3][pos - 1][t] > d) {
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) s_o[a][pos][t] = s_o[a][pos - 1][t];
+                        --pos;
+                    }
+                    s_o[0][pos][t] = cx; s_o[1][pos][t] = cy; s_o[2][pos][t] = r; s_o[3][pos][t] = d;
+                    ++cnt;
+                }
+            }
+            s_cnt[t] = cnt;
+            s_col[t] = collided ? 1 : 0;
+            s_pose[0][t] = px; s_pose[1][t] = py; s_pose[2][t] = pphi;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s_pose[3 + k][t] = corner_bearing<T>(p, px, py, k);
+            if (scan == 1) {
+                // ---- is_Terminal :431-449
+                T nk[4], err, ephi;
+                kin_obs<T>(p, x, y, vel, phi, omega, tgx, tgy, nk, &err, &ephi);
+                const bool succ = Mth<T>::abs(err) <= (T)0.05 && (p.variant != 0 || Mth<T>::abs(omega) < (T)0.01) &&
+                                  Mth<T>::abs(vel) < (T)0.01;
+                int flag = 0;
+                if (x > (T)p.map_x || x < (T)0 || y > (T)p.map_y || y < (T)0) flag = 1;
+                if (time > p.time_max) flag = 2;
+                if (succ) flag = 3;
+                if (collided) flag = 4;
+                const bool done = flag != 0;
+                const bool will_reset = done && (flags & B200ENV_AUTO_RESET);
+                // ---- get_reward :451-467 / demo copy :449-473
+                T reward;
+                if (p.variant == 0) {
+                    const T u_pos = -Mth<T>::abs(err) * (T)p.Q_pos, u_vel = -Mth<T>::abs(vel) * (T)p.Q_vel;
+                    const T u_phi = err > (T)0.1 ? -Mth<T>::abs(ephi) * (T)p.Q_phi : (T)0;
+                    const T u_omega = -Mth<T>::abs(omega) * (T)p.Q_omega;
+                    T u_psi = (T)0;
+                    if (flag == 1) u_psi = (T)((p.time_max - time) / p.dt) * (u_pos + u_vel + u_phi + u_omega);
+                    reward = u_pos + u_vel + u_phi + u_omega + u_psi;
+                } else {
+                    const T cur1 = ((T)(2 / p.v_max) * cur_vel - (T)1) * g;
+                    const T r1 = (T)-1 - Mth<T>::abs(omega) * (T)0.1;
+                    const T r2 = cur_e > nk[0] + (T)1e-3 ? (T)5 : ((T)1e-3 + cur_e < nk[0] ? (T)-5 : (T)0);
+                    const T r3 = Mth<T>::abs(cur1) > Mth<T>::abs(nk[1]) + (T)1e-2 ? (T)2
+                                 : ((T)1e-2 + Mth<T>::abs(cur1) < Mth<T>::abs(nk[1]) ? (T)-2 : (T)0);
+                    const T r4 = succ ? (T)500 : (flag == 4 ? (T)-300 : (T)0);
+                    reward = r1 + r2 + r3 + r4;
+                }
+                const bool mirror = !will_reset && io.reset_obs; // policy-facing obs = next_obs unless reset
+                s_mirror[t] = mirror ? 1 : 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    stio<T, IO32>(io.next_obs, n, k, i, nk[k]);
+                    if (mirror) stio<T, IO32>(io.reset_obs, n, k, i, nk[k]);
+                }
+                stio<T, IO32>(io.reward, n, 0, i, reward);
+                io.done[i] = done ? 1 : 0;
+                io.flag[i] = flag;
+                if (will_reset) {
+                    s_reset[atomicAdd(&s_nreset, 1)] = t;
+                } else {
+                    st<T>(io.state, n, F_X, i, x); st<T>(io.state, n, F_Y, i, y); st<T>(io.state, n, F_VEL, i, vel);
+                    st<T>(io.state, n, F_PHI, i, phi); st<T>(io.state, n, F_OMEGA, i, omega);
+                    io.time[i] = time;
+                }
             }
         }
+        __syncthreads();
+        // ---- phase 2: get_fake_laser :274-397 for all rays of the block
+        void *dst = scan ? io.next_obs : io.obs;
+        const int total = gv * NR;
+        for (int idx = t; idx < total; idx += TPB) {
+            const int li = idx / NR, ray = idx - li * NR;
+            Pose<T> q;
+            q.x = s_pose[0][li]; q.y = s_pose[1][li]; q.phi = s_pose[2][li];
+            q.th1 = s_pose[3][li]; q.th2 = s_pose[4][li]; q.th3 = s_pose[5][li]; q.th4 = s_pose[6][li];
+            q.collided = s_col[li] != 0;
+            ObsList<T> l;
+            l.x0 = &s_o[0][0][li]; l.y0 = &s_o[1][0][li]; l.r0 = &s_o[2][0][li]; l.d = &s_o[3][0][li];
+            l.stride = G; l.count = s_cnt[li];
+            const T v = ((T)2 * cast_ray<T>(p, q, ray, l) / (T)p.laser_dis - (T)1) * g;
+            stio<T, IO32>(dst, n, 4 + ray, base + li, v);
+            if (scan && s_mirror[li]) stio<T, IO32>(io.reset_obs, n, 4 + ray, base + li, v);
+        }
+        __syncthreads();
     }
-    // ---- get_reward :451-467 / demo copy :449-473
-    const T nxt0 = ((T)(2 / p.e_max) * err - (T)1) * g, nxt1 = ((T)(2 / p.v_max) * vel - (T)1) * g;
-    T reward;
-    if (p.variant == 0) {
-        const T u_pos = -Mth<T>::abs(err) * (T)p.Q_pos, u_vel = -Mth<T>::abs(vel) * (T)p.Q_vel;
-        const T u_phi = err > (T)0.1 ? -Mth<T>::abs(ephi) * (T)p.Q_phi : (T)0;
-        const T u_omega = -Mth<T>::abs(omega) * (T)p.Q_omega;
-        T u_psi = (T)0;
-        if (flag == 1) u_psi = (T)((p.time_max - time) / p.dt) * (u_pos + u_vel + u_phi + u_omega);
-        reward = u_pos + u_vel + u_phi + u_omega + u_psi;
-    } else {
-        const T cur1 = ((T)(2 / p.v_max) * cur_vel - (T)1) * g;
-        const T r1 = (T)-1 - Mth<T>::abs(omega) * (T)0.1;
-        const T r2 = cur_e > nxt0 + (T)1e-3 ? (T)5 : ((T)1e-3 + cur_e < nxt0 ? (T)-5 : (T)0);
-        const T r3 = Mth<T>::abs(cur1) > Mth<T>::abs(nxt1) + (T)1e-2 ? (T)2
-                     : ((T)1e-2 + Mth<T>::abs(cur1) < Mth<T>::abs(nxt1) ? (T)-2 : (T)0);
-        const T r4 = succ ? (T)500 : (flag == 4 ? (T)-300 : (T)0);
-        reward = r1 + r2 + r3 + r4;
+    // ---- phase 3: auto-reset (the `env.reset(True)` branch of the train loops), one warp per terminated instance
+    const int lane = t & 31, w = t >> 5, nres = s_nreset;
+    for (int k = w; k < nres; k += TPB / 32) {
+        const int64_t ir = base + s_reset[k];
+        WarpInst<T> e;
+        warp_load<T>(io, n, ir, lane, e);
+        warp_reset<T>(p, io, n, ir, seed, off, lane, e);
+        if (io.reset_obs) // the four [MAXO][G] shared arrays are free again: row w of each is this warp's list
+            warp_observe<T, IO32>(p, n, ir, lane, e, io.reset_obs, &s_o[0][w][0], &s_o[1][w][0], &s_o[2][w][0], &s_o[3][w][0]);
     }
-    if (lane == 0) {
-        const T o2 = ephi / (T)p.e_phi_max * g, o3 = omega / (T)p.omega_max * g;
-        stio<T, IO32>(io.next_obs, n, 0, i, nxt0);
-        stio<T, IO32>(io.next_obs, n, 1, i, nxt1);
-        stio<T, IO32>(io.next_obs, n, 2, i, o2);
-        stio<T, IO32>(io.next_obs, n, 3, i, o3);
-        if (mirror) { stio<T, IO32>(mirror, n, 0, i, nxt0); stio<T, IO32>(mirror, n, 1, i, nxt1); stio<T, IO32>(mirror, n, 2, i, o2); stio<T, IO32>(mirror, n, 3, i, o3); }
-        stio<T, IO32>(io.reward, n, 0, i, reward);
-        io.done[i] = done ? 1 : 0;
-        io.flag[i] = flag;
-    }
-    __syncwarp();
-    if (will_reset) {
-        do_reset();
-        if (io.reset_obs) observe_into(io.reset_obs, 0);
-    }
-    store_state();
 }
 
 int launch(int dtype, int64_t n, const void *params, const b200env_io *io, uint32_t flags, uint64_t seed, int64_t off,
            const uint8_t *mask, int mode, cudaStream_t s) {
     const P &p = *static_cast<const P *>(params);
     if (p.n_rays < 2 || p.n_rays > B200_UGVO_MAX_RAYS || p.obs_num < 0 || p.obs_num > MAXO) return B200ENV_EPARAMS;
-    const unsigned grid = (unsigned)((n + WARPS - 1) / WARPS);
-    B200_LAUNCH_TIO(ugvo_kernel, grid, WARPS * 32, s, p, *io, n, flags, seed, off, mask, mode);
+    if (mode == 0) {
+        const unsigned grid = (unsigned)((n + G - 1) / G);
+        B200_LAUNCH_TIO(ugvo_step_kernel, grid, TPB, s, p, *io, n, flags, seed, off);
+    } else {
+        const unsigned grid = (unsigned)((n + WARPS - 1) / WARPS);
+        B200_LAUNCH_TIO(ugvo_aux_kernel, grid, WARPS * 32, s, p, *io, n, seed, off, mask, mode);
+    }
     return b200_check_launch();
 }
 

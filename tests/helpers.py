@@ -260,3 +260,52 @@ def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None
                                   torch.from_numpy(orc.episode.astype(np.int32)))
     return dict(worst=worst, worst_io=worst_io, flag_mismatch=flag_mismatch, terminals=n_done,
                 tol=tol if tol is not None else ENGINE_TOL[name])
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 mode: stated per-env tolerances over short horizons (BASELINE north_star)
+# ---------------------------------------------------------------------------------------------
+# (one-step tolerance, 100-step free-running tolerance or None) on the mixed error of what the RL side sees
+# (next_state and reward), measured against the fp64 reference fixtures on B200 (tools/f32_field_report.py,
+# tests/parity_report.py engine_f32) and rounded up ~4x.  The bound applies to the 99.9 % quantile over (step, lane)
+# samples: the control laws contain genuine discontinuities -- k2*tanh(10 sigma) switching (gain ~1e4 through 1/J),
+# the thrust division uf = (u_z + g) m / (cos phi cos theta) near u_z = -g, the +-pi yaw wrap, steep laser rays
+# (slope tan(phi) up to 1e7 in fp32) -- where a 1e-7 input difference legitimately flips the branch; those samples are
+# counted (`outliers`) and must stay below 0.1 %.  Terminal flags must agree except within the same band.
+# None = no free-running statement (chaotic / open-loop unstable plant, or gains redrawn from U(0,5) every step).
+FP32_TOL = {
+    "cartpole": (2e-6, 2e-5), "cartpole_gentle": (2e-6, None), "cartpole_angleonly_env": (2e-6, 2e-5),
+    "cartpole_angleonly_ppo2": (2e-6, 1e-5),
+    "fas": (2e-6, 1e-5), "fas_ppo2": (2e-6, 1e-5), "soi": (1e-6, 5e-6), "soi_dppo2": (1e-6, 5e-6),
+    "ballbalancer": (4e-6, 3e-4), "twolink": (1e-5, None),
+    "ugv_forward": (1e-5, 2e-5), "ugv_bidirectional": (4e-6, 1e-5),
+    "ugvo": (2e-3, 2e-3), "ugvo_dppo2": (2e-3, 2e-3),
+    "uav_att": (3e-6, 2e-5), "uav_att_rand": (3e-6, 2e-5), "uav_att_edge": (3e-6, 2e-5),
+    "uav_pos": (8e-3, None), "uav_pos_dis": (8e-3, None), "uav_pos_crash": (1e-4, 4e-4), "uav_pos_edge": (1e-4, 4e-4),
+    "uavr_hover_outer": (1e-4, None), "uavr_hover": (1e-4, None), "uavr_inner": (3e-6, 2e-5), "uavr_tracking": (1e-4, None),
+}
+
+
+def fp32_replay(g, backend, steps, resync):
+    """Replay `steps` steps of a fixture through the fp32 engine; returns the per-(step, lane) mixed error of
+    (next_obs, reward) and the number of flag mismatches.  resync: inject the reference state before every step."""
+    T, L = g["reward"].shape
+    T = min(T, steps)
+    has_dis = "dis" in g
+    backend.set_state(g["state0"], g["time0"])
+    errs = np.zeros((T, L))
+    flag_mismatch = 0
+    for t in range(T):
+        if resync and t > 0:
+            st = np.where(np.isnan(g["reset_state"][t - 1]), g["state"][t - 1], g["reset_state"][t - 1])
+            tm = np.where(np.isnan(g["reset_time"][t - 1]), g["time"][t - 1], g["reset_time"][t - 1])
+            backend.set_state(st, tm)
+        out = backend.step(g["actions"][t], g["dis"][t] if has_dis else None)
+        e_obs = np.max(np.abs(out["next_obs"] - g["next_obs"][t]) / np.maximum(1.0, np.abs(g["next_obs"][t])), axis=1)
+        e_rew = np.abs(out["reward"] - g["reward"][t]) / np.maximum(1.0, np.abs(g["reward"][t]))
+        errs[t] = np.maximum(e_obs, e_rew)
+        flag_mismatch += int(np.sum(out["flag"] != g["flag"][t]))
+        lanes = np.nonzero(g["done"][t])[0]
+        if len(lanes) and not resync:
+            backend.set_state(g["reset_state"][t][lanes], g["reset_time"][t][lanes], lanes)
+    return errs, flag_mismatch

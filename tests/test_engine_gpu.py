@@ -4,7 +4,8 @@ re-sync mode; free-running tolerances are stated per env in helpers.ENGINE_TOL."
 import numpy as np
 import pytest
 
-from helpers import ENGINE_TOL, EngineBackend, engine_vs_oracle, env_specs, load_golden, replay
+from helpers import (ENGINE_TOL, FP32_TOL, EngineBackend, engine_vs_oracle, env_specs, fp32_replay, load_golden,
+                     replay)
 
 pytestmark = pytest.mark.gpu
 
@@ -76,3 +77,21 @@ def test_engine_f32_io_keeps_fp64_trajectory(name, oracle_lib):
     assert res["flag_mismatch"] == 0, res
     assert res["worst"] <= res["tol"], res
     assert 0.0 < res["worst_io"] <= 2.0 ** -24 + res["tol"], res
+
+
+@pytest.mark.parametrize("name", sorted(FP32_TOL))
+def test_engine_fp32_stated_tolerance(name):
+    """fp32 mode (state, arithmetic and I/O in float32; `time` stays float64) against the fp64 reference fixtures:
+    one-step and 100-step free-running errors within the per-env tolerance stated in helpers.FP32_TOL."""
+    import torch
+    g = load_golden(name)
+    L = g["reward"].shape[1]
+    one_tol, free_tol = FP32_TOL[name]
+    errs, fm = fp32_replay(g, EngineBackend(name, L, dtype=torch.float32), steps=200, resync=True)
+    assert np.quantile(errs, 0.999) <= one_tol, (name, float(np.quantile(errs, 0.999)), float(errs.max()))
+    assert np.mean(errs > one_tol) <= 1e-3 and fm <= max(1, int(1e-3 * errs.size)), (name, fm)
+    assert np.median(errs) <= 1e-6, (name, float(np.median(errs)))  # typical error: fp32 rounding level
+    if free_tol is not None:
+        errs, fm = fp32_replay(g, EngineBackend(name, L, dtype=torch.float32), steps=100, resync=False)
+        assert np.quantile(errs, 0.999) <= free_tol, (name, float(np.quantile(errs, 0.999)), float(errs.max()))
+        assert fm <= max(1, int(1e-3 * errs.size)), (name, fm)
