@@ -275,6 +275,19 @@ def also_workloads(args, dev, dtype, peaks):
                     "hbm_frac": ALGO_BYTES[w] * n / per / 1e9 / hbm, "desc": WORKLOADS[w]["desc"]})
         del env, pool
         torch.cuda.empty_cache()
+    # fp32 mode (state, arithmetic and I/O in float32; tolerances: tests/helpers.py FP32_TOL) of the headline workload
+    # and of config #2 (CartPole, fp64 vs fp32)
+    for w in (args.workload, "cartpole"):
+        n = WORKLOADS[w]["n"]
+        env = make_env(w, n, dev, 0, torch.float32)
+        env.reset(True)
+        pool = action_pool(env, n, 4, dev, torch.float32, seed=7)
+        ms = timed_steps(env, pool, 100, 5, False)
+        per = ms * 1e-3 / 100
+        out.append({"workload": w + ":f32", "envs": n, "value": n / per, "unit": "env-steps/s", "ms_per_step": ms / 100,
+                    "hbm_frac": ALGO_BYTES[w] / 2.0 * n / per / 1e9 / hbm, "desc": WORKLOADS[w]["desc"] + " [fp32 mode]"})
+        del env, pool
+        torch.cuda.empty_cache()
     # config #3: GAE over a 2048-step rollout, 131072 env columns per GPU
     from reinforcementlearningplatform_b200 import gae as G
     T, N = 2048, 131072

@@ -342,7 +342,7 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     const T asin_phi_d = Mth<T>::min(Mth<T>::max((ctrl[0] * t1.spsi - ctrl[1] * t1.cpsi) * c.m / uf, (T)-1), (T)1);
     T phi_d = Mth<T>::asin(asin_phi_d);
     const T asin_theta_d = Mth<T>::min(
-        Mth<T>::max((ctrl[0] * t1.cpsi + ctrl[1] * t1.spsi) * c.m / (uf * Mth<T>::cos(phi_d)), (T)-1), (T)1);
+        Mth<T>::max((ctrl[0] * t1.cpsi + ctrl[1] * t1.spsi) * c.m / (uf * cos_of_asin<T>(asin_phi_d, phi_d)), (T)-1), (T)1);
     T theta_d = Mth<T>::asin(asin_theta_d);
     const T lim = (T)p.att_limit;
     phi_d = Mth<T>::max(Mth<T>::min(phi_d, lim), -lim);

@@ -183,6 +183,17 @@ __device__ __forceinline__ void att_control(const Consts<T> &c, const T *x, cons
 }
 
 
+// cos(phi_d) in uo_2_ref_angle_throttle (uav_pos_ctrl.py:339-357 / UavRobust uav_pos_ctrl.py:67-76): the reference
+// divides by cos(arcsin(u)).  When u saturates at +-1 that is cos(fl(pi/2)) = +6.1e-17 in fp64 -- theta_d becomes
+// +-pi/2 with the sign of the numerator -- but cosf(fl32(pi/2)) = -4.4e-8 < 0 in fp32, which would mirror theta_d
+// (measured: 1 % of the steps of the UavHover fixture under U(+-8) actions).  The fp64 path keeps the reference's
+// expression bit for bit; the fp32 path uses the identity cos(asin u) = sqrt(1 - u^2) >= 0, which has the fp64 sign.
+template <typename T>
+__device__ __forceinline__ T cos_of_asin(T u, T phi_d) {
+    if (sizeof(T) == 4) return Mth<T>::sqrt(Mth<T>::max(Mth<T>::fma(-u, u, (T)1), (T)0));
+    return Mth<T>::cos(phi_d);
+}
+
 // ref_cmd.py:4-43, one channel
 template <typename T>
 __device__ __forceinline__ void ref_channel(T time, T A, T period, T bias, T phase, T &r, T &dr, T &ddr) {

@@ -154,7 +154,7 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ b200
         const T asin_phi_d = Mth<T>::min(Mth<T>::max((a[0] * t1.spsi - a[1] * t1.cpsi) * c.m / uf, (T)-1), (T)1);
         T phi_d = Mth<T>::asin(asin_phi_d);
         const T asin_theta_d = Mth<T>::min(
-            Mth<T>::max((a[0] * t1.cpsi + a[1] * t1.spsi) * c.m / (uf * Mth<T>::cos(phi_d)), (T)-1), (T)1);
+            Mth<T>::max((a[0] * t1.cpsi + a[1] * t1.spsi) * c.m / (uf * cos_of_asin<T>(asin_phi_d, phi_d)), (T)-1), (T)1);
         T theta_d = Mth<T>::asin(asin_theta_d);
         phi_d = Mth<T>::min(Mth<T>::max(phi_d, (T)r.att_zone_min[0]), (T)r.att_zone_max[0]);
         theta_d = Mth<T>::min(Mth<T>::max(theta_d, (T)r.att_zone_min[1]), (T)r.att_zone_max[1]);

@@ -265,25 +265,28 @@ def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None
 # ---------------------------------------------------------------------------------------------
 # fp32 mode: stated per-env tolerances over short horizons (BASELINE north_star)
 # ---------------------------------------------------------------------------------------------
-# (one-step tolerance, 100-step free-running tolerance or None) on the mixed error of what the RL side sees
-# (next_state and reward), measured against the fp64 reference fixtures on B200 (tools/f32_field_report.py,
-# tests/parity_report.py engine_f32) and rounded up ~4x.  The bound applies to the 99.9 % quantile over (step, lane)
-# samples: the control laws contain genuine discontinuities -- k2*tanh(10 sigma) switching (gain ~1e4 through 1/J),
-# the thrust division uf = (u_z + g) m / (cos phi cos theta) near u_z = -g, the +-pi yaw wrap, steep laser rays
-# (slope tan(phi) up to 1e7 in fp32) -- where a 1e-7 input difference legitimately flips the branch; those samples are
-# counted (`outliers`) and must stay below 0.1 %.  Terminal flags must agree except within the same band.
-# None = no free-running statement (chaotic / open-loop unstable plant, or gains redrawn from U(0,5) every step).
+# (one-step tolerance, 100-step free-running tolerance or None) on the mixed error |a-b| / max(1, |b|) of what the RL
+# side sees (next_state and reward), against the fp64 reference fixtures; measured on B200 with
+# tools/f32_tolerance_report.py and rounded up 2-4x.  The bound applies to the 99.9 % quantile over (step, lane)
+# samples (on these fixtures that is within 10 % of the maximum).  None = no free-running statement: open-loop
+# unstable (cart-pole replay) or chaotic (two-link arm) plants amplify any 1e-7 difference exponentially.
+# One fp32-specific change was needed to get here: cos(arcsin(u)) in the thrust/attitude allocation is evaluated as
+# sqrt(1 - u^2) in fp32 (uav_common.cuh cos_of_asin) because cosf(fl32(pi/2)) is negative where cos(fl64(pi/2)) is
+# positive, which mirrored theta_d whenever the allocation saturated.
 FP32_TOL = {
-    "cartpole": (2e-6, 2e-5), "cartpole_gentle": (2e-6, None), "cartpole_angleonly_env": (2e-6, 2e-5),
+    "cartpole": (2e-6, 1e-5), "cartpole_gentle": (2e-6, None), "cartpole_angleonly_env": (2e-6, 1e-5),
     "cartpole_angleonly_ppo2": (2e-6, 1e-5),
     "fas": (2e-6, 1e-5), "fas_ppo2": (2e-6, 1e-5), "soi": (1e-6, 5e-6), "soi_dppo2": (1e-6, 5e-6),
     "ballbalancer": (4e-6, 3e-4), "twolink": (1e-5, None),
-    "ugv_forward": (1e-5, 2e-5), "ugv_bidirectional": (4e-6, 1e-5),
-    "ugvo": (2e-3, 2e-3), "ugvo_dppo2": (2e-3, 2e-3),
-    "uav_att": (3e-6, 2e-5), "uav_att_rand": (3e-6, 2e-5), "uav_att_edge": (3e-6, 2e-5),
-    "uav_pos": (8e-3, None), "uav_pos_dis": (8e-3, None), "uav_pos_crash": (1e-4, 4e-4), "uav_pos_edge": (1e-4, 4e-4),
-    "uavr_hover_outer": (1e-4, None), "uavr_hover": (1e-4, None), "uavr_inner": (3e-6, 2e-5), "uavr_tracking": (1e-4, None),
+    "ugv_forward": (4e-5, 4e-5), "ugv_bidirectional": (2e-5, 2e-5),
+    "uav_att": (3e-6, 5e-6), "uav_att_rand": (3e-6, 5e-6), "uav_att_edge": (3e-6, 5e-6),
+    "uav_pos": (2e-5, 6e-5), "uav_pos_dis": (2e-5, 6e-5), "uav_pos_crash": (2e-6, 5e-6), "uav_pos_edge": (1e-4, 2e-4),
+    "uavr_hover_outer": (2e-6, 5e-6), "uavr_hover": (3e-5, 6e-5), "uavr_inner": (6e-6, 1e-5), "uavr_tracking": (1e-5, 2e-5),
+    # fake laser: the reference intersects in slope form (m = tan(phi), up to 1e7 in fp32); rays within ~1e-3 rad of
+    # the vertical lose most of their digits, so the bound is on the 99 % quantile (max observed 7e-2 of 2.0 m range)
+    "ugvo": (2e-3, 4e-3), "ugvo_dppo2": (2e-3, 4e-3),
 }
+FP32_QUANTILE = {"ugvo": 0.99, "ugvo_dppo2": 0.99}  # default 0.999
 
 
 def fp32_replay(g, backend, steps, resync):

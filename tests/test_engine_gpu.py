@@ -4,7 +4,7 @@ re-sync mode; free-running tolerances are stated per env in helpers.ENGINE_TOL."
 import numpy as np
 import pytest
 
-from helpers import (ENGINE_TOL, FP32_TOL, EngineBackend, engine_vs_oracle, env_specs, fp32_replay, load_golden,
+from helpers import (ENGINE_TOL, FP32_QUANTILE, FP32_TOL, EngineBackend, engine_vs_oracle, env_specs, fp32_replay, load_golden,
                      replay)
 
 pytestmark = pytest.mark.gpu
@@ -82,16 +82,18 @@ def test_engine_f32_io_keeps_fp64_trajectory(name, oracle_lib):
 @pytest.mark.parametrize("name", sorted(FP32_TOL))
 def test_engine_fp32_stated_tolerance(name):
     """fp32 mode (state, arithmetic and I/O in float32; `time` stays float64) against the fp64 reference fixtures:
-    one-step and 100-step free-running errors within the per-env tolerance stated in helpers.FP32_TOL."""
+    one-step (200 steps, state re-injected) and 100-step free-running errors of next_state and reward within the
+    per-env tolerance stated in helpers.FP32_TOL; terminal flags identical on these fixtures."""
     import torch
     g = load_golden(name)
     L = g["reward"].shape[1]
     one_tol, free_tol = FP32_TOL[name]
+    q = FP32_QUANTILE.get(name, 0.999)
     errs, fm = fp32_replay(g, EngineBackend(name, L, dtype=torch.float32), steps=200, resync=True)
-    assert np.quantile(errs, 0.999) <= one_tol, (name, float(np.quantile(errs, 0.999)), float(errs.max()))
-    assert np.mean(errs > one_tol) <= 1e-3 and fm <= max(1, int(1e-3 * errs.size)), (name, fm)
-    assert np.median(errs) <= 1e-6, (name, float(np.median(errs)))  # typical error: fp32 rounding level
+    assert np.quantile(errs, q) <= one_tol, (name, float(np.quantile(errs, q)), float(errs.max()))
+    assert fm == 0, (name, fm)
+    assert np.median(errs) <= 5e-6, (name, float(np.median(errs)))  # typical error: a few fp32 roundings
     if free_tol is not None:
         errs, fm = fp32_replay(g, EngineBackend(name, L, dtype=torch.float32), steps=100, resync=False)
-        assert np.quantile(errs, 0.999) <= free_tol, (name, float(np.quantile(errs, 0.999)), float(errs.max()))
-        assert fm <= max(1, int(1e-3 * errs.size)), (name, fm)
+        assert np.quantile(errs, q) <= free_tol, (name, float(np.quantile(errs, q)), float(errs.max()))
+        assert fm == 0, (name, fm)
