@@ -35,7 +35,7 @@ class B200EnvError(RuntimeError):
 class IO(C.Structure):
     """struct b200env_io"""
     _fields_ = [(k, C.c_void_p) for k in (
-        "state", "time", "episode", "action", "dis", "obs", "next_obs", "reward", "done", "flag", "reset_obs")] + [
+        "state", "time", "episode", "action", "dis", "obs", "next_obs", "reward", "done", "flag", "reset_obs", "work")] + [
         ("io_dtype", C.c_int32), ("pad_", C.c_int32)]
 
 

@@ -206,6 +206,13 @@ __device__ __forceinline__ Draw2 draw2(uint64_t seed, uint64_t gid, uint32_t ep,
     return d;
 }
 __device__ __forceinline__ double lerp_u(double lo, double hi, double u) { return ::fma(hi - lo, u, lo); }
+// dis_two_points(a, b) <= R, i.e. sqrt(dx^2 + dy^2) <= R (map.py:122,131-133), decided on the squares; the square root is
+// only taken when the two sides agree to ~14 digits, so the decision is the reference's in every case
+__device__ __forceinline__ bool within(double dx, double dy, double R) {
+    const double d2 = dx * dx + dy * dy, R2 = R * R;
+    if (fabs(d2 - R2) <= 1e-13 * R2) return sqrt(d2) <= R;
+    return d2 <= R2;
+}
 
 // reset(random=True) :527-557 + Map.generate_circle_obs_training (map.py:152-174), cooperative over the warp.
 // Outputs (uniform over the warp): start/target/phi0; per-lane obstacle k = lane (cx, cy, r), nobs.
@@ -246,11 +253,12 @@ __device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gi
             const Draw2 dr = draw2(seed, gid, ep, blk + 1u);
             const double cx = lerp_u(0., p.map_x, d.u0), cy = lerp_u(0., p.map_y, d.u1), r = lerp_u(p.r_min, p.r_max, dr.u0);
             bool legal = true; // map.py:129-139
-            if (sqrt((sx - cx) * (sx - cx) + (sy - cy) * (sy - cy)) <= r + p.safety_dis_st) legal = false;
-            if (sqrt((tx - cx) * (tx - cx) + (ty - cy) * (ty - cy)) <= r + p.safety_dis_st) legal = false;
-            for (int q = 0; q < nobs; ++q) {
+            if (within(sx - cx, sy - cy, r + p.safety_dis_st)) legal = false;
+            if (within(tx - cx, ty - cy, r + p.safety_dis_st)) legal = false;
+            for (int q = 0; q < nobs; ++q) { // placed obstacles: broadcast from lane q
+                if (!__any_sync(FULL, legal)) break; // all 32 candidates of this round are already rejected
                 const double qx = __shfl_sync(FULL, ocx, q), qy = __shfl_sync(FULL, ocy, q), qr = __shfl_sync(FULL, orr, q);
-                if (sqrt((qx - cx) * (qx - cx) + (qy - cy) * (qy - cy)) <= qr + r + p.safety_dis_obs) legal = false;
+                if (within(qx - cx, qy - cy, qr + r + p.safety_dis_obs)) legal = false;
             }
             const unsigned m = __ballot_sync(FULL, legal);
             if (m) {
@@ -378,8 +386,7 @@ ugvo_aux_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io 
 //            once per instance with every lane busy, and its loads / stores are coalesced over instances;
 //   phase 2  the G x n_rays rays are dealt round-robin to all threads of the block (a warp covers at most two
 //            instances, so the obstacle lists are shared-memory broadcasts) -- every lane casts a ray;
-//   phase 3  instances that terminated with auto-reset on: one warp each draws the new map (rejection sampling by
-//            ballot) and casts the reset observation.
+//   (phase 3, auto-reset of the terminated instances, is a second launch: ugvo_autoreset_kernel)
 // With io.obs == NULL (observation reuse, vec_env.py) only the post-update scan is cast (one scan per step).
 constexpr int G = 64;
 constexpr int TPB = 128;
@@ -390,7 +397,7 @@ ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io
                  uint64_t seed, int64_t off) {
     __shared__ T s_o[4][MAXO][G];                 // x0, y0, r0, d of the in-range obstacles, [slot][instance]
     __shared__ T s_pose[7][G];                    // x, y, phi, th1..th4
-    __shared__ int s_cnt[G], s_reset[G], s_nreset;
+    __shared__ int s_cnt[G];
     __shared__ unsigned char s_col[G], s_mirror[G];
     const int t = threadIdx.x;
     const int64_t base = (int64_t)blockIdx.x * G;
@@ -400,9 +407,6 @@ ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io
     const int64_t i = base + t;
     const bool scan_a = io.obs != nullptr;
     const T g = (T)p.static_gain;
-    if (t == 0) s_nreset = 0;
-    __syncthreads();
-
     T x = (T)0, y = (T)0, vel = (T)0, phi = (T)0, omega = (T)0, tgx = (T)0, tgy = (T)0;
     T xa = (T)0, ya = (T)0, phia = (T)0, cur_e = (T)0, cur_vel = (T)0;
     int nobs = 0;
@@ -525,8 +529,8 @@ ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io
                 stio<T, IO32>(io.reward, n, 0, i, reward);
                 io.done[i] = done ? 1 : 0;
                 io.flag[i] = flag;
-                if (will_reset) {
-                    s_reset[atomicAdd(&s_nreset, 1)] = t;
+                if (will_reset) { // re-initialised by ugvo_autoreset_kernel
+                    if (io.work) io.work[1 + atomicAdd(io.work, 1)] = (int32_t)i;
                 } else {
                     st<T>(io.state, n, F_X, i, x); st<T>(io.state, n, F_Y, i, y); st<T>(io.state, n, F_VEL, i, vel);
                     st<T>(io.state, n, F_PHI, i, phi); st<T>(io.state, n, F_OMEGA, i, omega);
@@ -553,15 +557,45 @@ ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io
         }
         __syncthreads();
     }
-    // ---- phase 3: auto-reset (the `env.reset(True)` branch of the train loops), one warp per terminated instance
-    const int lane = t & 31, w = t >> 5, nres = s_nreset;
-    for (int k = w; k < nres; k += TPB / 32) {
-        const int64_t ir = base + s_reset[k];
-        WarpInst<T> e;
-        warp_load<T>(io, n, ir, lane, e);
-        warp_reset<T>(p, io, n, ir, seed, off, lane, e);
-        if (io.reset_obs) // the four [MAXO][G] shared arrays are free again: row w of each is this warp's list
-            warp_observe<T, IO32>(p, n, ir, lane, e, io.reset_obs, &s_o[0][w][0], &s_o[1][w][0], &s_o[2][w][0], &s_o[3][w][0]);
+}
+
+// ---- phase 3 of a step with B200ENV_AUTO_RESET (the `env.reset(True)` branch of the train loops) as its own launch:
+// every warp looks at the `done` flags of 32 consecutive instances and re-initialises the terminated ones, one after
+// the other, with all 32 lanes (map rejection sampling by ballot, then the 37-ray reset observation).  Kept out of the
+// step kernel because a reset is ~3000 dependent warp instructions: inside the step it left three of the four warps of
+// a block idle behind it (0.60 -> 0.95 ms per step at ~1 reset per block, ncu/bench).  With the optional scratch list
+// io.work the step kernel appends the terminated instances and the warps of this grid share them evenly; without it
+// every warp scans the `done` flags of its 32-instance groups.
+constexpr int RESET_WARPS = 8;
+template <typename T, bool IO32>
+__global__ void __launch_bounds__(RESET_WARPS * 32, 4)
+ugvo_autoreset_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint64_t seed,
+                      int64_t off) {
+    __shared__ T s_o[RESET_WARPS][4][MAXO];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * RESET_WARPS + w, nw = (int64_t)gridDim.x * RESET_WARPS;
+    if (io.work) {
+        // the step kernel appended the terminated instances to io.work[1..]: deal them evenly to all warps of the grid
+        const int count = io.work[0];
+        for (int64_t k = gw; k < count; k += nw) {
+            const int64_t ir = io.work[1 + k];
+            WarpInst<T> e;
+            warp_reset<T>(p, io, n, ir, seed, off, lane, e);
+            if (io.reset_obs) warp_observe<T, IO32>(p, n, ir, lane, e, io.reset_obs, s_o[w][0], s_o[w][1], s_o[w][2], s_o[w][3]);
+        }
+        return;
+    }
+    // no scratch list: every warp scans the `done` flags of 32-instance groups
+    for (int64_t first = gw * 32; first < n; first += nw * 32) {
+        const int64_t mine = first + lane;
+        unsigned todo = __ballot_sync(FULL, mine < n && io.done[mine] != 0);
+        while (todo) {
+            const int64_t ir = first + (__ffs(todo) - 1);
+            todo &= todo - 1;
+            WarpInst<T> e;
+            warp_reset<T>(p, io, n, ir, seed, off, lane, e);
+            if (io.reset_obs) warp_observe<T, IO32>(p, n, ir, lane, e, io.reset_obs, s_o[w][0], s_o[w][1], s_o[w][2], s_o[w][3]);
+        }
     }
 }
 
@@ -571,7 +605,18 @@ int launch(int dtype, int64_t n, const void *params, const b200env_io *io, uint3
     if (p.n_rays < 2 || p.n_rays > B200_UGVO_MAX_RAYS || p.obs_num < 0 || p.obs_num > MAXO) return B200ENV_EPARAMS;
     if (mode == 0) {
         const unsigned grid = (unsigned)((n + G - 1) / G);
+        const bool ar = (flags & B200ENV_AUTO_RESET) != 0;
+        if (ar && io->work) {
+            if (n > (int64_t)0x7fffffff) return B200ENV_ESIZE; // the list holds 32-bit instance indices
+            if (cudaMemsetAsync(io->work, 0, sizeof(int32_t), s) != cudaSuccess) return b200_check_launch();
+        }
         B200_LAUNCH_TIO(ugvo_step_kernel, grid, TPB, s, p, *io, n, flags, seed, off);
+        if (ar) {
+            // enough warps to hold every SM at 4 blocks; with the list they stride over it, without it over the batch
+            int64_t rgrid = (n + RESET_WARPS * 32 - 1) / (RESET_WARPS * 32);
+            if (rgrid > 148 * 4) rgrid = 148 * 4;
+            B200_LAUNCH_TIO(ugvo_autoreset_kernel, (unsigned)rgrid, RESET_WARPS * 32, s, p, *io, n, seed, off);
+        }
     } else {
         const unsigned grid = (unsigned)((n + WARPS - 1) / WARPS);
         B200_LAUNCH_TIO(ugvo_aux_kernel, grid, WARPS * 32, s, p, *io, n, seed, off, mask, mode);

@@ -198,6 +198,7 @@ class UGVForwardObstacleAvoidance(_Simple):
     4 kinematic terms + 37 fake-laser ranges (kernel K-UGVO: one warp per instance, lanes = rays)."""
     ENV_ID = _lib.UGVO
     OBS_IS_PURE = True
+    USES_WORK_LIST = True
     MAX_OBS = 16
     STATE_FIELDS = tuple(["x", "y", "vel", "phi", "omega", "target_x", "target_y", "n_obs"] +
                          [f"{c}_{k}" for k in range(16) for c in ("cx", "cy", "r")])

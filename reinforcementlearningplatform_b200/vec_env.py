@@ -33,6 +33,7 @@ class VecEnvBase:
     # of UGVForwardObstacleAvoidance this removes one of the two 37-ray scans per step).  Not true for the
     # UAV envs (the reset observation is taken against the stale reference) nor the two-link arm (pre-wrap error).
     OBS_IS_PURE: bool = False
+    USES_WORK_LIST: bool = False  # the step kernel wants b200env_io.work (list of terminated instances)
 
     def __init__(self, n_envs: int = 1, device="cuda", dtype=torch.float64, seed: int = 0,
                  env_index_offset: int = 0, auto_reset: bool = False, host_only: bool = False, io_dtype=None,
@@ -80,6 +81,7 @@ class VecEnvBase:
         self._done = z(N, dt=torch.uint8)
         self._flag = z(N, dt=torch.int32)
         self._action = z(ad, N)
+        self._work = z(N + 1, dt=torch.int32) if self.USES_WORK_LIST else None  # b200env_io.work
 
         '''rl_base'''
         self.state_dim = od
@@ -116,6 +118,7 @@ class VecEnvBase:
         io.done = self._done.data_ptr()
         io.flag = self._flag.data_ptr()
         io.reset_obs = self._reset_obs.data_ptr() if reset_obs else None
+        io.work = None if self._work is None else self._work.data_ptr()
         io.io_dtype = _lib.F32 if (self.io_dtype == torch.float32 and self.dtype == torch.float64) else _lib.F64
         return io
 
