@@ -185,6 +185,21 @@ static inline int b200_check_launch() {
     return B200ENV_OK;
 }
 
+// grid of a persistent kernel: blocks_per_sm resident blocks on every SM of the current device (148 on B200), never
+// more blocks than tiles
+static inline unsigned b200_persistent_grid(int64_t n, int blocks_per_sm, int block = B200_BLOCK) {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sms[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev] = v;
+    }
+    const int64_t tiles = (n + block - 1) / block, cap = (int64_t)sms[dev] * blocks_per_sm;
+    return (unsigned)(tiles < cap ? tiles : cap);
+}
 // float32 I/O buffers with fp64 arithmetic (b200env_io::io_dtype); in F32 mode everything is float anyway
 static inline bool b200_io32(const b200env_io *io) { return io->io_dtype == B200ENV_F32; }
 // launches KERN<T, IO32> for (double, io32) / (double, native) / float; expects `dtype` and `io` in scope

@@ -95,12 +95,12 @@ __device__ __forceinline__ void att_observe(const T *x, const Trig<T> &t, const 
 
 template <typename T, typename I, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK, UAV_ATT_MINBLOCKS)
-uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n_, uint32_t flags,
-                    uint64_t seed, int64_t off) {
+uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ UavDerived dv,
+                    const __grid_constant__ b200env_io io, int64_t n_, uint32_t flags, uint64_t seed, int64_t off) {
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= n_) return;
     const I n = (I)n_, i = (I)gi;
-    const Consts<T> c(p);
+    const Consts<T> c(p.m, p.g, p.J, p.kr, p.kt, p.dt, dv);
     T x[12];
 #pragma unroll
     for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = ld<T>(io.state, n, k, i); }
@@ -271,14 +271,10 @@ __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io
     io.episode[i] = ep + 1u;
 }
 
+// one instance, one control period (the body of the step kernel)
 template <typename T, typename I, bool IO32>
-__global__ void __launch_bounds__(B200_BLOCK, UAV_POS_MINBLOCKS)
-uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n_, uint32_t flags,
-                    uint64_t seed, int64_t off) {
-    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= n_) return;
-    const I n = (I)n_, i = (I)gi;
-    const Consts<T> c(p);
+__device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c, const b200env_io &io, I n, I i,
+                                                 uint32_t flags, uint64_t seed, int64_t off) {
     T x[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) x[k] = ld<T>(io.state, n, k, i);
@@ -323,7 +319,7 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
         ref_channel<T>((T)time, rA[k], rT[k], (T)p.ref_bias_a[k], rP[k], ref[k], dref[k], ddref[k]);
     // ---- pos_control, uav_pos_ctrl.py:302-315 + FNTSMC.py:47-69 (obs = 0)
     T ctrl[3];
-    const T kt_m = c.kt / c.m;
+    const T kt_m = c.kt_m; // kt / m (uav_pos_ctrl.py:310), constant: the compiler folds it from the kernel arguments
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const T e = x[k] - ref[k], de = x[3 + k] - dref[k];
@@ -416,6 +412,45 @@ uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env
     }
 }
 
+#ifdef UAV_PREFETCH_AHEAD
+// Experiment (tools/build_variant.sh): L2 bulk prefetch of the SoA rows that the block UAV_PREFETCH_AHEAD positions
+// later in the grid will load.  Measured on B200: no gain (3.76e9 -> 3.4e9 with a persistent loop, whose blocks stay in
+// lock-step and all load at once), so it is off by default.
+__device__ __forceinline__ void prefetch_row_l2(const void *base, size_t elsize, int64_t n, int row, int64_t start, int count) {
+    const char *ptr = static_cast<const char *>(base) + ((int64_t)row * n + start) * (int64_t)elsize;
+    const unsigned bytes = (unsigned)((size_t)count * elsize) & ~15u;
+    if (bytes && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes));
+}
+#endif
+
+template <typename T, typename I, bool IO32>
+__global__ void __launch_bounds__(B200_BLOCK, UAV_POS_MINBLOCKS)
+uav_pos_step_kernel(const __grid_constant__ P p, const __grid_constant__ UavDerived dv,
+                    const __grid_constant__ b200env_io io, int64_t n_, uint32_t flags, uint64_t seed, int64_t off) {
+#ifdef UAV_PREFETCH_AHEAD
+    {
+        const int64_t start = ((int64_t)blockIdx.x + UAV_PREFETCH_AHEAD) * B200_BLOCK;
+        if (start < n_) {
+            const int count = (int)((n_ - start) < (int64_t)B200_BLOCK ? (n_ - start) : (int64_t)B200_BLOCK);
+            const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // warp-uniform for the compiler
+            const size_t es = sizeof(T), eio = IO32 ? sizeof(float) : sizeof(T);
+            if ((threadIdx.x & 31) == 0) {
+                for (int r = w; r < P_PREF + 9; r += B200_BLOCK / 32) {
+                    if (r < P_PREF) prefetch_row_l2(io.state, es, n_, r, start, count);
+                    else if (r < P_PREF + 8) prefetch_row_l2(io.action, eio, n_, r - P_PREF, start, count);
+                    else prefetch_row_l2(io.time, sizeof(double), n_, 0, start, count);
+                }
+            }
+        }
+    }
+#endif
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_) return;
+    const Consts<T> c(p.m, p.g, p.J, p.kr, p.kt, p.dt, dv);
+    uav_pos_step_one<T, I, IO32>(p, c, io, (I)n_, (I)gi, flags, seed, off);
+}
+
 template <typename T, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK)
 uav_pos_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n,
@@ -444,11 +479,11 @@ uav_pos_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200en
 #define UAV_LAUNCH(kern, ...) B200_LAUNCH_TIO(kern, b200_grid(n), B200_BLOCK, s, __VA_ARGS__)
 
 // step kernels: 32-bit SoA index arithmetic whenever every [field][n] offset fits in 32 bits
-#define UAV_LAUNCH_STEP(kern, fields, ...)                                                                         \
+#define UAV_LAUNCH_STEP(kern, fields, gridexpr, ...)                                                                        \
     do {                                                                                                           \
         const bool i32 = (int64_t)(fields) * n < ((int64_t)1 << 32);                                               \
         const bool o32 = b200_io32(io);                                                                            \
-        const unsigned g = b200_grid(n);                                                                           \
+        const unsigned g = (gridexpr);                                                                             \
         if (dtype == B200ENV_F64) {                                                                                \
             if (i32 && o32) kern<double, uint32_t, true><<<g, B200_BLOCK, 0, s>>>(__VA_ARGS__);                    \
             else if (i32) kern<double, uint32_t, false><<<g, B200_BLOCK, 0, s>>>(__VA_ARGS__);                     \
@@ -488,7 +523,7 @@ int uav_att_step(int dtype, int64_t n, const void *params, const b200env_io *io,
     int rc = uav_check_step(io, flags);
     if (rc) return rc;
     const P &p = *static_cast<const P *>(params);
-    UAV_LAUNCH_STEP(uav_att_step_kernel, B200_UAV_ATT_STATE_FIELDS, p, *io, n, flags, seed, off);
+    UAV_LAUNCH_STEP(uav_att_step_kernel, B200_UAV_ATT_STATE_FIELDS, b200_grid(n), p, uav_derive(p.m, p.J, p.kt), *io, n, flags, seed, off);
     return b200_check_launch();
 }
 int uav_pos_step(int dtype, int64_t n, const void *params, const b200env_io *io, uint32_t flags, uint64_t seed,
@@ -496,7 +531,7 @@ int uav_pos_step(int dtype, int64_t n, const void *params, const b200env_io *io,
     int rc = uav_check_step(io, flags);
     if (rc) return rc;
     const P &p = *static_cast<const P *>(params);
-    UAV_LAUNCH_STEP(uav_pos_step_kernel, B200_UAV_POS_STATE_FIELDS, p, *io, n, flags, seed, off);
+    UAV_LAUNCH_STEP(uav_pos_step_kernel, B200_UAV_POS_STATE_FIELDS, b200_grid(n), p, uav_derive(p.m, p.J, p.kt), *io, n, flags, seed, off);
     return b200_check_launch();
 }
 int uav_att_reset(int dtype, int64_t n, const void *params, const b200env_io *io, const uint8_t *mask, uint64_t seed,

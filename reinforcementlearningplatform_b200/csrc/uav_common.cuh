@@ -26,17 +26,28 @@ struct Trig {
     }
 };
 
+// constants derived from the parameters on the HOST (launcher) and passed as a kernel argument: the reciprocals of
+// J and m and kt / m used to be recomputed by every thread (five fp64 divisions, ~125 instructions per step)
+struct UavDerived {
+    double rJ[3], rm, kt_m, J21, J02, J10;
+};
+static inline UavDerived uav_derive(double m, const double *J, double kt) {
+    UavDerived d;
+    for (int k = 0; k < 3; ++k) d.rJ[k] = 1.0 / J[k];
+    d.rm = 1.0 / m;
+    d.kt_m = kt / m;
+    d.J21 = J[2] - J[1]; d.J02 = J[0] - J[2]; d.J10 = J[1] - J[0];
+    return d;
+}
+
 template <typename T>
 struct Consts {
-    T m, g, kr, kt, J0, J1, J2, J21, J02, J10, dt, rJ0, rJ1, rJ2, rm;
-    __device__ __forceinline__ Consts(double m_, double g_, const double *J, double kr_, double kt_, double dt_)
-        : m((T)m_), g((T)g_), kr((T)kr_), kt((T)kt_), J0((T)J[0]), J1((T)J[1]), J2((T)J[2]),
-          J21((T)(J[2] - J[1])), J02((T)(J[0] - J[2])), J10((T)(J[1] - J[0])), dt((T)dt_),
-          rJ0((T)(1.0 / J[0])), rJ1((T)(1.0 / J[1])), rJ2((T)(1.0 / J[2])), rm((T)(1.0 / m_)) {}
-    __device__ __forceinline__ Consts(const P &p)
-        : m((T)p.m), g((T)p.g), kr((T)p.kr), kt((T)p.kt), J0((T)p.J[0]), J1((T)p.J[1]), J2((T)p.J[2]),
-          J21((T)(p.J[2] - p.J[1])), J02((T)(p.J[0] - p.J[2])), J10((T)(p.J[1] - p.J[0])), dt((T)p.dt),
-          rJ0((T)(1.0 / p.J[0])), rJ1((T)(1.0 / p.J[1])), rJ2((T)(1.0 / p.J[2])), rm((T)(1.0 / p.m)) {}
+    T m, g, kr, kt, J0, J1, J2, J21, J02, J10, dt, rJ0, rJ1, rJ2, rm, kt_m;
+    __device__ __forceinline__ Consts(double m_, double g_, const double *J, double kr_, double kt_, double dt_,
+                                      const UavDerived &d)
+        : m((T)m_), g((T)g_), kr((T)kr_), kt((T)kt_), J0((T)J[0]), J1((T)J[1]), J2((T)J[2]), J21((T)d.J21),
+          J02((T)d.J02), J10((T)d.J10), dt((T)dt_), rJ0((T)d.rJ[0]), rJ1((T)d.rJ[1]), rJ2((T)d.rJ[2]), rm((T)d.rm),
+          kt_m((T)d.kt_m) {}
 };
 
 // uav.py:93-124.  x = (x y z vx vy vz phi th psi p q r); only the derivative entries that the caller needs.
@@ -92,12 +103,25 @@ __device__ __forceinline__ void uav_rk44(const Consts<T> &c, T *x, Trig<T> t, T 
 }
 
 // FNTSMC sliding surface pieces shared by both loops (FNTSMC.py:61-66 / 128-134), one axis.
+#ifdef B200_SMC_NOINLINE
+#define SMC_INLINE __noinline__
+#else
+#define SMC_INLINE __forceinline__
+#endif
 template <typename T>
-__device__ __forceinline__ void smc_axis(T e, T de, T k1, T gamma, T alpha, T beta, T lmd, T dt, T &integ,
+__device__ SMC_INLINE void smc_axis(T e, T de, T k1, T gamma, T alpha, T beta, T lmd, T dt, T &integ,
                                          T &s_out, T &dot_s1, T &pa1_de) {
-    const T L = Mth<T>::log(Mth<T>::abs(e)); // shared by |e|^alpha and |e|^(alpha-1)
-    const T pa = pow_from_log<T>(L, alpha);
+    // |e|^(alpha-1) = exp((alpha-1) log|e|) and |e|^alpha = |e|^(alpha-1) * |e|: one log, one exp and one product for the
+    // two powers of FNTSMC.py:61-63 (numpy evaluates two pow()).  e = 0: 0^alpha = 0 (alpha > 0) while 0^(alpha-1) = inf.
+    const T ae = Mth<T>::abs(e);
+    const T L = Mth<T>::log(ae);
     const T pa1 = pow_from_log<T>(L, alpha - (T)1);
+#ifdef B200_SMC_TWO_EXP
+    const T pa = pow_from_log<T>(L, alpha);
+#else
+    const T pa_ = pa1 * ae;
+    const T pa = alpha == (T)0 ? (T)1 : ((ae == (T)0 && alpha > (T)0) ? (T)0 : pa_);
+#endif
     const T s = de + k1 * e + gamma * pa * Mth<T>::tanh((T)5 * e);
     dot_s1 = pow_from_log<T>(Mth<T>::log(Mth<T>::abs(s)), beta) * Mth<T>::tanh((T)5 * s);
     integ += dot_s1 * dt;

@@ -110,12 +110,12 @@ __device__ __forceinline__ void reset_state(const RP &r, const b200env_io &io, i
 
 template <typename T, int V, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK, 4)
-uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
-                      uint64_t seed, int64_t off) {
+uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavDerived dv,
+                      const __grid_constant__ b200env_io io, int64_t n, uint32_t flags, uint64_t seed, int64_t off) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     constexpr int S = V == 1 ? 12 : 6, AD = V == 1 ? 6 : 3;
-    const Consts<T> c(r.m, r.g, r.J, r.kr, r.kt, r.dt);
+    const Consts<T> c(r.m, r.g, r.J, r.kr, r.kt, r.dt, dv);
     T x[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) x[k] = ld<T>(io.state, n, k, i);
@@ -283,11 +283,12 @@ uavrobust_reset_kernel(const __grid_constant__ RP r, const __grid_constant__ b20
 template <typename T, bool IO32>
 int launch_step(int V, const RP &r, const b200env_io &io, int64_t n, uint32_t flags, uint64_t seed, int64_t off, cudaStream_t s) {
     const unsigned g = b200_grid(n);
+    const UavDerived dv = uav_derive(r.m, r.J, r.kt);
     switch (V) {
-    case 0: uavrobust_step_kernel<T, 0, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
-    case 1: uavrobust_step_kernel<T, 1, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
-    case 2: uavrobust_step_kernel<T, 2, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
-    case 3: uavrobust_step_kernel<T, 3, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, flags, seed, off); break;
+    case 0: uavrobust_step_kernel<T, 0, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, io, n, flags, seed, off); break;
+    case 1: uavrobust_step_kernel<T, 1, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, io, n, flags, seed, off); break;
+    case 2: uavrobust_step_kernel<T, 2, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, io, n, flags, seed, off); break;
+    case 3: uavrobust_step_kernel<T, 3, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, io, n, flags, seed, off); break;
     default: return B200ENV_EENV;
     }
     return b200_check_launch();
