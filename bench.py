@@ -288,6 +288,15 @@ def also_workloads(args, dev, dtype, peaks):
                     "hbm_frac": ALGO_BYTES[w] / 2.0 * n / per / 1e9 / hbm, "desc": WORKLOADS[w]["desc"] + " [fp32 mode]"})
         del env, pool
         torch.cuda.empty_cache()
+    # config #3: 2048-step rollouts of SOI and FAS into the device-resident buffer + GAE, 131072 instances per GPU
+    for w in ("soi", "fas"):
+        T, N = 2048, 131072
+        ms_roll, ms_gae = rollout_pipeline(w, N, T, dev, False)
+        out.append({"workload": f"rollout_{w}", "T": T, "envs": N, "value": T * N / ((ms_roll + ms_gae) * 1e-3),
+                    "unit": "env-steps/s", "ms_rollout": ms_roll, "ms_gae_and_norm": ms_gae,
+                    "desc": f"{WORKLOADS[w]['desc']}: {T}-step rollout written in place into a time-major float32 "
+                            "buffer by the step kernel (fp64 state/arithmetic), then GAE + advantage normalisation"})
+        torch.cuda.empty_cache()
     # config #3: GAE over a 2048-step rollout, 131072 env columns per GPU
     from reinforcementlearningplatform_b200 import gae as G
     T, N = 2048, 131072
@@ -312,6 +321,37 @@ def also_workloads(args, dev, dtype, peaks):
                 "hbm_frac": 28.0 * T * N / per / 1e9 / hbm,
                 "desc": "PPO2 GAE reverse scan + (sum, sum^2, n) statistics, float32, time-major [T, N]"})
     return out
+
+
+def rollout_pipeline(workload, n, T, dev, dist_on, seed=5):
+    """config #3: a T-step rollout written by the step kernel straight into a device-resident time-major float32
+    buffer (rollout.RolloutBuffer), then K-GAE over it and the global advantage normalisation (3-double all-reduce when
+    sharded).  V(s), V(s') are synthetic N(0,1) columns (the critic is outside the hot path).  Returns the times of the
+    two stages in ms."""
+    import reinforcementlearningplatform_b200 as rlp
+    env = make_env(workload, n, dev, 0, torch.float64, io_dtype=torch.float32)
+    env.reset(True)
+    buf = rlp.RolloutBuffer(T, env)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    ar = torch.as_tensor(np.asarray(env.action_range, dtype=np.float64), device=dev, dtype=torch.float32)
+    lo, hi = ar[:, 0].view(1, -1, 1), ar[:, 1].view(1, -1, 1)
+    buf.a.copy_(lo + (hi - lo) * torch.rand(buf.a.shape, generator=g, device=dev, dtype=torch.float32))
+    vs = torch.randn((T, n), generator=g, device=dev, dtype=torch.float32)
+    vsn = torch.randn((T, n), generator=g, device=dev, dtype=torch.float32)
+    for t in range(3):  # warm-up
+        buf.step(env, t, buf.a[t])
+    buf.gae(vs, vsn, 0.99, 0.95)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    for t in range(T):
+        buf.step(env, t, buf.a[t])
+    e[1].record()
+    adv, vt = buf.gae(vs, vsn, 0.99, 0.95)
+    e[2].record()
+    torch.cuda.synchronize()
+    return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
 
 
 def main():

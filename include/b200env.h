@@ -341,6 +341,14 @@ B200_API int b200_gae(int64_t T, int64_t N, const float *r, const float *vs, con
                       const float *success, double gamma, double lmd, int acc_mode, float *adv, float *v_target,
                       double *stats, void *cuda_stream);
 
+/* Same scan over a device-resident rollout as the step kernels write it (rollout.py): `done` is the u8 is_terminal
+ * column, `flag` the i32 terminal_flag column, and success = done && flag != timeout_flag -- the rule by which the
+ * train loops fill RolloutBuffer.success (demonstration/PPO2/PPO2-4-CartPoleAngleOnly/train.py:198-205,
+ * PPO2-4-UavFntsmcParamPos/train.py:299-302).  25 instead of 28 bytes of HBM traffic per element. */
+B200_API int b200_gae_flags(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next,
+                            const uint8_t *done, const int32_t *flag, int32_t timeout_flag, double gamma, double lmd,
+                            int acc_mode, float *adv, float *v_target, double *stats, void *cuda_stream);
+
 /* adv <- (adv - mean) / (std + eps) with the unbiased std (torch.Tensor.std) derived from stats = (sum, sum of
  * squares, count): Proximal_Policy_Optimization2.py:99-100 (eps = 1e-5). */
 B200_API int b200_adv_normalize(int64_t count, float *adv, const double *stats, double eps, void *cuda_stream);

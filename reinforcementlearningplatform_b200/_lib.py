@@ -141,6 +141,8 @@ def load() -> C.CDLL:
     f64 = C.c_double
     lib.b200_gae.restype = i32
     lib.b200_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, f64, f64, i32, vp, vp, vp, vp]
+    lib.b200_gae_flags.restype = i32
+    lib.b200_gae_flags.argtypes = [i64, i64, vp, vp, vp, vp, vp, i32, f64, f64, i32, vp, vp, vp, vp]
     lib.b200_adv_normalize.restype = i32
     lib.b200_adv_normalize.argtypes = [i64, vp, vp, f64, vp]
     lib.b200_fastmath_eval.restype = i32

@@ -27,10 +27,30 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-template <bool F64_ACC>
+// how the two masks of the scan are stored: FloatMasks = the reference's float32 `done` / `success` columns
+// (RolloutBuffer.to_tensor, utils/classes.py:292-301); FlagMasks = what the step kernels write into a device-resident
+// rollout (rollout.py): `done` as u8 and the terminal flag as i32, with success = done && flag != timeout_flag -- the
+// rule of the train loops (PPO2-4-CartPoleAngleOnly/train.py:198-205, PPO2-4-UavFntsmcParamPos/train.py:299-302).
+struct FloatMasks {
+    const float *done, *succ;
+    __device__ __forceinline__ void load(int64_t idx, float &d, float &s) const { d = __ldcs(done + idx); s = __ldcs(succ + idx); }
+};
+struct FlagMasks {
+    const uint8_t *done;
+    const int32_t *flag;
+    int32_t timeout_flag;
+    __device__ __forceinline__ void load(int64_t idx, float &d, float &s) const {
+        const bool dn = __ldcs(done + idx) != 0;
+        const int32_t f = __ldcs(flag + idx);
+        d = dn ? 1.0f : 0.0f;
+        s = (dn && f != timeout_flag) ? 1.0f : 0.0f;
+    }
+};
+
+template <bool F64_ACC, class Masks>
 __global__ void __launch_bounds__(GAE_BLOCK)
 gae_kernel(int64_t T, int64_t N, const float *__restrict__ r, const float *__restrict__ vs,
-           const float *__restrict__ vsn, const float *__restrict__ done, const float *__restrict__ succ, float g32,
+           const float *__restrict__ vsn, const Masks mk, float g32,
            float gl32, double gl64, float *__restrict__ adv, float *__restrict__ vt, double *stats) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
@@ -45,7 +65,7 @@ gae_kernel(int64_t T, int64_t N, const float *__restrict__ r, const float *__res
             for (int u = 0; u < GAE_UNROLL; ++u) {
                 const int64_t idx = (t - u) * N + n;
                 rr[u] = __ldcs(r + idx); v0[u] = __ldcs(vs + idx); v1[u] = __ldcs(vsn + idx);
-                dd[u] = __ldcs(done + idx); ss[u] = __ldcs(succ + idx);
+                mk.load(idx, dd[u], ss[u]);
             }
 #pragma unroll
             for (int u = 0; u < GAE_UNROLL; ++u) {
@@ -70,13 +90,15 @@ gae_kernel(int64_t T, int64_t N, const float *__restrict__ r, const float *__res
         for (; t >= 0; --t) {
             const int64_t idx = t * N + n;
             const float v0 = vs[idx];
-            const float delta = __fsub_rn(__fadd_rn(r[idx], __fmul_rn(__fmul_rn(g32, __fsub_rn(1.0f, succ[idx])), vsn[idx])), v0);
+            float dn, sc;
+            mk.load(idx, dn, sc);
+            const float delta = __fsub_rn(__fadd_rn(r[idx], __fmul_rn(__fmul_rn(g32, __fsub_rn(1.0f, sc)), vsn[idx])), v0);
             float a;
             if (F64_ACC) {
-                gae64 = (double)delta + gl64 * gae64 * (1.0 - (double)done[idx]);
+                gae64 = (double)delta + gl64 * gae64 * (1.0 - (double)dn);
                 a = (float)gae64;
             } else {
-                gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl32, gae), __fsub_rn(1.0f, done[idx])));
+                gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl32, gae), __fsub_rn(1.0f, dn)));
                 a = gae;
             }
             adv[idx] = a;
@@ -124,10 +146,28 @@ extern "C" B200_API int b200_gae(int64_t T, int64_t N, const float *r, const flo
     cudaStream_t s = (cudaStream_t)cuda_stream;
     const unsigned grid = (unsigned)((N + GAE_BLOCK - 1) / GAE_BLOCK);
     const float g32 = (float)gamma, gl32 = (float)(gamma * lmd);
+    const FloatMasks mk{done, success};
     if (acc_mode == 0)
-        gae_kernel<false><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, done, success, g32, gl32, gamma * lmd, adv, v_target, stats);
+        gae_kernel<false, FloatMasks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats);
     else
-        gae_kernel<true><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, done, success, g32, gl32, gamma * lmd, adv, v_target, stats);
+        gae_kernel<true, FloatMasks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats);
+    return b200_check_launch();
+}
+
+extern "C" B200_API int b200_gae_flags(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next,
+                                       const uint8_t *done, const int32_t *flag, int32_t timeout_flag, double gamma,
+                                       double lmd, int acc_mode, float *adv, float *v_target, double *stats,
+                                       void *cuda_stream) {
+    if (T <= 0 || N <= 0) return B200ENV_ESIZE;
+    if (!r || !vs || !vs_next || !done || !flag || !adv || !v_target) return B200ENV_ENULL;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const unsigned grid = (unsigned)((N + GAE_BLOCK - 1) / GAE_BLOCK);
+    const float g32 = (float)gamma, gl32 = (float)(gamma * lmd);
+    const FlagMasks mk{done, flag, timeout_flag};
+    if (acc_mode == 0)
+        gae_kernel<false, FlagMasks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats);
+    else
+        gae_kernel<true, FlagMasks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats);
     return b200_check_launch();
 }
 

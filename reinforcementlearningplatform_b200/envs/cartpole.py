@@ -22,6 +22,7 @@ def deg2rad(deg):  # utils/functions.py:4-5 (same expression, same rounding)
 class CartPole(VecEnvBase):
     """CartPole.py:11-295.  obs = (theta, dtheta, x, dx) / max * 2; flags 1 angle, 2 position, 3 time, 4 success."""
     ENV_ID = _lib.CARTPOLE
+    TIMEOUT_FLAG = 3  # success = done and flag != 3 (PPO2-4-CartPoleAngleOnly/train.py:198-205)
     OBS_IS_PURE = True
     VARIANT = 0
     STATE_FIELDS = ("theta", "dtheta", "x", "dx")

@@ -27,6 +27,7 @@ class Flight_Attitude_Simulator(_Simple):
     """environment/FlightAttitudeSimulator/FlightAttitudeSimulator.py:9-287.  ``variant='ppo2'`` selects the
     PPO2/DPPO2 demo copy (timeMax = 10, reward Q = 1, R = 0.05; flight_attitude_simulator.py:42,211-224)."""
     ENV_ID = _lib.FAS
+    TIMEOUT_FLAG = 3  # terminal_flag of a time-out: success = done and flag != 3 (PPO2-4-FlightAttitudeSimulator/train.py:190)
     OBS_IS_PURE = True
     STATE_FIELDS = ("theta", "dTheta")
 
@@ -63,6 +64,7 @@ class SecondOrderIntegration(_Simple):
     """environment/SecondOrderIntegration/SecondOrderIntegration.py:13-352.  ``variant='dppo2'``: the DPPO2 demo copy
     (obs * static_gain :213, success terminal disabled :243-246, Q_vel = Q_acc = 0 :260-261)."""
     ENV_ID = _lib.SOI
+    TIMEOUT_FLAG = 2  # terminal_flag of a time-out: success = done and flag != 2 (PPO2-4-SecondOrderIntegration/train.py:205)
     OBS_IS_PURE = True
     STATE_FIELDS = ("x", "y", "vx", "vy")
 
@@ -95,6 +97,7 @@ class SecondOrderIntegration(_Simple):
 class BallBalancer1D(_Simple):
     """environment/BallBalancer/BallBalancer1D.py:14-322."""
     ENV_ID = _lib.BALLBALANCER
+    TIMEOUT_FLAG = 2  # terminal_flag of a time-out: success = done and flag != 2 (PPO2-4-BallBalancer1D/train.py:201)
     OBS_IS_PURE = True
     STATE_FIELDS = ("pos", "vel", "theta", "error")
 
@@ -127,6 +130,7 @@ class BallBalancer1D(_Simple):
 class TwoLinkManipulator(_Simple):
     """environment/RobotManipulator/TwoLinkManipulator.py:8-312."""
     ENV_ID = _lib.TWOLINK
+    TIMEOUT_FLAG = 2  # terminal_flag of a time-out: success = done and flag != 2 (PPO2-4-TwoLinkManipulator/train.py:191)
     STATE_FIELDS = ("theta1", "theta2", "omega1", "omega2", "err_x", "err_y", "target_x", "target_y")
 
     def __init__(self, n_envs: int = 1, **kw):
@@ -156,6 +160,7 @@ class TwoLinkManipulator(_Simple):
 class UGVForward(_Simple):
     """environment/UGV/UGVForward.py:10-362."""
     ENV_ID = _lib.UGV
+    TIMEOUT_FLAG = 2  # terminal_flag of a time-out: success = done and flag != 2 (PPO2-4-UGVForward/train.py:201)
     OBS_IS_PURE = True
     STATE_FIELDS = ("x", "y", "vel", "phi", "omega")
     BIDIRECTIONAL = 0
@@ -197,6 +202,7 @@ class UGVForwardObstacleAvoidance(_Simple):
     progress reward, success ignores omega, pose frozen when the previous velocity was negative).  Observation =
     4 kinematic terms + 37 fake-laser ranges (kernel K-UGVO: one warp per instance, lanes = rays)."""
     ENV_ID = _lib.UGVO
+    TIMEOUT_FLAG = 2  # terminal_flag of a time-out: success = done and flag != 2 (PPO2-4-UGVForwardObstacleAvoidance/train.py:201)
     OBS_IS_PURE = True
     USES_WORK_LIST = True
     MAX_OBS = 16

@@ -156,6 +156,7 @@ class UavAttCtrlRL(_UavBase):
     """``uav_att_ctrl_RL`` (uav_att_ctrl_RL.py:10-178): attitude tracking, obs = (att - ref, Euler rate - ref rate),
     action = 8 gains in [0, 3] (k1 x10, k2 /10 as in get_param_from_actor :141-156)."""
     ENV_ID = _lib.UAV_ATT
+    TIMEOUT_FLAG = 1  # success = done and flag != 1 (PPO2-4-UavFntsmcParamPos/train.py:299-302, ...Att/train.py:278)
     STATE_FIELDS = tuple("phi theta psi p q r s1_0 s1_1 s1_2 k1_0 k1_1 k1_2 k2_0 k2_1 k2_2 gamma_0 gamma_1 gamma_2 "
                          "lmd_0 lmd_1 lmd_2 A_0 A_1 A_2 T_0 T_1 T_2 phase_0 phase_1 phase_2 "
                          "ref_0 ref_1 ref_2 dref_0 dref_1 dref_2".split())
@@ -200,6 +201,7 @@ class UavPosCtrlRL(_UavBase):
     """``uav_pos_ctrl_RL`` (uav_pos_ctrl_RL.py:12-207): position tracking with the FNTSMC outer + inner loops,
     obs = (pos - ref, vel - ref vel), action = 8 outer-loop gains in [0, 5]; optional injected disturbance [3]."""
     ENV_ID = _lib.UAV_POS
+    TIMEOUT_FLAG = 1  # success = done and flag != 1 (PPO2-4-UavFntsmcParamPos/train.py:299-302, ...Att/train.py:278)
     STATE_FIELDS = tuple("x y z vx vy vz phi theta psi p q r sig_0 sig_1 sig_2 s1_0 s1_1 s1_2 aref_0 aref_1 aref_2 "
                          "k1_0 k1_1 k1_2 k2_0 k2_1 k2_2 gamma_0 gamma_1 gamma_2 lmd_0 lmd_1 lmd_2 "
                          "A_0 A_1 A_2 A_3 T_0 T_1 T_2 T_3 phase_0 phase_1 phase_2 phase_3 "

@@ -36,6 +36,7 @@ def robust_att_ctrl_param() -> fntsmc_param:
 
 class _UavRobustBase(VecEnvBase):
     ENV_ID = _lib.UAVROBUST
+    TIMEOUT_FLAG = 1  # uav.py:543-560: flag 1 = time out
     STATE_FIELDS = tuple("x y z vx vy vz phi theta psi p q r s1_0 s1_1 s1_2 aref_0 aref_1 aref_2 daref_0 daref_1 daref_2 "
                          "pref_0 pref_1 pref_2 A_0 A_1 A_2 T_0 T_1 T_2 phase_0 phase_1 phase_2".split())
     Q = (1, 0.1, 0.02)

@@ -38,6 +38,30 @@ def gae(r, vs, vs_next, done, success, gamma: float, lmd: float, acc_mode: int =
     return adv, vt, stats
 
 
+def gae_flags(r, vs, vs_next, done_u8, flag_i32, timeout_flag: int, gamma: float, lmd: float, acc_mode: int = 0,
+              stats: torch.Tensor = None):
+    """:func:`gae` over a device-resident rollout (``rollout.RolloutBuffer``): ``done_u8`` / ``flag_i32`` are the
+    ``is_terminal`` / ``terminal_flag`` columns the step kernel wrote, success = done and flag != timeout_flag."""
+    lib = _lib.load()
+    for t in (r, vs, vs_next):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == r.shape and t.dim() == 2):
+            raise ValueError("gae_flags: r, vs, vs_next must be contiguous CUDA float32 tensors of one [T, N] shape")
+    if not (done_u8.dtype == torch.uint8 and flag_i32.dtype == torch.int32 and done_u8.shape == r.shape
+            and flag_i32.shape == r.shape and done_u8.is_contiguous() and flag_i32.is_contiguous()):
+        raise ValueError("gae_flags: done must be uint8 and flag int32, contiguous [T, N]")
+    T, N = r.shape
+    adv = torch.empty_like(r)
+    vt = torch.empty_like(r)
+    if stats is None:
+        stats = torch.zeros(3, dtype=torch.float64, device=r.device)
+    with torch.cuda.device(r.device):
+        stream = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
+        _lib.check(lib.b200_gae_flags(T, N, _p(r), _p(vs), _p(vs_next), _p(done_u8), _p(flag_i32), int(timeout_flag),
+                                      float(gamma), float(lmd), int(acc_mode), _p(adv), _p(vt), _p(stats), stream),
+                   "b200_gae_flags")
+    return adv, vt, stats
+
+
 def normalize_advantage(adv: torch.Tensor, stats: torch.Tensor, eps: float = 1e-5, group=None) -> torch.Tensor:
     """In place ``adv <- (adv - mean) / (std + eps)`` (PPO2.py:99-100); ``stats`` from :func:`gae`.  If a process group
     is initialised the 3 statistics are summed over ranks first (global normalisation)."""

@@ -33,6 +33,7 @@ class VecEnvBase:
     # of UGVForwardObstacleAvoidance this removes one of the two 37-ray scans per step).  Not true for the
     # UAV envs (the reset observation is taken against the stale reference) nor the two-link arm (pre-wrap error).
     OBS_IS_PURE: bool = False
+    TIMEOUT_FLAG: int = 0  # terminal_flag value of a time-out (train loops: success = done and flag != TIMEOUT_FLAG)
     USES_WORK_LIST: bool = False  # the step kernel wants b200env_io.work (list of terminated instances)
 
     def __init__(self, n_envs: int = 1, device="cuda", dtype=torch.float64, seed: int = 0,
@@ -206,6 +207,34 @@ class VecEnvBase:
             if reuse:  # current_state(t+1) == policy_state(t): swap the buffers instead of recomputing get_state()
                 self._obs, self._reset_obs = self._reset_obs, self._obs
             io = self._io(action_soa, dis_soa, obs=not reuse)
+            self._policy_obs_valid = True
+            flags = _lib.AUTO_RESET if self.auto_reset else 0
+            _lib.check(self._lib.b200env_step(self.ENV_ID, self._dt_code, self.n_envs, C.byref(self._params),
+                                              C.sizeof(self._params), C.byref(io), flags, self.seed,
+                                              self.env_index_offset, self._stream()), "b200env_step")
+
+    def step_into(self, action_soa: torch.Tensor, dis_soa: Optional[torch.Tensor] = None, *, obs: torch.Tensor,
+                  next_obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, flag: torch.Tensor) -> None:
+        """``step_soa`` with the outputs of this step stored into caller-owned tensors (one row of a device-resident
+        ``rollout.RolloutBuffer``) instead of the env's own ``current_state / next_state / reward / is_terminal /
+        terminal_flag`` buffers, which are left untouched.  ``policy_state`` is updated as usual.  Shapes:
+        ``obs, next_obs [state_dim, N]``, ``reward [N]`` in ``io_dtype``; ``done [N]`` uint8; ``flag [N]`` int32."""
+        io_dt = self.io_dtype
+        for t, shape, dt in ((obs, (self._od, self.n_envs), io_dt), (next_obs, (self._od, self.n_envs), io_dt),
+                             (reward, (self.n_envs,), io_dt), (done, (self.n_envs,), torch.uint8),
+                             (flag, (self.n_envs,), torch.int32)):
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self._state.device:
+                raise _lib.B200EnvError(f"step_into: expected contiguous {dt} tensor of shape {shape} on {self.device}")
+        if action_soa.dtype != io_dt or (dis_soa is not None and dis_soa.dtype != io_dt):
+            raise _lib.B200EnvError(f"step_into: action/dis must be {io_dt}")
+        with torch.cuda.device(self.device):
+            reuse = self.reuse_obs and self._policy_obs_valid
+            if reuse:  # current_state(t) == policy_state(t-1): a row copy instead of a second get_state()
+                obs.copy_(self._reset_obs)
+            io = self._io(action_soa, dis_soa, obs=not reuse)
+            if not reuse:
+                io.obs = obs.data_ptr()
+            io.next_obs, io.reward, io.done, io.flag = next_obs.data_ptr(), reward.data_ptr(), done.data_ptr(), flag.data_ptr()
             self._policy_obs_valid = True
             flags = _lib.AUTO_RESET if self.auto_reset else 0
             _lib.check(self._lib.b200env_step(self.ENV_ID, self._dt_code, self.n_envs, C.byref(self._params),
