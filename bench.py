@@ -339,14 +339,12 @@ def rollout_pipeline(workload, n, T, dev, dist_on, seed=5):
     buf.a.copy_(lo + (hi - lo) * torch.rand(buf.a.shape, generator=g, device=dev, dtype=torch.float32))
     vs = torch.randn((T, n), generator=g, device=dev, dtype=torch.float32)
     vsn = torch.randn((T, n), generator=g, device=dev, dtype=torch.float32)
-    for t in range(3):  # warm-up
-        buf.step(env, t, buf.a[t])
+    buf.collect(env, 0, 8)  # warm-up
     buf.gae(vs, vsn, 0.99, 0.95)
     torch.cuda.synchronize()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     e[0].record()
-    for t in range(T):
-        buf.step(env, t, buf.a[t])
+    buf.collect(env)  # b200env_rollout: all T steps in one call (one fused kernel for SOI / FAS)
     e[1].record()
     adv, vt = buf.gae(vs, vsn, 0.99, 0.95)
     e[2].record()

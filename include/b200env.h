@@ -103,6 +103,14 @@ typedef struct b200env_io {
     int32_t        pad_;
 } b200env_io;
 
+/* Row strides of a time-major rollout (b200env_rollout): row t of an array starts `stride` ELEMENTS (of that array's
+ * element type) after row t-1.  For the device-resident buffer of rollout.py: action_stride = action_dim * n,
+ * obs_stride = next_obs_stride = obs_dim * n, reward_stride = done_stride = flag_stride = n. */
+typedef struct b200env_rollout_spec {
+    int64_t steps;
+    int64_t action_stride, dis_stride, obs_stride, next_obs_stride, reward_stride, done_stride, flag_stride;
+} b200env_rollout_spec;
+
 /* ------------------------------------------------------ per-env parameters */
 /* All parameter structs are plain doubles/ints.  The host mirror fills them
  * from the attribute names of the reference classes; thresholds that the
@@ -340,6 +348,17 @@ B200_API int b200env_observe(int env_id, int dtype, int64_t n_envs,
 B200_API int b200_gae(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next, const float *done,
                       const float *success, double gamma, double lmd, int acc_mode, float *adv, float *v_target,
                       double *stats, void *cuda_stream);
+
+/* `spec->steps` control periods with pre-computed actions in one call: the collection loop of the train scripts
+ * (`while buffer_index < batch_size: step_update; buffer.append`, PPO2-4-CartPoleAngleOnly/train.py:186-216) when the
+ * actions do not depend on the observations (random-action benchmarks, open-loop replays) or are produced on the
+ * device ahead of time.  io->action / dis / obs / next_obs / reward / done / flag point at row 0 of time-major arrays
+ * whose rows are `spec` strides apart; reset_obs receives the observation after the last step.  Families built on the
+ * generic one-thread-per-instance kernel (FAS, SOI, BallBalancer, TwoLink, UGV) run all steps in ONE launch with the
+ * instance state held in registers; the others launch their step kernel once per time step. */
+B200_API int b200env_rollout(int env_id, int dtype, int64_t n_envs, const void *params, size_t params_bytes,
+                             const b200env_io *io, const b200env_rollout_spec *spec, uint32_t flags, uint64_t seed,
+                             int64_t env_index_offset, void *cuda_stream);
 
 /* Same scan over a device-resident rollout as the step kernels write it (rollout.py): `done` is the u8 is_terminal
  * column, `flag` the i32 terminal_flag column, and success = done && flag != timeout_flag -- the rule by which the

@@ -39,6 +39,13 @@ class IO(C.Structure):
         ("io_dtype", C.c_int32), ("pad_", C.c_int32)]
 
 
+class RolloutSpec(C.Structure):
+    """struct b200env_rollout_spec"""
+    _fields_ = [(k, C.c_int64) for k in (
+        "steps", "action_stride", "dis_stride", "obs_stride", "next_obs_stride", "reward_stride", "done_stride",
+        "flag_stride")]
+
+
 class CartPoleParams(C.Structure):
     """struct b200_cartpole_params"""
     _fields_ = [(k, C.c_double) for k in (
@@ -134,6 +141,8 @@ def load() -> C.CDLL:
     lib.b200env_dims.argtypes = [i32, i32, ip, ip, ip, ip]
     lib.b200env_step.restype = i32
     lib.b200env_step.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), u32, u64, i64, vp]
+    lib.b200env_rollout.restype = i32
+    lib.b200env_rollout.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), C.POINTER(RolloutSpec), u32, u64, i64, vp]
     lib.b200env_reset.restype = i32
     lib.b200env_reset.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), vp, u64, i64, vp]
     lib.b200env_observe.restype = i32

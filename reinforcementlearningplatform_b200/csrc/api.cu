@@ -11,9 +11,13 @@ struct Family {
     int (*step)(int, int64_t, const void *, const b200env_io *, uint32_t, uint64_t, int64_t, cudaStream_t);
     int (*reset)(int, int64_t, const void *, const b200env_io *, const uint8_t *, uint64_t, int64_t, cudaStream_t);
     int (*observe)(int, int64_t, const void *, const b200env_io *, cudaStream_t);
+    // fused multi-step kernel, or NULL: b200env_rollout then launches `step` once per time step
+    int (*rollout)(int, int64_t, const void *, const b200env_io *, const b200env_rollout_spec *, uint32_t, uint64_t,
+                   int64_t, cudaStream_t);
 };
 
-#define FAM(name, P) Family{sizeof(P), name##_dims, name##_step, name##_reset, name##_observe}
+#define FAM(name, P) Family{sizeof(P), name##_dims, name##_step, name##_reset, name##_observe, nullptr}
+#define FAMR(name, P) Family{sizeof(P), name##_dims, name##_step, name##_reset, name##_observe, name##_rollout}
 const Family *family(int env_id) {
     static Family table[B200ENV_COUNT] = {};
     static bool init = false;
@@ -21,11 +25,11 @@ const Family *family(int env_id) {
         table[B200ENV_CARTPOLE] = FAM(cartpole, b200_cartpole_params);
         table[B200ENV_UAV_ATT] = FAM(uav_att, b200_uav_params);
         table[B200ENV_UAV_POS] = FAM(uav_pos, b200_uav_params);
-        table[B200ENV_FAS] = FAM(fas, b200_fas_params);
-        table[B200ENV_SOI] = FAM(soi, b200_soi_params);
-        table[B200ENV_BALLBALANCER] = FAM(ballbalancer, b200_ballbalancer_params);
-        table[B200ENV_TWOLINK] = FAM(twolink, b200_twolink_params);
-        table[B200ENV_UGV] = FAM(ugv, b200_ugv_params);
+        table[B200ENV_FAS] = FAMR(fas, b200_fas_params);
+        table[B200ENV_SOI] = FAMR(soi, b200_soi_params);
+        table[B200ENV_BALLBALANCER] = FAMR(ballbalancer, b200_ballbalancer_params);
+        table[B200ENV_TWOLINK] = FAMR(twolink, b200_twolink_params);
+        table[B200ENV_UGV] = FAMR(ugv, b200_ugv_params);
         table[B200ENV_UGVO] = FAM(ugvo, b200_ugvo_params);
         table[B200ENV_UAVROBUST] = FAM(uavrobust, b200_uavrobust_params);
         init = true;
@@ -68,6 +72,36 @@ int b200env_step(int env_id, int dtype, int64_t n_envs, const void *params, size
     int rc = check_common(f, dtype, n_envs, params, params_bytes, io);
     if (rc) return rc;
     return f->step(dtype, n_envs, params, io, flags, seed, env_index_offset, (cudaStream_t)cuda_stream);
+}
+
+int b200env_rollout(int env_id, int dtype, int64_t n_envs, const void *params, size_t params_bytes,
+                    const b200env_io *io, const b200env_rollout_spec *spec, uint32_t flags, uint64_t seed,
+                    int64_t env_index_offset, void *cuda_stream) {
+    const Family *f = family(env_id);
+    int rc = check_common(f, dtype, n_envs, params, params_bytes, io);
+    if (rc) return rc;
+    if (!spec) return B200ENV_ENULL;
+    if (spec->steps <= 0) return B200ENV_ESIZE;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    if (f->rollout) return f->rollout(dtype, n_envs, params, io, spec, flags, seed, env_index_offset, s);
+    // no fused kernel for this family: one step launch per time step, rows addressed by the strides
+    const size_t eio = (dtype == B200ENV_F32 || io->io_dtype == B200ENV_F32) ? 4 : 8;
+    for (int64_t t = 0; t < spec->steps; ++t) {
+        b200env_io it = *io;
+        auto adv = [&](const void *ptr, int64_t stride, size_t es) -> void * {
+            return ptr ? (void *)((const char *)ptr + (size_t)t * (size_t)stride * es) : nullptr;
+        };
+        it.action = adv(io->action, spec->action_stride, eio);
+        it.dis = adv(io->dis, spec->dis_stride, eio);
+        it.obs = adv(io->obs, spec->obs_stride, eio);
+        it.next_obs = adv(io->next_obs, spec->next_obs_stride, eio);
+        it.reward = adv(io->reward, spec->reward_stride, eio);
+        it.done = (uint8_t *)adv(io->done, spec->done_stride, 1);
+        it.flag = (int32_t *)adv(io->flag, spec->flag_stride, 4);
+        rc = f->step(dtype, n_envs, params, &it, flags, seed, env_index_offset, s);
+        if (rc) return rc;
+    }
+    return B200ENV_OK;
 }
 
 int b200env_reset(int env_id, int dtype, int64_t n_envs, const void *params, size_t params_bytes,

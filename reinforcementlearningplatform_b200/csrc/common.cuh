@@ -230,3 +230,12 @@ B200_FAMILY_DECL(twolink)
 B200_FAMILY_DECL(ugv)
 B200_FAMILY_DECL(ugvo)
 B200_FAMILY_DECL(uavrobust)
+// families built on env_kernel.cuh also have a fused multi-step kernel (state in registers across the steps)
+#define B200_FAMILY_ROLLOUT_DECL(name)                                                                          \
+    int name##_rollout(int dtype, int64_t n, const void *params, const b200env_io *io,                          \
+                       const b200env_rollout_spec *rs, uint32_t flags, uint64_t seed, int64_t off, cudaStream_t s);
+B200_FAMILY_ROLLOUT_DECL(fas)
+B200_FAMILY_ROLLOUT_DECL(soi)
+B200_FAMILY_ROLLOUT_DECL(ballbalancer)
+B200_FAMILY_ROLLOUT_DECL(twolink)
+B200_FAMILY_ROLLOUT_DECL(ugv)

@@ -9,6 +9,7 @@
 // and the kernels below add the common data movement: all loads first, outputs, optional auto-reset.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 template <typename T, class E, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK)
@@ -74,6 +75,59 @@ env_reset_kernel(const __grid_constant__ typename E::P p, const __grid_constant_
     }
 }
 
+// T_steps control periods in ONE launch (b200env_rollout): the instance state stays in registers between steps, so per
+// step only the action row is read and the transition row (s, s', r, done, flag) is written -- no state round trip
+// through HBM and no per-step launch.  Row t of an array lives `stride` elements after row t-1 (time-major rollout
+// buffer, rollout.py).  Same arithmetic as env_step_kernel step by step, including the in-kernel auto-reset.
+template <typename T, class E, bool IO32>
+__global__ void __launch_bounds__(B200_BLOCK)
+env_rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ b200env_io io,
+                   const __grid_constant__ b200env_rollout_spec rs, int64_t n, uint32_t flags, uint64_t seed, int64_t off) {
+    typedef typename std::conditional<IO32, float, T>::type TIO;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    E e;
+    e.load(io, n, i);
+    T nxt[E::OD];
+    for (int64_t t = 0; t < rs.steps; ++t) {
+        const TIO *act_row = static_cast<const TIO *>(io.action) + t * rs.action_stride;
+        T act[E::AD];
+#pragma unroll
+        for (int k = 0; k < E::AD; ++k) act[k] = ldio<T, IO32>(act_row, n, k, i);
+        T cur[E::OD];
+        e.observe(p, cur);
+        if (io.obs) {
+            TIO *row = static_cast<TIO *>(io.obs) + t * rs.obs_stride;
+#pragma unroll
+            for (int k = 0; k < E::OD; ++k) stio<T, IO32>(row, n, k, i, cur[k]);
+        }
+        int flag = 0;
+        bool done = false;
+        T reward = (T)0;
+        e.step(p, act, cur, flag, done, reward, nxt);
+        {
+            TIO *row = static_cast<TIO *>(io.next_obs) + t * rs.next_obs_stride;
+#pragma unroll
+            for (int k = 0; k < E::OD; ++k) stio<T, IO32>(row, n, k, i, nxt[k]);
+        }
+        stio<T, IO32>(static_cast<TIO *>(io.reward) + t * rs.reward_stride, n, 0, i, reward);
+        io.done[t * rs.done_stride + i] = done ? 1 : 0;
+        io.flag[t * rs.flag_stride + i] = flag;
+        if (done && (flags & B200ENV_AUTO_RESET)) {
+            const uint32_t ep = io.episode[i];
+            Philox rng(seed, (uint64_t)(off + i), ep);
+            e.reset(p, rng);
+            io.episode[i] = ep + 1u;
+            e.observe(p, nxt);
+        }
+    }
+    if (io.reset_obs) {
+#pragma unroll
+        for (int k = 0; k < E::OD; ++k) stio<T, IO32>(io.reset_obs, n, k, i, nxt[k]);
+    }
+    e.store(io, n, i);
+}
+
 // host-side launchers: EnvT is the family template, instantiated for double and float
 template <template <typename> class EnvT>
 int env_launch_step(int dtype, int64_t n, const void *params, const b200env_io *io, uint32_t flags, uint64_t seed,
@@ -89,6 +143,23 @@ int env_launch_step(int dtype, int64_t n, const void *params, const b200env_io *
         env_step_kernel<double, EnvT<double>, false><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
     else
         env_step_kernel<float, EnvT<float>, false><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, n, flags, seed, off);
+    return b200_check_launch();
+}
+
+template <template <typename> class EnvT>
+int env_launch_rollout(int dtype, int64_t n, const void *params, const b200env_io *io, const b200env_rollout_spec *rs,
+                       uint32_t flags, uint64_t seed, int64_t off, cudaStream_t s) {
+    typedef typename EnvT<double>::P P;
+    if (!io->state || !io->time || !io->action || !io->next_obs || !io->reward || !io->done || !io->flag)
+        return B200ENV_ENULL;
+    if ((flags & B200ENV_AUTO_RESET) && !io->episode) return B200ENV_ENULL;
+    const P &p = *static_cast<const P *>(params);
+    if (dtype == B200ENV_F64 && b200_io32(io))
+        env_rollout_kernel<double, EnvT<double>, true><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, *rs, n, flags, seed, off);
+    else if (dtype == B200ENV_F64)
+        env_rollout_kernel<double, EnvT<double>, false><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, *rs, n, flags, seed, off);
+    else
+        env_rollout_kernel<float, EnvT<float>, false><<<b200_grid(n), B200_BLOCK, 0, s>>>(p, *io, *rs, n, flags, seed, off);
     return b200_check_launch();
 }
 
@@ -121,6 +192,10 @@ int env_launch_reset(int dtype, int64_t n, const void *params, const b200env_io 
     int name##_step(int dtype, int64_t n, const void *params, const b200env_io *io, uint32_t flags, uint64_t seed,    \
                     int64_t off, cudaStream_t s) {                                                                    \
         return env_launch_step<EnvT>(dtype, n, params, io, flags, seed, off, s);                                      \
+    }                                                                                                                 \
+    int name##_rollout(int dtype, int64_t n, const void *params, const b200env_io *io,                                \
+                       const b200env_rollout_spec *rs, uint32_t flags, uint64_t seed, int64_t off, cudaStream_t s) {  \
+        return env_launch_rollout<EnvT>(dtype, n, params, io, rs, flags, seed, off, s);                               \
     }                                                                                                                 \
     int name##_reset(int dtype, int64_t n, const void *params, const b200env_io *io, const uint8_t *mask,             \
                      uint64_t seed, int64_t off, cudaStream_t s) {                                                    \

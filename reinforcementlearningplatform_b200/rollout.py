@@ -60,6 +60,15 @@ class RolloutBuffer:
                       flag=self.flag[t])
         self.index = t + 1
 
+    def collect(self, env, t0: int = 0, steps: Optional[int] = None, dis: Optional[torch.Tensor] = None) -> None:
+        """Rows ``t0 .. t0 + steps - 1`` in one call from the actions already stored in ``self.a`` (random-action
+        benchmarks, open-loop replays, actions produced on the device ahead of time): ``b200env_rollout``."""
+        steps = self.batch_size - t0 if steps is None else int(steps)
+        sl = slice(t0, t0 + steps)
+        env.rollout_into(steps, self.a[sl], obs=self.s[sl], next_obs=self.s_[sl], reward=self.r[sl],
+                         done=self.done[sl], flag=self.flag[sl], dis=dis)
+        self.index = t0 + steps
+
     # ------------------------------------------------------------------ reading
     def success(self) -> torch.Tensor:
         """float32 ``[T, N]`` success column as the reference's learner sees it (utils/classes.py:299)."""

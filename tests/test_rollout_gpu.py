@@ -58,3 +58,32 @@ def test_rollout_rows_equal_oracle_transitions(name, oracle_lib):
     s, a, a_lp, r, s_, done, success = buf.to_tensor()
     assert s.shape == (T * n, env.state_dim) and a.shape == (T * n, env.action_dim) and r.shape == (T * n, 1)
     assert torch.equal(s[n + 3], buf.s[1, :, 3])
+
+
+@pytest.mark.parametrize("name", ["soi", "fas_ppo2", "ugv_forward", "ballbalancer", "twolink", "cartpole", "uav_att_rand"])
+def test_rollout_collect_equals_step_by_step(name):
+    """b200env_rollout (fused multi-step kernel for the generic families, per-step launches for the others) fills the
+    buffer with exactly the bits that T separate step calls produce, and leaves the env in the same state."""
+    import torch
+    from reinforcementlearningplatform_b200 import RolloutBuffer
+    cls, kw = env_specs()[name]
+    n, T, seed = 3000, 40, 4
+    mk = lambda: cls(n_envs=n, device="cuda", dtype=torch.float64, io_dtype=torch.float32, seed=seed, auto_reset=True, **kw)
+    e1, e2 = mk(), mk()
+    e1.reset(True)
+    e2.reset(True)
+    b1, b2 = RolloutBuffer(T, e1), RolloutBuffer(T, e2)
+    ar = torch.as_tensor(np.asarray(e1.action_range, dtype=np.float64), device="cuda", dtype=torch.float32)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = ar[:, :1].view(1, -1, 1) + (ar[:, 1:] - ar[:, :1]).view(1, -1, 1) * torch.rand(b1.a.shape, generator=g, device="cuda")
+    b1.a.copy_(a)
+    b2.a.copy_(a)
+    for t in range(T):
+        b1.step(e1, t, b1.a[t])
+    b2.collect(e2)
+    torch.cuda.synchronize()
+    for f in ("s", "s_", "r", "done", "flag"):
+        assert torch.equal(getattr(b1, f), getattr(b2, f)), (name, f)
+    assert torch.equal(e1._state, e2._state) and torch.equal(e1._time, e2._time) and torch.equal(e1._episode, e2._episode)
+    assert torch.equal(e1.policy_state, e2.policy_state)
+    assert int(b1.done.sum()) > 0 or name in ("uav_att_rand", "twolink", "ballbalancer", "ugv_forward", "soi")
