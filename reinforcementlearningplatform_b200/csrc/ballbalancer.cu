@@ -42,9 +42,9 @@ struct BallBalancer {
             // K3[1] = h K sin(theta + K2[2] / 2) with K2[2] = K1[2] = h omega: the same sine as stage 2, bit for bit
             const T k3p = hT * (vel + k2v * half), k3v = k2v;
             const T k4p = hT * (vel + k3v), k4v = hT * (K * Mth<T>::sin(theta + kth));
-            pos = pos + (k1p + (T)2 * k2p + (T)2 * k3p + k4p) / (T)6;
-            const T nv = vel + (k1v + (T)2 * k2v + (T)2 * k3v + k4v) / (T)6;
-            const T nt = theta + (kth + (T)2 * kth + (T)2 * kth + kth) / (T)6;
+            pos = pos + div6<T>(k1p + (T)2 * k2p + (T)2 * k3p + k4p);
+            const T nv = vel + div6<T>(k1v + (T)2 * k2v + (T)2 * k3v + k4v);
+            const T nt = theta + div6<T>(kth + (T)2 * kth + (T)2 * kth + kth);
             vel = Mth<T>::min(Mth<T>::max(nv, (T)p.v_min), (T)p.v_max);
             theta = Mth<T>::min(Mth<T>::max(nt, (T)p.theta_min), (T)p.theta_max);
             time += h;

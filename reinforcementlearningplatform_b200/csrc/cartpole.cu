@@ -53,23 +53,25 @@ struct CartPole {
         ode(theta + k3_th, dtheta + k3_dth, dx + k3_dx, a4, b4);
         const T k4_th = h * (dtheta + k3_dth), k4_dth = h * a4, k4_x = h * (dx + k3_dx), k4_dx = h * b4;
         const T two = (T)2, six = (T)6;
-        theta = theta + (k1_th + two * k2_th + two * k3_th + k4_th) / six;
-        dtheta = dtheta + (k1_dth + two * k2_dth + two * k3_dth + k4_dth) / six;
-        x = x + (k1_x + two * k2_x + two * k3_x + k4_x) / six;
-        dx = dx + (k1_dx + two * k2_dx + two * k3_dx + k4_dx) / six;
+        theta = theta + div6<T>(k1_th + two * k2_th + two * k3_th + k4_th);
+        dtheta = dtheta + div6<T>(k1_dth + two * k2_dth + two * k3_dth + k4_dth);
+        x = x + div6<T>(k1_x + two * k2_x + two * k3_x + k4_x);
+        dx = dx + div6<T>(k1_dx + two * k2_dx + two * k3_dx + k4_dx);
     }
 
     // get_state(): CartPole.py:145-153 / cartpole_angleonly.py:137-143
     __device__ __forceinline__ void observe(const b200_cartpole_params &p, T *o) const {
         const T g = (T)p.static_gain;
+        const Divisor<T> d0((T)p.theta_max);
+        o[0] = d0.div(theta) * g;
         if (p.variant == 0) {
-            o[0] = theta / (T)p.theta_max * g;
-            o[1] = dtheta / (T)p.dtheta_max * g;
-            o[2] = x / (T)p.x_max * g;
-            o[3] = dx / (T)p.dx_max * g;
+            const Divisor<T> d1((T)p.dtheta_max), d2((T)p.x_max), d3((T)p.dx_max);
+            o[1] = d1.div(dtheta) * g;
+            o[2] = d2.div(x) * g;
+            o[3] = d3.div(dx) * g;
         } else {
-            o[0] = theta / (T)p.theta_max * g;
-            o[1] = dtheta / (T)p.norm_boundless * g;
+            const Divisor<T> d1((T)p.norm_boundless);
+            o[1] = d1.div(dtheta) * g;
         }
     }
 

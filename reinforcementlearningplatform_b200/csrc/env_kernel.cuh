@@ -89,36 +89,47 @@ env_rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constan
     E e;
     e.load(io, n, i);
     T nxt[E::OD];
-    for (int64_t t = 0; t < rs.steps; ++t) {
-        const TIO *act_row = static_cast<const TIO *>(io.action) + t * rs.action_stride;
-        T act[E::AD];
+    constexpr int U = 4; // time steps per trip: their action rows are loaded together, ahead of the dependent steps
+    for (int64_t t0 = 0; t0 < rs.steps; t0 += U) {
+        T acts[U][E::AD];
 #pragma unroll
-        for (int k = 0; k < E::AD; ++k) act[k] = ldio<T, IO32>(act_row, n, k, i);
-        T cur[E::OD];
-        e.observe(p, cur);
-        if (io.obs) {
-            TIO *row = static_cast<TIO *>(io.obs) + t * rs.obs_stride;
+        for (int u = 0; u < U; ++u) {
+            const int64_t t = (t0 + u < rs.steps) ? t0 + u : rs.steps - 1;
+            const TIO *act_row = static_cast<const TIO *>(io.action) + t * rs.action_stride;
 #pragma unroll
-            for (int k = 0; k < E::OD; ++k) stio<T, IO32>(row, n, k, i, cur[k]);
+            for (int k = 0; k < E::AD; ++k) acts[u][k] = ldio<T, IO32>(act_row, n, k, i);
         }
-        int flag = 0;
-        bool done = false;
-        T reward = (T)0;
-        e.step(p, act, cur, flag, done, reward, nxt);
-        {
-            TIO *row = static_cast<TIO *>(io.next_obs) + t * rs.next_obs_stride;
 #pragma unroll
-            for (int k = 0; k < E::OD; ++k) stio<T, IO32>(row, n, k, i, nxt[k]);
-        }
-        stio<T, IO32>(static_cast<TIO *>(io.reward) + t * rs.reward_stride, n, 0, i, reward);
-        io.done[t * rs.done_stride + i] = done ? 1 : 0;
-        io.flag[t * rs.flag_stride + i] = flag;
-        if (done && (flags & B200ENV_AUTO_RESET)) {
-            const uint32_t ep = io.episode[i];
-            Philox rng(seed, (uint64_t)(off + i), ep);
-            e.reset(p, rng);
-            io.episode[i] = ep + 1u;
-            e.observe(p, nxt);
+        for (int u = 0; u < U; ++u) {
+            const int64_t t = t0 + u;
+            if (t < rs.steps) {
+                T cur[E::OD];
+                e.observe(p, cur);
+                if (io.obs) {
+                    TIO *row = static_cast<TIO *>(io.obs) + t * rs.obs_stride;
+#pragma unroll
+                    for (int k = 0; k < E::OD; ++k) stio<T, IO32>(row, n, k, i, cur[k]);
+                }
+                int flag = 0;
+                bool done = false;
+                T reward = (T)0;
+                e.step(p, acts[u], cur, flag, done, reward, nxt);
+                {
+                    TIO *row = static_cast<TIO *>(io.next_obs) + t * rs.next_obs_stride;
+#pragma unroll
+                    for (int k = 0; k < E::OD; ++k) stio<T, IO32>(row, n, k, i, nxt[k]);
+                }
+                stio<T, IO32>(static_cast<TIO *>(io.reward) + t * rs.reward_stride, n, 0, i, reward);
+                io.done[t * rs.done_stride + i] = done ? 1 : 0;
+                io.flag[t * rs.flag_stride + i] = flag;
+                if (done && (flags & B200ENV_AUTO_RESET)) {
+                    const uint32_t ep = io.episode[i];
+                    Philox rng(seed, (uint64_t)(off + i), ep);
+                    e.reset(p, rng);
+                    io.episode[i] = ep + 1u;
+                    e.observe(p, nxt);
+                }
+            }
         }
     }
     if (io.reset_obs) {

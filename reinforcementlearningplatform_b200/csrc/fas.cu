@@ -23,30 +23,32 @@ struct Fas {
     }
     // :173-185
     __device__ __forceinline__ void observe(const P &p, T *o) const {
-        o[0] = ((T)2 * theta - (T)p.max_theta - (T)p.min_theta) / (T)(p.max_theta - p.min_theta) * (T)p.static_gain;
-        o[1] = ((T)2 * dtheta - (T)p.max_omega - (T)p.min_omega) / (T)(p.max_omega - p.min_omega) * (T)p.static_gain;
+        const Divisor<T> dth((T)(p.max_theta - p.min_theta)), dom((T)(p.max_omega - p.min_omega));
+        o[0] = dth.div((T)2 * theta - (T)p.max_theta - (T)p.min_theta) * (T)p.static_gain;
+        o[1] = dom.div((T)2 * dtheta - (T)p.max_omega - (T)p.min_omega) * (T)p.static_gain;
     }
     __device__ __forceinline__ void step(const P &p, const T *act, const T *cur, int &flag, bool &done, T &reward, T *nxt) {
         const T force = act[0];
         const T FL = force * (T)p.L - (T)p.mgd; // self.force * self.L - self.m * self.g * self.dis
-        const T kk = (T)p.k, den = (T)p.denom;
+        const T kk = (T)p.k;
+        const Divisor<T> den((T)p.denom); // J + m d^2: 40+ quotients per control period
         // rk44 :238-252: `while self.time < tt` with h = dt / 10 (10 or 11 trips, note N1)
         const double h = p.dt / 10.0, tt = time + p.dt;
         const T hT = (T)h, half = (T)0.5;
         while (time < tt) {
-            const T a1 = (FL - kk * dtheta) / den;
+            const T a1 = den.div(FL - kk * dtheta);
             const T k1a = hT * dtheta, k1b = hT * a1;
             const T w2 = dtheta + k1b * half;
-            const T a2 = (FL - kk * w2) / den;
+            const T a2 = den.div(FL - kk * w2);
             const T k2a = hT * w2, k2b = hT * a2;
             const T w3 = dtheta + k2b * half;
-            const T a3 = (FL - kk * w3) / den;
+            const T a3 = den.div(FL - kk * w3);
             const T k3a = hT * w3, k3b = hT * a3;
             const T w4 = dtheta + k3b;
-            const T a4 = (FL - kk * w4) / den;
+            const T a4 = den.div(FL - kk * w4);
             const T k4a = hT * w4, k4b = hT * a4;
-            theta = theta + (k1a + (T)2 * k2a + (T)2 * k3a + k4a) / (T)6;
-            dtheta = dtheta + (k1b + (T)2 * k2b + (T)2 * k3b + k4b) / (T)6;
+            theta = theta + div6<T>(k1a + (T)2 * k2a + (T)2 * k3a + k4a);
+            dtheta = dtheta + div6<T>(k1b + (T)2 * k2b + (T)2 * k3b + k4b);
             time += h;
         }
         // is_Terminal :193-211 (all tests run, the last true one wins)

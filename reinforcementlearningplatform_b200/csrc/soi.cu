@@ -25,10 +25,11 @@ struct Soi {
     // get_state :211-219 (use_norm = True)
     __device__ __forceinline__ void observe(const P &p, T *o) const {
         const T g = (T)p.obs_gain;
-        o[0] = ((T)p.target_x - x) / (T)p.map_x * g;
-        o[1] = ((T)p.target_y - y) / (T)p.map_y * g;
-        o[2] = -vx / (T)p.vmax * g;
-        o[3] = -vy / (T)p.vmax * g;
+        const Divisor<T> dx_((T)p.map_x), dy_((T)p.map_y), dv_((T)p.vmax);
+        o[0] = dx_.div((T)p.target_x - x) * g;
+        o[1] = dy_.div((T)p.target_y - y) * g;
+        o[2] = dv_.div(-vx) * g;
+        o[3] = dv_.div(-vy) * g;
     }
     __device__ __forceinline__ void step(const P &p, const T *act, const T *cur, int &flag, bool &done, T &reward, T *nxt) {
         const T fx = act[0], fy = act[1], k = (T)p.k;
@@ -42,13 +43,14 @@ struct Soi {
             const T k3x = h * u3, k3y = h * v3, k3u = h * (fx - k * u3), k3v = h * (fy - k * v3);
             const T u4 = vx + k3u, v4 = vy + k3v;
             const T k4x = h * u4, k4y = h * v4, k4u = h * (fx - k * u4), k4v = h * (fy - k * v4);
-            x = x + (k1x + (T)2 * k2x + (T)2 * k3x + k4x) / (T)6;
-            y = y + (k1y + (T)2 * k2y + (T)2 * k3y + k4y) / (T)6;
-            vx = vx + (k1u + (T)2 * k2u + (T)2 * k3u + k4u) / (T)6;
-            vy = vy + (k1v + (T)2 * k2v + (T)2 * k3v + k4v) / (T)6;
+            x = x + div6<T>(k1x + (T)2 * k2x + (T)2 * k3x + k4x);
+            y = y + div6<T>(k1y + (T)2 * k2y + (T)2 * k3y + k4y);
+            vx = vx + div6<T>(k1u + (T)2 * k2u + (T)2 * k3u + k4u);
+            vy = vy + div6<T>(k1v + (T)2 * k2v + (T)2 * k3v + k4v);
             time += p.dt;
         }
-        const T ax = (fx - k * vx) / (T)p.mass, ay = (fy - k * vy) / (T)p.mass; // self.acc :313
+        const Divisor<T> dm((T)p.mass);
+        const T ax = dm.div(fx - k * vx), ay = dm.div(fy - k * vy); // self.acc :313
         const T ex = (T)p.target_x - x, ey = (T)p.target_y - y;
         const T e_pos = Mth<T>::sqrt(ex * ex + ey * ey);
         const T e_vel = Mth<T>::sqrt(vx * vx + vy * vy);

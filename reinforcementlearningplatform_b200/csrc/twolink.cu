@@ -67,10 +67,10 @@ struct TwoLink {
         const T k3t1 = h * (w1 + k2w1 * half), k3t2 = h * (w2 + k2w2 * half), k3w1 = h * a3, k3w2 = h * b3;
         ode(p, th1 + k3t1, th2 + k3t2, w1 + k3w1, w2 + k3w2, tq0, tq1, a4, b4);
         const T k4t1 = h * (w1 + k3w1), k4t2 = h * (w2 + k3w2), k4w1 = h * a4, k4w2 = h * b4;
-        th1 = th1 + (k1t1 + (T)2 * k2t1 + (T)2 * k3t1 + k4t1) / (T)6;
-        th2 = th2 + (k1t2 + (T)2 * k2t2 + (T)2 * k3t2 + k4t2) / (T)6;
-        w1 = w1 + (k1w1 + (T)2 * k2w1 + (T)2 * k3w1 + k4w1) / (T)6;
-        w2 = w2 + (k1w2 + (T)2 * k2w2 + (T)2 * k3w2 + k4w2) / (T)6;
+        th1 = th1 + div6<T>(k1t1 + (T)2 * k2t1 + (T)2 * k3t1 + k4t1);
+        th2 = th2 + div6<T>(k1t2 + (T)2 * k2t2 + (T)2 * k3t2 + k4t2);
+        w1 = w1 + div6<T>(k1w1 + (T)2 * k2w1 + (T)2 * k3w1 + k4w1);
+        w2 = w2 + div6<T>(k1w2 + (T)2 * k2w2 + (T)2 * k3w2 + k4w2);
         time += p.dt;
         // forward kinematics :252-257, error BEFORE the angle wrap
         const T l = (T)p.l;

@@ -73,11 +73,11 @@ struct Ugv {
         const T v4 = vel + k3v, o4 = omega + k3o;
         Mth<T>::sincos(phi + k3p, &s, &c);
         const T k4x = h * (v4 * c), k4y = h * (v4 * s), k4v = h * (al - kf * v4), k4p = h * o4, k4o = h * (aa - kt * o4);
-        x = x + (k1x + (T)2 * k2x + (T)2 * k3x + k4x) / (T)6;
-        y = y + (k1y + (T)2 * k2y + (T)2 * k3y + k4y) / (T)6;
-        vel = vel + (k1v + (T)2 * k2v + (T)2 * k3v + k4v) / (T)6;
-        phi = phi + (k1p + (T)2 * k2p + (T)2 * k3p + k4p) / (T)6;
-        omega = omega + (k1o + (T)2 * k2o + (T)2 * k3o + k4o) / (T)6;
+        x = x + div6<T>(k1x + (T)2 * k2x + (T)2 * k3x + k4x);
+        y = y + div6<T>(k1y + (T)2 * k2y + (T)2 * k3y + k4y);
+        vel = vel + div6<T>(k1v + (T)2 * k2v + (T)2 * k3v + k4v);
+        phi = phi + div6<T>(k1p + (T)2 * k2p + (T)2 * k3p + k4p);
+        omega = omega + div6<T>(k1o + (T)2 * k2o + (T)2 * k3o + k4o);
         if (!p.bidirectional && vel < (T)0) vel = (T)0; // UGVForward.py:303-304
         time += p.dt;
         if (phi > (T)M_PI) phi -= (T)(2 * M_PI);

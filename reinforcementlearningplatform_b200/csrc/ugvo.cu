@@ -71,19 +71,6 @@ struct ObsList {
     int stride, count;
 };
 
-// a / d with d fixed per ray: one IEEE reciprocal, then per quotient a product and one FMA-corrected Newton step
-// (Markstein: with r = RN(1/d) and q within 1 ulp, q + (a - q d) r rounds to the IEEE quotient) -- 3 instructions instead
-// of the ~25 of a fp64 division, same result as the reference's `/`.  NaN numerators stay NaN.
-template <typename T>
-struct Divisor {
-    T d, r;
-    __device__ __forceinline__ explicit Divisor(T d_) : d(d_), r((T)1 / d_) {}
-    __device__ __forceinline__ T div(T a) const {
-        const T q = a * r;
-        return Mth<T>::fma(Mth<T>::fma(-q, d, a), r, q);
-    }
-};
-
 // bearings of the four map corners seen from (x, y), :304-309
 template <typename T>
 __device__ __forceinline__ T corner_bearing(const P &p, T x, T y, int k) {
@@ -443,11 +430,11 @@ ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io
         const T v4 = vel + k3v, o4 = omega + k3o;
         Mth<T>::sincos(phi + k3p, &s, &c);
         const T k4x = h * (v4 * c), k4y = h * (v4 * s), k4v = h * (a_lin - kf * v4), k4p = h * o4, k4o = h * (a_ang - kt * o4);
-        const T nx = x + (k1x + (T)2 * k2x + (T)2 * k3x + k4x) / (T)6;
-        const T ny = y + (k1y + (T)2 * k2y + (T)2 * k3y + k4y) / (T)6;
-        const T nv = vel + (k1v + (T)2 * k2v + (T)2 * k3v + k4v) / (T)6;
-        const T np_ = phi + (k1p + (T)2 * k2p + (T)2 * k3p + k4p) / (T)6;
-        const T no = omega + (k1o + (T)2 * k2o + (T)2 * k3o + k4o) / (T)6;
+        const T nx = x + div6<T>(k1x + (T)2 * k2x + (T)2 * k3x + k4x);
+        const T ny = y + div6<T>(k1y + (T)2 * k2y + (T)2 * k3y + k4y);
+        const T nv = vel + div6<T>(k1v + (T)2 * k2v + (T)2 * k3v + k4v);
+        const T np_ = phi + div6<T>(k1p + (T)2 * k2p + (T)2 * k3p + k4p);
+        const T no = omega + div6<T>(k1o + (T)2 * k2o + (T)2 * k3o + k4o);
         if (p.variant == 0) {
             x = nx; y = ny; vel = nv; phi = np_; omega = no;
             if (vel < (T)0) vel = (T)0;
