@@ -54,7 +54,8 @@ enum b200env_id {
     B200ENV_UAV_ATT       = 7, /* environment/UavFntsmcParam/uav_att_ctrl_RL.py (+ uav.py, FNTSMC.py, ref_cmd.py) */
     B200ENV_UAV_POS       = 8, /* environment/UavFntsmcParam/uav_pos_ctrl_RL.py (+ uav.py, FNTSMC.py, ref_cmd.py) */
     B200ENV_UAVROBUST     = 9, /* environment/UavRobust/Uav{Hover,HoverOuterLoop,InnerLoop,TrackingOuterLoop}.py */
-    B200ENV_COUNT         = 10
+    B200ENV_FAS_DISCRETE  = 10,/* environment/FlightAttitudeSimulator/FlightAttitudeSimulatorDiscrete.py (DQN-family demos) */
+    B200ENV_COUNT         = 11
 };
 
 enum b200env_dtype { B200ENV_F64 = 0, B200ENV_F32 = 1 };
@@ -186,6 +187,22 @@ typedef struct b200_fas_params {
     double reset_lo, reset_hi;          /* theta0 ~ U(minTheta, maxTheta) :270-271 */
 } b200_fas_params;
 #define B200_FAS_STATE_FIELDS 2         /* theta, dTheta */
+
+/* FlightAttitudeSimulatorDiscrete (B200ENV_FAS_DISCRETE): environment/FlightAttitudeSimulator/
+ * FlightAttitudeSimulatorDiscrete.py:9-274.  The action is the force VALUE picked from the discrete action_space
+ * (:56-59); the dynamics are the file's own closure f() (:199-203, incl. its `dis + m dis^2` denominator) integrated by
+ * `while t_sim <= dt` with h = dt, i.e. TWO RK4 steps of h = dt per control period (:205-219), followed by the
+ * +-theta_max bounce (:220-225). */
+typedef struct b200_fas_discrete_params {
+    double a2, a1;                      /* -k/(J+m d^2); -m g d/(d + m d^2) (sic)          :202-203 (host-evaluated) */
+    double L, denom;                    /* a0 = L * action / (J + m d^2)                   :204 */
+    double dt, time_max;                /* :28, :30 */
+    double theta_max, dtheta_max, static_gain; /* :23-25 */
+    double theta_out;                   /* theta_max + deg2rad(1)                          :170-177 */
+    double Q, R;                        /* get_reward locals :233-234 */
+    double bounce;                      /* -0.8                                            :222,225 */
+} b200_fas_discrete_params;
+#define B200_FAS_DISCRETE_STATE_FIELDS 2 /* theta, dTheta */
 
 /* SecondOrderIntegration (B200ENV_SOI): environment/SecondOrderIntegration/SecondOrderIntegration.py:13-352;
  * DPPO2 demo copy: obs multiplied by static_gain, success terminal disabled, Q_vel = Q_acc = 0. */
@@ -371,6 +388,37 @@ B200_API int b200_gae_flags(int64_t T, int64_t N, const float *r, const float *v
 /* adv <- (adv - mean) / (std + eps) with the unbiased std (torch.Tensor.std) derived from stats = (sum, sum of
  * squares, count): Proximal_Policy_Optimization2.py:99-100 (eps = 1e-5). */
 B200_API int b200_adv_normalize(int64_t count, float *adv, const double *stats, double eps, void *cuda_stream);
+
+/* Monte-Carlo return scan of PPO / DPPO (v1): algorithm/policy_base/Proximal_Policy_Optimization.py:113-119,
+ * Distributed_PPO.py:58-64.  r is [T][N] in r_dtype (B200ENV_F64 like RolloutBuffer.r, or B200ENV_F32), done [T][N] u8;
+ * the recurrence `R = 0 if done; R = r + gamma * R` runs backwards in float64, returns [T][N] are float32 like
+ * `torch.tensor(np.array(rewards), dtype=torch.float32)`. */
+B200_API int b200_mc_returns(int r_dtype, int64_t T, int64_t N, const void *r, const uint8_t *done, double gamma,
+                             float *returns, void *cuda_stream);
+
+/* ------------------------------------------------------------- running normalisation */
+
+/* Replaces RunningMeanStd.update + Normalization.__call__ (utils/classes.py:626-656) as used on rewards
+ * (demonstration/PPO2/PPO2-4-CartPoleAngleOnly/train.py:139,210) and UAV observations
+ * (PPO2-4-UavFntsmcParamPos/train.py:291,308).  Running state: double run[3][dim] = (n, mean, S); the reference's
+ * `std` is n == 1 ? mean (sic, `self.std = x`) : sqrt(S / n).  x, y: [dim][n] field-major in `dtype`.
+ *
+ * b200_norm_seq: the reference recurrence sample by sample over `rows` samples (x, y = [dim][rows]); bit-exact.
+ *   y may be NULL (update only); update = 0 normalises with the stored statistics.
+ * b200_norm_batch_stats: (count, mean, M2) of one batch of n instances per feature -> batch_stats[3][dim], summed in
+ *   float64 about run's mean (run may be NULL).  scratch: b200_norm_scratch_bytes(dim) bytes, zeroed once by the caller.
+ * b200_norm_merge_apply: merges n_batches batch statistics (batch_stats[n_batches][3][dim], e.g. all-gathered over
+ *   ranks, merged in index order) into run_in -> run_out (may alias only if y == NULL), then y = (x - mean) / (std +
+ *   eps) with the MERGED statistics.  The merge is Chan's pairwise update written so that a batch of one sample is
+ *   bit-identical to the reference's update; update = 0 skips the merge (evaluation: `update=False`). */
+B200_API size_t b200_norm_scratch_bytes(int dim);
+B200_API int b200_norm_seq(int dtype, int64_t rows, int dim, const void *x, void *y, double *run, int update, double eps,
+                           void *cuda_stream);
+B200_API int b200_norm_batch_stats(int dtype, int64_t n, int dim, const void *x, const double *run, double *batch_stats,
+                                   void *scratch, void *cuda_stream);
+B200_API int b200_norm_merge_apply(int dtype, int64_t n, int dim, const void *x, void *y, const double *batch_stats,
+                                   int n_batches, const double *run_in, double *run_out, int update, double eps,
+                                   void *cuda_stream);
 
 /* ------------------------------------------------------------- diagnostics */
 

@@ -21,6 +21,7 @@ DECL(twolink)
 DECL(ugv)
 DECL(ugvo)
 DECL(uavrobust)
+DECL(fas_discrete)
 
 static step_one_fn step_of(int env_id) {
     switch (env_id) {
@@ -34,6 +35,7 @@ static step_one_fn step_of(int env_id) {
     case B200ENV_UGV: return orc_ugv_step_one;
     case B200ENV_UGVO: return orc_ugvo_step_one;
     case B200ENV_UAVROBUST: return orc_uavrobust_step_one;
+    case B200ENV_FAS_DISCRETE: return orc_fas_discrete_step_one;
     default: return 0;
     }
 }
@@ -49,6 +51,7 @@ static reset_one_fn reset_of(int env_id) {
     case B200ENV_UGV: return orc_ugv_reset_one;
     case B200ENV_UGVO: return orc_ugvo_reset_one;
     case B200ENV_UAVROBUST: return orc_uavrobust_reset_one;
+    case B200ENV_FAS_DISCRETE: return orc_fas_discrete_reset_one;
     default: return 0;
     }
 }

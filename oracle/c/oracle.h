@@ -52,6 +52,13 @@ void oracle_gae(int64_t T, int64_t N, const float *r, const float *vs, const flo
                 const float *success, float gamma, float lambda_gamma /* float32(gamma * lmd) */, float *adv,
                 float *v_target, double *stats /* += (sum adv, sum adv^2, T*N), may be NULL */);
 
+/* RunningMeanStd.update + Normalization.__call__ (utils/classes.py:626-656), sample by sample; run = [4][dim] =
+ * (n, mean, S, std) */
+void oracle_norm_seq(int64_t rows, int dim, const double *x, double *y, double *run, int update, double eps);
+
+/* PPO / DPPO (v1) Monte-Carlo returns (Proximal_Policy_Optimization.py:113-119) */
+void oracle_mc_returns(int64_t T, int64_t N, const double *r, const uint8_t *done, double gamma, float *ret);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,65 @@ void orc_fas_reset_one(const void *params, const oracle_io *io, int64_t n, int64
     if (io->next_obs) { double o[2]; fas_obs(p, SF(0), SF(1), o); for (int k = 0; k < 2; ++k) OUT(io->next_obs, k) = o[k]; }
 }
 
+/* ============================================================ FlightAttitudeSimulatorDiscrete */
+/* environment/FlightAttitudeSimulator/FlightAttitudeSimulatorDiscrete.py */
+typedef b200_fas_discrete_params FDP;
+static void fasd_obs(const FDP *p, double th, double dth, double *o) { /* :158-162 */
+    o[0] = -th / p->theta_max * p->static_gain;
+    o[1] = dth / p->dtheta_max * p->static_gain;
+}
+static double fasd_f(const FDP *p, double a0, double angle, double dangle) { /* :199-203 */
+    return p->a2 * dangle + p->a1 * cos(angle) + a0;
+}
+static void fasd_reset(const FDP *p, const oracle_io *io, int64_t n, int64_t i, uint64_t seed, int64_t off) {
+    orc_rng g;
+    uint32_t ep = io->episode[i];
+    orc_rng_init(&g, seed, (uint64_t)(off + i), ep);
+    SF(0) = orc_uniform(&g, -p->theta_max, p->theta_max); /* :257-260 */
+    SF(1) = 0.;
+    io->time[i] = 0.;
+    io->episode[i] = ep + 1u;
+}
+void orc_fas_discrete_step_one(const void *params, const oracle_io *io, int64_t n, int64_t i, uint32_t flags, uint64_t seed, int64_t off) {
+    const FDP *p = (const FDP *)params;
+    double th = SF(0), dth = SF(1), time = io->time[i];
+    const double a0 = p->L * io->action[i] / p->denom; /* :204 */
+    double cur[2], nxt[2];
+    fasd_obs(p, th, dth, cur);
+    double h = p->dt / 1, t_sim = 0.0; /* :205-219 */
+    int sub = 0;
+    while (t_sim <= p->dt) {
+        double K1 = dth, L1 = fasd_f(p, a0, th, dth);
+        double K2 = dth + h * L1 / 2, L2 = fasd_f(p, a0, th + h * K1 / 2, dth + h * L1 / 2);
+        double K3 = dth + h * L2 / 2, L3 = fasd_f(p, a0, th + h * K2 / 2, dth + h * L2 / 2);
+        double K4 = dth + h * L3, L4 = fasd_f(p, a0, th + h * K3, dth + h * L3);
+        th = th + h * (K1 + 2 * K2 + 2 * K3 + K4) / 6;
+        dth = dth + h * (L1 + 2 * L2 + 2 * L3 + L4) / 6;
+        t_sim = t_sim + h;
+        ++sub;
+    }
+    if (th > p->theta_max) { th = p->theta_max; dth = p->bounce * dth; }   /* :220-222 */
+    if (th < -p->theta_max) { th = -p->theta_max; dth = p->bounce * dth; } /* :223-225 */
+    time = time + p->dt;
+    fasd_obs(p, th, dth, nxt);
+    int flag = 0; /* is_Terminal :178-196: first true test returns */
+    if (th > p->theta_out || th < -p->theta_out) flag = 1;
+    else if (time > p->time_max) flag = 2;
+    int done = flag != 0;
+    double r1 = -pow(th, 2.0) * p->Q, r2 = -pow(dth, 2.0) * p->R, r3 = 0.; /* :232-244 */
+    if (flag == 1 || flag == 2) { double _n = (p->time_max - time) / p->dt; r3 = _n * (r1 + r2); }
+    emit(io, n, i, 2, cur, nxt, r1 + r2 + r3, done, flag);
+    if (io->substeps) io->substeps[i] = sub;
+    SF(0) = th; SF(1) = dth; io->time[i] = time;
+    if (done && (flags & B200ENV_AUTO_RESET)) { fasd_reset(p, io, n, i, seed, off); fasd_obs(p, SF(0), SF(1), nxt); }
+    emit_policy(io, n, i, 2, nxt);
+}
+void orc_fas_discrete_reset_one(const void *params, const oracle_io *io, int64_t n, int64_t i, uint64_t seed, int64_t off, int observe_only) {
+    const FDP *p = (const FDP *)params;
+    if (!observe_only) fasd_reset(p, io, n, i, seed, off);
+    if (io->next_obs) { double o[2]; fasd_obs(p, SF(0), SF(1), o); for (int k = 0; k < 2; ++k) OUT(io->next_obs, k) = o[k]; }
+}
+
 /* ============================================================ SecondOrderIntegration */
 /* environment/SecondOrderIntegration/SecondOrderIntegration.py */
 typedef b200_soi_params SP;

@@ -43,6 +43,10 @@ def load() -> C.CDLL:
         lib.oracle_observe.argtypes = [i32, i64, vp, C.POINTER(OracleIO)]
         lib.oracle_gae.restype = None
         lib.oracle_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp]
+        lib.oracle_norm_seq.restype = None
+        lib.oracle_norm_seq.argtypes = [i64, i32, vp, vp, vp, i32, C.c_double]
+        lib.oracle_mc_returns.restype = None
+        lib.oracle_mc_returns.argtypes = [i64, i64, vp, vp, C.c_double, vp]
         lib.oracle_philox4x32_10.restype = None
         lib.oracle_philox4x32_10.argtypes = [vp, vp, vp]
         _lib = lib
@@ -120,3 +124,24 @@ def gae(r, vs, vs_next, done, success, gamma, lmd):
     load().oracle_gae(T, N, *[a.ctypes.data for a in arrs], np.float32(gamma), np.float32(gamma * lmd),
                       adv.ctypes.data, vt.ctypes.data, stats.ctypes.data)
     return adv, vt, stats
+
+
+def norm_seq(x_soa, run=None, update=True, eps=1e-8):
+    """C restatement of Normalization.__call__ fed sample by sample: x_soa [dim, rows] float64 ->
+    (y [dim, rows], run [4, dim] = n, mean, S, std)."""
+    x = np.ascontiguousarray(x_soa, dtype=np.float64)
+    dim, rows = x.shape
+    run = np.zeros((4, dim)) if run is None else np.ascontiguousarray(run, dtype=np.float64).copy()
+    y = np.zeros_like(x)
+    load().oracle_norm_seq(rows, dim, x.ctypes.data, y.ctypes.data, run.ctypes.data, 1 if update else 0, eps)
+    return y, run
+
+
+def mc_returns(r, done, gamma):
+    """C restatement of the PPO (v1) return scan on time-major [T, N] arrays -> float32 [T, N]."""
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    d = np.ascontiguousarray(done, dtype=np.uint8)
+    T, N = r.shape
+    out = np.zeros((T, N), np.float32)
+    load().oracle_mc_returns(T, N, r.ctypes.data, d.ctypes.data, float(gamma), out.ctypes.data)
+    return out

@@ -336,6 +336,31 @@ class FasPPO2A(FasA):
         return m.Flight_Attitude_Simulator(0.)
 
 
+class FasDiscreteA(Adapter):
+    name = "fas_discrete"
+    cites = "environment/FlightAttitudeSimulator/FlightAttitudeSimulatorDiscrete.py:158-274"
+    F, S, A, D = 2, 2, 1, 0
+    action_lo, action_hi = np.array([-1.6]), np.array([3.0])
+    perturb_attrs = ("theta", "dTheta")
+
+    def make(self):
+        m = R.load("environment.FlightAttitudeSimulator.FlightAttitudeSimulatorDiscrete")
+        return m.FlightAttitudeSimulatorDiscrete(0.)
+
+    def internal(self, env):
+        return np.array([env.theta, env.dTheta], dtype=float), float(env.time)
+
+    def sample_action(self, rng, t, l, env=None):
+        space = env.action_space[0]
+        if l % 3 == 0:  # uniformly random discrete action
+            return np.array([space[int(rng.integers(len(space)))]])
+        if l % 3 == 1:  # pushes up: bounce at +theta_max, stays inside theta_out -> time-out flag
+            return np.array([space[int(rng.integers(len(space) - 8, len(space)))]])
+        # nearest discrete force of a PD law around level: long episodes, small angles
+        want = 0.81 - 3.0 * env.theta - 0.8 * env.dTheta
+        return np.array([space[int(np.argmin(np.abs(np.array(space) - want)))]])
+
+
 class SoiA(Adapter):
     name = "soi"
     cites = "environment/SecondOrderIntegration/SecondOrderIntegration.py:211-352"
@@ -452,6 +477,7 @@ class UgvBidirectionalA(UgvForwardA):
 REGISTRY.update({
     "fas": (FasA, 4, 800, 31),
     "fas_ppo2": (FasPPO2A, 2, 1200, 32),
+    "fas_discrete": (FasDiscreteA, 3, 700, 39),
     "soi": (SoiA, 4, 800, 33),
     "soi_dppo2": (SoiDPPO2A, 2, 600, 34),
     "ballbalancer": (BallBalancerA, 4, 1000, 35),

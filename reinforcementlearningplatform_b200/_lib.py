@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200ENV_LIB") or os.path.join(_HERE, "libb200env.so")
 
 # enum b200env_id
-CARTPOLE, FAS, SOI, BALLBALANCER, TWOLINK, UGV, UGVO, UAV_ATT, UAV_POS, UAVROBUST = range(10)
+CARTPOLE, FAS, SOI, BALLBALANCER, TWOLINK, UGV, UGVO, UAV_ATT, UAV_POS, UAVROBUST, FAS_DISCRETE = range(11)
 F64, F32 = 0, 1
 AUTO_RESET = 1
 
@@ -81,6 +81,8 @@ def _struct(name, doc, doubles, ints=()):
 FasParams = _struct("FasParams", "struct b200_fas_params", (
     "L", "k", "mgd", "denom", "dt", "time_max", "min_theta", "max_theta", "min_omega", "max_omega", "static_gain",
     "theta_term_hi", "theta_term_lo", "Q", "R", "reset_lo", "reset_hi"))
+FasDiscreteParams = _struct("FasDiscreteParams", "struct b200_fas_discrete_params", (
+    "a2", "a1", "L", "denom", "dt", "time_max", "theta_max", "dtheta_max", "static_gain", "theta_out", "Q", "R", "bounce"))
 SoiParams = _struct("SoiParams", "struct b200_soi_params", (
     "map_x", "map_y", "target_x", "target_y", "mass", "k", "vmax", "dt", "time_max", "admissible_error", "obs_gain",
     "Q_pos", "Q_vel", "Q_acc", "reset_margin"), ("success_terminal", "pad_"))
@@ -112,7 +114,7 @@ class UavRobustParams(C.Structure):
         _d("sig_phase_hi"), _d("init_pos_r"), ("variant", C.c_int32), ("pad_", C.c_int32)]
 
 
-PARAMS_OF = {UAVROBUST: UavRobustParams, UGVO: UgvoParams, CARTPOLE: CartPoleParams, UAV_ATT: UavParams, UAV_POS: UavParams, FAS: FasParams, SOI: SoiParams,
+PARAMS_OF = {UAVROBUST: UavRobustParams, FAS_DISCRETE: FasDiscreteParams, UGVO: UgvoParams, CARTPOLE: CartPoleParams, UAV_ATT: UavParams, UAV_POS: UavParams, FAS: FasParams, SOI: SoiParams,
              BALLBALANCER: BallBalancerParams, TWOLINK: TwoLinkParams, UGV: UgvParams}
 
 _lib = None
@@ -154,6 +156,16 @@ def load() -> C.CDLL:
     lib.b200_gae_flags.argtypes = [i64, i64, vp, vp, vp, vp, vp, i32, f64, f64, i32, vp, vp, vp, vp]
     lib.b200_adv_normalize.restype = i32
     lib.b200_adv_normalize.argtypes = [i64, vp, vp, f64, vp]
+    lib.b200_mc_returns.restype = i32
+    lib.b200_mc_returns.argtypes = [i32, i64, i64, vp, vp, f64, vp, vp]
+    lib.b200_norm_scratch_bytes.restype = sz
+    lib.b200_norm_scratch_bytes.argtypes = [i32]
+    lib.b200_norm_seq.restype = i32
+    lib.b200_norm_seq.argtypes = [i32, i64, i32, vp, vp, vp, i32, f64, vp]
+    lib.b200_norm_batch_stats.restype = i32
+    lib.b200_norm_batch_stats.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp]
+    lib.b200_norm_merge_apply.restype = i32
+    lib.b200_norm_merge_apply.argtypes = [i32, i64, i32, vp, vp, vp, i32, vp, vp, i32, f64, vp]
     lib.b200_fastmath_eval.restype = i32
     lib.b200_fastmath_eval.argtypes = [i32, i64, vp, vp, vp, vp]
     lib.b200_measure_fma_peak.restype = i32

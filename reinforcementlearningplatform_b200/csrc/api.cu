@@ -32,6 +32,7 @@ const Family *family(int env_id) {
         table[B200ENV_UGV] = FAMR(ugv, b200_ugv_params);
         table[B200ENV_UGVO] = FAM(ugvo, b200_ugvo_params);
         table[B200ENV_UAVROBUST] = FAM(uavrobust, b200_uavrobust_params);
+        table[B200ENV_FAS_DISCRETE] = FAMR(fas_discrete, b200_fas_discrete_params);
         init = true;
     }
     if (env_id < 0 || env_id >= B200ENV_COUNT) return nullptr;

@@ -251,6 +251,7 @@ B200_FAMILY_DECL(twolink)
 B200_FAMILY_DECL(ugv)
 B200_FAMILY_DECL(ugvo)
 B200_FAMILY_DECL(uavrobust)
+B200_FAMILY_DECL(fas_discrete)
 // families built on env_kernel.cuh also have a fused multi-step kernel (state in registers across the steps)
 #define B200_FAMILY_ROLLOUT_DECL(name)                                                                          \
     int name##_rollout(int dtype, int64_t n, const void *params, const b200env_io *io,                          \
@@ -260,3 +261,4 @@ B200_FAMILY_ROLLOUT_DECL(soi)
 B200_FAMILY_ROLLOUT_DECL(ballbalancer)
 B200_FAMILY_ROLLOUT_DECL(twolink)
 B200_FAMILY_ROLLOUT_DECL(ugv)
+B200_FAMILY_ROLLOUT_DECL(fas_discrete)

@@ -136,6 +136,46 @@ adv_normalize_kernel(int64_t count, float *__restrict__ adv, const double *__res
         adv[i] = (adv[i] - m) * inv;
 }
 
+// PPO / DPPO (v1) Monte-Carlo return scan, SURVEY 8(f)-4: algorithm/policy_base/Proximal_Policy_Optimization.py:113-119,
+// Distributed_PPO.py:58-64:
+//     for reward, is_terminal in zip(reversed(buffer.r), reversed(buffer.done)):
+//         if is_terminal: discounted_reward = 0
+//         discounted_reward = reward + gamma * discounted_reward;  rewards.insert(0, discounted_reward)
+//     rewards = torch.tensor(np.array(rewards), dtype=torch.float32)
+// buffer.r is a float64 numpy array, so the recurrence runs in float64 (separately rounded multiply and add) and only
+// the stored return is rounded to float32.  One thread per instance column, like K-GAE.
+template <typename TR>
+__global__ void __launch_bounds__(GAE_BLOCK)
+mc_returns_kernel(int64_t T, int64_t N, const TR *__restrict__ r, const uint8_t *__restrict__ done, double gamma,
+                  float *__restrict__ ret) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double acc = 0.0;
+    int64_t t = T - 1;
+    for (; t >= GAE_UNROLL - 1; t -= GAE_UNROLL) {
+        double rr[GAE_UNROLL];
+        uint8_t dd[GAE_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GAE_UNROLL; ++u) {
+            const int64_t idx = (t - u) * N + n;
+            rr[u] = (double)__ldcs(r + idx);
+            dd[u] = __ldcs(done + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < GAE_UNROLL; ++u) {
+            if (dd[u]) acc = 0.0;
+            acc = __dadd_rn(rr[u], __dmul_rn(gamma, acc));
+            __stcs(ret + (t - u) * N + n, (float)acc);
+        }
+    }
+    for (; t >= 0; --t) {
+        const int64_t idx = t * N + n;
+        if (done[idx]) acc = 0.0;
+        acc = __dadd_rn((double)r[idx], __dmul_rn(gamma, acc));
+        ret[idx] = (float)acc;
+    }
+}
+
 } // namespace
 
 extern "C" B200_API int b200_gae(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next,
@@ -181,5 +221,17 @@ extern "C" B200_API int b200_adv_normalize(int64_t count, float *adv, const doub
     int64_t blocks = (count + 255) / 256;
     if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
     adv_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(count, adv, stats, eps);
+    return b200_check_launch();
+}
+
+extern "C" B200_API int b200_mc_returns(int r_dtype, int64_t T, int64_t N, const void *r, const uint8_t *done,
+                                        double gamma, float *returns, void *cuda_stream) {
+    if (T <= 0 || N <= 0) return B200ENV_ESIZE;
+    if (r_dtype != B200ENV_F64 && r_dtype != B200ENV_F32) return B200ENV_EDTYPE;
+    if (!r || !done || !returns) return B200ENV_ENULL;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const unsigned grid = (unsigned)((N + GAE_BLOCK - 1) / GAE_BLOCK);
+    if (r_dtype == B200ENV_F64) mc_returns_kernel<double><<<grid, GAE_BLOCK, 0, s>>>(T, N, (const double *)r, done, gamma, returns);
+    else mc_returns_kernel<float><<<grid, GAE_BLOCK, 0, s>>>(T, N, (const float *)r, done, gamma, returns);
     return b200_check_launch();
 }

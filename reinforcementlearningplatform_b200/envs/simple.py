@@ -60,6 +60,50 @@ class Flight_Attitude_Simulator(_Simple):
         return p
 
 
+class FlightAttitudeSimulatorDiscrete(_Simple):
+    """environment/FlightAttitudeSimulator/FlightAttitudeSimulatorDiscrete.py:9-274 (the DQN-family demos).  The action
+    handed to ``step_update`` is the force VALUE, an element of ``action_space[0]`` (:56-59), exactly as in the
+    reference; ``action_index_to_value`` maps a batch of discrete indices to values on the device."""
+    ENV_ID = _lib.FAS_DISCRETE
+    TIMEOUT_FLAG = 2
+    OBS_IS_PURE = True
+    STATE_FIELDS = ("theta", "dTheta")
+
+    def __init__(self, n_envs: int = 1, **kw):
+        self.name = 'FlightAttitudeSimulatorDiscrete'
+        self.f_max, self.f_min, self.f_step = 3.0, -1.6, 0.1            # :20-22
+        self.theta_max, self.dtheta_max = deg2rad(60.0), deg2rad(90)    # :23-24
+        self.static_gain = 2.0
+        self.dt, self.timeMax = 0.02, 5.0                               # :28,30
+        self.J, self.k, self.m, self.g = 0.082, 0.09, 0.3, 9.8          # :32-35
+        self.dis, self.L = 0.3, 0.362                                   # :79,83
+        super().__init__(n_envs, **kw)
+        self.use_norm = True
+        self.action_step = [self.f_step]
+        self.action_range = [[self.f_min, self.f_max]]
+        self.action_num = [int((self.f_max - self.f_min) / self.f_step + 1)]                           # :58
+        self.action_space = [[self.f_min + i * self.f_step for i in range(self.action_num[0])]]        # :59
+        self.isActionContinuous = False
+
+    def make_params(self):
+        p = _lib.FasDiscreteParams()
+        p.a2 = -self.k / (self.J + self.m * self.dis ** 2)                                   # :202
+        p.a1 = -self.m * self.g * self.dis / (self.dis + self.m * self.dis ** 2)             # :203 (sic)
+        p.L, p.denom = self.L, self.J + self.m * self.dis ** 2                               # :204
+        p.dt, p.time_max = self.dt, self.timeMax
+        p.theta_max, p.dtheta_max, p.static_gain = self.theta_max, self.dtheta_max, self.static_gain
+        p.theta_out = self.theta_max + deg2rad(1)                                            # :170,174
+        p.Q, p.R = 3., 0.0                                                                   # :233-234
+        p.bounce = -0.8
+        return p
+
+    def action_index_to_value(self, index):
+        """[N] integer tensor of discrete action numbers -> [1, N] force values (``action_space[0][i]``)."""
+        import torch
+        table = torch.tensor(self.action_space[0], dtype=self.io_dtype, device=self.device)
+        return table[index.to(self.device).long()].view(1, -1)
+
+
 class SecondOrderIntegration(_Simple):
     """environment/SecondOrderIntegration/SecondOrderIntegration.py:13-352.  ``variant='dppo2'``: the DPPO2 demo copy
     (obs * static_gain :213, success terminal disabled :243-246, Q_vel = Q_acc = 0 :260-261)."""

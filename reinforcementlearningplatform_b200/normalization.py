@@ -1,0 +1,190 @@
+"""Running mean/std normalisation on device (kernel K-NORM, csrc/norm.cu) -- the vector mirror of
+``RunningMeanStd`` / ``Normalization`` (utils/classes.py:626-656).
+
+The reference applies one ``Normalization`` object to every reward (``reward_norm(env.reward)``,
+demonstration/PPO2/PPO2-4-CartPoleAngleOnly/train.py:139,210) and, in the UAV envs, to every observation
+(``env.current_state_norm(env.current_state, update=True)``, PPO2-4-UavFntsmcParamPos/train.py:291,308).  Each call
+there sees ONE sample.  Here a call sees the N samples of one step:
+
+* they enter the statistics together (pairwise Chan merge of ``(count, mean, M2)``) and all N are normalised with the
+  merged statistics -- a batch of one sample reproduces the reference's update bit for bit (tests/test_norm.py);
+* with ``torch.distributed`` initialised, the per-rank batch statistics (3 x dim doubles) are all-gathered and merged
+  in rank order, so every rank holds identical running statistics (``sync=True``);
+* ``seq(x)`` feeds ``rows`` samples one after the other (the reference recurrence, bit-exact) for single-instance
+  rollouts.
+
+State: ``run[3, dim]`` float64 on device = ``(n, mean, S)``; ``running_ms`` exposes the reference's ``n / mean / S /
+std`` names (``std = mean`` while ``n == 1``, sic).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+EPS = 1e-8  # utils/classes.py:654
+
+
+class _RunningView:
+    """``Normalization.running_ms`` with the reference's attribute names, read from / written to the device state."""
+
+    def __init__(self, owner: "Normalization"):
+        self._o = owner
+
+    @property
+    def n(self):
+        return float(self._o._run[0, 0].item())
+
+    @n.setter
+    def n(self, v):
+        self._o._run[0].fill_(float(np.asarray(v).reshape(-1)[0]))
+
+    @property
+    def mean(self):
+        return self._o._run[1].cpu().numpy().copy()
+
+    @mean.setter
+    def mean(self, v):
+        self._o._run[1].copy_(torch.as_tensor(np.asarray(v, dtype=np.float64).reshape(-1)))
+
+    @property
+    def S(self):
+        return self._o._run[2].cpu().numpy().copy()
+
+    @S.setter
+    def S(self, v):
+        self._o._run[2].copy_(torch.as_tensor(np.asarray(v, dtype=np.float64).reshape(-1)))
+
+    @property
+    def std(self):
+        n, mean, S = self.n, self.mean, self.S
+        if n == 1:
+            return mean  # `self.std = x` (utils/classes.py:637-639)
+        return np.sqrt(S / n) if n > 0 else np.zeros_like(S)
+
+    @std.setter
+    def std(self, v):  # derived from (n, S); accepted for load_norm_normalizer_from_file compatibility
+        pass
+
+
+class Normalization:
+    """``Normalization(shape)`` of utils/classes.py:646-656 for ``[dim, N]`` field-major batches on one CUDA device."""
+
+    def __init__(self, shape: int, device="cuda", sync: bool = True, group=None):
+        self._lib = _lib.load()
+        self.dim = int(shape)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.B200EnvError("the engine has no CPU path: device must be a CUDA device")
+        self.sync, self.group = bool(sync), group
+        self._run = torch.zeros(3, self.dim, dtype=torch.float64, device=self.device)
+        self._run_next = torch.zeros_like(self._run)
+        self._batch = torch.zeros(1, 3, self.dim, dtype=torch.float64, device=self.device)
+        self._gathered = None
+        self._scratch = torch.zeros(self._lib.b200_norm_scratch_bytes(self.dim), dtype=torch.uint8, device=self.device)
+        self.running_ms = _RunningView(self)
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _code(t: torch.Tensor) -> int:
+        if t.dtype == torch.float64:
+            return _lib.F64
+        if t.dtype == torch.float32:
+            return _lib.F32
+        raise ValueError("normalisation input must be float32 or float64")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _world(self) -> int:
+        import torch.distributed as dist
+        if self.sync and dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group)
+        return 1
+
+    # ------------------------------------------------------------------ hot call
+    def normalize_soa(self, x: torch.Tensor, update: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``x``: contiguous ``[dim, N]`` (or ``[N]`` when dim == 1) CUDA tensor; returns the normalised batch (``out``
+        or a new tensor).  One statistics launch + one merge/apply launch; no host synchronisation."""
+        if x.dim() == 1:
+            x = x.view(1, -1)
+        if not (x.is_cuda and x.is_contiguous() and x.shape[0] == self.dim):
+            raise ValueError(f"normalize_soa: expected a contiguous CUDA [{self.dim}, N] tensor")
+        code, n = self._code(x), x.shape[1]
+        y = torch.empty_like(x) if out is None else out.view_as(x)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            nb, batch = 0, self._batch
+            if update:
+                _lib.check(self._lib.b200_norm_batch_stats(code, n, self.dim, p(x), p(self._run), p(self._batch),
+                                                           p(self._scratch), self._stream()), "b200_norm_batch_stats")
+                nb = 1
+                w = self._world()
+                if w > 1:
+                    import torch.distributed as dist
+                    if self._gathered is None or self._gathered.shape[0] != w:
+                        self._gathered = torch.zeros(w, 3, self.dim, dtype=torch.float64, device=self.device)
+                    dist.all_gather_into_tensor(self._gathered, self._batch, group=self.group)
+                    nb, batch = w, self._gathered
+            _lib.check(self._lib.b200_norm_merge_apply(code, n, self.dim, p(x), p(y), p(batch), nb, p(self._run),
+                                                       p(self._run_next), 1 if update else 0, EPS, self._stream()),
+                       "b200_norm_merge_apply")
+            if update:
+                self._run, self._run_next = self._run_next, self._run
+        return y
+
+    def __call__(self, x, update: bool = True):
+        """Reference call shape: ``x`` is ``[N, dim]`` (or ``[N]`` / a scalar batch for dim == 1); returns the same
+        orientation.  ``[dim, N]`` views of the engine's SoA buffers (``env.current_state`` is such a view) are used in
+        place, without a transpose copy."""
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(np.asarray(x, dtype=np.float64), device=self.device)
+        if x.dim() == 0:
+            x = x.view(1)
+        if x.dim() == 1:
+            if self.dim == 1:
+                return self.normalize_soa(x.contiguous().view(1, -1), update).view(-1)
+            return self.normalize_soa(x.contiguous().view(self.dim, 1), update).view(-1)  # one sample of `dim` features
+        if x.shape[1] != self.dim:
+            raise ValueError(f"expected [N, {self.dim}], got {tuple(x.shape)}")
+        soa = x.t() if x.t().is_contiguous() else x.t().contiguous()
+        return self.normalize_soa(soa, update).t()
+
+    def seq(self, x: torch.Tensor, update: bool = True) -> torch.Tensor:
+        """The reference recurrence over ``rows`` samples fed one by one: ``x`` is ``[dim, rows]`` contiguous."""
+        if x.dim() == 1:
+            x = x.view(1, -1)
+        if not (x.is_cuda and x.is_contiguous() and x.shape[0] == self.dim):
+            raise ValueError(f"seq: expected a contiguous CUDA [{self.dim}, rows] tensor")
+        y = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b200_norm_seq(self._code(x), x.shape[1], self.dim, C.c_void_p(x.data_ptr()),
+                                               C.c_void_p(y.data_ptr()), C.c_void_p(self._run.data_ptr()),
+                                               1 if update else 0, EPS, self._stream()), "b200_norm_seq")
+        return y
+
+    # ------------------------------------------------------------------ state
+    def state_dict(self) -> dict:
+        return {"run": self._run.clone()}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self._run.copy_(sd["run"].to(self.device, torch.float64))
+
+
+def merge_stats_reference(run, batches):
+    """Host restatement (numpy float64) of the merge rule of csrc/norm.cu, for tests and offline tooling:
+    ``run`` = (n, mean, S) arrays, ``batches`` = iterable of (count, mean, M2)."""
+    n, mean, S = (np.array(a, dtype=np.float64, copy=True) for a in run)
+    for nb, mb, Mb in batches:
+        nb, mb, Mb = (np.asarray(a, dtype=np.float64) for a in (nb, mb, Mb))
+        first = n <= 0
+        tot = n + nb
+        delta = mb - mean
+        new_mean = np.where(first, mb, mean + delta * nb / np.where(tot > 0, tot, 1))
+        S = np.where(first, Mb, (S + Mb) + delta * (mb - new_mean) * nb)
+        n, mean = tot, new_mean
+    return n, mean, S

@@ -33,6 +33,7 @@ def env_specs():
         "cartpole_angleonly_ppo2": (rlp.CartPoleAngleOnly, {"variant": "ppo2"}),
         "fas": (rlp.Flight_Attitude_Simulator, {}),
         "fas_ppo2": (rlp.Flight_Attitude_Simulator, {"variant": "ppo2"}),
+        "fas_discrete": (rlp.FlightAttitudeSimulatorDiscrete, {}),
         "soi": (rlp.SecondOrderIntegration, {}),
         "soi_dppo2": (rlp.SecondOrderIntegration, {"variant": "dppo2"}),
         "ballbalancer": (rlp.BallBalancer1D, {}),
@@ -196,7 +197,7 @@ ENGINE_TOL = {
     "cartpole": 1e-9, "cartpole_gentle": 1e-9, "cartpole_angleonly_env": 1e-9, "cartpole_angleonly_ppo2": 1e-9,
     "uav_pos": 1e-7, "uav_pos_dis": 1e-9, "uav_pos_crash": 1e-9, "uav_pos_edge": 1e-9,
     "uav_att": 1e-9, "uav_att_rand": 1e-9, "uav_att_edge": 1e-9,
-    "fas": 1e-9, "fas_ppo2": 1e-9, "soi": 1e-9, "soi_dppo2": 1e-9, "ballbalancer": 1e-9, "twolink": 1e-5,
+    "fas": 1e-9, "fas_ppo2": 1e-9, "fas_discrete": 1e-9, "soi": 1e-9, "soi_dppo2": 1e-9, "ballbalancer": 1e-9, "twolink": 1e-5,
     "ugv_forward": 1e-9, "ugv_bidirectional": 1e-9, "ugvo": 1e-9, "ugvo_dppo2": 1e-9,
     "uavr_hover_outer": 1e-7, "uavr_hover": 1e-7, "uavr_inner": 1e-7, "uavr_tracking": 1e-7,
 }
@@ -276,7 +277,7 @@ def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None
 FP32_TOL = {
     "cartpole": (2e-6, 1e-5), "cartpole_gentle": (2e-6, None), "cartpole_angleonly_env": (2e-6, 1e-5),
     "cartpole_angleonly_ppo2": (2e-6, 1e-5),
-    "fas": (2e-6, 1e-5), "fas_ppo2": (2e-6, 1e-5), "soi": (1e-6, 5e-6), "soi_dppo2": (1e-6, 5e-6),
+    "fas": (2e-6, 1e-5), "fas_ppo2": (2e-6, 1e-5), "fas_discrete": (2e-6, 2e-5), "soi": (1e-6, 5e-6), "soi_dppo2": (1e-6, 5e-6),
     "ballbalancer": (4e-6, 3e-4), "twolink": (1e-5, None),
     "ugv_forward": (4e-5, 4e-5), "ugv_bidirectional": (2e-5, 2e-5),
     "uav_att": (3e-6, 5e-6), "uav_att_rand": (3e-6, 5e-6), "uav_att_edge": (3e-6, 5e-6),
