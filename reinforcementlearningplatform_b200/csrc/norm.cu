@@ -94,8 +94,9 @@ norm_batch_stats_kernel(int64_t n, int dim, const TX *__restrict__ x, const doub
         const double cnt = (double)n;
         const double dm = a / cnt;
         batch[f] = cnt;
-        batch[dim + f] = pivot + dm;
-        batch[2 * dim + f] = fmax(b - a * dm, 0.0);
+        // a one-sample batch is the sample itself (pivot + (x - pivot) would round): keeps N = 1 on the reference's bits
+        batch[dim + f] = n == 1 ? (double)xf[0] : pivot + dm;
+        batch[2 * dim + f] = n == 1 ? 0.0 : fmax(b - a * dm, 0.0);
         ticket[f] = 0u; // ready for the next launch
     }
 }

@@ -86,4 +86,4 @@ def test_rollout_collect_equals_step_by_step(name):
         assert torch.equal(getattr(b1, f), getattr(b2, f)), (name, f)
     assert torch.equal(e1._state, e2._state) and torch.equal(e1._time, e2._time) and torch.equal(e1._episode, e2._episode)
     assert torch.equal(e1.policy_state, e2.policy_state)
-    assert int(b1.done.sum()) > 0 or name in ("uav_att_rand", "twolink", "ballbalancer", "ugv_forward", "soi")
+    assert int(b1.done.sum()) > 0 or name in ("uav_att_rand", "twolink", "ballbalancer", "ugv_forward", "soi", "fas_discrete")
