@@ -163,8 +163,11 @@ typedef struct b200_uav_params {
     double traj_A_hi[4];                /* random trajectory: A ~ U(0, hi)   uav_att_ctrl.py:157-159 / uav_pos_ctrl.py:405-406 */
     double traj_T_lo, traj_T_hi;        /* random trajectory: T ~ U(lo, hi)  uav_att_ctrl.py:160 / uav_pos_ctrl.py:407 */
     double traj_phase_hi;               /* att: phi0 ~ U(0, pi/2) uav_att_ctrl.py:161; pos: unused (phi0 fixed) */
+    double init_pos_r[3];               /* random_pos0: admissible radius r = 0.3 * ones(3)              uav_pos_ctrl.py:512 */
     int32_t random_trajectory;          /* reset_..._tracking(random_trajectory=...) */
     int32_t yaw_fixed;
+    int32_t random_pos0;                /* position env, layout variant 1 only: reset_uav_pos_ctrl(random_pos0=True) */
+    int32_t pad_;
 } b200_uav_params;
 
 /* state fields, attitude env: phi theta psi p q r | s1[3] | k1[3] k2[3] gamma[3] lmd[3] | A[3] T[3] phase[3] | ref[3] dot_ref[3] */
@@ -172,6 +175,12 @@ typedef struct b200_uav_params {
 /* state fields, position env: x y z vx vy vz phi theta psi p q r | sigma_o1[3] | s1[3] | att_ref[3] |
  *                             k1[3] k2[3] gamma[3] lmd[3] | A[4] T[4] phase[4] | pos_ref[3] dot_pos_ref[3] */
 #define B200_UAV_POS_STATE_FIELDS 51
+/* Layout variant 1 of the position env (b200env_dims(B200ENV_UAV_POS, 1)) appends next_pqr0[3], the reference's
+ * `init_state[9:12]`: with random_pos0=True every reset draws pos0 ~ U(trajectory[0] - r, trajectory[0] + r)
+ * (set_random_init_pos, uav_pos_ctrl.py:457-465,510-513) and, because init_state = concat(pos0, vel0, angle0, pos0)
+ * (uav.py:268, note N5), loads p, q, r from the pos0 of the PREVIOUS reset.  Reproduced as is; the three fields are
+ * only touched by resets. */
+#define B200_UAV_POS_STATE_FIELDS_V1 54
 /* `ref/dot_ref` (att) and `pos_ref/dot_pos_ref` (pos) are only stored on a terminal step without auto-reset and read by
  * b200env_reset / b200env_observe: the reference's reset does not clear them, so the first observation of the next
  * episode is taken against the previous episode's last reference (uav_att_ctrl.py:187-216, uav_pos_ctrl.py:488-533). */

@@ -337,7 +337,7 @@ void orc_uav_att_reset_one(const void *params, const oracle_io *io, int64_t n, i
 
 /* ------------------------------------------------------------------ position env */
 enum { P_SIG = 12, P_S1 = 15, P_AREF = 18, P_K1 = 21, P_K2 = 24, P_GAM = 27, P_LMD = 30, P_AMP = 33, P_PER = 37,
-       P_PHS = 41, P_PREF = 45, P_DPREF = 48 };
+       P_PHS = 41, P_PREF = 45, P_DPREF = 48, P_NEXT_PQR0 = 51 /* layout variant 1 */ };
 
 static void pos_draw_reset(const P *p, const oracle_io *io, int64_t n, int64_t i, uint64_t seed, int64_t off) {
     uint32_t ep = io->episode[i];
@@ -347,9 +347,9 @@ static void pos_draw_reset(const P *p, const oracle_io *io, int64_t n, int64_t i
         SF(P_K1 + k) = p->pos_k1[k]; SF(P_K2 + k) = p->pos_k2[k];
         SF(P_GAM + k) = p->pos_gamma[k]; SF(P_LMD + k) = p->pos_lmd[k];
     }
+    orc_rng g;
+    orc_rng_init(&g, seed, (uint64_t)(off + i), ep);
     if (p->random_trajectory) { /* uav_pos_ctrl.py:404-408 */
-        orc_rng g;
-        orc_rng_init(&g, seed, (uint64_t)(off + i), ep);
         double a = orc_uniform(&g, 0., p->traj_A_hi[0]);
         double T = orc_uniform(&g, p->traj_T_lo, p->traj_T_hi);
         for (int k = 0; k < 3; ++k) SF(P_AMP + k) = a;
@@ -361,6 +361,16 @@ static void pos_draw_reset(const P *p, const oracle_io *io, int64_t n, int64_t i
         }
     }
     if (p->yaw_fixed) { SF(P_AMP + 3) = 0.; SF(P_PHS + 3) = 0.; }
+    if (p->random_pos0) { /* uav_pos_ctrl.py:510-513, set_random_init_pos :457-465, reset_uav_with_param uav.py:252-268 */
+        for (int k = 0; k < 3; ++k) {
+            double t0 = p->ref_bias_a[k] + SF(P_AMP + k) * sin(SF(P_PHS + k)); /* trajectory[0][k], :386-390 at t = 0 */
+            double r = fabs(p->init_pos_r[k]);
+            double pos0 = orc_uniform(&g, t0 - r, t0 + r);
+            SF(k) = pos0;
+            SF(9 + k) = SF(P_NEXT_PQR0 + k); /* pqr0 = init_state[9:12] = previous pos0 (N5) */
+            SF(P_NEXT_PQR0 + k) = pos0;      /* init_state = concatenate((pos0, vel0, angle0, pos0)) uav.py:268 */
+        }
+    }
     /* att_ref is NOT reset by the reference (uav_pos_ctrl.py:488-533) */
     io->time[i] = 0.;
     io->episode[i] = ep + 1u;

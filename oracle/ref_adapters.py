@@ -199,6 +199,27 @@ class UavPosDisA(UavPosA):
     with_dis = True
 
 
+class UavPosRandomPos0A(UavPosA):
+    """reset_uav_pos_ctrl(random_pos0=True): uav_pos_ctrl.py:510-513, set_random_init_pos :457-465, uav.py:252-268.
+    State layout variant 1: the trailing 3 fields are the reference's init_state[9:12] (note N5)."""
+    name = "uav_pos_rp0"
+    F = 54
+
+    def reset(self, env):
+        _zero(self.pos)
+        env.reset_uav_pos_ctrl_RL_tracking(random_trajectroy=True, random_pos0=True, new_att_ctrl_param=None,
+                                           new_pos_ctrl_parma=self.pos, outer_param=None)
+
+    def internal(self, env):
+        s, t = super().internal(env)
+        return np.concatenate((s, np.array(env.init_state[9:12], dtype=float))), t
+
+    def sample_action(self, rng, t, l, env=None):
+        if l % 2 == 0:  # weak random gains: short episodes, many resets (each loads p, q, r from the previous pos0)
+            return rng.uniform(0., 1.0, 8)
+        return super().sample_action(rng, t, 1, env)
+
+
 class UavAttA(Adapter):
     """Loop body of PPO2-4-UavFntsmcParamAtt/train.py:254-276 around uav_att_ctrl_RL."""
     name = "uav_att"
@@ -255,6 +276,7 @@ class UavAttRandA(UavAttA):
 
 REGISTRY.update({
     "uav_pos": (UavPosA, 6, 1000, 21),
+    "uav_pos_rp0": (UavPosRandomPos0A, 4, 600, 28),
     "uav_pos_dis": (UavPosDisA, 3, 1000, 22),
     "uav_att": (UavAttA, 6, 1000, 23),
     "uav_att_rand": (UavAttRandA, 3, 1000, 24),

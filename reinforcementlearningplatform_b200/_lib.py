@@ -70,7 +70,8 @@ class UavParams(C.Structure):
         _d("Q_e", 3), _d("Q_de", 3), _d("R", 3),
         _d("ref_amplitude", 4), _d("ref_period", 4), _d("ref_bias_a", 4), _d("ref_bias_phase", 4),
         _d("dot_att_ref_limit"), _d("att_limit"), _d("traj_A_hi", 4), _d("traj_T_lo"), _d("traj_T_hi"),
-        _d("traj_phase_hi"), ("random_trajectory", C.c_int32), ("yaw_fixed", C.c_int32)]
+        _d("traj_phase_hi"), _d("init_pos_r", 3), ("random_trajectory", C.c_int32), ("yaw_fixed", C.c_int32),
+        ("random_pos0", C.c_int32), ("pad_", C.c_int32)]
 
 
 def _struct(name, doc, doubles, ints=()):

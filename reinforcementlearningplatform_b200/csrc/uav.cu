@@ -230,7 +230,7 @@ uav_att_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200en
 
 // ------------------------------------------------------------------------------------------ position env
 enum { P_SIG = 12, P_S1 = 15, P_AREF = 18, P_K1 = 21, P_K2 = 24, P_GAM = 27, P_LMD = 30, P_AMP = 33, P_PER = 37,
-       P_PHS = 41, P_PREF = 45, P_DPREF = 48 };
+       P_PHS = 41, P_PREF = 45, P_DPREF = 48, P_NEXT_PQR0 = 51 /* layout variant 1 only */ };
 
 template <typename T, typename I>
 __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io, I n, I i, uint64_t seed,
@@ -248,8 +248,8 @@ __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io
         st<T>(io.state, n, P_LMD + k, i, (T)p.pos_lmd[k]);
     }
     double A[4], Tp[4], ph[4];
+    Philox rng(seed, (uint64_t)(off + (int64_t)i), ep);
     if (p.random_trajectory) { // uav_pos_ctrl.py:404-408
-        Philox rng(seed, (uint64_t)(off + (int64_t)i), ep);
         const double a = rng.uniform(0., p.traj_A_hi[0]);
         const double tt = rng.uniform(p.traj_T_lo, p.traj_T_hi);
         A[0] = A[1] = A[2] = a; A[3] = 0.;
@@ -265,6 +265,20 @@ __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io
         st<T>(io.state, n, P_AMP + k, i, (T)A[k]);
         st<T>(io.state, n, P_PER + k, i, (T)Tp[k]);
         st<T>(io.state, n, P_PHS + k, i, (T)ph[k]);
+    }
+    if (p.random_pos0) { // uav_pos_ctrl.py:510-513 -> set_random_init_pos :457-465 -> reset_uav_with_param uav.py:252-268
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            // trajectory[0][k] = bias_a + A sin(2 pi / T * 0 + phase)                       uav_pos_ctrl.py:386-390
+            const double t0 = p.ref_bias_a[k] + A[k] * ::sin(ph[k]);
+            const double r = ::fabs(p.init_pos_r[k]);
+            const double pos0 = rng.uniform(t0 - r, t0 + r);
+            x[k] = (T)pos0;
+            x[9 + k] = ld<T>(io.state, n, P_NEXT_PQR0 + k, i); // new_param.pqr0 = init_state[9:12] = the previous pos0 (N5)
+            st<T>(io.state, n, k, i, x[k]);
+            st<T>(io.state, n, 9 + k, i, x[9 + k]);
+            st<T>(io.state, n, P_NEXT_PQR0 + k, i, x[k]);      // init_state = concat(pos0, vel0, angle0, pos0)
+        }
     }
     // att_ref is not reset by the reference (uav_pos_ctrl.py:488-533): left as stored
     io.time[i] = 0.0;
@@ -504,8 +518,8 @@ int uav_att_dims(int variant, int *sf, int *od, int *ad, int *dd) {
     return B200ENV_OK;
 }
 int uav_pos_dims(int variant, int *sf, int *od, int *ad, int *dd) {
-    if (variant != 0) return B200ENV_EENV;
-    if (sf) *sf = B200_UAV_POS_STATE_FIELDS;
+    if (variant != 0 && variant != 1) return B200ENV_EENV;
+    if (sf) *sf = variant == 1 ? B200_UAV_POS_STATE_FIELDS_V1 : B200_UAV_POS_STATE_FIELDS;
     if (od) *od = 6;
     if (ad) *ad = 8;
     if (dd) *dd = 3;
@@ -531,7 +545,7 @@ int uav_pos_step(int dtype, int64_t n, const void *params, const b200env_io *io,
     int rc = uav_check_step(io, flags);
     if (rc) return rc;
     const P &p = *static_cast<const P *>(params);
-    UAV_LAUNCH_STEP(uav_pos_step_kernel, B200_UAV_POS_STATE_FIELDS, b200_grid(n), p, uav_derive(p.m, p.J, p.kt), *io, n, flags, seed, off);
+    UAV_LAUNCH_STEP(uav_pos_step_kernel, B200_UAV_POS_STATE_FIELDS_V1, b200_grid(n), p, uav_derive(p.m, p.J, p.kt), *io, n, flags, seed, off);
     return b200_check_launch();
 }
 int uav_att_reset(int dtype, int64_t n, const void *params, const b200env_io *io, const uint8_t *mask, uint64_t seed,

@@ -142,6 +142,64 @@ class _UavBase(VecEnvBase):
         p.dot_att_ref_limit = 60. * np.pi / 180.              # uav_pos_ctrl.py:25
         p.att_limit = np.pi / 4                               # uav_pos_ctrl.py:314
 
+    # ------------------------------------------------------------------ reference method names (host side, not hot)
+    K1_SCALE, K2_DIV = 1.0, 1.0     # get_param_from_actor scaling of the first six actor outputs
+    _GAIN_FIELDS = ("k1_0", "k2_0", "gamma_0", "lmd_0")
+
+    def get_param_from_actor(self, action_from_actor) -> None:
+        """``get_param_from_actor`` on its own (uav_pos_ctrl_RL.py:158-173, uav_att_ctrl_RL.py:141-156): overwrite the
+        per-instance gains where the actor output is > 0.  ``step_update(a8)`` already fuses this; the separate call
+        exists for scripts that set gains once and then run the controller with them (``step_fixed_gains``)."""
+        a = self._as_soa(action_from_actor, 8).to(self.dtype)
+        k1, k2, gm, ld = (self.STATE_FIELDS.index(f) for f in self._GAIN_FIELDS)
+        st = self._state
+        for i in range(3):
+            st[k1 + i] = torch.where(a[i] > 0, a[i] * self.K1_SCALE, st[k1 + i])
+            st[k2 + i] = torch.where(a[3 + i] > 0, a[3 + i] / self.K2_DIV, st[k2 + i])
+            st[gm + i] = torch.where(a[6] > 0, a[6], st[gm + i])
+            st[ld + i] = torch.where(a[7] > 0, a[7], st[ld + i])
+
+    def step_fixed_gains(self, dis=None) -> None:
+        """One control period with the gains currently stored per instance: ``generate_action_4_uav()`` /
+        ``att_control()`` + ``step_update()`` of the reference's non-RL scripts (test_pos_tracking_ctrl.py:66-102).
+        An all-zero actor output leaves every gain untouched (note N6), so this is the same fused kernel."""
+        if getattr(self, "_zero_action", None) is None:
+            self._zero_action = torch.zeros(8, self.n_envs, dtype=self.io_dtype, device=self.device)
+        d = None if dis is None else self._as_soa(dis, self._dd)
+        self.step_soa(self._zero_action, d)
+
+    @property
+    def current_state_norm(self):
+        """``Normalization(state_dim)`` applied by the train loop to ``current_state`` (uav_pos_ctrl_RL.py:36,
+        PPO2-4-UavFntsmcParamPos/train.py:291); device-resident, see normalization.py."""
+        if getattr(self, "_cur_norm", None) is None:
+            from ..normalization import Normalization
+            self._cur_norm = Normalization(self.state_dim, device=self.device)
+        return self._cur_norm
+
+    @property
+    def next_state_norm(self):
+        if getattr(self, "_next_norm", None) is None:
+            from ..normalization import Normalization
+            self._next_norm = Normalization(self.state_dim, device=self.device)
+        return self._next_norm
+
+    _NORM_COLS = ("cur_n", "cur_mean", "cur_std", "cur_S", "next_n", "next_mean", "next_std", "next_S")
+
+    def save_state_norm(self, path, msg=None):
+        """Same CSV as uav_pos_ctrl_RL.py:208-222 (columns cur_n, cur_mean, cur_std, cur_S, next_n, ...)."""
+        c, x = self.current_state_norm.running_ms, self.next_state_norm.running_ms
+        cols = [c.n * np.ones(self.state_dim), c.mean, c.std, c.S, x.n * np.ones(self.state_dim), x.mean, x.std, x.S]
+        name = path + ('state_norm.csv' if msg is None else 'state_norm_' + msg + '.csv')
+        np.savetxt(name, np.stack(cols, axis=1), delimiter=',', header=','.join(self._NORM_COLS), comments='', fmt='%.17g')
+
+    def load_norm_normalizer_from_file(self, path, file):
+        """uav_pos_ctrl_RL.py:224-233; reads the reference's own ``state_norm.csv`` files."""
+        data = np.atleast_2d(np.genfromtxt(path + file, delimiter=',', skip_header=1))
+        c, x = self.current_state_norm.running_ms, self.next_state_norm.running_ms
+        c.n, c.mean, c.S = data[0, 0], data[:, 1], data[:, 3]
+        x.n, x.mean, x.S = data[0, 4], data[:, 5], data[:, 7]
+
     # reference attribute names
     @property
     def time_max(self):
@@ -156,6 +214,7 @@ class UavAttCtrlRL(_UavBase):
     """``uav_att_ctrl_RL`` (uav_att_ctrl_RL.py:10-178): attitude tracking, obs = (att - ref, Euler rate - ref rate),
     action = 8 gains in [0, 3] (k1 x10, k2 /10 as in get_param_from_actor :141-156)."""
     ENV_ID = _lib.UAV_ATT
+    K1_SCALE, K2_DIV = 10.0, 10.0   # k1 = 10 a, k2 = a / 10 (uav_att_ctrl_RL.py:149-152)
     TIMEOUT_FLAG = 1  # success = done and flag != 1 (PPO2-4-UavFntsmcParamPos/train.py:299-302, ...Att/train.py:278)
     STATE_FIELDS = tuple("phi theta psi p q r s1_0 s1_1 s1_2 k1_0 k1_1 k1_2 k2_0 k2_1 k2_2 gamma_0 gamma_1 gamma_2 "
                          "lmd_0 lmd_1 lmd_2 A_0 A_1 A_2 T_0 T_1 T_2 phase_0 phase_1 phase_2 "
@@ -208,7 +267,15 @@ class UavPosCtrlRL(_UavBase):
                          "pref_0 pref_1 pref_2 dpref_0 dpref_1 dpref_2".split())
 
     def __init__(self, n_envs: int = 1, _uav_param: uav_param = None, _uav_att_param: fntsmc_param = None,
-                 _uav_pos_param: fntsmc_param = None, random_trajectory: bool = True, yaw_fixed: bool = False, **kw):
+                 _uav_pos_param: fntsmc_param = None, random_trajectory: bool = True, yaw_fixed: bool = False,
+                 random_pos0: bool = False, **kw):
+        """``random_pos0``: ``reset_uav_pos_ctrl(random_pos0=True)`` (uav_pos_ctrl.py:510-513): every reset starts the
+        quadrotor within +-0.3 m of the first trajectory point; selects state layout variant 1 (3 extra fields holding
+        the reference's ``init_state[9:12]``, from which the NEXT reset loads p, q, r -- note N5, reproduced)."""
+        self.random_pos0 = bool(random_pos0)
+        if self.random_pos0:
+            self.VARIANT = 1
+            self.STATE_FIELDS = type(self).STATE_FIELDS + ("next_pqr0_0", "next_pqr0_1", "next_pqr0_2")
         self._uav_param = _uav_param or train_uav_param('pos')
         self._att_param = _uav_att_param or train_att_ctrl_param()
         self._pos_param = _uav_pos_param or zero_gains(train_pos_ctrl_param())
@@ -220,6 +287,9 @@ class UavPosCtrlRL(_UavBase):
         self.Q_vel = np.array([0.05, 0.05, 0.05])
         self.R = np.array([0.01, 0.01, 0.01])
         super().__init__(n_envs, **kw)
+        if self.random_pos0 and not self.host_only:  # init_state[9:12] = pos0 of the constructor (uav.py:64)
+            for k in range(3):
+                self._state[51 + k].fill_(float(self._params.init_state[9 + k]))
         self.action_range = [[0, 5.0] for _ in range(8)]  # uav_pos_ctrl_RL.py:44
 
     def make_params(self):
@@ -243,4 +313,6 @@ class UavPosCtrlRL(_UavBase):
         _set3(p.traj_A_hi, [1.5, 1.5, 1.5, 0.])
         p.traj_T_lo, p.traj_T_hi, p.traj_phase_hi = 5, 10, 0.
         p.random_trajectory, p.yaw_fixed = int(self.random_trajectory), int(self.yaw_fixed)
+        p.random_pos0 = int(self.random_pos0)
+        _set3(p.init_pos_r, 0.3 * np.ones(3))                 # uav_pos_ctrl.py:512
         return p

@@ -16,7 +16,7 @@ CASES = {
     "fas": 0.0, "fas_ppo2": 0.0, "fas_discrete": 0.0, "soi": 1e-15, "soi_dppo2": 1e-15, "ballbalancer": 1e-12, "twolink": 1e-12,
     "ugv_forward": 1e-12, "ugv_bidirectional": 1e-12, "ugvo": 1e-12, "ugvo_dppo2": 1e-12,
     "uavr_hover_outer": 1e-12, "uavr_hover": 1e-12, "uavr_inner": 1e-12, "uavr_tracking": 1e-12,
-    "uav_pos": 1e-12, "uav_pos_dis": 1e-12, "uav_pos_crash": 1e-12, "uav_pos_edge": 1e-12,
+    "uav_pos": 1e-12, "uav_pos_dis": 1e-12, "uav_pos_rp0": 1e-12, "uav_pos_crash": 1e-12, "uav_pos_edge": 1e-12,
     "uav_att": 1e-12, "uav_att_rand": 1e-12, "uav_att_edge": 1e-12,
 }
 
@@ -34,3 +34,40 @@ def test_oracle_matches_reference_fixture(name, resync, oracle_lib):
     else:
         # free-running: within 1e4 x the reference's own drift under one-ulp nudges (floor 1e-12), see helpers.replay
         assert res["worst_ratio"] <= 1.0, res
+
+
+def test_random_pos0_reset_quirk_fixture_and_oracle(oracle_lib):
+    """reset_uav_pos_ctrl(random_pos0=True), note N5: the reference loads p, q, r from the pos0 of the PREVIOUS reset
+    (init_state = concat(pos0, vel0, angle0, pos0), uav.py:268).  Shown on the recorded fixture, then on the C
+    restatement's own Philox resets: pos0 within 0.3 m of the trajectory start, p, q, r = previous pos0."""
+    import numpy as np
+    from oracle import oracle
+    from reinforcementlearningplatform_b200 import _lib
+    import reinforcementlearningplatform_b200 as rlp
+    g = load_golden("uav_pos_rp0")
+    T, L = g["reward"].shape
+    seen = 0
+    for l in range(L):
+        prev_pos0 = g["state0"][l, 0:3]
+        assert np.array_equal(g["state0"][l, 51:54], prev_pos0)
+        for t in np.where(g["done"][:, l])[0]:
+            rs = g["reset_state"][t, l]
+            assert np.array_equal(rs[9:12], prev_pos0)          # p, q, r <- previous pos0
+            assert np.array_equal(rs[51:54], rs[0:3])           # init_state[9:12] <- the new pos0
+            traj0 = np.array([0.0, 0.0, 1.5]) + rs[33:36] * np.sin(rs[41:44])
+            assert np.all(np.abs(rs[0:3] - traj0) <= 0.3 + 1e-12)
+            prev_pos0 = rs[0:3].copy()
+            seen += 1
+    assert seen >= 3
+    host = rlp.UavPosCtrlRL(n_envs=64, host_only=True, random_trajectory=True, random_pos0=True)
+    sf, od, ad, dd = _lib.dims(_lib.UAV_POS, 1)
+    assert sf == 54
+    orc = oracle.OracleEnv(_lib.UAV_POS, host._params, 64, sf, od, ad, dd, seed=3)
+    orc.reset()
+    first = orc.state[0:3].copy()
+    assert np.all(orc.state[9:12] == 0.0)
+    traj0 = np.array([0.0, 0.0, 1.5])[:, None] + orc.state[33:36] * np.sin(orc.state[41:44])
+    assert np.all(np.abs(first - traj0) <= 0.3 + 1e-12) and np.std(first) > 0.05
+    orc.reset()
+    assert np.array_equal(orc.state[9:12], first)
+    assert np.array_equal(orc.state[51:54], orc.state[0:3]) and not np.array_equal(orc.state[0:3], first)
