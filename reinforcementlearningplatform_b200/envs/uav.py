@@ -153,9 +153,12 @@ class _UavBase(VecEnvBase):
         a = self._as_soa(action_from_actor, 8).to(self.dtype)
         k1, k2, gm, ld = (self.STATE_FIELDS.index(f) for f in self._GAIN_FIELDS)
         st = self._state
+        # a device-side divisor: torch turns division by a host scalar into a multiplication by its reciprocal,
+        # which is not the IEEE quotient `a / 10` of the reference (and of the fused kernel)
+        k2_div = torch.full((), self.K2_DIV, dtype=self.dtype, device=self.device)
         for i in range(3):
             st[k1 + i] = torch.where(a[i] > 0, a[i] * self.K1_SCALE, st[k1 + i])
-            st[k2 + i] = torch.where(a[3 + i] > 0, a[3 + i] / self.K2_DIV, st[k2 + i])
+            st[k2 + i] = torch.where(a[3 + i] > 0, a[3 + i] / k2_div, st[k2 + i])
             st[gm + i] = torch.where(a[6] > 0, a[6], st[gm + i])
             st[ld + i] = torch.where(a[7] > 0, a[7], st[ld + i])
 
