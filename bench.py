@@ -40,6 +40,13 @@ ALGO_BYTES = {
     "ugvo": (5 * 2 + 3 + 48 + 2 + 2 + 41 + 41 + 1) * 8 + 5,
     "soi": (4 * 2 + 2 + 2 + 4 + 4 + 1) * 8 + 5,
     "fas": (2 * 2 + 1 + 2 + 2 + 2 + 1) * 8 + 5,
+    # generic families: state fields R+W, action R, time R+W, next_obs + policy obs W, reward W (8 B each) + done + flag
+    "fas_discrete": (2 * 2 + 1 + 2 + 2 + 2 + 1) * 8 + 5,
+    "ballbalancer": (4 * 2 + 1 + 2 + 3 + 3 + 1) * 8 + 5,
+    "twolink": (8 * 2 + 2 + 2 + 6 + 6 + 6 + 1) * 8 + 5,   # + current_state (not a pure function of the state)
+    "ugv": (5 * 2 + 2 + 2 + 4 + 4 + 1) * 8 + 5,
+    # UavRobust hover: 12 ODE + 3 s1 + 3 att_ref + 3 dot_att_ref R+W, 3 pos_ref R, 6 action, time, 3 x 12 obs, reward
+    "uavr_hover": (21 * 2 + 3 + 6 + 2 + 12 * 3 + 1) * 8 + 5,
 }
 # algorithmic fp64 work per env-step (weighted flops, SURVEY.md section 8d convention), used for the fp64-pipe view
 ALGO_FLOPS = {"uav_pos": 5100.0, "uav_att": 3300.0, "cartpole": 3100.0, "ugvo": 54000.0, "soi": 125.0, "fas": 570.0}
@@ -57,6 +64,11 @@ WORKLOADS = {
     "ugvo": dict(n=262144, desc="UGVForwardObstacleAvoidance DPPO2 variant, dt=0.05, 15 circles, 37-ray laser x2 scans/step"),
     "soi": dict(n=1 << 20, desc="SecondOrderIntegration (ENV), RK4 step"),
     "fas": dict(n=1 << 20, desc="Flight_Attitude_Simulator (PPO2 variant), RK4 time-loop step"),
+    "fas_discrete": dict(n=1 << 20, desc="FlightAttitudeSimulatorDiscrete, 2 RK4 steps/period, force from the discrete action set"),
+    "ballbalancer": dict(n=1 << 20, desc="BallBalancer1D, RK4 time-loop step"),
+    "twolink": dict(n=1 << 20, desc="TwoLinkManipulator, RK4 step with in-register 2x2 solve"),
+    "ugv": dict(n=1 << 20, desc="UGVForward, RK4 step"),
+    "uavr_hover": dict(n=1 << 20, desc="UavRobust uav_hover (acceleration + torque actions), dt=0.01"),
 }
 
 
@@ -76,6 +88,10 @@ def make_env(workload, n, device, offset, dtype=torch.float64, host_only=False, 
         return rlp.SecondOrderIntegration(**kw)
     if workload == "fas":
         return rlp.Flight_Attitude_Simulator(variant="ppo2", **kw)
+    simple = {"fas_discrete": rlp.FlightAttitudeSimulatorDiscrete, "ballbalancer": rlp.BallBalancer1D,
+              "twolink": rlp.TwoLinkManipulator, "ugv": rlp.UGVForward, "uavr_hover": rlp.uav_hover}
+    if workload in simple:
+        return simple[workload](**kw)
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -261,7 +277,7 @@ def also_workloads(args, dev, dtype, peaks):
     """Short device-resident measurements of the other single-GPU configs (same timing rules, fewer steps)."""
     out = []
     hbm = peaks.get("hbm_gbs", 6650.0)
-    for w in ("uav_att", "cartpole", "soi", "fas", "ugvo"):
+    for w in ("uav_att", "cartpole", "soi", "fas", "ugvo", "fas_discrete", "ballbalancer", "twolink", "ugv", "uavr_hover"):
         if w == args.workload:
             continue
         n = WORKLOADS[w]["n"]
@@ -399,7 +415,7 @@ def main():
     achieved = algo_bytes / per_launch_s / 1e9
     from reinforcementlearningplatform_b200 import _lib
     fma_peak = _lib.measure_fma_peak(_lib.F64 if el == 8 else _lib.F32)  # TFLOP/s, live, this GPU
-    pipe = {"achieved_tflops_weighted": ALGO_FLOPS[args.workload] * n / per_launch_s / 1e12,
+    pipe = {"achieved_tflops_weighted": ALGO_FLOPS.get(args.workload, float("nan")) * n / per_launch_s / 1e12,
             "peak_tflops_fma": fma_peak, "peak_source": "b200_measure_fma_peak, live (8 independent FMA chains/thread)",
             "note": "weighted = algorithmic flops in the SURVEY 8d convention (transcendentals at fixed weights)"}
     if args.workload in EXEC_F64 and el == 8:

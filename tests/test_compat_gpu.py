@@ -1,0 +1,78 @@
+"""GPU: the single-instance rl_base view (compat.SingleEnv) driven with the call sequence of the reference train loops
+(demonstration/PPO2/PPO2-4-CartPoleAngleOnly/train.py:184-216, PPO2-4-UavFntsmcParamPos/train.py:273-310,
+PPO2-4-UavFntsmcParamAtt/train.py:254-290) on the recorded fixtures: numpy attributes, python scalars, same numbers."""
+import numpy as np
+import pytest
+
+from helpers import env_specs, load_golden, mixed_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _drive(name, lane, steps, uav=None):
+    import reinforcementlearningplatform_b200 as rlp
+    g = load_golden(name)
+    cls, kw = env_specs()[name]
+    env = rlp.single(cls(n_envs=1, **kw))
+    assert isinstance(env.state_dim, int) and np.asarray(env.action_range).shape == (env.action_dim, 2)
+    env.set_state(g["state0"][lane], g["time0"][lane])
+    worst, episodes = 0.0, 0
+    T = min(steps, g["reward"].shape[0])
+    for t in range(T):
+        env.current_state = env.next_state.copy()                      # train.py:193
+        a = g["actions"][t, lane]
+        if uav == "pos":
+            env.get_param_from_actor(a)                                 # Pos/train.py:292
+            action_4_uav = env.generate_action_4_uav()                  # :293
+            env.step_update(action_4_uav)                               # :294
+        elif uav == "att":
+            env.get_param_from_actor(a)                                 # Att/train.py:265
+            torque = env.att_control(None, None, None)                  # :268 (ref_inner is fused into the step)
+            env.step_update([torque[0], torque[1], torque[2]])          # :269
+        else:
+            env.step_update(a)                                          # train.py:195
+        assert isinstance(env.reward, float) and isinstance(env.is_terminal, bool) and isinstance(env.terminal_flag, int)
+        assert env.next_state.dtype == np.float64 and env.next_state.shape == (env.state_dim,)
+        worst = max(worst, mixed_err(env.next_state, g["next_obs"][t, lane]), mixed_err(env.current_state, g["obs"][t, lane]),
+                    mixed_err(np.array([env.reward]), np.array([g["reward"][t, lane]])))
+        assert env.is_terminal == bool(g["done"][t, lane]) and env.terminal_flag == int(g["flag"][t, lane]), (name, t)
+        assert env.time == g["time"][t, lane]
+        if env.is_terminal:                                             # train.py:187-191: the loop resets the env itself
+            episodes += 1
+            env.reset(True)                                             # Philox draw; the fixture's own reset is injected next
+            assert not env.is_terminal and env.reward == 0.0 and env.time == 0.0
+            env.set_state(g["reset_state"][t, lane], g["reset_time"][t, lane])
+    return worst, episodes
+
+
+@pytest.mark.parametrize("name,lane,tol", [("cartpole_angleonly_ppo2", 0, 1e-9), ("cartpole", 1, 1e-9), ("soi", 0, 1e-9),
+                                           ("fas_discrete", 0, 1e-9), ("ugv_forward", 0, 1e-9), ("ugvo_dppo2", 0, 1e-8)])
+def test_single_env_runs_the_reference_loop_shape(name, lane, tol):
+    worst, episodes = _drive(name, lane, 400)
+    assert worst <= tol, (name, worst)
+
+
+def test_single_uav_pos_three_call_protocol():
+    worst, _ = _drive("uav_pos", 1, 300, uav="pos")
+    assert worst <= 1e-9, worst
+
+
+def test_single_uav_att_three_call_protocol():
+    worst, _ = _drive("uav_att_rand", 1, 300, uav="att")
+    assert worst <= 1e-9, worst
+
+
+def test_single_uav_reset_with_new_controller_params():
+    """reset_uav_pos_ctrl_RL_tracking(new_pos_ctrl_parma=...) re-seeds the per-instance gains (Pos/train.py:275-286)."""
+    import reinforcementlearningplatform_b200 as rlp
+    from reinforcementlearningplatform_b200.envs import uav as U
+    env = rlp.single(rlp.UavPosCtrlRL(n_envs=1, random_trajectory=True))
+    par = U.train_pos_ctrl_param()
+    env.reset_uav_pos_ctrl_RL_tracking(random_trajectroy=True, random_pos0=False, new_att_ctrl_param=None,
+                                       new_pos_ctrl_parma=par)
+    st = env._env._state[:, 0].cpu().numpy()
+    i = env.STATE_FIELDS.index("k1_0")
+    assert np.array_equal(st[i:i + 3], par.k1) and np.array_equal(st[i + 3:i + 6], par.k2)
+    assert env.time == 0.0 and not env.is_terminal and env.next_state.shape == (6,)
+    env.step_update(env.generate_action_4_uav())   # no get_param_from_actor: fixed gains (test_pos_tracking_ctrl.py loop)
+    assert np.isfinite(env.reward) and env.time == pytest.approx(0.02)

@@ -1,0 +1,54 @@
+"""Device-resident micro-benchmarks of the scan / normalisation kernels (K-GAE, K-RET, K-NORM) for ncu captures and
+for the `also` block of bench.py.  python tools/microbench.py gae|gae_flags|mc_returns|norm [reps]"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+
+def run(kind, reps=10, T=2048, N=131072, dev="cuda"):
+    import reinforcementlearningplatform_b200 as rlp
+    from reinforcementlearningplatform_b200 import gae as G
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    mk = lambda: torch.randn((T, N), generator=g, device=dev, dtype=torch.float32)
+    if kind in ("gae", "gae_flags", "mc_returns"):
+        r, vs, vsn = mk(), mk(), mk()
+        dn = torch.rand((T, N), generator=g, device=dev) < 0.002
+        done_u8 = dn.to(torch.uint8)
+        flag = (dn & (torch.rand((T, N), generator=g, device=dev) < 0.5)).to(torch.int32) * 3
+        done, succ = dn.float(), (dn & (flag != 3)).float()
+        if kind == "gae":
+            fn, nbytes = (lambda: G.gae(r, vs, vsn, done, succ, 0.99, 0.95)), 28.0
+        elif kind == "gae_flags":
+            fn, nbytes = (lambda: G.gae_flags(r, vs, vsn, done_u8, flag, 3, 0.99, 0.95)), 25.0
+        else:
+            fn, nbytes = (lambda: G.mc_returns(r, done_u8, 0.99)), 9.0
+        units = T * N
+    elif kind == "norm":
+        dim, n = 6, 1 << 22  # 6 x 4 M float32 = 100 MB per pass: larger than what L2 keeps between the two kernels
+        x = torch.randn((dim, n), generator=g, device=dev, dtype=torch.float32)
+        y = torch.empty_like(x)
+        nz = rlp.Normalization(dim, device=dev, sync=False)
+        fn, nbytes, units = (lambda: nz.normalize_soa(x, out=y)), 12.0, dim * n
+    else:
+        raise SystemExit(f"unknown kind {kind}")
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    per = e0.elapsed_time(e1) * 1e-3 / reps
+    return {"workload": kind, "value": units / per, "unit": "elements/s", "ms_per_step": per * 1e3,
+            "algorithmic_bytes_per_element": nbytes, "achieved_gbs": nbytes * units / per / 1e9}
+
+
+if __name__ == "__main__":
+    print(json.dumps(run(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 10)))

@@ -1,0 +1,31 @@
+#!/bin/bash
+# One `ncu --set full` capture of the dominant kernel of every workload (run on the GPU box, after the same commands
+# exited 0 without ncu).  Reports land in gpurun_out/prof_<name>.ncu-rep; profiles/tools/summarise.py turns them into
+# profiles/<round>/kernels.md.
+set -u
+out=gpurun_out
+NCU="ncu --set full --clock-control none --import-source on -f"
+prof_env() { # workload kernel-regex
+  python bench.py --workload $1 --steps 12 --warmup 3 --no-extras > $out/plain_$1.log 2>&1 || { echo "plain $1 failed"; return; }
+  $NCU -k regex:$2 -s 4 -c 1 -o $out/prof_$1 python bench.py --workload $1 --steps 12 --warmup 3 --no-extras > $out/ncu_$1.log 2>&1
+}
+prof_micro() { # kind kernel-regex
+  python tools/microbench.py $1 4 > $out/plain_$1.log 2>&1 || { echo "plain $1 failed"; return; }
+  $NCU -k regex:$2 -s 3 -c 1 -o $out/prof_$1 python tools/microbench.py $1 4 > $out/ncu_$1.log 2>&1
+}
+for w in "$@"; do
+  case $w in
+    uav_pos) prof_env uav_pos uav_pos_step ;;
+    uav_att) prof_env uav_att uav_att_step ;;
+    cartpole) prof_env cartpole cartpole_step ;;
+    ugvo) prof_env ugvo ugvo_step ;;
+    uavr_hover) prof_env uavr_hover uavrobust_step ;;
+    soi|fas|fas_discrete|ballbalancer|twolink|ugv) prof_env $w env_step_kernel ;;
+    gae) prof_micro gae gae_kernel ;;
+    gae_flags) prof_micro gae_flags gae_kernel ;;
+    mc_returns) prof_micro mc_returns mc_returns_kernel ;;
+    norm_stats) python tools/microbench.py norm 4 > $out/plain_norm.log 2>&1 && $NCU -k regex:norm_batch_stats -s 3 -c 1 -o $out/prof_norm_stats python tools/microbench.py norm 4 > $out/ncu_norm_stats.log 2>&1 ;;
+    norm_apply) $NCU -k regex:norm_merge_apply -s 3 -c 1 -o $out/prof_norm_apply python tools/microbench.py norm 4 > $out/ncu_norm_apply.log 2>&1 ;;
+  esac
+done
+ls -la $out/prof_*.ncu-rep | wc -l
