@@ -429,6 +429,33 @@ B200_API int b200_norm_merge_apply(int dtype, int64_t n, int dim, const void *x,
                                    int n_batches, const double *run_in, double *run_out, int update, double eps,
                                    void *cuda_stream);
 
+/* ------------------------------------------------------------- batched policy forward */
+
+/* A small tanh MLP as torch.nn.Linear stores it: layer l maps dims[l] -> dims[l + 1]; w[l] is the DEVICE pointer of
+ * `weight` ([dims[l+1]][dims[l]] row-major, float32), b[l] of `bias`.  Hidden layers use tanh; out_act selects the
+ * output activation: 0 identity (PPOCritic.forward, utils/classes.py:610-614), 1 relu (PPOActor_Gaussian.forward
+ * :563-569). */
+typedef struct b200_mlp {
+    int32_t n_layers;       /* 1..4 */
+    int32_t dims[5];
+    int32_t out_act;
+    int32_t pad_;
+    const float *w[4];
+    const float *b[4];
+} b200_mlp;
+
+/* Replaces Proximal_Policy_Optimization2.choose_action (algorithm/policy_base/Proximal_Policy_Optimization2.py:69-76)
+ * and the critic forward of learn() (:88-90) for n instances: obs [S][n] float32 field-major (the step kernels'
+ * policy-state buffer) ->  mean = actor(obs);  action = clamp(mean + std * eps, a_min, a_max);
+ * log_prob = Normal(mean, std).log_prob(action);  value = critic(obs).  eps = noise[A][n] if given, else N(0,1) from
+ * Philox4x32-10 keyed by (seed, env_index_offset + i, step) (Box-Muller).  actor or critic may be NULL (then action /
+ * value are not written); log_prob, mean may be NULL.  a_min, a_max: device float32 [A].  All nets must fit in shared
+ * memory together with the tile's activations (the reference's 64-64-32 / 64-32 nets use 100 KB), else B200ENV_ESIZE. */
+B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const float *obs,
+                                 const float *a_min, const float *a_max, float std, const float *noise, uint64_t seed,
+                                 uint64_t step, int64_t env_index_offset, float *action, float *log_prob, float *mean,
+                                 float *value, void *cuda_stream);
+
 /* ------------------------------------------------------------- diagnostics */
 
 /* Measures the FP64 (dtype = B200ENV_F64) or FP32 vector FMA peak of the current device in TFLOP/s (2 flops per

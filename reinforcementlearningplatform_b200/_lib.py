@@ -46,6 +46,12 @@ class RolloutSpec(C.Structure):
         "flag_stride")]
 
 
+class MLP(C.Structure):
+    """struct b200_mlp"""
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * 5), ("out_act", C.c_int32), ("pad_", C.c_int32),
+                ("w", C.c_void_p * 4), ("b", C.c_void_p * 4)]
+
+
 class CartPoleParams(C.Structure):
     """struct b200_cartpole_params"""
     _fields_ = [(k, C.c_double) for k in (
@@ -167,6 +173,8 @@ def load() -> C.CDLL:
     lib.b200_norm_batch_stats.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp]
     lib.b200_norm_merge_apply.restype = i32
     lib.b200_norm_merge_apply.argtypes = [i32, i64, i32, vp, vp, vp, i32, vp, vp, i32, f64, vp]
+    lib.b200_policy_forward.restype = i32
+    lib.b200_policy_forward.argtypes = [i64, vp, vp, vp, vp, vp, C.c_float, vp, u64, u64, i64, vp, vp, vp, vp, vp]
     lib.b200_fastmath_eval.restype = i32
     lib.b200_fastmath_eval.argtypes = [i32, i64, vp, vp, vp, vp]
     lib.b200_measure_fma_peak.restype = i32

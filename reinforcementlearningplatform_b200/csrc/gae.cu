@@ -152,17 +152,18 @@ mc_returns_kernel(int64_t T, int64_t N, const TR *__restrict__ r, const uint8_t 
     if (n >= N) return;
     double acc = 0.0;
     int64_t t = T - 1;
-    for (; t >= GAE_UNROLL - 1; t -= GAE_UNROLL) {
-        double rr[GAE_UNROLL];
-        uint8_t dd[GAE_UNROLL];
+    constexpr int RET_UNROLL = 8;
+    for (; t >= RET_UNROLL - 1; t -= RET_UNROLL) {
+        double rr[RET_UNROLL];
+        uint8_t dd[RET_UNROLL];
 #pragma unroll
-        for (int u = 0; u < GAE_UNROLL; ++u) {
+        for (int u = 0; u < RET_UNROLL; ++u) {
             const int64_t idx = (t - u) * N + n;
             rr[u] = (double)__ldcs(r + idx);
             dd[u] = __ldcs(done + idx);
         }
 #pragma unroll
-        for (int u = 0; u < GAE_UNROLL; ++u) {
+        for (int u = 0; u < RET_UNROLL; ++u) {
             if (dd[u]) acc = 0.0;
             acc = __dadd_rn(rr[u], __dmul_rn(gamma, acc));
             __stcs(ret + (t - u) * N + n, (float)acc);

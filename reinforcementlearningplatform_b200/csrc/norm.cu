@@ -65,7 +65,20 @@ norm_batch_stats_kernel(int64_t n, int dim, const TX *__restrict__ x, const doub
     const TX *xf = x + (int64_t)f * n;
     const double pivot = (run && run[f] > 0.0) ? run[dim + f] : (double)xf[0];
     double s1 = 0.0, s2 = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * NORM_BLOCK + threadIdx.x; i < n; i += (int64_t)nb * NORM_BLOCK) {
+    const int64_t stride = (int64_t)nb * NORM_BLOCK;
+    int64_t i = (int64_t)blockIdx.x * NORM_BLOCK + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) { // 4 loads in flight per thread
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (double)__ldg(xf + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double d = v[u] - pivot;
+            s1 += d;
+            s2 = fma(d, d, s2);
+        }
+    }
+    for (; i < n; i += stride) {
         const double d = (double)__ldg(xf + i) - pivot;
         s1 += d;
         s2 = fma(d, d, s2);
@@ -146,8 +159,26 @@ norm_merge_apply_kernel(int64_t n, int dim, const TX *__restrict__ x, TX *__rest
     const double mean = s.mean, den = __dadd_rn(std_of(s), eps);
     const TX *xf = x + (int64_t)f * n;
     TX *yf = y + (int64_t)f * n;
-    for (int64_t i = (int64_t)blockIdx.x * NORM_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * NORM_BLOCK)
-        yf[i] = (TX)__ddiv_rn(__dsub_rn((double)xf[i], mean), den);
+    // float32 I/O: the quotient is rounded to float32 on store, so the reciprocal + one FMA-corrected Newton step of
+    // common.cuh (<= 1 ulp of the float64 quotient in rare half-way cases) is invisible; float64 I/O keeps the IEEE
+    // division (bit-exact against the reference for one-sample batches).  4 elements per trip: loads issued together.
+    const Divisor<double> dv(den);
+    const int64_t stride = (int64_t)gridDim.x * NORM_BLOCK;
+    int64_t i = (int64_t)blockIdx.x * NORM_BLOCK + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (double)__ldcs(xf + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double d = __dsub_rn(v[u], mean);
+            __stcs(yf + i + u * stride, (TX)(sizeof(TX) == 4 ? dv.div(d) : __ddiv_rn(d, den)));
+        }
+    }
+    for (; i < n; i += stride) {
+        const double d = __dsub_rn((double)xf[i], mean);
+        yf[i] = (TX)(sizeof(TX) == 4 ? dv.div(d) : __ddiv_rn(d, den));
+    }
 }
 
 // the reference recurrence, sample by sample; x, y are [dim][rows]

@@ -1,0 +1,252 @@
+// policy.cu -- K-POLICY: batched Gaussian actor + critic forward for N instances (sm_100a), SURVEY 8(f)-2.
+//
+// Replaces, for a whole batch of observations, `Proximal_Policy_Optimization2.choose_action`
+// (algorithm/policy_base/Proximal_Policy_Optimization2.py:69-76):
+//     dist = actor.get_dist(s)            PPOActor_Gaussian.forward, utils/classes.py:563-579:
+//                                         tanh(fc1) -> tanh(fc2) -> tanh(fc3) -> relu(mean_layer); Normal(mean, std)
+//     a = dist.sample(); a = max(min(a, a_max), a_min); a_logprob = dist.log_prob(a)
+// and the critic forward `PPOCritic.forward` (utils/classes.py:610-614: tanh(fc1) -> tanh(fc2) -> fc3) that the
+// learner evaluates on s and s' (Proximal_Policy_Optimization2.py:88-90).  Observations come in and actions go out in
+// the engine's field-major float32 layout ([dim][N]), i.e. exactly the buffers the step kernels read and write
+// (b200env_io with io_dtype = F32): policy_state -> K-POLICY -> action -> step kernel, no host round trip.
+//
+// Arithmetic: float32 like the reference (torch CPU float32); FMA accumulation in k order, so results differ from
+// torch's blocked GEMM only by summation order (tests: <= 2e-6 absolute on mean / value).  tanhf, logf are the
+// accurate libdevice versions.  Sampling: a = mean + std * eps with eps either injected ([A][N], parity tests) or
+// drawn in-kernel from Philox4x32-10 keyed by (seed, global instance index, step) through Box-Muller, independent of
+// launch geometry and sharding.
+//
+// Mapping: one thread per instance, persistent blocks of 128 threads.  Every layer's W^T (zero-padded to a multiple of
+// 16 outputs) and bias live in shared memory for the whole kernel; activations of the 128 instances of a tile ping-pong
+// between two [dim][128] shared buffers (column = thread, conflict-free).  Per k: one activation load, CH/4 broadcast
+// LDS.128 of weights and CH independent FFMAs (CH = 32 or 16 accumulators in registers), so the loop is bound by the
+// FP32 FMA pipe (CUDA cores).  The nets of the reference (6..41 -> 64 -> 64 -> 32 -> A, critic 64 -> 32 -> 1) are far
+// too small for a tensor-core tile pipeline to pay unless this kernel dominates a training step; bench.py reports its
+// time next to the env step so that decision is made on a measurement.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PB = 128;          // threads (= instances) per tile
+constexpr int MAX_LAYERS = 4;
+
+struct NetDev {
+    int n_layers;
+    int dims[MAX_LAYERS + 1];    // dims[0] = input, dims[l + 1] = outputs of layer l
+    int pad[MAX_LAYERS];         // outputs padded to a multiple of 16
+    int w_off[MAX_LAYERS];       // float offsets into the shared weight arena: W^T [in][pad]
+    int b_off[MAX_LAYERS];
+    int out_act;                 // 0 = identity, 1 = relu
+    const float *w[MAX_LAYERS];  // global: nn.Linear.weight [out][in] row-major
+    const float *b[MAX_LAYERS];  // global: [out]
+};
+
+struct PolicyArgs {
+    NetDev actor, critic;
+    int has_actor, has_critic;
+    int act_dim_max;             // rows of one activation buffer
+    int arena_floats;
+    const float *obs;            // [S][n]
+    const float *a_min, *a_max;  // [A] device
+    const float *noise;          // [A][n] or NULL
+    float std_;
+    uint64_t seed, step;
+    int64_t off;
+    float *action, *log_prob, *mean, *value;
+};
+
+__device__ __forceinline__ void stage_net(const NetDev &nd, float *arena) {
+    for (int l = 0; l < nd.n_layers; ++l) {
+        const int in = nd.dims[l], out = nd.dims[l + 1], pd = nd.pad[l];
+        float *wt = arena + nd.w_off[l], *bs = arena + nd.b_off[l];
+        for (int e = threadIdx.x; e < in * pd; e += PB) {
+            const int k = e / pd, j = e - k * pd;
+            wt[e] = j < out ? __ldg(nd.w[l] + (int64_t)j * in + k) : 0.0f;
+        }
+        for (int j = threadIdx.x; j < pd; j += PB) bs[j] = j < out ? __ldg(nd.b[l] + j) : 0.0f;
+    }
+}
+
+// one dense layer for this thread's instance: out[j] = act(b[j] + sum_k W[j][k] in[k]), CH outputs at a time
+template <int CH>
+__device__ __forceinline__ void dense(const float *__restrict__ wt, const float *__restrict__ bs, int in, int pd,
+                                      const float *__restrict__ src, float *__restrict__ dst, int act) {
+    const int t = threadIdx.x;
+    for (int j0 = 0; j0 < pd; j0 += CH) {
+        float acc[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] = bs[j0 + c];
+#pragma unroll 2
+        for (int k = 0; k < in; ++k) {
+            const float x = src[k * PB + t];
+            const float4 *w4 = reinterpret_cast<const float4 *>(wt + k * pd + j0);
+#pragma unroll
+            for (int c = 0; c < CH / 4; ++c) {
+                const float4 w = w4[c];
+                acc[4 * c + 0] = fmaf(w.x, x, acc[4 * c + 0]);
+                acc[4 * c + 1] = fmaf(w.y, x, acc[4 * c + 1]);
+                acc[4 * c + 2] = fmaf(w.z, x, acc[4 * c + 2]);
+                acc[4 * c + 3] = fmaf(w.w, x, acc[4 * c + 3]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            float v = acc[c];
+            if (act == 2) v = tanhf(v);
+            else if (act == 1) v = fmaxf(v, 0.0f);
+            dst[(j0 + c) * PB + t] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PB)
+policy_forward_kernel(const __grid_constant__ PolicyArgs a, int64_t n) {
+    extern __shared__ __align__(16) float smem[];
+    float *arena = smem;
+    float *obs_s = smem + a.arena_floats;                    // [S][PB]: kept for the critic pass
+    float *buf0 = obs_s + (size_t)a.actor.dims[0] * PB;      // two activation buffers [act_dim_max][PB]
+    float *buf1 = buf0 + (size_t)a.act_dim_max * PB;
+    if (a.has_actor) stage_net(a.actor, arena);
+    if (a.has_critic) stage_net(a.critic, arena);
+    __syncthreads();
+    const int S = a.has_actor ? a.actor.dims[0] : a.critic.dims[0];
+    const int t = threadIdx.x;
+    const int64_t tiles = (n + PB - 1) / PB;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t i = tile * PB + t;
+        const bool live = i < n;
+        for (int k = 0; k < S; ++k) obs_s[k * PB + t] = live ? __ldcs(a.obs + (int64_t)k * n + i) : 0.0f;
+        // (each thread only ever touches its own column t of obs_s / buf0 / buf1: no block synchronisation needed)
+        if (a.has_actor) {
+            const int A = a.actor.dims[a.actor.n_layers];
+            // layer 0 reads the observations in place
+            float *src = obs_s, *dst = buf0;
+            for (int l = 0; l < a.actor.n_layers; ++l) {
+                const int act = l + 1 < a.actor.n_layers ? 2 : a.actor.out_act;
+                const float *wt = arena + a.actor.w_off[l], *bs = arena + a.actor.b_off[l];
+                if (a.actor.pad[l] % 32 == 0) dense<32>(wt, bs, a.actor.dims[l], a.actor.pad[l], src, dst, act);
+                else dense<16>(wt, bs, a.actor.dims[l], a.actor.pad[l], src, dst, act);
+                src = dst;
+                dst = dst == buf0 ? buf1 : buf0;
+            }
+            if (live) {
+                Philox rng(a.seed, (uint64_t)(a.off + i), (uint32_t)a.step);
+                rng.c3 = (uint32_t)(a.step >> 32) << 8; // high step bits above the block counter
+                const float lstd = logf(a.std_), var2 = 2.0f * (a.std_ * a.std_);
+                for (int j = 0; j < A; j += 2) {
+                    float e0, e1;
+                    if (a.noise) {
+                        e0 = __ldcs(a.noise + (int64_t)j * n + i);
+                        e1 = j + 1 < A ? __ldcs(a.noise + (int64_t)(j + 1) * n + i) : 0.0f;
+                    } else { // Box-Muller on two 32-bit uniforms; u1 in (0, 1]
+                        if (rng.have < 2) rng.block();
+                        const uint32_t r0 = rng.r[4 - rng.have], r1 = rng.r[5 - rng.have];
+                        rng.have -= 2;
+                        const float u1 = ((float)(r0 >> 8) + 1.0f) * (1.0f / 16777216.0f);
+                        const float u2 = (float)(r1 >> 8) * (1.0f / 16777216.0f);
+                        const float rad = sqrtf(-2.0f * logf(u1));
+                        float sn, cs;
+                        sincospif(2.0f * u2, &sn, &cs);
+                        e0 = rad * cs;
+                        e1 = rad * sn;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (j + q >= A) break;
+                        const float m = src[(j + q) * PB + t];
+                        float act = fmaf(a.std_, q ? e1 : e0, m);                       // dist.sample()
+                        act = fmaxf(fminf(act, __ldg(a.a_max + j + q)), __ldg(a.a_min + j + q));
+                        const float d = act - m;                                         // Normal.log_prob
+                        const float lp = -(d * d) / var2 - lstd - 0.91893853320467274178f;
+                        __stcs(a.action + (int64_t)(j + q) * n + i, act);
+                        if (a.log_prob) __stcs(a.log_prob + (int64_t)(j + q) * n + i, lp);
+                        if (a.mean) __stcs(a.mean + (int64_t)(j + q) * n + i, m);
+                    }
+                }
+            }
+        }
+        if (a.has_critic) {
+            float *src = obs_s, *dst = buf0;
+            for (int l = 0; l < a.critic.n_layers; ++l) {
+                const int act = l + 1 < a.critic.n_layers ? 2 : a.critic.out_act;
+                const float *wt = arena + a.critic.w_off[l], *bs = arena + a.critic.b_off[l];
+                if (a.critic.pad[l] % 32 == 0) dense<32>(wt, bs, a.critic.dims[l], a.critic.pad[l], src, dst, act);
+                else dense<16>(wt, bs, a.critic.dims[l], a.critic.pad[l], src, dst, act);
+                src = dst;
+                dst = dst == buf0 ? buf1 : buf0;
+            }
+            if (live) __stcs(a.value + i, src[t]);
+        }
+    }
+}
+
+int fill_net(const b200_mlp *m, NetDev *nd, int *arena, int *act_rows) {
+    if (m->n_layers < 1 || m->n_layers > MAX_LAYERS) return B200ENV_ESIZE;
+    nd->n_layers = m->n_layers;
+    nd->out_act = m->out_act;
+    for (int l = 0; l <= m->n_layers; ++l) {
+        if (m->dims[l] < 1 || m->dims[l] > 1024) return B200ENV_ESIZE;
+        nd->dims[l] = m->dims[l];
+    }
+    for (int l = 0; l < m->n_layers; ++l) {
+        if (!m->w[l] || !m->b[l]) return B200ENV_ENULL;
+        nd->w[l] = m->w[l];
+        nd->b[l] = m->b[l];
+        nd->pad[l] = (m->dims[l + 1] + 15) / 16 * 16;
+        nd->w_off[l] = *arena;
+        *arena += nd->dims[l] * nd->pad[l];
+        nd->b_off[l] = *arena;
+        *arena += nd->pad[l];
+        if (nd->pad[l] > *act_rows) *act_rows = nd->pad[l];
+    }
+    return B200ENV_OK;
+}
+
+} // namespace
+
+extern "C" B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const float *obs,
+                                            const float *a_min, const float *a_max, float std_, const float *noise,
+                                            uint64_t seed, uint64_t step, int64_t env_index_offset, float *action,
+                                            float *log_prob, float *mean, float *value, void *cuda_stream) {
+    if (n <= 0) return B200ENV_ESIZE;
+    if (!obs || (!actor && !critic)) return B200ENV_ENULL;
+    if (actor && (!action || !a_min || !a_max)) return B200ENV_ENULL;
+    if (critic && !value) return B200ENV_ENULL;
+    if (actor && !(std_ > 0.0f)) return B200ENV_EPARAMS;
+    PolicyArgs a = {};
+    int arena = 0, rows = 16, rc;
+    if (actor) {
+        if ((rc = fill_net(actor, &a.actor, &arena, &rows))) return rc;
+        a.has_actor = 1;
+    }
+    if (critic) {
+        if ((rc = fill_net(critic, &a.critic, &arena, &rows))) return rc;
+        a.has_critic = 1;
+        if (critic->dims[critic->n_layers] != 1) return B200ENV_EPARAMS;
+        if (actor && actor->dims[0] != critic->dims[0]) return B200ENV_EPARAMS;
+    }
+    if (!actor) a.actor.dims[0] = critic->dims[0]; // obs_s is sized from actor.dims[0]
+    const int S = a.actor.dims[0];
+    a.arena_floats = (arena + 3) / 4 * 4;
+    a.act_dim_max = rows;
+    a.obs = obs; a.a_min = a_min; a.a_max = a_max; a.noise = noise; a.std_ = std_;
+    a.seed = seed; a.step = step; a.off = env_index_offset;
+    a.action = action; a.log_prob = log_prob; a.mean = mean; a.value = value;
+    const size_t smem = ((size_t)a.arena_floats + (size_t)(S + 2 * rows) * PB) * sizeof(float);
+    if (smem > 227 * 1024) return B200ENV_ESIZE; // nets wider than shared memory holds: not supported by this kernel
+    static size_t configured[64] = {0}; // per device: the opt-in dynamic shared-memory limit set so far
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (smem > 48 * 1024 && smem > configured[dev]) {
+        if (cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return b200_check_launch();
+        configured[dev] = smem;
+    }
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const unsigned grid = b200_persistent_grid(n, per_sm, PB);
+    policy_forward_kernel<<<grid, PB, smem, (cudaStream_t)cuda_stream>>>(a, n);
+    return b200_check_launch();
+}

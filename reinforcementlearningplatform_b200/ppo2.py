@@ -1,0 +1,175 @@
+"""Vectorised PPO2 / DPPO2 over the engine's device-resident pieces (SURVEY 8(f)-2,3).
+
+The learner of the reference (algorithm/policy_base/Proximal_Policy_Optimization2.py:17-160, Distributed_PPO2.py) with
+the same hyper-parameter dictionary (``ppo_msg``) and the same loss, restructured around N instances on one GPU:
+
+    collect():  policy_state --K-POLICY--> a, log_prob  --step kernel--> s, s_, r, done, flag written straight into the
+                time-major RolloutBuffer; rewards optionally through the running normaliser (K-NORM), T times, no host copy
+    learn():    V(s), V(s_) by K-POLICY (critic only) -> K-GAE + global advantage normalisation ->
+                K_epochs x mini-batches of the clipped-surrogate / entropy / value losses with torch autograd on the
+                caller's own actor / critic modules (Adam eps 1e-5, grad-norm clip 0.5, linear lr decay, as the reference)
+                -> with torch.distributed: one flat gradient all-reduce per mini-batch (dist.FlatGradAllReducer), the
+                synchronous form of the DPPO2 gradient push (Distributed_PPO2.py:86-104)
+
+Only the update itself uses torch's library kernels (the learner is outside the hot path); everything
+per env-step runs in this repo's CUDA kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import dist as _dist
+from .normalization import Normalization
+from .policy import GaussianPolicy, linear_layers
+from .rollout import RolloutBuffer
+
+DEFAULT_PPO_MSG = {  # demonstration/PPO2/PPO2-4-CartPoleAngleOnly/train.py:141-158
+    'gamma': 0.99, 'K_epochs': 25, 'eps_clip': 0.2, 'buffer_size': 128, 'a_lr': 1e-4, 'c_lr': 1e-3, 'set_adam_eps': True,
+    'lmd': 0.95, 'use_adv_norm': True, 'mini_batch_size': 4096, 'entropy_coef': 0.01, 'use_grad_clip': True,
+    'use_lr_decay': True, 'max_train_steps': int(5e8), 'using_mini_batch': True,
+}
+
+
+class VecPPO2:
+    def __init__(self, env, actor: torch.nn.Module, critic: torch.nn.Module, ppo_msg: Optional[dict] = None,
+                 std: Optional[float] = None, reward_norm: bool = True, seed: int = 0, group=None):
+        """``env``: a vector env built with ``io_dtype=torch.float32, auto_reset=True``; ``actor`` / ``critic``: tanh
+        MLPs on ``env.device`` (the reference's PPOActor_Gaussian / PPOCritic shapes, utils/classes.py:529-615);
+        ``buffer_size`` of ``ppo_msg`` is the number of time steps T per rollout (T x N transitions per learn())."""
+        self.env, self.actor, self.critic, self.group = env, actor, critic, group
+        m = dict(DEFAULT_PPO_MSG)
+        m.update(ppo_msg or {})
+        self.msg = m
+        self.gamma, self.lmd, self.K_epochs, self.eps_clip = m['gamma'], m['lmd'], m['K_epochs'], m['eps_clip']
+        self.buffer = RolloutBuffer(m['buffer_size'], env)
+        ar = torch.as_tensor(env.action_range, dtype=torch.float32)
+        self.std = float(std if std is not None else getattr(actor, 'std', 0.5))
+        self.policy = GaussianPolicy(linear_layers(actor), linear_layers(critic), ar[:, 0], ar[:, 1], self.std,
+                                     device=env.device, seed=seed, env_index_offset=env.env_index_offset)
+        self.value_net = GaussianPolicy(None, linear_layers(critic), ar[:, 0], ar[:, 1], 1.0, device=env.device)
+        eps = 1e-5 if m['set_adam_eps'] else 1e-8                                   # PPO2.py:50-55
+        self.optimizer_actor = torch.optim.Adam(actor.parameters(), lr=m['a_lr'], eps=eps)
+        self.optimizer_critic = torch.optim.Adam(critic.parameters(), lr=m['c_lr'], eps=eps)
+        self.reduce_actor = _dist.FlatGradAllReducer(actor.parameters(), group)
+        self.reduce_critic = _dist.FlatGradAllReducer(critic.parameters(), group)
+        _dist.broadcast_parameters([actor, critic], 0, group)
+        self.reward_norm = Normalization(1, device=env.device, group=group) if reward_norm else None
+        self.total_steps = 0
+        self._raw_reward_sum = torch.zeros((), dtype=torch.float64, device=env.device)
+        self._gen = torch.Generator(device=env.device)
+        self._gen.manual_seed(seed + 1)
+
+    # ------------------------------------------------------------------ collection (train.py:186-216, vectorised)
+    def collect(self) -> float:
+        """One rollout of T steps of all N instances; returns the mean raw reward per step (for logging)."""
+        env, buf = self.env, self.buffer
+        if not env._policy_obs_valid:
+            env.reset(True)
+        self._raw_reward_sum.zero_()
+        for t in range(buf.batch_size):
+            self.policy(env._reset_obs, action=buf.a[t], log_prob=buf.a_lp[t])      # choose_action, PPO2.py:69-76
+            buf.step(env, t, buf.a[t])                                              # step_update + buffer.append
+            if self.reward_norm is not None:
+                self._raw_reward_sum += buf.r[t].sum(dtype=torch.float64)
+                self.reward_norm.normalize_soa(buf.r[t], out=buf.r[t])              # r = reward_norm(env.reward), :210
+        self.total_steps += buf.batch_size * buf.n_envs
+        if self.reward_norm is None:
+            return float(buf.r.mean())
+        return float(self._raw_reward_sum) / (buf.batch_size * buf.n_envs)
+
+    # ------------------------------------------------------------------ update (PPO2.py:78-170)
+    def _log_prob_entropy(self, s, a):
+        mean = self.actor(s)
+        var = self.std * self.std
+        lp = -((a - mean) ** 2) / (2 * var) - math.log(self.std) - math.log(math.sqrt(2 * math.pi))
+        ent = (0.5 + 0.5 * math.log(2 * math.pi) + math.log(self.std)) * a.shape[1]   # Normal.entropy().sum(1)
+        return lp, ent
+
+    def learn(self) -> dict:
+        buf, m = self.buffer, self.msg
+        T, N = buf.batch_size, buf.n_envs
+        S, A = buf.state_dim, buf.action_dim
+        with torch.no_grad():
+            vs = self.value_net(buf.s.permute(1, 0, 2).reshape(S, T * N).contiguous())["value"].view(T, N)
+            vs_ = self.value_net(buf.s_.permute(1, 0, 2).reshape(S, T * N).contiguous())["value"].view(T, N)
+            adv, v_target = buf.gae(vs, vs_, self.gamma, self.lmd, normalize=m['use_adv_norm'], group=self.group)
+            s, a, a_lp, _, _, _, _ = buf.to_tensor()
+            adv, v_target = adv.reshape(T * N, 1), v_target.reshape(T * N, 1)
+            a_lp_sum = a_lp.sum(1, keepdim=True)
+        B = T * N
+        mb = min(m['mini_batch_size'], B) if m['using_mini_batch'] else B
+        last = {}
+        for _ in range(self.K_epochs):
+            perm = torch.randperm(B, device=s.device, generator=self._gen)
+            for k in range(0, B - mb + 1, mb):                                       # BatchSampler(..., drop_last=False)
+                idx = perm[k:k + mb]
+                lp_now, ent = self._log_prob_entropy(s[idx], a[idx])
+                ratios = torch.exp(lp_now.sum(1, keepdim=True) - a_lp_sum[idx])
+                surr1 = ratios * adv[idx]
+                surr2 = torch.clamp(ratios, 1 - self.eps_clip, 1 + self.eps_clip) * adv[idx]
+                actor_loss = (-torch.min(surr1, surr2) - m['entropy_coef'] * ent).mean()
+                self.optimizer_actor.zero_grad(set_to_none=False)
+                actor_loss.backward()
+                self.reduce_actor()
+                if m['use_grad_clip']:
+                    torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 0.5)
+                self.optimizer_actor.step()
+                critic_loss = F.mse_loss(v_target[idx], self.critic(s[idx]))
+                self.optimizer_critic.zero_grad(set_to_none=False)
+                critic_loss.backward()
+                self.reduce_critic()
+                if m['use_grad_clip']:
+                    torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 0.5)
+                self.optimizer_critic.step()
+                last = {"actor_loss": actor_loss.detach(), "critic_loss": critic_loss.detach()}
+        if m['use_lr_decay']:
+            self.lr_decay(self.total_steps)
+        return {k: float(v) for k, v in last.items()}
+
+    def lr_decay(self, total_steps):                                                 # PPO2.py:162-171
+        if total_steps < self.msg['max_train_steps']:
+            f = 1 - total_steps / self.msg['max_train_steps']
+            for opt, lr in ((self.optimizer_actor, self.msg['a_lr']), (self.optimizer_critic, self.msg['c_lr'])):
+                for p in opt.param_groups:
+                    p['lr'] = max(lr * f, 1e-6)
+
+    def evaluate(self, obs_soa: torch.Tensor) -> torch.Tensor:
+        """actor mean for ``[state_dim, N]`` observations (``agent.evaluate``, PPO2.py:62-66)."""
+        zero = torch.zeros(self.policy.action_dim, obs_soa.shape[1], dtype=torch.float32, device=obs_soa.device)
+        return self.policy(obs_soa, noise=zero)["action"]
+
+
+def reference_nets(state_dim: int, action_dim: int, device, init_std: float = 0.5, mean_act: str = "relu"):
+    """Actor / critic with the layer shapes, tanh activations and orthogonal init of the reference's
+    PPOActor_Gaussian / PPOCritic (utils/classes.py:529-615), as plain nn.Modules on ``device``."""
+    class Actor(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2 = torch.nn.Linear(state_dim, 64), torch.nn.Linear(64, 64)
+            self.fc3, self.mean_layer = torch.nn.Linear(64, 32), torch.nn.Linear(32, action_dim)
+            self.std = init_std
+            for l, g in ((self.fc1, 1.0), (self.fc2, 1.0), (self.fc3, 1.0), (self.mean_layer, 0.01)):
+                torch.nn.init.orthogonal_(l.weight, gain=g)
+                torch.nn.init.constant_(l.bias, 0)
+
+        def forward(self, s):
+            s = torch.tanh(self.fc3(torch.tanh(self.fc2(torch.tanh(self.fc1(s))))))
+            m = self.mean_layer(s)
+            return torch.relu(m) if mean_act == "relu" else m
+
+    class Critic(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2, self.fc3 = torch.nn.Linear(state_dim, 64), torch.nn.Linear(64, 32), torch.nn.Linear(32, 1)
+            for l in (self.fc1, self.fc2, self.fc3):
+                torch.nn.init.orthogonal_(l.weight, gain=1.0)
+                torch.nn.init.constant_(l.bias, 0)
+
+        def forward(self, s):
+            return self.fc3(torch.tanh(self.fc2(torch.tanh(self.fc1(s)))))
+
+    return Actor().to(device), Critic().to(device)
