@@ -16,18 +16,20 @@
 // drawn in-kernel from Philox4x32-10 keyed by (seed, global instance index, step) through Box-Muller, independent of
 // launch geometry and sharding.
 //
-// Mapping: one thread per instance, persistent blocks of 128 threads.  Every layer's W^T (zero-padded to a multiple of
-// 16 outputs) and bias live in shared memory for the whole kernel; activations of the 128 instances of a tile ping-pong
-// between two [dim][128] shared buffers (column = thread, conflict-free).  Per k: one activation load, CH/4 broadcast
-// LDS.128 of weights and CH independent FFMAs (CH = 32 or 16 accumulators in registers), so the loop is bound by the
-// FP32 FMA pipe (CUDA cores).  The nets of the reference (6..41 -> 64 -> 64 -> 32 -> A, critic 64 -> 32 -> 1) are far
-// too small for a tensor-core tile pipeline to pay unless this kernel dominates a training step; bench.py reports its
-// time next to the env step so that decision is made on a measurement.
+// Mapping: one thread per instance, persistent blocks of 256 threads, 2 blocks per SM.  Every layer's W^T (zero-padded
+// to 16 / 32 / 64 outputs) and bias live in shared memory for the whole kernel; the activations of the 256 instances of
+// a tile live in ONE [64][256] shared buffer (column = thread, conflict-free) that each layer overwrites in place: a
+// thread keeps all (<= 64) outputs of the layer in registers while it walks k, then stores them over its own column.
+// Per k: one activation load, CH/4 broadcast LDS.128 of weights, CH independent FFMAs -- bound by the FP32 FMA pipe
+// (CUDA cores).  The nets of the reference (6..41 -> 64 -> 64 -> 32 -> A, critic 64 -> 32 -> 1) are far too small for
+// a tensor-core tile pipeline to pay unless this kernel dominates a training step; bench.py reports its time next to
+// the env step so that decision is made on a measurement.
 #include "common.cuh"
 
 namespace {
 
-constexpr int PB = 128;          // threads (= instances) per tile
+constexpr int PB = 256;          // threads (= instances) per tile
+constexpr int MAX_OUT = 64;      // widest layer (padded) this kernel keeps in registers
 constexpr int MAX_LAYERS = 4;
 
 struct NetDev {
@@ -67,45 +69,52 @@ __device__ __forceinline__ void stage_net(const NetDev &nd, float *arena) {
     }
 }
 
-// one dense layer for this thread's instance: out[j] = act(b[j] + sum_k W[j][k] in[k]), CH outputs at a time
+// one dense layer for this thread's instance, in place: buf[j] <- act(b[j] + sum_k W[j][k] buf[k]); all CH (= padded
+// width) outputs stay in registers until the last input has been read
 template <int CH>
-__device__ __forceinline__ void dense(const float *__restrict__ wt, const float *__restrict__ bs, int in, int pd,
-                                      const float *__restrict__ src, float *__restrict__ dst, int act) {
+__device__ __forceinline__ void dense(const float *__restrict__ wt, const float *__restrict__ bs, int in,
+                                      float *__restrict__ buf, int act) {
     const int t = threadIdx.x;
-    for (int j0 = 0; j0 < pd; j0 += CH) {
-        float acc[CH];
+    float acc[CH];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) acc[c] = bs[j0 + c];
-#pragma unroll 2
-        for (int k = 0; k < in; ++k) {
-            const float x = src[k * PB + t];
-            const float4 *w4 = reinterpret_cast<const float4 *>(wt + k * pd + j0);
+    for (int c = 0; c < CH; ++c) acc[c] = bs[c];
+#pragma unroll 4
+    for (int k = 0; k < in; ++k) {
+        const float x = buf[k * PB + t];
+        const float4 *w4 = reinterpret_cast<const float4 *>(wt + k * CH);
 #pragma unroll
-            for (int c = 0; c < CH / 4; ++c) {
-                const float4 w = w4[c];
-                acc[4 * c + 0] = fmaf(w.x, x, acc[4 * c + 0]);
-                acc[4 * c + 1] = fmaf(w.y, x, acc[4 * c + 1]);
-                acc[4 * c + 2] = fmaf(w.z, x, acc[4 * c + 2]);
-                acc[4 * c + 3] = fmaf(w.w, x, acc[4 * c + 3]);
-            }
+        for (int c = 0; c < CH / 4; ++c) {
+            const float4 w = w4[c];
+            acc[4 * c + 0] = fmaf(w.x, x, acc[4 * c + 0]);
+            acc[4 * c + 1] = fmaf(w.y, x, acc[4 * c + 1]);
+            acc[4 * c + 2] = fmaf(w.z, x, acc[4 * c + 2]);
+            acc[4 * c + 3] = fmaf(w.w, x, acc[4 * c + 3]);
         }
+    }
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            float v = acc[c];
-            if (act == 2) v = tanhf(v);
-            else if (act == 1) v = fmaxf(v, 0.0f);
-            dst[(j0 + c) * PB + t] = v;
-        }
+    for (int c = 0; c < CH; ++c) {
+        float v = acc[c];
+        if (act == 2) v = tanhf(v);
+        else if (act == 1) v = fmaxf(v, 0.0f);
+        buf[c * PB + t] = v;
     }
 }
 
-__global__ void __launch_bounds__(PB)
+__device__ __forceinline__ void run_net(const NetDev &nd, const float *arena, float *buf) {
+    for (int l = 0; l < nd.n_layers; ++l) {
+        const int act = l + 1 < nd.n_layers ? 2 : nd.out_act;
+        const float *wt = arena + nd.w_off[l], *bs = arena + nd.b_off[l];
+        if (nd.pad[l] == 64) dense<64>(wt, bs, nd.dims[l], buf, act);
+        else if (nd.pad[l] == 32) dense<32>(wt, bs, nd.dims[l], buf, act);
+        else dense<16>(wt, bs, nd.dims[l], buf, act);
+    }
+}
+
+__global__ void __launch_bounds__(PB, 2)
 policy_forward_kernel(const __grid_constant__ PolicyArgs a, int64_t n) {
     extern __shared__ __align__(16) float smem[];
     float *arena = smem;
-    float *obs_s = smem + a.arena_floats;                    // [S][PB]: kept for the critic pass
-    float *buf0 = obs_s + (size_t)a.actor.dims[0] * PB;      // two activation buffers [act_dim_max][PB]
-    float *buf1 = buf0 + (size_t)a.act_dim_max * PB;
+    float *buf = smem + a.arena_floats;                      // activations [act_dim_max][PB], overwritten in place
     if (a.has_actor) stage_net(a.actor, arena);
     if (a.has_critic) stage_net(a.critic, arena);
     __syncthreads();
@@ -115,20 +124,12 @@ policy_forward_kernel(const __grid_constant__ PolicyArgs a, int64_t n) {
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t i = tile * PB + t;
         const bool live = i < n;
-        for (int k = 0; k < S; ++k) obs_s[k * PB + t] = live ? __ldcs(a.obs + (int64_t)k * n + i) : 0.0f;
-        // (each thread only ever touches its own column t of obs_s / buf0 / buf1: no block synchronisation needed)
+        // (each thread only ever touches its own column t of buf: no block synchronisation needed)
+        for (int k = 0; k < S; ++k) buf[k * PB + t] = live ? __ldg(a.obs + (int64_t)k * n + i) : 0.0f;
         if (a.has_actor) {
             const int A = a.actor.dims[a.actor.n_layers];
-            // layer 0 reads the observations in place
-            float *src = obs_s, *dst = buf0;
-            for (int l = 0; l < a.actor.n_layers; ++l) {
-                const int act = l + 1 < a.actor.n_layers ? 2 : a.actor.out_act;
-                const float *wt = arena + a.actor.w_off[l], *bs = arena + a.actor.b_off[l];
-                if (a.actor.pad[l] % 32 == 0) dense<32>(wt, bs, a.actor.dims[l], a.actor.pad[l], src, dst, act);
-                else dense<16>(wt, bs, a.actor.dims[l], a.actor.pad[l], src, dst, act);
-                src = dst;
-                dst = dst == buf0 ? buf1 : buf0;
-            }
+            run_net(a.actor, arena, buf);
+            const float *src = buf;
             if (live) {
                 Philox rng(a.seed, (uint64_t)(a.off + i), (uint32_t)a.step);
                 rng.c3 = (uint32_t)(a.step >> 32) << 8; // high step bits above the block counter
@@ -166,16 +167,10 @@ policy_forward_kernel(const __grid_constant__ PolicyArgs a, int64_t n) {
             }
         }
         if (a.has_critic) {
-            float *src = obs_s, *dst = buf0;
-            for (int l = 0; l < a.critic.n_layers; ++l) {
-                const int act = l + 1 < a.critic.n_layers ? 2 : a.critic.out_act;
-                const float *wt = arena + a.critic.w_off[l], *bs = arena + a.critic.b_off[l];
-                if (a.critic.pad[l] % 32 == 0) dense<32>(wt, bs, a.critic.dims[l], a.critic.pad[l], src, dst, act);
-                else dense<16>(wt, bs, a.critic.dims[l], a.critic.pad[l], src, dst, act);
-                src = dst;
-                dst = dst == buf0 ? buf1 : buf0;
-            }
-            if (live) __stcs(a.value + i, src[t]);
+            if (a.has_actor) // the observations again (24..164 B per instance, an L2 hit)
+                for (int k = 0; k < S; ++k) buf[k * PB + t] = live ? __ldg(a.obs + (int64_t)k * n + i) : 0.0f;
+            run_net(a.critic, arena, buf);
+            if (live) __stcs(a.value + i, buf[t]);
         }
     }
 }
@@ -192,7 +187,9 @@ int fill_net(const b200_mlp *m, NetDev *nd, int *arena, int *act_rows) {
         if (!m->w[l] || !m->b[l]) return B200ENV_ENULL;
         nd->w[l] = m->w[l];
         nd->b[l] = m->b[l];
-        nd->pad[l] = (m->dims[l + 1] + 15) / 16 * 16;
+        const int o = m->dims[l + 1];
+        if (o > MAX_OUT) return B200ENV_ESIZE; // wider layers: not supported by this kernel (no fallback)
+        nd->pad[l] = o <= 16 ? 16 : (o <= 32 ? 32 : 64);
         nd->w_off[l] = *arena;
         *arena += nd->dims[l] * nd->pad[l];
         nd->b_off[l] = *arena;
@@ -215,6 +212,8 @@ extern "C" B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, co
     if (actor && !(std_ > 0.0f)) return B200ENV_EPARAMS;
     PolicyArgs a = {};
     int arena = 0, rows = 16, rc;
+    const int in_dim = actor ? actor->dims[0] : critic->dims[0];
+    if (in_dim > rows) rows = in_dim;
     if (actor) {
         if ((rc = fill_net(actor, &a.actor, &arena, &rows))) return rc;
         a.has_actor = 1;
@@ -225,14 +224,12 @@ extern "C" B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, co
         if (critic->dims[critic->n_layers] != 1) return B200ENV_EPARAMS;
         if (actor && actor->dims[0] != critic->dims[0]) return B200ENV_EPARAMS;
     }
-    if (!actor) a.actor.dims[0] = critic->dims[0]; // obs_s is sized from actor.dims[0]
-    const int S = a.actor.dims[0];
     a.arena_floats = (arena + 3) / 4 * 4;
     a.act_dim_max = rows;
     a.obs = obs; a.a_min = a_min; a.a_max = a_max; a.noise = noise; a.std_ = std_;
     a.seed = seed; a.step = step; a.off = env_index_offset;
     a.action = action; a.log_prob = log_prob; a.mean = mean; a.value = value;
-    const size_t smem = ((size_t)a.arena_floats + (size_t)(S + 2 * rows) * PB) * sizeof(float);
+    const size_t smem = ((size_t)a.arena_floats + (size_t)rows * PB) * sizeof(float);
     if (smem > 227 * 1024) return B200ENV_ESIZE; // nets wider than shared memory holds: not supported by this kernel
     static size_t configured[64] = {0}; // per device: the opt-in dynamic shared-memory limit set so far
     int dev = 0;

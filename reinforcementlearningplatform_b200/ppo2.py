@@ -72,7 +72,7 @@ class VecPPO2:
         self._raw_reward_sum.zero_()
         for t in range(buf.batch_size):
             self.policy(env._reset_obs, action=buf.a[t], log_prob=buf.a_lp[t])      # choose_action, PPO2.py:69-76
-            buf.step(env, t, buf.a[t])                                              # step_update + buffer.append
+            buf.step(env, t, buf.a[t], store_policy_obs=True)                       # step_update + buffer.append
             if self.reward_norm is not None:
                 self._raw_reward_sum += buf.r[t].sum(dtype=torch.float64)
                 self.reward_norm.normalize_soa(buf.r[t], out=buf.r[t])              # r = reward_norm(env.reward), :210

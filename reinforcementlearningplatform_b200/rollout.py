@@ -47,7 +47,7 @@ class RolloutBuffer:
 
     # ------------------------------------------------------------------ filling
     def step(self, env, t: int, action_soa: torch.Tensor, log_prob_soa: Optional[torch.Tensor] = None,
-             dis_soa: Optional[torch.Tensor] = None) -> None:
+             dis_soa: Optional[torch.Tensor] = None, store_policy_obs: bool = False) -> None:
         """``env.step_update(a); buffer.append(s, a, a_lp, r, s_, done, success, t)`` of the train loops (e.g.
         PPO2-4-CartPoleAngleOnly/train.py:193-215) for every instance, in one kernel launch: the step kernel stores
         current_state, next_state, reward, is_terminal and terminal_flag straight into row ``t``.  ``action_soa`` is
@@ -56,7 +56,16 @@ class RolloutBuffer:
             self.a[t].copy_(action_soa)
         if log_prob_soa is not None and self.a_lp is not None:
             self.a_lp[t].copy_(log_prob_soa)
-        env.step_into(self.a[t], dis_soa, obs=self.s[t], next_obs=self.s_[t], reward=self.r[t], done=self.done[t],
+        obs_row = self.s[t]
+        if store_policy_obs and not (env.reuse_obs and env._policy_obs_valid):
+            # Row s[t] = the observation the policy acted on (`s` of PPO2-4-UavFntsmcParamPos/train.py:290-303, the copy
+            # of the previous next_state), not the current_state step_update recomputes against the new reference.  For
+            # pure-observation envs the two are the same bits and step_into makes this copy itself.
+            self.s[t].copy_(env._reset_obs)
+            if getattr(self, "_obs_scratch", None) is None:
+                self._obs_scratch = torch.empty_like(self.s[0])
+            obs_row = self._obs_scratch
+        env.step_into(self.a[t], dis_soa, obs=obs_row, next_obs=self.s_[t], reward=self.r[t], done=self.done[t],
                       flag=self.flag[t])
         self.index = t + 1
 

@@ -42,8 +42,9 @@ def test_rollout_rows_written_by_policy_and_step_kernels():
     lp = -((a - mean) ** 2) / (2 * 0.45 ** 2) - math.log(0.45) - math.log(math.sqrt(2 * math.pi))
     assert torch.allclose(a_lp, lp, atol=3e-5)
     assert float(a.min()) >= 0.0 and float(a.max()) <= 5.0 and float((a == 0).float().mean()) > 0.01
-    assert torch.equal(b.s[1:][:, :, :], b.s[1:]) and torch.isfinite(r).all()
-    # s of step t+1 is s_ of step t wherever no episode ended (the loop's `current_state = next_state.copy()`)
+    assert torch.isfinite(r).all()
+    # s of step t+1 is s_ of step t wherever no episode ended (the loop's `current_state = next_state.copy()`,
+    # PPO2-4-UavFntsmcParamPos/train.py:290): the buffer holds what the policy acted on
     keep = (b.done[:-1] == 0).unsqueeze(1).expand(-1, 6, -1)
     assert torch.equal(b.s[1:][keep], b.s_[:-1][keep])
     out = agent.learn()
