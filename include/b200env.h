@@ -450,11 +450,17 @@ typedef struct b200_mlp {
  * log_prob = Normal(mean, std).log_prob(action);  value = critic(obs).  eps = noise[A][n] if given, else N(0,1) from
  * Philox4x32-10 keyed by (seed, env_index_offset + i, step) (Box-Muller).  actor or critic may be NULL (then action /
  * value are not written); log_prob, mean may be NULL.  a_min, a_max: device float32 [A].  All nets must fit in shared
- * memory together with the tile's activations (the reference's 64-64-32 / 64-32 nets use 100 KB), else B200ENV_ESIZE. */
+ * memory together with the tile's activations (the reference's 64-64-32 / 64-32 nets use ~110 KB) and no layer may be
+ * wider than 64, else B200ENV_ESIZE. */
+/* precision: B200_POLICY_FP32 = float32 FMA pipe, sums in k order (<= 2e-6 absolute from torch's float32 GEMM);
+ * B200_POLICY_TF32X3 = tensor cores with every operand split into two TF32 halves (3 MMAs per product, fp32
+ * accumulation; <= 5e-6 absolute), ~4x faster -- the forward is otherwise 4x the cost of the env step it feeds. */
+#define B200_POLICY_FP32   0
+#define B200_POLICY_TF32X3 1
 B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const float *obs,
                                  const float *a_min, const float *a_max, float std, const float *noise, uint64_t seed,
-                                 uint64_t step, int64_t env_index_offset, float *action, float *log_prob, float *mean,
-                                 float *value, void *cuda_stream);
+                                 uint64_t step, int64_t env_index_offset, int precision, float *action,
+                                 float *log_prob, float *mean, float *value, void *cuda_stream);
 
 /* ------------------------------------------------------------- diagnostics */
 

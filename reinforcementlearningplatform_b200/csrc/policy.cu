@@ -24,7 +24,7 @@
 // (CUDA cores).  The nets of the reference (6..41 -> 64 -> 64 -> 32 -> A, critic 64 -> 32 -> 1) are far too small for
 // a tensor-core tile pipeline to pay unless this kernel dominates a training step; bench.py reports its time next to
 // the env step so that decision is made on a measurement.
-#include "common.cuh"
+#include "policy_common.cuh"
 
 namespace {
 
@@ -48,13 +48,7 @@ struct PolicyArgs {
     int has_actor, has_critic;
     int act_dim_max;             // rows of one activation buffer
     int arena_floats;
-    const float *obs;            // [S][n]
-    const float *a_min, *a_max;  // [A] device
-    const float *noise;          // [A][n] or NULL
-    float std_;
-    uint64_t seed, step;
-    int64_t off;
-    float *action, *log_prob, *mean, *value;
+    PolicyIO io;
 };
 
 __device__ __forceinline__ void stage_net(const NetDev &nd, float *arena) {
@@ -125,52 +119,17 @@ policy_forward_kernel(const __grid_constant__ PolicyArgs a, int64_t n) {
         const int64_t i = tile * PB + t;
         const bool live = i < n;
         // (each thread only ever touches its own column t of buf: no block synchronisation needed)
-        for (int k = 0; k < S; ++k) buf[k * PB + t] = live ? __ldg(a.obs + (int64_t)k * n + i) : 0.0f;
+        for (int k = 0; k < S; ++k) buf[k * PB + t] = live ? __ldg(a.io.obs + (int64_t)k * n + i) : 0.0f;
         if (a.has_actor) {
             const int A = a.actor.dims[a.actor.n_layers];
             run_net(a.actor, arena, buf);
-            const float *src = buf;
-            if (live) {
-                Philox rng(a.seed, (uint64_t)(a.off + i), (uint32_t)a.step);
-                rng.c3 = (uint32_t)(a.step >> 32) << 8; // high step bits above the block counter
-                const float lstd = logf(a.std_), var2 = 2.0f * (a.std_ * a.std_);
-                for (int j = 0; j < A; j += 2) {
-                    float e0, e1;
-                    if (a.noise) {
-                        e0 = __ldcs(a.noise + (int64_t)j * n + i);
-                        e1 = j + 1 < A ? __ldcs(a.noise + (int64_t)(j + 1) * n + i) : 0.0f;
-                    } else { // Box-Muller on two 32-bit uniforms; u1 in (0, 1]
-                        if (rng.have < 2) rng.block();
-                        const uint32_t r0 = rng.r[4 - rng.have], r1 = rng.r[5 - rng.have];
-                        rng.have -= 2;
-                        const float u1 = ((float)(r0 >> 8) + 1.0f) * (1.0f / 16777216.0f);
-                        const float u2 = (float)(r1 >> 8) * (1.0f / 16777216.0f);
-                        const float rad = sqrtf(-2.0f * logf(u1));
-                        float sn, cs;
-                        sincospif(2.0f * u2, &sn, &cs);
-                        e0 = rad * cs;
-                        e1 = rad * sn;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        if (j + q >= A) break;
-                        const float m = src[(j + q) * PB + t];
-                        float act = fmaf(a.std_, q ? e1 : e0, m);                       // dist.sample()
-                        act = fmaxf(fminf(act, __ldg(a.a_max + j + q)), __ldg(a.a_min + j + q));
-                        const float d = act - m;                                         // Normal.log_prob
-                        const float lp = -(d * d) / var2 - lstd - 0.91893853320467274178f;
-                        __stcs(a.action + (int64_t)(j + q) * n + i, act);
-                        if (a.log_prob) __stcs(a.log_prob + (int64_t)(j + q) * n + i, lp);
-                        if (a.mean) __stcs(a.mean + (int64_t)(j + q) * n + i, m);
-                    }
-                }
-            }
+            if (live) policy_sample_store(a.io, n, i, A, buf + t, PB);
         }
         if (a.has_critic) {
             if (a.has_actor) // the observations again (24..164 B per instance, an L2 hit)
-                for (int k = 0; k < S; ++k) buf[k * PB + t] = live ? __ldg(a.obs + (int64_t)k * n + i) : 0.0f;
+                for (int k = 0; k < S; ++k) buf[k * PB + t] = live ? __ldg(a.io.obs + (int64_t)k * n + i) : 0.0f;
             run_net(a.critic, arena, buf);
-            if (live) __stcs(a.value + i, buf[t]);
+            if (live) __stcs(a.io.value + i, buf[t]);
         }
     }
 }
@@ -201,15 +160,7 @@ int fill_net(const b200_mlp *m, NetDev *nd, int *arena, int *act_rows) {
 
 } // namespace
 
-extern "C" B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const float *obs,
-                                            const float *a_min, const float *a_max, float std_, const float *noise,
-                                            uint64_t seed, uint64_t step, int64_t env_index_offset, float *action,
-                                            float *log_prob, float *mean, float *value, void *cuda_stream) {
-    if (n <= 0) return B200ENV_ESIZE;
-    if (!obs || (!actor && !critic)) return B200ENV_ENULL;
-    if (actor && (!action || !a_min || !a_max)) return B200ENV_ENULL;
-    if (critic && !value) return B200ENV_ENULL;
-    if (actor && !(std_ > 0.0f)) return B200ENV_EPARAMS;
+int policy_launch_fp32(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const PolicyIO &io, cudaStream_t stream) {
     PolicyArgs a = {};
     int arena = 0, rows = 16, rc;
     const int in_dim = actor ? actor->dims[0] : critic->dims[0];
@@ -221,14 +172,10 @@ extern "C" B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, co
     if (critic) {
         if ((rc = fill_net(critic, &a.critic, &arena, &rows))) return rc;
         a.has_critic = 1;
-        if (critic->dims[critic->n_layers] != 1) return B200ENV_EPARAMS;
-        if (actor && actor->dims[0] != critic->dims[0]) return B200ENV_EPARAMS;
     }
     a.arena_floats = (arena + 3) / 4 * 4;
     a.act_dim_max = rows;
-    a.obs = obs; a.a_min = a_min; a.a_max = a_max; a.noise = noise; a.std_ = std_;
-    a.seed = seed; a.step = step; a.off = env_index_offset;
-    a.action = action; a.log_prob = log_prob; a.mean = mean; a.value = value;
+    a.io = io;
     const size_t smem = ((size_t)a.arena_floats + (size_t)rows * PB) * sizeof(float);
     if (smem > 227 * 1024) return B200ENV_ESIZE; // nets wider than shared memory holds: not supported by this kernel
     static size_t configured[64] = {0}; // per device: the opt-in dynamic shared-memory limit set so far
@@ -244,6 +191,27 @@ extern "C" B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, co
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     const unsigned grid = b200_persistent_grid(n, per_sm, PB);
-    policy_forward_kernel<<<grid, PB, smem, (cudaStream_t)cuda_stream>>>(a, n);
+    policy_forward_kernel<<<grid, PB, smem, stream>>>(a, n);
     return b200_check_launch();
+}
+
+extern "C" B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const float *obs,
+                                            const float *a_min, const float *a_max, float std_, const float *noise,
+                                            uint64_t seed, uint64_t step, int64_t env_index_offset, int precision,
+                                            float *action, float *log_prob, float *mean, float *value,
+                                            void *cuda_stream) {
+    if (n <= 0) return B200ENV_ESIZE;
+    if (!obs || (!actor && !critic)) return B200ENV_ENULL;
+    if (actor && (!action || !a_min || !a_max)) return B200ENV_ENULL;
+    if (critic && !value) return B200ENV_ENULL;
+    if (actor && !(std_ > 0.0f)) return B200ENV_EPARAMS;
+    if (critic && critic->dims[critic->n_layers > 0 && critic->n_layers <= 4 ? critic->n_layers : 0] != 1) return B200ENV_EPARAMS;
+    if (actor && critic && actor->dims[0] != critic->dims[0]) return B200ENV_EPARAMS;
+    PolicyIO io;
+    io.obs = obs; io.a_min = a_min; io.a_max = a_max; io.noise = noise; io.std_ = std_;
+    io.seed = seed; io.step = step; io.off = env_index_offset;
+    io.action = action; io.log_prob = log_prob; io.mean = mean; io.value = value;
+    if (precision == B200_POLICY_FP32) return policy_launch_fp32(n, actor, critic, io, (cudaStream_t)cuda_stream);
+    if (precision == B200_POLICY_TF32X3) return policy_launch_tc(n, actor, critic, io, (cudaStream_t)cuda_stream);
+    return B200ENV_EPARAMS;
 }

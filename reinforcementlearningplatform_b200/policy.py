@@ -29,7 +29,8 @@ def linear_layers(module) -> list:
 
 class GaussianPolicy:
     def __init__(self, actor_layers: Optional[Sequence], critic_layers: Optional[Sequence], a_min, a_max, std: float,
-                 device="cuda", seed: int = 0, env_index_offset: int = 0, actor_out_act: str = "relu"):
+                 device="cuda", seed: int = 0, env_index_offset: int = 0, actor_out_act: str = "relu",
+                 precision: str = "tf32x3"):
         """``actor_layers`` / ``critic_layers``: sequences of ``torch.nn.Linear`` (CUDA, float32) or modules accepted by
         :func:`linear_layers`.  ``a_min, a_max``: action clamp (``actor.a_min / a_max``), ``std``: ``actor.std``."""
         self._lib = _lib.load()
@@ -91,7 +92,8 @@ class GaussianPolicy:
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(self._lib.b200_policy_forward(
                 n, None if am is None else C.byref(am), None if cm is None else C.byref(cm), p(obs_soa), p(self.a_min),
-                p(self.a_max), self.std, p(noise), self.seed, self.step, self.env_index_offset, p(out.get("action")),
+                p(self.a_max), self.std, p(noise), self.seed, self.step, self.env_index_offset, self.precision,
+                p(out.get("action")),
                 p(out.get("log_prob")), p(out.get("mean")), p(out.get("value")), stream), "b200_policy_forward")
         if noise is None:
             self.step += 1

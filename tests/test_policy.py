@@ -54,26 +54,27 @@ def _build(c, torch):
 
 
 @pytest.mark.gpu
-def test_engine_policy_matches_reference_nets():
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-6), ("tf32x3", 5e-6)])
+def test_engine_policy_matches_reference_nets(precision, tol):
     import torch
     import reinforcementlearningplatform_b200 as rlp
     for c in cases():
         actor, critic = _build(c, torch)
-        pol = rlp.GaussianPolicy(actor, critic, c["a_min"], c["a_max"], float(c["std"]))
+        pol = rlp.GaussianPolicy(actor, critic, c["a_min"], c["a_max"], float(c["std"]), precision=precision)
         obs = torch.from_numpy(np.ascontiguousarray(c["s"].T)).cuda()
         eps = torch.from_numpy(np.ascontiguousarray(c["eps"].T)).cuda()
         out = pol(obs, noise=eps, want_mean=True)
         f = lambda t: t.cpu().numpy().T
-        np.testing.assert_allclose(f(out["mean"]), c["mean"], atol=2e-6)
-        np.testing.assert_allclose(out["value"].cpu().numpy(), c["value"], atol=2e-6)
-        np.testing.assert_allclose(f(out["action"]), c["action"], atol=3e-6)
-        np.testing.assert_allclose(f(out["log_prob"]), c["log_prob"], atol=2e-5)
+        np.testing.assert_allclose(f(out["mean"]), c["mean"], atol=tol)
+        np.testing.assert_allclose(out["value"].cpu().numpy(), c["value"], atol=tol)
+        np.testing.assert_allclose(f(out["action"]), c["action"], atol=tol + 1e-6)
+        np.testing.assert_allclose(f(out["log_prob"]), c["log_prob"], atol=10 * tol)
         lo, hi = c["a_min"][None, :], c["a_max"][None, :]
         assert np.all(f(out["action"]) >= lo) and np.all(f(out["action"]) <= hi)
         # critic-only and actor-only calls give the same numbers
-        v2 = rlp.GaussianPolicy(None, critic, c["a_min"], c["a_max"], 1.0)(obs)["value"]
+        v2 = rlp.GaussianPolicy(None, critic, c["a_min"], c["a_max"], 1.0, precision=precision)(obs)["value"]
         assert torch.equal(v2, out["value"])
-        a2 = rlp.GaussianPolicy(actor, None, c["a_min"], c["a_max"], float(c["std"]))(obs, noise=eps)["action"]
+        a2 = rlp.GaussianPolicy(actor, None, c["a_min"], c["a_max"], float(c["std"]), precision=precision)(obs, noise=eps)["action"]
         assert torch.equal(a2, out["action"])
 
 
@@ -133,6 +134,7 @@ def test_wide_nets_are_rejected_not_silently_slow():
         m.w[l] = 1 << 20
         m.b[l] = 1 << 20
     m.out_act = 1
-    rc = lib.b200_policy_forward(16, C.byref(m), None, C.c_void_p(1 << 20), C.c_void_p(1 << 20), C.c_void_p(1 << 20),
-                                 C.c_float(0.5), None, 0, 0, 0, C.c_void_p(1 << 20), None, None, None, None)
-    assert rc == -6
+    for precision in (0, 1):
+        rc = lib.b200_policy_forward(16, C.byref(m), None, C.c_void_p(1 << 20), C.c_void_p(1 << 20), C.c_void_p(1 << 20),
+                                     C.c_float(0.5), None, 0, 0, 0, precision, C.c_void_p(1 << 20), None, None, None, None)
+        assert rc == -6

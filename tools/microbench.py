@@ -34,14 +34,15 @@ def run(kind, reps=10, T=2048, N=131072, dev="cuda"):
         y = torch.empty_like(x)
         nz = rlp.Normalization(dim, device=dev, sync=False)
         fn, nbytes, units = (lambda: nz.normalize_soa(x, out=y)), 12.0, dim * n
-    elif kind == "policy":
+    elif kind in ("policy", "policy_fp32"):
         # the reference's PPOActor_Gaussian / PPOCritic shapes for UavFntsmcParamPos (state 6, 8 gains), 1 M instances
         S, A, n = 6, 8, 1 << 20
         torch.manual_seed(0)
         mk_l = lambda i, o: torch.nn.Linear(i, o).to(dev)
         actor = [mk_l(S, 64), mk_l(64, 64), mk_l(64, 32), mk_l(32, A)]
         critic = [mk_l(S, 64), mk_l(64, 32), mk_l(32, 1)]
-        pol = rlp.GaussianPolicy(actor, critic, [0.0] * A, [5.0] * A, 0.45, device=dev)
+        pol = rlp.GaussianPolicy(actor, critic, [0.0] * A, [5.0] * A, 0.45, device=dev,
+                                 precision="fp32" if kind == "policy_fp32" else "tf32x3")
         obs = torch.randn((S, n), generator=g, device=dev, dtype=torch.float32)
         outs = pol(obs)
         fn = lambda: pol(obs, action=outs["action"], log_prob=outs["log_prob"], value=outs["value"])
@@ -61,7 +62,7 @@ def run(kind, reps=10, T=2048, N=131072, dev="cuda"):
     per = e0.elapsed_time(e1) * 1e-3 / reps
     res = {"workload": kind, "value": units / per, "unit": "elements/s", "ms_per_step": per * 1e3,
            "algorithmic_bytes_per_element": nbytes, "achieved_gbs": nbytes * units / per / 1e9}
-    if kind == "policy":
+    if kind.startswith("policy"):
         res.update({"unit": "instances/s", "flops_per_instance": flops, "achieved_tflops_fp32": flops * units / per / 1e12})
     return res
 

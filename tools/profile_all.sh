@@ -24,7 +24,8 @@ for w in "$@"; do
     gae) prof_micro gae gae_kernel ;;
     gae_flags) prof_micro gae_flags gae_kernel ;;
     mc_returns) prof_micro mc_returns mc_returns_kernel ;;
-    policy) prof_micro policy policy_forward ;;
+    policy) prof_micro policy policy_forward_tc ;;
+    policy_fp32) prof_micro policy_fp32 policy_forward_kernel ;;
     norm_stats) python tools/microbench.py norm 4 > $out/plain_norm.log 2>&1 && $NCU -k regex:norm_batch_stats -s 3 -c 1 -o $out/prof_norm_stats python tools/microbench.py norm 4 > $out/ncu_norm_stats.log 2>&1 ;;
     norm_apply) $NCU -k regex:norm_merge_apply -s 3 -c 1 -o $out/prof_norm_apply python tools/microbench.py norm 4 > $out/ncu_norm_apply.log 2>&1 ;;
   esac
