@@ -32,7 +32,10 @@ class GaussianPolicy:
                  device="cuda", seed: int = 0, env_index_offset: int = 0, actor_out_act: str = "relu",
                  precision: str = "tf32x3"):
         """``actor_layers`` / ``critic_layers``: sequences of ``torch.nn.Linear`` (CUDA, float32) or modules accepted by
-        :func:`linear_layers`.  ``a_min, a_max``: action clamp (``actor.a_min / a_max``), ``std``: ``actor.std``."""
+        :func:`linear_layers`.  ``a_min, a_max``: action clamp (``actor.a_min / a_max``), ``std``: ``actor.std``.
+        ``precision``: "tf32x3" (tensor cores, every operand split into two TF32 halves: fp32-level accuracy, default) or
+        "fp32" (FMA pipe, sums in k order)."""
+        self.precision = {"fp32": 0, "tf32x3": 1}[precision]
         self._lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
