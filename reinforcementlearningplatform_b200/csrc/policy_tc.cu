@@ -46,10 +46,16 @@ struct TcArgs {
     PolicyIO io;
 };
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
+// round-to-nearest (ties away) to TF32's 10-bit mantissa on the bit pattern: what cvt.rna.tf32.f32 does for finite
+// values, in two integer instructions instead of the multi-instruction sequence ptxas emits for the cvt
+__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the SFU (ex2.approx, rcp.approx): 5 instructions, absolute error <= 3e-7 over the
+// whole range (the quotient saturates to 0 / 2 for large |x|), against ~25 instructions for the 1-ulp tanhf.  The
+// 3xTF32 products carry ~1e-6 themselves, so the accurate version would buy nothing here (policy.cu keeps it).
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
     hi = to_tf32(x);
@@ -124,7 +130,7 @@ __device__ __forceinline__ void layer_tc(const float2 *__restrict__ wf, const fl
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 v[q] = d[mt][nt][q];
-                if (actfn == 2) v[q] = tanhf(v[q]);
+                if (actfn == 2) v[q] = tanh_fast(v[q]);
                 else if (actfn == 1) v[q] = fmaxf(v[q], 0.0f);
             }
             float *r0 = act + (mt * 16 + g) * LD + nt * 8 + 2 * t; // c0, c1: (row g, cols 2t, 2t + 1)
