@@ -51,11 +51,11 @@ ALGO_BYTES = {
 # algorithmic fp64 work per env-step (weighted flops, SURVEY.md section 8d convention), used for the fp64-pipe view
 ALGO_FLOPS = {"uav_pos": 5100.0, "uav_att": 3300.0, "cartpole": 3100.0, "ugvo": 54000.0, "soi": 125.0, "fas": 570.0}
 # what the kernel really executes per env-step, counted from the ncu SASS page of the profiled launch
-# (profiles/r1/uav_pos_step_ncu_v4_ophist.txt): fp64-pipe instructions (DFMA + DMUL + DADD + DSETP) and flops (DFMA = 2)
-EXEC_F64 = {"uav_pos": {"pipe_inst": 2342.0, "flops": 3530.0, "src": "profiles/r1/uav_pos_step_ncu_v4_ophist.txt"}}
+# (profiles/r1/uav_pos_step_ncu_v5_ophist.txt): fp64-pipe instructions (DFMA + DMUL + DADD + DSETP) and flops (DFMA = 2)
+EXEC_F64 = {"uav_pos": {"pipe_inst": 2129.8, "flops": 3222.9, "src": "profiles/r1/uav_pos_step_ncu_v5_ophist.txt"}}
 # DRAM bytes per launch of the dominant kernel from the `ncu --set full` capture (dram__bytes_read + write), at the
 # profiled size; None where no capture is committed
-NCU_TRAFFIC = {("uav_pos", "f64", 1 << 20): {"bytes": 344107520 + 426992640, "src": "profiles/r1/uav_pos_step_ncu_v4_keys.txt"}}
+NCU_TRAFFIC = {("uav_pos", "f64", 1 << 20): {"bytes": 347939840 + 498304256, "src": "profiles/r1/uav_pos_step_ncu_v5_keys.txt"}}
 
 WORKLOADS = {
     "uav_pos": dict(n=1 << 20, desc="UavFntsmcParam position tracking, dt=0.02, time_max=10, 8 gains~U(0,5)/step"),
@@ -336,6 +336,22 @@ def also_workloads(args, dev, dtype, peaks):
     out.append({"workload": "gae", "T": T, "N": N, "value": T * N / per, "unit": "elements/s", "ms_per_step": per * 1e3,
                 "hbm_frac": 28.0 * T * N / per / 1e9 / hbm,
                 "desc": "PPO2 GAE reverse scan + (sum, sum^2, n) statistics, float32, time-major [T, N]"})
+    del r, vs, vsn, done, succ, adv, vt
+    torch.cuda.empty_cache()
+    # the kernels either side of the step: GAE over the rollout's own u8 / i32 columns, PPO v1 returns,
+    # running normalisation, and the batched actor + critic forward (tensor cores, 3xTF32, and the FP32-FMA version)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import microbench
+    descs = {"gae_flags": "K-GAE over the device-resident rollout (u8 done, i32 flag)", "mc_returns": "PPO v1 Monte-Carlo returns",
+             "norm": "running mean/std normalisation of a [6, 4 M] float32 batch (statistics + merge/apply)",
+             "policy": "actor 6-64-64-32-8 + critic 6-64-32-1 forward, sample, clamp, log-prob for 1 M instances (3xTF32 MMA)",
+             "policy_fp32": "the same forward on the FP32 FMA pipe"}
+    for kind, desc in descs.items():
+        m = microbench.run(kind, 10, dev=dev)
+        m["hbm_frac"] = m["achieved_gbs"] / hbm
+        m["desc"] = desc
+        out.append(m)
+        torch.cuda.empty_cache()
     return out
 
 
