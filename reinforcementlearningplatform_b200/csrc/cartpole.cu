@@ -251,7 +251,12 @@ int cartpole_step(int dtype, int64_t n, const void *params, const b200env_io *io
     if (!io->state || !io->time || !io->action || !io->next_obs || !io->reward || !io->done || !io->flag)
         return B200ENV_ENULL;
     if ((flags & B200ENV_AUTO_RESET) && !io->episode) return B200ENV_ENULL;
-    B200_LAUNCH_TIO(cartpole_step_kernel, b200_grid(n), B200_BLOCK, s, p, *io, n, flags, seed, off);
+    // Small batches (config #2: 65,536 instances = 512 blocks of 128 on 148 SMs, 3.46 blocks per SM -> the SMs that get
+    // a 4th block set the time): halve the block until the grid has >= 8 blocks per SM so that the tail is <= 1 / 8
+    int block = B200_BLOCK;
+    const int64_t want = (int64_t)b200_persistent_grid((int64_t)1 << 40, 8, 32);
+    while (block > 32 && (n + block - 1) / block < want) block >>= 1;
+    B200_LAUNCH_TIO(cartpole_step_kernel, b200_grid(n, block), block, s, p, *io, n, flags, seed, off);
     return b200_check_launch();
 }
 
