@@ -68,6 +68,8 @@ def main(argv=None):
         log.append(row)
         if rank == 0:
             print(json.dumps(row))
+    if world > 1:
+        torch.distributed.destroy_process_group()
     return log
 
 

@@ -71,3 +71,30 @@ def test_random_pos0_reset_quirk_fixture_and_oracle(oracle_lib):
     orc.reset()
     assert np.array_equal(orc.state[9:12], first)
     assert np.array_equal(orc.state[51:54], orc.state[0:3]) and not np.array_equal(orc.state[0:3], first)
+
+
+@pytest.mark.parametrize("name,h,both", [("cartpole", 0.002, False), ("cartpole_angleonly_env", 0.001, True),
+                                         ("fas", 0.002, True), ("ballbalancer", 0.002, True)])
+def test_time_loop_substep_trace(name, h, both, oracle_lib):
+    """Note N1: `while self.time < tt` with h = dt / 10 takes 10 OR 11 RK4 sub-steps per control period,
+    depending on how the float64 additions of h round.  The fixture's recorded `time` column gives the reference's count
+    per step; the restatement must take exactly the same number on every step, and both counts occur (`both`: the
+    CartPole fixture's episodes are too short for an 11)."""
+    import numpy as np
+    g = load_golden(name)
+    T, L = g["reward"].shape
+    be = OracleBackend(name, L)
+    be.set_state(g["state0"], g["time0"])
+    prev_time = g["time0"].copy()
+    seen = set()
+    for t in range(T):
+        be.step(g["actions"][t])
+        ref_count = np.rint((g["time"][t] - prev_time) / h).astype(int)
+        assert np.array_equal(be.env.substeps, ref_count), (name, t, be.env.substeps, ref_count)
+        seen.update(ref_count.tolist())
+        prev_time = g["time"][t].copy()
+        lanes = np.nonzero(g["done"][t])[0]
+        if len(lanes):
+            be.set_state(g["reset_state"][t][lanes], g["reset_time"][t][lanes], lanes)
+            prev_time[lanes] = g["reset_time"][t][lanes]
+    assert seen == ({10, 11} if both else {10}), seen
