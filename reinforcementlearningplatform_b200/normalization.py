@@ -29,6 +29,18 @@ from . import _lib
 EPS = 1e-8  # utils/classes.py:654
 
 
+def gather_batch_stats(batch: torch.Tensor, out: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
+    """All-gather the per-rank batch statistics ``[1, 3, dim]`` into ``[world, 3, dim]`` (rank order): the only exchange
+    of the multi-GPU normaliser, 3 x dim doubles per rank.  Every rank then merges the same list in the same order
+    (``b200_norm_merge_apply`` with ``n_batches = world``), so the running statistics stay bit-identical across ranks."""
+    import torch.distributed as dist
+    w = dist.get_world_size(group)
+    if out is None or out.shape[0] != w:
+        out = torch.zeros((w,) + tuple(batch.shape[1:]), dtype=batch.dtype, device=batch.device)
+    dist.all_gather_into_tensor(out, batch.contiguous(), group=group)
+    return out
+
+
 class _RunningView:
     """``Normalization.running_ms`` with the reference's attribute names, read from / written to the device state."""
 
@@ -125,10 +137,7 @@ class Normalization:
                 nb = 1
                 w = self._world()
                 if w > 1:
-                    import torch.distributed as dist
-                    if self._gathered is None or self._gathered.shape[0] != w:
-                        self._gathered = torch.zeros(w, 3, self.dim, dtype=torch.float64, device=self.device)
-                    dist.all_gather_into_tensor(self._gathered, self._batch, group=self.group)
+                    self._gathered = gather_batch_stats(self._batch, self._gathered, self.group)
                     nb, batch = w, self._gathered
             _lib.check(self._lib.b200_norm_merge_apply(code, n, self.dim, p(x), p(y), p(batch), nb, p(self._run),
                                                        p(self._run_next), 1 if update else 0, EPS, self._stream()),

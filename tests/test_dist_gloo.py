@@ -61,7 +61,14 @@ def _worker(rank, world, port, q):
     for t in range(40):
         orc.step(acts[t][:, off:off + n_local])
         traj.append(orc.state.copy())
-    q.put((rank, [s.tolist() for s in sizes], ok_grad, st.tolist(), np.stack(traj), red.nbytes))
+    # 5. running normaliser: per-rank batch statistics gathered in rank order, merged by the rule of csrc/norm.cu
+    from reinforcementlearningplatform_b200.normalization import gather_batch_stats, merge_stats_reference
+    xs = np.random.default_rng(100 + rank).normal(rank, 1.0 + rank, (3, 500 + 100 * rank))
+    mine = torch.from_numpy(np.stack([np.full(3, xs.shape[1], dtype=np.float64), xs.mean(1),
+                                      ((xs - xs.mean(1, keepdims=True)) ** 2).sum(1)])[None])
+    allb = gather_batch_stats(mine).numpy()
+    run = merge_stats_reference((np.zeros(3), np.zeros(3), np.zeros(3)), [tuple(b) for b in allb])
+    q.put((rank, [s.tolist() for s in sizes], ok_grad, st.tolist(), np.stack(traj), red.nbytes, [r.tolist() for r in run]))
     dist.destroy_process_group()
 
 
@@ -85,6 +92,12 @@ def test_world2_gloo(oracle_lib):
     for r in res:
         np.testing.assert_allclose(r[3], [adv.sum(), (adv ** 2).sum(), adv.size])
         assert r[5] == (4 * 8 + 8 + 8 * 2 + 2) * 4
+    # normaliser: both ranks hold the same merged statistics, equal to those of the concatenated batch
+    xs = np.concatenate([np.random.default_rng(100 + r).normal(r, 1.0 + r, (3, 500 + 100 * r)) for r in range(world)], axis=1)
+    assert res[0][6] == res[1][6]
+    np.testing.assert_allclose(res[0][6][0], np.full(3, xs.shape[1]))
+    np.testing.assert_allclose(res[0][6][1], xs.mean(1), rtol=1e-13)
+    np.testing.assert_allclose(np.array(res[0][6][2]) / xs.shape[1], xs.var(1), rtol=1e-12)
     # trajectories: the two shards side by side == one unsharded run (auto-reset draws keyed by the global index)
     from oracle import oracle
     import reinforcementlearningplatform_b200 as rlp
