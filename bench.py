@@ -355,6 +355,44 @@ def also_workloads(args, dev, dtype, peaks):
     return out
 
 
+def exchange_times(dev, reps=50):
+    """The only collectives of the path, timed on the device over NCCL: the DPPO2 gradient
+    average as one all-reduce of a flat fp32 buffer (154 k parameters of the 41-256-256-{2,1} demo nets, and 9.5 k of
+    the 6-64-64-32 / 6-64-32 nets), the 3-double advantage statistics, the 3 x dim doubles of the normaliser."""
+    import torch.distributed as dist
+    out = {}
+    for name, t in (("grad_allreduce_154k_fp32", torch.zeros(154_000, dtype=torch.float32, device=dev)),
+                    ("grad_allreduce_9k5_fp32", torch.zeros(9_500, dtype=torch.float32, device=dev)),
+                    ("adv_stats_3xf64", torch.zeros(3, dtype=torch.float64, device=dev))):
+        for _ in range(5):
+            dist.all_reduce(t)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dist.all_reduce(t)
+        e1.record()
+        torch.cuda.synchronize()
+        us = torch.tensor([e0.elapsed_time(e1) * 1e3 / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(us, op=dist.ReduceOp.MAX)
+        out[name] = {"us": float(us.item()), "bytes": t.numel() * t.element_size()}
+    g = torch.zeros(dist.get_world_size(), 3, 6, dtype=torch.float64, device=dev)
+    b = torch.zeros(1, 3, 6, dtype=torch.float64, device=dev)
+    for _ in range(5):
+        dist.all_gather_into_tensor(g, b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dist.all_gather_into_tensor(g, b)
+    e1.record()
+    torch.cuda.synchronize()
+    us = torch.tensor([e0.elapsed_time(e1) * 1e3 / reps], device=dev, dtype=torch.float64)
+    dist.all_reduce(us, op=dist.ReduceOp.MAX)
+    out["norm_stats_allgather_18xf64"] = {"us": float(us.item()), "bytes": 144}
+    return out
+
+
 def rollout_pipeline(workload, n, T, dev, dist_on, seed=5):
     """config #3: a T-step rollout written by the step kernel straight into a device-resident time-major float32
     buffer (rollout.RolloutBuffer), then K-GAE over it and the global advantage normalisation (3-double all-reduce when
@@ -485,8 +523,12 @@ def main():
             line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{cn} instances x {csteps} steps ({cdt:.1f} s), C restatement of the "
                                               "reference (oracle/), OpenMP over instances",
-                                    "reference_python_loop": "1.36e3 env-steps/s per core measured in the build container "
-                                                             "(BASELINE.md section 2); pure Python, cannot travel to the GPU box"}
+                                    "reference_python_loop": "1.6e3 env-steps/s on one core measured in the build container "
+                                                             "(oracle/bench_reference_python.py -> profiles/r1/"
+                                                             "reference_python_cpu.json); pure Python, cannot travel to "
+                                                             "the GPU box"}
+    if dist_on:
+        line["exchange"] = exchange_times(dev)
     if rank == 0:
         print(json.dumps(line))
     if dist_on:
