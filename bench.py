@@ -352,6 +352,28 @@ def also_workloads(args, dev, dtype, peaks):
         m["desc"] = desc
         out.append(m)
         torch.cuda.empty_cache()
+    # the whole on-device collection step of a PPO2 iteration (ppo2.VecPPO2.collect): K-POLICY -> step kernel (rows of
+    # the rollout buffer written in place) -> K-NORM on the reward, 1 M UavFntsmcParam-pos instances, 16-step rollout
+    import reinforcementlearningplatform_b200 as rlp
+    from reinforcementlearningplatform_b200.ppo2 import VecPPO2, reference_nets
+    n = WORKLOADS["uav_pos"]["n"]
+    env = make_env("uav_pos", n, dev, 0, torch.float64, io_dtype=torch.float32)
+    env.reset(True)
+    actor, critic = reference_nets(env.state_dim, env.action_dim, dev, init_std=0.45)
+    agent = VecPPO2(env, actor, critic, {"buffer_size": 16, "K_epochs": 1}, std=0.45)
+    agent.collect()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    agent.collect()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out.append({"workload": "ppo2_collect_uav_pos", "T": 16, "envs": n, "value": 16 * n / (ms * 1e-3), "unit": "env-steps/s",
+                "ms_per_step": ms / 16, "desc": "policy forward (3xTF32) + fused UAV step + reward normalisation per time step, "
+                                                 "everything device-resident (float32 I/O, fp64 state and arithmetic)"})
+    del agent, env
+    torch.cuda.empty_cache()
     return out
 
 
