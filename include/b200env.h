@@ -67,7 +67,7 @@ enum b200env_err {
     B200ENV_EPARAMS = -3, /* params_bytes does not match the struct of this env */
     B200ENV_ENULL   = -4, /* a required pointer is NULL */
     B200ENV_ECUDA   = -5, /* CUDA error at launch; see b200env_last_cuda_error() */
-    B200ENV_ESIZE   = -6  /* n_envs <= 0 or too large */
+    B200ENV_ESIZE   = -6  /* n_envs <= 0 or >= 2^31 (one GPU cannot hold more), or a net too wide for K-POLICY */
 };
 
 /* step flags */

@@ -43,7 +43,7 @@ const Family *family(int env_id) {
 int check_common(const Family *f, int dtype, int64_t n, const void *params, size_t bytes, const b200env_io *io) {
     if (!f) return B200ENV_EENV;
     if (dtype != B200ENV_F64 && dtype != B200ENV_F32) return B200ENV_EDTYPE;
-    if (n <= 0 || n > ((int64_t)1 << 40)) return B200ENV_ESIZE;
+    if (n <= 0 || n >= ((int64_t)1 << 31)) return B200ENV_ESIZE; // 32-bit instance index in the SoA accessors (common.cuh)
     if (!params || !io) return B200ENV_ENULL;
     if (bytes != f->params_bytes) return B200ENV_EPARAMS;
     return B200ENV_OK;

@@ -102,6 +102,28 @@ __device__ __forceinline__ T pow_from_log(T L, T a) {
 // the kernel computes in T = double (b200env_io::io_dtype == B200ENV_F32): the RL side of the reference is float32
 // (actor output, RolloutBuffer.to_tensor utils/classes.py:292-301), so float32 I/O halves the PCIe / HBM bytes of the
 // interface without touching the fp64 trajectory.  float -> double is exact; outputs are rounded once on store.
+// Addressing of element (field, i) of a field-major [fields][n] buffer.  Default: byte address = base + i * ES + n *
+// (field * ES) with i and n taken as 32-bit values (b200env_* rejects n >= 2^31: no env fits more instances in 180 GB)
+// -- two IMAD.WIDE.U32, the second with an immediate multiplier, and the first is common to all fields of a buffer.
+// The index form `base[field * n + i]` cost ~8 instructions per access in the UAV kernels (ncu source page: 15 % of all
+// executed instructions); switching gave +18 % on K-UAVP and +16 % on K-UAVA.  B200_SOA_INDEX (defined by ugvo.cu,
+// whose warp-cooperative kernel gets slower with the extra live pointer pairs) keeps the index form.
+#ifndef B200_SOA_INDEX
+template <typename T, bool IO32, typename I>
+__device__ __forceinline__ T ldio(const void *base, I n, int field, I i) {
+    constexpr int ES = IO32 ? 4 : (int)sizeof(T);
+    const char *p = static_cast<const char *>(base) + (uint64_t)(uint32_t)i * ES + (uint64_t)(uint32_t)n * (uint32_t)(field * ES);
+    if (IO32) return (T) * reinterpret_cast<const float *>(p);
+    return *reinterpret_cast<const T *>(p);
+}
+template <typename T, bool IO32, typename I>
+__device__ __forceinline__ void stio(void *base, I n, int field, I i, T v) {
+    constexpr int ES = IO32 ? 4 : (int)sizeof(T);
+    char *p = static_cast<char *>(base) + (uint64_t)(uint32_t)i * ES + (uint64_t)(uint32_t)n * (uint32_t)(field * ES);
+    if (IO32) *reinterpret_cast<float *>(p) = (float)v;
+    else *reinterpret_cast<T *>(p) = v;
+}
+#else
 template <typename T, bool IO32, typename I>
 __device__ __forceinline__ T ldio(const void *base, I n, int field, I i) {
     if (IO32) return (T) static_cast<const float *>(base)[(I)field * n + i];
@@ -112,6 +134,7 @@ __device__ __forceinline__ void stio(void *base, I n, int field, I i, T v) {
     if (IO32) static_cast<float *>(base)[(I)field * n + i] = (float)v;
     else static_cast<T *>(base)[(I)field * n + i] = v;
 }
+#endif
 
 // Division by a quantity that is fixed over many quotients.  One IEEE reciprocal r = RN(1 / d), then per quotient
 // q = a r and one FMA-corrected Newton step q + (a - q d) r (Markstein): 3 instructions instead of the ~25 of an fp64
@@ -182,6 +205,18 @@ struct Philox {
 // The index type I is int64_t in general; the hot UAV kernels are also instantiated with uint32_t (chosen by the
 // launcher when fields * n < 2^32), which turns ~5 instructions of 64-bit address arithmetic per access into
 // IMAD + IMAD.WIDE.U32 (8 % of the executed instructions of the UAV-pos step, ncu).
+#ifndef B200_SOA_INDEX
+template <typename T, typename I>
+__device__ __forceinline__ T ld(const void *base, I n, int field, I i) {
+    const char *bi = static_cast<const char *>(base) + (uint64_t)(uint32_t)i * sizeof(T);
+    return *reinterpret_cast<const T *>(bi + (uint64_t)(uint32_t)n * (uint32_t)(field * (int)sizeof(T)));
+}
+template <typename T, typename I>
+__device__ __forceinline__ void st(void *base, I n, int field, I i, T v) {
+    char *bi = static_cast<char *>(base) + (uint64_t)(uint32_t)i * sizeof(T);
+    *reinterpret_cast<T *>(bi + (uint64_t)(uint32_t)n * (uint32_t)(field * (int)sizeof(T))) = v;
+}
+#else
 template <typename T, typename I>
 __device__ __forceinline__ T ld(const void *base, I n, int field, I i) {
     return static_cast<const T *>(base)[(I)field * n + i];
@@ -190,6 +225,7 @@ template <typename T, typename I>
 __device__ __forceinline__ void st(void *base, I n, int field, I i, T v) {
     static_cast<T *>(base)[(I)field * n + i] = v;
 }
+#endif
 
 // ---------------------------------------------------------------------------
 // host-side launch helpers

@@ -15,6 +15,7 @@
 // nearest crossing).  Reset / observe and the in-step auto-reset run one warp per instance: warp votes implement the
 // lane-parallel rejection sampling of the obstacle map (32 candidates per round, lowest legal index wins, so the
 // result is identical to trying the candidates one by one).
+#define B200_SOA_INDEX // see common.cuh: the index form is faster for this warp-cooperative kernel
 #include "common.cuh"
 
 namespace {
