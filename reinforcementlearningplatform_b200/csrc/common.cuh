@@ -30,6 +30,7 @@ template <> struct Mth<double> {
         ::sincos(a, sa, ca); ::sincos(b, sb, cb);
     }
     static __device__ __forceinline__ double rcp(double y) { return 1.0 / y; }
+    static __device__ __forceinline__ double div(double x, double y) { return x / y; }
     static __device__ __forceinline__ double tanh(double x) { return ::tanh(x); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
@@ -44,6 +45,7 @@ template <> struct Mth<double> {
         fm64::sincos2(a, b, sa, ca, sb, cb);
     }
     static __device__ __forceinline__ double rcp(double y) { return fm64::rcp(y); }
+    static __device__ __forceinline__ double div(double x, double y) { return fm64::div(x, y); }
     static __device__ __forceinline__ double tanh(double x) { return fm64::tanh(x); }
     static __device__ __forceinline__ double log(double x) { return fm64::log(x); }
     static __device__ __forceinline__ double exp(double x) { return fm64::exp(x); }
@@ -74,6 +76,7 @@ template <> struct Mth<float> {
         ::sincosf(a, sa, ca); ::sincosf(b, sb, cb);
     }
     static __device__ __forceinline__ float rcp(float y) { return 1.0f / y; }
+    static __device__ __forceinline__ float div(float x, float y) { return x / y; }
     static __device__ __forceinline__ float tan(float x) { return ::tanf(x); }
     static __device__ __forceinline__ float tanh(float x) { return ::tanhf(x); }
     static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }

@@ -78,12 +78,11 @@ __device__ __forceinline__ void sincos_core(double x, double *sn, double *cs) {
     double pc = kC[5];
     pc = fma(pc, z, kC[4]); pc = fma(pc, z, kC[3]); pc = fma(pc, z, kC[2]); pc = fma(pc, z, kC[1]); pc = fma(pc, z, kC[0]);
     pc = fma(z, fma(z, pc, -0.5), 1.0);
-    double s = (n & 1) ? pc : ps;
-    double c = (n & 1) ? ps : pc;
-    if (n & 2) s = -s;
-    if ((n + 1) & 2) c = -c;
-    *sn = s;
-    *cs = c;
+    const double s = (n & 1) ? pc : ps;
+    const double c = (n & 1) ? ps : pc;
+    // quadrant signs straight into the sign bit: bit 1 of n (resp. n + 1) moved to bit 31 of the high word
+    *sn = __hiloint2double(__double2hiint(s) ^ ((n & 2) << 30), __double2loint(s));
+    *cs = __hiloint2double(__double2hiint(c) ^ (((n + 1) & 2) << 30), __double2loint(c));
 }
 
 __device__ __forceinline__ void sincos(double x, double *sn, double *cs) {
@@ -97,7 +96,7 @@ __device__ __forceinline__ void sincos(double x, double *sn, double *cs) {
 // three angles behind ONE range check, so that the six polynomial chains share a basic block
 __device__ __forceinline__ void sincos3(double a, double b, double c, double *sa, double *ca, double *sb, double *cb,
                                         double *sc, double *cc) {
-    if (!(fmax(fmax(fabs(a), fabs(b)), fabs(c)) < 1.0e5) || a != a || b != b || c != c) {
+    if (!(fabs(a) + fabs(b) + fabs(c) < 1.0e5)) { // huge, inf or NaN in any of the three (the sum propagates NaN)
         ::sincos(a, sa, ca);
         ::sincos(b, sb, cb);
         ::sincos(c, sc, cc);
@@ -108,7 +107,7 @@ __device__ __forceinline__ void sincos3(double a, double b, double c, double *sa
     sincos_core(c, sc, cc);
 }
 __device__ __forceinline__ void sincos2(double a, double b, double *sa, double *ca, double *sb, double *cb) {
-    if (!(fmax(fabs(a), fabs(b)) < 1.0e5) || a != a || b != b) {
+    if (!(fabs(a) + fabs(b) < 1.0e5)) {
         ::sincos(a, sa, ca);
         ::sincos(b, sb, cb);
         return;

@@ -215,13 +215,15 @@ __device__ __forceinline__ void att_control(const Consts<T> &c, const T *x, cons
 template <typename T>
 __device__ __forceinline__ T cos_of_asin(T u, T phi_d) {
     if (sizeof(T) == 4) return Mth<T>::sqrt(Mth<T>::max(Mth<T>::fma(-u, u, (T)1), (T)0));
-    return Mth<T>::cos(phi_d);
+    T sn, cs;
+    Mth<T>::sincos(phi_d, &sn, &cs); // constant-bank kernels instead of libdevice's cos()
+    return cs;
 }
 
 // ref_cmd.py:4-43, one channel
 template <typename T>
 __device__ __forceinline__ void ref_channel(T time, T A, T period, T bias, T phase, T &r, T &dr, T &ddr) {
-    const T w = (T)(2 * M_PI) / period;
+    const T w = Mth<T>::div((T)(2 * M_PI), period); // <= 1 ulp from the IEEE quotient (fastmath64.cuh), ~half the instructions
     T s, co;
     Mth<T>::sincos(w * time + phase, &s, &co);
     r = A * s + bias;
