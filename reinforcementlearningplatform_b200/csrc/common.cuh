@@ -144,6 +144,14 @@ __device__ __forceinline__ void stio(void *base, I n, int field, I i, T v) {
 // division.  The corrected quotient is the IEEE quotient except in rare half-way cases (<= 1 ulp there), far inside
 // the 1e-12 parity bar; NaN / inf numerators propagate.  The RK4 updates of every reference env divide by 6
 // (`(K1 + 2 K2 + 2 K3 + K4) / 6`), the time-loop envs 40+ times per control period.
+// clamp against bounds that are never NaN: two compare-selects instead of the NaN-aware fmin / fmax pair (6 instructions
+// each in fp64).  A NaN x passes through, like np.clip.
+template <typename T>
+__device__ __forceinline__ T clampc(T x, T lo, T hi) {
+    x = x < lo ? lo : x;
+    return x > hi ? hi : x;
+}
+
 template <typename T>
 struct Divisor {
     T d, r;

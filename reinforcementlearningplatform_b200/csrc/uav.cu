@@ -349,21 +349,22 @@ __device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c,
     t1.eval(x[6], x[7], x[8], true);
     // ---- uo_2_ref_angle_throttle(limit = pi/4), uav_pos_ctrl.py:339-357
     const T uf = (ctrl[2] + c.g) * c.m / (t1.cphi * t1.cth);
-    const T asin_phi_d = Mth<T>::min(Mth<T>::max((ctrl[0] * t1.spsi - ctrl[1] * t1.cpsi) * c.m / uf, (T)-1), (T)1);
+    const T asin_phi_d = clampc<T>(Mth<T>::div((ctrl[0] * t1.spsi - ctrl[1] * t1.cpsi) * c.m, uf), (T)-1, (T)1);
     T phi_d = Mth<T>::asin(asin_phi_d);
-    const T asin_theta_d = Mth<T>::min(
-        Mth<T>::max((ctrl[0] * t1.cpsi + ctrl[1] * t1.spsi) * c.m / (uf * cos_of_asin<T>(asin_phi_d, phi_d)), (T)-1), (T)1);
+    const T asin_theta_d = clampc<T>(
+        Mth<T>::div((ctrl[0] * t1.cpsi + ctrl[1] * t1.spsi) * c.m, uf * cos_of_asin<T>(asin_phi_d, phi_d)), (T)-1, (T)1);
     T theta_d = Mth<T>::asin(asin_theta_d);
     const T lim = (T)p.att_limit;
-    phi_d = Mth<T>::max(Mth<T>::min(phi_d, lim), -lim);
-    theta_d = Mth<T>::max(Mth<T>::min(theta_d, lim), -lim);
+    phi_d = clampc<T>(phi_d, -lim, lim);
+    theta_d = clampc<T>(theta_d, -lim, lim);
     // ---- generate_action_4_uav, uav_pos_ctrl.py:470-481: finite-difference reference rates, clipped, integrated back
     T rho_d[3] = {phi_d, theta_d, ref[3]};
-    T drho_d[3] = {(phi_d - aref0) / c.dt, (theta_d - aref1) / c.dt, dref[3]};
+    const Divisor<T> by_dt(c.dt);
+    T drho_d[3] = {by_dt.div(phi_d - aref0), by_dt.div(theta_d - aref1), dref[3]};
     const T rl = (T)p.dot_att_ref_limit;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        drho_d[k] = Mth<T>::min(Mth<T>::max(drho_d[k], -rl), rl);
+        drho_d[k] = clampc<T>(drho_d[k], -rl, rl);
         rho_d[k] = rho_d[k] + drho_d[k] * c.dt;
         st<T>(io.state, n, P_AREF + k, i, rho_d[k]); // att_ref = rho_d (persists across resets, uav_pos_ctrl.py:329)
     }

@@ -151,20 +151,20 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
     } else {
         // uo_2_ref_angle_throttle, uav_pos_ctrl.py:67-76 (+ np.clip to the attitude zone)
         uf = (a[2] + c.g) * c.m / (t1.cphi * t1.cth);
-        const T asin_phi_d = Mth<T>::min(Mth<T>::max((a[0] * t1.spsi - a[1] * t1.cpsi) * c.m / uf, (T)-1), (T)1);
+        const T asin_phi_d = clampc<T>(Mth<T>::div((a[0] * t1.spsi - a[1] * t1.cpsi) * c.m, uf), (T)-1, (T)1);
         T phi_d = Mth<T>::asin(asin_phi_d);
-        const T asin_theta_d = Mth<T>::min(
-            Mth<T>::max((a[0] * t1.cpsi + a[1] * t1.spsi) * c.m / (uf * cos_of_asin<T>(asin_phi_d, phi_d)), (T)-1), (T)1);
+        const T asin_theta_d = clampc<T>(
+            Mth<T>::div((a[0] * t1.cpsi + a[1] * t1.spsi) * c.m, uf * cos_of_asin<T>(asin_phi_d, phi_d)), (T)-1, (T)1);
         T theta_d = Mth<T>::asin(asin_theta_d);
-        phi_d = Mth<T>::min(Mth<T>::max(phi_d, (T)r.att_zone_min[0]), (T)r.att_zone_max[0]);
-        theta_d = Mth<T>::min(Mth<T>::max(theta_d, (T)r.att_zone_min[1]), (T)r.att_zone_max[1]);
+        phi_d = clampc<T>(phi_d, (T)r.att_zone_min[0], (T)r.att_zone_max[0]);
+        theta_d = clampc<T>(theta_d, (T)r.att_zone_min[1], (T)r.att_zone_max[1]);
         // reference shaping: rate-limited attitude command (UavHoverOuterLoop.py:127-131)
         const T att_new[3] = {phi_d, theta_d, (T)0};
         T att_ref[3], datt[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             T d = (att_new[k] - aref_old[k]) / c.dt;
-            d = Mth<T>::min(Mth<T>::max(d, (T)r.dot_att_min[k]), (T)r.dot_att_max[k]);
+            d = clampc<T>(d, (T)r.dot_att_min[k], (T)r.dot_att_max[k]);
             datt[k] = d;
             att_ref[k] = d * c.dt + aref_old[k];
             st<T>(io.state, n, R_AREF + k, i, att_ref[k]);
@@ -183,7 +183,7 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
             att_control<T>(c, x, t1, k1, k2, gam, lmd, al, be, s1, att_ref, datt, torque, d1);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                torque[k] = Mth<T>::min(Mth<T>::max(torque[k], -(T)r.att_saturation[k]), (T)r.att_saturation[k]);
+                torque[k] = clampc<T>(torque[k], -(T)r.att_saturation[k], (T)r.att_saturation[k]);
                 st<T>(io.state, n, R_S1 + k, i, s1[k]);
             }
         }
