@@ -22,10 +22,32 @@ template <typename T> __device__ __forceinline__ T sq3_tanh10(const T *v) { // n
     return sq3<T>(t);
 }
 
+// Reciprocals of the observation normalisers, computed once on the host (launcher): the 36 IEEE divisions of the three
+// get_state() evaluations per step were 19 % of the kernel's instructions (ncu source page).  a / d is evaluated as
+// q = a r, q + (a - q d) r (Markstein: the IEEE quotient except in rare half-way cases, <= 1 ulp).
+struct RobDerived {
+    double r_pos[3], r_vel[3], r_att[3], r_datt[3];
+};
+static inline RobDerived rob_derive(const RP &r) {
+    RobDerived d;
+    for (int k = 0; k < 3; ++k) {
+        d.r_pos[k] = 1.0 / r.e_pos_span[k];
+        d.r_vel[k] = 1.0 / r.vel_span[k];
+        d.r_att[k] = 1.0 / r.e_att_span[k];
+        d.r_datt[k] = 1.0 / r.e_dot_att_span_neg[k];
+    }
+    return d;
+}
+template <typename T>
+__device__ __forceinline__ T qdiv(T a, double d, double rcp) {
+    const T q = a * (T)rcp;
+    return Mth<T>::fma(Mth<T>::fma(-q, (T)d, a), (T)rcp, q);
+}
+
 // get_state of the four wrappers.  x: 12 states, t: trig of the attitude, time: self.time
 template <typename T, int V>
-__device__ __forceinline__ void observe(const RP &r, const b200env_io &io, int64_t n, int64_t i, const T *x,
-                                        const Trig<T> &t, double time, T *o, T *e_out, T *de_out) {
+__device__ __forceinline__ void observe(const RP &r, const RobDerived &rd, const b200env_io &io, int64_t n, int64_t i,
+                                        const T *x, const Trig<T> &t, double time, T *o, T *e_out, T *de_out) {
     const T g = (T)r.static_gain;
     T d1[3];
     d1[0] = x[9] + (t.sphi * t.tth) * x[10] + (t.cphi * t.tth) * x[11]; // dot_rho1 = f1 . pqr
@@ -36,14 +58,14 @@ __device__ __forceinline__ void observe(const RP &r, const b200env_io &io, int64
         for (int k = 0; k < 3; ++k) {
             e_out[k] = x[k] - ld<T>(io.state, n, R_PREF + k, i);
             de_out[k] = x[3 + k];
-            o[k] = e_out[k] / (T)r.e_pos_span[k] * g;
-            o[3 + k] = (T)2 * x[3 + k] / (T)r.vel_span[k] * g;
+            o[k] = qdiv<T>(e_out[k], r.e_pos_span[k], rd.r_pos[k]) * g;
+            o[3 + k] = qdiv<T>((T)2 * x[3 + k], r.vel_span[k], rd.r_vel[k]) * g;
         }
         if (V == 1) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                o[6 + k] = (x[6 + k] - ld<T>(io.state, n, R_AREF + k, i)) / (T)r.e_att_span[k] * g;
-                o[9 + k] = (d1[k] - ld<T>(io.state, n, R_DAREF + k, i)) / (T)r.e_dot_att_span_neg[k] * g; // sic (N10)
+                o[6 + k] = qdiv<T>(x[6 + k] - ld<T>(io.state, n, R_AREF + k, i), r.e_att_span[k], rd.r_att[k]) * g;
+                o[9 + k] = qdiv<T>(d1[k] - ld<T>(io.state, n, R_DAREF + k, i), r.e_dot_att_span_neg[k], rd.r_datt[k]) * g; // sic (N10)
             }
         }
     } else {
@@ -54,12 +76,12 @@ __device__ __forceinline__ void observe(const RP &r, const b200env_io &io, int64
                            V == 2 ? (T)0 : (T)r.ref_bias_a[k], ld<T>(io.state, n, R_PHS + k, i), ref, dref, dd);
             if (V == 2) {
                 e_out[k] = x[6 + k] - ref; de_out[k] = d1[k] - dref;
-                o[k] = e_out[k] / (T)r.e_att_span[k] * g;
-                o[3 + k] = de_out[k] / (T)r.e_dot_att_span_neg[k] * g; // sic (N10)
+                o[k] = qdiv<T>(e_out[k], r.e_att_span[k], rd.r_att[k]) * g;
+                o[3 + k] = qdiv<T>(de_out[k], r.e_dot_att_span_neg[k], rd.r_datt[k]) * g; // sic (N10)
             } else {
                 e_out[k] = x[k] - ref; de_out[k] = x[3 + k] - dref;
-                o[k] = e_out[k] / (T)r.e_pos_span[k] * g;
-                o[3 + k] = de_out[k] / (T)r.vel_span[k] * g;
+                o[k] = qdiv<T>(e_out[k], r.e_pos_span[k], rd.r_pos[k]) * g;
+                o[3 + k] = qdiv<T>(de_out[k], r.vel_span[k], rd.r_vel[k]) * g;
             }
         }
     }
@@ -111,7 +133,7 @@ __device__ __forceinline__ void reset_state(const RP &r, const b200env_io &io, i
 template <typename T, int V, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK, 4)
 uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavDerived dv,
-                      const __grid_constant__ b200env_io io, int64_t n, uint32_t flags, uint64_t seed, int64_t off) {
+                      const __grid_constant__ RobDerived rd, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags, uint64_t seed, int64_t off) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     constexpr int S = V == 1 ? 12 : 6, AD = V == 1 ? 6 : 3;
@@ -136,7 +158,7 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
     Trig<T> t1;
     t1.eval(x[6], x[7], x[8], V != 2);
     T cur[S], nxt[S], e[3], de[3];
-    observe<T, V>(r, io, n, i, x, t1, time, cur, e, de); // current_state = get_state()
+    observe<T, V>(r, rd, io, n, i, x, t1, time, cur, e, de); // current_state = get_state()
     if (io.obs) {
 #pragma unroll
         for (int k = 0; k < S; ++k) stio<T, IO32>(io.obs, n, k, i, cur[k]);
@@ -208,7 +230,7 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
     io.time[i] = time;
     Trig<T> t2;
     t2.eval(x[6], x[7], x[8], false);
-    observe<T, V>(r, io, n, i, x, t2, time, nxt, e, de);
+    observe<T, V>(r, rd, io, n, i, x, t2, time, nxt, e, de);
     // rewards
     const T Qx = (T)r.Qx, Qv = (T)r.Qv, R = (T)r.R;
     T an2;
@@ -247,7 +269,7 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
         reset_state<T, V>(r, io, n, i, seed, off, xr);
         Trig<T> tr;
         tr.eval(xr[6], xr[7], xr[8], false);
-        observe<T, V>(r, io, n, i, xr, tr, 0.0, nxt, e, de);
+        observe<T, V>(r, rd, io, n, i, xr, tr, 0.0, nxt, e, de);
     }
     if (io.reset_obs) {
 #pragma unroll
@@ -257,7 +279,8 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
 
 template <typename T, int V, bool IO32>
 __global__ void __launch_bounds__(B200_BLOCK)
-uavrobust_reset_kernel(const __grid_constant__ RP r, const __grid_constant__ b200env_io io, int64_t n,
+uavrobust_reset_kernel(const __grid_constant__ RP r, const __grid_constant__ RobDerived rd,
+                       const __grid_constant__ b200env_io io, int64_t n,
                        const uint8_t *mask, uint64_t seed, int64_t off, int observe_only) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -274,7 +297,7 @@ uavrobust_reset_kernel(const __grid_constant__ RP r, const __grid_constant__ b20
         T o[S], e[3], de[3];
         Trig<T> t;
         t.eval(x[6], x[7], x[8], false);
-        observe<T, V>(r, io, n, i, x, t, io.time[i], o, e, de);
+        observe<T, V>(r, rd, io, n, i, x, t, io.time[i], o, e, de);
 #pragma unroll
         for (int k = 0; k < S; ++k) stio<T, IO32>(io.next_obs, n, k, i, o[k]);
     }
@@ -284,11 +307,12 @@ template <typename T, bool IO32>
 int launch_step(int V, const RP &r, const b200env_io &io, int64_t n, uint32_t flags, uint64_t seed, int64_t off, cudaStream_t s) {
     const unsigned g = b200_grid(n);
     const UavDerived dv = uav_derive(r.m, r.J, r.kt);
+    const RobDerived rd = rob_derive(r);
     switch (V) {
-    case 0: uavrobust_step_kernel<T, 0, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, io, n, flags, seed, off); break;
-    case 1: uavrobust_step_kernel<T, 1, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, io, n, flags, seed, off); break;
-    case 2: uavrobust_step_kernel<T, 2, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, io, n, flags, seed, off); break;
-    case 3: uavrobust_step_kernel<T, 3, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, io, n, flags, seed, off); break;
+    case 0: uavrobust_step_kernel<T, 0, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, rd, io, n, flags, seed, off); break;
+    case 1: uavrobust_step_kernel<T, 1, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, rd, io, n, flags, seed, off); break;
+    case 2: uavrobust_step_kernel<T, 2, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, rd, io, n, flags, seed, off); break;
+    case 3: uavrobust_step_kernel<T, 3, IO32><<<g, B200_BLOCK, 0, s>>>(r, dv, rd, io, n, flags, seed, off); break;
     default: return B200ENV_EENV;
     }
     return b200_check_launch();
@@ -297,11 +321,12 @@ template <typename T, bool IO32>
 int launch_reset(int V, const RP &r, const b200env_io &io, int64_t n, const uint8_t *mask, uint64_t seed, int64_t off,
                  int observe_only, cudaStream_t s) {
     const unsigned g = b200_grid(n);
+    const RobDerived rd = rob_derive(r);
     switch (V) {
-    case 0: uavrobust_reset_kernel<T, 0, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
-    case 1: uavrobust_reset_kernel<T, 1, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
-    case 2: uavrobust_reset_kernel<T, 2, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
-    case 3: uavrobust_reset_kernel<T, 3, IO32><<<g, B200_BLOCK, 0, s>>>(r, io, n, mask, seed, off, observe_only); break;
+    case 0: uavrobust_reset_kernel<T, 0, IO32><<<g, B200_BLOCK, 0, s>>>(r, rd, io, n, mask, seed, off, observe_only); break;
+    case 1: uavrobust_reset_kernel<T, 1, IO32><<<g, B200_BLOCK, 0, s>>>(r, rd, io, n, mask, seed, off, observe_only); break;
+    case 2: uavrobust_reset_kernel<T, 2, IO32><<<g, B200_BLOCK, 0, s>>>(r, rd, io, n, mask, seed, off, observe_only); break;
+    case 3: uavrobust_reset_kernel<T, 3, IO32><<<g, B200_BLOCK, 0, s>>>(r, rd, io, n, mask, seed, off, observe_only); break;
     default: return B200ENV_EENV;
     }
     return b200_check_launch();
