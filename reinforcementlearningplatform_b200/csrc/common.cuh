@@ -156,6 +156,9 @@ template <typename T>
 struct Divisor {
     T d, r;
     __device__ __forceinline__ explicit Divisor(T d_) : d(d_), r((T)1 / d_) {}
+    // reciprocal supplied by the caller: a host-side 1 / d, or Mth<T>::rcp(d) (<= 1 ulp) where the divisor changes per
+    // thread -- the compiler's IEEE division costs ~25 instructions and a slow-path branch that splits the basic block
+    __device__ __forceinline__ Divisor(T d_, T r_) : d(d_), r(r_) {}
     __device__ __forceinline__ T div(T a) const {
         const T q = a * r;
         return Mth<T>::fma(Mth<T>::fma(-q, d, a), r, q);

@@ -90,17 +90,18 @@ __device__ __forceinline__ T cast_ray(const P &p, const Pose<T> &q, int ray, con
     const T x = q.x, y = q.y, xm = (T)p.map_x, ym = (T)p.map_y;
     // np.linspace(phi - R, phi + R, n): arange * step + start, last element = stop
     const T a0 = q.phi - (T)p.laser_range, a1 = q.phi + (T)p.laser_range;
-    const T step = (a1 - a0) / (T)(p.n_rays - 1);
+    const T nm1 = (T)(p.n_rays - 1);
+    const T step = Divisor<T>(nm1, Mth<T>::rcp(nm1)).div(a1 - a0);
     T phi = (ray == p.n_rays - 1) ? a1 : (T)ray * step + a0;
     if (phi > (T)M_PI) phi -= (T)(2 * M_PI);
     if (phi < (T)-M_PI) phi += (T)(2 * M_PI);
     T sphi, cphi;
     Mth<T>::sincos(phi, &sphi, &cphi);
-    const T m = sphi / cphi; // np.tan(phi) :311 (constant-bank sincos + one IEEE division, <= 2.5 ulp)
+    const T m = Mth<T>::div(sphi, cphi); // np.tan(phi) :311 (constant-bank sincos + rcp-based quotient, <= 2.5 ulp)
     const T b = y - m * x;
     const T m2p1 = m * m + (T)1;
     const T sq = Mth<T>::sqrt(m2p1);
-    const Divisor<T> dsq(sq), dm2(m2p1);
+    const Divisor<T> dsq(sq, Mth<T>::rcp(sq)), dm2(m2p1, Mth<T>::rcp(m2p1));
     const T am = Mth<T>::abs(m);
     const T cosT = dsq.div(am), sinT = dsq.r; // |m| / sqrt(m^2 + 1), 1 / sqrt(m^2 + 1)
     const T ld_sq = dsq.div(LD);               // laserDis / sqrt(m^2 + 1)
@@ -530,6 +531,7 @@ ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io
         // ---- phase 2: get_fake_laser :274-397 for all rays of the block
         void *dst = scan ? io.next_obs : io.obs;
         const int total = gv * NR;
+        const Divisor<T> by_ld((T)p.laser_dis);
         for (int idx = t; idx < total; idx += TPB) {
             const int li = idx / NR, ray = idx - li * NR;
             Pose<T> q;
@@ -539,7 +541,7 @@ ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io
             ObsList<T> l;
             l.x0 = &s_o[0][0][li]; l.y0 = &s_o[1][0][li]; l.r0 = &s_o[2][0][li]; l.d = &s_o[3][0][li];
             l.stride = G; l.count = s_cnt[li];
-            const T v = ((T)2 * cast_ray<T>(p, q, ray, l) / (T)p.laser_dis - (T)1) * g;
+            const T v = (by_ld.div((T)2 * cast_ray<T>(p, q, ray, l)) - (T)1) * g;
             stio<T, IO32>(dst, n, 4 + ray, base + li, v);
             if (scan && s_mirror[li]) stio<T, IO32>(io.reset_obs, n, 4 + ray, base + li, v);
         }
