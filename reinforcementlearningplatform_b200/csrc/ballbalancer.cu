@@ -23,9 +23,10 @@ struct BallBalancer {
     // get_state :200-211
     __device__ __forceinline__ void observe(const P &p, T *o) const {
         const T g = (T)p.static_gain;
-        o[0] = pos / (T)p.L * g;
-        o[1] = ((T)2 * vel - (T)p.v_max - (T)p.v_min) / (T)(p.v_max - p.v_min) * g;
-        o[2] = ((T)2 * theta - (T)p.theta_max - (T)p.theta_min) / (T)(p.theta_max - p.theta_min) * g;
+        // quotients by step-constant normalisers: reciprocal + Markstein correction (common.cuh Divisor), no IEEE-division slow path
+        o[0] = Divisor<T>((T)(p.L), Mth<T>::rcp((T)(p.L))).div(pos) * g;
+        o[1] = Divisor<T>((T)(p.v_max - p.v_min), Mth<T>::rcp((T)(p.v_max - p.v_min))).div((T)2 * vel - (T)p.v_max - (T)p.v_min) * g;
+        o[2] = Divisor<T>((T)(p.theta_max - p.theta_min), Mth<T>::rcp((T)(p.theta_max - p.theta_min))).div((T)2 * theta - (T)p.theta_max - (T)p.theta_min) * g;
     }
     __device__ __forceinline__ bool success(const P &p) const { // :213-216
         return Mth<T>::abs(error) <= (T)0.001 && Mth<T>::abs(vel) <= (T)0.005 && Mth<T>::abs(theta) <= (T)p.deg1;
@@ -57,7 +58,7 @@ struct BallBalancer {
         error = (T)p.target - pos; // :281
         observe(p, nxt);
         // get_reward :238-246
-        const T e = error / (T)p.L * (T)p.static_gain;
+        const T e = Divisor<T>((T)(p.L), Mth<T>::rcp((T)(p.L))).div(error) * (T)p.static_gain;
         const T r1 = -(e * e) - Mth<T>::tanh((T)100 * e) + (T)0.5;
         const T r3 = success(p) ? (T)1000 : (T)0;
         reward = r1 + (T)0 + r3;

@@ -25,14 +25,14 @@ struct FasDiscrete {
     }
     // :158-162
     __device__ __forceinline__ void observe(const P &p, T *o) const {
-        o[0] = -theta / (T)p.theta_max * (T)p.static_gain;
-        o[1] = dtheta / (T)p.dtheta_max * (T)p.static_gain;
+        o[0] = Divisor<T>((T)(p.theta_max), Mth<T>::rcp((T)(p.theta_max))).div(-theta) * (T)p.static_gain;
+        o[1] = Divisor<T>((T)(p.dtheta_max), Mth<T>::rcp((T)(p.dtheta_max))).div(dtheta) * (T)p.static_gain;
     }
     static __device__ __forceinline__ T f(const P &p, T a0, T angle, T dangle) { // :199-203
         return (T)p.a2 * dangle + (T)p.a1 * Mth<T>::cos(angle) + a0;
     }
     __device__ __forceinline__ void step(const P &p, const T *act, const T *cur, int &flag, bool &done, T &reward, T *nxt) {
-        const T a0 = (T)p.L * act[0] / (T)p.denom;
+        const T a0 = Divisor<T>((T)(p.denom), Mth<T>::rcp((T)(p.denom))).div((T)p.L * act[0]);
         const T h = (T)p.dt, half = (T)0.5;
         // `t_sim = 0; while t_sim <= dt: ...; t_sim += h` with h = dt: trips at t_sim = 0 and t_sim = dt (:205-219)
 #pragma unroll 1

@@ -41,17 +41,17 @@ struct TwoLink {
         const T b1 = tq1 - (T)1.5 * J * s2 * (o1 * o1) - (T)0.5 * (T)p.m * (T)p.g * (T)p.l * s12;
         // dgesv on [[a00, a01], [a01, a11]]: pivot on the larger |.| of column 0
         if (Mth<T>::abs(a01) > Mth<T>::abs(a00)) {
-            const T l = a00 * ((T)1 / a01);
+            const T l = a00 * Mth<T>::rcp(a01); // rcp-based (<= 1 ulp): the LU solve runs 4 times per step
             const T u11 = a01 - l * a11;
             const T y1 = b0 - l * b1;
-            d2 = y1 / u11;
-            d1 = (b1 - a11 * d2) / a01;
+            d2 = Mth<T>::div(y1, u11);
+            d1 = Mth<T>::div(b1 - a11 * d2, a01);
         } else {
-            const T l = a01 * ((T)1 / a00);
+            const T l = a01 * Mth<T>::rcp(a00);
             const T u11 = a11 - l * a01;
             const T y1 = b1 - l * b0;
-            d2 = y1 / u11;
-            d1 = (b0 - a01 * d2) / a00;
+            d2 = Mth<T>::div(y1, u11);
+            d1 = Mth<T>::div(b0 - a01 * d2, a00);
         }
     }
     __device__ __forceinline__ void step(const P &p, const T *act, const T *cur, int &flag, bool &done, T &reward, T *nxt) {

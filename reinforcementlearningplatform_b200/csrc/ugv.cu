@@ -48,14 +48,14 @@ struct Ugv {
         errors(p, e, ephi);
         const T g = (T)p.static_gain;
         if (p.bidirectional) {
-            o[0] = e / (T)p.e_max * g;
-            o[1] = vel / (T)p.v_max * g;
+            o[0] = Divisor<T>((T)(p.e_max), Mth<T>::rcp((T)(p.e_max))).div(e) * g;
+            o[1] = Divisor<T>((T)(p.v_max), Mth<T>::rcp((T)(p.v_max))).div(vel) * g;
         } else {
             o[0] = ((T)(2 / p.e_max) * e - (T)1) * g;
             o[1] = ((T)(2 / p.v_max) * vel - (T)1) * g;
         }
-        o[2] = ephi / (T)p.e_phi_max * g;
-        o[3] = omega / (T)p.omega_max * g;
+        o[2] = Divisor<T>((T)(p.e_phi_max), Mth<T>::rcp((T)(p.e_phi_max))).div(ephi) * g;
+        o[3] = Divisor<T>((T)(p.omega_max), Mth<T>::rcp((T)(p.omega_max))).div(omega) * g;
     }
     __device__ __forceinline__ void step(const P &p, const T *act, const T *cur, int &flag, bool &done, T &reward, T *nxt) {
         const T al = act[0], aa = act[1], kf = (T)p.kf, kt = (T)p.kt;
