@@ -97,7 +97,7 @@ env_rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constan
             const int64_t t = (t0 + u < rs.steps) ? t0 + u : rs.steps - 1;
             const TIO *act_row = static_cast<const TIO *>(io.action) + t * rs.action_stride;
 #pragma unroll
-            for (int k = 0; k < E::AD; ++k) acts[u][k] = ldio<T, IO32>(act_row, n, k, i);
+            for (int k = 0; k < E::AD; ++k) acts[u][k] = ldio_idx<T, IO32>(act_row, n, k, i);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -108,7 +108,7 @@ env_rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constan
                 if (io.obs) {
                     TIO *row = static_cast<TIO *>(io.obs) + t * rs.obs_stride;
 #pragma unroll
-                    for (int k = 0; k < E::OD; ++k) stio<T, IO32>(row, n, k, i, cur[k]);
+                    for (int k = 0; k < E::OD; ++k) stio_idx<T, IO32>(row, n, k, i, cur[k]);
                 }
                 int flag = 0;
                 bool done = false;
@@ -117,9 +117,9 @@ env_rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constan
                 {
                     TIO *row = static_cast<TIO *>(io.next_obs) + t * rs.next_obs_stride;
 #pragma unroll
-                    for (int k = 0; k < E::OD; ++k) stio<T, IO32>(row, n, k, i, nxt[k]);
+                    for (int k = 0; k < E::OD; ++k) stio_idx<T, IO32>(row, n, k, i, nxt[k]);
                 }
-                stio<T, IO32>(static_cast<TIO *>(io.reward) + t * rs.reward_stride, n, 0, i, reward);
+                stio_idx<T, IO32>(static_cast<TIO *>(io.reward) + t * rs.reward_stride, n, 0, i, reward);
                 io.done[t * rs.done_stride + i] = done ? 1 : 0;
                 io.flag[t * rs.flag_stride + i] = flag;
                 if (done && (flags & B200ENV_AUTO_RESET)) {
@@ -134,7 +134,7 @@ env_rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constan
     }
     if (io.reset_obs) {
 #pragma unroll
-        for (int k = 0; k < E::OD; ++k) stio<T, IO32>(io.reset_obs, n, k, i, nxt[k]);
+        for (int k = 0; k < E::OD; ++k) stio_idx<T, IO32>(io.reset_obs, n, k, i, nxt[k]);
     }
     e.store(io, n, i);
 }
