@@ -62,6 +62,23 @@ __device__ __forceinline__ double div(double x, double y) {
     return fma(fma(-y, q, x), r, q);
 }
 
+// sqrt without the compiler's slow-path branch (which would split the caller's basic block): MUFU.RSQ64H seed, two
+// Goldschmidt steps, one FMA correction.  Correctly rounded except in rare half-way cases (<= 1 ulp); 0 -> 0,
+// +inf -> +inf, negative / NaN -> NaN like IEEE sqrt; subnormal arguments are treated as 0.
+__device__ __forceinline__ double sqrt_nb(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    g = fma(fma(-g, g, x), h, g);
+    return (x == 0.0 || x == CUDART_INF) ? x : g;
+}
+
 // sin and cos of x for |x| < 1e5 (three-term Cody-Waite reduction by pi/2, two degree-5 kernels in z = r^2).
 // No argument check: callers go through sincos() / sincos3() below.
 __device__ __forceinline__ void sincos_core(double x, double *sn, double *cs) {
@@ -181,7 +198,7 @@ __device__ __forceinline__ double asin(double x) {
     const double ax = fabs(x);
     const bool big = ax > 0.5;
     const double w = big ? 0.5 * (1.0 - ax) : ax * ax; // z = t^2
-    const double t = big ? ::sqrt(w) : ax;
+    const double t = big ? sqrt_nb(w) : ax;
     double p = kA[11];
     p = fma(p, w, kA[10]); p = fma(p, w, kA[9]); p = fma(p, w, kA[8]); p = fma(p, w, kA[7]); p = fma(p, w, kA[6]);
     p = fma(p, w, kA[5]); p = fma(p, w, kA[4]); p = fma(p, w, kA[3]); p = fma(p, w, kA[2]); p = fma(p, w, kA[1]);

@@ -83,3 +83,16 @@ def test_pow_from_log_matches_pow():
     rel = np.abs(p - ref) / np.maximum(np.abs(ref), 1e-300)
     assert rel.max() <= 2e-14, rel.max()   # (|a log x| + 1) ulp, see common.cuh:pow_from_log
     assert p[-4] == 0 and p[-3] == 1 and p[-2] == 0 and p[-1] == 1
+
+
+def test_asin_accuracy_and_limits():
+    rng = np.random.default_rng(6)
+    x = np.concatenate((rng.uniform(-1, 1, 400000), rng.uniform(0.49, 0.51, 50000), 1 - 10.0 ** rng.uniform(-16, -1, 50000),
+                        [0.0, -0.0, 0.5, -0.5, 1.0, -1.0]))
+    a, _ = _eval(5, x)
+    ref = np.arcsin(x)
+    err = np.abs(a - ref) / np.maximum(np.spacing(np.abs(ref)), 2 ** -53 * 1e-3)
+    assert err.max() <= 2.5, err.max()   # branch-free kernel + Goldschmidt sqrt on the folded half
+    assert a[-2] == np.pi / 2 and a[-1] == -np.pi / 2 and a[-6] == 0
+    a, _ = _eval(5, np.array([1.0000001, -2.0, np.nan]))
+    assert np.all(np.isnan(a))
