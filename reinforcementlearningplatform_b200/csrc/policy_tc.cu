@@ -50,12 +50,14 @@ struct TcArgs {
 // values, in two integer instructions instead of the multi-instruction sequence ptxas emits for the cvt
 __device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 
-// tanh(x) = 1 - 2 / (exp(2x) + 1) on the SFU (ex2.approx, rcp.approx): 5 instructions, absolute error <= 3e-7 over the
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the SFU (ex2.approx, rcp.approx): 5 instructions, absolute error <= 4e-7 over the
 // whole range (the quotient saturates to 0 / 2 for large |x|), against ~25 instructions for the 1-ulp tanhf.  The
 // 3xTF32 products carry ~1e-6 themselves, so the accurate version would buy nothing here (policy.cu keeps it).
 __device__ __forceinline__ float tanh_fast(float x) {
-    const float e = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, e + 1.0f);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f)); // exp(2x) = 2^(2 x log2 e)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));               // e = inf -> 0, e = 0 -> 1
+    return fmaf(-2.0f, r, 1.0f);
 }
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
     hi = to_tf32(x);
