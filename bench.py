@@ -466,6 +466,8 @@ def main():
     dist_on = world > 1
     torch.cuda.set_device(local)
     if dist_on:
+        # NCCL's own log lines (e.g. "NCCL version ..." when NCCL_DEBUG=VERSION) go to stderr: stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     n = args.envs or WORKLOADS[args.workload]["n"]
