@@ -466,9 +466,19 @@ def main():
     dist_on = world > 1
     torch.cuda.set_device(local)
     if dist_on:
-        # NCCL's own log lines (e.g. "NCCL version ..." when NCCL_DEBUG=VERSION) go to stderr: stdout carries ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints "NCCL version ..." on stdout when the communicator is created: route fd 1 to stderr around the
+        # initialisation (and the first collective), so that stdout carries exactly ONE JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     n = args.envs or WORKLOADS[args.workload]["n"]
     dev = torch.device("cuda", local)
