@@ -1,0 +1,1 @@
+"""Vector mirrors of the reference environments (one class per env family)."""
