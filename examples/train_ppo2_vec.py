@@ -25,6 +25,9 @@ ENVS = {
     "soi": (lambda **kw: rlp.SecondOrderIntegration(**kw), dict(std=0.8, mean_act="identity")),
     "fas": (lambda **kw: rlp.Flight_Attitude_Simulator(variant="ppo2", **kw), dict(std=0.8, mean_act="identity")),
     "uav_pos": (lambda **kw: rlp.UavPosCtrlRL(random_trajectory=True, **kw), dict(std=0.45, mean_act="relu")),
+    # BASELINE config #5: the DPPO2 copy of UGVForwardObstacleAvoidance (41-dim observation with the 37-ray laser);
+    # under torchrun this is DPPO2 as synchronous data parallelism (flat gradient all-reduce per mini-batch)
+    "ugvo": (lambda **kw: rlp.UGVForwardObstacleAvoidance(variant="dppo2", **kw), dict(std=0.8, mean_act="identity")),
 }
 
 
