@@ -119,7 +119,9 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.nv = None
 
-    def run(self):
+    def sample_once(self):
+        """One NVML reading.  Also called from the main thread right after the timed launches have been enqueued (the
+        GPU is then busy with them for tens of milliseconds), so the clocks line never depends on thread scheduling."""
         if self.nv is None:
             return
         nv = self.nv
@@ -129,16 +131,19 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
         }
-        while not self.stop_flag:
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.02)
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            self.sample_once()
+            time.sleep(0.01)
 
     def result(self):
         self.stop_flag = True
@@ -147,7 +152,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def timed_steps(env, pool, steps, warmup, dist_on):
+def timed_steps(env, pool, steps, warmup, dist_on, sampler=None):
     import torch.distributed as dist
     P = pool.shape[0]
     for k in range(warmup):
@@ -161,6 +166,9 @@ def timed_steps(env, pool, steps, warmup, dist_on):
     for k in range(steps):
         env.step_soa(pool[(warmup + k) % P])
     e1.record()
+    if sampler is not None:  # the launches are enqueued, the GPU is executing them: read the clocks under load
+        for _ in range(3):
+            sampler.sample_once()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if dist_on:
@@ -488,7 +496,7 @@ def main():
     pool = action_pool(env, n, 4, dev, dtype, seed=rank + 1)
     sampler = ClockSampler(local)
     sampler.start()
-    ms = timed_steps(env, pool, args.steps, args.warmup, dist_on)
+    ms = timed_steps(env, pool, args.steps, args.warmup, dist_on, sampler)
     clocks = sampler.result()
     value = world * n * args.steps / (ms * 1e-3)
     per_launch_s = ms * 1e-3 / args.steps
