@@ -59,6 +59,7 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
     static __device__ __forceinline__ double cos(double x) { return ::cos(x); }
 #endif
+    static __device__ __forceinline__ double sin_ld(double x) { return ::sin(x); } // libdevice: faster where only sin is needed twice (K-TLM, A/B)
     static __device__ __forceinline__ double tan(double x) { return ::tan(x); }
     static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
@@ -72,6 +73,7 @@ template <> struct Mth<double> {
 
 template <> struct Mth<float> {
     static __device__ __forceinline__ float sin(float x) { return ::sinf(x); }
+    static __device__ __forceinline__ float sin_ld(float x) { return ::sinf(x); }
     static __device__ __forceinline__ float cos(float x) { return ::cosf(x); }
     static __device__ __forceinline__ void sincos(float x, float *s, float *c) { ::sincosf(x, s, c); }
     static __device__ __forceinline__ void sincos3(float a, float b, float c, float *sa, float *ca, float *sb, float *cb,

@@ -35,7 +35,7 @@ struct TwoLink {
         const T J = (T)p.J, mgl = (T)(p.m * p.g * p.l);
         T s2, c2;
         Mth<T>::sincos(t2, &s2, &c2);
-        const T s1 = Mth<T>::sin(t1), s12 = Mth<T>::sin(t1 + t2);
+        const T s1 = Mth<T>::sin_ld(t1), s12 = Mth<T>::sin_ld(t1 + t2);
         const T a00 = J * ((T)5 + (T)3 * c2), a01 = J * ((T)1 + (T)1.5 * c2), a11 = J;
         const T b0 = tq0 + (T)1.5 * J * s2 * (o2 * o2) + (T)3 * J * s2 * o1 * o2 - mgl * ((T)1.5 * s1 + (T)0.5 * s12);
         const T b1 = tq1 - (T)1.5 * J * s2 * (o1 * o1) - (T)0.5 * (T)p.m * (T)p.g * (T)p.l * s12;
