@@ -276,6 +276,8 @@ class UavAttRandA(UavAttA):
 
 REGISTRY.update({
     "uav_pos": (UavPosA, 6, 1000, 21),
+    # wide fixtures (SURVEY 8c-i asks for many seeds): one full episode each for 24 / 32 independent seeds
+    "uav_pos_wide": (UavPosDisA, 24, 520, 41),
     "uav_pos_rp0": (UavPosRandomPos0A, 4, 600, 28),
     "uav_pos_dis": (UavPosDisA, 3, 1000, 22),
     "uav_att": (UavAttA, 6, 1000, 23),
@@ -497,6 +499,7 @@ class UgvBidirectionalA(UgvForwardA):
 
 
 REGISTRY.update({
+    "cartpole_wide": (CartPoleA, 32, 300, 42),
     "fas": (FasA, 4, 800, 31),
     "fas_ppo2": (FasPPO2A, 2, 1200, 32),
     "fas_discrete": (FasDiscreteA, 3, 700, 39),

@@ -29,6 +29,7 @@ def env_specs():
     return {
         "cartpole": (rlp.CartPole, {}),
         "cartpole_gentle": (rlp.CartPole, {}),
+        "cartpole_wide": (rlp.CartPole, {}),
         "cartpole_angleonly_env": (rlp.CartPoleAngleOnly, {"variant": "env"}),
         "cartpole_angleonly_ppo2": (rlp.CartPoleAngleOnly, {"variant": "ppo2"}),
         "fas": (rlp.Flight_Attitude_Simulator, {}),
@@ -48,6 +49,7 @@ def env_specs():
         "ugvo_dppo2": (rlp.UGVForwardObstacleAvoidance, {"variant": "dppo2"}),
         "uav_pos": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
         "uav_pos_dis": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
+        "uav_pos_wide": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
         "uav_pos_rp0": (rlp.UavPosCtrlRL, {"random_trajectory": True, "random_pos0": True}),
         "uav_pos_crash": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
         "uav_pos_edge": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
@@ -195,8 +197,8 @@ def smoke_cases():
 
 # fp64 tolerance of the free-running engine-vs-oracle comparison (mixed metric), per fixture family
 ENGINE_TOL = {
-    "cartpole": 1e-9, "cartpole_gentle": 1e-9, "cartpole_angleonly_env": 1e-9, "cartpole_angleonly_ppo2": 1e-9,
-    "uav_pos": 1e-7, "uav_pos_dis": 1e-9, "uav_pos_rp0": 1e-7, "uav_pos_crash": 1e-9, "uav_pos_edge": 1e-9,
+    "cartpole": 1e-9, "cartpole_gentle": 1e-9, "cartpole_wide": 1e-9, "cartpole_angleonly_env": 1e-9, "cartpole_angleonly_ppo2": 1e-9,
+    "uav_pos": 1e-7, "uav_pos_dis": 1e-9, "uav_pos_wide": 1e-7, "uav_pos_rp0": 1e-7, "uav_pos_crash": 1e-9, "uav_pos_edge": 1e-9,
     "uav_att": 1e-9, "uav_att_rand": 1e-9, "uav_att_edge": 1e-9,
     "fas": 1e-9, "fas_ppo2": 1e-9, "fas_discrete": 1e-9, "soi": 1e-9, "soi_dppo2": 1e-9, "ballbalancer": 1e-9, "twolink": 1e-5,
     "ugv_forward": 1e-9, "ugv_bidirectional": 1e-9, "ugvo": 1e-9, "ugvo_dppo2": 1e-9,
