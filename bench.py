@@ -52,10 +52,10 @@ ALGO_BYTES = {
 ALGO_FLOPS = {"uav_pos": 5100.0, "uav_att": 3300.0, "cartpole": 3100.0, "ugvo": 54000.0, "soi": 125.0, "fas": 570.0}
 # what the kernel really executes per env-step, counted from the ncu SASS page of the profiled launch
 # (profiles/r1/uav_pos_final_ophist.txt): fp64-pipe instructions (DFMA + DMUL + DADD + DSETP) and flops (DFMA = 2)
-EXEC_F64 = {"uav_pos": {"pipe_inst": 2077.3, "flops": 3185.6, "src": "profiles/r1/uav_pos_final_ophist.txt"}}
+EXEC_F64 = {"uav_pos": {"pipe_inst": 2081.9, "flops": 3193.9, "src": "profiles/r1/uav_pos_final_ophist.txt"}}
 # DRAM bytes per launch of the dominant kernel from the `ncu --set full` capture (dram__bytes_read + write), at the
 # profiled size; None where no capture is committed
-NCU_TRAFFIC = {("uav_pos", "f64", 1 << 20): {"bytes": 344044032 + 418785280, "src": "profiles/r1/uav_pos_final_keys.txt"}}
+NCU_TRAFFIC = {("uav_pos", "f64", 1 << 20): {"bytes": 344037888 + 418002944, "src": "profiles/r1/uav_pos_final_keys.txt"}}
 
 WORKLOADS = {
     "uav_pos": dict(n=1 << 20, desc="UavFntsmcParam position tracking, dt=0.02, time_max=10, 8 gains~U(0,5)/step"),

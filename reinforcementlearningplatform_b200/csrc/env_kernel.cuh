@@ -4,7 +4,8 @@
 //     using P = <params struct>;  static constexpr int SF, OD, AD;       (state fields, obs dim, action dim)
 //     load(io, n, i) / store(io, n, i)           SoA state <-> registers (time included)
 //     observe(p, o[OD])                          get_state()
-//     step(p, act[AD], cur[OD], flag, done, reward)   rk44 + is_Terminal + get_reward (next obs is taken afterwards)
+//     step(p, act[AD], cur[OD], flag, done, reward)   rk44 + is_Terminal + get_reward (next obs is taken afterwards);
+//                                                cur is only valid when io.obs != NULL and must not be read by step()
 //     reset(p, rng)                              reset(random=True) with Philox draws in the reference's draw order
 // and the kernels below add the common data movement: all loads first, outputs, optional auto-reset.
 #pragma once
@@ -22,9 +23,10 @@ env_step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__
     T act[E::AD];
 #pragma unroll
     for (int k = 0; k < E::AD; ++k) act[k] = ldio<T, IO32>(io.action, n, k, i);
-    T cur[E::OD], nxt[E::OD];
-    e.observe(p, cur); // self.current_state = self.get_state()
-    if (io.obs) {
+    T cur[E::OD] = {}, nxt[E::OD];
+    if (io.obs) { // self.current_state = self.get_state(); no family's step() reads it, so it is only evaluated when the
+                  // caller wants it stored (pure-observation envs reuse the previous policy observation, vec_env.py)
+        e.observe(p, cur);
 #pragma unroll
         for (int k = 0; k < E::OD; ++k) stio<T, IO32>(io.obs, n, k, i, cur[k]);
     }
@@ -103,9 +105,9 @@ env_rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constan
         for (int u = 0; u < U; ++u) {
             const int64_t t = t0 + u;
             if (t < rs.steps) {
-                T cur[E::OD];
-                e.observe(p, cur);
+                T cur[E::OD] = {};
                 if (io.obs) {
+                    e.observe(p, cur);
                     TIO *row = static_cast<TIO *>(io.obs) + t * rs.obs_stride;
 #pragma unroll
                     for (int k = 0; k < E::OD; ++k) stio_idx<T, IO32>(row, n, k, i, cur[k]);
