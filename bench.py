@@ -473,12 +473,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist_on = world > 1
     torch.cuda.set_device(local)
-    try:  # run this rank's host threads (and place its pinned buffers) on the CPUs next to its GPU: the end-to-end path
-        import pynvml  # streams ~75 GB/s per GPU through host memory
-        pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-    except Exception:
-        pass
     if dist_on:
         # NCCL prints "NCCL version ..." on stdout when the communicator is created: route fd 1 to stderr around the
         # initialisation (and the first collective), so that stdout carries exactly ONE JSON line
