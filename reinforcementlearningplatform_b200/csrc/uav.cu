@@ -119,7 +119,9 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ UavDeri
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         k1[k] = a[k] > (T)0 ? (T)10 * a[k] : ld<T>(io.state, n, A_K1 + k, i);
-        k2[k] = a[k + 3] > (T)0 ? a[k + 3] / (T)10 : ld<T>(io.state, n, A_K2 + k, i);
+        // a / 10 as q = a r, q + (a - 10 q) r with r = RN(1 / 10): the correctly rounded quotient (Markstein; checked
+        // against 300 k IEEE quotients incl. float32-valued a), without the IEEE division's slow-path branch
+        k2[k] = a[k + 3] > (T)0 ? Divisor<T>((T)10, (T)0.1).div(a[k + 3]) : ld<T>(io.state, n, A_K2 + k, i);
         gam[k] = a[6] > (T)0 ? a[6] : ld<T>(io.state, n, A_GAM + k, i);
         lmd[k] = a[7] > (T)0 ? a[7] : ld<T>(io.state, n, A_LMD + k, i);
         alpha[k] = (T)p.att_alpha[k];
