@@ -50,9 +50,8 @@ def main(argv=None):
                env_index_offset=off)
     actor, critic = reference_nets(env.state_dim, env.action_dim, dev, init_std=net_kw["std"], mean_act=net_kw["mean_act"])
     agent = VecPPO2(env, actor, critic, {"buffer_size": args.steps, "K_epochs": args.epochs,
-                                          "mini_batch_size": min(16384, args.steps * n_local)}, std=net_kw["std"],
+                                          "mini_batch_size": 16384}, std=net_kw["std"],
                     seed=args.seed)
-    agent.policy.out_act = 1 if net_kw["mean_act"] == "relu" else 0
     env.reset(True)
     log = []
     for it in range(args.iters):

@@ -418,7 +418,7 @@ B200_API int b200_mc_returns(int r_dtype, int64_t T, int64_t N, const void *r, c
  *   float64 about run's mean (run may be NULL).  scratch: b200_norm_scratch_bytes(dim) bytes, zeroed once by the caller.
  * b200_norm_merge_apply: merges n_batches batch statistics (batch_stats[n_batches][3][dim], e.g. all-gathered over
  *   ranks, merged in index order) into run_in -> run_out (may alias only if y == NULL), then y = (x - mean) / (std +
- *   eps) with the MERGED statistics.  The merge is Chan's pairwise update written so that a batch of one sample is
+ *   eps) with the MERGED statistics (y may be x: in-place normalisation).  The merge is Chan's pairwise update written so that a batch of one sample is
  *   bit-identical to the reference's update; update = 0 skips the merge (evaluation: `update=False`). */
 B200_API size_t b200_norm_scratch_bytes(int dim);
 B200_API int b200_norm_seq(int dtype, int64_t rows, int dim, const void *x, void *y, double *run, int update, double eps,
@@ -438,7 +438,7 @@ B200_API int b200_norm_merge_apply(int dtype, int64_t n, int dim, const void *x,
 typedef struct b200_mlp {
     int32_t n_layers;       /* 1..4 */
     int32_t dims[5];
-    int32_t out_act;
+    int32_t out_act;        /* 0 identity, 1 relu, 2 tanh mapped onto [a_min, a_max] (actor heads of the DPPO2 demos) */
     int32_t pad_;
     const float *w[4];
     const float *b[4];
@@ -453,14 +453,33 @@ typedef struct b200_mlp {
  * memory together with the tile's activations (the reference's 64-64-32 / 64-32 nets use ~110 KB) and no layer may be
  * wider than 64, else B200ENV_ESIZE. */
 /* precision: B200_POLICY_FP32 = float32 FMA pipe, sums in k order (<= 2e-6 absolute from torch's float32 GEMM);
- * B200_POLICY_TF32X3 = tensor cores with every operand split into two TF32 halves (3 MMAs per product, fp32
- * accumulation; <= 5e-6 absolute), ~4x faster -- the forward is otherwise 4x the cost of the env step it feeds. */
+ * B200_POLICY_TF32X3 = legacy warp-level tensor-core MMA with every operand split into two TF32 halves (3 MMAs per
+ * product, fp32 accumulation; <= 5e-6 absolute).  Both keep every net in shared memory and reject layers wider than 64
+ * (B200ENV_ESIZE); the tcgen05 path below has neither limit and is the one the Python mirror uses. */
 #define B200_POLICY_FP32   0
 #define B200_POLICY_TF32X3 1
 B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const float *obs,
                                  const float *a_min, const float *a_max, float std, const float *noise, uint64_t seed,
                                  uint64_t step, int64_t env_index_offset, int precision, float *action,
                                  float *log_prob, float *mean, float *value, void *cuda_stream);
+
+/* The same forward on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, weights fed by bulk-copy TMA;
+ * csrc/policy_umma.cu): 128-instance tiles, 3xTF32 split (<= 5e-6 absolute on the reference's 64-wide nets, <= 2e-5 on
+ * 256-wide ones whose fp32 sums are 4x longer), layers up to 256 wide -- the 41-256-256-{2,1} nets of
+ * demonstration/DPPO2/DPPO2-4-UGVForwardObstacleAvoidance/train.py:26-107.  The weights are first packed into a
+ * caller-owned device workspace (128-byte aligned, b200_policy_workspace_bytes) in the tensor core's operand layout:
+ * b200_policy_pack once per optimizer step, b200_policy_forward_packed once per env step (it reads only dims / out_act
+ * from the two structs).  actor->out_act = 2 selects the range-mapped head of those demo nets, mean = tanh(z) * gain + off
+ * with off = (a_min + a_max) / 2, gain = a_max - off; std_vec (device float32 [A], may be NULL -> scalar std) is their
+ * per-dimension init_std.  Output heads: <= 16 actions, critic 1. */
+B200_API size_t b200_policy_workspace_bytes(const b200_mlp *actor, const b200_mlp *critic);
+B200_API int b200_policy_pack(const b200_mlp *actor, const b200_mlp *critic, void *workspace, size_t workspace_bytes,
+                              void *cuda_stream);
+B200_API int b200_policy_forward_packed(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const void *workspace,
+                                        size_t workspace_bytes, const float *obs, const float *a_min, const float *a_max,
+                                        float std, const float *std_vec, const float *noise, uint64_t seed, uint64_t step,
+                                        int64_t env_index_offset, float *action, float *log_prob, float *mean,
+                                        float *value, void *cuda_stream);
 
 /* ------------------------------------------------------------- diagnostics */
 
@@ -472,6 +491,11 @@ B200_API int b200_measure_fma_peak(int dtype, int iters, double *tflops, void *c
 /* Element-wise evaluation of the in-house fp64 math used by the kernels (csrc/fastmath64.cuh), for accuracy tests:
  * func 0 sincos (out0 = sin, out1 = cos), 1 exp, 2 log, 3 tanh, 4 x^a with a read from out1.  Device pointers. */
 B200_API int b200_fastmath_eval(int func, int64_t n, const double *x, double *out0, double *out1, void *cuda_stream);
+
+/* One 128 x N x K product (A [128][K], W [N][K] row-major float32 device arrays, D [128][N] out) through the shared-memory
+ * descriptors, instruction descriptor, tcgen05.mma / tcgen05.ld sequence of csrc/policy_umma.cu; three_pass = 1: 3xTF32
+ * split, 0: one TF32 pass.  N multiple of 16 <= 256, K multiple of 8 <= 64.  For tests/test_umma_gpu.py. */
+B200_API int b200_umma_probe(const float *A, const float *W, float *D, int N, int K, int three_pass, void *cuda_stream);
 
 #ifdef __cplusplus
 }

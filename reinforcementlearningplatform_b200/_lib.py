@@ -24,7 +24,7 @@ ERRORS = {
     -3: "B200ENV_EPARAMS: params struct size mismatch (ABI drift between Python mirror and library)",
     -4: "B200ENV_ENULL: required pointer is NULL",
     -5: "B200ENV_ECUDA: CUDA launch failed",
-    -6: "B200ENV_ESIZE: bad n_envs",
+    -6: "B200ENV_ESIZE: bad n_envs, or a net the selected K-POLICY kernel cannot hold",
 }
 
 
@@ -175,6 +175,15 @@ def load() -> C.CDLL:
     lib.b200_norm_merge_apply.argtypes = [i32, i64, i32, vp, vp, vp, i32, vp, vp, i32, f64, vp]
     lib.b200_policy_forward.restype = i32
     lib.b200_policy_forward.argtypes = [i64, vp, vp, vp, vp, vp, C.c_float, vp, u64, u64, i64, i32, vp, vp, vp, vp, vp]
+    lib.b200_policy_workspace_bytes.restype = sz
+    lib.b200_policy_workspace_bytes.argtypes = [vp, vp]
+    lib.b200_policy_pack.restype = i32
+    lib.b200_policy_pack.argtypes = [vp, vp, vp, sz, vp]
+    lib.b200_policy_forward_packed.restype = i32
+    lib.b200_policy_forward_packed.argtypes = [i64, vp, vp, vp, sz, vp, vp, vp, C.c_float, vp, vp, u64, u64, i64, vp, vp, vp,
+                                               vp, vp]
+    lib.b200_umma_probe.restype = i32
+    lib.b200_umma_probe.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.b200_fastmath_eval.restype = i32
     lib.b200_fastmath_eval.argtypes = [i32, i64, vp, vp, vp, vp]
     lib.b200_measure_fma_peak.restype = i32

@@ -140,7 +140,8 @@ __device__ __forceinline__ double std_of(Stat s) {
 
 template <typename TX>
 __global__ void __launch_bounds__(NORM_BLOCK)
-norm_merge_apply_kernel(int64_t n, int dim, const TX *__restrict__ x, TX *__restrict__ y,
+norm_merge_apply_kernel(int64_t n, int dim, const TX *x, TX *y, // no __restrict__: y == x is allowed (in-place
+                        // normalisation of a rollout row); every element is read and then written by the same thread
                         const double *__restrict__ batch, int n_batches, const double *__restrict__ run_in,
                         double *__restrict__ run_out, int update, double eps) {
     const int f = blockIdx.y;

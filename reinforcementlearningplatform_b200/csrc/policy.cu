@@ -137,7 +137,7 @@ policy_forward_kernel(const __grid_constant__ PolicyArgs a, int64_t n) {
 int fill_net(const b200_mlp *m, NetDev *nd, int *arena, int *act_rows) {
     if (m->n_layers < 1 || m->n_layers > MAX_LAYERS) return B200ENV_ESIZE;
     nd->n_layers = m->n_layers;
-    nd->out_act = m->out_act;
+    nd->out_act = m->out_act == 2 ? 0 : m->out_act; // 2 (tanh range map) is applied by policy_sample_store
     for (int l = 0; l <= m->n_layers; ++l) {
         if (m->dims[l] < 1 || m->dims[l] > 1024) return B200ENV_ESIZE;
         nd->dims[l] = m->dims[l];
@@ -195,23 +195,68 @@ int policy_launch_fp32(int64_t n, const b200_mlp *actor, const b200_mlp *critic,
     return b200_check_launch();
 }
 
+namespace {
+int policy_check(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const float *obs, const float *a_min,
+                 const float *a_max, float std_, const float *std_vec, const float *action, const float *value) {
+    if (n <= 0) return B200ENV_ESIZE;
+    if (!obs || (!actor && !critic)) return B200ENV_ENULL;
+    if (actor && (!action || !a_min || !a_max)) return B200ENV_ENULL;
+    if (critic && !value) return B200ENV_ENULL;
+    if (actor && !std_vec && !(std_ > 0.0f)) return B200ENV_EPARAMS;
+    if (actor && (actor->out_act < 0 || actor->out_act > 2)) return B200ENV_EPARAMS;
+    if (critic && critic->dims[critic->n_layers > 0 && critic->n_layers <= 4 ? critic->n_layers : 0] != 1) return B200ENV_EPARAMS;
+    if (actor && critic && actor->dims[0] != critic->dims[0]) return B200ENV_EPARAMS;
+    return B200ENV_OK;
+}
+} // namespace
+
 extern "C" B200_API int b200_policy_forward(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const float *obs,
                                             const float *a_min, const float *a_max, float std_, const float *noise,
                                             uint64_t seed, uint64_t step, int64_t env_index_offset, int precision,
                                             float *action, float *log_prob, float *mean, float *value,
                                             void *cuda_stream) {
-    if (n <= 0) return B200ENV_ESIZE;
-    if (!obs || (!actor && !critic)) return B200ENV_ENULL;
-    if (actor && (!action || !a_min || !a_max)) return B200ENV_ENULL;
-    if (critic && !value) return B200ENV_ENULL;
-    if (actor && !(std_ > 0.0f)) return B200ENV_EPARAMS;
-    if (critic && critic->dims[critic->n_layers > 0 && critic->n_layers <= 4 ? critic->n_layers : 0] != 1) return B200ENV_EPARAMS;
-    if (actor && critic && actor->dims[0] != critic->dims[0]) return B200ENV_EPARAMS;
-    PolicyIO io;
+    const int rc = policy_check(n, actor, critic, obs, a_min, a_max, std_, nullptr, action, value);
+    if (rc) return rc;
+    PolicyIO io = {};
     io.obs = obs; io.a_min = a_min; io.a_max = a_max; io.noise = noise; io.std_ = std_;
+    io.out_affine = actor && actor->out_act == 2;
     io.seed = seed; io.step = step; io.off = env_index_offset;
     io.action = action; io.log_prob = log_prob; io.mean = mean; io.value = value;
     if (precision == B200_POLICY_FP32) return policy_launch_fp32(n, actor, critic, io, (cudaStream_t)cuda_stream);
     if (precision == B200_POLICY_TF32X3) return policy_launch_tc(n, actor, critic, io, (cudaStream_t)cuda_stream);
     return B200ENV_EPARAMS;
+}
+
+extern "C" B200_API size_t b200_policy_workspace_bytes(const b200_mlp *actor, const b200_mlp *critic) {
+    if (!actor && !critic) return 0;
+    return policy_umma_workspace_bytes(actor, critic);
+}
+
+extern "C" B200_API int b200_policy_pack(const b200_mlp *actor, const b200_mlp *critic, void *workspace,
+                                         size_t workspace_bytes, void *cuda_stream) {
+    if (!actor && !critic) return B200ENV_ENULL;
+    return policy_umma_pack(actor, critic, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
+}
+
+extern "C" B200_API int b200_policy_forward_packed(int64_t n, const b200_mlp *actor, const b200_mlp *critic,
+                                                   const void *workspace, size_t workspace_bytes, const float *obs,
+                                                   const float *a_min, const float *a_max, float std_,
+                                                   const float *std_vec, const float *noise, uint64_t seed, uint64_t step,
+                                                   int64_t env_index_offset, float *action, float *log_prob, float *mean,
+                                                   float *value, void *cuda_stream) {
+    const int rc = policy_check(n, actor, critic, obs, a_min, a_max, std_, std_vec, action, value);
+    if (rc) return rc;
+    PolicyIO io = {};
+    io.obs = obs; io.a_min = a_min; io.a_max = a_max; io.noise = noise; io.std_ = std_vec ? 1.0f : std_;
+    io.std_vec = std_vec;
+    io.out_affine = actor && actor->out_act == 2;
+    io.seed = seed; io.step = step; io.off = env_index_offset;
+    io.action = action; io.log_prob = log_prob; io.mean = mean; io.value = value;
+    return policy_launch_umma(n, actor, critic, workspace, workspace_bytes, io, (cudaStream_t)cuda_stream);
+}
+
+extern "C" B200_API int b200_umma_probe(const float *A, const float *W, float *D, int N, int K, int three_pass,
+                                        void *cuda_stream) {
+    if (!A || !W || !D) return B200ENV_ENULL;
+    return policy_umma_probe(A, W, D, N, K, three_pass, (cudaStream_t)cuda_stream);
 }

@@ -197,7 +197,7 @@ policy_forward_tc_kernel(const __grid_constant__ TcArgs a, int64_t n) {
 int fill_tc(const b200_mlp *m, TcNet *nd, int *arena) {
     if (m->n_layers < 1 || m->n_layers > TC_MAX_LAYERS) return B200ENV_ESIZE;
     nd->n_layers = m->n_layers;
-    nd->out_act = m->out_act;
+    nd->out_act = m->out_act == 2 ? 0 : m->out_act; // 2 (tanh range map) is applied by policy_sample_store
     for (int l = 0; l <= m->n_layers; ++l) {
         if (m->dims[l] < 1 || m->dims[l] > TC_MAX_DIM) return B200ENV_ESIZE; // wider layers: not supported (no fallback)
         nd->dims[l] = m->dims[l];

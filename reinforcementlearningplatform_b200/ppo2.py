@@ -36,10 +36,14 @@ DEFAULT_PPO_MSG = {  # demonstration/PPO2/PPO2-4-CartPoleAngleOnly/train.py:141-
 
 class VecPPO2:
     def __init__(self, env, actor: torch.nn.Module, critic: torch.nn.Module, ppo_msg: Optional[dict] = None,
-                 std: Optional[float] = None, reward_norm: bool = True, seed: int = 0, group=None):
+                 std=None, reward_norm: bool = True, seed: int = 0, group=None, actor_out_act: Optional[str] = None):
         """``env``: a vector env built with ``io_dtype=torch.float32, auto_reset=True``; ``actor`` / ``critic``: tanh
         MLPs on ``env.device`` (the reference's PPOActor_Gaussian / PPOCritic shapes, utils/classes.py:529-615);
-        ``buffer_size`` of ``ppo_msg`` is the number of time steps T per rollout (T x N transitions per learn())."""
+        ``buffer_size`` of ``ppo_msg`` is the number of time steps T per rollout (T x N transitions per learn()).
+        ``actor_out_act``: the head of ``actor.forward`` ("relu", "identity" or "tanh_range"); default: the module's own
+        ``out_act`` attribute, else "relu" (PPOActor_Gaussian.forward, utils/classes.py:563-569).  The behaviour policy
+        (K-POLICY in ``collect``) and the learner's ``actor(s)`` must use the same head, or the ratios are wrong.
+        ``std``: a float or one value per action dimension."""
         self.env, self.actor, self.critic, self.group = env, actor, critic, group
         m = dict(DEFAULT_PPO_MSG)
         m.update(ppo_msg or {})
@@ -47,9 +51,12 @@ class VecPPO2:
         self.gamma, self.lmd, self.K_epochs, self.eps_clip = m['gamma'], m['lmd'], m['K_epochs'], m['eps_clip']
         self.buffer = RolloutBuffer(m['buffer_size'], env)
         ar = torch.as_tensor(env.action_range, dtype=torch.float32)
-        self.std = float(std if std is not None else getattr(actor, 'std', 0.5))
-        self.policy = GaussianPolicy(linear_layers(actor), linear_layers(critic), ar[:, 0], ar[:, 1], self.std,
-                                     device=env.device, seed=seed, env_index_offset=env.env_index_offset)
+        std = std if std is not None else getattr(actor, 'std', 0.5)
+        self.std = torch.as_tensor(std, dtype=torch.float32).reshape(-1).to(env.device)   # [1] or [A]
+        out_act = actor_out_act or getattr(actor, 'out_act', 'relu')
+        self.policy = GaussianPolicy(linear_layers(actor), linear_layers(critic), ar[:, 0], ar[:, 1],
+                                     self.std.cpu().numpy(), device=env.device, seed=seed,
+                                     env_index_offset=env.env_index_offset, actor_out_act=out_act)
         self.value_net = GaussianPolicy(None, linear_layers(critic), ar[:, 0], ar[:, 1], 1.0, device=env.device)
         eps = 1e-5 if m['set_adam_eps'] else 1e-8                                   # PPO2.py:50-55
         self.optimizer_actor = torch.optim.Adam(actor.parameters(), lr=m['a_lr'], eps=eps)
@@ -84,9 +91,9 @@ class VecPPO2:
     # ------------------------------------------------------------------ update (PPO2.py:78-170)
     def _log_prob_entropy(self, s, a):
         mean = self.actor(s)
-        var = self.std * self.std
-        lp = -((a - mean) ** 2) / (2 * var) - math.log(self.std) - math.log(math.sqrt(2 * math.pi))
-        ent = (0.5 + 0.5 * math.log(2 * math.pi) + math.log(self.std)) * a.shape[1]   # Normal.entropy().sum(1)
+        std = self.std.expand(a.shape[1])
+        lp = -((a - mean) ** 2) / (2 * std * std) - torch.log(std) - math.log(math.sqrt(2 * math.pi))
+        ent = float((0.5 + 0.5 * math.log(2 * math.pi) + torch.log(std)).sum())           # Normal.entropy().sum(1)
         return lp, ent
 
     def learn(self) -> dict:
@@ -102,11 +109,18 @@ class VecPPO2:
             a_lp_sum = a_lp.sum(1, keepdim=True)
         B = T * N
         mb = min(m['mini_batch_size'], B) if m['using_mini_batch'] else B
+        # BatchSampler(SubsetRandomSampler(range(B)), mb, drop_last=False) (PPO2.py:104): ceil(B / mb) mini-batches, the last
+        # one partial.  Every mini-batch issues gradient all-reduces, so all ranks must run the SAME number of them even
+        # when dist.shard() gave them n_local values that differ by one: the count comes from the smallest B of the group
+        # and each rank spreads its own B samples over that many batches.
+        n_mb = _dist.agree_min(-(-B // mb), self.group)
+        bounds = [(B * j) // n_mb for j in range(n_mb + 1)] if n_mb != -(-B // mb) else \
+                 [min(j * mb, B) for j in range(n_mb + 1)]
         last = {}
         for _ in range(self.K_epochs):
             perm = torch.randperm(B, device=s.device, generator=self._gen)
-            for k in range(0, B - mb + 1, mb):                                       # BatchSampler(..., drop_last=False)
-                idx = perm[k:k + mb]
+            for j in range(n_mb):
+                idx = perm[bounds[j]:bounds[j + 1]]
                 lp_now, ent = self._log_prob_entropy(s[idx], a[idx])
                 ratios = torch.exp(lp_now.sum(1, keepdim=True) - a_lp_sum[idx])
                 surr1 = ratios * adv[idx]
@@ -144,6 +158,7 @@ class VecPPO2:
 
 
 def reference_nets(state_dim: int, action_dim: int, device, init_std: float = 0.5, mean_act: str = "relu"):
+    # the Actor carries `out_act` so that VecPPO2 gives K-POLICY the same head as Actor.forward
     """Actor / critic with the layer shapes, tanh activations and orthogonal init of the reference's
     PPOActor_Gaussian / PPOCritic (utils/classes.py:529-615), as plain nn.Modules on ``device``."""
     class Actor(torch.nn.Module):
@@ -152,6 +167,7 @@ def reference_nets(state_dim: int, action_dim: int, device, init_std: float = 0.
             self.fc1, self.fc2 = torch.nn.Linear(state_dim, 64), torch.nn.Linear(64, 64)
             self.fc3, self.mean_layer = torch.nn.Linear(64, 32), torch.nn.Linear(32, action_dim)
             self.std = init_std
+            self.out_act = mean_act
             for l, g in ((self.fc1, 1.0), (self.fc2, 1.0), (self.fc3, 1.0), (self.mean_layer, 0.01)):
                 torch.nn.init.orthogonal_(l.weight, gain=g)
                 torch.nn.init.constant_(l.bias, 0)

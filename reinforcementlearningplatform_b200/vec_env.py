@@ -124,16 +124,29 @@ class VecEnvBase:
         io.io_dtype = _lib.F32 if (self.io_dtype == torch.float32 and self.dtype == torch.float64) else _lib.F64
         return io
 
-    def _as_soa(self, x, rows: int) -> torch.Tensor:
-        """Accept [N, rows] (reference orientation, preferred when ambiguous) or [rows, N] (engine SoA)."""
+    def _as_soa(self, x, rows: int, layout: Optional[str] = None) -> torch.Tensor:
+        """Accept [N, rows] (reference orientation) or [rows, N] (engine SoA).  A 1-D vector of ``rows`` values is one
+        action broadcast to every instance; of ``N`` values (rows == 1) one value per instance.  When n_envs == rows a
+        2-D input fits both orientations: ``layout`` ("rows_first" = [rows, N] or "envs_first" = [N, rows]) must then
+        say which one is meant -- guessing would silently hand every instance the wrong action components."""
         if not torch.is_tensor(x):
             x = torch.as_tensor(np.asarray(x), dtype=self.io_dtype)
         x = x.to(device=self.device, dtype=self.io_dtype)
         if x.dim() == 1:
-            x = x.view(1, -1) if rows == 1 and x.numel() == self.n_envs else x.view(-1, 1).expand(rows, self.n_envs)
-        if x.shape == (self.n_envs, rows):  # reference orientation wins when n_envs == rows
+            if rows == 1 and x.numel() == self.n_envs:
+                return x.view(1, -1).contiguous()
+            if x.numel() != rows:
+                raise ValueError(f"expected {rows} values (one action for all instances), got {x.numel()}")
+            return x.view(-1, 1).expand(rows, self.n_envs).contiguous()
+        if layout not in (None, "rows_first", "envs_first"):
+            raise ValueError("layout must be 'rows_first' or 'envs_first'")
+        ef, rf = x.shape == (self.n_envs, rows), x.shape == (rows, self.n_envs)
+        if ef and rf and layout is None and rows > 1:
+            raise ValueError(f"a [{rows},{rows}] input is ambiguous when n_envs == {rows}: pass layout='envs_first' "
+                             "([N, dim], the reference's orientation) or layout='rows_first' ([dim, N], engine SoA)")
+        if ef and layout != "rows_first":
             return x.t().contiguous()
-        if x.shape == (rows, self.n_envs):
+        if rf and layout != "envs_first":
             return x.contiguous()
         raise ValueError(f"expected [{self.n_envs},{rows}] or [{rows},{self.n_envs}], got {tuple(x.shape)}")
 
@@ -166,7 +179,13 @@ class VecEnvBase:
                                                    self.env_index_offset, self._stream()), "b200env_reset")
         else:
             self._reset_default(mask)
-            self.observe()
+            if mask is None:
+                self.observe()
+            else:  # get_state() of the re-initialised lanes only: the other lanes keep their next_state (s' of the last step)
+                keep = self._next_obs.clone()
+                self.observe()
+                m = mask.to(self.device).bool()
+                self._next_obs[:, ~m] = keep[:, ~m]
         sel = slice(None) if mask is None else mask.to(self.device).bool()
         self._obs[:, sel] = self._next_obs[:, sel]
         self._reset_obs[:, sel] = self._next_obs[:, sel]
@@ -190,13 +209,14 @@ class VecEnvBase:
 
     get_state = observe
 
-    def step_update(self, action, dis=None) -> None:
+    def step_update(self, action, dis=None, layout: Optional[str] = None) -> None:
         """``env.step_update(action)`` (rl_base.py:126) for every instance; results land in
-        ``current_state, next_state, reward, is_terminal, terminal_flag`` like the reference."""
-        a = self._as_soa(action, self._ad)
+        ``current_state, next_state, reward, is_terminal, terminal_flag`` like the reference.  ``layout``: see
+        :meth:`_as_soa` (only needed when n_envs == action_dim)."""
+        a = self._as_soa(action, self._ad, layout)
         self._action = a
         self.current_action = a.t()
-        d = None if dis is None else self._as_soa(dis, self._dd)
+        d = None if dis is None else self._as_soa(dis, self._dd, layout)
         self.step_soa(a, d)
 
     def step_soa(self, action_soa: torch.Tensor, dis_soa: Optional[torch.Tensor] = None) -> None:

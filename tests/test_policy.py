@@ -54,7 +54,7 @@ def _build(c, torch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-6), ("tf32x3", 5e-6)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-6), ("tf32x3", 5e-6), ("umma", 5e-6)])
 def test_engine_policy_matches_reference_nets(precision, tol):
     import torch
     import reinforcementlearningplatform_b200 as rlp
@@ -121,8 +121,87 @@ def test_policy_drives_env_on_device():
     assert out["value"].shape == (n,) and out["log_prob"].shape == (8, n)
 
 
-def test_wide_nets_are_rejected_not_silently_slow():
-    """nets that do not fit shared memory return B200ENV_ESIZE (no fallback path exists)"""
+def wide_case():
+    with np.load(os.path.join(GOLDEN, "policy_wide.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_wide_fixture_is_consistent_with_a_float64_restatement():
+    c = wide_case()
+    h = c["s"].astype(np.float64)
+    for l in ("fc1", "fc2"):
+        h = np.tanh(h @ c[f"actor_{l}_w"].astype(np.float64).T + c[f"actor_{l}_b"])
+    off = (c["a_min"].astype(np.float64) + c["a_max"]) / 2
+    mean = np.tanh(h @ c["actor_mean_layer_w"].astype(np.float64).T + c["actor_mean_layer_b"]) * (c["a_max"] - off) + off
+    v = c["s"].astype(np.float64)
+    for k in range(2):
+        v = np.tanh(v @ c[f"critic_l{k}_w"].astype(np.float64).T + c[f"critic_l{k}_b"])
+    v = (v @ c["critic_l2_w"].astype(np.float64).T + c["critic_l2_b"])[:, 0]
+    np.testing.assert_allclose(c["mean"], mean, atol=2e-5)
+    np.testing.assert_allclose(c["value"], v, atol=2e-5)
+
+
+@pytest.mark.gpu
+def test_engine_policy_matches_the_256_wide_dppo2_demo_nets():
+    """41-256-256-2 actor with the tanh range head and per-dimension std, 41-256-256-1 critic
+    (demonstration/DPPO2/DPPO2-4-UGVForwardObstacleAvoidance/train.py:26-107): weights streamed through shared memory.
+    Tolerance 2e-5 absolute on mean / value: 256-term float32 sums (the reference's own float32 GEMM is ~1e-5 from the
+    float64 restatement above), head gain up to 2 pi."""
+    import torch
+    import reinforcementlearningplatform_b200 as rlp
+    c = wide_case()
+
+    def lin(w, b):
+        l = torch.nn.Linear(w.shape[1], w.shape[0])
+        with torch.no_grad():
+            l.weight.copy_(torch.from_numpy(w))
+            l.bias.copy_(torch.from_numpy(b))
+        return l.cuda()
+    actor = [lin(c[f"actor_{n}_w"], c[f"actor_{n}_b"]) for n in ("fc1", "fc2", "mean_layer")]
+    critic = [lin(c[f"critic_l{k}_w"], c[f"critic_l{k}_b"]) for k in range(3)]
+    pol = rlp.GaussianPolicy(actor, critic, c["a_min"], c["a_max"], c["std"], actor_out_act="tanh_range")
+    # 400 fixture rows, tiled to cover several 128-instance tiles per CTA and a ragged last tile
+    reps = 53
+    obs = torch.from_numpy(np.ascontiguousarray(np.tile(c["s"], (reps, 1)).T)).cuda()
+    eps = torch.from_numpy(np.ascontiguousarray(np.tile(c["eps"], (reps, 1)).T)).cuda()
+    out = pol(obs, noise=eps, want_mean=True)
+    f = lambda t: t.cpu().numpy().T
+    tol = 2e-5
+    for name, t in (("mean", tol), ("action", tol + 1e-6), ("log_prob", 10 * tol)):
+        np.testing.assert_allclose(f(out[name]), np.tile(c[name], (reps, 1)), atol=t, err_msg=name)
+    np.testing.assert_allclose(out["value"].cpu().numpy(), np.tile(c["value"], reps), atol=tol)
+    with pytest.raises(ValueError):
+        rlp.GaussianPolicy(actor, critic, c["a_min"], c["a_max"], c["std"], precision="tf32x3")  # vector std: umma only
+
+
+@pytest.mark.gpu
+def test_umma_policy_sees_optimizer_steps_and_ragged_sizes():
+    """the packed weight copy follows in-place parameter updates; n need not be a multiple of the 128-instance tile"""
+    import torch
+    import reinforcementlearningplatform_b200 as rlp
+    c = cases()[0]
+    actor, critic = _build(c, torch)
+    pol = rlp.GaussianPolicy(actor, critic, c["a_min"], c["a_max"], float(c["std"]))
+    ref = rlp.GaussianPolicy(actor, critic, c["a_min"], c["a_max"], float(c["std"]), precision="fp32")
+    for n in (1, 127, 129, 1000, 128 * 148 * 2 + 77):
+        obs = torch.randn(6, n, device="cuda")
+        eps = torch.randn(8, n, device="cuda")
+        a, b = pol(obs, noise=eps, want_mean=True), ref(obs, noise=eps, want_mean=True)
+        for k in ("mean", "action", "value"):
+            assert float((a[k] - b[k]).abs().max()) <= 7e-6, (n, k)
+    with torch.no_grad():
+        for l in actor + critic:
+            l.weight.mul_(0.5)
+            l.bias.add_(0.1)
+    obs = torch.randn(6, 777, device="cuda")
+    eps = torch.randn(8, 777, device="cuda")
+    a, b = pol(obs, noise=eps, want_mean=True), ref(obs, noise=eps, want_mean=True)
+    assert float((a["mean"] - b["mean"]).abs().max()) <= 7e-6 and float((a["value"] - b["value"]).abs().max()) <= 7e-6
+
+
+def test_wide_nets_are_rejected_by_the_round1_kernels_not_silently_slow():
+    """nets that do not fit the shared-memory design of policy.cu / policy_tc.cu return B200ENV_ESIZE there (the tcgen05
+    kernel streams them; no fallback path exists)"""
     import ctypes as C
     from reinforcementlearningplatform_b200 import _lib
     lib = _lib.load()

@@ -34,7 +34,21 @@ def run(kind, reps=10, T=2048, N=131072, dev="cuda"):
         y = torch.empty_like(x)
         nz = rlp.Normalization(dim, device=dev, sync=False)
         fn, nbytes, units = (lambda: nz.normalize_soa(x, out=y)), 12.0, dim * n
-    elif kind in ("policy", "policy_fp32"):
+    elif kind == "policy_wide":
+        # the 41-256-256-{2,1} nets of the DPPO2 UGV-FOA demo (train.py:26-107), 262,144 instances (config #5 per GPU)
+        S, A, n = 41, 2, 1 << 18
+        torch.manual_seed(0)
+        mk_l = lambda i, o: torch.nn.Linear(i, o).to(dev)
+        actor = [mk_l(S, 256), mk_l(256, 256), mk_l(256, A)]
+        critic = [mk_l(S, 256), mk_l(256, 256), mk_l(256, 1)]
+        pol = rlp.GaussianPolicy(actor, critic, [-3.0, -6.28], [3.0, 6.28], [1.0, 2.09], device=dev,
+                                 actor_out_act="tanh_range")
+        obs = torch.randn((S, n), generator=g, device=dev, dtype=torch.float32)
+        outs = pol(obs)
+        fn = lambda: pol(obs, action=outs["action"], log_prob=outs["log_prob"], value=outs["value"])
+        flops = 2.0 * (2 * (S * 256 + 256 * 256) + 256 * A + 256)
+        nbytes, units = (S + 2 * A + 1) * 4.0, n
+    elif kind in ("policy", "policy_fp32", "policy_tf32x3"):
         # the reference's PPOActor_Gaussian / PPOCritic shapes for UavFntsmcParamPos (state 6, 8 gains), 1 M instances
         S, A, n = 6, 8, 1 << 20
         torch.manual_seed(0)
@@ -42,7 +56,7 @@ def run(kind, reps=10, T=2048, N=131072, dev="cuda"):
         actor = [mk_l(S, 64), mk_l(64, 64), mk_l(64, 32), mk_l(32, A)]
         critic = [mk_l(S, 64), mk_l(64, 32), mk_l(32, 1)]
         pol = rlp.GaussianPolicy(actor, critic, [0.0] * A, [5.0] * A, 0.45, device=dev,
-                                 precision="fp32" if kind == "policy_fp32" else "tf32x3")
+                                 precision={"policy": "umma", "policy_fp32": "fp32", "policy_tf32x3": "tf32x3"}[kind])
         obs = torch.randn((S, n), generator=g, device=dev, dtype=torch.float32)
         outs = pol(obs)
         fn = lambda: pol(obs, action=outs["action"], log_prob=outs["log_prob"], value=outs["value"])
