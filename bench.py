@@ -9,10 +9,17 @@ one launch of the fused step kernel over all instances of this rank.  Instances 
 scaling, no data-path collective); the timed region is bracketed by barrier + synchronize and the reported time is
 the max over ranks.
 
-The JSON line carries, besides the contract keys: `roofline` (algorithmic HBM bytes of the step kernel / measured
-HBM peak, plus the fp64-pipe view), `cpu_baseline` (the C port of the reference timed on the host cores on a bounded
-sample), `e2e` (same metric through the public VecEnv API with host buffers: pinned H2D of the actions and D2H of
-next_state/reward/done every step), `clocks`, `gpu_launches`, and `also` (the other single-GPU workloads).
+The JSON line carries, besides the contract keys: `roofline` (the binding resource of the step kernel -- the FP64 pipe
+for the UAV / cart-pole kernels -- with the HBM view beside it; DRAM traffic and executed-instruction counts are parsed at
+run time from the committed ncu summaries under profiles/), `repeats` (the timed block of K steps run 5 times: median
+and spread), `cpu_baseline` (the UNMODIFIED Python reference on every host core, one process per core, from the
+byte-compiled staging oracle/_ref, and the C port beside it), `e2e` (same metric through the public VecEnv API with host
+buffers: pinned H2D of the actions and D2H of next_state / reward / done every step, plus a raw cudaMemcpyAsync probe of
+the same bytes), `clocks`, `gpu_launches`, and `also` (the other configs of BASELINE.json; under torchrun every rank
+takes part in the sharded ones -- config #3's rollout + GAE + statistics all-reduce, config #5's DPPO2 iteration).
+
+`--impl reference` times the reference's own Python loop (oracle/_ref, or /root/reference where it exists) on all host
+cores and never imports the product package.
 """
 from __future__ import annotations
 
@@ -20,6 +27,9 @@ import argparse
 import json
 import os
 import sys
+import glob
+import re
+import subprocess
 import threading
 import time
 
@@ -50,12 +60,41 @@ ALGO_BYTES = {
 }
 # algorithmic fp64 work per env-step (weighted flops, SURVEY.md section 8d convention), used for the fp64-pipe view
 ALGO_FLOPS = {"uav_pos": 5100.0, "uav_att": 3300.0, "cartpole": 3100.0, "ugvo": 54000.0, "soi": 125.0, "fas": 570.0}
-# what the kernel really executes per env-step, counted from the ncu SASS page of the profiled launch
-# (profiles/r1/uav_pos_final_ophist.txt): fp64-pipe instructions (DFMA + DMUL + DADD + DSETP) and flops (DFMA = 2)
-EXEC_F64 = {"uav_pos": {"pipe_inst": 2081.9, "flops": 3193.9, "src": "profiles/r1/uav_pos_final_ophist.txt"}}
-# DRAM bytes per launch of the dominant kernel from the `ncu --set full` capture (dram__bytes_read + write), at the
-# profiled size; None where no capture is committed
-NCU_TRAFFIC = {("uav_pos", "f64", 1 << 20): {"bytes": 344037888 + 418002944, "src": "profiles/r1/uav_pos_final_keys.txt"}}
+PROFILED_ENVS = {"uav_pos": 1 << 20, "uav_att": 1 << 20, "cartpole": 65536, "ugvo": 262144}   # tools/profile_all.sh sizes
+
+
+def profile_facts(workload):
+    """What the committed ncu summaries say about the step kernel of `workload`: DRAM bytes per launch
+    (dram__bytes_read + write of the `--set full` capture) and the executed instruction mix per env-step
+    (profiles/tools/op_hist.py).  Parsed at run time from profiles/r*/<workload>_final_{keys,ophist}.txt, newest round
+    first, so that the roofline follows the profile that is committed, not a constant pasted into this file."""
+    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    for d in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*")), reverse=True):
+        keys, hist = os.path.join(d, f"{workload}_final_keys.txt"), os.path.join(d, f"{workload}_final_ophist.txt")
+        if not os.path.exists(keys):
+            continue
+        out = {"src": os.path.relpath(keys, ROOT), "profiled_envs": PROFILED_ENVS.get(workload)}
+        traffic = 0.0
+        for line in open(keys):
+            m = re.match(r"(dram__bytes_(?:read|write)\.sum)\s+(\w+)\s+\['([0-9.eE+-]+)'\]", line)
+            if m:
+                traffic += float(m.group(3)) * unit.get(m.group(2), 1.0)
+            m = re.match(r"(sm__pipe_fp64_cycles_active\S*|smsp__issue_active\S*|gpu__time_duration\.sum)\s+\S+\s+\['([0-9.eE+-]+)'\]", line)
+            if m:
+                out[m.group(1)] = float(m.group(2))
+        out["dram_bytes"] = traffic or None
+        if os.path.exists(hist):
+            per = {}
+            for line in open(hist):
+                m = re.match(r"(\w+)\s+\d+\s+[0-9.]+%\s+per-thread\s+([0-9.]+)", line)
+                if m:
+                    per[m.group(1)] = float(m.group(2))
+            out["fp64_pipe_inst"] = sum(per.get(k, 0.0) for k in ("DFMA", "DMUL", "DADD", "DSETP"))
+            out["fp64_flops"] = 2 * per.get("DFMA", 0.0) + per.get("DMUL", 0.0) + per.get("DADD", 0.0)
+            out["hist_src"] = os.path.relpath(hist, ROOT)
+        return out
+    return None
+
 
 WORKLOADS = {
     "uav_pos": dict(n=1 << 20, desc="UavFntsmcParam position tracking, dt=0.02, time_max=10, 8 gains~U(0,5)/step"),
@@ -152,11 +191,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def timed_steps(env, pool, steps, warmup, dist_on, sampler=None):
+def timed_steps(env, pool, steps, warmup, dist_on, sampler=None, dis_pool=None):
     import torch.distributed as dist
     P = pool.shape[0]
+    dis = (lambda k: dis_pool[k % dis_pool.shape[0]]) if dis_pool is not None else (lambda k: None)
     for k in range(warmup):
-        env.step_soa(pool[k % P])
+        env.step_soa(pool[k % P], dis(k))
     torch.cuda.synchronize()
     if dist_on:
         dist.barrier()
@@ -164,7 +204,7 @@ def timed_steps(env, pool, steps, warmup, dist_on, sampler=None):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(steps):
-        env.step_soa(pool[(warmup + k) % P])
+        env.step_soa(pool[(warmup + k) % P], dis(warmup + k))
     e1.record()
     if sampler is not None:  # the launches are enqueued, the GPU is executing them: read the clocks under load
         for _ in range(3):
@@ -255,37 +295,124 @@ def cpu_port(workload, n, steps, threads, seed=2024):
     return n * steps / dt, dt
 
 
+def reference_tree():
+    """Where the UNMODIFIED Python reference can be imported from: the live tree in the build container, else the
+    byte-compiled staging made by oracle/stage_reference.py (travels to the GPU box as a built artefact)."""
+    for d in (os.environ.get("RLP_REFERENCE"), "/root/reference", os.path.join(ROOT, "oracle", "_ref")):
+        if d and os.path.isdir(os.path.join(d, "environment")):
+            return d
+    return None
+
+
+def reference_python(workload, seconds, procs):
+    """The reference's own Python step loop (oracle/bench_reference_python.py --worker: e.g. the body of
+    PPO2-4-UavFntsmcParamPos/train.py:290-297 with uniform random gains, reset(True) on terminal) in `procs` processes at
+    once, one per host core, OMP_NUM_THREADS=1 like the reference sets it (DPPO2-4-UGVForwardObstacleAvoidance/
+    train.py:22).  Returns aggregate env-steps/s, per-core mean and the tree the modules came from."""
+    tree = reference_tree()
+    if tree is None:
+        return None
+    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", RLP_REFERENCE=tree,
+               CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "bench_reference_python.py"), "--worker", workload,
+           "--seconds", str(seconds)]
+    ps = [subprocess.Popen(cmd + ["--seed", str(k + 1)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, text=True)
+          for k in range(procs)]
+    rates = []
+    for q in ps:
+        out, _ = q.communicate(timeout=600)
+        try:
+            d = json.loads(out.strip().splitlines()[-1])
+            rates.append(d["steps"] / d["seconds"])
+        except Exception:
+            pass
+    if not rates:
+        return None
+    return {"value": float(sum(rates)), "unit": "env-steps/s", "cores": len(rates), "per_core": float(np.mean(rates)),
+            "kind": "reference", "tree": os.path.relpath(tree, ROOT) if tree.startswith(ROOT) else tree,
+            "sample": f"{len(rates)} processes x {seconds:g} s of the reference's Python step loop (200 warm-up steps), "
+                      "uniform random actions, reset(True) on terminal"}
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores.  The reference is pure
-    Python and cannot travel to the GPU box, so this arm times its C restatement (oracle/, kind "port") with all host
-    threads on a bounded sample of the same workload."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores -- the unmodified
+    Python classes (byte-compiled staging oracle/_ref on the GPU box), one process per core.  Nothing of the product
+    package is imported here.  Only if no reference tree exists at all does this arm fall back to the C port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n = min(WORKLOADS[args.workload]["n"], 1 << 17)
-    total_steps = args.steps
-    for _ in range(max(args.warmup, 1)):
-        cpu_port(args.workload, n, 1, threads)
-    val, dt = cpu_port(args.workload, n, total_steps, threads)
+    cores = os.cpu_count() or 1
+    # a "step" of this arm = one env-step on every core; --steps K is honoured as K seconds-long windows, bounded
+    seconds = float(min(max(args.steps * 0.25, 3.0), 30.0))
+    reference_python(args.workload, min(1.0, seconds), cores)         # warm-up: page in numpy / cv2 on every core
+    ref = reference_python(args.workload, seconds, cores)
+    if ref is not None:
+        val = ref["value"]
+        base = ref
+        envs, per_step = ref["cores"], ref["cores"] / val * 1e3
+    else:
+        threads = cores
+        n = min(WORKLOADS[args.workload]["n"], 1 << 17)
+        for _ in range(max(args.warmup, 1)):
+            cpu_port(args.workload, n, 1, threads)
+        val, dt = cpu_port(args.workload, n, args.steps, threads)
+        base = {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                "sample": f"{n} instances x {args.steps} steps, OpenMP over instances (no reference tree found)"}
+        envs, per_step = n, dt * 1e3 / args.steps
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / total_steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "envs": n, "desc": WORKLOADS[args.workload]["desc"]},
-        "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} instances x {total_steps} steps, OpenMP over instances"},
+        "config": {"workload": args.workload, "envs": envs, "desc": WORKLOADS[args.workload]["desc"],
+                   "note": "one env instance per host core, all cores at once; a step = one env-step on every core"},
+        "cpu_baseline": base,
         "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+def copy_probe(n, A, S, steps, dev, dist_on, chunks=4):
+    """The bytes of one e2e step moved by plain cudaMemcpyAsync (torch copy_ of pinned float32 buffers, one call per
+    buffer), no kernel in between, same shard / stream structure: what the host link alone allows at this GPU count."""
+    import torch.distributed as dist
+    nc = n // chunks
+    streams = [torch.cuda.Stream(device=dev) for _ in range(chunks)]
+    h_a = [torch.empty((A, nc), dtype=torch.float32).pin_memory() for _ in range(chunks)]
+    d_a = [torch.empty((A, nc), dtype=torch.float32, device=dev) for _ in range(chunks)]
+    d_o = [torch.empty((S + 1, nc), dtype=torch.float32, device=dev) for _ in range(chunks)]
+    h_o = [torch.empty((S + 1, nc), dtype=torch.float32).pin_memory() for _ in range(chunks)]
+    d_d = [torch.empty((nc,), dtype=torch.uint8, device=dev) for _ in range(chunks)]
+    h_d = [torch.empty((nc,), dtype=torch.uint8).pin_memory() for _ in range(chunks)]
+
+    def one():
+        for c in range(chunks):
+            with torch.cuda.stream(streams[c]):
+                d_a[c].copy_(h_a[c], non_blocking=True)
+                h_o[c].copy_(d_o[c], non_blocking=True)
+                h_d[c].copy_(d_d[c], non_blocking=True)
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    if dist_on:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
 def also_workloads(args, dev, dtype, peaks):
     """Short device-resident measurements of the other single-GPU configs (same timing rules, fewer steps)."""
     out = []
     hbm = peaks.get("hbm_gbs", 6650.0)
-    for w in ("uav_att", "cartpole", "soi", "fas", "ugvo", "fas_discrete", "ballbalancer", "twolink", "ugv", "uavr_hover"):
+    for w in ("cartpole", "soi", "fas", "ugvo", "fas_discrete", "ballbalancer", "twolink", "ugv", "uavr_hover"):
         if w == args.workload:
             continue
         n = WORKLOADS[w]["n"]
@@ -311,15 +438,6 @@ def also_workloads(args, dev, dtype, peaks):
         out.append({"workload": w + ":f32", "envs": n, "value": n / per, "unit": "env-steps/s", "ms_per_step": ms / 100,
                     "hbm_frac": ALGO_BYTES[w] / 2.0 * n / per / 1e9 / hbm, "desc": WORKLOADS[w]["desc"] + " [fp32 mode]"})
         del env, pool
-        torch.cuda.empty_cache()
-    # config #3: 2048-step rollouts of SOI and FAS into the device-resident buffer + GAE, 131072 instances per GPU
-    for w in ("soi", "fas"):
-        T, N = 2048, 131072
-        ms_roll, ms_gae = rollout_pipeline(w, N, T, dev, False)
-        out.append({"workload": f"rollout_{w}", "T": T, "envs": N, "value": T * N / ((ms_roll + ms_gae) * 1e-3),
-                    "unit": "env-steps/s", "ms_rollout": ms_roll, "ms_gae_and_norm": ms_gae,
-                    "desc": f"{WORKLOADS[w]['desc']}: {T}-step rollout written in place into a time-major float32 "
-                            "buffer by the step kernel (fp64 state/arithmetic), then GAE + advantage normalisation"})
         torch.cuda.empty_cache()
     # config #3: GAE over a 2048-step rollout, 131072 env columns per GPU
     from reinforcementlearningplatform_b200 import gae as G
@@ -385,6 +503,88 @@ def also_workloads(args, dev, dtype, peaks):
     return out
 
 
+def also_sharded(args, dev, dtype, world, rank, group_on):
+    """The configs of BASELINE.json that shard over GPUs, run by EVERY rank at every GPU count (rank 0 reports; times are
+    the max over ranks):
+      #3  rollout_soi / rollout_fas: 131,072 instances per GPU x 2048 steps written in place into the time-major buffer,
+          then K-GAE and the global advantage normalisation (3-double all-reduce) -- Proximal_Policy_Optimization2.py:88-100;
+      #5  dppo2_ugvo: one DPPO2 iteration of UGVForwardObstacleAvoidance with the demo's 41-256-256 nets: K-POLICY (tcgen05,
+          streamed weights) -> step kernel -> reward normalisation for T steps, then K-GAE + statistics all-reduce and
+          k_epo = 6 full-batch epochs with one flat-gradient all-reduce per net and epoch (Distributed_PPO2.py:86-104 made
+          synchronous).  T = 16 instead of the demo's 300-step buffer: the update runs on torch autograd (not this repo's
+          kernels) and would otherwise dominate the bench's wall time;
+      #4  uav_att, uav_pos at 2 M instances per GPU, uav_pos with an injected disturbance buffer."""
+    import torch.distributed as dist
+    import reinforcementlearningplatform_b200 as rlp
+    from reinforcementlearningplatform_b200.ppo2 import VecPPO2, dppo2_nets
+    out = []
+
+    def maxr(x):
+        if not group_on:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for w in ("soi", "fas"):
+        T, N = 2048, 131072
+        ms_roll, ms_gae = rollout_pipeline(w, N, T, dev, group_on, offset=rank * N)
+        ms_roll, ms_gae = maxr(ms_roll), maxr(ms_gae)
+        out.append({"workload": f"rollout_{w}", "T": T, "envs_per_gpu": N, "n_gpus": world,
+                    "value": world * T * N / ((ms_roll + ms_gae) * 1e-3), "unit": "env-steps/s", "ms_rollout": ms_roll,
+                    "ms_gae_allreduce_norm": ms_gae,
+                    "desc": f"config #3, {WORKLOADS[w]['desc']}: {T}-step rollout into the device buffer, K-GAE, 3-double "
+                            "all-reduce, normalise"})
+        torch.cuda.empty_cache()
+    # config #5
+    N, T = WORKLOADS["ugvo"]["n"], 16
+    env = make_env("ugvo", N, dev, rank * N, torch.float64, io_dtype=torch.float32)
+    env.reset(True)
+    ar = np.asarray(env.action_range, dtype=np.float64)
+    actor, critic = dppo2_nets(env.state_dim, env.action_dim, ar[:, 0], ar[:, 1], dev)
+    agent = VecPPO2(env, actor, critic, {"buffer_size": T, "K_epochs": 6, "using_mini_batch": False, "a_lr": 2e-5,
+                                          "c_lr": 2e-4, "use_lr_decay": False}, std=actor.std, seed=3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    agent.collect()
+    agent.learn()
+    torch.cuda.synchronize()
+    if group_on:
+        dist.barrier()
+    ev[0].record()
+    agent.collect()
+    ev[1].record()
+    agent.learn()
+    ev[2].record()
+    torch.cuda.synchronize()
+    ms_c, ms_l = maxr(ev[0].elapsed_time(ev[1])), maxr(ev[1].elapsed_time(ev[2]))
+    out.append({"workload": "dppo2_ugvo", "T": T, "envs_per_gpu": N, "n_gpus": world,
+                "value": world * T * N / ((ms_c + ms_l) * 1e-3), "collect_value": world * T * N / (ms_c * 1e-3),
+                "unit": "env-steps/s", "ms_collect": ms_c, "ms_learn": ms_l, "grad_allreduces": 12,
+                "desc": "config #5: UGVForwardObstacleAvoidance (DPPO2 variant) x 41-256-256 nets; collect = K-POLICY + step "
+                        "+ reward normalisation per time step; learn = K-GAE + statistics all-reduce + 6 full-batch epochs "
+                        "(torch autograd) with one flat-gradient all-reduce per net and epoch"})
+    del agent, env, actor, critic
+    torch.cuda.empty_cache()
+    # config #4 variants
+    for name, w, n, with_dis in (("uav_att", "uav_att", 1 << 20, False), ("uav_pos_2M", "uav_pos", 1 << 21, False),
+                                 ("uav_pos_dis", "uav_pos", 1 << 20, True)):
+        env = make_env(w, n, dev, rank * n, dtype)
+        env.reset(True)
+        pool = action_pool(env, n, 4, dev, dtype, seed=rank + 7)
+        dis = None
+        if with_dis:  # sinusoid + noise force disturbance per instance, 4 rotating buffers (UavRobust/ref_cmd.py:46-61 style)
+            g = torch.Generator(device=dev)
+            g.manual_seed(rank + 9)
+            dis = (0.5 * torch.randn((4, env._dd, n), generator=g, device=dev, dtype=torch.float64)).to(dtype).contiguous()
+        ms = timed_steps(env, pool, 40, 5, group_on, dis_pool=dis)
+        out.append({"workload": name, "envs_per_gpu": n, "n_gpus": world, "value": world * n * 40 / (ms * 1e-3),
+                    "unit": "env-steps/s", "ms_per_step": ms / 40,
+                    "desc": WORKLOADS[w]["desc"] + (" + injected disturbance [3, N] per step" if with_dis else "")})
+        del env, pool, dis
+        torch.cuda.empty_cache()
+    return out
+
+
 def exchange_times(dev, reps=50):
     """The only collectives of the path, timed on the device over NCCL: the DPPO2 gradient
     average as one all-reduce of a flat fp32 buffer (154 k parameters of the 41-256-256-{2,1} demo nets, and 9.5 k of
@@ -423,13 +623,13 @@ def exchange_times(dev, reps=50):
     return out
 
 
-def rollout_pipeline(workload, n, T, dev, dist_on, seed=5):
+def rollout_pipeline(workload, n, T, dev, dist_on, seed=5, offset=0):
     """config #3: a T-step rollout written by the step kernel straight into a device-resident time-major float32
     buffer (rollout.RolloutBuffer), then K-GAE over it and the global advantage normalisation (3-double all-reduce when
     sharded).  V(s), V(s') are synthetic N(0,1) columns (the critic is outside the hot path).  Returns the times of the
     two stages in ms."""
     import reinforcementlearningplatform_b200 as rlp
-    env = make_env(workload, n, dev, 0, torch.float64, io_dtype=torch.float32)
+    env = make_env(workload, n, dev, offset, torch.float64, io_dtype=torch.float32)
     env.reset(True)
     buf = rlp.RolloutBuffer(T, env)
     g = torch.Generator(device=dev)
@@ -442,6 +642,9 @@ def rollout_pipeline(workload, n, T, dev, dist_on, seed=5):
     buf.collect(env, 0, 8)  # warm-up
     buf.gae(vs, vsn, 0.99, 0.95)
     torch.cuda.synchronize()
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     e[0].record()
     buf.collect(env)  # b200env_rollout: all T steps in one call (one fused kernel for SOI / FAS)
@@ -496,8 +699,12 @@ def main():
     pool = action_pool(env, n, 4, dev, dtype, seed=rank + 1)
     sampler = ClockSampler(local)
     sampler.start()
-    ms = timed_steps(env, pool, args.steps, args.warmup, dist_on, sampler)
+    # the timed block (exactly K steps between barrier + synchronize, CUDA events, max over ranks), five times: `value`
+    # comes from the median block, the spread is reported
+    REPEATS = 5
+    blocks = [timed_steps(env, pool, args.steps, args.warmup if r == 0 else 1, dist_on, sampler) for r in range(REPEATS)]
     clocks = sampler.result()
+    ms = float(np.median(blocks))
     value = world * n * args.steps / (ms * 1e-3)
     per_launch_s = ms * 1e-3 / args.steps
     el = 8 if dtype == torch.float64 else 4
@@ -508,19 +715,34 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    achieved = algo_bytes / per_launch_s / 1e9
+    achieved_gbs = algo_bytes / per_launch_s / 1e9
     from reinforcementlearningplatform_b200 import _lib
     fma_peak = _lib.measure_fma_peak(_lib.F64 if el == 8 else _lib.F32)  # TFLOP/s, live, this GPU
-    pipe = {"achieved_tflops_weighted": ALGO_FLOPS.get(args.workload, float("nan")) * n / per_launch_s / 1e12,
-            "peak_tflops_fma": fma_peak, "peak_source": "b200_measure_fma_peak, live (8 independent FMA chains/thread)",
-            "note": "weighted = algorithmic flops in the SURVEY 8d convention (transcendentals at fixed weights)"}
-    if args.workload in EXEC_F64 and el == 8:
-        ex = EXEC_F64[args.workload]
-        pipe.update({"executed_tflops": ex["flops"] * n / per_launch_s / 1e12,
-                     "frac_flops": ex["flops"] * n / per_launch_s / 1e12 / fma_peak,
-                     "frac_pipe_slots": ex["pipe_inst"] * n / per_launch_s / 1e12 / (fma_peak / 2.0),
-                     "executed_per_step": ex})
-    tr = NCU_TRAFFIC.get((args.workload, args.dtype, n))
+    facts = profile_facts(args.workload) if el == 8 else None
+    hbm_view = {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                "algorithmic_bytes": algo_bytes, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"}
+    kernel = f"{args.workload}_step_kernel<{'double' if el == 8 else 'float'}>"
+    compute_bound = args.workload not in ("soi", "fas", "fas_discrete")
+    if compute_bound and facts and facts.get("fp64_flops"):
+        # binding resource = the FP64 pipe: executed fp64 flops (DFMA = 2) per env-step from the committed SASS histogram
+        # x instances / launch time against the FMA peak measured live; `frac_pipe_slots` counts every fp64-pipe
+        # instruction as one issue slot of that pipe (peak / 2 instructions per second)
+        ach = facts["fp64_flops"] * n / per_launch_s / 1e12
+        roofline = {"bound": "fp64_pipe", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s", "frac": ach / fma_peak,
+                    "frac_pipe_slots": facts["fp64_pipe_inst"] * n / per_launch_s / 1e12 / (fma_peak / 2.0),
+                    "peak_source": "b200_measure_fma_peak, live (8 independent FMA chains per thread)",
+                    "executed_per_env_step": {"fp64_flops": facts["fp64_flops"], "fp64_pipe_inst": facts["fp64_pipe_inst"],
+                                              "src": facts.get("hist_src")},
+                    "ncu_fp64_pipe_active_pct": facts.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "weighted_algorithmic_tflops": ALGO_FLOPS.get(args.workload, float("nan")) * n / per_launch_s / 1e12,
+                    "hbm": hbm_view}
+    else:
+        roofline = dict(hbm_view, bound="hbm")
+        roofline["fp64_pipe"] = {"peak_tflops_fma": fma_peak,
+                                 "weighted_algorithmic_tflops": ALGO_FLOPS.get(args.workload, float("nan")) * n / per_launch_s / 1e12}
+    same_size = facts and facts.get("profiled_envs") == n
+    roofline.update({"traffic": facts["dram_bytes"] if (facts and same_size) else None,
+                     "traffic_source": facts["src"] if (facts and same_size) else None, "kernel": kernel})
     line = {
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -529,46 +751,57 @@ def main():
                    "auto_reset": True, "parallelism": f"env-shard x{world}",
                    "l2": "per-step working set (state + action + outputs) exceeds the 126 MB L2; 4 rotating action buffers"
                    if n >= (1 << 19) else "working set fits L2 (config size); launch-bound"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": tr["bytes"] if tr else None, "traffic_source": tr["src"] if tr else None,
-                     "algorithmic_bytes": algo_bytes,
-                     "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
-                     "kernel": f"{args.workload}_step_kernel<{'double' if el == 8 else 'float'}>",
-                     "binding": "fp64 pipe / issue (not HBM): see fp64_pipe", "fp64_pipe": pipe},
-        "clocks": clocks, "gpu_launches": args.steps,
+        "repeats": {"blocks": REPEATS, "steps_per_block": args.steps, "ms_per_step": [b_ / args.steps for b_ in blocks],
+                    "median_ms_per_step": ms / args.steps,
+                    "spread": (max(blocks) - min(blocks)) / ms},
+        "roofline": roofline,
+        "clocks": clocks, "gpu_launches": args.steps * REPEATS,
     }
     if not args.no_extras:
+        A_dim, S_dim = env.action_dim, env.state_dim
         del env, pool
         torch.cuda.empty_cache()
-        e_steps = max(10, args.steps // 4)
+        e_steps = max(20, args.steps // 2)
         e_ms, e_n, h2d, d2h = timed_e2e(args.workload, n, e_steps, 3, dist_on, rank + 11, dev, rank * n, dtype,
                                         io_dtype=torch.float32)
-        line["e2e"] = {"value": world * e_n * e_steps / (e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": d2h, "io_dtype": "f32", "state_and_arithmetic": args.dtype,
+        p_ms = copy_probe(n, A_dim, S_dim, e_steps, dev, dist_on)
+        e_val = world * e_n * e_steps / (e_ms * 1e-3)
+        line["e2e"] = {"value": e_val, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "io_dtype": "f32", "state_and_arithmetic": args.dtype, "steps": e_steps,
+                       "copy_probe": {"value": world * e_n * e_steps / (p_ms * 1e-3), "unit": "env-steps/s-equivalent",
+                                      "h2d_gbs": world * h2d * e_steps / (p_ms * 1e-3) / 1e9,
+                                      "d2h_gbs": world * d2h * e_steps / (p_ms * 1e-3) / 1e9,
+                                      "what": "the same pinned buffers moved by one cudaMemcpyAsync each (torch copy_), no "
+                                              "kernel in between, same 4 shards / streams"},
+                       "frac_of_copy_probe": p_ms / e_ms,
                        "api": "VecEnv.step_soa on 4 shards / 4 streams: pinned host float32 actions in (the reference's "
                               "actor emits float32), float32 policy_state + reward and u8 is_terminal out every step; "
                               "state and arithmetic stay in the env dtype; the host waits for a shard's result before "
                               "its next action"}
-        if dtype == torch.float64:
+        if dtype == torch.float64 and world == 1:
             f_ms, f_n, fh, fd = timed_e2e(args.workload, n, e_steps, 3, dist_on, rank + 11, dev, rank * n, dtype)
             line["e2e_f64_io"] = {"value": world * f_n * e_steps / (f_ms * 1e-3), "unit": "env-steps/s",
                                   "h2d_bytes_per_step": fh, "d2h_bytes_per_step": fd, "io_dtype": "f64"}
+        also = also_sharded(args, dev, dtype, world, rank, dist_on)          # every rank takes part
         if rank == 0 and world == 1:
-            line["also"] = also_workloads(args, dev, dtype, peaks)
+            also += also_workloads(args, dev, dtype, peaks)
+        if rank == 0:
+            line["also"] = also
         if rank == 0 and world == 1:
             threads = os.cpu_count() or 1
+            ref = reference_python(args.workload, 4.0, threads)
             cn = min(n, 1 << 17)
-            csteps = 40
+            cval, cdt = cpu_port(args.workload, cn, 40, threads)
+            csteps = int(min(max(40 * 6.0 / max(cdt, 1e-3), 40), 4000))  # ~6 s of CPU work
             cval, cdt = cpu_port(args.workload, cn, csteps, threads)
-            csteps = int(min(max(csteps * 12.0 / max(cdt, 1e-3), 40), 4000))  # ~12 s of CPU work
-            cval, cdt = cpu_port(args.workload, cn, csteps, threads)
-            line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{cn} instances x {csteps} steps ({cdt:.1f} s), C restatement of the "
-                                              "reference (oracle/), OpenMP over instances",
-                                    "reference_python_loop": "1.6e3 env-steps/s on one core measured in the build container "
-                                                             "(oracle/bench_reference_python.py -> profiles/r1/"
-                                                             "reference_python_cpu.json); pure Python, cannot travel to "
-                                                             "the GPU box"}
+            port = {"value": cval, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                    "sample": f"{cn} instances x {csteps} steps ({cdt:.1f} s), C restatement of the reference (oracle/), "
+                              "OpenMP over instances"}
+            if ref is not None:
+                line["cpu_baseline"] = dict(ref, port=port, reference_python=ref)
+            else:
+                line["cpu_baseline"] = dict(port, reference_python=None,
+                                            note="no reference tree (oracle/_ref not staged): C port only")
     if dist_on:
         line["exchange"] = exchange_times(dev)
     if rank == 0:

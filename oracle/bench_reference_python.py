@@ -111,12 +111,48 @@ def per_env(seconds: float):
     return out
 
 
+# bench.py workload -> adapter that reproduces the bench's action distribution with the reference's own loop body
+WORKER_ADAPTER = {"uav_pos": "uav_pos", "uav_att": "uav_att_rand", "cartpole": "cartpole", "ugvo": "ugvo", "soi": "soi",
+                  "fas": "fas_ppo2", "fas_discrete": "fas_discrete", "ballbalancer": "ballbalancer", "twolink": "twolink",
+                  "ugv": "ugv_forward", "uavr_hover": "uavr_hover"}
+
+
+def worker(workload: str, seconds: float, seed: int) -> dict:
+    """One process = one host core: the reference's own step loop (e.g. PPO2-4-UavFntsmcParamPos/train.py:290-297:
+    get_param_from_actor + generate_action_4_uav + step_update) with uniform random actions and reset(True) on terminal,
+    200 warm-up steps, then `seconds` of stepping.  Prints one JSON line."""
+    ad = A.REGISTRY[WORKER_ADAPTER[workload]][0]()
+    rng = np.random.default_rng(seed)
+    np.random.seed(seed)
+    with R.quiet():
+        env = ad.make()
+        ad.reset(env)
+        act = lambda k: (rng.uniform(ad.action_lo, ad.action_hi) if ad.action_lo is not None
+                         else ad.sample_action(rng, k, 0, env))
+        for t in range(200 if workload != "ugvo" else 20):
+            if ad.step(env, act(t), ad.sample_dis(rng, t, 0, env) if ad.D else None)[3]:
+                ad.reset(env)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            done = ad.step(env, act(n), ad.sample_dis(rng, n, 0, env) if ad.D else None)[3]
+            n += 1
+            if done:
+                ad.reset(env)
+        dt = time.perf_counter() - t0
+    return {"steps": n, "seconds": dt, "reference_tree": R.REF, "cites": ad.cites}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--epochs", type=int, default=5)
     ap.add_argument("--seconds", type=float, default=2.0)
+    ap.add_argument("--worker", default=None, help="bench.py workload name: run one timed loop and print JSON")
+    ap.add_argument("--seed", type=int, default=1)
     args = ap.parse_args()
     torch.set_num_threads(1)
+    if args.worker:
+        print(json.dumps(worker(args.worker, args.seconds, args.seed)))
+        return
     res = {"python": sys.version.split()[0], "numpy": np.__version__, "torch": torch.__version__,
            "cores_used": 1, "host_cores": os.cpu_count()}
     res["config1"] = config1(args.epochs)

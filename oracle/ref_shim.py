@@ -25,7 +25,11 @@ import os
 import sys
 import types
 
-REF = os.environ.get("RLP_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+# The live source tree in the build container; on the GPU box (no /root/reference) the byte-compiled staging of the same
+# files made by oracle/stage_reference.py (sourceless .pyb bytecode modules under oracle/_ref/, git-ignored).
+REF = os.environ.get("RLP_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/environment")
+                                          else os.path.join(HERE, "_ref"))
 _CLASH = ("uav", "FNTSMC", "collector", "ref_cmd", "uav_att_ctrl", "uav_pos_ctrl", "uav_att_ctrl_RL",
           "uav_pos_ctrl_RL", "UavHover", "UavHoverOuterLoop", "UavInnerLoop", "UavTrackingOuterLoop", "Color")
 _installed = False
@@ -58,6 +62,13 @@ def install() -> None:
             m.pyplot = plt
             sys.modules["matplotlib"] = m
             sys.modules["matplotlib.pyplot"] = plt
+    if os.path.exists(os.path.join(REF, "STAGED")):
+        # byte-compiled staging (oracle/stage_reference.py): modules are <name>.pyb files; teach the path finder about them
+        import importlib.machinery as M
+        hook = M.FileFinder.path_hook((M.SourcelessFileLoader, [".pyb"]), (M.SourceFileLoader, M.SOURCE_SUFFIXES),
+                                      (M.ExtensionFileLoader, M.EXTENSION_SUFFIXES))
+        sys.path_hooks.insert(0, hook)
+        sys.path_importer_cache.clear()
     if REF not in sys.path:
         sys.path.insert(0, REF)
     _installed = True
@@ -92,9 +103,15 @@ def load(modname: str):
 def load_file(path: str, name: str):
     """Import a demo-copy env file (e.g. demonstration/PPO2/.../cartpole_angleonly.py) by path."""
     install()
+    import importlib.machinery
     import importlib.util
     full = os.path.join(REF, path)
-    spec = importlib.util.spec_from_file_location(name, full)
+    staged = full[:-3] + ".pyb"
+    if not os.path.exists(full) and os.path.exists(staged):            # staged bytecode (oracle/_ref)
+        loader = importlib.machinery.SourcelessFileLoader(name, staged)
+        spec = importlib.util.spec_from_loader(name, loader, origin=staged)
+    else:
+        spec = importlib.util.spec_from_file_location(name, full)
     mod = importlib.util.module_from_spec(spec)
     with quiet():
         spec.loader.exec_module(mod)

@@ -189,3 +189,44 @@ def reference_nets(state_dim: int, action_dim: int, device, init_std: float = 0.
             return self.fc3(torch.tanh(self.fc2(torch.tanh(self.fc1(s)))))
 
     return Actor().to(device), Critic().to(device)
+
+
+def dppo2_nets(state_dim: int, action_dim: int, a_min, a_max, device, hidden: int = 256):
+    """Actor / critic with the shapes and heads of the DPPO2 demo nets (demonstration/DPPO2/
+    DPPO2-4-UGVForwardObstacleAvoidance/train.py:26-107): state-256-256-action with mean = tanh(mean_layer) * gain + off
+    (gain = a_max - off, off = (a_min + a_max) / 2, per-dimension init_std = range / 6, :128) and state-256-256-1, tanh
+    hidden layers, orthogonal init (gain 0.01 on the mean layer).  ``actor.out_act = "tanh_range"`` tells VecPPO2 which
+    head K-POLICY has to apply."""
+    a_min_t = torch.as_tensor(a_min, dtype=torch.float32, device=device)
+    a_max_t = torch.as_tensor(a_max, dtype=torch.float32, device=device)
+
+    class Actor(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2 = torch.nn.Linear(state_dim, hidden), torch.nn.Linear(hidden, hidden)
+            self.mean_layer = torch.nn.Linear(hidden, action_dim)
+            self.off = (a_min_t + a_max_t) / 2.0
+            self.gain = a_max_t - self.off
+            self.std = ((a_max_t - a_min_t) / 2 / 3).cpu().numpy()
+            self.out_act = "tanh_range"
+            for l, g in ((self.fc1, 1.0), (self.fc2, 1.0), (self.mean_layer, 0.01)):
+                torch.nn.init.orthogonal_(l.weight, gain=g)
+                torch.nn.init.constant_(l.bias, 0)
+
+        def forward(self, s):
+            s = torch.tanh(self.fc2(torch.tanh(self.fc1(s))))
+            return torch.tanh(self.mean_layer(s)) * self.gain + self.off
+
+    class Critic(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2, self.fc3 = (torch.nn.Linear(state_dim, hidden), torch.nn.Linear(hidden, hidden),
+                                            torch.nn.Linear(hidden, 1))
+            for l in (self.fc1, self.fc2, self.fc3):
+                torch.nn.init.orthogonal_(l.weight, gain=1.0)
+                torch.nn.init.constant_(l.bias, 0)
+
+        def forward(self, s):
+            return self.fc3(torch.tanh(self.fc2(torch.tanh(self.fc1(s)))))
+
+    return Actor().to(device), Critic().to(device)
