@@ -370,10 +370,13 @@ B200_API int b200env_observe(int env_id, int dtype, int64_t n_envs,
  *   adv = gae;  v_target = adv + vs
  * acc_mode 0: float32 sequential, bit-identical to the reference loop under numpy >= 2; 1: float64 carry (numpy 1.x).
  * stats (device double[3], may be NULL) is INCREMENTED by (sum adv, sum adv^2, T * N): zero it first; all-reduce it
- * over ranks for a global advantage normalisation. */
+ * over ranks for a global advantage normalisation.  scratch (device, 8-byte aligned, b200_gae_scratch_bytes(N) bytes,
+ * may be NULL): with it the sums are reduced in a fixed order -- the same bits on every run; without it the per-block
+ * partial sums are added atomically (order-dependent in the last bits). */
+B200_API size_t b200_gae_scratch_bytes(int64_t N);
 B200_API int b200_gae(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next, const float *done,
                       const float *success, double gamma, double lmd, int acc_mode, float *adv, float *v_target,
-                      double *stats, void *cuda_stream);
+                      double *stats, void *scratch, size_t scratch_bytes, void *cuda_stream);
 
 /* `spec->steps` control periods with pre-computed actions in one call: the collection loop of the train scripts
  * (`while buffer_index < batch_size: step_update; buffer.append`, PPO2-4-CartPoleAngleOnly/train.py:186-216) when the
@@ -392,10 +395,11 @@ B200_API int b200env_rollout(int env_id, int dtype, int64_t n_envs, const void *
  * PPO2-4-UavFntsmcParamPos/train.py:299-302).  25 instead of 28 bytes of HBM traffic per element. */
 B200_API int b200_gae_flags(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next,
                             const uint8_t *done, const int32_t *flag, int32_t timeout_flag, double gamma, double lmd,
-                            int acc_mode, float *adv, float *v_target, double *stats, void *cuda_stream);
+                            int acc_mode, float *adv, float *v_target, double *stats, void *scratch,
+                            size_t scratch_bytes, void *cuda_stream);
 
 /* adv <- (adv - mean) / (std + eps) with the unbiased std (torch.Tensor.std) derived from stats = (sum, sum of
- * squares, count): Proximal_Policy_Optimization2.py:99-100 (eps = 1e-5). */
+ * squares, count): Proximal_Policy_Optimization2.py:99-100 (eps = 1e-5); a true float32 division per element. */
 B200_API int b200_adv_normalize(int64_t count, float *adv, const double *stats, double eps, void *cuda_stream);
 
 /* Monte-Carlo return scan of PPO / DPPO (v1): algorithm/policy_base/Proximal_Policy_Optimization.py:113-119,

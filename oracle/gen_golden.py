@@ -41,8 +41,10 @@ from oracle import ref_adapters as A  # noqa: E402
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
-def record(adapter: "A.Adapter", lanes: int, steps: int, seed: int) -> dict:
-    rng = np.random.default_rng(seed)
+def record(adapter: "A.Adapter", lanes: int, steps: int, seed: int, lane_offset: int = 0) -> dict:
+    """lane_offset > 0: record lanes lane_offset .. lane_offset + lanes - 1 of a wider run with a generator of their own
+    (oracle/live_record.py records one lane per process); 0 keeps the committed fixtures reproducible bit for bit."""
+    rng = np.random.default_rng([seed, lane_offset]) if lane_offset else np.random.default_rng(seed)
     F, S, Adim, D = adapter.F, adapter.S, adapter.A, adapter.D
     out = {
         "state0": np.zeros((lanes, F)), "time0": np.zeros(lanes),
@@ -57,7 +59,8 @@ def record(adapter: "A.Adapter", lanes: int, steps: int, seed: int) -> dict:
     if D:
         out["dis"] = np.zeros((steps, lanes, D))
     for l in range(lanes):
-        np.random.seed(seed * 1000 + l)  # the reference's resets use the global numpy RNG
+        gl = l + lane_offset
+        np.random.seed(seed * 1000 + gl)  # the reference's resets use the global numpy RNG
         with R.quiet():
             env = adapter.make()
             twin = adapter.make()
@@ -68,8 +71,8 @@ def record(adapter: "A.Adapter", lanes: int, steps: int, seed: int) -> dict:
             adapter.perturb(twin, 0)
         out["state0"][l], out["time0"][l] = adapter.internal(env)
         for t in range(steps):
-            a = adapter.sample_action(rng, t, l, env)
-            d = adapter.sample_dis(rng, t, l, env) if D else None
+            a = adapter.sample_action(rng, t, gl, env)
+            d = adapter.sample_dis(rng, t, gl, env) if D else None
             with R.quiet():
                 o, o2, r, done, flag = adapter.step(env, a, d)
                 _, t2, _, tdone, _ = adapter.step(twin, a, d)

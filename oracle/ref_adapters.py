@@ -276,7 +276,8 @@ class UavAttRandA(UavAttA):
 
 REGISTRY.update({
     "uav_pos": (UavPosA, 6, 1000, 21),
-    # wide fixtures (SURVEY 8c-i asks for many seeds): one full episode each for 24 / 32 independent seeds
+    # wide fixtures: one full episode each for 24 / 32 independent seeds.  The 64 seeds x 1000 steps of SURVEY 8c-i are
+    # not committed (28 MB per env): tests/test_live_reference_gpu.py records them from the staged reference at test time.
     "uav_pos_wide": (UavPosDisA, 24, 520, 41),
     "uav_pos_rp0": (UavPosRandomPos0A, 4, 600, 28),
     "uav_pos_dis": (UavPosDisA, 3, 1000, 22),

@@ -158,9 +158,11 @@ def load() -> C.CDLL:
     lib.b200env_observe.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), vp]
     f64 = C.c_double
     lib.b200_gae.restype = i32
-    lib.b200_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, f64, f64, i32, vp, vp, vp, vp]
+    lib.b200_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, f64, f64, i32, vp, vp, vp, vp, sz, vp]
     lib.b200_gae_flags.restype = i32
-    lib.b200_gae_flags.argtypes = [i64, i64, vp, vp, vp, vp, vp, i32, f64, f64, i32, vp, vp, vp, vp]
+    lib.b200_gae_flags.argtypes = [i64, i64, vp, vp, vp, vp, vp, i32, f64, f64, i32, vp, vp, vp, vp, sz, vp]
+    lib.b200_gae_scratch_bytes.restype = sz
+    lib.b200_gae_scratch_bytes.argtypes = [i64]
     lib.b200_adv_normalize.restype = i32
     lib.b200_adv_normalize.argtypes = [i64, vp, vp, f64, vp]
     lib.b200_mc_returns.restype = i32

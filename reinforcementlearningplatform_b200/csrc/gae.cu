@@ -12,8 +12,11 @@
 // Exactness: with acc_mode 0 every operation is a separately rounded float32 multiply/add (__fmul_rn/__fadd_rn, no
 // FMA contraction) in the reference's evaluation order, i.e. bit-identical to the loop under numpy >= 2 (NEP 50:
 // python floats are weak, the scan runs in float32).  acc_mode 1 carries gae in float64 (the numpy 1.x behaviour).
-// The per-launch (sum adv, sum adv^2, count) are accumulated in float64 and added atomically to stats[3], ready for a
-// 3-double all-reduce when the rollout is sharded over GPUs (global advantage normalisation).
+// The per-launch (sum adv, sum adv^2, count) are accumulated in float64: every block writes its two partial sums to a
+// caller-owned scratch array and a one-block kernel adds them up in a fixed order (strided per-thread sums, then a fixed
+// tree) before incrementing stats[3] -- the same bits on every run, like K-NORM's statistics; ready for a 3-double
+// all-reduce when the rollout is sharded over GPUs (global advantage normalisation).  Without scratch the partial sums
+// fall back to atomicAdd (order-dependent in the last bits).
 #include "common.cuh"
 
 namespace {
@@ -51,7 +54,7 @@ template <bool F64_ACC, class Masks>
 __global__ void __launch_bounds__(GAE_BLOCK)
 gae_kernel(int64_t T, int64_t N, const float *__restrict__ r, const float *__restrict__ vs,
            const float *__restrict__ vsn, const Masks mk, float g32,
-           float gl32, double gl64, float *__restrict__ adv, float *__restrict__ vt, double *stats) {
+           float gl32, double gl64, float *__restrict__ adv, float *__restrict__ vt, double *stats, double *partial) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
     if (n < N) {
@@ -118,10 +121,42 @@ gae_kernel(int64_t T, int64_t N, const float *__restrict__ r, const float *__res
             double a = 0, b = 0;
 #pragma unroll
             for (int k = 0; k < GAE_BLOCK / 32; ++k) { a += sh1[k]; b += sh2[k]; }
-            atomicAdd(stats + 0, a);
-            atomicAdd(stats + 1, b);
-            if (blockIdx.x == 0) atomicAdd(stats + 2, (double)T * (double)N);
+            if (partial) {                      // deterministic path: block b owns partial[2 b], partial[2 b + 1]
+                partial[2 * (int64_t)blockIdx.x] = a;
+                partial[2 * (int64_t)blockIdx.x + 1] = b;
+            } else {
+                atomicAdd(stats + 0, a);
+                atomicAdd(stats + 1, b);
+                if (blockIdx.x == 0) atomicAdd(stats + 2, (double)T * (double)N);
+            }
         }
+    }
+}
+
+// fixed-order sum of the per-block partials: thread k adds partials k, k + 256, ... sequentially, then the 256 thread sums
+// are combined by a fixed shared-memory tree; one thread increments stats
+__global__ void __launch_bounds__(256) gae_stats_reduce_kernel(int64_t blocks, const double *__restrict__ partial,
+                                                               double count, double *stats) {
+    __shared__ double sh[2][256];
+    double a = 0.0, b = 0.0;
+    for (int64_t k = threadIdx.x; k < blocks; k += 256) {
+        a += partial[2 * k];
+        b += partial[2 * k + 1];
+    }
+    sh[0][threadIdx.x] = a;
+    sh[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        stats[0] += sh[0][0];
+        stats[1] += sh[1][0];
+        stats[2] += count;
     }
 }
 
@@ -131,9 +166,10 @@ adv_normalize_kernel(int64_t count, float *__restrict__ adv, const double *__res
     const double cnt = stats[2];
     const double mean = stats[0] / cnt;
     const double var = fmax((stats[1] - cnt * mean * mean) / (cnt - 1.0), 0.0);
-    const float m = (float)mean, inv = (float)(1.0 / (sqrt(var) + eps));
+    // (adv - adv.mean()) / (adv.std() + 1e-5) on float32 tensors: a true float32 division, like the reference
+    const float m = (float)mean, den = __fadd_rn((float)sqrt(var), (float)eps);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
-        adv[i] = (adv[i] - m) * inv;
+        adv[i] = __fdiv_rn(__fsub_rn(adv[i], m), den);
 }
 
 // PPO / DPPO (v1) Monte-Carlo return scan, SURVEY 8(f)-4: algorithm/policy_base/Proximal_Policy_Optimization.py:113-119,
@@ -179,37 +215,49 @@ mc_returns_kernel(int64_t T, int64_t N, const TR *__restrict__ r, const uint8_t 
 
 } // namespace
 
-extern "C" B200_API int b200_gae(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next,
-                                 const float *done, const float *success, double gamma, double lmd, int acc_mode,
-                                 float *adv, float *v_target, double *stats, void *cuda_stream) {
-    if (T <= 0 || N <= 0) return B200ENV_ESIZE;
-    if (!r || !vs || !vs_next || !done || !success || !adv || !v_target) return B200ENV_ENULL;
-    cudaStream_t s = (cudaStream_t)cuda_stream;
+namespace {
+template <class Masks>
+int gae_launch(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next, const Masks &mk, double gamma,
+               double lmd, int acc_mode, float *adv, float *v_target, double *stats, void *scratch, size_t scratch_bytes,
+               cudaStream_t s) {
     const unsigned grid = (unsigned)((N + GAE_BLOCK - 1) / GAE_BLOCK);
     const float g32 = (float)gamma, gl32 = (float)(gamma * lmd);
-    const FloatMasks mk{done, success};
+    double *partial = nullptr;
+    if (stats && scratch) {
+        if (scratch_bytes < (size_t)grid * 2 * sizeof(double) || ((uintptr_t)scratch & 7)) return B200ENV_EPARAMS;
+        partial = static_cast<double *>(scratch);
+    }
     if (acc_mode == 0)
-        gae_kernel<false, FloatMasks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats);
+        gae_kernel<false, Masks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats, partial);
     else
-        gae_kernel<true, FloatMasks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats);
+        gae_kernel<true, Masks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats, partial);
+    if (partial) gae_stats_reduce_kernel<<<1, 256, 0, s>>>((int64_t)grid, partial, (double)T * (double)N, stats);
     return b200_check_launch();
+}
+} // namespace
+
+extern "C" B200_API size_t b200_gae_scratch_bytes(int64_t N) {
+    return N <= 0 ? 0 : (size_t)((N + GAE_BLOCK - 1) / GAE_BLOCK) * 2 * sizeof(double);
+}
+
+extern "C" B200_API int b200_gae(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next,
+                                 const float *done, const float *success, double gamma, double lmd, int acc_mode,
+                                 float *adv, float *v_target, double *stats, void *scratch, size_t scratch_bytes,
+                                 void *cuda_stream) {
+    if (T <= 0 || N <= 0) return B200ENV_ESIZE;
+    if (!r || !vs || !vs_next || !done || !success || !adv || !v_target) return B200ENV_ENULL;
+    return gae_launch(T, N, r, vs, vs_next, FloatMasks{done, success}, gamma, lmd, acc_mode, adv, v_target, stats, scratch,
+                      scratch_bytes, (cudaStream_t)cuda_stream);
 }
 
 extern "C" B200_API int b200_gae_flags(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next,
                                        const uint8_t *done, const int32_t *flag, int32_t timeout_flag, double gamma,
-                                       double lmd, int acc_mode, float *adv, float *v_target, double *stats,
-                                       void *cuda_stream) {
+                                       double lmd, int acc_mode, float *adv, float *v_target, double *stats, void *scratch,
+                                       size_t scratch_bytes, void *cuda_stream) {
     if (T <= 0 || N <= 0) return B200ENV_ESIZE;
     if (!r || !vs || !vs_next || !done || !flag || !adv || !v_target) return B200ENV_ENULL;
-    cudaStream_t s = (cudaStream_t)cuda_stream;
-    const unsigned grid = (unsigned)((N + GAE_BLOCK - 1) / GAE_BLOCK);
-    const float g32 = (float)gamma, gl32 = (float)(gamma * lmd);
-    const FlagMasks mk{done, flag, timeout_flag};
-    if (acc_mode == 0)
-        gae_kernel<false, FlagMasks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats);
-    else
-        gae_kernel<true, FlagMasks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats);
-    return b200_check_launch();
+    return gae_launch(T, N, r, vs, vs_next, FlagMasks{done, flag, timeout_flag}, gamma, lmd, acc_mode, adv, v_target, stats,
+                      scratch, scratch_bytes, (cudaStream_t)cuda_stream);
 }
 
 extern "C" B200_API int b200_adv_normalize(int64_t count, float *adv, const double *stats, double eps,

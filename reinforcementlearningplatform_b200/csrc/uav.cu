@@ -121,7 +121,11 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ UavDeri
         k1[k] = a[k] > (T)0 ? (T)10 * a[k] : ld<T>(io.state, n, A_K1 + k, i);
         // a / 10 as q = a r, q + (a - 10 q) r with r = RN(1 / 10): the correctly rounded quotient (Markstein; checked
         // against 300 k IEEE quotients incl. float32-valued a), without the IEEE division's slow-path branch
+#ifdef B200_STRICT_DIV
+        k2[k] = a[k + 3] > (T)0 ? a[k + 3] / (T)10 : ld<T>(io.state, n, A_K2 + k, i);
+#else
         k2[k] = a[k + 3] > (T)0 ? Divisor<T>((T)10, (T)0.1).div(a[k + 3]) : ld<T>(io.state, n, A_K2 + k, i);
+#endif
         gam[k] = a[6] > (T)0 ? a[6] : ld<T>(io.state, n, A_GAM + k, i);
         lmd[k] = a[7] > (T)0 ? a[7] : ld<T>(io.state, n, A_LMD + k, i);
         alpha[k] = (T)p.att_alpha[k];
@@ -361,8 +365,12 @@ __device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c,
     theta_d = clampc<T>(theta_d, -lim, lim);
     // ---- generate_action_4_uav, uav_pos_ctrl.py:470-481: finite-difference reference rates, clipped, integrated back
     T rho_d[3] = {phi_d, theta_d, ref[3]};
+#ifdef B200_STRICT_DIV
+    T drho_d[3] = {(phi_d - aref0) / c.dt, (theta_d - aref1) / c.dt, dref[3]};
+#else
     const Divisor<T> by_dt(c.dt);
     T drho_d[3] = {by_dt.div(phi_d - aref0), by_dt.div(theta_d - aref1), dref[3]};
+#endif
     const T rl = (T)p.dot_att_ref_limit;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {

@@ -4,6 +4,30 @@
 #pragma once
 #include "common.cuh"
 
+// ------------------------------------------------------------------------------------------------------------------
+// B200_STRICT: the reference's operation order and library calls, one switch per shortcut of the shipped kernels, so that
+// the free-running drift of the shipped build can be bounded and decomposed (tests/test_drift_gpu.py, `make strict`):
+//   B200_STRICT_POW   |e|^alpha, |e|^(alpha-1), |s|^beta by three pow() calls      (shipped: one log + exp(a log x))
+//   B200_STRICT_TAN   tan(theta) by tan()                                           (shipped: sin / cos)
+//   B200_STRICT_DIV   IEEE divisions by J, m, cos(theta), cos^2(theta), 6, dt, 10   (shipped: reciprocal multiplies,
+//                                                                                    Markstein-corrected quotients)
+//   B200_UAV_LAPACK_INV  control = -inv(f1 h) (u1 + u2) by LU with partial pivoting (shipped: closed-form diag(J) f1^-1)
+//   B200_LIBDEVICE_MATH  libdevice sincos / tanh / log / exp / asin                (shipped: fastmath64.cuh)
+//   -fmad=false          no FMA contraction                                         (shipped: contraction on)
+#ifdef B200_STRICT
+#define B200_STRICT_POW
+#define B200_STRICT_TAN
+#define B200_STRICT_DIV
+#ifndef B200_UAV_LAPACK_INV
+#define B200_UAV_LAPACK_INV
+#endif
+#endif
+#ifdef B200_STRICT_DIV
+#define UAV_DIV(a, b, rb) ((a) / (b))
+#else
+#define UAV_DIV(a, b, rb) ((a) * (rb))
+#endif
+
 namespace uavk {
 
 typedef b200_uav_params P;
@@ -22,7 +46,11 @@ struct Trig {
             spsi = (T)0; cpsi = (T)1;
         }
         rcth = Mth<T>::rcp(cth);
+#ifdef B200_STRICT_TAN
+        tth = Mth<T>::tan(th);
+#else
         tth = sth * rcth;
+#endif
     }
 };
 
@@ -56,17 +84,17 @@ __device__ __forceinline__ void uav_ode(const Consts<T> &c, const T *x, const Tr
                                         const T *dis, T *d) {
     const T p = x[9], q = x[10], r = x[11];
     // divisions by the constants J, m are multiplications by their reciprocals (<= 1 ulp from the reference's x / J)
-    d[9] = (-c.kr * p - q * r * c.J21 + tq[0]) * c.rJ0;
-    d[10] = (-c.kr * q - p * r * c.J02 + tq[1]) * c.rJ1;
-    d[11] = (-c.kr * r - p * q * c.J10 + tq[2]) * c.rJ2;
+    d[9] = UAV_DIV(-c.kr * p - q * r * c.J21 + tq[0], c.J0, c.rJ0);
+    d[10] = UAV_DIV(-c.kr * q - p * r * c.J02 + tq[1], c.J1, c.rJ1);
+    d[11] = UAV_DIV(-c.kr * r - p * q * c.J10 + tq[2], c.J2, c.rJ2);
     d[6] = p + (t.tth * t.sphi) * q + (t.tth * t.cphi) * r;
     d[7] = t.cphi * q - t.sphi * r;
-    d[8] = (t.sphi * t.rcth) * q + (t.cphi * t.rcth) * r;
+    d[8] = UAV_DIV(t.sphi, t.cth, t.rcth) * q + UAV_DIV(t.cphi, t.cth, t.rcth) * r;
     if (!ATT_ONLY) {
         d[0] = x[3]; d[1] = x[4]; d[2] = x[5];
-        d[3] = (throttle * (t.cpsi * t.sth * t.cphi + t.spsi * t.sphi) - c.kt * x[3] + dis[0]) * c.rm;
-        d[4] = (throttle * (t.spsi * t.sth * t.cphi - t.cpsi * t.sphi) - c.kt * x[4] + dis[1]) * c.rm;
-        d[5] = -c.g + (throttle * t.cphi * t.cth - c.kt * x[5] + dis[2]) * c.rm;
+        d[3] = UAV_DIV(throttle * (t.cpsi * t.sth * t.cphi + t.spsi * t.sphi) - c.kt * x[3] + dis[0], c.m, c.rm);
+        d[4] = UAV_DIV(throttle * (t.spsi * t.sth * t.cphi - t.cpsi * t.sphi) - c.kt * x[4] + dis[1], c.m, c.rm);
+        d[5] = -c.g + UAV_DIV(throttle * t.cphi * t.cth - c.kt * x[5] + dis[2], c.m, c.rm);
     }
 }
 
@@ -97,7 +125,7 @@ __device__ __forceinline__ void uav_rk44(const Consts<T> &c, T *x, Trig<T> t, T 
         if (s < 3) t.eval(xs[6], xs[7], xs[8], !ATT_ONLY);
     }
 #pragma unroll
-    for (int i = LO; i < 12; ++i) x[i] = x[i] + acc[i] * (T)(1.0 / 6.0);
+    for (int i = LO; i < 12; ++i) x[i] = x[i] + UAV_DIV(acc[i], (T)6, (T)(1.0 / 6.0));
     if (x[8] > (T)M_PI) x[8] -= (T)(2 * M_PI);
     if (x[8] < (T)-M_PI) x[8] += (T)(2 * M_PI);
 }
@@ -114,6 +142,15 @@ __device__ SMC_INLINE void smc_axis(T e, T de, T k1, T gamma, T alpha, T beta, T
     // |e|^(alpha-1) = exp((alpha-1) log|e|) and |e|^alpha = |e|^(alpha-1) * |e|: one log, one exp and one product for the
     // two powers of FNTSMC.py:61-63 (numpy evaluates two pow()).  e = 0: 0^alpha = 0 (alpha > 0) while 0^(alpha-1) = inf.
     const T ae = Mth<T>::abs(e);
+#ifdef B200_STRICT_POW
+    // FNTSMC.py:61-66 / 128-134 literally: np.fabs(e) ** alpha, np.fabs(e) ** (alpha - 1), np.fabs(s) ** beta
+    const T s_ = de + k1 * e + gamma * Mth<T>::pow(ae, alpha) * Mth<T>::tanh((T)5 * e);
+    dot_s1 = Mth<T>::pow(Mth<T>::abs(s_), beta) * Mth<T>::tanh((T)5 * s_);
+    integ += dot_s1 * dt;
+    s_out = s_ + lmd * integ;
+    pa1_de = gamma * alpha * Mth<T>::pow(ae, alpha - (T)1) * de;
+    return;
+#endif
     const T L = Mth<T>::log(ae);
     const T pa1 = pow_from_log<T>(L, alpha - (T)1);
 #ifdef B200_SMC_TWO_EXP
@@ -164,21 +201,23 @@ __device__ __forceinline__ void att_control(const Consts<T> &c, const T *x, cons
                                             const T *ref, const T *dref, T *torque, T *d1) {
     const T p = x[9], q = x[10], r = x[11];
     const T f01 = t.sphi * t.tth, f02 = t.cphi * t.tth, f11 = t.cphi, f12 = -t.sphi;
-    const T f21 = t.sphi * t.rcth, f22 = t.cphi * t.rcth;
+    const T f21 = UAV_DIV(t.sphi, t.cth, t.rcth), f22 = UAV_DIV(t.cphi, t.cth, t.rcth);
     d1[0] = p + f01 * q + f02 * r;
     d1[1] = f11 * q + f12 * r;
     d1[2] = f21 * q + f22 * r;
     // F() (uav.py:340-354) . rho2
     const T rc2 = t.rcth * t.rcth;
-    const T F01 = d1[0] * t.tth * t.cphi + d1[1] * t.sphi * rc2;
-    const T F02 = -d1[0] * t.tth * t.sphi + d1[1] * t.cphi * rc2;
+    const T c2 = t.cth * t.cth; // np.cos(theta) ** 2
+    (void)c2;
+    const T F01 = d1[0] * t.tth * t.cphi + UAV_DIV(d1[1] * t.sphi, c2, rc2);
+    const T F02 = -d1[0] * t.tth * t.sphi + UAV_DIV(d1[1] * t.cphi, c2, rc2);
     const T F11 = -d1[0] * t.sphi, F12 = -d1[0] * t.cphi;
-    const T F21 = (d1[0] * t.cphi * t.cth + d1[1] * t.sphi * t.sth) * rc2;
-    const T F22 = (-d1[0] * t.sphi * t.cth + d1[1] * t.cphi * t.sth) * rc2;
+    const T F21 = UAV_DIV(d1[0] * t.cphi * t.cth + d1[1] * t.sphi * t.sth, c2, rc2);
+    const T F22 = UAV_DIV(-d1[0] * t.sphi * t.cth + d1[1] * t.cphi * t.sth, c2, rc2);
     // f2() (uav.py:302-313)
-    const T g0 = (c.kr * p + q * r * (c.J1 - c.J2)) * c.rJ0;
-    const T g1 = (c.kr * q + p * r * (c.J2 - c.J0)) * c.rJ1;
-    const T g2 = (c.kr * r + p * q * (c.J0 - c.J1)) * c.rJ2;
+    const T g0 = UAV_DIV(c.kr * p + q * r * (c.J1 - c.J2), c.J0, c.rJ0);
+    const T g1 = UAV_DIV(c.kr * q + p * r * (c.J2 - c.J0), c.J1, c.rJ1);
+    const T g2 = UAV_DIV(c.kr * r + p * q * (c.J0 - c.J1), c.J2, c.rJ2);
     T sec[3];
     sec[0] = (F01 * q + F02 * r) + (g0 + f01 * g1 + f02 * g2);
     sec[1] = (F11 * q + F12 * r) + (f11 * g1 + f12 * g2);

@@ -18,6 +18,11 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
+def _scratch(N: int, device) -> torch.Tensor:
+    """Per-block partial sums of the advantage statistics (fixed-order reduction: bit-reproducible runs)."""
+    return torch.empty(max(1, int(_lib.load().b200_gae_scratch_bytes(N)) // 8), dtype=torch.float64, device=device)
+
+
 def gae(r, vs, vs_next, done, success, gamma: float, lmd: float, acc_mode: int = 0, stats: torch.Tensor = None):
     """adv, v_target, stats = gae(...).  All inputs: CUDA float32 ``[T, N]`` contiguous (done / success as 0.0 / 1.0).
     acc_mode 0 = float32 sequential (bit-identical to the reference loop under numpy >= 2), 1 = float64 carry."""
@@ -33,8 +38,9 @@ def gae(r, vs, vs_next, done, success, gamma: float, lmd: float, acc_mode: int =
         stats = torch.zeros(3, dtype=torch.float64, device=r.device)
     with torch.cuda.device(r.device):
         stream = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
+        scr = _scratch(N, r.device)
         _lib.check(lib.b200_gae(T, N, *[_p(t) for t in ts], float(gamma), float(lmd), int(acc_mode), _p(adv), _p(vt),
-                                _p(stats), stream), "b200_gae")
+                                _p(stats), _p(scr), scr.numel() * 8, stream), "b200_gae")
     return adv, vt, stats
 
 
@@ -56,9 +62,10 @@ def gae_flags(r, vs, vs_next, done_u8, flag_i32, timeout_flag: int, gamma: float
         stats = torch.zeros(3, dtype=torch.float64, device=r.device)
     with torch.cuda.device(r.device):
         stream = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
+        scr = _scratch(N, r.device)
         _lib.check(lib.b200_gae_flags(T, N, _p(r), _p(vs), _p(vs_next), _p(done_u8), _p(flag_i32), int(timeout_flag),
-                                      float(gamma), float(lmd), int(acc_mode), _p(adv), _p(vt), _p(stats), stream),
-                   "b200_gae_flags")
+                                      float(gamma), float(lmd), int(acc_mode), _p(adv), _p(vt), _p(stats), _p(scr),
+                                      scr.numel() * 8, stream), "b200_gae_flags")
     return adv, vt, stats
 
 

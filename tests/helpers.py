@@ -104,7 +104,8 @@ class EngineBackend:
     def step(self, actions, dis=None):
         t = self.torch
         e = self.env
-        e.step_update(t.from_numpy(np.ascontiguousarray(actions)), None if dis is None else t.from_numpy(np.ascontiguousarray(dis)))
+        e.step_update(t.from_numpy(np.ascontiguousarray(actions)), None if dis is None else t.from_numpy(np.ascontiguousarray(dis)),
+                      layout="envs_first")   # fixtures are [lanes, dim]; explicit because some have lanes == dim
         t.cuda.synchronize()
         f = lambda x: x.detach().cpu().numpy().astype(np.float64)
         return dict(obs=f(e.current_state), next_obs=f(e.next_state), reward=f(e.reward),
@@ -148,6 +149,8 @@ def replay(g, backend, resync=False, steps=None, name="", sens_k=None, floor=1e-
     first_bad = None
     run_sens = np.zeros(L)
     worst_ratio = 0.0
+    lane_state = np.zeros(L)   # worst mixed state error per lane (drift statistics over seeds, tests/test_drift_gpu.py)
+    live_steps, all_steps = 0, 0
     lane_err = lambda a, b: np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)), axis=1) if a.ndim == 2 else np.abs(a - b) / np.maximum(1.0, np.abs(b))
     for t in range(T):
         if resync and t > 0:
@@ -159,10 +162,14 @@ def replay(g, backend, resync=False, steps=None, name="", sens_k=None, floor=1e-
             run_sens = np.maximum(run_sens, g["twin_err"][t])
         tol = np.maximum(floor, sens_k * run_sens)
         live = (run_sens <= chaos_cut) | resync
+        live_steps += int(np.sum(live))
+        all_steps += L
         for k in ("obs", "next_obs", "reward", "state"):
             a, b = out[k], g[k][t]
             if k == "state" and nf:
                 a, b = a[:, :nf], b[:, :nf]
+            if k == "state":
+                lane_state = np.maximum(lane_state, lane_err(np.asarray(a, np.float64), np.asarray(b, np.float64)))
             if live.any():
                 worst[k] = max(worst[k], mixed_err(np.asarray(a)[live], np.asarray(b)[live]))
                 if k != "obs":
@@ -180,7 +187,7 @@ def replay(g, backend, resync=False, steps=None, name="", sens_k=None, floor=1e-
             if not resync:
                 backend.set_state(g["reset_state"][t][lanes], g["reset_time"][t][lanes], lanes)
     return dict(worst=worst, worst_ratio=worst_ratio, flag_mismatch=flag_mismatch, done_mismatch=done_mismatch,
-                first_bad=first_bad, steps=T)
+                first_bad=first_bad, steps=T, lane_state=lane_state, live_fraction=live_steps / max(1, all_steps))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -72,3 +72,31 @@ def test_engine_gae_vs_oracle_batched(T, N, oracle_lib):
         ref = (adv_o.astype(np.float64) - adv_o.astype(np.float64).mean()) / (adv_o.astype(np.float64).std(ddof=1) + 1e-5)
         G.normalize_advantage(adv, st)
         np.testing.assert_allclose(adv.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_advantage_statistics_are_bit_reproducible_and_normalisation_divides():
+    """K-GAE's (sum, sum of squares, count) come from a fixed-order reduction over per-block partial sums: two runs give
+    the same bits (the atomicAdd path of round 1 did not), and agree with a float64 numpy sum to rounding.  The
+    normalisation is a true float32 division by (std + eps), like `(adv - adv.mean()) / (adv.std() + 1e-5)`."""
+    import torch
+    from reinforcementlearningplatform_b200 import gae as G
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    T, N = 512, 40000
+    mk = lambda: torch.randn((T, N), generator=g, device="cuda", dtype=torch.float32)
+    r, vs, vsn = mk(), mk(), mk()
+    done = (torch.rand((T, N), generator=g, device="cuda") < 0.01).float()
+    succ = done * (torch.rand((T, N), generator=g, device="cuda") < 0.5).float()
+    runs = [G.gae(r, vs, vsn, done, succ, 0.99, 0.95) for _ in range(4)]
+    for adv, vt, st in runs[1:]:
+        assert torch.equal(st, runs[0][2]) and torch.equal(adv, runs[0][0])
+    adv, _, st = runs[0]
+    a64 = adv.double().cpu().numpy()
+    assert st[2].item() == T * N
+    assert abs(st[0].item() - a64.sum()) <= 1e-9 * np.abs(a64).sum()
+    assert abs(st[1].item() - (a64 ** 2).sum()) <= 1e-12 * (a64 ** 2).sum()
+    mean, std = a64.mean(), a64.std(ddof=1)
+    want = ((adv - np.float32(mean)) / np.float32(np.float32(std) + np.float32(1e-5))).clone()
+    G.normalize_advantage(adv, st.clone())
+    assert torch.equal(adv, want) or float((adv - want).abs().max()) <= 2.5e-7 * float(want.abs().max())

@@ -1,0 +1,47 @@
+"""SURVEY.md 8c-i at full width: 64 seeds x 1000 steps per environment, recorded from the reference AT TEST TIME (one
+process per lane; /root/reference in the build container, the byte-compiled staging oracle/_ref on the GPU box) and
+replayed through the CUDA engine -- one-step mode within 1e-12 with exact flags and time, free-running within the
+per-family tolerance with exact flags on every lane that is still reproducible by the reference itself."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from helpers import ENGINE_TOL, EngineBackend, replay  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+# fixture family (helpers.env_specs / ENGINE_TOL key) for each recorded adapter, and the share of (step, lane) samples that
+# must stay comparable in free-running mode (the rest are lanes past the chaos cut-off: their self-drift exceeds 1e-11)
+CASES = {"cartpole": ("cartpole", 0.5), "uav_att_rand": ("uav_att_rand", 0.99), "uav_pos_dis": ("uav_pos_dis", 0.9)}
+
+
+def _have_reference():
+    from oracle import ref_shim
+    return ref_shim.available()
+
+
+@pytest.mark.parametrize("adapter", sorted(CASES))
+def test_64_seeds_1000_steps_against_the_live_reference(adapter):
+    if not _have_reference():
+        pytest.skip("no reference tree (neither /root/reference nor the staging oracle/_ref): run build() where the reference is")
+    from oracle.live_record import record_parallel
+    family, live_min = CASES[adapter]
+    g = record_parallel(adapter, lanes=64, steps=1000, seed=77)
+    L = g["reward"].shape[1]
+    assert g["reward"].shape == (1000, 64) and int(g["done"].sum()) >= 64   # every lane finishes at least one episode
+    res = replay(g, EngineBackend(family, L), resync=True, name=family)
+    assert res["flag_mismatch"] == 0 and res["done_mismatch"] == 0 and res["worst"]["time"] == 0.0, res
+    for k, v in res["worst"].items():
+        assert v <= 1e-12, (adapter, k, v)
+    res = replay(g, EngineBackend(family, L), resync=False, name=family)
+    assert res["flag_mismatch"] == 0 and res["done_mismatch"] == 0 and res["worst"]["time"] == 0.0, res
+    assert res["live_fraction"] >= live_min, (adapter, res["live_fraction"])
+    assert res["worst_ratio"] <= 1.0, res
+    for k, v in res["worst"].items():
+        assert v <= ENGINE_TOL[family], (adapter, k, v)
+    print(f"{adapter}: 64 x 1000 live-reference lanes, one-step <= 1e-12, free-running worst state "
+          f"{res['worst']['state']:.1e} (median lane {np.median(res['lane_state']):.1e}), live {res['live_fraction']:.2f}")

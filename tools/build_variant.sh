@@ -8,6 +8,6 @@ src=reinforcementlearningplatform_b200/csrc
 mkdir -p tools/variants /tmp/var_$name
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
      --expt-relaxed-constexpr -diag-suppress 177 "$@" -c -o /tmp/var_$name/$file.o $src/$file.cu
-objs=$(ls $src/*.o | grep -v "/$file\.o\$")
+objs=$(ls $src/*.o | grep -v "\.strict\.o$" | grep -v "/$file\.o\$")
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tools/variants/libb200env_$name.so $objs /tmp/var_$name/$file.o -Xcompiler -fPIC -lcudart
 echo built tools/variants/libb200env_$name.so
