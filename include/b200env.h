@@ -485,6 +485,72 @@ B200_API int b200_policy_forward_packed(int64_t n, const b200_mlp *actor, const 
                                         int64_t env_index_offset, float *action, float *log_prob, float *mean,
                                         float *value, void *cuda_stream);
 
+/* ------------------------------------------------------------- PPO2 / DPPO2 update (K-LEARN) */
+
+/* One mini-batch of the update loop of Proximal_Policy_Optimization2.learn (algorithm/policy_base/
+ * Proximal_Policy_Optimization2.py:102-131; the DPPO2 worker copies Distributed_PPO2.py:77-104) taken straight from the
+ * device-resident rollout (rollout.py: time-major, field-major float32):  s [T][S][N], a [T][A][N], a_lp [T][A][N]
+ * (per-dimension log-probabilities at collection time), adv [T][N] (already normalised), v_target [T][N].  Sample
+ * b = t * N + i.  The mini-batch is positions first .. first + count - 1 of
+ *   - `index` (device int64 [>= first + count], values in [0, T * N)) when given -- a caller-made permutation;
+ *   - else of the pseudo-random permutation of [0, T * N) keyed by `perm_key` (a 6-round Feistel network with cycle
+ *     walking, evaluated per sample inside the kernel: the BatchSampler(SubsetRandomSampler(range(B)), mb, False) of
+ *     PPO2.py:104 without materialising the permutation; one key per epoch visits every sample exactly once). */
+typedef struct b200_ppo2_batch {
+    int64_t T, N;
+    const float *s, *a, *a_lp, *adv, *v_target;
+    const int64_t *index;
+    int64_t first, count;
+    uint64_t perm_key;
+} b200_ppo2_batch;
+
+/* b200_ppo2_grad: forward, loss, backward of BOTH nets for one mini-batch in one launch (fp32 FMA pipe, register-tiled
+ * GEMMs over 128-sample tiles held in shared memory; weights resident in shared memory):
+ *   actor  (PPO2.py:106-117):  mean = head(actor(s));  lp = sum_d Normal(mean_d, std_d).log_prob(a_d);
+ *          ratio = exp(lp - sum_d a_lp_d);  loss = mean(-min(ratio * adv, clamp(ratio, 1 - eps_clip, 1 + eps_clip) * adv))
+ *          (the entropy bonus of a fixed-std Gaussian is a constant: it shifts the loss value by -entropy_coef * H and
+ *          has no gradient; loss_out[0] includes it);
+ *   critic (PPO2.py:123-124):  loss = mse(v_target, critic(s)).
+ * Gradients of the MEAN losses with respect to every weight and bias are written to grad_actor / grad_critic (device
+ * float32, in torch's parameter order: per layer `weight` [out][in] row-major, then `bias`), summed over samples in a
+ * fixed order (per-block partial sums in `workspace`, added up in block order by a second small launch: bit-reproducible
+ * for a given device).
+ * loss_out: device float32 [2] = (actor loss, critic loss).  Either net may be NULL.  std_vec (device [A]) overrides
+ * the scalar std.  a_min / a_max are only read for actor->out_act == 2.
+ * Limits of this kernel: every layer <= 64 wide, state_dim <= 64, <= 16 actions, <= 4 layers per net (the nets of
+ * every PPO2 demo, utils/classes.py:529-615); wider nets return B200ENV_ESIZE.
+ * workspace: b200_ppo2_workspace_bytes() bytes of device memory (contents irrelevant). */
+B200_API size_t b200_ppo2_workspace_bytes(const b200_mlp *actor, const b200_mlp *critic);
+B200_API int b200_ppo2_grad(const b200_ppo2_batch *batch, const b200_mlp *actor, const b200_mlp *critic, float std,
+                            const float *std_vec, const float *a_min, const float *a_max, float eps_clip,
+                            float entropy_coef, float *grad_actor, float *grad_critic, float *loss_out, void *workspace,
+                            size_t workspace_bytes, void *cuda_stream);
+
+/* torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam.step() (PPO2.py:118-121,126-129; Adam
+ * eps 1e-5, :50-55) as ONE kernel over flat buffers: for each of the n_seg segments (one per net) the global gradient
+ * norm is computed in a fixed order, grad is scaled by min(1, max_norm / (norm + 1e-6)) (max_norm <= 0: no clipping)
+ * and param, exp_avg (m), exp_avg_sq (v) are updated in place with bias corrections for step number `step` (1-based).
+ * grad is first multiplied by grad_scale (1 / world size after a SUM all-reduce of the flat gradient buffer: the DPPO2
+ * gradient push, Distributed_PPO2.py:86-104).  Segment j covers elements seg_off[j] .. seg_off[j] + seg_len[j] - 1 of
+ * all four buffers and uses learning rate lr[j] (host arrays).  grad_norm_out: device float32 [n_seg] or NULL. */
+B200_API int b200_adam_step(int n_seg, const int64_t *seg_off, const int64_t *seg_len, const float *lr, float *param,
+                            const float *grad, float *exp_avg, float *exp_avg_sq, int64_t step, float beta1,
+                            float beta2, float eps, float max_norm, float grad_scale, float *grad_norm_out,
+                            void *cuda_stream);
+
+/* The whole K_epochs x mini-batch loop of learn() on one stream without returning to the host between mini-batches
+ * (single-GPU training; with several ranks the caller alternates b200_ppo2_grad, the all-reduce and b200_adam_step
+ * itself).  Epoch e uses permutation key perm_key + e; mini-batch j covers positions j * mini_batch .. of it (the last
+ * one partial, drop_last=False).  `param` is the flat buffer [actor params | critic params] the two b200_mlp structs
+ * point into; grad / exp_avg / exp_avg_sq: flat buffers of the same length; `step` is the 1-based Adam step number of
+ * the first mini-batch.  loss_out [2]: losses of the last mini-batch. */
+B200_API int b200_ppo2_learn(const b200_ppo2_batch *batch, const b200_mlp *actor, const b200_mlp *critic, float std,
+                             const float *std_vec, const float *a_min, const float *a_max, float eps_clip,
+                             float entropy_coef, int k_epochs, int64_t mini_batch, float lr_actor, float lr_critic,
+                             float beta1, float beta2, float adam_eps, float max_norm, int64_t step, float *param,
+                             float *grad, float *exp_avg, float *exp_avg_sq, float *loss_out, void *workspace,
+                             size_t workspace_bytes, void *cuda_stream);
+
 /* ------------------------------------------------------------- diagnostics */
 
 /* Measures the FP64 (dtype = B200ENV_F64) or FP32 vector FMA peak of the current device in TFLOP/s (2 flops per

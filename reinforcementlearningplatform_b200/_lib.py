@@ -52,6 +52,12 @@ class MLP(C.Structure):
                 ("w", C.c_void_p * 4), ("b", C.c_void_p * 4)]
 
 
+class PPO2Batch(C.Structure):
+    """struct b200_ppo2_batch"""
+    _fields_ = [("T", C.c_int64), ("N", C.c_int64)] + [(k, C.c_void_p) for k in ("s", "a", "a_lp", "adv", "v_target", "index")] + [
+        ("first", C.c_int64), ("count", C.c_int64), ("perm_key", C.c_uint64)]
+
+
 class CartPoleParams(C.Structure):
     """struct b200_cartpole_params"""
     _fields_ = [(k, C.c_double) for k in (
@@ -184,6 +190,17 @@ def load() -> C.CDLL:
     lib.b200_policy_forward_packed.restype = i32
     lib.b200_policy_forward_packed.argtypes = [i64, vp, vp, vp, sz, vp, vp, vp, C.c_float, vp, vp, u64, u64, i64, vp, vp, vp,
                                                vp, vp]
+    f32 = C.c_float
+    lib.b200_ppo2_workspace_bytes.restype = sz
+    lib.b200_ppo2_workspace_bytes.argtypes = [vp, vp]
+    lib.b200_ppo2_grad.restype = i32
+    lib.b200_ppo2_grad.argtypes = [vp, vp, vp, f32, vp, vp, vp, f32, f32, vp, vp, vp, vp, sz, vp]
+    lib.b200_adam_step.restype = i32
+    lib.b200_adam_step.argtypes = [i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(f32), vp, vp, vp, vp, i64, f32, f32, f32,
+                                   f32, f32, vp, vp]
+    lib.b200_ppo2_learn.restype = i32
+    lib.b200_ppo2_learn.argtypes = [vp, vp, vp, f32, vp, vp, vp, f32, f32, i32, i64, f32, f32, f32, f32, f32, f32, i64, vp,
+                                    vp, vp, vp, vp, vp, sz, vp]
     lib.b200_umma_probe.restype = i32
     lib.b200_umma_probe.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.b200_fastmath_eval.restype = i32

@@ -1,0 +1,740 @@
+// learn.cu -- K-LEARN: the PPO2 / DPPO2 network update on device.
+//
+// Replaces the body of the mini-batch loop of Proximal_Policy_Optimization2.learn (algorithm/policy_base/
+// Proximal_Policy_Optimization2.py:102-131) -- actor forward, Normal.log_prob, ratio, clipped surrogate, backward,
+// clip_grad_norm_, Adam; critic forward, mse_loss, backward, clip, Adam -- which round 1 left to torch autograd (about
+// forty library kernels per mini-batch, 0.24 s per learn() of 4096 x 64 samples against 8 ms for collecting them).
+//
+// ppo2_grad_kernel: one block works on 128-sample tiles of the mini-batch; blockIdx.y selects the net (actor / critic),
+// so both nets' gradients come out of ONE launch.  Everything of a tile stays in shared memory:
+//     H_l [128][K_l + 4]   input of layer l (H_0 = the gathered observations, H_l = tanh outputs), sample-major;
+//     W_l [N_l][K_l + 4]   the layer's weights as nn.Linear stores them (zero-padded), loaded once per block;
+// and the three products of a layer are register-tiled fp32 GEMMs whose operands are both read along their contiguous
+// index with 16-byte loads (row pitch = width + 4 floats, so that the rows a warp touches fall into distinct banks):
+//     forward   Z[s][n]  = sum_k H_l[s][k] W_l[n][k]          thread: 4 samples x (N/8) outputs, 12 LDS.128 per 128 FFMA
+//     dW        dW[n][k] = sum_s dZ_l[s][n] H_l[s][k]         thread: 4 x 4 entries, kept in REGISTERS across all tiles
+//     dH        dH[s][k] = sum_n dZ_l[s][n] W_l[n][k]         thread: 4 samples x (K/32) 4-vectors
+// dZ_{l-1} = dH * (1 - H_l^2) overwrites H_l in place (its last reader was dW_l), so no separate gradient buffers exist.
+// A block adds up its tiles in program order and stores its partial gradient once; ppo2_reduce_kernel (a second, wide
+// launch: one thread per parameter) sums the partials in block order: the result does not depend on scheduling (no
+// floating-point atomics anywhere).
+//
+// adam_kernel: clip_grad_norm_ + Adam.step over flat parameter / gradient / moment buffers (one segment per net), the
+// global norm recomputed in a fixed order by every block so that no grid-wide synchronisation is needed.
+//
+// Arithmetic is fp32 on the FMA pipe with CUDA's accurate tanhf / expf (the test compares gradients and the updated
+// parameters with torch autograd: <= 1e-6).  Tensor cores are not used here on purpose: a 3xTF32 split would need the
+// activations in two operand layouts per layer (K-major for forward / dH, sample-major for dW) and the mini-batches of
+// the reference's configurations (4096 .. 16384 samples of a 6-64-64-32-8 net = 0.2 .. 0.9 GFLOP) are launch-latency
+// bound either way.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LT = 256;     // threads per block
+constexpr int TM = 128;     // samples per tile
+constexpr int LMAX = 4;     // layers per net
+constexpr int WMAX = 64;    // widest layer / input
+constexpr int GRID_CAP = 148;
+
+struct LLayer {
+    int K, N;            // padded: K to a multiple of 8, N to 8 / 16 / 32 / 64
+    int k_real, n_real;
+    int w_off, b_off;    // shared-memory float offsets: weights [N][K + 4], bias [N]
+    int h_off;           // shared-memory float offset of the layer's input H_l [TM][K + 4]
+    int g_w, g_b;        // offsets of weight / bias inside the net's flat gradient
+    const float *w, *b;  // global parameters
+};
+
+struct LNet {
+    int n_layers, P, out_act;
+    int gout_off;        // dZ of the output layer [TM][N_out + 4]
+    int smem_floats;
+    LLayer L[LMAX];
+};
+
+struct LearnArgs {
+    LNet net[2];                 // 0 actor, 1 critic
+    int net_of_y[2];             // blockIdx.y -> net
+    int S, A;
+    int64_t T, N, first, count;
+    const float *s, *a, *a_lp, *adv, *v_target;
+    const int64_t *index;
+    uint64_t perm_key;
+    int perm_half_bits;
+    float eps_clip, inv_count, entropy_coef;
+    float std_;
+    const float *std_vec, *a_min, *a_max;
+    float *partial[2];           // [gridDim.x][P + 4]
+    float *grad[2];
+    float *loss_out;             // [2]
+    unsigned int *counter;       // [2]
+};
+
+// ------------------------------------------------------------------------------------------------ sample permutation
+__host__ __device__ __forceinline__ uint32_t feistel_round(uint32_t r, uint32_t k) {
+    uint32_t h = (r + k) * 0x9E3779B1u;
+    h ^= h >> 15; h *= 0x85EBCA77u;
+    h ^= h >> 13; h *= 0xC2B2AE3Du;
+    h ^= h >> 16;
+    return h;
+}
+// bijection of [0, 2^(2 * half_bits)) restricted to [0, B) by cycle walking (B > 2^(2 * half_bits - 2): < 4 walks expected)
+__host__ __device__ __forceinline__ int64_t perm_index(uint64_t key, int64_t j, int64_t B, int half_bits) {
+    const uint32_t mask = (1u << half_bits) - 1u;
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    uint64_t x = (uint64_t)j;
+    do {
+        uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const uint32_t f = feistel_round(r, (q & 1 ? k1 : k0) + 0x632BE5ABu * (uint32_t)q) & mask;
+            const uint32_t t = l ^ f;
+            l = r;
+            r = t;
+        }
+        x = ((uint64_t)l << half_bits) | r;
+    } while ((int64_t)x >= B);
+    return (int64_t)x;
+}
+int half_bits_for(int64_t B) {
+    int bits = 1;
+    while (((int64_t)1 << bits) < B) ++bits;
+    return (bits + 1) / 2 < 1 ? 1 : (bits + 1) / 2;
+}
+
+// ------------------------------------------------------------------------------------------------ tile GEMMs
+// thread coordinates of the sample-by-feature products: sg = 0..31 -> samples sg + 32 i, ng = 0..7 -> features ng + 8 j
+template <int NJ>
+__device__ __forceinline__ void fwd_layer(const float *__restrict__ H, int ph, const float *__restrict__ W, int pw,
+                                          const float *__restrict__ bias, int K, float *__restrict__ out, int po,
+                                          bool hidden, int sg, int ng) {
+    float acc[4][NJ];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0f;
+    const float *hp = H + sg * ph, *wp = W + ng * pw;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        float4 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(hp + 32 * i * ph + k0);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float4 w = *reinterpret_cast<const float4 *>(wp + 8 * j * pw + k0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i][j] = fmaf(a[i].x, w.x, acc[i][j]);
+                acc[i][j] = fmaf(a[i].y, w.y, acc[i][j]);
+                acc[i][j] = fmaf(a[i].z, w.z, acc[i][j]);
+                acc[i][j] = fmaf(a[i].w, w.w, acc[i][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const float b = bias[ng + 8 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float z = acc[i][j] + b;
+            out[(sg + 32 * i) * po + ng + 8 * j] = hidden ? tanhf(z) : z;
+        }
+    }
+}
+
+// dH[s][k] = sum_n G[s][n] W[n][k], then dZ = dH * (1 - H^2) written over H.  k-vectors of 4: v = ng + 8 jv
+template <int NV>
+__device__ __forceinline__ void bwd_layer(const float *__restrict__ G, int pg, const float *__restrict__ W, int pw, int N,
+                                          float *H, int ph, int KG, int sg, int ng) {
+    if (ng >= KG) return;
+    float4 acc[4][NV];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jv = 0; jv < NV; ++jv) acc[i][jv] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *gp = G + sg * pg, *wp = W + 4 * ng;
+    for (int n0 = 0; n0 < N; n0 += 4) {
+        float g[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 t = *reinterpret_cast<const float4 *>(gp + 32 * i * pg + n0);
+            g[i][0] = t.x; g[i][1] = t.y; g[i][2] = t.z; g[i][3] = t.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int jv = 0; jv < NV; ++jv) {
+                const float4 w = *reinterpret_cast<const float4 *>(wp + (n0 + q) * pw + 32 * jv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][jv].x = fmaf(g[i][q], w.x, acc[i][jv].x);
+                    acc[i][jv].y = fmaf(g[i][q], w.y, acc[i][jv].y);
+                    acc[i][jv].z = fmaf(g[i][q], w.z, acc[i][jv].z);
+                    acc[i][jv].w = fmaf(g[i][q], w.w, acc[i][jv].w);
+                }
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jv = 0; jv < NV; ++jv) {
+            float4 *hp = reinterpret_cast<float4 *>(H + (sg + 32 * i) * ph + 4 * ng + 32 * jv);
+            const float4 h = *hp;
+            float4 d;
+            d.x = acc[i][jv].x * (1.0f - h.x * h.x);
+            d.y = acc[i][jv].y * (1.0f - h.y * h.y);
+            d.z = acc[i][jv].z * (1.0f - h.z * h.z);
+            d.w = acc[i][jv].w * (1.0f - h.w * h.w);
+            *hp = d;
+        }
+}
+
+// dW[4 ng .. +3][4 kg .. +3] += sum over the tile's samples of dZ[s][n] H[s][k]; db likewise for the kg == 0 threads
+__device__ __forceinline__ void dw_layer(const float *__restrict__ G, int pg, const float *__restrict__ H, int ph, int ng,
+                                         int kg, float (&dw)[16], float (&db)[4]) {
+    const float *gp = G + 4 * ng, *hp = H + 4 * kg;
+#pragma unroll 4
+    for (int s = 0; s < TM; ++s) {
+        const float4 g = *reinterpret_cast<const float4 *>(gp + s * pg);
+        const float4 h = *reinterpret_cast<const float4 *>(hp + s * ph);
+        dw[0] = fmaf(g.x, h.x, dw[0]);   dw[1] = fmaf(g.x, h.y, dw[1]);   dw[2] = fmaf(g.x, h.z, dw[2]);   dw[3] = fmaf(g.x, h.w, dw[3]);
+        dw[4] = fmaf(g.y, h.x, dw[4]);   dw[5] = fmaf(g.y, h.y, dw[5]);   dw[6] = fmaf(g.y, h.z, dw[6]);   dw[7] = fmaf(g.y, h.w, dw[7]);
+        dw[8] = fmaf(g.z, h.x, dw[8]);   dw[9] = fmaf(g.z, h.y, dw[9]);   dw[10] = fmaf(g.z, h.z, dw[10]); dw[11] = fmaf(g.z, h.w, dw[11]);
+        dw[12] = fmaf(g.w, h.x, dw[12]); dw[13] = fmaf(g.w, h.y, dw[13]); dw[14] = fmaf(g.w, h.z, dw[14]); dw[15] = fmaf(g.w, h.w, dw[15]);
+        if (kg == 0) { db[0] += g.x; db[1] += g.y; db[2] += g.z; db[3] += g.w; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the gradient kernel
+__global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant__ LearnArgs A) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ int s_t[TM], s_i[TM];
+    __shared__ float s_red[LT / 32];
+    const int net_id = A.net_of_y[blockIdx.y];
+    const LNet &net = A.net[net_id];
+    const int L = net.n_layers;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sg = (lane & 3) + 4 * warp, ng = lane >> 2;
+
+    // weights and biases -> shared memory, zero-padded
+    for (int l = 0; l < L; ++l) {
+        const LLayer &Ly = net.L[l];
+        const int pw = Ly.K + 4;
+        for (int e = tid; e < Ly.N * pw; e += LT) {
+            const int n = e / pw, k = e - n * pw;
+            sm[Ly.w_off + e] = (n < Ly.n_real && k < Ly.k_real) ? __ldg(Ly.w + n * Ly.k_real + k) : 0.0f;
+        }
+        for (int n = tid; n < Ly.N; n += LT) sm[Ly.b_off + n] = n < Ly.n_real ? __ldg(Ly.b + n) : 0.0f;
+    }
+
+    float dw[LMAX][16], db[LMAX][4];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dw[l][e] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) db[l][e] = 0.0f;
+    }
+    float loss_acc = 0.0f;
+
+    const int64_t tiles = (A.count + TM - 1) / TM;
+    const LLayer &L0 = net.L[0];
+    const LLayer &LO = net.L[L - 1];
+    float *gout = sm + net.gout_off;
+    const int pgo = LO.N + 4;
+
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        __syncthreads();   // the previous tile's last phase has finished with H and s_t / s_i
+        if (tid < TM) {
+            const int64_t j = tile * TM + tid;
+            int t = -1, i = 0;
+            if (j < A.count) {
+                const int64_t b = A.index ? A.index[A.first + j] : perm_index(A.perm_key, A.first + j, A.T * A.N, A.perm_half_bits);
+                t = (int)(b / A.N);
+                i = (int)(b - (int64_t)t * A.N);
+            }
+            s_t[tid] = t;
+            s_i[tid] = i;
+        }
+        __syncthreads();
+        {   // gather the observations: H_0[s][k]
+            float *H0 = sm + L0.h_off;
+            const int p0 = L0.K + 4;
+            for (int e = tid; e < TM * L0.K; e += LT) {
+                const int s = e & (TM - 1), k = e >> 7;
+                const int t = s_t[s];
+                H0[s * p0 + k] = (t >= 0 && k < A.S) ? __ldg(A.s + ((int64_t)t * A.S + k) * A.N + s_i[s]) : 0.0f;
+            }
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- forward
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) {
+            if (l < L) {
+                const LLayer &Ly = net.L[l];
+                const bool last = l == L - 1;
+                float *out = last ? gout : sm + net.L[l + 1 < LMAX ? l + 1 : l].h_off;
+                const float *H = sm + Ly.h_off, *W = sm + Ly.w_off, *bs = sm + Ly.b_off;
+                const int ph = Ly.K + 4, po = Ly.N + 4;
+                switch (Ly.N >> 3) {
+                case 1: fwd_layer<1>(H, ph, W, ph, bs, Ly.K, out, po, !last, sg, ng); break;
+                case 2: fwd_layer<2>(H, ph, W, ph, bs, Ly.K, out, po, !last, sg, ng); break;
+                case 4: fwd_layer<4>(H, ph, W, ph, bs, Ly.K, out, po, !last, sg, ng); break;
+                default: fwd_layer<8>(H, ph, W, ph, bs, Ly.K, out, po, !last, sg, ng); break;
+                }
+                __syncthreads();
+            }
+        }
+        // ---------------------------------------------------------------- loss and its gradient at the net's output
+        if (tid < TM) {
+            float *z = gout + tid * pgo;
+            const int t = s_t[tid], i = s_i[tid];
+            if (t < 0) {
+                for (int d = 0; d < LO.N; ++d) z[d] = 0.0f;
+            } else if (net_id == 0) {
+                // Normal(mean, std).log_prob(a) summed over dimensions, PPO2.py:106-112
+                float lp = 0.0f, lp_old = 0.0f;
+                float dm[16];   // d lp / d z_d
+#pragma unroll 1
+                for (int d = 0; d < A.A; ++d) {
+                    const int64_t off = ((int64_t)t * A.A + d) * A.N + i;
+                    const float act = __ldg(A.a + off);
+                    lp_old += __ldg(A.a_lp + off);
+                    const float sd = A.std_vec ? __ldg(A.std_vec + d) : A.std_;
+                    float m = z[d], dmdz = 1.0f;
+                    if (net.out_act == 1) {
+                        dmdz = m > 0.0f ? 1.0f : 0.0f;
+                        m = fmaxf(m, 0.0f);
+                    } else if (net.out_act == 2) {
+                        const float lo = __ldg(A.a_min + d), hi = __ldg(A.a_max + d);
+                        const float off2 = (lo + hi) / 2.0f, gain = hi - off2;
+                        const float th = tanhf(m);
+                        m = th * gain + off2;
+                        dmdz = gain * (1.0f - th * th);
+                    }
+                    const float diff = act - m, var = sd * sd;
+                    lp += -(diff * diff) / (2.0f * var) - logf(sd) - 0.91893853320467274178f;
+                    dm[d & 15] = diff / var * dmdz;
+                }
+                const float ratio = expf(lp - lp_old);
+                const float adv = __ldg(A.adv + (int64_t)t * A.N + i);
+                const float lo = 1.0f - A.eps_clip, hi = 1.0f + A.eps_clip;
+                const float surr1 = ratio * adv, surr2 = fminf(fmaxf(ratio, lo), hi) * adv;
+                loss_acc += -fminf(surr1, surr2);
+                // d(-min(surr1, surr2)) / d ratio: -adv unless the clamp is active and selected
+                const bool clamped = ratio < lo || ratio > hi;
+                const float dldr = (clamped && !(surr1 < surr2)) ? 0.0f : -adv;
+                const float c = dldr * ratio * A.inv_count;
+                for (int d = 0; d < LO.N; ++d) z[d] = d < A.A ? c * dm[d & 15] : 0.0f;
+            } else {
+                const float v = z[0], vt = __ldg(A.v_target + (int64_t)t * A.N + i);
+                const float e = v - vt;
+                loss_acc += e * e;
+                z[0] = 2.0f * e * A.inv_count;
+                for (int d = 1; d < LO.N; ++d) z[d] = 0.0f;
+            }
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- backward
+#pragma unroll
+        for (int l = LMAX - 1; l >= 0; --l) {
+            if (l < L) {
+                const LLayer &Ly = net.L[l];
+                const float *G = (l == L - 1) ? gout : sm + net.L[l + 1 < LMAX ? l + 1 : l].h_off;
+                float *H = sm + Ly.h_off;
+                const int pg = Ly.N + 4, ph = Ly.K + 4;
+                const int kgs = Ly.K >> 2;
+                if (tid < (Ly.N >> 2) * kgs) dw_layer(G, pg, H, ph, tid / kgs, tid % kgs, dw[l], db[l]);
+                if (l > 0) {
+                    __syncthreads();
+                    if (kgs == 16) bwd_layer<2>(G, pg, sm + Ly.w_off, ph, Ly.N, H, ph, kgs, sg, ng);
+                    else bwd_layer<1>(G, pg, sm + Ly.w_off, ph, Ly.N, H, ph, kgs, sg, ng);
+                    __syncthreads();
+                }
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- this block's partial gradient
+    float *part = A.partial[net_id] + (size_t)blockIdx.x * (size_t)(net.P + 4);
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+        if (l < L) {
+            const LLayer &Ly = net.L[l];
+            const int kgs = Ly.K >> 2;
+            if (tid < (Ly.N >> 2) * kgs) {
+                const int n0 = 4 * (tid / kgs), k0 = 4 * (tid % kgs);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int n = n0 + a;
+                    if (n < Ly.n_real) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (k0 + c < Ly.k_real) part[Ly.g_w + n * Ly.k_real + k0 + c] = dw[l][4 * a + c];
+                        if (k0 == 0) part[Ly.g_b + n] = db[l][a];
+                    }
+                }
+            }
+        }
+    }
+    // block sum of the loss in a fixed order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+    if (lane == 0) s_red[warp] = loss_acc;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < LT / 32; ++w) t += s_red[w];
+        part[net.P] = t;
+    }
+}
+
+// Sum of the per-block partial gradients in block order: one thread per parameter (consecutive threads read consecutive
+// addresses of every partial), the loads of eight partials in flight at a time.  A separate, wide launch: folded into
+// the gradient kernel as "the last block to finish reduces" it serialised 64 x 6.9 k dependent L2 reads on one SM and
+// cost three times the gradient computation itself (130 of 190 us per 16 k-sample mini-batch).
+struct ReduceArgs {
+    const float *partial[2];
+    float *grad[2];
+    float *loss_out;
+    int P[2], first_block[2];   // net j owns blocks first_block[j] .. of the launch
+    int nets, nblk;
+    float inv_count;
+    // entropy bonus of the fixed-std Gaussian (a constant of the loss value): slot `ent_slot` (-1: none) gets
+    // -entropy_coef * sum_d (0.5 + 0.5 log(2 pi) + log std_d), PPO2.py:107,116
+    int ent_slot, A;
+    float ent_coef, std_;
+    const float *std_vec;
+};
+__global__ void __launch_bounds__(256) ppo2_reduce_kernel(const __grid_constant__ ReduceArgs a) {
+    const int j = (a.nets > 1 && (int)blockIdx.x >= a.first_block[1]) ? 1 : 0;
+    const int p = ((int)blockIdx.x - a.first_block[j]) * 256 + (int)threadIdx.x;
+    const int P = a.P[j];
+    if (p > P) return;
+    const size_t stride = (size_t)(P + 4);
+    const float *base = a.partial[j] + p;
+    float t = 0.0f;
+    int b = 0;
+    for (; b + 8 <= a.nblk; b += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldcg(base + (size_t)(b + q) * stride);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += v[q];
+    }
+    for (; b < a.nblk; ++b) t += __ldcg(base + (size_t)b * stride);
+    if (p < P) {
+        a.grad[j][p] = t;
+        return;
+    }
+    float loss = t * a.inv_count;
+    if (j == a.ent_slot) {
+        float h = 0.0f;
+        for (int d = 0; d < a.A; ++d) h += 0.5f + 0.9189385332046727f + logf(a.std_vec ? a.std_vec[d] : a.std_);
+        loss -= a.ent_coef * h;
+    }
+    a.loss_out[j] = loss;
+}
+
+// ------------------------------------------------------------------------------------------------ clip + Adam
+struct AdamArgs {
+    int64_t off[2], len[2];
+    float lr[2];
+    float *param, *m, *v;
+    const float *grad;
+    float one_minus_b1, b2, one_minus_b2, eps, bc1, bc2_sqrt, max_norm, grad_scale;
+    float *norm_out;
+};
+constexpr int AT = 1024;
+
+__global__ void __launch_bounds__(AT) adam_kernel(const __grid_constant__ AdamArgs a) {
+    __shared__ float s_red[AT / 32];
+    __shared__ float s_total;
+    const int seg = blockIdx.y, tid = threadIdx.x;
+    const int64_t off = a.off[seg], P = a.len[seg];
+    const float *g = a.grad + off;
+    // total_norm of clip_grad_norm_, every block in the same order
+    float ss = 0.0f;
+    for (int64_t p = tid; p < P; p += AT) {
+        const float x = __ldcg(g + p) * a.grad_scale;
+        ss = fmaf(x, x, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < AT / 32; ++w) t += s_red[w];
+        s_total = t;
+    }
+    __syncthreads();
+    const float norm = sqrtf(s_total);
+    float coef = a.grad_scale;
+    if (a.max_norm > 0.0f) coef *= fminf(a.max_norm / (norm + 1e-6f), 1.0f);
+    if (blockIdx.x == 0 && tid == 0 && a.norm_out) a.norm_out[seg] = norm;
+    const float step_size = a.lr[seg] / a.bc1;
+    float *pp = a.param + off, *pm = a.m + off, *pv = a.v + off;
+    for (int64_t p = (int64_t)blockIdx.x * AT + tid; p < P; p += (int64_t)gridDim.x * AT) {
+        const float gr = __ldcg(g + p) * coef;
+        float m = pm[p], v = pv[p];
+        m = m + (gr - m) * a.one_minus_b1;                  // exp_avg.lerp_(grad, 1 - beta1)
+        v = v * a.b2 + a.one_minus_b2 * gr * gr;            // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+        const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+        pp[p] = pp[p] - step_size * (m / denom);            // param.addcdiv_(exp_avg, denom, value=-step_size)
+        pm[p] = m;
+        pv[p] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int pad_n(int n) { return n <= 8 ? 8 : n <= 16 ? 16 : n <= 32 ? 32 : 64; }
+
+int fill_net(const b200_mlp *m, bool is_actor, LNet *net) {
+    *net = LNet{};
+    if (m->n_layers < 1 || m->n_layers > LMAX) return B200ENV_ESIZE;
+    net->n_layers = m->n_layers;
+    net->out_act = m->out_act;
+    int off = 0, P = 0;
+    for (int l = 0; l < m->n_layers; ++l) {
+        const int in = m->dims[l], out = m->dims[l + 1];
+        if (in < 1 || out < 1 || in > WMAX || out > WMAX) return B200ENV_ESIZE;
+        if (!m->w[l] || !m->b[l]) return B200ENV_ENULL;
+        LLayer &Ly = net->L[l];
+        const bool last = l + 1 == m->n_layers;
+        if (last && out > 16) return B200ENV_ESIZE;
+        Ly.k_real = in;
+        Ly.n_real = out;
+        Ly.K = l == 0 ? (in + 7) / 8 * 8 : net->L[l - 1].N;
+        Ly.N = pad_n(out);
+        Ly.w = m->w[l];
+        Ly.b = m->b[l];
+        Ly.g_w = P;
+        Ly.g_b = P + in * out;
+        P += in * out + out;
+        Ly.w_off = off; off += Ly.N * (Ly.K + 4);
+        Ly.b_off = off; off += Ly.N;
+    }
+    for (int l = 0; l < m->n_layers; ++l) {
+        net->L[l].h_off = off;
+        off += TM * (net->L[l].K + 4);
+    }
+    net->gout_off = off;
+    off += TM * (net->L[m->n_layers - 1].N + 4);
+    net->P = P;
+    net->smem_floats = off;
+    (void)is_actor;
+    return B200ENV_OK;
+}
+
+int grid_cap() {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sms[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = GRID_CAP;
+        sms[dev] = v > GRID_CAP ? GRID_CAP : v;
+    }
+    return sms[dev];
+}
+
+size_t partial_floats(const LNet &n) { return (size_t)GRID_CAP * (size_t)(n.P + 4); }
+
+struct Plan {
+    LearnArgs a;
+    int nets;
+    size_t smem;
+};
+
+int make_plan(const b200_ppo2_batch *bt, const b200_mlp *actor, const b200_mlp *critic, float std_, const float *std_vec,
+              const float *a_min, const float *a_max, float eps_clip, float entropy_coef, float *grad_actor,
+              float *grad_critic, float *loss_out, void *workspace, size_t workspace_bytes, Plan *pl) {
+    if (!bt || (!actor && !critic) || !loss_out || !workspace) return B200ENV_ENULL;
+    if (!bt->s || (actor && !bt->adv) || (critic && !bt->v_target)) return B200ENV_ENULL;
+    if (bt->T <= 0 || bt->N <= 0 || bt->N >= ((int64_t)1 << 31) || bt->T >= ((int64_t)1 << 31)) return B200ENV_ESIZE;
+    const int64_t B = bt->T * bt->N;
+    if (bt->count <= 0 || bt->first < 0 || (!bt->index && bt->first + bt->count > B)) return B200ENV_ESIZE;
+    LearnArgs &a = pl->a;
+    a = LearnArgs{};
+    int rc;
+    pl->nets = 0;
+    size_t smem_f = 0, ws = 64;
+    if (actor) {
+        if (!grad_actor || !bt->a || !bt->a_lp) return B200ENV_ENULL;
+        if (!std_vec && !(std_ > 0.0f)) return B200ENV_EPARAMS;
+        if (actor->out_act < 0 || actor->out_act > 2) return B200ENV_EPARAMS;
+        if (actor->out_act == 2 && (!a_min || !a_max)) return B200ENV_ENULL;
+        if ((rc = fill_net(actor, true, &a.net[0]))) return rc;
+        a.net_of_y[pl->nets++] = 0;
+        smem_f = a.net[0].smem_floats;
+        a.partial[0] = reinterpret_cast<float *>(static_cast<char *>(workspace) + ws);
+        ws += partial_floats(a.net[0]) * 4;
+        a.S = actor->dims[0];
+        a.A = actor->dims[actor->n_layers];
+    }
+    if (critic) {
+        if (!grad_critic) return B200ENV_ENULL;
+        if (critic->dims[critic->n_layers > 0 && critic->n_layers <= 4 ? critic->n_layers : 0] != 1) return B200ENV_EPARAMS;
+        if (actor && actor->dims[0] != critic->dims[0]) return B200ENV_EPARAMS;
+        if ((rc = fill_net(critic, false, &a.net[1]))) return rc;
+        a.net[1].out_act = 0;
+        a.net_of_y[pl->nets++] = 1;
+        if ((size_t)a.net[1].smem_floats > smem_f) smem_f = a.net[1].smem_floats;
+        a.partial[1] = reinterpret_cast<float *>(static_cast<char *>(workspace) + ws);
+        ws += partial_floats(a.net[1]) * 4;
+        a.S = critic->dims[0];
+    }
+    if (ws > workspace_bytes) return B200ENV_ESIZE;
+    pl->smem = smem_f * sizeof(float);
+    if (pl->smem > 227 * 1024 - 2048) return B200ENV_ESIZE;
+    a.T = bt->T; a.N = bt->N; a.first = bt->first; a.count = bt->count;
+    a.s = bt->s; a.a = bt->a; a.a_lp = bt->a_lp; a.adv = bt->adv; a.v_target = bt->v_target;
+    a.index = bt->index;
+    a.perm_key = bt->perm_key;
+    a.perm_half_bits = half_bits_for(B);
+    a.eps_clip = eps_clip;
+    a.inv_count = 1.0f / (float)bt->count;
+    a.std_ = std_; a.std_vec = std_vec; a.a_min = a_min; a.a_max = a_max;
+    a.entropy_coef = entropy_coef;
+    a.grad[0] = grad_actor; a.grad[1] = grad_critic;
+    a.loss_out = loss_out;
+    a.counter = static_cast<unsigned int *>(workspace);
+    return B200ENV_OK;
+}
+
+int launch_grad(Plan &pl, cudaStream_t stream) {
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (pl.smem > 48 * 1024 && pl.smem > configured[dev]) {
+        if (cudaFuncSetAttribute(ppo2_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
+            return b200_check_launch();
+        configured[dev] = pl.smem;
+    }
+    const int64_t tiles = (pl.a.count + TM - 1) / TM;
+    const int cap = grid_cap() / pl.nets > 0 ? grid_cap() / pl.nets : 1;
+    dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)pl.nets);
+    ppo2_grad_kernel<<<grid, LT, pl.smem, stream>>>(pl.a);
+    ReduceArgs r = {};
+    int blocks = 0;
+    for (int y = 0; y < pl.nets; ++y) {
+        const int id = pl.a.net_of_y[y];
+        r.partial[y] = pl.a.partial[id];
+        r.grad[y] = pl.a.grad[id];
+        r.P[y] = pl.a.net[id].P;
+        r.first_block[y] = blocks;
+        blocks += (pl.a.net[id].P + 1 + 255) / 256;
+    }
+    // loss_out is indexed by net id (0 actor, 1 critic): with a single net present its slot is selected here
+    r.loss_out = pl.a.loss_out + (pl.nets == 1 ? pl.a.net_of_y[0] : 0);
+    r.nets = pl.nets;
+    r.nblk = (int)grid.x;
+    r.inv_count = pl.a.inv_count;
+    r.ent_slot = (pl.a.net_of_y[0] == 0 && pl.a.entropy_coef != 0.0f) ? 0 : -1;
+    r.A = pl.a.A; r.ent_coef = pl.a.entropy_coef; r.std_ = pl.a.std_; r.std_vec = pl.a.std_vec;
+    ppo2_reduce_kernel<<<blocks, 256, 0, stream>>>(r);
+    return b200_check_launch();
+}
+
+int launch_adam(int n_seg, const int64_t *seg_off, const int64_t *seg_len, const float *lr, float *param, const float *grad,
+                float *m, float *v, int64_t step, float beta1, float beta2, float eps, float max_norm, float grad_scale,
+                float *norm_out, cudaStream_t stream) {
+    if (n_seg < 1 || n_seg > 2 || !seg_off || !seg_len || !lr) return B200ENV_EPARAMS;
+    if (!param || !grad || !m || !v) return B200ENV_ENULL;
+    if (step < 1) return B200ENV_EPARAMS;
+    AdamArgs a = {};
+    int64_t longest = 0;
+    for (int j = 0; j < n_seg; ++j) {
+        if (seg_len[j] <= 0 || seg_off[j] < 0) return B200ENV_ESIZE;
+        a.off[j] = seg_off[j]; a.len[j] = seg_len[j]; a.lr[j] = lr[j];
+        if (seg_len[j] > longest) longest = seg_len[j];
+    }
+    a.param = param; a.m = m; a.v = v; a.grad = grad;
+    a.one_minus_b1 = (float)(1.0 - (double)beta1);
+    a.b2 = beta2;
+    a.one_minus_b2 = (float)(1.0 - (double)beta2);
+    a.eps = eps;
+    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    a.max_norm = max_norm;
+    a.grad_scale = grad_scale;
+    a.norm_out = norm_out;
+    int64_t bx = (longest + (int64_t)AT * 4 - 1) / ((int64_t)AT * 4);
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    adam_kernel<<<dim3((unsigned)bx, (unsigned)n_seg), AT, 0, stream>>>(a);
+    return b200_check_launch();
+}
+
+} // namespace
+
+extern "C" B200_API size_t b200_ppo2_workspace_bytes(const b200_mlp *actor, const b200_mlp *critic) {
+    size_t ws = 64;
+    LNet n;
+    if (actor) {
+        if (fill_net(actor, true, &n)) return 0;
+        ws += partial_floats(n) * 4;
+    }
+    if (critic) {
+        if (fill_net(critic, false, &n)) return 0;
+        ws += partial_floats(n) * 4;
+    }
+    return (actor || critic) ? ws : 0;
+}
+
+extern "C" B200_API int b200_ppo2_grad(const b200_ppo2_batch *batch, const b200_mlp *actor, const b200_mlp *critic,
+                                       float std_, const float *std_vec, const float *a_min, const float *a_max,
+                                       float eps_clip, float entropy_coef, float *grad_actor, float *grad_critic,
+                                       float *loss_out, void *workspace, size_t workspace_bytes, void *cuda_stream) {
+    Plan pl;
+    int rc = make_plan(batch, actor, critic, std_, std_vec, a_min, a_max, eps_clip, entropy_coef, grad_actor, grad_critic,
+                       loss_out, workspace, workspace_bytes, &pl);
+    if (rc) return rc;
+    return launch_grad(pl, (cudaStream_t)cuda_stream);
+}
+
+extern "C" B200_API int b200_adam_step(int n_seg, const int64_t *seg_off, const int64_t *seg_len, const float *lr,
+                                       float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t step,
+                                       float beta1, float beta2, float eps, float max_norm, float grad_scale,
+                                       float *grad_norm_out, void *cuda_stream) {
+    return launch_adam(n_seg, seg_off, seg_len, lr, param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, eps, max_norm,
+                       grad_scale, grad_norm_out, (cudaStream_t)cuda_stream);
+}
+
+extern "C" B200_API int b200_ppo2_learn(const b200_ppo2_batch *batch, const b200_mlp *actor, const b200_mlp *critic,
+                                        float std_, const float *std_vec, const float *a_min, const float *a_max,
+                                        float eps_clip, float entropy_coef, int k_epochs, int64_t mini_batch,
+                                        float lr_actor, float lr_critic, float beta1, float beta2, float adam_eps,
+                                        float max_norm, int64_t step, float *param, float *grad, float *exp_avg,
+                                        float *exp_avg_sq, float *loss_out, void *workspace, size_t workspace_bytes,
+                                        void *cuda_stream) {
+    if (!batch || !actor || !critic || !param || !grad || !exp_avg || !exp_avg_sq) return B200ENV_ENULL;
+    if (batch->index) return B200ENV_EPARAMS;   // the loop draws its own permutation per epoch
+    if (k_epochs < 1 || mini_batch < 1 || step < 1) return B200ENV_EPARAMS;
+    const int64_t B = batch->T * batch->N;
+    LNet na, nc;
+    int rc;
+    if ((rc = fill_net(actor, true, &na)) || (rc = fill_net(critic, false, &nc))) return rc;
+    const int64_t seg_off[2] = {0, na.P}, seg_len[2] = {na.P, nc.P};
+    const float lr[2] = {lr_actor, lr_critic};
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    b200_ppo2_batch bt = *batch;
+    Plan pl;
+    for (int e = 0; e < k_epochs; ++e) {
+        bt.perm_key = batch->perm_key + (uint64_t)e;
+        for (int64_t first = 0; first < B; first += mini_batch) {
+            bt.first = first;
+            bt.count = B - first < mini_batch ? B - first : mini_batch;
+            if ((rc = make_plan(&bt, actor, critic, std_, std_vec, a_min, a_max, eps_clip, entropy_coef, grad, grad + na.P,
+                                loss_out, workspace, workspace_bytes, &pl))) return rc;
+            if ((rc = launch_grad(pl, stream))) return rc;
+            if ((rc = launch_adam(2, seg_off, seg_len, lr, param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, adam_eps,
+                                  max_norm, 1.0f, nullptr, stream))) return rc;
+            ++step;
+        }
+    }
+    return B200ENV_OK;
+}

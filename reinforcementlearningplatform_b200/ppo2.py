@@ -6,13 +6,15 @@ the same hyper-parameter dictionary (``ppo_msg``) and the same loss, restructure
     collect():  policy_state --K-POLICY--> a, log_prob  --step kernel--> s, s_, r, done, flag written straight into the
                 time-major RolloutBuffer; rewards optionally through the running normaliser (K-NORM), T times, no host copy
     learn():    V(s), V(s_) by K-POLICY (critic only) -> K-GAE + global advantage normalisation ->
-                K_epochs x mini-batches of the clipped-surrogate / entropy / value losses with torch autograd on the
-                caller's own actor / critic modules (Adam eps 1e-5, grad-norm clip 0.5, linear lr decay, as the reference)
-                -> with torch.distributed: one flat gradient all-reduce per mini-batch (dist.FlatGradAllReducer), the
-                synchronous form of the DPPO2 gradient push (Distributed_PPO2.py:86-104)
+                K_epochs x mini-batches of the clipped-surrogate / entropy / value losses (Adam eps 1e-5, grad-norm clip
+                0.5, linear lr decay, as the reference) by K-LEARN (learn.py / csrc/learn.cu: forward + loss + backward
+                of both nets in one launch, clip + Adam in a second one, mini-batches drawn by an in-kernel keyed
+                permutation) -> with torch.distributed: one flat gradient all-reduce per mini-batch, the synchronous form
+                of the DPPO2 gradient push (Distributed_PPO2.py:86-104)
 
-Only the update itself uses torch's library kernels (the learner is outside the hot path); everything
-per env-step runs in this repo's CUDA kernels.
+``learner="fused"`` (default whenever the nets fit K-LEARN: layers <= 64 wide, i.e. every PPO2 demo net) runs no torch
+library kernel in learn(); ``learner="torch"`` keeps round 1's autograd update on the caller's modules (the 256-wide
+DPPO2 demo nets, or as the comparison the tests check K-LEARN against).
 """
 from __future__ import annotations
 
@@ -23,6 +25,7 @@ import torch
 import torch.nn.functional as F
 
 from . import dist as _dist
+from .learn import FusedPPO2Update, fused_supported
 from .normalization import Normalization
 from .policy import GaussianPolicy, linear_layers
 from .rollout import RolloutBuffer
@@ -36,14 +39,16 @@ DEFAULT_PPO_MSG = {  # demonstration/PPO2/PPO2-4-CartPoleAngleOnly/train.py:141-
 
 class VecPPO2:
     def __init__(self, env, actor: torch.nn.Module, critic: torch.nn.Module, ppo_msg: Optional[dict] = None,
-                 std=None, reward_norm: bool = True, seed: int = 0, group=None, actor_out_act: Optional[str] = None):
+                 std=None, reward_norm: bool = True, seed: int = 0, group=None, actor_out_act: Optional[str] = None,
+                 learner: str = "auto"):
         """``env``: a vector env built with ``io_dtype=torch.float32, auto_reset=True``; ``actor`` / ``critic``: tanh
         MLPs on ``env.device`` (the reference's PPOActor_Gaussian / PPOCritic shapes, utils/classes.py:529-615);
         ``buffer_size`` of ``ppo_msg`` is the number of time steps T per rollout (T x N transitions per learn()).
         ``actor_out_act``: the head of ``actor.forward`` ("relu", "identity" or "tanh_range"); default: the module's own
         ``out_act`` attribute, else "relu" (PPOActor_Gaussian.forward, utils/classes.py:563-569).  The behaviour policy
         (K-POLICY in ``collect``) and the learner's ``actor(s)`` must use the same head, or the ratios are wrong.
-        ``std``: a float or one value per action dimension."""
+        ``std``: a float or one value per action dimension.
+        ``learner``: "fused" (K-LEARN, nets <= 64 wide), "torch" (autograd on the modules) or "auto" (fused if it fits)."""
         self.env, self.actor, self.critic, self.group = env, actor, critic, group
         m = dict(DEFAULT_PPO_MSG)
         m.update(ppo_msg or {})
@@ -59,11 +64,20 @@ class VecPPO2:
                                      env_index_offset=env.env_index_offset, actor_out_act=out_act)
         self.value_net = GaussianPolicy(None, linear_layers(critic), ar[:, 0], ar[:, 1], 1.0, device=env.device)
         eps = 1e-5 if m['set_adam_eps'] else 1e-8                                   # PPO2.py:50-55
-        self.optimizer_actor = torch.optim.Adam(actor.parameters(), lr=m['a_lr'], eps=eps)
-        self.optimizer_critic = torch.optim.Adam(critic.parameters(), lr=m['c_lr'], eps=eps)
-        self.reduce_actor = _dist.FlatGradAllReducer(actor.parameters(), group)
-        self.reduce_critic = _dist.FlatGradAllReducer(critic.parameters(), group)
         _dist.broadcast_parameters([actor, critic], 0, group)
+        if learner not in ("auto", "fused", "torch"):
+            raise ValueError("learner must be 'auto', 'fused' or 'torch'")
+        self.fused = None
+        if learner == "fused" or (learner == "auto" and fused_supported(actor, critic)):
+            self.fused = FusedPPO2Update(actor, critic, self.std, ar[:, 0], ar[:, 1], out_act, a_lr=m['a_lr'],
+                                         c_lr=m['c_lr'], adam_eps=eps, max_grad_norm=0.5 if m['use_grad_clip'] else 0.0,
+                                         eps_clip=m['eps_clip'], entropy_coef=m['entropy_coef'], group=group)
+        else:
+            self.optimizer_actor = torch.optim.Adam(actor.parameters(), lr=m['a_lr'], eps=eps)
+            self.optimizer_critic = torch.optim.Adam(critic.parameters(), lr=m['c_lr'], eps=eps)
+            self.reduce_actor = _dist.FlatGradAllReducer(actor.parameters(), group)
+            self.reduce_critic = _dist.FlatGradAllReducer(critic.parameters(), group)
+        self._epoch_key = (int(seed) * 0x9E3779B97F4A7C15 + 0x5851F42D4C957F2D) & (2 ** 64 - 1)
         self.reward_norm = Normalization(1, device=env.device, group=group) if reward_norm else None
         self.total_steps = 0
         self._raw_reward_sum = torch.zeros((), dtype=torch.float64, device=env.device)
@@ -104,6 +118,8 @@ class VecPPO2:
             vs = self.value_net(buf.s.permute(1, 0, 2).reshape(S, T * N).contiguous())["value"].view(T, N)
             vs_ = self.value_net(buf.s_.permute(1, 0, 2).reshape(S, T * N).contiguous())["value"].view(T, N)
             adv, v_target = buf.gae(vs, vs_, self.gamma, self.lmd, normalize=m['use_adv_norm'], group=self.group)
+            if self.fused is not None:
+                return self._learn_fused(adv, v_target)
             s, a, a_lp, _, _, _, _ = buf.to_tensor()
             adv, v_target = adv.reshape(T * N, 1), v_target.reshape(T * N, 1)
             a_lp_sum = a_lp.sum(1, keepdim=True)
@@ -144,7 +160,30 @@ class VecPPO2:
             self.lr_decay(self.total_steps)
         return {k: float(v) for k, v in last.items()}
 
+    def _learn_fused(self, adv, v_target) -> dict:
+        """The K_epochs x mini-batch loop on K-LEARN: mini-batches are consecutive slices of a keyed pseudo-random
+        permutation of the T x N samples (one key per epoch: every sample once per epoch, like BatchSampler over
+        SubsetRandomSampler, PPO2.py:104)."""
+        buf, m = self.buffer, self.msg
+        B = buf.batch_size * buf.n_envs
+        mb = min(m['mini_batch_size'], B) if m['using_mini_batch'] else B
+        n_mb = None
+        if _dist.dist.is_initialized() and _dist.dist.get_world_size(self.group) > 1:
+            n_mb = _dist.agree_min(-(-B // mb), self.group)
+        loss = self.fused.learn(buf.s, buf.a, buf.a_lp, adv, v_target, self.K_epochs, mb, self._epoch_key, n_mb)
+        self._epoch_key = (self._epoch_key + self.K_epochs) & (2 ** 64 - 1)
+        self.policy.refresh()            # K-POLICY multiplies from a packed copy of the weights
+        self.value_net.refresh()
+        if m['use_lr_decay']:
+            self.lr_decay(self.total_steps)
+        la, lc = loss.tolist()
+        return {"actor_loss": la, "critic_loss": lc}
+
     def lr_decay(self, total_steps):                                                 # PPO2.py:162-171
+        if total_steps < self.msg['max_train_steps'] and self.fused is not None:
+            f = 1 - total_steps / self.msg['max_train_steps']
+            self.fused.lr = [max(self.msg['a_lr'] * f, 1e-6), max(self.msg['c_lr'] * f, 1e-6)]
+            return
         if total_steps < self.msg['max_train_steps']:
             f = 1 - total_steps / self.msg['max_train_steps']
             for opt, lr in ((self.optimizer_actor, self.msg['a_lr']), (self.optimizer_critic, self.msg['c_lr'])):

@@ -62,6 +62,40 @@ def run(kind, reps=10, T=2048, N=131072, dev="cuda"):
         fn = lambda: pol(obs, action=outs["action"], log_prob=outs["log_prob"], value=outs["value"])
         flops = 2.0 * (S * 64 + 64 * 64 + 64 * 32 + 32 * A + S * 64 + 64 * 32 + 32)
         nbytes, units = (S + 2 * A + 1) * 4.0, n
+    elif kind in ("learn", "learn_torch"):
+        # one mini-batch of the PPO2 update on the reference nets (6-64-64-32-8 / 6-64-32-1) out of a 64 x 16384 rollout:
+        # K-LEARN (grad + reduce + clip/Adam launches) vs the torch autograd restatement of PPO2.py:102-131
+        from reinforcementlearningplatform_b200.learn import FusedPPO2Update
+        from reinforcementlearningplatform_b200.ppo2 import reference_nets
+        S, A, Tn, Nn, mb = 6, 8, 64, 16384, int(os.environ.get("MB", "16384"))
+        torch.manual_seed(0)
+        actor, critic = reference_nets(S, A, dev, init_std=0.45)
+        rn = lambda *sh: torch.randn(sh, generator=g, device=dev, dtype=torch.float32)
+        s, a, a_lp, adv, vt = rn(Tn, S, Nn), rn(Tn, A, Nn).abs(), -1.0 - rn(Tn, A, Nn).abs() * 0.1, rn(Tn, Nn), rn(Tn, Nn)
+        if kind == "learn":
+            upd = FusedPPO2Update(actor, critic, 0.45, [0.0] * A, [5.0] * A, "relu")
+            state = {"j": 0}
+            def fn():
+                upd.grad_step(s, a, a_lp, adv, vt, (state["j"] * mb) % (Tn * Nn - mb), mb, perm_key=7)
+                upd.adam_step()
+                state["j"] += 1
+        else:
+            import math
+            oa = torch.optim.Adam(actor.parameters(), lr=1e-4, eps=1e-5)
+            oc = torch.optim.Adam(critic.parameters(), lr=1e-3, eps=1e-5)
+            sf, af = s.permute(0, 2, 1).reshape(Tn * Nn, S), a.permute(0, 2, 1).reshape(Tn * Nn, A)
+            lpf, advf, vtf = a_lp.permute(0, 2, 1).reshape(Tn * Nn, A).sum(1, keepdim=True), adv.reshape(-1, 1), vt.reshape(-1, 1)
+            def fn():
+                idx = torch.randint(0, Tn * Nn, (mb,), device=dev)
+                mean = actor(sf[idx])
+                lp = -((af[idx] - mean) ** 2) / (2 * 0.45 ** 2) - math.log(0.45) - math.log(math.sqrt(2 * math.pi))
+                ratios = torch.exp(lp.sum(1, keepdim=True) - lpf[idx])
+                la = (-torch.min(ratios * advf[idx], torch.clamp(ratios, 0.8, 1.2) * advf[idx])).mean()
+                oa.zero_grad(); la.backward(); torch.nn.utils.clip_grad_norm_(actor.parameters(), 0.5); oa.step()
+                lc = torch.nn.functional.mse_loss(vtf[idx], critic(sf[idx]))
+                oc.zero_grad(); lc.backward(); torch.nn.utils.clip_grad_norm_(critic.parameters(), 0.5); oc.step()
+        flops = 3 * 2.0 * (S * 64 + 64 * 64 + 64 * 32 + 32 * A + S * 64 + 64 * 32 + 32)
+        nbytes, units = (S + 2 * A + 2) * 4.0, mb
     else:
         raise SystemExit(f"unknown kind {kind}")
     for _ in range(3):
@@ -78,6 +112,9 @@ def run(kind, reps=10, T=2048, N=131072, dev="cuda"):
            "algorithmic_bytes_per_element": nbytes, "achieved_gbs": nbytes * units / per / 1e9}
     if kind.startswith("policy"):
         res.update({"unit": "instances/s", "flops_per_instance": flops, "achieved_tflops_fp32": flops * units / per / 1e12})
+    if kind.startswith("learn"):
+        res.update({"unit": "samples/s", "flops_per_sample": flops, "achieved_tflops_fp32": flops * units / per / 1e12,
+                    "mini_batch": units})
     return res
 
 
