@@ -470,8 +470,11 @@ def also_workloads(args, dev, dtype, peaks):
     import microbench
     descs = {"gae_flags": "K-GAE over the device-resident rollout (u8 done, i32 flag)", "mc_returns": "PPO v1 Monte-Carlo returns",
              "norm": "running mean/std normalisation of a [6, 4 M] float32 batch (statistics + merge/apply)",
-             "policy": "actor 6-64-64-32-8 + critic 6-64-32-1 forward, sample, clamp, log-prob for 1 M instances (3xTF32 MMA)",
-             "policy_fp32": "the same forward on the FP32 FMA pipe"}
+             "policy": "actor 6-64-64-32-8 + critic 6-64-32-1 forward, sample, clamp, log-prob for 1 M instances (tcgen05 UMMA, activations in TMEM, 3xTF32 split)",
+             "policy_fp32": "the same forward on the FP32 FMA pipe",
+             "learn": "K-LEARN: one 16,384-sample mini-batch of the PPO2 update (both nets: forward, loss, backward, "
+                      "fixed-order reduction, clip + Adam) out of a 64 x 16,384 device rollout",
+             "learn_torch": "the same mini-batch update by torch autograd + torch.optim.Adam (round 1's learner)"}
     for kind, desc in descs.items():
         m = microbench.run(kind, 10, dev=dev)
         m["hbm_frac"] = m["achieved_gbs"] / hbm
@@ -526,15 +529,14 @@ def also_sharded(args, dev, dtype, world, rank, group_on):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for w in ("soi", "fas"):
-        T, N = 2048, 131072
+    for w, T, N, cfg in (("soi", 2048, 131072, "#3"), ("fas", 2048, 131072, "#3"), ("cartpole", 1000, 65536, "#2")):
         ms_roll, ms_gae = rollout_pipeline(w, N, T, dev, group_on, offset=rank * N)
         ms_roll, ms_gae = maxr(ms_roll), maxr(ms_gae)
         out.append({"workload": f"rollout_{w}", "T": T, "envs_per_gpu": N, "n_gpus": world,
-                    "value": world * T * N / ((ms_roll + ms_gae) * 1e-3), "unit": "env-steps/s", "ms_rollout": ms_roll,
-                    "ms_gae_allreduce_norm": ms_gae,
-                    "desc": f"config #3, {WORKLOADS[w]['desc']}: {T}-step rollout into the device buffer, K-GAE, 3-double "
-                            "all-reduce, normalise"})
+                    "value": world * T * N / ((ms_roll + ms_gae) * 1e-3), "rollout_value": world * T * N / (ms_roll * 1e-3),
+                    "unit": "env-steps/s", "ms_rollout": ms_roll, "ms_gae_allreduce_norm": ms_gae,
+                    "desc": f"config {cfg}, {WORKLOADS[w]['desc']}: {T}-step rollout into the device buffer by ONE "
+                            "b200env_rollout launch (state in registers), K-GAE, 3-double all-reduce, normalise"})
         torch.cuda.empty_cache()
     # config #5
     N, T = WORKLOADS["ugvo"]["n"], 16
@@ -563,6 +565,41 @@ def also_sharded(args, dev, dtype, world, rank, group_on):
                 "desc": "config #5: UGVForwardObstacleAvoidance (DPPO2 variant) x 41-256-256 nets; collect = K-POLICY + step "
                         "+ reward normalisation per time step; learn = K-GAE + statistics all-reduce + 6 full-batch epochs "
                         "(torch autograd) with one flat-gradient all-reduce per net and epoch"})
+    del agent, env, actor, critic
+    torch.cuda.empty_cache()
+    # a whole PPO2 iteration on config #4's env and the reference's nets, nothing but this repo's kernels between the
+    # first observation and the updated weights: collect (K-POLICY -> step kernel -> K-NORM, T steps) and learn (critic
+    # values by K-POLICY, K-GAE, statistics all-reduce, K_epochs x mini-batches of K-LEARN with one flat-gradient
+    # all-reduce per mini-batch when sharded)
+    from reinforcementlearningplatform_b200.ppo2 import reference_nets
+    N, T, K, mb = 1 << 18, 32, 4, 1 << 16
+    env = make_env("uav_pos", N, dev, rank * N, torch.float64, io_dtype=torch.float32)
+    env.reset(True)
+    actor, critic = reference_nets(env.state_dim, env.action_dim, dev, init_std=0.45)
+    agent = VecPPO2(env, actor, critic, {"buffer_size": T, "K_epochs": K, "mini_batch_size": mb, "use_lr_decay": False},
+                    std=0.45, seed=5)
+    assert agent.fused is not None
+    agent.collect()
+    agent.learn()
+    torch.cuda.synchronize()
+    if group_on:
+        dist.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    agent.collect()
+    ev[1].record()
+    agent.learn()
+    ev[2].record()
+    torch.cuda.synchronize()
+    ms_c, ms_l = maxr(ev[0].elapsed_time(ev[1])), maxr(ev[1].elapsed_time(ev[2]))
+    n_upd = K * (-(-T * N // mb))
+    out.append({"workload": "ppo2_iter_uav_pos", "T": T, "envs_per_gpu": N, "n_gpus": world, "K_epochs": K, "mini_batch": mb,
+                "value": world * T * N / ((ms_c + ms_l) * 1e-3), "collect_value": world * T * N / (ms_c * 1e-3),
+                "learn_samples_per_s": world * K * T * N / (ms_l * 1e-3), "unit": "env-steps/s", "ms_collect": ms_c,
+                "ms_learn": ms_l, "updates": n_upd, "us_per_update": ms_l * 1e3 / n_upd,
+                "desc": "config #4 env + the reference's 6-64-64-32-8 / 6-64-32-1 nets: one full PPO2 iteration on device; "
+                        "learn = K-POLICY critic values + K-GAE + K-LEARN (grad, reduce, clip + Adam launches per "
+                        "mini-batch, flat-gradient all-reduce in between when sharded); no torch autograd"})
     del agent, env, actor, critic
     torch.cuda.empty_cache()
     # config #4 variants

@@ -22,7 +22,7 @@ const Family *family(int env_id) {
     static Family table[B200ENV_COUNT] = {};
     static bool init = false;
     if (!init) {
-        table[B200ENV_CARTPOLE] = FAM(cartpole, b200_cartpole_params);
+        table[B200ENV_CARTPOLE] = FAMR(cartpole, b200_cartpole_params);
         table[B200ENV_UAV_ATT] = FAM(uav_att, b200_uav_params);
         table[B200ENV_UAV_POS] = FAM(uav_pos, b200_uav_params);
         table[B200ENV_FAS] = FAMR(fas, b200_fas_params);

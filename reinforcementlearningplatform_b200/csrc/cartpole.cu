@@ -9,6 +9,7 @@
 // registers for the whole control period (10|11 RK4 sub-steps of h = dt/10 for
 // variants 0/1 -- the reference's `while self.time < tt` loop on an fp64 time
 // accumulated with plain adds, note N1 -- or one step of size dt for variant 2).
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
@@ -104,23 +105,28 @@ __device__ __forceinline__ void store_state(const CartPole<T> &e, const b200env_
     io.time[i] = e.time;
 }
 
-template <typename T, bool IO32>
-__global__ void __launch_bounds__(B200_BLOCK)
-cartpole_step_kernel(const __grid_constant__ b200_cartpole_params p, const __grid_constant__ b200env_io io,
-                     int64_t n, uint32_t flags, uint64_t seed, int64_t off) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int obs_dim = p.variant == 0 ? 4 : 2;
+// Row pointers of one control period: the b200env_io buffers of a single step, or row t of a time-major rollout.
+struct StepRows {
+    const void *action;
+    void *obs, *next_obs, *reward;
+    uint8_t *done;
+    int32_t *flag;
+};
 
-    CartPole<T> e;
-    e.init_consts(p);
-    load_state(e, io, n, i);
-    e.force = ldio<T, IO32>(io.action, n, 0, i);
+// step_update(action) of one instance whose state is in `e` (registers): current_state, rk44, is_Terminal, next_state,
+// get_reward, stores of this step's outputs, auto-reset.  `ep` is the instance's episode counter (register copy).
+// On return nxt holds what the policy sees next (next_state, or the reset observation).
+template <typename T, bool IO32>
+__device__ __forceinline__ void cartpole_step_body(CartPole<T> &e, const b200_cartpole_params &p, const StepRows &r,
+                                                   int64_t n, int64_t i, uint32_t flags, uint64_t seed, int64_t off,
+                                                   uint32_t &ep, T (&nxt)[4]) {
+    const int obs_dim = p.variant == 0 ? 4 : 2;
+    e.force = ldio<T, IO32>(r.action, n, 0, i);
 
     T cur[4];
     e.observe(p, cur); // self.current_state = self.get_state()
-    if (io.obs) {
-        for (int k = 0; k < obs_dim; ++k) stio<T, IO32>(io.obs, n, k, i, cur[k]);
+    if (r.obs) {
+        for (int k = 0; k < obs_dim; ++k) stio<T, IO32>(r.obs, n, k, i, cur[k]);
     }
 
     // ---- rk44
@@ -157,7 +163,6 @@ cartpole_step_kernel(const __grid_constant__ b200_cartpole_params p, const __gri
         if (Mth<T>::sqrt(eth * eth + e.dtheta * e.dtheta) < (T)1e-2) { flag = 4; done = true; }
     }
 
-    T nxt[4];
     e.observe(p, nxt);
 
     // ---- get_reward
@@ -177,11 +182,11 @@ cartpole_step_kernel(const __grid_constant__ b200_cartpole_params p, const __gri
         // rad2deg(s[0] / staticGain * thetaMax) = (...) * 180. / np.pi
         const T ce = Mth<T>::abs(cur[0] / (T)p.static_gain * (T)p.theta_max * (T)180.0 / (T)M_PI);
         const T ne = Mth<T>::abs(nxt[0] / (T)p.static_gain * (T)p.theta_max * (T)180.0 / (T)M_PI);
-        T r = ne > ce ? (T)-2 : (ne == ce ? (T)0 : (T)2);
-        if (ce <= (T)0.5 && ne <= (T)0.5) r += (T)5;
-        if (flag == 1) r -= (T)100;
-        else if (flag == 3) r += (T)500;
-        reward = r;
+        T rr = ne > ce ? (T)-2 : (ne == ce ? (T)0 : (T)2);
+        if (ce <= (T)0.5 && ne <= (T)0.5) rr += (T)5;
+        if (flag == 1) rr -= (T)100;
+        else if (flag == 3) rr += (T)500;
+        reward = rr;
     } else { // cartpole_angleonly.py:170-195
         const T r1 = -(e.theta * e.theta) * (T)10;
         T r4 = (T)0;
@@ -192,18 +197,73 @@ cartpole_step_kernel(const __grid_constant__ b200_cartpole_params p, const __gri
         reward = r1 + r4;
     }
 
-    for (int k = 0; k < obs_dim; ++k) stio<T, IO32>(io.next_obs, n, k, i, nxt[k]);
-    stio<T, IO32>(io.reward, n, 0, i, reward);
-    io.done[i] = done ? 1 : 0;
-    io.flag[i] = flag;
+    for (int k = 0; k < obs_dim; ++k) stio<T, IO32>(r.next_obs, n, k, i, nxt[k]);
+    stio<T, IO32>(r.reward, n, 0, i, reward);
+    r.done[i] = done ? 1 : 0;
+    r.flag[i] = flag;
 
     if (done && (flags & B200ENV_AUTO_RESET)) {
-        const uint32_t ep = io.episode[i];
         e.reset(p, seed, (uint64_t)(off + i), ep);
-        io.episode[i] = ep + 1u;
+        ++ep;
         e.observe(p, nxt);
     }
+}
+
+template <typename T, bool IO32>
+__global__ void __launch_bounds__(B200_BLOCK)
+cartpole_step_kernel(const __grid_constant__ b200_cartpole_params p, const __grid_constant__ b200env_io io,
+                     int64_t n, uint32_t flags, uint64_t seed, int64_t off) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    CartPole<T> e;
+    e.init_consts(p);
+    load_state(e, io, n, i);
+    const bool ar = (flags & B200ENV_AUTO_RESET) != 0;
+    uint32_t ep = ar ? io.episode[i] : 0u;
+    const uint32_t ep0 = ep;
+    const StepRows r = {io.action, io.obs, io.next_obs, io.reward, io.done, io.flag};
+    T nxt[4];
+    cartpole_step_body<T, IO32>(e, p, r, n, i, flags, seed, off, ep, nxt);
+    if (ep != ep0) io.episode[i] = ep;
     if (io.reset_obs) {
+        const int obs_dim = p.variant == 0 ? 4 : 2;
+        for (int k = 0; k < obs_dim; ++k) stio<T, IO32>(io.reset_obs, n, k, i, nxt[k]);
+    }
+    store_state(e, io, n, i);
+}
+
+// b200env_rollout: rs.steps control periods in ONE launch, the four ODE states, time and the episode counter in
+// registers from the first step to the last (config #2: 65,536 instances x 1000 steps would otherwise pay 1000 launches
+// of a 19 us kernel, each re-reading and re-writing the state).  Row t of every time-major array is `stride` elements
+// after row t - 1 (b200env_rollout_spec).
+template <typename T, bool IO32>
+__global__ void __launch_bounds__(B200_BLOCK)
+cartpole_rollout_kernel(const __grid_constant__ b200_cartpole_params p, const __grid_constant__ b200env_io io,
+                        const __grid_constant__ b200env_rollout_spec rs, int64_t n, uint32_t flags, uint64_t seed,
+                        int64_t off) {
+    typedef typename std::conditional<IO32, float, T>::type TIO;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    CartPole<T> e;
+    e.init_consts(p);
+    load_state(e, io, n, i);
+    const bool ar = (flags & B200ENV_AUTO_RESET) != 0;
+    uint32_t ep = ar ? io.episode[i] : 0u;
+    const uint32_t ep0 = ep;
+    T nxt[4] = {};
+    for (int64_t t = 0; t < rs.steps; ++t) {
+        StepRows r;
+        r.action = static_cast<const TIO *>(io.action) + t * rs.action_stride;
+        r.obs = io.obs ? static_cast<TIO *>(io.obs) + t * rs.obs_stride : nullptr;
+        r.next_obs = static_cast<TIO *>(io.next_obs) + t * rs.next_obs_stride;
+        r.reward = static_cast<TIO *>(io.reward) + t * rs.reward_stride;
+        r.done = io.done + t * rs.done_stride;
+        r.flag = io.flag + t * rs.flag_stride;
+        cartpole_step_body<T, IO32>(e, p, r, n, i, flags, seed, off, ep, nxt);
+    }
+    if (ep != ep0) io.episode[i] = ep;
+    if (io.reset_obs) {
+        const int obs_dim = p.variant == 0 ? 4 : 2;
         for (int k = 0; k < obs_dim; ++k) stio<T, IO32>(io.reset_obs, n, k, i, nxt[k]);
     }
     store_state(e, io, n, i);
@@ -257,6 +317,22 @@ int cartpole_step(int dtype, int64_t n, const void *params, const b200env_io *io
     const int64_t want = (int64_t)b200_persistent_grid((int64_t)1 << 40, 8, 32);
     while (block > 32 && (n + block - 1) / block < want) block >>= 1;
     B200_LAUNCH_TIO(cartpole_step_kernel, b200_grid(n, block), block, s, p, *io, n, flags, seed, off);
+    return b200_check_launch();
+}
+
+int cartpole_rollout(int dtype, int64_t n, const void *params, const b200env_io *io, const b200env_rollout_spec *rs,
+                     uint32_t flags, uint64_t seed, int64_t off, cudaStream_t s) {
+    const b200_cartpole_params &p = *static_cast<const b200_cartpole_params *>(params);
+    if (p.variant < 0 || p.variant > 2) return B200ENV_EENV;
+    if (!io->state || !io->time || !io->action || !io->next_obs || !io->reward || !io->done || !io->flag)
+        return B200ENV_ENULL;
+    if ((flags & B200ENV_AUTO_RESET) && !io->episode) return B200ENV_ENULL;
+    // one launch for the whole rollout: the grid is sized for latency hiding, not for a short tail -- 32-thread blocks
+    // spread a small batch over every SM sub-partition
+    int block = B200_BLOCK;
+    const int64_t want = (int64_t)b200_persistent_grid((int64_t)1 << 40, 8, 32);
+    while (block > 32 && (n + block - 1) / block < want) block >>= 1;
+    B200_LAUNCH_TIO(cartpole_rollout_kernel, b200_grid(n, block), block, s, p, *io, *rs, n, flags, seed, off);
     return b200_check_launch();
 }
 

@@ -328,6 +328,7 @@ B200_FAMILY_DECL(fas_discrete)
 #define B200_FAMILY_ROLLOUT_DECL(name)                                                                          \
     int name##_rollout(int dtype, int64_t n, const void *params, const b200env_io *io,                          \
                        const b200env_rollout_spec *rs, uint32_t flags, uint64_t seed, int64_t off, cudaStream_t s);
+B200_FAMILY_ROLLOUT_DECL(cartpole)
 B200_FAMILY_ROLLOUT_DECL(fas)
 B200_FAMILY_ROLLOUT_DECL(soi)
 B200_FAMILY_ROLLOUT_DECL(ballbalancer)

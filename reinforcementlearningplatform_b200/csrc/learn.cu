@@ -55,7 +55,8 @@ struct LNet {
 
 struct LearnArgs {
     LNet net[2];                 // 0 actor, 1 critic
-    int net_of_y[2];             // blockIdx.y -> net
+    int net_of_y[2];             // slot -> net: blocks 0 .. nblk[0] - 1 work on slot 0, the next nblk[1] on slot 1
+    int nblk[2];
     int S, A;
     int64_t T, N, first, count;
     const float *s, *a, *a_lp, *adv, *v_target;
@@ -210,7 +211,9 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
     extern __shared__ __align__(16) float sm[];
     __shared__ int s_t[TM], s_i[TM];
     __shared__ float s_red[LT / 32];
-    const int net_id = A.net_of_y[blockIdx.y];
+    const int slot = (int)blockIdx.x >= A.nblk[0] ? 1 : 0;
+    const int bx = (int)blockIdx.x - (slot ? A.nblk[0] : 0), nbx = A.nblk[slot];
+    const int net_id = A.net_of_y[slot];
     const LNet &net = A.net[net_id];
     const int L = net.n_layers;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
     float *gout = sm + net.gout_off;
     const int pgo = LO.N + 4;
 
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int64_t tile = bx; tile < tiles; tile += nbx) {
         __syncthreads();   // the previous tile's last phase has finished with H and s_t / s_i
         if (tid < TM) {
             const int64_t j = tile * TM + tid;
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
     }
 
     // ---------------------------------------------------------------- this block's partial gradient
-    float *part = A.partial[net_id] + (size_t)blockIdx.x * (size_t)(net.P + 4);
+    float *part = A.partial[net_id] + (size_t)bx * (size_t)(net.P + 4);
 #pragma unroll
     for (int l = 0; l < LMAX; ++l) {
         if (l < L) {
@@ -398,7 +401,7 @@ struct ReduceArgs {
     float *grad[2];
     float *loss_out;
     int P[2], first_block[2];   // net j owns blocks first_block[j] .. of the launch
-    int nets, nblk;
+    int nets, nblk[2];
     float inv_count;
     // entropy bonus of the fixed-std Gaussian (a constant of the loss value): slot `ent_slot` (-1: none) gets
     // -entropy_coef * sum_d (0.5 + 0.5 log(2 pi) + log std_d), PPO2.py:107,116
@@ -415,14 +418,15 @@ __global__ void __launch_bounds__(256) ppo2_reduce_kernel(const __grid_constant_
     const float *base = a.partial[j] + p;
     float t = 0.0f;
     int b = 0;
-    for (; b + 8 <= a.nblk; b += 8) {
+    const int nblk = a.nblk[j];
+    for (; b + 8 <= nblk; b += 8) {
         float v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = __ldcg(base + (size_t)(b + q) * stride);
 #pragma unroll
         for (int q = 0; q < 8; ++q) t += v[q];
     }
-    for (; b < a.nblk; ++b) t += __ldcg(base + (size_t)b * stride);
+    for (; b < nblk; ++b) t += __ldcg(base + (size_t)b * stride);
     if (p < P) {
         a.grad[j][p] = t;
         return;
@@ -615,9 +619,25 @@ int launch_grad(Plan &pl, cudaStream_t stream) {
         configured[dev] = pl.smem;
     }
     const int64_t tiles = (pl.a.count + TM - 1) / TM;
-    const int cap = grid_cap() / pl.nets > 0 ? grid_cap() / pl.nets : 1;
-    dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)pl.nets);
-    ppo2_grad_kernel<<<grid, LT, pl.smem, stream>>>(pl.a);
+    // one block per SM; the SMs are dealt to the two nets in proportion to their work per sample (3 x sum K N), so that
+    // the actor's and the critic's blocks finish together (an even split left the critic's SMs idle 60 % of the time)
+    const int cap = grid_cap();
+    double work[2] = {0.0, 0.0};
+    for (int y = 0; y < pl.nets; ++y) {
+        const LNet &n = pl.a.net[pl.a.net_of_y[y]];
+        for (int l = 0; l < n.n_layers; ++l) work[y] += (double)n.L[l].K * n.L[l].N;
+        work[y] += 64.0;   // per-sample gather + loss
+    }
+    pl.a.nblk[1] = 0;
+    if (pl.nets == 2) {
+        int nb1 = (int)(cap * work[1] / (work[0] + work[1]) + 0.5);
+        nb1 = nb1 < 1 ? 1 : (nb1 > cap - 1 ? cap - 1 : nb1);
+        pl.a.nblk[0] = (int)(tiles < cap - nb1 ? tiles : cap - nb1);
+        pl.a.nblk[1] = (int)(tiles < nb1 ? tiles : nb1);
+    } else {
+        pl.a.nblk[0] = (int)(tiles < cap ? tiles : cap);
+    }
+    ppo2_grad_kernel<<<pl.a.nblk[0] + pl.a.nblk[1], LT, pl.smem, stream>>>(pl.a);
     ReduceArgs r = {};
     int blocks = 0;
     for (int y = 0; y < pl.nets; ++y) {
@@ -631,7 +651,7 @@ int launch_grad(Plan &pl, cudaStream_t stream) {
     // loss_out is indexed by net id (0 actor, 1 critic): with a single net present its slot is selected here
     r.loss_out = pl.a.loss_out + (pl.nets == 1 ? pl.a.net_of_y[0] : 0);
     r.nets = pl.nets;
-    r.nblk = (int)grid.x;
+    r.nblk[0] = pl.a.nblk[0]; r.nblk[1] = pl.a.nblk[1];
     r.inv_count = pl.a.inv_count;
     r.ent_slot = (pl.a.net_of_y[0] == 0 && pl.a.entropy_coef != 0.0f) ? 0 : -1;
     r.A = pl.a.A; r.ent_coef = pl.a.entropy_coef; r.std_ = pl.a.std_; r.std_vec = pl.a.std_vec;

@@ -115,8 +115,15 @@ class VecPPO2:
         T, N = buf.batch_size, buf.n_envs
         S, A = buf.state_dim, buf.action_dim
         with torch.no_grad():
-            vs = self.value_net(buf.s.permute(1, 0, 2).reshape(S, T * N).contiguous())["value"].view(T, N)
-            vs_ = self.value_net(buf.s_.permute(1, 0, 2).reshape(S, T * N).contiguous())["value"].view(T, N)
+            # V(s), V(s'): K-POLICY (critic only) row by row -- row t of the time-major buffer IS a [S, N] field-major
+            # observation block, so no transposed copy is made
+            if getattr(self, "_vs", None) is None or self._vs.shape != (T, N):
+                self._vs = torch.empty(T, N, dtype=torch.float32, device=buf.s.device)
+                self._vs_next = torch.empty_like(self._vs)
+            vs, vs_ = self._vs, self._vs_next
+            for t in range(T):
+                self.value_net(buf.s[t], value=vs[t])
+                self.value_net(buf.s_[t], value=vs_[t])
             adv, v_target = buf.gae(vs, vs_, self.gamma, self.lmd, normalize=m['use_adv_norm'], group=self.group)
             if self.fused is not None:
                 return self._learn_fused(adv, v_target)

@@ -60,9 +60,10 @@ def test_rollout_rows_equal_oracle_transitions(name, oracle_lib):
     assert torch.equal(s[n + 3], buf.s[1, :, 3])
 
 
-@pytest.mark.parametrize("name", ["soi", "fas_ppo2", "fas_discrete", "ugv_forward", "ballbalancer", "twolink", "cartpole", "uav_att_rand"])
+@pytest.mark.parametrize("name", ["soi", "fas_ppo2", "fas_discrete", "ugv_forward", "ballbalancer", "twolink", "cartpole",
+                                  "cartpole_angleonly_env", "cartpole_angleonly_ppo2", "uav_att_rand"])
 def test_rollout_collect_equals_step_by_step(name):
-    """b200env_rollout (fused multi-step kernel for the generic families, per-step launches for the others) fills the
+    """b200env_rollout (fused multi-step kernel for the generic families and CartPole, per-step launches for the others) fills the
     buffer with exactly the bits that T separate step calls produce, and leaves the env in the same state."""
     import torch
     from reinforcementlearningplatform_b200 import RolloutBuffer
