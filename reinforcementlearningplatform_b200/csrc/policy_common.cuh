@@ -23,6 +23,14 @@ int policy_umma_pack(const b200_mlp *actor, const b200_mlp *critic, void *worksp
 int policy_launch_umma(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const void *workspace, size_t bytes,
                        const PolicyIO &io, cudaStream_t s);
 int policy_umma_probe(const float *A, const float *W, float *D, int N, int K, int three_pass, cudaStream_t s);
+// policy_umma16.cu (tcgen05 / TMEM, fp16-split operands, four tiles in flight): the nets it holds (layers <= 64 wide,
+// <= 32 observation fields) are routed to it by the three policy_umma_* entry points above; B200_POLICY_UMMA16=0 in the
+// environment keeps them on policy_umma.cu (A/B runs)
+bool policy_umma16_fits(const b200_mlp *actor, const b200_mlp *critic);
+size_t policy_umma16_workspace_bytes(const b200_mlp *actor, const b200_mlp *critic);
+int policy_umma16_pack(const b200_mlp *actor, const b200_mlp *critic, void *workspace, size_t bytes, cudaStream_t s);
+int policy_launch_umma16(int64_t n, const b200_mlp *actor, const b200_mlp *critic, const void *workspace, size_t bytes,
+                         const PolicyIO &io, cudaStream_t s);
 
 // Philox key domain of the exploration noise.  The env resets draw from Philox(seed, instance, episode) (common.cuh); with
 // equal seeds the reset of (instance i, episode e) and the noise of (instance i, step e) would consume the same 128-bit
