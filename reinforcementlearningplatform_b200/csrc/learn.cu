@@ -43,6 +43,7 @@ struct LLayer {
     int w_off, b_off;    // shared-memory float offsets: weights [N][K + 4], bias [N]
     int h_off;           // shared-memory float offset of the layer's input H_l [TM][K + 4]
     int g_w, g_b;        // offsets of weight / bias inside the net's flat gradient
+    int rn, rk;          // register tile of the weight-gradient product (dw_layer)
     const float *w, *b;  // global parameters
 };
 
@@ -190,19 +191,48 @@ __device__ __forceinline__ void bwd_layer(const float *__restrict__ G, int pg, c
         }
 }
 
-// dW[4 ng .. +3][4 kg .. +3] += sum over the tile's samples of dZ[s][n] H[s][k]; db likewise for the kg == 0 threads
+// dW[RN ng .. ][RK kg .. ] += sum over the tile's samples of dZ[s][n] H[s][k]; db likewise for the kg == 0 threads.
+// The RN x RK register tile is chosen per layer (host: fill_net) so that ALL 256 threads share a layer's N x K entries:
+// 4 x 4 for 64 x 64, 2 x 4 for 32 x 64, 1 x 2 for 64 x 8, 1 x 1 for 8 x 32 -- with a fixed 4 x 4 tile the small layers
+// kept one or two warps busy for 128 iterations while the other warps waited at the barrier (ncu: stall_barrier 1.36 per
+// issued instruction, the largest stall of the first version).
+template <int RN, int RK>
 __device__ __forceinline__ void dw_layer(const float *__restrict__ G, int pg, const float *__restrict__ H, int ph, int ng,
                                          int kg, float (&dw)[16], float (&db)[4]) {
-    const float *gp = G + 4 * ng, *hp = H + 4 * kg;
+    const float *gp = G + RN * ng, *hp = H + RK * kg;
 #pragma unroll 4
     for (int s = 0; s < TM; ++s) {
-        const float4 g = *reinterpret_cast<const float4 *>(gp + s * pg);
-        const float4 h = *reinterpret_cast<const float4 *>(hp + s * ph);
-        dw[0] = fmaf(g.x, h.x, dw[0]);   dw[1] = fmaf(g.x, h.y, dw[1]);   dw[2] = fmaf(g.x, h.z, dw[2]);   dw[3] = fmaf(g.x, h.w, dw[3]);
-        dw[4] = fmaf(g.y, h.x, dw[4]);   dw[5] = fmaf(g.y, h.y, dw[5]);   dw[6] = fmaf(g.y, h.z, dw[6]);   dw[7] = fmaf(g.y, h.w, dw[7]);
-        dw[8] = fmaf(g.z, h.x, dw[8]);   dw[9] = fmaf(g.z, h.y, dw[9]);   dw[10] = fmaf(g.z, h.z, dw[10]); dw[11] = fmaf(g.z, h.w, dw[11]);
-        dw[12] = fmaf(g.w, h.x, dw[12]); dw[13] = fmaf(g.w, h.y, dw[13]); dw[14] = fmaf(g.w, h.z, dw[14]); dw[15] = fmaf(g.w, h.w, dw[15]);
-        if (kg == 0) { db[0] += g.x; db[1] += g.y; db[2] += g.z; db[3] += g.w; }
+        float g[RN], h[RK];
+        if (RN == 4) { const float4 t = *reinterpret_cast<const float4 *>(gp + s * pg); g[0] = t.x; g[1 % RN] = t.y; g[2 % RN] = t.z; g[3 % RN] = t.w; }
+        else if (RN == 2) { const float2 t = *reinterpret_cast<const float2 *>(gp + s * pg); g[0] = t.x; g[1 % RN] = t.y; }
+        else g[0] = gp[s * pg];
+        if (RK == 4) { const float4 t = *reinterpret_cast<const float4 *>(hp + s * ph); h[0] = t.x; h[1 % RK] = t.y; h[2 % RK] = t.z; h[3 % RK] = t.w; }
+        else if (RK == 2) { const float2 t = *reinterpret_cast<const float2 *>(hp + s * ph); h[0] = t.x; h[1 % RK] = t.y; }
+        else h[0] = hp[s * ph];
+#pragma unroll
+        for (int a = 0; a < RN; ++a)
+#pragma unroll
+            for (int c = 0; c < RK; ++c) dw[a * RK + c] = fmaf(g[a], h[c], dw[a * RK + c]);
+        if (kg == 0) {
+#pragma unroll
+            for (int a = 0; a < RN; ++a) db[a] += g[a];
+        }
+    }
+}
+
+// the thread's RN x RK entries of dW (and RN of db) -> this block's partial gradient, torch parameter layout
+template <int RN, int RK>
+__device__ __forceinline__ void dw_store(const LLayer &Ly, float *part, int ng, int kg, const float (&dw)[16],
+                                         const float (&db)[4]) {
+#pragma unroll
+    for (int a = 0; a < RN; ++a) {
+        const int n = RN * ng + a;
+        if (n < Ly.n_real) {
+#pragma unroll
+            for (int c = 0; c < RK; ++c)
+                if (RK * kg + c < Ly.k_real) part[Ly.g_w + n * Ly.k_real + RK * kg + c] = dw[a * RK + c];
+            if (kg == 0) part[Ly.g_b + n] = db[a];
+        }
     }
 }
 
@@ -210,6 +240,8 @@ __device__ __forceinline__ void dw_layer(const float *__restrict__ G, int pg, co
 __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant__ LearnArgs A) {
     extern __shared__ __align__(16) float sm[];
     __shared__ int s_t[TM], s_i[TM];
+    __shared__ float s_act[16 * TM], s_alp[16 * TM], s_tgt[TM];   // the tile's actions, old log-probs [d][s]; adv / v_target
+    __shared__ float s_cst[16][4];                                 // per action dimension: var, log std, gain, offset
     __shared__ float s_red[LT / 32];
     const int slot = (int)blockIdx.x >= A.nblk[0] ? 1 : 0;
     const int bx = (int)blockIdx.x - (slot ? A.nblk[0] : 0), nbx = A.nblk[slot];
@@ -230,6 +262,17 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
         for (int n = tid; n < Ly.N; n += LT) sm[Ly.b_off + n] = n < Ly.n_real ? __ldg(Ly.b + n) : 0.0f;
     }
 
+    if (net_id == 0 && tid < 16) {
+        const int d = tid;
+        const float sd = d < A.A ? (A.std_vec ? __ldg(A.std_vec + d) : A.std_) : 1.0f;
+        float gain = 1.0f, off2 = 0.0f;
+        if (net.out_act == 2 && d < A.A) {
+            const float lo = __ldg(A.a_min + d), hi = __ldg(A.a_max + d);
+            off2 = (lo + hi) / 2.0f;
+            gain = hi - off2;
+        }
+        s_cst[d][0] = sd * sd; s_cst[d][1] = logf(sd); s_cst[d][2] = gain; s_cst[d][3] = off2;
+    }
     float dw[LMAX][16], db[LMAX][4];
 #pragma unroll
     for (int l = 0; l < LMAX; ++l) {
@@ -268,6 +311,21 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
                 const int t = s_t[s];
                 H0[s * p0 + k] = (t >= 0 && k < A.S) ? __ldg(A.s + ((int64_t)t * A.S + k) * A.N + s_i[s]) : 0.0f;
             }
+            // the loss phase's inputs, fetched here so that their DRAM latency overlaps the forward pass
+            if (net_id == 0) {
+                for (int e = tid; e < TM * A.A; e += LT) {
+                    const int s = e & (TM - 1), d = e >> 7;
+                    const int t = s_t[s];
+                    const int64_t off = ((int64_t)(t < 0 ? 0 : t) * A.A + d) * A.N + s_i[s];
+                    s_act[d * TM + s] = t >= 0 ? __ldg(A.a + off) : 0.0f;
+                    s_alp[d * TM + s] = t >= 0 ? __ldg(A.a_lp + off) : 0.0f;
+                }
+            }
+            if (tid < TM) {
+                const int t = s_t[tid];
+                const float *src = net_id == 0 ? A.adv : A.v_target;
+                s_tgt[tid] = t >= 0 ? __ldg(src + (int64_t)t * A.N + s_i[tid]) : 0.0f;
+            }
         }
         __syncthreads();
         // ---------------------------------------------------------------- forward
@@ -289,51 +347,55 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
             }
         }
         // ---------------------------------------------------------------- loss and its gradient at the net's output
-        if (tid < TM) {
-            float *z = gout + tid * pgo;
-            const int t = s_t[tid], i = s_i[tid];
-            if (t < 0) {
-                for (int d = 0; d < LO.N; ++d) z[d] = 0.0f;
-            } else if (net_id == 0) {
+        {   // two threads per sample: thread `half` takes the action dimensions half, half + 2, ...
+            const int sx = tid >> 1, half = tid & 1;
+            float *z = gout + sx * pgo;
+            const bool live = s_t[sx] >= 0;
+            if (net_id == 0) {
                 // Normal(mean, std).log_prob(a) summed over dimensions, PPO2.py:106-112
                 float lp = 0.0f, lp_old = 0.0f;
-                float dm[16];   // d lp / d z_d
-#pragma unroll 1
-                for (int d = 0; d < A.A; ++d) {
-                    const int64_t off = ((int64_t)t * A.A + d) * A.N + i;
-                    const float act = __ldg(A.a + off);
-                    lp_old += __ldg(A.a_lp + off);
-                    const float sd = A.std_vec ? __ldg(A.std_vec + d) : A.std_;
-                    float m = z[d], dmdz = 1.0f;
-                    if (net.out_act == 1) {
-                        dmdz = m > 0.0f ? 1.0f : 0.0f;
-                        m = fmaxf(m, 0.0f);
-                    } else if (net.out_act == 2) {
-                        const float lo = __ldg(A.a_min + d), hi = __ldg(A.a_max + d);
-                        const float off2 = (lo + hi) / 2.0f, gain = hi - off2;
-                        const float th = tanhf(m);
-                        m = th * gain + off2;
-                        dmdz = gain * (1.0f - th * th);
+                float dm[8];   // d lp / d z_d of this thread's dimensions
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int d = 2 * q + half;
+                    dm[q] = 0.0f;
+                    if (d < A.A) {
+                        const float act = s_act[d * TM + sx], var = s_cst[d][0];
+                        lp_old += s_alp[d * TM + sx];
+                        float m = z[d], dmdz = 1.0f;
+                        if (net.out_act == 1) {
+                            dmdz = m > 0.0f ? 1.0f : 0.0f;
+                            m = fmaxf(m, 0.0f);
+                        } else if (net.out_act == 2) {
+                            const float th = tanhf(m), gain = s_cst[d][2];
+                            m = th * gain + s_cst[d][3];
+                            dmdz = gain * (1.0f - th * th);
+                        }
+                        const float diff = act - m;
+                        lp += -(diff * diff) / (2.0f * var) - s_cst[d][1] - 0.91893853320467274178f;
+                        dm[q] = diff / var * dmdz;
                     }
-                    const float diff = act - m, var = sd * sd;
-                    lp += -(diff * diff) / (2.0f * var) - logf(sd) - 0.91893853320467274178f;
-                    dm[d & 15] = diff / var * dmdz;
                 }
+                lp += __shfl_xor_sync(0xffffffffu, lp, 1);
+                lp_old += __shfl_xor_sync(0xffffffffu, lp_old, 1);
                 const float ratio = expf(lp - lp_old);
-                const float adv = __ldg(A.adv + (int64_t)t * A.N + i);
+                const float adv = s_tgt[sx];
                 const float lo = 1.0f - A.eps_clip, hi = 1.0f + A.eps_clip;
                 const float surr1 = ratio * adv, surr2 = fminf(fmaxf(ratio, lo), hi) * adv;
-                loss_acc += -fminf(surr1, surr2);
+                if (live && half == 0) loss_acc += -fminf(surr1, surr2);
                 // d(-min(surr1, surr2)) / d ratio: -adv unless the clamp is active and selected
                 const bool clamped = ratio < lo || ratio > hi;
                 const float dldr = (clamped && !(surr1 < surr2)) ? 0.0f : -adv;
-                const float c = dldr * ratio * A.inv_count;
-                for (int d = 0; d < LO.N; ++d) z[d] = d < A.A ? c * dm[d & 15] : 0.0f;
-            } else {
-                const float v = z[0], vt = __ldg(A.v_target + (int64_t)t * A.N + i);
-                const float e = v - vt;
-                loss_acc += e * e;
-                z[0] = 2.0f * e * A.inv_count;
+                const float c = live ? dldr * ratio * A.inv_count : 0.0f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int d = 2 * q + half;
+                    if (d < LO.N) z[d] = d < A.A ? c * dm[q] : 0.0f;
+                }
+            } else if (half == 0) {
+                const float e = z[0] - s_tgt[sx];
+                if (live) loss_acc += e * e;
+                z[0] = live ? 2.0f * e * A.inv_count : 0.0f;
                 for (int d = 1; d < LO.N; ++d) z[d] = 0.0f;
             }
         }
@@ -347,7 +409,19 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
                 float *H = sm + Ly.h_off;
                 const int pg = Ly.N + 4, ph = Ly.K + 4;
                 const int kgs = Ly.K >> 2;
-                if (tid < (Ly.N >> 2) * kgs) dw_layer(G, pg, H, ph, tid / kgs, tid % kgs, dw[l], db[l]);
+                {
+                    const int kt = Ly.K / Ly.rk, nt = Ly.N / Ly.rn;
+                    if (tid < nt * kt) {
+                        const int tn = tid / kt, tk = tid - tn * kt;
+                        switch (Ly.rn * 8 + Ly.rk) {
+                        case 4 * 8 + 4: dw_layer<4, 4>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
+                        case 2 * 8 + 4: dw_layer<2, 4>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
+                        case 1 * 8 + 4: dw_layer<1, 4>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
+                        case 1 * 8 + 2: dw_layer<1, 2>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
+                        default: dw_layer<1, 1>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
+                        }
+                    }
+                }
                 if (l > 0) {
                     __syncthreads();
                     if (kgs == 16) bwd_layer<2>(G, pg, sm + Ly.w_off, ph, Ly.N, H, ph, kgs, sg, ng);
@@ -364,18 +438,15 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
     for (int l = 0; l < LMAX; ++l) {
         if (l < L) {
             const LLayer &Ly = net.L[l];
-            const int kgs = Ly.K >> 2;
-            if (tid < (Ly.N >> 2) * kgs) {
-                const int n0 = 4 * (tid / kgs), k0 = 4 * (tid % kgs);
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const int n = n0 + a;
-                    if (n < Ly.n_real) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (k0 + c < Ly.k_real) part[Ly.g_w + n * Ly.k_real + k0 + c] = dw[l][4 * a + c];
-                        if (k0 == 0) part[Ly.g_b + n] = db[l][a];
-                    }
+            const int kt = Ly.K / Ly.rk, nt = Ly.N / Ly.rn;
+            if (tid < nt * kt) {
+                const int tn = tid / kt, tk = tid - tn * kt;
+                switch (Ly.rn * 8 + Ly.rk) {
+                case 4 * 8 + 4: dw_store<4, 4>(Ly, part, tn, tk, dw[l], db[l]); break;
+                case 2 * 8 + 4: dw_store<2, 4>(Ly, part, tn, tk, dw[l], db[l]); break;
+                case 1 * 8 + 4: dw_store<1, 4>(Ly, part, tn, tk, dw[l], db[l]); break;
+                case 1 * 8 + 2: dw_store<1, 2>(Ly, part, tn, tk, dw[l], db[l]); break;
+                default: dw_store<1, 1>(Ly, part, tn, tk, dw[l], db[l]); break;
                 }
             }
         }
@@ -516,6 +587,12 @@ int fill_net(const b200_mlp *m, bool is_actor, LNet *net) {
         Ly.g_w = P;
         Ly.g_b = P + in * out;
         P += in * out + out;
+        {   // entries per thread e = N K / 256 (>= 1), as RN x RK with RK the widest vector load that fits
+            int e = 1;   // the smallest power of two with N K / e <= 256 threads (N is a power of two, K a multiple of 8)
+            while (e < 16 && Ly.N * Ly.K > e * LT) e *= 2;
+            Ly.rk = e >= 4 ? 4 : e;
+            Ly.rn = e / Ly.rk;
+        }
         Ly.w_off = off; off += Ly.N * (Ly.K + 4);
         Ly.b_off = off; off += Ly.N;
     }
@@ -592,7 +669,7 @@ int make_plan(const b200_ppo2_batch *bt, const b200_mlp *actor, const b200_mlp *
     }
     if (ws > workspace_bytes) return B200ENV_ESIZE;
     pl->smem = smem_f * sizeof(float);
-    if (pl->smem > 227 * 1024 - 2048) return B200ENV_ESIZE;
+    if (pl->smem > 227 * 1024 - 20 * 1024) return B200ENV_ESIZE;   // 18.3 KB of static shared memory next to it
     a.T = bt->T; a.N = bt->N; a.first = bt->first; a.count = bt->count;
     a.s = bt->s; a.a = bt->a; a.a_lp = bt->a_lp; a.adv = bt->adv; a.v_target = bt->v_target;
     a.index = bt->index;
