@@ -412,7 +412,9 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
                 {
                     const int kt = Ly.K / Ly.rk, nt = Ly.N / Ly.rn;
                     if (tid < nt * kt) {
-                        const int tn = tid / kt, tk = tid - tn * kt;
+                        // tn runs fastest: the threads that also sum the bias gradient (tk == 0) are the first nt of
+                        // the block, so the other warps skip those adds (they were 5 % of all issued instructions)
+                        const int tk = tid / nt, tn = tid - tk * nt;
                         switch (Ly.rn * 8 + Ly.rk) {
                         case 4 * 8 + 4: dw_layer<4, 4>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
                         case 2 * 8 + 4: dw_layer<2, 4>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
             const LLayer &Ly = net.L[l];
             const int kt = Ly.K / Ly.rk, nt = Ly.N / Ly.rn;
             if (tid < nt * kt) {
-                const int tn = tid / kt, tk = tid - tn * kt;
+                const int tk = tid / nt, tn = tid - tk * nt;
                 switch (Ly.rn * 8 + Ly.rk) {
                 case 4 * 8 + 4: dw_store<4, 4>(Ly, part, tn, tk, dw[l], db[l]); break;
                 case 2 * 8 + 4: dw_store<2, 4>(Ly, part, tn, tk, dw[l], db[l]); break;
