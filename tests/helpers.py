@@ -202,15 +202,26 @@ def smoke_cases():
     return ["cartpole", "uav_att", "uav_pos"]
 
 
-# fp64 tolerance of the free-running engine-vs-oracle comparison (mixed metric), per fixture family
+# fp64 tolerance (mixed metric |a - b| / max(1, |b|)) of (i) the free-running replay of the reference fixtures and (ii) the
+# engine-vs-oracle comparison on seeded random inputs (8192 instances x 60 steps with Philox auto-resets), per fixture.
+# About 10x the larger of the two values measured on B200 (tools/tolerance_report.py, tests/parity_report.py; round 2:
+# cartpole 1.3e-13, fas / soi <= 7e-15, ballbalancer 1.6e-13, ugv 7e-14, uav_att 1.7e-14, uav_pos 3.8e-9 on the lane whose
+# gains are redrawn every step -- profiles/r2/drift.md -- and 1.5e-11 on the wide / dis fixtures, uavr 7e-13, ugvo laser
+# ranges 4.3e-10: the reference's line / circle intersection is ill-conditioned on steep rays, test_engine_gpu.py).
+# twolink: chaotic arm, 1.7e-8 over the stretches the reference itself reproduces.
 ENGINE_TOL = {
-    "cartpole": 1e-9, "cartpole_gentle": 1e-9, "cartpole_wide": 1e-9, "cartpole_angleonly_env": 1e-9, "cartpole_angleonly_ppo2": 1e-9,
-    "uav_pos": 1e-7, "uav_pos_dis": 1e-9, "uav_pos_wide": 1e-7, "uav_pos_rp0": 1e-7, "uav_pos_crash": 1e-9, "uav_pos_edge": 1e-9,
-    "uav_att": 1e-9, "uav_att_rand": 1e-9, "uav_att_edge": 1e-9,
-    "fas": 1e-9, "fas_ppo2": 1e-9, "fas_discrete": 1e-9, "soi": 1e-9, "soi_dppo2": 1e-9, "ballbalancer": 1e-9, "twolink": 1e-5,
-    "ugv_forward": 1e-9, "ugv_bidirectional": 1e-9, "ugvo": 1e-9, "ugvo_dppo2": 1e-9,
-    "uavr_hover_outer": 1e-7, "uavr_hover": 1e-7, "uavr_inner": 1e-7, "uavr_tracking": 1e-7,
+    "cartpole": 2e-12, "cartpole_gentle": 2e-11, "cartpole_wide": 2e-12, "cartpole_angleonly_env": 2e-12, "cartpole_angleonly_ppo2": 2e-12,
+    "uav_pos": 5e-8, "uav_pos_dis": 2e-10, "uav_pos_wide": 2e-10, "uav_pos_rp0": 5e-10, "uav_pos_crash": 5e-11, "uav_pos_edge": 5e-11,
+    "uav_att": 2e-13, "uav_att_rand": 2e-13, "uav_att_edge": 2e-13,
+    "fas": 1e-13, "fas_ppo2": 1e-13, "fas_discrete": 1e-13, "soi": 1e-13, "soi_dppo2": 1e-13, "ballbalancer": 2e-12, "twolink": 2e-7,
+    "ugv_forward": 1e-12, "ugv_bidirectional": 1e-12, "ugvo": 2e-9, "ugvo_dppo2": 2e-9,
+    "uavr_hover_outer": 2e-12, "uavr_hover": 1e-11, "uavr_inner": 2e-12, "uavr_tracking": 2e-12,
 }
+# Share of (step, lane) samples of a free-running replay that must stay comparable (lanes are dropped until their next
+# reset once the reference's own one-ulp drift exceeds 1e-11).  A fixture that falls below its share fails instead of
+# passing on an empty comparison.
+MIN_LIVE = {"twolink": 0.5, "ugvo_dppo2": 0.4}
+MIN_LIVE_DEFAULT = 0.95
 
 
 def engine_vs_oracle(name, n, steps, seed, dtype=None, auto_reset=True, tol=None, offset=0, io_dtype=None):

@@ -17,6 +17,10 @@ pytestmark = pytest.mark.gpu
 # fixture family (helpers.env_specs / ENGINE_TOL key) for each recorded adapter, and the share of (step, lane) samples that
 # must stay comparable in free-running mode (the rest are lanes past the chaos cut-off: their self-drift exceeds 1e-11)
 CASES = {"cartpole": ("cartpole", 0.5), "uav_att_rand": ("uav_att_rand", 0.99), "uav_pos_dis": ("uav_pos_dis", 0.9)}
+# free-running ceilings over 64 fresh seeds, ~10x the values measured on B200 (cartpole 5.9e-14, uav_att_rand 2.4e-14,
+# uav_pos_dis 7.4e-10 .. 4.0e-9 depending on the seed: the worst of 64 lanes is a lane whose redrawn gains amplify a
+# last-bit difference ~1e7-fold, profiles/r2/drift.md -- the reference's own one-ulp twin drifts 1e-8 there)
+LIVE_TOL = {"cartpole": 2e-12, "uav_att_rand": 2e-13, "uav_pos_dis": 5e-8}
 
 
 def _have_reference():
@@ -42,6 +46,6 @@ def test_64_seeds_1000_steps_against_the_live_reference(adapter):
     assert res["live_fraction"] >= live_min, (adapter, res["live_fraction"])
     assert res["worst_ratio"] <= 1.0, res
     for k, v in res["worst"].items():
-        assert v <= ENGINE_TOL[family], (adapter, k, v)
+        assert v <= LIVE_TOL[adapter], (adapter, k, v)
     print(f"{adapter}: 64 x 1000 live-reference lanes, one-step <= 1e-12, free-running worst state "
           f"{res['worst']['state']:.1e} (median lane {np.median(res['lane_state']):.1e}), live {res['live_fraction']:.2f}")
