@@ -472,6 +472,8 @@ def also_workloads(args, dev, dtype, peaks):
              "norm": "running mean/std normalisation of a [6, 4 M] float32 batch (statistics + merge/apply)",
              "policy": "actor 6-64-64-32-8 + critic 6-64-32-1 forward, sample, clamp, log-prob for 1 M instances (tcgen05 UMMA, activations in TMEM, 3xTF32 split)",
              "policy_fp32": "the same forward on the FP32 FMA pipe",
+             "gae_small_seq": "K-GAE on the reference's own rollout shape (T = 2048, 8 columns): one thread per column, 2048 dependent steps",
+             "gae_small_scan": "the same with acc_mode 2: warp-level scan along time (32 steps per trip composed by shuffles)",
              "learn": "K-LEARN: one 16,384-sample mini-batch of the PPO2 update (both nets: forward, loss, backward, "
                       "fixed-order reduction, clip + Adam) out of a 64 x 16,384 device rollout",
              "learn_torch": "the same mini-batch update by torch autograd + torch.optim.Adam (round 1's learner)"}

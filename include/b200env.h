@@ -368,7 +368,10 @@ B200_API int b200env_observe(int env_id, int dtype, int64_t n_envs,
  * the reference's RolloutBuffer (utils/classes.py:250-301).
  *   delta = r + gamma * (1 - success) * vs_next - vs;  gae_t = delta_t + gamma * lmd * gae_{t+1} * (1 - done_t)
  *   adv = gae;  v_target = adv + vs
- * acc_mode 0: float32 sequential, bit-identical to the reference loop under numpy >= 2; 1: float64 carry (numpy 1.x).
+ * acc_mode 0: float32 sequential, bit-identical to the reference loop under numpy >= 2; 1: float64 carry (numpy 1.x);
+ * 2: the float64-carry scan evaluated as a warp-level parallel scan along time (one warp per column, 32 time steps per
+ *    trip composed by shuffles): for rollouts with few columns -- the reference's own shape is N = 1 -- where one thread
+ *    per column leaves the GPU empty; equal to mode 1 up to float64 reassociation (<= 1 float32 ulp in the outputs).
  * stats (device double[3], may be NULL) is INCREMENTED by (sum adv, sum adv^2, T * N): zero it first; all-reduce it
  * over ranks for a global advantage normalisation.  scratch (device, 8-byte aligned, b200_gae_scratch_bytes(N) bytes,
  * may be NULL): with it the sums are reduced in a fixed order -- the same bits on every run; without it the per-block

@@ -133,6 +133,74 @@ gae_kernel(int64_t T, int64_t N, const float *__restrict__ r, const float *__res
     }
 }
 
+// acc_mode 2: the same recurrence as a warp-level scan ALONG TIME, for rollouts with few columns (the reference's own
+// shape is N = 1, T = 1000 .. 2048: one thread per column would walk 2048 dependent steps on one lane of one SM).  One
+// warp owns a column; lane l of a trip holds time step hi - l with the affine map g -> b + a g (a = gamma lmd (1 - done),
+// b = delta, delta rounded in float32 exactly like the reference); five shuffle steps compose the 32 maps (Kogge-Stone,
+// the operator is associative), the carry g_{hi+1} enters at the end: T / 32 trips instead of T dependent steps.  The
+// composition runs in float64, so the result is the float64-carry scan (acc_mode 1, numpy 1.x behaviour, note N12) up to
+// float64 reassociation (~1e-15 relative), i.e. within one float32 ulp of it after the final rounding.
+constexpr int SCAN_WARPS = 4;
+template <class Masks>
+__global__ void __launch_bounds__(SCAN_WARPS * 32)
+gae_scan_kernel(int64_t T, int64_t N, const float *__restrict__ r, const float *__restrict__ vs,
+                const float *__restrict__ vsn, const Masks mk, float g32, double gl64, float *__restrict__ adv,
+                float *__restrict__ vt, double *stats, double *partial) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t n = (int64_t)blockIdx.x * SCAN_WARPS + w;
+    double s1 = 0.0, s2 = 0.0;
+    if (n < N) {
+        double carry = 0.0;
+        for (int64_t hi = T - 1; hi >= 0; hi -= 32) {
+            const int64_t t = hi - lane;
+            const bool valid = t >= 0;
+            const int64_t idx = (valid ? t : 0) * N + n;
+            const float v0 = vs[idx];
+            float dn, sc;
+            mk.load(idx, dn, sc);
+            const float delta = __fsub_rn(__fadd_rn(r[idx], __fmul_rn(__fmul_rn(g32, __fsub_rn(1.0f, sc)), vsn[idx])), v0);
+            double a = valid ? gl64 * (1.0 - (double)dn) : 1.0, b = valid ? (double)delta : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {          // (a, b) of lanes 0 .. l composed: g(l) = b + a * g(-1)
+                const double ap = __shfl_up_sync(0xffffffffu, a, o), bp = __shfl_up_sync(0xffffffffu, b, o);
+                if (lane >= o) {
+                    b = b + a * bp;
+                    a = a * ap;
+                }
+            }
+            const double g = b + a * carry;
+            carry = __shfl_sync(0xffffffffu, g, 31);
+            if (valid) {
+                const float af = (float)g;
+                adv[idx] = af;
+                vt[idx] = __fadd_rn(af, v0);
+                s1 += (double)af;
+                s2 += (double)af * (double)af;
+            }
+        }
+    }
+    if (stats) {
+        __shared__ double sh1[SCAN_WARPS], sh2[SCAN_WARPS];
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) { sh1[w] = s1; sh2[w] = s2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0, b = 0;
+#pragma unroll
+            for (int k = 0; k < SCAN_WARPS; ++k) { a += sh1[k]; b += sh2[k]; }
+            if (partial) {
+                partial[2 * (int64_t)blockIdx.x] = a;
+                partial[2 * (int64_t)blockIdx.x + 1] = b;
+            } else {
+                atomicAdd(stats + 0, a);
+                atomicAdd(stats + 1, b);
+                if (blockIdx.x == 0) atomicAdd(stats + 2, (double)T * (double)N);
+            }
+        }
+    }
+}
+
 // fixed-order sum of the per-block partials: thread k adds partials k, k + 256, ... sequentially, then the 256 thread sums
 // are combined by a fixed shared-memory tree; one thread increments stats
 __global__ void __launch_bounds__(256) gae_stats_reduce_kernel(int64_t blocks, const double *__restrict__ partial,
@@ -220,14 +288,17 @@ template <class Masks>
 int gae_launch(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next, const Masks &mk, double gamma,
                double lmd, int acc_mode, float *adv, float *v_target, double *stats, void *scratch, size_t scratch_bytes,
                cudaStream_t s) {
-    const unsigned grid = (unsigned)((N + GAE_BLOCK - 1) / GAE_BLOCK);
+    if (acc_mode < 0 || acc_mode > 2) return B200ENV_EPARAMS;
+    const unsigned grid = acc_mode == 2 ? (unsigned)((N + SCAN_WARPS - 1) / SCAN_WARPS) : (unsigned)((N + GAE_BLOCK - 1) / GAE_BLOCK);
     const float g32 = (float)gamma, gl32 = (float)(gamma * lmd);
     double *partial = nullptr;
     if (stats && scratch) {
         if (scratch_bytes < (size_t)grid * 2 * sizeof(double) || ((uintptr_t)scratch & 7)) return B200ENV_EPARAMS;
         partial = static_cast<double *>(scratch);
     }
-    if (acc_mode == 0)
+    if (acc_mode == 2)
+        gae_scan_kernel<Masks><<<grid, SCAN_WARPS * 32, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gamma * lmd, adv, v_target, stats, partial);
+    else if (acc_mode == 0)
         gae_kernel<false, Masks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats, partial);
     else
         gae_kernel<true, Masks><<<grid, GAE_BLOCK, 0, s>>>(T, N, r, vs, vs_next, mk, g32, gl32, gamma * lmd, adv, v_target, stats, partial);
@@ -237,7 +308,7 @@ int gae_launch(int64_t T, int64_t N, const float *r, const float *vs, const floa
 } // namespace
 
 extern "C" B200_API size_t b200_gae_scratch_bytes(int64_t N) {
-    return N <= 0 ? 0 : (size_t)((N + GAE_BLOCK - 1) / GAE_BLOCK) * 2 * sizeof(double);
+    return N <= 0 ? 0 : (size_t)((N + SCAN_WARPS - 1) / SCAN_WARPS) * 2 * sizeof(double);   // the finest grid (acc_mode 2)
 }
 
 extern "C" B200_API int b200_gae(int64_t T, int64_t N, const float *r, const float *vs, const float *vs_next,

@@ -100,3 +100,27 @@ def test_advantage_statistics_are_bit_reproducible_and_normalisation_divides():
     want = ((adv - np.float32(mean)) / np.float32(np.float32(std) + np.float32(1e-5))).clone()
     G.normalize_advantage(adv, st.clone())
     assert torch.equal(adv, want) or float((adv - want).abs().max()) <= 2.5e-7 * float(want.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,N", [(2048, 1), (1000, 7), (77, 130), (33, 4)])
+def test_warp_scan_along_time_matches_float64_carry_scan(T, N):
+    """acc_mode 2 (warp-level scan along time, for few columns) against acc_mode 1 (sequential float64 carry): outputs
+    within one float32 ulp, statistics within 1e-12 relative; episode boundaries (done) and success flags exercised."""
+    import torch
+    from reinforcementlearningplatform_b200 import gae as G
+    g = torch.Generator(device="cuda").manual_seed(T * 1000 + N)
+    mk = lambda: torch.randn((T, N), generator=g, device="cuda", dtype=torch.float32)
+    r, vs, vsn = mk(), mk(), mk()
+    dn = torch.rand((T, N), generator=g, device="cuda") < 0.03
+    succ = (dn & (torch.rand((T, N), generator=g, device="cuda") < 0.5)).float()
+    done = dn.float()
+    a1, v1, s1 = G.gae(r, vs, vsn, done, succ, 0.99, 0.95, acc_mode=1)
+    a2, v2, s2 = G.gae(r, vs, vsn, done, succ, 0.99, 0.95, acc_mode=2)
+    ulp = lambda x: torch.maximum(x.abs(), torch.tensor(1e-30, device="cuda")) * 2.0 ** -23
+    assert bool(((a1 - a2).abs() <= ulp(a1)).all()) and bool(((v1 - v2).abs() <= ulp(v1)).all())
+    assert float((a1 != a2).float().mean()) < 0.01            # all but a handful of roundings agree exactly
+    assert torch.allclose(s1, s2, rtol=1e-9, atol=1e-9) and float(s2[2]) == T * N
+    # and against the float32-sequential reference order: within the 1e-5 relative band of note N12
+    a0, _, _ = G.gae(r, vs, vsn, done, succ, 0.99, 0.95, acc_mode=0)
+    assert float(((a0 - a2).abs() / torch.clamp(a0.abs(), min=1.0)).max()) <= 1e-5

@@ -28,6 +28,14 @@ def run(kind, reps=10, T=2048, N=131072, dev="cuda"):
         else:
             fn, nbytes = (lambda: G.mc_returns(r, done_u8, 0.99)), 9.0
         units = T * N
+    elif kind in ("gae_small_seq", "gae_small_scan"):
+        # the reference's own rollout shape (one env, T = 2048) and a handful of envs: sequential column walk vs warp scan
+        Ts, Ns = 2048, int(os.environ.get("GAE_N", "8"))
+        mk2 = lambda: torch.randn((Ts, Ns), generator=g, device=dev, dtype=torch.float32)
+        r, vs, vsn = mk2(), mk2(), mk2()
+        done = (torch.rand((Ts, Ns), generator=g, device=dev) < 0.002).float()
+        mode = 2 if kind == "gae_small_scan" else 1
+        fn, nbytes, units = (lambda: G.gae(r, vs, vsn, done, done, 0.99, 0.95, acc_mode=mode)), 28.0, Ts * Ns
     elif kind == "norm":
         dim, n = 6, 1 << 22  # 6 x 4 M float32 = 100 MB per pass: larger than what L2 keeps between the two kernels
         x = torch.randn((dim, n), generator=g, device=dev, dtype=torch.float32)
