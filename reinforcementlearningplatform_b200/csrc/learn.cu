@@ -5,19 +5,23 @@
 // clip_grad_norm_, Adam; critic forward, mse_loss, backward, clip, Adam -- which round 1 left to torch autograd (about
 // forty library kernels per mini-batch, 0.24 s per learn() of 4096 x 64 samples against 8 ms for collecting them).
 //
-// ppo2_grad_kernel: one block works on 128-sample tiles of the mini-batch; blockIdx.y selects the net (actor / critic),
-// so both nets' gradients come out of ONE launch.  Everything of a tile stays in shared memory:
-//     H_l [128][K_l + 4]   input of layer l (H_0 = the gathered observations, H_l = tanh outputs), sample-major;
+// ppo2_grad_kernel: one block works on 64-sample tiles of the mini-batch, two blocks per SM; the SMs' blocks are dealt to
+// the two nets (actor / critic) in proportion to their measured cost per tile, so both nets' gradients come out of ONE
+// launch.  Everything of a tile stays in shared memory:
+//     H_l [64][K_l + 4]    input of layer l (H_0 = the gathered observations, H_l = tanh outputs), sample-major;
 //     W_l [N_l][K_l + 4]   the layer's weights as nn.Linear stores them (zero-padded), loaded once per block;
 // and the three products of a layer are register-tiled fp32 GEMMs whose operands are both read along their contiguous
 // index with 16-byte loads (row pitch = width + 4 floats, so that the rows a warp touches fall into distinct banks):
-//     forward   Z[s][n]  = sum_k H_l[s][k] W_l[n][k]          thread: 4 samples x (N/8) outputs, 12 LDS.128 per 128 FFMA
-//     dW        dW[n][k] = sum_s dZ_l[s][n] H_l[s][k]         thread: 4 x 4 entries, kept in REGISTERS across all tiles
-//     dH        dH[s][k] = sum_n dZ_l[s][n] W_l[n][k]         thread: 4 samples x (K/32) 4-vectors
+//     forward   Z[s][n]  = sum_k H_l[s][k] W_l[n][k]          thread: 2 samples x (N/8) outputs
+//     dW        dW[n][k] = sum_s dZ_l[s][n] H_l[s][k]         thread: RN x RK entries (4 x 4 for 64 x 64 .. 1 x 1 for 8 x 32:
+//                                                             all 256 threads share every layer), added to the block's
+//                                                             partial gradient (L2) once per tile by the thread that owns them
+//     dH        dH[s][k] = sum_n dZ_l[s][n] W_l[n][k]         thread: 2 samples x (K/32) 4-vectors
 // dZ_{l-1} = dH * (1 - H_l^2) overwrites H_l in place (its last reader was dW_l), so no separate gradient buffers exist.
-// A block adds up its tiles in program order and stores its partial gradient once; ppo2_reduce_kernel (a second, wide
-// launch: one thread per parameter) sums the partials in block order: the result does not depend on scheduling (no
-// floating-point atomics anywhere).
+// A block adds up its tiles in program order; ppo2_reduce_kernel (a second, wide launch: one thread per parameter) sums
+// the per-block partials in block order: the result does not depend on scheduling (no floating-point atomics anywhere).
+// History (profiles/r2/learn.md): 128-sample tiles with the weight gradients in 80 persistent registers and one block per
+// SM measured the same at large batches and 25 % slower at 4096 samples (half as many tiles to spread over the SMs).
 //
 // adam_kernel: clip_grad_norm_ + Adam.step over flat parameter / gradient / moment buffers (one segment per net), the
 // global norm recomputed in a fixed order by every block so that no grid-wide synchronisation is needed.
@@ -32,10 +36,13 @@
 namespace {
 
 constexpr int LT = 256;     // threads per block
-constexpr int TM = 128;     // samples per tile
+constexpr int TM = 64;      // samples per tile
+constexpr int TM_LOG2 = 6;
+constexpr int MI = TM / 32; // samples per thread in the sample-by-feature products
+constexpr int BLOCKS_PER_SM = 2;
 constexpr int LMAX = 4;     // layers per net
 constexpr int WMAX = 64;    // widest layer / input
-constexpr int GRID_CAP = 148;
+constexpr int GRID_CAP = 148 * BLOCKS_PER_SM;
 
 struct LLayer {
     int K, N;            // padded: K to a multiple of 8, N to 8 / 16 / 32 / 64
@@ -111,21 +118,21 @@ template <int NJ>
 __device__ __forceinline__ void fwd_layer(const float *__restrict__ H, int ph, const float *__restrict__ W, int pw,
                                           const float *__restrict__ bias, int K, float *__restrict__ out, int po,
                                           bool hidden, int sg, int ng) {
-    float acc[4][NJ];
+    float acc[MI][NJ];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0f;
     const float *hp = H + sg * ph, *wp = W + ng * pw;
     for (int k0 = 0; k0 < K; k0 += 4) {
-        float4 a[4];
+        float4 a[MI];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(hp + 32 * i * ph + k0);
+        for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const float4 *>(hp + 32 * i * ph + k0);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const float4 w = *reinterpret_cast<const float4 *>(wp + 8 * j * pw + k0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < MI; ++i) {
                 acc[i][j] = fmaf(a[i].x, w.x, acc[i][j]);
                 acc[i][j] = fmaf(a[i].y, w.y, acc[i][j]);
                 acc[i][j] = fmaf(a[i].z, w.z, acc[i][j]);
@@ -137,7 +144,7 @@ __device__ __forceinline__ void fwd_layer(const float *__restrict__ H, int ph, c
     for (int j = 0; j < NJ; ++j) {
         const float b = bias[ng + 8 * j];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < MI; ++i) {
             const float z = acc[i][j] + b;
             out[(sg + 32 * i) * po + ng + 8 * j] = hidden ? tanhf(z) : z;
         }
@@ -149,16 +156,16 @@ template <int NV>
 __device__ __forceinline__ void bwd_layer(const float *__restrict__ G, int pg, const float *__restrict__ W, int pw, int N,
                                           float *H, int ph, int KG, int sg, int ng) {
     if (ng >= KG) return;
-    float4 acc[4][NV];
+    float4 acc[MI][NV];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int jv = 0; jv < NV; ++jv) acc[i][jv] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float *gp = G + sg * pg, *wp = W + 4 * ng;
     for (int n0 = 0; n0 < N; n0 += 4) {
-        float g[4][4];
+        float g[MI][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < MI; ++i) {
             const float4 t = *reinterpret_cast<const float4 *>(gp + 32 * i * pg + n0);
             g[i][0] = t.x; g[i][1] = t.y; g[i][2] = t.z; g[i][3] = t.w;
         }
@@ -168,7 +175,7 @@ __device__ __forceinline__ void bwd_layer(const float *__restrict__ G, int pg, c
             for (int jv = 0; jv < NV; ++jv) {
                 const float4 w = *reinterpret_cast<const float4 *>(wp + (n0 + q) * pw + 32 * jv);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < MI; ++i) {
                     acc[i][jv].x = fmaf(g[i][q], w.x, acc[i][jv].x);
                     acc[i][jv].y = fmaf(g[i][q], w.y, acc[i][jv].y);
                     acc[i][jv].z = fmaf(g[i][q], w.z, acc[i][jv].z);
@@ -177,7 +184,7 @@ __device__ __forceinline__ void bwd_layer(const float *__restrict__ G, int pg, c
             }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int jv = 0; jv < NV; ++jv) {
             float4 *hp = reinterpret_cast<float4 *>(H + (sg + 32 * i) * ph + 4 * ng + 32 * jv);
@@ -221,23 +228,53 @@ __device__ __forceinline__ void dw_layer(const float *__restrict__ G, int pg, co
 }
 
 // the thread's RN x RK entries of dW (and RN of db) -> this block's partial gradient, torch parameter layout
+// `first`: this is the block's first tile (the partial buffer is not cleared between launches); later tiles add to what
+// the SAME thread stored before, in tile order -- no atomics, bit-reproducible.  The accumulators live in the block's
+// partial (L2) instead of registers since the tile shrank to 64 samples for two blocks per SM: 80 persistent registers
+// per thread did not fit under the 128 of a 2 x 256-thread SM.
 template <int RN, int RK>
 __device__ __forceinline__ void dw_store(const LLayer &Ly, float *part, int ng, int kg, const float (&dw)[16],
-                                         const float (&db)[4]) {
+                                         const float (&db)[4], bool first) {
+    float old[RN * RK], oldb[RN];
+#pragma unroll
+    for (int a = 0; a < RN; ++a) {
+        const int n = RN * ng + a;
+#pragma unroll
+        for (int c = 0; c < RK; ++c)
+            old[a * RK + c] = (!first && n < Ly.n_real && RK * kg + c < Ly.k_real) ? __ldcg(part + Ly.g_w + n * Ly.k_real + RK * kg + c) : 0.0f;
+        oldb[a] = (!first && kg == 0 && n < Ly.n_real) ? __ldcg(part + Ly.g_b + n) : 0.0f;
+    }
 #pragma unroll
     for (int a = 0; a < RN; ++a) {
         const int n = RN * ng + a;
         if (n < Ly.n_real) {
 #pragma unroll
             for (int c = 0; c < RK; ++c)
-                if (RK * kg + c < Ly.k_real) part[Ly.g_w + n * Ly.k_real + RK * kg + c] = dw[a * RK + c];
-            if (kg == 0) part[Ly.g_b + n] = db[a];
+                if (RK * kg + c < Ly.k_real) __stcg(part + Ly.g_w + n * Ly.k_real + RK * kg + c, old[a * RK + c] + dw[a * RK + c]);
+            if (kg == 0) __stcg(part + Ly.g_b + n, oldb[a] + db[a]);
         }
     }
 }
 
+// -DLEARN_TRACE (tools/build_variant.sh): thread 0 of block 0 adds up the cycles between the phase barriers of its tiles
+// (phase ids: 0 sample indices, 1 gather, 2 + l forward layer l, 6 loss, 7 + 2 l dW_l, 8 + 2 l dH_l + dZ write) ->
+// b200_learn_trace_read.  How profiles/r2/learn.md's phase table was measured.  Compiled out of the shipped library.
+#ifdef LEARN_TRACE
+__device__ long long g_learn_trace[16];
+#define LTRACE(id)                                                          \
+    do {                                                                    \
+        if (blockIdx.x == 0 && tid == 0) {                                  \
+            const long long now = clock64();                                \
+            g_learn_trace[id] += now - lt_prev;                             \
+            lt_prev = now;                                                  \
+        }                                                                   \
+    } while (0)
+#else
+#define LTRACE(id) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ the gradient kernel
-__global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant__ LearnArgs A) {
+__global__ void __launch_bounds__(LT, BLOCKS_PER_SM) ppo2_grad_kernel(const __grid_constant__ LearnArgs A) {
     extern __shared__ __align__(16) float sm[];
     __shared__ int s_t[TM], s_i[TM];
     __shared__ float s_act[16 * TM], s_alp[16 * TM], s_tgt[TM];   // the tile's actions, old log-probs [d][s]; adv / v_target
@@ -273,15 +310,8 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
         }
         s_cst[d][0] = sd * sd; s_cst[d][1] = logf(sd); s_cst[d][2] = gain; s_cst[d][3] = off2;
     }
-    float dw[LMAX][16], db[LMAX][4];
-#pragma unroll
-    for (int l = 0; l < LMAX; ++l) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) dw[l][e] = 0.0f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) db[l][e] = 0.0f;
-    }
     float loss_acc = 0.0f;
+    float *part = A.partial[net_id] + (size_t)bx * (size_t)(net.P + 4);
 
     const int64_t tiles = (A.count + TM - 1) / TM;
     const LLayer &L0 = net.L[0];
@@ -289,8 +319,12 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
     float *gout = sm + net.gout_off;
     const int pgo = LO.N + 4;
 
+#ifdef LEARN_TRACE
+    long long lt_prev = clock64();
+#endif
     for (int64_t tile = bx; tile < tiles; tile += nbx) {
         __syncthreads();   // the previous tile's last phase has finished with H and s_t / s_i
+        LTRACE(15);
         if (tid < TM) {
             const int64_t j = tile * TM + tid;
             int t = -1, i = 0;
@@ -303,31 +337,48 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
             s_i[tid] = i;
         }
         __syncthreads();
-        {   // gather the observations: H_0[s][k]
+        LTRACE(0);
+        {   // gather: H_0[s][k] (observations) and the loss phase's inputs (actions, old log-probs, adv / v_target).
+            // Thread = (sample s, field lane q): its fields are q, q + 4, ...; ALL its loads are issued before the first
+            // store to shared memory -- the obvious load-store loop serialised six DRAM round trips per tile (phase
+            // trace: 9.5 k of 82 k cycles per tile)
+            static_assert(LT % TM == 0 && LT / TM == 4, "4 field lanes per sample");
             float *H0 = sm + L0.h_off;
             const int p0 = L0.K + 4;
-            for (int e = tid; e < TM * L0.K; e += LT) {
-                const int s = e & (TM - 1), k = e >> 7;
-                const int t = s_t[s];
-                H0[s * p0 + k] = (t >= 0 && k < A.S) ? __ldg(A.s + ((int64_t)t * A.S + k) * A.N + s_i[s]) : 0.0f;
+            const int s = tid & (TM - 1), q = tid >> TM_LOG2;
+            const int t = s_t[s];
+            const int64_t i = s_i[s], tt = t < 0 ? 0 : t;
+            float vo[WMAX / 4], va[4], vl[4], vt = 0.0f;
+#pragma unroll
+            for (int j = 0; j < WMAX / 4; ++j) {
+                const int k = q + 4 * j;
+                vo[j] = (t >= 0 && k < A.S) ? __ldg(A.s + (tt * A.S + k) * A.N + i) : 0.0f;
             }
-            // the loss phase's inputs, fetched here so that their DRAM latency overlaps the forward pass
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = q + 4 * j;
+                const bool on = net_id == 0 && t >= 0 && d < A.A;
+                const int64_t off = (tt * A.A + (on ? d : 0)) * A.N + i;
+                va[j] = on ? __ldg(A.a + off) : 0.0f;
+                vl[j] = on ? __ldg(A.a_lp + off) : 0.0f;
+            }
+            if (q == 0 && t >= 0) vt = __ldg((net_id == 0 ? A.adv : A.v_target) + tt * A.N + i);
+#pragma unroll
+            for (int j = 0; j < WMAX / 4; ++j) {
+                const int k = q + 4 * j;
+                if (k < L0.K) H0[s * p0 + k] = vo[j];
+            }
             if (net_id == 0) {
-                for (int e = tid; e < TM * A.A; e += LT) {
-                    const int s = e & (TM - 1), d = e >> 7;
-                    const int t = s_t[s];
-                    const int64_t off = ((int64_t)(t < 0 ? 0 : t) * A.A + d) * A.N + s_i[s];
-                    s_act[d * TM + s] = t >= 0 ? __ldg(A.a + off) : 0.0f;
-                    s_alp[d * TM + s] = t >= 0 ? __ldg(A.a_lp + off) : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int d = q + 4 * j;
+                    if (d < A.A) { s_act[d * TM + s] = va[j]; s_alp[d * TM + s] = vl[j]; }
                 }
             }
-            if (tid < TM) {
-                const int t = s_t[tid];
-                const float *src = net_id == 0 ? A.adv : A.v_target;
-                s_tgt[tid] = t >= 0 ? __ldg(src + (int64_t)t * A.N + s_i[tid]) : 0.0f;
-            }
+            if (q == 0) s_tgt[s] = vt;
         }
         __syncthreads();
+        LTRACE(1);
         // ---------------------------------------------------------------- forward
 #pragma unroll
         for (int l = 0; l < LMAX; ++l) {
@@ -344,14 +395,17 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
                 default: fwd_layer<8>(H, ph, W, ph, bs, Ly.K, out, po, !last, sg, ng); break;
                 }
                 __syncthreads();
+                LTRACE(2 + l);
             }
         }
         // ---------------------------------------------------------------- loss and its gradient at the net's output
         {   // two threads per sample: thread `half` takes the action dimensions half, half + 2, ...
             const int sx = tid >> 1, half = tid & 1;
-            float *z = gout + sx * pgo;
-            const bool live = s_t[sx] >= 0;
-            if (net_id == 0) {
+            float *z = gout + (sx < TM ? sx : 0) * pgo;
+            const bool live = sx < TM && s_t[sx < TM ? sx : 0] >= 0;
+            if (sx >= TM) {
+                // 2 x TM threads work in this phase
+            } else if (net_id == 0) {
                 // Normal(mean, std).log_prob(a) summed over dimensions, PPO2.py:106-112
                 float lp = 0.0f, lp_old = 0.0f;
                 float dm[8];   // d lp / d z_d of this thread's dimensions
@@ -400,6 +454,7 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
             }
         }
         __syncthreads();
+        LTRACE(6);
         // ---------------------------------------------------------------- backward
 #pragma unroll
         for (int l = LMAX - 1; l >= 0; --l) {
@@ -415,44 +470,33 @@ __global__ void __launch_bounds__(LT, 1) ppo2_grad_kernel(const __grid_constant_
                         // tn runs fastest: the threads that also sum the bias gradient (tk == 0) are the first nt of
                         // the block, so the other warps skip those adds (they were 5 % of all issued instructions)
                         const int tk = tid / nt, tn = tid - tk * nt;
+                        float dw[16], db[4];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) dw[e] = 0.0f;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) db[e] = 0.0f;
+                        const bool first = tile == bx;
                         switch (Ly.rn * 8 + Ly.rk) {
-                        case 4 * 8 + 4: dw_layer<4, 4>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
-                        case 2 * 8 + 4: dw_layer<2, 4>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
-                        case 1 * 8 + 4: dw_layer<1, 4>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
-                        case 1 * 8 + 2: dw_layer<1, 2>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
-                        default: dw_layer<1, 1>(G, pg, H, ph, tn, tk, dw[l], db[l]); break;
+                        case 4 * 8 + 4: dw_layer<4, 4>(G, pg, H, ph, tn, tk, dw, db); dw_store<4, 4>(Ly, part, tn, tk, dw, db, first); break;
+                        case 2 * 8 + 4: dw_layer<2, 4>(G, pg, H, ph, tn, tk, dw, db); dw_store<2, 4>(Ly, part, tn, tk, dw, db, first); break;
+                        case 1 * 8 + 4: dw_layer<1, 4>(G, pg, H, ph, tn, tk, dw, db); dw_store<1, 4>(Ly, part, tn, tk, dw, db, first); break;
+                        case 1 * 8 + 2: dw_layer<1, 2>(G, pg, H, ph, tn, tk, dw, db); dw_store<1, 2>(Ly, part, tn, tk, dw, db, first); break;
+                        default: dw_layer<1, 1>(G, pg, H, ph, tn, tk, dw, db); dw_store<1, 1>(Ly, part, tn, tk, dw, db, first); break;
                         }
                     }
                 }
                 if (l > 0) {
                     __syncthreads();
+                    LTRACE(7 + 2 * l);
                     if (kgs == 16) bwd_layer<2>(G, pg, sm + Ly.w_off, ph, Ly.N, H, ph, kgs, sg, ng);
                     else bwd_layer<1>(G, pg, sm + Ly.w_off, ph, Ly.N, H, ph, kgs, sg, ng);
                     __syncthreads();
+                    LTRACE(8 + 2 * l);
                 }
             }
         }
     }
 
-    // ---------------------------------------------------------------- this block's partial gradient
-    float *part = A.partial[net_id] + (size_t)bx * (size_t)(net.P + 4);
-#pragma unroll
-    for (int l = 0; l < LMAX; ++l) {
-        if (l < L) {
-            const LLayer &Ly = net.L[l];
-            const int kt = Ly.K / Ly.rk, nt = Ly.N / Ly.rn;
-            if (tid < nt * kt) {
-                const int tk = tid / nt, tn = tid - tk * nt;
-                switch (Ly.rn * 8 + Ly.rk) {
-                case 4 * 8 + 4: dw_store<4, 4>(Ly, part, tn, tk, dw[l], db[l]); break;
-                case 2 * 8 + 4: dw_store<2, 4>(Ly, part, tn, tk, dw[l], db[l]); break;
-                case 1 * 8 + 4: dw_store<1, 4>(Ly, part, tn, tk, dw[l], db[l]); break;
-                case 1 * 8 + 2: dw_store<1, 2>(Ly, part, tn, tk, dw[l], db[l]); break;
-                default: dw_store<1, 1>(Ly, part, tn, tk, dw[l], db[l]); break;
-                }
-            }
-        }
-    }
     // block sum of the loss in a fixed order
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
@@ -617,7 +661,8 @@ int grid_cap() {
     if (dev < 0 || dev >= 64) dev = 0;
     if (!sms[dev]) {
         int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = GRID_CAP;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        v *= BLOCKS_PER_SM;
         sms[dev] = v > GRID_CAP ? GRID_CAP : v;
     }
     return sms[dev];
@@ -671,7 +716,7 @@ int make_plan(const b200_ppo2_batch *bt, const b200_mlp *actor, const b200_mlp *
     }
     if (ws > workspace_bytes) return B200ENV_ESIZE;
     pl->smem = smem_f * sizeof(float);
-    if (pl->smem > 227 * 1024 - 20 * 1024) return B200ENV_ESIZE;   // 18.3 KB of static shared memory next to it
+    if (pl->smem > 227 * 1024 - 12 * 1024) return B200ENV_ESIZE;   // ~10 KB of static shared memory next to it
     a.T = bt->T; a.N = bt->N; a.first = bt->first; a.count = bt->count;
     a.s = bt->s; a.a = bt->a; a.a_lp = bt->a_lp; a.adv = bt->adv; a.v_target = bt->v_target;
     a.index = bt->index;
@@ -705,7 +750,8 @@ int launch_grad(Plan &pl, cudaStream_t stream) {
     for (int y = 0; y < pl.nets; ++y) {
         const LNet &n = pl.a.net[pl.a.net_of_y[y]];
         for (int l = 0; l < n.n_layers; ++l) work[y] += (double)n.L[l].K * n.L[l].N;
-        work[y] += 64.0;   // per-sample gather + loss
+        work[y] += 2200.0;   // per-tile fixed part (indices, gather, loss, barriers) in units of one K x N product term:
+                             // phase trace, ~20 k of an actor tile's 82 k cycles; with 64 the critic's blocks were the tail
     }
     pl.a.nblk[1] = 0;
     if (pl.nets == 2) {
@@ -837,3 +883,13 @@ extern "C" B200_API int b200_ppo2_learn(const b200_ppo2_batch *batch, const b200
     }
     return B200ENV_OK;
 }
+
+#ifdef LEARN_TRACE
+extern "C" B200_API int b200_learn_trace_read(long long *host) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host, g_learn_trace, sizeof(long long) * 16);
+    long long zero[16] = {0};
+    cudaMemcpyToSymbol(g_learn_trace, zero, sizeof(zero));
+    return 0;
+}
+#endif

@@ -138,9 +138,12 @@ def test_clip_and_adam_match_torch_over_several_steps():
         mine = upd.grad_norm.tolist()
         assert abs(mine[0] - float(na)) <= 1e-5 * max(1.0, float(na)) and abs(mine[1] - float(nc)) <= 1e-5 * max(1.0, float(nc))
         assert float(nc) > 0.5                      # the critic's gradient is actually clipped
-        for net, ref in ((actor, actor_t), (critic, critic_t)):
+        # |delta param| <= 1e-6 for the actor; for the critic (lr 1e-3, value targets x10) 2e-3 of one Adam step (whose
+        # size is <= lr): where |g| ~ eps = 1e-5 the update lr g / (|g| + eps) turns a 1e-8 difference of float32
+        # summation order into 2.5e-4 lr -- torch against torch with another reduction order differs as much
+        for net, ref, tol in ((actor, actor_t, 1e-6), (critic, critic_t, 2e-6)):
             for p, q in zip(net.parameters(), ref.parameters()):
-                assert float((p - q).abs().max()) <= 1e-6, (step, float((p - q).abs().max()))
+                assert float((p.detach() - q.detach()).abs().max()) <= tol, (step, float((p.detach() - q.detach()).abs().max()))
 
 
 def test_keyed_permutation_visits_every_sample_once_and_loop_matches_steps():
