@@ -180,7 +180,7 @@ void orc_soi_step_one(const void *params, const oracle_io *io, int64_t n, int64_
     }
     double acc[2] = {(f[0] - p->k * s[2]) / p->mass, (f[1] - p->k * s[3]) / p->mass};
     double ex = p->target_x - s[0], ey = p->target_y - s[1];
-    double e_pos = sqrt(ex * ex + ey * ey), e_vel = sqrt(s[2] * s[2] + s[3] * s[3]);
+    double e_pos = sqrt(fma(ey, ey, ex * ex)), e_vel = sqrt(fma(s[3], s[3], s[2] * s[2]));   /* np.linalg.norm: see norm2 in ugvo.c */
     int flag = 0; /* :235-249 */
     if (s[0] > p->map_x + p->admissible_error || s[0] < 0 - p->admissible_error ||
         s[1] > p->map_y + p->admissible_error || s[1] < 0 - p->admissible_error) flag = 1;
@@ -188,7 +188,7 @@ void orc_soi_step_one(const void *params, const oracle_io *io, int64_t n, int64_
     if (p->success_terminal && e_pos <= 0.05 && e_vel < 0.05) flag = 3;
     int done = flag != 0;
     soi_obs(p, s, nxt);
-    double a_n = sqrt(acc[0] * acc[0] + acc[1] * acc[1]); /* :251-284 */
+    double a_n = sqrt(fma(acc[1], acc[1], acc[0] * acc[0])); /* :251-284 */
     double u_pos = -e_pos * p->Q_pos, u_vel = -e_vel * p->Q_vel, u_acc = -a_n * p->Q_acc, u_extra = 0.;
     if (flag == 1) { double _n = (p->time_max - time) / p->dt; u_extra = _n * (u_pos + u_vel + u_acc); }
     emit(io, n, i, 4, cur, nxt, u_pos + u_vel + u_acc + u_extra, done, flag);
@@ -339,13 +339,13 @@ void orc_twolink_step_one(const void *params, const oracle_io *io, int64_t n, in
     if (xx[1] > p->theta_max) xx[1] -= 2 * p->theta_max; else if (xx[1] < -p->theta_max) xx[1] += 2 * p->theta_max;
     for (int k = 0; k < 4; ++k) SF(k) = xx[k];
     io->time[i] = time;
-    double en = sqrt(SF(4) * SF(4) + SF(5) * SF(5)), wn = sqrt(xx[2] * xx[2] + xx[3] * xx[3]);
+    double en = sqrt(fma(SF(5), SF(5), SF(4) * SF(4))), wn = sqrt(fma(xx[3], xx[3], xx[2] * xx[2]));
     int flag, done; /* :199-209 */
     if (time > p->time_max) { flag = 2; done = 1; }
     else if (en <= p->miss && wn <= p->omega_ok) { flag = 3; done = 1; }
     else { flag = 0; done = 0; }
     tlm_obs(io, n, i, nxt);
-    double tn = sqrt(tq[0] * tq[0] + tq[1] * tq[1]); /* :211-224 */
+    double tn = sqrt(fma(tq[1], tq[1], tq[0] * tq[0])); /* :211-224 */
     double reward = -en * p->Q_pos + -wn * p->Q_omega + -tn * p->Q_acc + 0.;
     emit(io, n, i, 6, cur, nxt, reward, done, flag);
     if (done && (flags & B200ENV_AUTO_RESET)) { tlm_reset(p, io, n, i, seed, off); tlm_obs(io, n, i, nxt); }
@@ -361,13 +361,13 @@ void orc_twolink_reset_one(const void *params, const oracle_io *io, int64_t n, i
 /* environment/UGV/UGVForward.py, UGVBidirectional.py; utils/functions.py:49-60 */
 typedef b200_ugv_params UP;
 static double vec_rad_oriented(double x1, double y1, double x2, double y2) {
-    if (sqrt(x2 * x2 + y2 * y2) < 1e-4 || sqrt(x1 * x1 + y1 * y1) < 1e-4) return 0;
+    if (sqrt(fma(y2, y2, x2 * x2)) < 1e-4 || sqrt(fma(y1, y1, x1 * x1)) < 1e-4) return 0;
     double dot = x1 * x2 + y1 * y2, det = x1 * y2 - y1 * x2;
     return atan2(det, dot);
 }
 static void ugv_err(const UP *p, const double *s, double *e, double *ephi) {
     double dx = p->target_x - s[0], dy = p->target_y - s[1];
-    *e = sqrt(dx * dx + dy * dy);
+    *e = sqrt(fma(dy, dy, dx * dx));
     *ephi = vec_rad_oriented(cos(s[3]), sin(s[3]), dx, dy);
     if (p->bidirectional) { /* UGVBidirectional.py:314-325 */
         double d = cos(s[3]) * dx + sin(s[3]) * dy;

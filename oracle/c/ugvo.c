@@ -19,7 +19,9 @@ typedef struct {
     double time;
 } ugvo_t;
 
-static double norm2(double a, double b) { return sqrt(a * a + b * b); }
+/* np.linalg.norm of a 2-vector = sqrt(x.dot(x)): OpenBLAS' ddot accumulates with FMA, i.e. sqrt(fma(b, b, a * a)) -- pinned by
+ * the collision-radius-equality fixture tests/golden/ugvo_edge.npz (plain a * a + b * b flips 2 of 180 decisions) */
+static double norm2(double a, double b) { return sqrt(fma(b, b, a * a)); }
 
 /* utils/functions.py:35-46 */
 static double cal_vector_rad(double x1, double y1, double x2, double y2) {

@@ -561,9 +561,60 @@ class UgvoDPPO2A(UgvoA):
         return super().sample_action(rng, t, 1, env)
 
 
+class UgvoEdgeA(UgvoA):
+    """Collision-radius equality (collision_check :261-272: `dis_two_points(pos, centre) <= r + r_vehicle`): after every
+    reset the vehicle is parked (vel = omega = 0, zero actions) at a point whose distance to the first obstacle's centre --
+    evaluated exactly like the reference does, np.linalg.norm of the difference -- is EQUAL to r + r_vehicle (lanes 0, 3),
+    the closest representable distance above it (lanes 1, 4: no collision) or below it (lanes 2, 5).  The point is found
+    by a search over +-12 ulp offsets of both coordinates around the nominal point."""
+    name = "ugvo_edge"
+
+    def make(self):
+        env = super().make()
+        n = getattr(self, "_made", 0)          # gen_golden makes (env, twin) per lane, in lane order
+        self._made = n + 1
+        env._edge_lane = n // 2
+        return env
+
+    def reset(self, env):
+        env.reset(True)
+        mode = env._edge_lane % 3
+        c = np.array(env.obs[0][1], dtype=float)
+        R = env.obs[0][2][0] + env.r_vehicle
+        centre = np.array([env.x_size / 2.0, env.y_size / 2.0]) if hasattr(env, "x_size") else np.array([2.5, 2.5])
+        u = centre - c
+        u = u / max(np.linalg.norm(u), 1e-9) if np.linalg.norm(u) > 1e-9 else np.array([1.0, 0.0])
+        nominal = c + R * u
+        best = None
+        for ix in range(-12, 13):
+            px = nominal[0]
+            for _ in range(abs(ix)):
+                px = np.nextafter(px, np.inf if ix > 0 else -np.inf)
+            for iy in range(-12, 13):
+                py = nominal[1]
+                for _ in range(abs(iy)):
+                    py = np.nextafter(py, np.inf if iy > 0 else -np.inf)
+                d = float(np.linalg.norm(np.array([px, py]) - c))
+                if mode == 0:
+                    key = (abs(d - R), 0)
+                elif mode == 1:
+                    key = (d - R if d > R else np.inf, 0)
+                else:
+                    key = (R - d if d < R else np.inf, 0)
+                if best is None or key < best[0]:
+                    best = (key, px, py, d)
+        env.pos = np.array([best[1], best[2]], dtype=float)
+        env.vel, env.omega = 0.0, 0.0
+        self.last_edge = (mode, best[3], R)
+
+    def sample_action(self, rng, t, l, env=None):
+        return np.zeros(2)
+
+
 REGISTRY.update({
     "ugvo": (UgvoA, 4, 300, 41),
     "ugvo_dppo2": (UgvoDPPO2A, 4, 400, 42),
+    "ugvo_edge": (UgvoEdgeA, 6, 30, 43),
 })
 
 

@@ -166,6 +166,13 @@ __device__ __forceinline__ void stio_idx(void *base, I n, int field, I i, T v) {
     else static_cast<T *>(base)[(I)field * n + i] = v;
 }
 
+// np.linalg.norm of a 2-vector (a, b) as the reference's numpy evaluates it: sqrt(x.dot(x)) with OpenBLAS' ddot, whose
+// accumulation is FMA-contracted -- sqrt(fma(b, b, a * a)), not sqrt(a * a + b * b).  Pinned by the collision-radius-equality
+// fixture tests/golden/ugvo_edge.npz (the plain form flips 2 of 180 `distance <= r + r_vehicle` decisions) and by
+// SecondOrderIntegration's reward, which is bit-exact only with this form (oracle/c/small_envs.c).
+template <typename T>
+__device__ __forceinline__ T np_norm2(T a, T b) { return Mth<T>::sqrt(Mth<T>::fma(b, b, a * a)); }
+
 // clamp against bounds that are never NaN: two compare-selects instead of the NaN-aware fmin / fmax pair (6 instructions
 // each in fp64).  A NaN x passes through, like np.clip.
 template <typename T>

@@ -52,8 +52,8 @@ struct Soi {
         const Divisor<T> dm((T)p.mass);
         const T ax = dm.div(fx - k * vx), ay = dm.div(fy - k * vy); // self.acc :313
         const T ex = (T)p.target_x - x, ey = (T)p.target_y - y;
-        const T e_pos = Mth<T>::sqrt(ex * ex + ey * ey);
-        const T e_vel = Mth<T>::sqrt(vx * vx + vy * vy);
+        const T e_pos = np_norm2<T>(ex, ey);
+        const T e_vel = np_norm2<T>(vx, vy);
         // is_Terminal :235-249
         flag = 0;
         const T adm = (T)p.admissible_error;
@@ -63,7 +63,7 @@ struct Soi {
         done = flag != 0;
         observe(p, nxt);
         // get_reward :251-284
-        const T acc = Mth<T>::sqrt(ax * ax + ay * ay);
+        const T acc = np_norm2<T>(ax, ay);
         const T u_pos = -e_pos * (T)p.Q_pos, u_vel = -e_vel * (T)p.Q_vel, u_acc = -acc * (T)p.Q_acc;
         T u_extra = (T)0;
         if (flag == 1) u_extra = (T)((p.time_max - time) / p.dt) * (u_pos + u_vel + u_acc);

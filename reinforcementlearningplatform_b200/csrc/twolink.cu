@@ -84,13 +84,13 @@ struct TwoLink {
         if (th1 > tm) th1 -= (T)2 * tm; else if (th1 < -tm) th1 += (T)2 * tm;
         if (th2 > tm) th2 -= (T)2 * tm; else if (th2 < -tm) th2 += (T)2 * tm;
         // is_Terminal :199-209 (returns at the first true test)
-        const T en = Mth<T>::sqrt(ex * ex + ey * ey), wn = Mth<T>::sqrt(w1 * w1 + w2 * w2);
+        const T en = np_norm2<T>(ex, ey), wn = np_norm2<T>(w1, w2);
         if (time > p.time_max) { flag = 2; done = true; }
         else if (en <= (T)p.miss && wn <= (T)p.omega_ok) { flag = 3; done = true; }
         else { flag = 0; done = false; }
         observe(p, nxt);
         // get_reward :211-224
-        const T tn = Mth<T>::sqrt(tq0 * tq0 + tq1 * tq1);
+        const T tn = np_norm2<T>(tq0, tq1);
         reward = -en * (T)p.Q_pos + -wn * (T)p.Q_omega + -tn * (T)p.Q_acc + (T)0;
     }
     // reset(random=True) :282-312

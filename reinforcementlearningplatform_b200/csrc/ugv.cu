@@ -6,7 +6,7 @@ namespace {
 // utils/functions.py:49-60 with v1 = (cos phi, sin phi)
 template <typename T>
 __device__ __forceinline__ T vector_rad_oriented(T x1, T y1, T x2, T y2) {
-    if (Mth<T>::sqrt(x2 * x2 + y2 * y2) < (T)1e-4 || Mth<T>::sqrt(x1 * x1 + y1 * y1) < (T)1e-4) return (T)0;
+    if (np_norm2<T>(x2, y2) < (T)1e-4 || np_norm2<T>(x1, y1) < (T)1e-4) return (T)0;
     return Mth<T>::atan2(x1 * y2 - y1 * x2, x1 * x2 + y1 * y2);
 }
 
@@ -32,7 +32,7 @@ struct Ugv {
         T s, c;
         Mth<T>::sincos(phi, &s, &c);
         const T dx = (T)p.target_x - x, dy = (T)p.target_y - y;
-        e = Mth<T>::sqrt(dx * dx + dy * dy);
+        e = np_norm2<T>(dx, dy);
         ephi = vector_rad_oriented<T>(c, s, dx, dy);
         if (p.bidirectional) {
             const T d = c * dx + s * dy;

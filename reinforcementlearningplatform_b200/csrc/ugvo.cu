@@ -30,7 +30,7 @@ template <> __device__ __forceinline__ double shfl<double>(double v, int src) { 
 template <> __device__ __forceinline__ float shfl<float>(float v, int src) { return __shfl_sync(FULL, v, src); }
 
 template <typename T>
-__device__ __forceinline__ T norm2(T a, T b) { return Mth<T>::sqrt(a * a + b * b); }
+__device__ __forceinline__ T norm2(T a, T b) { return np_norm2<T>(a, b); }   // np.linalg.norm / dis_two_points, common.cuh
 
 // utils/functions.py:35-46
 template <typename T>
@@ -198,7 +198,7 @@ __device__ __forceinline__ double lerp_u(double lo, double hi, double u) { retur
 // dis_two_points(a, b) <= R, i.e. sqrt(dx^2 + dy^2) <= R (map.py:122,131-133), decided on the squares; the square root is
 // only taken when the two sides agree to ~14 digits, so the decision is the reference's in every case
 __device__ __forceinline__ bool within(double dx, double dy, double R) {
-    const double d2 = dx * dx + dy * dy, R2 = R * R;
+    const double d2 = ::fma(dy, dy, dx * dx), R2 = R * R;   // the squared np.linalg.norm (common.cuh np_norm2)
     if (fabs(d2 - R2) <= 1e-13 * R2) return sqrt(d2) <= R;
     return d2 <= R2;
 }
@@ -217,7 +217,7 @@ __device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gi
     for (int round = 0; round < 2; ++round) {
         d = draw2(seed, gid, ep, 1u + (uint32_t)(round * 32 + lane));
         const double cx = lerp_u(lo, hx, d.u0), cy = lerp_u(lo, hy, d.u1);
-        const bool ok = !(sqrt((cx - sx) * (cx - sx) + (cy - sy) * (cy - sy)) < p.safety_dis_st);
+        const bool ok = !(sqrt(::fma(cy - sy, cy - sy, (cx - sx) * (cx - sx))) < p.safety_dis_st);
         const unsigned m = __ballot_sync(FULL, ok);
         if (m) {
             const int src = __ffs(m) - 1;

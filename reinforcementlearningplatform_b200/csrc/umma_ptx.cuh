@@ -5,6 +5,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef UMMA_WAIT_HINT_NS
+#define UMMA_WAIT_HINT_NS 20000u
+#endif
+
 namespace umma {
 
 constexpr long long WAIT_TIMEOUT = 4000000000ll;       // cycles (~2 s): a wait that long is a protocol bug -> trap
@@ -46,7 +50,7 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(UMMA_WAIT_HINT_NS) : "memory");
     return ok;
 }
 // `parity`: the phase parity whose completion is awaited; on a fresh barrier parity 1 passes at once (free-type barriers).

@@ -47,6 +47,7 @@ def env_specs():
         "uavr_tracking": (rlp.uav_tracking_outer_loop, {}),
         "ugvo": (rlp.UGVForwardObstacleAvoidance, {}),
         "ugvo_dppo2": (rlp.UGVForwardObstacleAvoidance, {"variant": "dppo2"}),
+        "ugvo_edge": (rlp.UGVForwardObstacleAvoidance, {}),
         "uav_pos": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
         "uav_pos_dis": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
         "uav_pos_wide": (rlp.UavPosCtrlRL, {"random_trajectory": True}),
@@ -214,7 +215,7 @@ ENGINE_TOL = {
     "uav_pos": 5e-8, "uav_pos_dis": 2e-10, "uav_pos_wide": 2e-10, "uav_pos_rp0": 5e-10, "uav_pos_crash": 5e-11, "uav_pos_edge": 5e-11,
     "uav_att": 2e-13, "uav_att_rand": 2e-13, "uav_att_edge": 2e-13,
     "fas": 1e-13, "fas_ppo2": 1e-13, "fas_discrete": 1e-13, "soi": 1e-13, "soi_dppo2": 1e-13, "ballbalancer": 2e-12, "twolink": 2e-7,
-    "ugv_forward": 1e-12, "ugv_bidirectional": 1e-12, "ugvo": 2e-9, "ugvo_dppo2": 2e-9,
+    "ugv_forward": 1e-12, "ugv_bidirectional": 1e-12, "ugvo": 2e-9, "ugvo_dppo2": 2e-9, "ugvo_edge": 2e-9,
     "uavr_hover_outer": 2e-12, "uavr_hover": 1e-11, "uavr_inner": 2e-12, "uavr_tracking": 2e-12,
 }
 # Share of (step, lane) samples of a free-running replay that must stay comparable (lanes are dropped until their next

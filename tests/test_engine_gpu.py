@@ -16,7 +16,7 @@ GOLDEN_CASES = sorted(ENGINE_TOL)
 # loses ~eps * m^2 there, so a 1-ulp difference between numpy's and CUDA's tan() moves a range (the reference itself
 # moves as much under a 1-ulp nudge: fixture twin_err).  Measured on B200: 1.3e-12 (ugvo), 5.1e-11 (ugvo_dppo2, 8 lanes x
 # 400 steps x 37 rays); the bounds are 10x that.  Kinematic state, reward and flags stay exact.
-ONE_STEP_TOL = {"ugvo": 2e-11, "ugvo_dppo2": 5e-10}
+ONE_STEP_TOL = {"ugvo": 2e-11, "ugvo_dppo2": 5e-10, "ugvo_edge": 2e-11}
 
 # Fixtures whose actions were recorded from a closed loop around an open-loop-unstable plant: replaying them
 # open loop amplifies a 1-ulp difference by e^(lambda*t) (inverted pendulum: lambda ~ 6/s, 5 s episodes -> 1e13),
@@ -26,7 +26,10 @@ OPEN_LOOP_UNSTABLE = {"cartpole_gentle": "open-loop replay of closed-loop action
                       # the bit-exact flag in one-step mode; free-running, the reference's own one-ulp twin crosses the
                       # edge at a different step in every lane (live fraction 0), so there is nothing to compare
                       "uav_att_edge": "every lane sits on a terminal threshold: one-step (re-sync) comparison only",
-                      "uav_pos_edge": "every lane sits on a terminal threshold: one-step (re-sync) comparison only"}
+                      "uav_pos_edge": "every lane sits on a terminal threshold: one-step (re-sync) comparison only",
+                      # collision_check's `distance <= r + r_vehicle` at equality and one ulp either side (UGVForward
+                      # ObstacleAvoidance.py:261-272): the vehicle is parked there after every reset
+                      "ugvo_edge": "every lane sits on the collision radius: one-step (re-sync) comparison only"}
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)

@@ -14,8 +14,8 @@ CASES = {
     "cartpole_wide": 0.0,
     "cartpole_angleonly_env": 0.0,
     "cartpole_angleonly_ppo2": 0.0,
-    "fas": 0.0, "fas_ppo2": 0.0, "fas_discrete": 0.0, "soi": 1e-15, "soi_dppo2": 1e-15, "ballbalancer": 1e-12, "twolink": 1e-12,
-    "ugv_forward": 1e-12, "ugv_bidirectional": 1e-12, "ugvo": 1e-12, "ugvo_dppo2": 1e-12,
+    "fas": 0.0, "fas_ppo2": 0.0, "fas_discrete": 0.0, "soi": 0.0, "soi_dppo2": 0.0, "ballbalancer": 1e-12, "twolink": 1e-12,
+    "ugv_forward": 1e-12, "ugv_bidirectional": 1e-12, "ugvo": 1e-12, "ugvo_dppo2": 1e-12, "ugvo_edge": 1e-12,
     "uavr_hover_outer": 1e-12, "uavr_hover": 1e-12, "uavr_inner": 1e-12, "uavr_tracking": 1e-12,
     "uav_pos": 1e-12, "uav_pos_dis": 1e-12, "uav_pos_wide": 1e-12, "uav_pos_rp0": 1e-12, "uav_pos_crash": 1e-12, "uav_pos_edge": 1e-12,
     "uav_att": 1e-12, "uav_att_rand": 1e-12, "uav_att_edge": 1e-12,
