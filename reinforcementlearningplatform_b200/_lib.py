@@ -154,6 +154,10 @@ def load() -> C.CDLL:
     lib.b200env_params_bytes.argtypes = [i32]
     lib.b200env_dims.restype = i32
     lib.b200env_dims.argtypes = [i32, i32, ip, ip, ip, ip]
+    lib.b200env_state_layout.restype = i32
+    lib.b200env_state_layout.argtypes = [i32, i32, ip, ip]
+    lib.b200env_state_elems.restype = sz
+    lib.b200env_state_elems.argtypes = [i32, i32, i64]
     lib.b200env_step.restype = i32
     lib.b200env_step.argtypes = [i32, i32, i64, vp, sz, C.POINTER(IO), u32, u64, i64, vp]
     lib.b200env_rollout.restype = i32
@@ -224,6 +228,13 @@ def check(rc: int, what: str) -> None:
         if rc == -5:
             extra = f" (cudaError {load().b200env_last_cuda_error()})"
         raise B200EnvError(f"{what}: {ERRORS.get(rc, rc)}{extra}")
+
+
+def state_layout(env_id: int, variant: int = 0):
+    """(block, slots) of the persistent state buffer: block == 0 -> field-major [slots = state_fields][n]."""
+    b, s = C.c_int(), C.c_int()
+    check(load().b200env_state_layout(env_id, variant, C.byref(b), C.byref(s)), "b200env_state_layout")
+    return b.value, s.value
 
 
 def dims(env_id: int, variant: int = 0):

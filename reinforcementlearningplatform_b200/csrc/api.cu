@@ -75,6 +75,25 @@ int b200env_step(int env_id, int dtype, int64_t n_envs, const void *params, size
     return f->step(dtype, n_envs, params, io, flags, seed, env_index_offset, (cudaStream_t)cuda_stream);
 }
 
+int b200env_state_layout(int env_id, int variant, int *block, int *slots) {
+    const Family *f = family(env_id);
+    if (!f) return B200ENV_EENV;
+    int sf = 0;
+    const int rc = f->dims(variant, &sf, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    const bool blocked = env_id == B200ENV_UAV_ATT || env_id == B200ENV_UAV_POS;
+    if (block) *block = blocked ? B200_UAV_STATE_BLOCK : 0;
+    if (slots) *slots = blocked ? B200_UAV_STATE_SLOTS : sf;
+    return B200ENV_OK;
+}
+
+size_t b200env_state_elems(int env_id, int variant, int64_t n_envs) {
+    int block = 0, slots = 0;
+    if (n_envs <= 0 || b200env_state_layout(env_id, variant, &block, &slots)) return 0;
+    if (!block) return (size_t)slots * (size_t)n_envs;
+    return (size_t)((n_envs + block - 1) / block) * (size_t)block * (size_t)slots;
+}
+
 int b200env_rollout(int env_id, int dtype, int64_t n_envs, const void *params, size_t params_bytes,
                     const b200env_io *io, const b200env_rollout_spec *spec, uint32_t flags, uint64_t seed,
                     int64_t env_index_offset, void *cuda_stream) {

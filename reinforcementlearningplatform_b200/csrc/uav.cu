@@ -23,6 +23,27 @@
 #endif
 #include "uav_common.cuh"
 
+// Accessors of the persistent state buffer of the two UavFntsmcParam families: block-interleaved, element (field f,
+// instance i) at [((i / 128) * B200_UAV_STATE_SLOTS + f) * 128 + i % 128] (include/b200env.h, b200env_state_layout).
+// A thread's accesses to all fields are then ONE base register plus an immediate (f * 1024 B); with the field-major
+// layout of the other buffers ([f][n], n a run-time value) every access needed its own IMAD.WIDE and a live 64-bit register
+// pair: 144 -> 61 IMAD.WIDE in the position kernel, 0.220 -> 0.198 ms per 1 M instances (A/B on one box).  Coalescing is
+// unchanged (128 consecutive doubles per field and block).  -DB200_UAV_FIELD_MAJOR restores [f][n] (A/B only: the host
+// side follows b200env_state_layout).
+#ifndef B200_UAV_FIELD_MAJOR
+template <typename T, typename I>
+__device__ __forceinline__ const char *uav_blk_base(const void *base, I i) {
+    return static_cast<const char *>(base) +
+           (uint64_t)((uint32_t)i >> 7) * (uint64_t)(B200_UAV_STATE_SLOTS * 128 * sizeof(T)) +
+           ((uint32_t)i & 127u) * (uint32_t)sizeof(T);
+}
+#define UAV_LDS(base, n, field, i) (*reinterpret_cast<const T *>(uav_blk_base<T>(base, i) + (field) * (int)(128 * sizeof(T))))
+#define UAV_STS(base, n, field, i, v) (*reinterpret_cast<T *>(const_cast<char *>(uav_blk_base<T>(base, i)) + (field) * (int)(128 * sizeof(T))) = (v))
+#else
+#define UAV_LDS(base, n, field, i) ld<T>(base, n, field, i)
+#define UAV_STS(base, n, field, i, v) st<T>(base, n, field, i, v)
+#endif
+
 namespace {
 using namespace uavk;
 
@@ -50,14 +71,14 @@ __device__ __forceinline__ void att_reset_state(const P &p, const b200env_io &io
                                                 int64_t off, T *x /* out: 12 states */) {
     const uint32_t ep = io.episode[i];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = (T)p.init_state[6 + k]; st<T>(io.state, n, k, i, x[6 + k]); }
+    for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = (T)p.init_state[6 + k]; UAV_STS(io.state, n, k, i, x[6 + k]); }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        st<T>(io.state, n, A_S1 + k, i, (T)0);
-        st<T>(io.state, n, A_K1 + k, i, (T)p.att_k1[k]);
-        st<T>(io.state, n, A_K2 + k, i, (T)p.att_k2[k]);
-        st<T>(io.state, n, A_GAM + k, i, (T)p.att_gamma[k]);
-        st<T>(io.state, n, A_LMD + k, i, (T)p.att_lmd[k]);
+        UAV_STS(io.state, n, A_S1 + k, i, (T)0);
+        UAV_STS(io.state, n, A_K1 + k, i, (T)p.att_k1[k]);
+        UAV_STS(io.state, n, A_K2 + k, i, (T)p.att_k2[k]);
+        UAV_STS(io.state, n, A_GAM + k, i, (T)p.att_gamma[k]);
+        UAV_STS(io.state, n, A_LMD + k, i, (T)p.att_lmd[k]);
     }
     double A[3], Tp[3], ph[3];
     if (p.random_trajectory) { // uav_att_ctrl.py:156-161
@@ -75,9 +96,9 @@ __device__ __forceinline__ void att_reset_state(const P &p, const b200env_io &io
     if (p.yaw_fixed) { A[2] = 0.; ph[2] = 0.; }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        st<T>(io.state, n, A_AMP + k, i, (T)A[k]);
-        st<T>(io.state, n, A_PER + k, i, (T)Tp[k]);
-        st<T>(io.state, n, A_PHS + k, i, (T)ph[k]);
+        UAV_STS(io.state, n, A_AMP + k, i, (T)A[k]);
+        UAV_STS(io.state, n, A_PER + k, i, (T)Tp[k]);
+        UAV_STS(io.state, n, A_PHS + k, i, (T)ph[k]);
     }
     io.time[i] = 0.0;
     io.episode[i] = ep + 1u;
@@ -103,7 +124,7 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ UavDeri
     const Consts<T> c(p.m, p.g, p.J, p.kr, p.kt, p.dt, dv);
     T x[12];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = ld<T>(io.state, n, k, i); }
+    for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = UAV_LDS(io.state, n, k, i); }
     double time = io.time[i];
     T s1[3], k1[3], k2[3], gam[3], lmd[3], alpha[3], beta[3], ref[3], dref[3];
     T a[8], rA[3], rT[3], rP[3];
@@ -112,31 +133,31 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ UavDeri
     // all loads before the first store (see uav_pos_step_kernel)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        s1[k] = ld<T>(io.state, n, A_S1 + k, i);
-        rA[k] = ld<T>(io.state, n, A_AMP + k, i); rT[k] = ld<T>(io.state, n, A_PER + k, i); rP[k] = ld<T>(io.state, n, A_PHS + k, i);
+        s1[k] = UAV_LDS(io.state, n, A_S1 + k, i);
+        rA[k] = UAV_LDS(io.state, n, A_AMP + k, i); rT[k] = UAV_LDS(io.state, n, A_PER + k, i); rP[k] = UAV_LDS(io.state, n, A_PHS + k, i);
     }
     // get_param_from_actor, uav_att_ctrl_RL.py:141-156: a gain is overwritten only where the actor output is > 0 (N6)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        k1[k] = a[k] > (T)0 ? (T)10 * a[k] : ld<T>(io.state, n, A_K1 + k, i);
+        k1[k] = a[k] > (T)0 ? (T)10 * a[k] : UAV_LDS(io.state, n, A_K1 + k, i);
         // a / 10 as q = a r, q + (a - 10 q) r with r = RN(1 / 10): the correctly rounded quotient (Markstein; checked
         // against 300 k IEEE quotients incl. float32-valued a), without the IEEE division's slow-path branch
 #ifdef B200_STRICT_DIV
-        k2[k] = a[k + 3] > (T)0 ? a[k + 3] / (T)10 : ld<T>(io.state, n, A_K2 + k, i);
+        k2[k] = a[k + 3] > (T)0 ? a[k + 3] / (T)10 : UAV_LDS(io.state, n, A_K2 + k, i);
 #else
-        k2[k] = a[k + 3] > (T)0 ? Divisor<T>((T)10, (T)0.1).div(a[k + 3]) : ld<T>(io.state, n, A_K2 + k, i);
+        k2[k] = a[k + 3] > (T)0 ? Divisor<T>((T)10, (T)0.1).div(a[k + 3]) : UAV_LDS(io.state, n, A_K2 + k, i);
 #endif
-        gam[k] = a[6] > (T)0 ? a[6] : ld<T>(io.state, n, A_GAM + k, i);
-        lmd[k] = a[7] > (T)0 ? a[7] : ld<T>(io.state, n, A_LMD + k, i);
+        gam[k] = a[6] > (T)0 ? a[6] : UAV_LDS(io.state, n, A_GAM + k, i);
+        lmd[k] = a[7] > (T)0 ? a[7] : UAV_LDS(io.state, n, A_LMD + k, i);
         alpha[k] = (T)p.att_alpha[k];
         beta[k] = (T)p.att_beta[k];
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) { // early write-back
-        st<T>(io.state, n, A_K1 + k, i, k1[k]);
-        st<T>(io.state, n, A_K2 + k, i, k2[k]);
-        st<T>(io.state, n, A_GAM + k, i, gam[k]);
-        st<T>(io.state, n, A_LMD + k, i, lmd[k]);
+        UAV_STS(io.state, n, A_K1 + k, i, k1[k]);
+        UAV_STS(io.state, n, A_K2 + k, i, k2[k]);
+        UAV_STS(io.state, n, A_GAM + k, i, gam[k]);
+        UAV_STS(io.state, n, A_LMD + k, i, lmd[k]);
     }
     // ref_inner(time, A, T, 0, phase), ref_cmd.py:4-22
 #pragma unroll
@@ -149,7 +170,7 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ UavDeri
     T torque[3], d1[3];
     att_control<T>(c, x, t1, k1, k2, gam, lmd, alpha, beta, s1, ref, dref, torque, d1);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) st<T>(io.state, n, A_S1 + k, i, s1[k]);
+    for (int k = 0; k < 3; ++k) UAV_STS(io.state, n, A_S1 + k, i, s1[k]);
     const T u_acc = -(torque[0] * torque[0] * (T)p.R[0] + torque[1] * torque[1] * (T)p.R[1] + torque[2] * torque[2] * (T)p.R[2]);
     if (io.obs) { // current_state = get_state()
 #pragma unroll
@@ -195,11 +216,11 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ UavDeri
         att_observe<T>(xr, tr, ref, dref, nxt); // first obs of the next episode against the stale ref (reference quirk)
     } else {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) st<T>(io.state, n, k, i, x[6 + k]);
+        for (int k = 0; k < 6; ++k) UAV_STS(io.state, n, k, i, x[6 + k]);
         io.time[i] = time;
         if (done) { // keep the last reference for a later explicit reset()/observe()
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { st<T>(io.state, n, A_REF + k, i, ref[k]); st<T>(io.state, n, A_DREF + k, i, dref[k]); }
+            for (int k = 0; k < 3; ++k) { UAV_STS(io.state, n, A_REF + k, i, ref[k]); UAV_STS(io.state, n, A_DREF + k, i, dref[k]); }
         }
     }
     if (io.reset_obs) {
@@ -218,14 +239,14 @@ uav_att_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200en
     T x[12];
     if (observe_only) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = ld<T>(io.state, n, k, i); }
+        for (int k = 0; k < 6; ++k) { x[k] = (T)0; x[6 + k] = UAV_LDS(io.state, n, k, i); }
     } else {
         att_reset_state<T, int64_t>(p, io, n, i, seed, off, x);
     }
     if (io.next_obs) {
         T ref[3], dref[3], o[6];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { ref[k] = ld<T>(io.state, n, A_REF + k, i); dref[k] = ld<T>(io.state, n, A_DREF + k, i); }
+        for (int k = 0; k < 3; ++k) { ref[k] = UAV_LDS(io.state, n, A_REF + k, i); dref[k] = UAV_LDS(io.state, n, A_DREF + k, i); }
         Trig<T> t;
         t.eval(x[6], x[7], x[8], false);
         att_observe<T>(x, t, ref, dref, o);
@@ -243,15 +264,15 @@ __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io
                                                 int64_t off, T *x) {
     const uint32_t ep = io.episode[i];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) { x[k] = (T)p.init_state[k]; st<T>(io.state, n, k, i, x[k]); }
+    for (int k = 0; k < 12; ++k) { x[k] = (T)p.init_state[k]; UAV_STS(io.state, n, k, i, x[k]); }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        st<T>(io.state, n, P_SIG + k, i, (T)0);
-        st<T>(io.state, n, P_S1 + k, i, (T)0);
-        st<T>(io.state, n, P_K1 + k, i, (T)p.pos_k1[k]);
-        st<T>(io.state, n, P_K2 + k, i, (T)p.pos_k2[k]);
-        st<T>(io.state, n, P_GAM + k, i, (T)p.pos_gamma[k]);
-        st<T>(io.state, n, P_LMD + k, i, (T)p.pos_lmd[k]);
+        UAV_STS(io.state, n, P_SIG + k, i, (T)0);
+        UAV_STS(io.state, n, P_S1 + k, i, (T)0);
+        UAV_STS(io.state, n, P_K1 + k, i, (T)p.pos_k1[k]);
+        UAV_STS(io.state, n, P_K2 + k, i, (T)p.pos_k2[k]);
+        UAV_STS(io.state, n, P_GAM + k, i, (T)p.pos_gamma[k]);
+        UAV_STS(io.state, n, P_LMD + k, i, (T)p.pos_lmd[k]);
     }
     double A[4], Tp[4], ph[4];
     Philox rng(seed, (uint64_t)(off + (int64_t)i), ep);
@@ -268,9 +289,9 @@ __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io
     if (p.yaw_fixed) { A[3] = 0.; ph[3] = 0.; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        st<T>(io.state, n, P_AMP + k, i, (T)A[k]);
-        st<T>(io.state, n, P_PER + k, i, (T)Tp[k]);
-        st<T>(io.state, n, P_PHS + k, i, (T)ph[k]);
+        UAV_STS(io.state, n, P_AMP + k, i, (T)A[k]);
+        UAV_STS(io.state, n, P_PER + k, i, (T)Tp[k]);
+        UAV_STS(io.state, n, P_PHS + k, i, (T)ph[k]);
     }
     if (p.random_pos0) { // uav_pos_ctrl.py:510-513 -> set_random_init_pos :457-465 -> reset_uav_with_param uav.py:252-268
 #pragma unroll
@@ -280,10 +301,10 @@ __device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io
             const double r = ::fabs(p.init_pos_r[k]);
             const double pos0 = rng.uniform(t0 - r, t0 + r);
             x[k] = (T)pos0;
-            x[9 + k] = ld<T>(io.state, n, P_NEXT_PQR0 + k, i); // new_param.pqr0 = init_state[9:12] = the previous pos0 (N5)
-            st<T>(io.state, n, k, i, x[k]);
-            st<T>(io.state, n, 9 + k, i, x[9 + k]);
-            st<T>(io.state, n, P_NEXT_PQR0 + k, i, x[k]);      // init_state = concat(pos0, vel0, angle0, pos0)
+            x[9 + k] = UAV_LDS(io.state, n, P_NEXT_PQR0 + k, i); // new_param.pqr0 = init_state[9:12] = the previous pos0 (N5)
+            UAV_STS(io.state, n, k, i, x[k]);
+            UAV_STS(io.state, n, 9 + k, i, x[9 + k]);
+            UAV_STS(io.state, n, P_NEXT_PQR0 + k, i, x[k]);      // init_state = concat(pos0, vel0, angle0, pos0)
         }
     }
     // att_ref is not reset by the reference (uav_pos_ctrl.py:488-533): left as stored
@@ -297,7 +318,7 @@ __device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c,
                                                  uint32_t flags, uint64_t seed, int64_t off) {
     T x[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) x[k] = ld<T>(io.state, n, k, i);
+    for (int k = 0; k < 12; ++k) x[k] = UAV_LDS(io.state, n, k, i);
     double time = io.time[i];
     T a[8], dis[3] = {(T)0, (T)0, (T)0};
 #pragma unroll
@@ -310,12 +331,12 @@ __device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c,
     // buffer (possible aliasing), and a mid-kernel DRAM load is not hidden by the 4 resident warps per scheduler.
     T sig[3], s1[3], aref0, aref1, rA[4], rT[4], rP[4];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { sig[k] = ld<T>(io.state, n, P_SIG + k, i); s1[k] = ld<T>(io.state, n, P_S1 + k, i); }
-    aref0 = ld<T>(io.state, n, P_AREF + 0, i);
-    aref1 = ld<T>(io.state, n, P_AREF + 1, i);
+    for (int k = 0; k < 3; ++k) { sig[k] = UAV_LDS(io.state, n, P_SIG + k, i); s1[k] = UAV_LDS(io.state, n, P_S1 + k, i); }
+    aref0 = UAV_LDS(io.state, n, P_AREF + 0, i);
+    aref1 = UAV_LDS(io.state, n, P_AREF + 1, i);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        rA[k] = ld<T>(io.state, n, P_AMP + k, i); rT[k] = ld<T>(io.state, n, P_PER + k, i); rP[k] = ld<T>(io.state, n, P_PHS + k, i);
+        rA[k] = UAV_LDS(io.state, n, P_AMP + k, i); rT[k] = UAV_LDS(io.state, n, P_PER + k, i); rP[k] = UAV_LDS(io.state, n, P_PHS + k, i);
     }
     // Every persistent field is written back as soon as its new value is known (short register live ranges; a later
     // auto-reset simply overwrites what it redefines).
@@ -323,14 +344,14 @@ __device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c,
     T k1[3], k2[3], gam[3], lmd[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        k1[k] = a[k] > (T)0 ? a[k] : ld<T>(io.state, n, P_K1 + k, i);
-        k2[k] = a[k + 3] > (T)0 ? a[k + 3] : ld<T>(io.state, n, P_K2 + k, i);
-        gam[k] = a[6] > (T)0 ? a[6] : ld<T>(io.state, n, P_GAM + k, i);
-        lmd[k] = a[7] > (T)0 ? a[7] : ld<T>(io.state, n, P_LMD + k, i);
-        st<T>(io.state, n, P_K1 + k, i, k1[k]);
-        st<T>(io.state, n, P_K2 + k, i, k2[k]);
-        st<T>(io.state, n, P_GAM + k, i, gam[k]);
-        st<T>(io.state, n, P_LMD + k, i, lmd[k]);
+        k1[k] = a[k] > (T)0 ? a[k] : UAV_LDS(io.state, n, P_K1 + k, i);
+        k2[k] = a[k + 3] > (T)0 ? a[k + 3] : UAV_LDS(io.state, n, P_K2 + k, i);
+        gam[k] = a[6] > (T)0 ? a[6] : UAV_LDS(io.state, n, P_GAM + k, i);
+        lmd[k] = a[7] > (T)0 ? a[7] : UAV_LDS(io.state, n, P_LMD + k, i);
+        UAV_STS(io.state, n, P_K1 + k, i, k1[k]);
+        UAV_STS(io.state, n, P_K2 + k, i, k2[k]);
+        UAV_STS(io.state, n, P_GAM + k, i, gam[k]);
+        UAV_STS(io.state, n, P_LMD + k, i, lmd[k]);
     }
     // ---- ref_uav(time, A, T, bias, phase), ref_cmd.py:25-43
     T ref[4], dref[4], ddref[4];
@@ -345,7 +366,7 @@ __device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c,
         const T e = x[k] - ref[k], de = x[3 + k] - dref[k];
         T so, dso1, pa1_de;
         smc_axis<T>(e, de, k1[k], gam[k], (T)p.pos_alpha[k], (T)p.pos_beta[k], lmd[k], c.dt, sig[k], so, dso1, pa1_de);
-        st<T>(io.state, n, P_SIG + k, i, sig[k]);
+        UAV_STS(io.state, n, P_SIG + k, i, sig[k]);
         const T uo1 = kt_m * x[3 + k] + ddref[k] - k1[k] * de - pa1_de - lmd[k] * dso1;
         const T uo2 = -k2[k] * so;
         ctrl[k] = uo1 + uo2;
@@ -376,7 +397,7 @@ __device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c,
     for (int k = 0; k < 3; ++k) {
         drho_d[k] = clampc<T>(drho_d[k], -rl, rl);
         rho_d[k] = rho_d[k] + drho_d[k] * c.dt;
-        st<T>(io.state, n, P_AREF + k, i, rho_d[k]); // att_ref = rho_d (persists across resets, uav_pos_ctrl.py:329)
+        UAV_STS(io.state, n, P_AREF + k, i, rho_d[k]); // att_ref = rho_d (persists across resets, uav_pos_ctrl.py:329)
     }
     // ---- att_control, uav_pos_ctrl.py:317-337
     T torque[3], d1[3], ak1[3], ak2[3], agam[3], almd[3], aalpha[3], abeta[3];
@@ -387,7 +408,7 @@ __device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c,
     }
     att_control<T>(c, x, t1, ak1, ak2, agam, almd, aalpha, abeta, s1, rho_d, drho_d, torque, d1);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) st<T>(io.state, n, P_S1 + k, i, s1[k]);
+    for (int k = 0; k < 3; ++k) UAV_STS(io.state, n, P_S1 + k, i, s1[k]);
     if (io.obs) { // current_state = get_state(), uav_pos_ctrl_RL.py:59-68
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -424,11 +445,11 @@ __device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c,
         for (int k = 0; k < 3; ++k) { nxt[k] = xr[k] - ref[k]; nxt[3 + k] = xr[3 + k] - dref[k]; } // stale pos_ref (quirk)
     } else {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) st<T>(io.state, n, k, i, x[k]);
+        for (int k = 0; k < 12; ++k) UAV_STS(io.state, n, k, i, x[k]);
         io.time[i] = time;
         if (done) { // keep the last reference for a later explicit reset()/observe()
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { st<T>(io.state, n, P_PREF + k, i, ref[k]); st<T>(io.state, n, P_DPREF + k, i, dref[k]); }
+            for (int k = 0; k < 3; ++k) { UAV_STS(io.state, n, P_PREF + k, i, ref[k]); UAV_STS(io.state, n, P_DPREF + k, i, dref[k]); }
         }
     }
     if (io.reset_obs) {
@@ -486,15 +507,15 @@ uav_pos_reset_kernel(const __grid_constant__ P p, const __grid_constant__ b200en
     T x[12];
     if (observe_only) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) x[k] = ld<T>(io.state, n, k, i);
+        for (int k = 0; k < 12; ++k) x[k] = UAV_LDS(io.state, n, k, i);
     } else {
         pos_reset_state<T, int64_t>(p, io, n, i, seed, off, x);
     }
     if (io.next_obs) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            stio<T, IO32>(io.next_obs, n, k, i, x[k] - ld<T>(io.state, n, P_PREF + k, i));
-            stio<T, IO32>(io.next_obs, n, 3 + k, i, x[3 + k] - ld<T>(io.state, n, P_DPREF + k, i));
+            stio<T, IO32>(io.next_obs, n, k, i, x[k] - UAV_LDS(io.state, n, P_PREF + k, i));
+            stio<T, IO32>(io.next_obs, n, 3 + k, i, x[3 + k] - UAV_LDS(io.state, n, P_DPREF + k, i));
         }
     }
 }

@@ -152,7 +152,7 @@ class _UavBase(VecEnvBase):
         exists for scripts that set gains once and then run the controller with them (``step_fixed_gains``)."""
         a = self._as_soa(action_from_actor, 8).to(self.dtype)
         k1, k2, gm, ld = (self.STATE_FIELDS.index(f) for f in self._GAIN_FIELDS)
-        st = self._state
+        st = self._state                # logical copy (the UAV state buffer is block-interleaved on the device)
         # a device-side divisor: torch turns division by a host scalar into a multiplication by its reciprocal,
         # which is not the IEEE quotient `a / 10` of the reference (and of the fused kernel)
         k2_div = torch.full((), self.K2_DIV, dtype=self.dtype, device=self.device)
@@ -161,6 +161,7 @@ class _UavBase(VecEnvBase):
             st[k2 + i] = torch.where(a[3 + i] > 0, a[3 + i] / k2_div, st[k2 + i])
             st[gm + i] = torch.where(a[6] > 0, a[6], st[gm + i])
             st[ld + i] = torch.where(a[7] > 0, a[7], st[ld + i])
+        self._write_state(st)
 
     def step_fixed_gains(self, dis=None) -> None:
         """One control period with the gains currently stored per instance: ``generate_action_4_uav()`` /

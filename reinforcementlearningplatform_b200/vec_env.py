@@ -15,6 +15,7 @@ and fills the parameter struct from the reference attribute names.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -73,7 +74,13 @@ class VecEnvBase:
         self._sf, self._od, self._ad, self._dd = sf, od, ad, dd
         N, dev = self.n_envs, self.device
         z = lambda *shape, dt=io_dtype: torch.zeros(*shape, dtype=dt, device=dev)
-        self._state = z(sf, N, dt=dtype)
+        # the buffer the kernels see: field-major [sf, N], or block-interleaved [blocks, slots, B] (UAV families,
+        # include/b200env.h b200env_state_layout); `self._state` is always the logical [sf, N] picture
+        self._blk, self._slots = _lib.state_layout(self.ENV_ID, self.VARIANT)
+        if self._blk:
+            self._state_raw = z((N + self._blk - 1) // self._blk, self._slots, self._blk, dt=dtype)
+        else:
+            self._state_raw = z(sf, N, dt=dtype)
         self._time = z(N, dt=torch.float64)
         self._episode = z(N, dt=torch.int32)  # bit pattern of the u32 episode counter
         self._obs = z(od, N)
@@ -109,7 +116,7 @@ class VecEnvBase:
 
     def _io(self, action=None, dis=None, obs=True, reset_obs=True) -> _lib.IO:
         io = _lib.IO()
-        io.state = self._state.data_ptr()
+        io.state = self._state_raw.data_ptr()
         io.time = self._time.data_ptr()
         io.episode = self._episode.data_ptr()
         io.action = None if action is None else action.data_ptr()
@@ -232,13 +239,13 @@ class VecEnvBase:
             io = self._hot_io = self._io()
             self._hot_args = (self.ENV_ID, self._dt_code, self.n_envs, C.byref(self._params), C.sizeof(self._params),
                               C.byref(io))
-            self._dev_index = self._state.device.index
+            self._dev_index = self._state_raw.device.index
         io.action = action_soa.data_ptr()
         io.dis = None if dis_soa is None else dis_soa.data_ptr()
         io.obs = None if reuse else self._obs.data_ptr()
         io.reset_obs = self._reset_obs.data_ptr()
         self._policy_obs_valid = True
-        stream = torch.cuda.current_stream(self._state.device).cuda_stream
+        stream = torch.cuda.current_stream(self._state_raw.device).cuda_stream
         if torch.cuda.current_device() != self._dev_index:
             with torch.cuda.device(self._dev_index):
                 rc = self._lib.b200env_step(*self._hot_args, _lib.AUTO_RESET if self.auto_reset else 0, self.seed,
@@ -259,7 +266,7 @@ class VecEnvBase:
         for t, shape, dt in ((obs, (self._od, self.n_envs), io_dt), (next_obs, (self._od, self.n_envs), io_dt),
                              (reward, (self.n_envs,), io_dt), (done, (self.n_envs,), torch.uint8),
                              (flag, (self.n_envs,), torch.int32)):
-            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self._state.device:
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self._state_raw.device:
                 raise _lib.B200EnvError(f"step_into: expected contiguous {dt} tensor of shape {shape} on {self.device}")
         if action_soa.dtype != io_dt or (dis_soa is not None and dis_soa.dtype != io_dt):
             raise _lib.B200EnvError(f"step_into: action/dis must be {io_dt}")
@@ -289,12 +296,12 @@ class VecEnvBase:
                (next_obs, (T, self._od, N), self.io_dtype), (reward, (T, N), self.io_dtype),
                (done, (T, N), torch.uint8), (flag, (T, N), torch.int32))
         for t, shape, dt in chk:
-            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self._state.device:
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self._state_raw.device:
                 raise _lib.B200EnvError(f"rollout_into: expected contiguous {dt} tensor of shape {shape}")
         if dis is not None and (tuple(dis.shape) != (T, self._dd, N) or dis.dtype != self.io_dtype or not dis.is_contiguous()):
             raise _lib.B200EnvError("rollout_into: bad dis tensor")
         spec = _lib.RolloutSpec(T, self._ad * N, self._dd * N, self._od * N, self._od * N, N, N, N)
-        with torch.cuda.device(self._state.device):
+        with torch.cuda.device(self._state_raw.device):
             io = self._io(action, dis)
             io.obs, io.next_obs, io.reward = obs.data_ptr(), next_obs.data_ptr(), reward.data_ptr()
             io.done, io.flag = done.data_ptr(), flag.data_ptr()
@@ -310,6 +317,29 @@ class VecEnvBase:
     def is_Terminal(self) -> torch.Tensor:
         return self.is_terminal
 
+    # ------------------------------------------------------- logical view of the persistent state
+    @property
+    def _state(self) -> torch.Tensor:
+        """The persistent state as ``[state_fields, N]``.  Field-major envs: the device buffer itself (writes go through).
+        Block-interleaved envs (UAV): a COPY in logical order -- write back with ``_write_state``."""
+        if not self._blk:
+            return self._state_raw
+        raw = self._state_raw
+        nb, slots, B = raw.shape
+        return raw.permute(1, 0, 2).reshape(slots, nb * B)[:self._sf, :self.n_envs].contiguous()
+
+    def _write_state(self, logical: torch.Tensor) -> None:
+        """Logical ``[state_fields, N]`` -> the device layout."""
+        logical = torch.as_tensor(logical).to(self.device, self.dtype)
+        if not self._blk:
+            self._state_raw.copy_(logical)
+            return
+        raw = self._state_raw
+        nb, slots, B = raw.shape
+        full = torch.zeros(slots, nb * B, dtype=self.dtype, device=self.device)
+        full[:self._sf, :self.n_envs] = logical
+        raw.copy_(full.view(slots, nb, B).permute(1, 0, 2))
+
     # ------------------------------------------------------- state injection
     def get_state_buffers(self) -> dict:
         return {"state": self._state.clone(), "time": self._time.clone(), "episode": self._episode.clone()}
@@ -318,7 +348,7 @@ class VecEnvBase:
         """Inject SoA state ([fields, N]), time ([N]) -- parity re-sync and checkpoint restore."""
         self._policy_obs_valid = False  # the next step recomputes current_state in-kernel
         if state is not None:
-            self._state.copy_(torch.as_tensor(state).to(self.device, self.dtype))
+            self._write_state(state)
         if time is not None:
             self._time.copy_(torch.as_tensor(time).to(self.device, torch.float64))
         if episode is not None:
