@@ -170,7 +170,7 @@ typedef struct b200_uav_params {
     int32_t pad_;
 } b200_uav_params;
 
-/* The `state` buffer of B200ENV_UAV_ATT and B200ENV_UAV_POS is BLOCK-INTERLEAVED, not field-major: instances are grouped in
+/* The `state` buffer of B200ENV_UAV_ATT, B200ENV_UAV_POS and B200ENV_UAVROBUST is BLOCK-INTERLEAVED, not field-major: instances are grouped in
  * blocks of 128, every block holds B200_UAV_STATE_SLOTS field slots of 128 values, element (field f, instance i) lives at
  * [((i / 128) * B200_UAV_STATE_SLOTS + f) * 128 + i % 128], and the buffer has b200env_state_elems() elements (n rounded up to
  * a multiple of 128).  The kernels then reach every field of an instance with one base register plus an immediate offset

@@ -81,7 +81,7 @@ int b200env_state_layout(int env_id, int variant, int *block, int *slots) {
     int sf = 0;
     const int rc = f->dims(variant, &sf, nullptr, nullptr, nullptr);
     if (rc) return rc;
-    const bool blocked = env_id == B200ENV_UAV_ATT || env_id == B200ENV_UAV_POS;
+    const bool blocked = env_id == B200ENV_UAV_ATT || env_id == B200ENV_UAV_POS || env_id == B200ENV_UAVROBUST;
     if (block) *block = blocked ? B200_UAV_STATE_BLOCK : 0;
     if (slots) *slots = blocked ? B200_UAV_STATE_SLOTS : sf;
     return B200ENV_OK;

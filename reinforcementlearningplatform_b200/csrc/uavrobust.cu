@@ -56,7 +56,7 @@ __device__ __forceinline__ void observe(const RP &r, const RobDerived &rd, const
     if (V == 0 || V == 1) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            e_out[k] = x[k] - ld<T>(io.state, n, R_PREF + k, i);
+            e_out[k] = x[k] - UAV_LDS(io.state, n, R_PREF + k, i);
             de_out[k] = x[3 + k];
             o[k] = qdiv<T>(e_out[k], r.e_pos_span[k], rd.r_pos[k]) * g;
             o[3 + k] = qdiv<T>((T)2 * x[3 + k], r.vel_span[k], rd.r_vel[k]) * g;
@@ -64,16 +64,16 @@ __device__ __forceinline__ void observe(const RP &r, const RobDerived &rd, const
         if (V == 1) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                o[6 + k] = qdiv<T>(x[6 + k] - ld<T>(io.state, n, R_AREF + k, i), r.e_att_span[k], rd.r_att[k]) * g;
-                o[9 + k] = qdiv<T>(d1[k] - ld<T>(io.state, n, R_DAREF + k, i), r.e_dot_att_span_neg[k], rd.r_datt[k]) * g; // sic (N10)
+                o[6 + k] = qdiv<T>(x[6 + k] - UAV_LDS(io.state, n, R_AREF + k, i), r.e_att_span[k], rd.r_att[k]) * g;
+                o[9 + k] = qdiv<T>(d1[k] - UAV_LDS(io.state, n, R_DAREF + k, i), r.e_dot_att_span_neg[k], rd.r_datt[k]) * g; // sic (N10)
             }
         }
     } else {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             T ref, dref, dd;
-            ref_channel<T>((T)time, ld<T>(io.state, n, R_AMP + k, i), ld<T>(io.state, n, R_PER + k, i),
-                           V == 2 ? (T)0 : (T)r.ref_bias_a[k], ld<T>(io.state, n, R_PHS + k, i), ref, dref, dd);
+            ref_channel<T>((T)time, UAV_LDS(io.state, n, R_AMP + k, i), UAV_LDS(io.state, n, R_PER + k, i),
+                           V == 2 ? (T)0 : (T)r.ref_bias_a[k], UAV_LDS(io.state, n, R_PHS + k, i), ref, dref, dd);
             if (V == 2) {
                 e_out[k] = x[6 + k] - ref; de_out[k] = d1[k] - dref;
                 o[k] = qdiv<T>(e_out[k], r.e_att_span[k], rd.r_att[k]) * g;
@@ -96,10 +96,10 @@ __device__ __forceinline__ void reset_state(const RP &r, const b200env_io &io, i
     for (int k = 0; k < 3; ++k) { x[k] = (T)r.pos0[k]; x[3 + k] = (T)r.vel0[k]; x[6 + k] = (T)r.angle0[k]; x[9 + k] = (T)r.pqr0[k]; }
     if (V == 0 || V == 1) { // generate_random_point(offset = 1.0)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) st<T>(io.state, n, R_PREF + k, i, (T)rng.uniform(r.target_lo[k], r.target_hi[k]));
+        for (int k = 0; k < 3; ++k) UAV_STS(io.state, n, R_PREF + k, i, (T)rng.uniform(r.target_lo[k], r.target_hi[k]));
         if (V == 1) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) st<T>(io.state, n, R_AREF + k, i, (T)0); // UavHover.py:209
+            for (int k = 0; k < 3; ++k) UAV_STS(io.state, n, R_AREF + k, i, (T)0); // UavHover.py:209
         }
     } else {
         double A[3], Tp[3], ph[3];
@@ -111,9 +111,9 @@ __device__ __forceinline__ void reset_state(const RP &r, const b200env_io &io, i
         for (int k = 0; k < 3; ++k) ph[k] = rng.uniform(0., r.sig_phase_hi);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            st<T>(io.state, n, R_AMP + k, i, (T)A[k]);
-            st<T>(io.state, n, R_PER + k, i, (T)Tp[k]);
-            st<T>(io.state, n, R_PHS + k, i, (T)ph[k]);
+            UAV_STS(io.state, n, R_AMP + k, i, (T)A[k]);
+            UAV_STS(io.state, n, R_PER + k, i, (T)Tp[k]);
+            UAV_STS(io.state, n, R_PHS + k, i, (T)ph[k]);
         }
         if (V == 3) { // set_random_init_pos(trajectory[0], 0.3)
 #pragma unroll
@@ -124,7 +124,7 @@ __device__ __forceinline__ void reset_state(const RP &r, const b200env_io &io, i
         }
     }
 #pragma unroll
-    for (int k = 0; k < 12; ++k) st<T>(io.state, n, k, i, x[k]);
+    for (int k = 0; k < 12; ++k) UAV_STS(io.state, n, k, i, x[k]);
     // s1 (and att_ref / dot_att_ref except where noted) survive the reference's reset()
     io.time[i] = 0.0;
     io.episode[i] = ep + 1u;
@@ -140,7 +140,7 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
     const Consts<T> c(r.m, r.g, r.J, r.kr, r.kt, r.dt, dv);
     T x[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) x[k] = ld<T>(io.state, n, k, i);
+    for (int k = 0; k < 12; ++k) x[k] = UAV_LDS(io.state, n, k, i);
     double time = io.time[i];
     T a[AD], dis[3] = {(T)0, (T)0, (T)0};
 #pragma unroll
@@ -152,8 +152,8 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
     T s1[3], aref_old[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        s1[k] = (V == 0 || V == 3) ? ld<T>(io.state, n, R_S1 + k, i) : (T)0;
-        aref_old[k] = (V != 2) ? ld<T>(io.state, n, R_AREF + k, i) : (T)0;
+        s1[k] = (V == 0 || V == 3) ? UAV_LDS(io.state, n, R_S1 + k, i) : (T)0;
+        aref_old[k] = (V != 2) ? UAV_LDS(io.state, n, R_AREF + k, i) : (T)0;
     }
     Trig<T> t1;
     t1.eval(x[6], x[7], x[8], V != 2);
@@ -189,8 +189,8 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
             d = clampc<T>(d, (T)r.dot_att_min[k], (T)r.dot_att_max[k]);
             datt[k] = d;
             att_ref[k] = d * c.dt + aref_old[k];
-            st<T>(io.state, n, R_AREF + k, i, att_ref[k]);
-            st<T>(io.state, n, R_DAREF + k, i, d);
+            UAV_STS(io.state, n, R_AREF + k, i, att_ref[k]);
+            UAV_STS(io.state, n, R_DAREF + k, i, d);
         }
         if (V == 1) {
 #pragma unroll
@@ -206,7 +206,7 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 torque[k] = clampc<T>(torque[k], -(T)r.att_saturation[k], (T)r.att_saturation[k]);
-                st<T>(io.state, n, R_S1 + k, i, s1[k]);
+                UAV_STS(io.state, n, R_S1 + k, i, s1[k]);
             }
         }
         uav_rk44<T, false>(c, x, t1, uf, torque, dis);
@@ -226,7 +226,7 @@ uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavD
     const bool done = flag != 0;
     // the observation of the new state needs the freshly written att_ref / dot_att_ref (variant 1): program order
 #pragma unroll
-    for (int k = 0; k < 12; ++k) st<T>(io.state, n, k, i, x[k]);
+    for (int k = 0; k < 12; ++k) UAV_STS(io.state, n, k, i, x[k]);
     io.time[i] = time;
     Trig<T> t2;
     t2.eval(x[6], x[7], x[8], false);
@@ -289,7 +289,7 @@ uavrobust_reset_kernel(const __grid_constant__ RP r, const __grid_constant__ Rob
     T x[12];
     if (observe_only) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) x[k] = ld<T>(io.state, n, k, i);
+        for (int k = 0; k < 12; ++k) x[k] = UAV_LDS(io.state, n, k, i);
     } else {
         reset_state<T, V>(r, io, n, i, seed, off, x);
     }
