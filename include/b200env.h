@@ -557,6 +557,11 @@ B200_API int b200_adam_step(int n_seg, const int64_t *seg_off, const int64_t *se
                             float beta2, float eps, float max_norm, float grad_scale, float *grad_norm_out,
                             void *cuda_stream);
 
+/* The keyed permutation of [0, B) the kernels above draw mini-batches from, evaluated on the HOST (no GPU involved):
+ * out_host[j] = position first + j of the permutation with key perm_key.  For tests and for callers that want to know
+ * which samples a mini-batch held. */
+B200_API int b200_ppo2_permutation(uint64_t perm_key, int64_t B, int64_t first, int64_t count, int64_t *out_host);
+
 /* The whole K_epochs x mini-batch loop of learn() on one stream without returning to the host between mini-batches
  * (single-GPU training; with several ranks the caller alternates b200_ppo2_grad, the all-reduce and b200_adam_step
  * itself).  Epoch e uses permutation key perm_key + e; mini-batch j covers positions j * mini_batch .. of it (the last

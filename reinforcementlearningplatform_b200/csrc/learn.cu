@@ -884,6 +884,14 @@ extern "C" B200_API int b200_ppo2_learn(const b200_ppo2_batch *batch, const b200
     return B200ENV_OK;
 }
 
+extern "C" B200_API int b200_ppo2_permutation(uint64_t perm_key, int64_t B, int64_t first, int64_t count, int64_t *out_host) {
+    if (B <= 0 || first < 0 || count < 0 || first + count > B) return B200ENV_ESIZE;
+    if (!out_host && count) return B200ENV_ENULL;
+    const int hb = half_bits_for(B);
+    for (int64_t j = 0; j < count; ++j) out_host[j] = perm_index(perm_key, first + j, B, hb);
+    return B200ENV_OK;
+}
+
 #ifdef LEARN_TRACE
 extern "C" B200_API int b200_learn_trace_read(long long *host) {
     cudaDeviceSynchronize();
