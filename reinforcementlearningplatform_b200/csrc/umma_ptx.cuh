@@ -58,8 +58,14 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;
     const long long t0 = clock64();
-    for (uint32_t spins = 1; !mbar_try(bar, parity); ++spins)
-        if ((spins & 63u) == 0 && clock64() - t0 > WAIT_TIMEOUT) __trap();
+    for (;;) {
+        // the clock is read once per 1024 probes: inside the probe loop it was a third of the loop's instructions, and
+        // the epilogue warps of the policy kernels spend ~18 probes per layer hand-off
+#pragma unroll 1
+        for (int k = 0; k < 1024; ++k)
+            if (mbar_try(bar, parity)) return;
+        if (clock64() - t0 > WAIT_TIMEOUT) __trap();
+    }
 }
 // true for exactly one lane of a converged warp
 __device__ __forceinline__ bool elect_one_sync() {
