@@ -37,7 +37,13 @@ def gather_batch_stats(batch: torch.Tensor, out: Optional[torch.Tensor] = None, 
     w = dist.get_world_size(group)
     if out is None or out.shape[0] != w:
         out = torch.zeros((w,) + tuple(batch.shape[1:]), dtype=batch.dtype, device=batch.device)
-    dist.all_gather_into_tensor(out, batch.contiguous(), group=group)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, batch.contiguous(), group=group)
+    else:   # gloo (CPU tests, two ranks on one GPU): all_gather has no CUDA path there -- 3 x dim doubles via the host
+        mine = batch.detach().cpu().contiguous()
+        parts = [torch.empty_like(mine) for _ in range(w)]
+        dist.all_gather(parts, mine, group=group)
+        out.copy_(torch.cat(parts, 0).to(out.device))
     return out
 
 
