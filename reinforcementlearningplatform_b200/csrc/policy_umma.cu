@@ -41,6 +41,7 @@
 // (LBO): element (row, k) of an operand with R rows lives at (k / 4) * R * 16 + row * 16 + (k % 4) * 4.  With thread =
 // row the epilogue's 16-byte stores of a warp are 512 contiguous bytes: conflict-free without swizzling.
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "policy_common.cuh"
 #include "umma_ptx.cuh"
 
@@ -67,6 +68,8 @@ struct ULayer {
     int out_act;     // output layers: 0 identity, 1 relu
     uint32_t w_off;  // byte offset of the layer's image: k-step kk at w_off + kk * N * 64 (hi plane N * 32 B, then lo)
     int b_off;       // float offset of the layer's bias (tanh layers: pre-multiplied by 2 log2 e)
+    int f16;         // operands as fp16 hi / lo pairs, weights pre-scaled by a power of two (streamed mode, layers after the
+                     // first): k-steps of 16, half the image bytes and half the MMAs of the 3xTF32 form (policy_umma16.cu)
 };
 
 struct UPlan {
@@ -76,7 +79,7 @@ struct UPlan {
     int tmem_cols, slot_cols, pong_off, a_col;   // per slot: D ping at +0, D pong at +pong_off, A hi plane at +a_col,
                                                  // A lo plane at +a_col + 32 * nbuf (a_tmem only)
     uint32_t img_bytes;
-    int bias_floats;
+    int bias_floats, zs_off;   // zs_off: per-layer accumulator scale (x 2 log2 e for tanh layers) inside the bias array
     uint32_t stage_bytes;
     uint32_t off_a, off_b, off_bias, off_scr, smem_bytes;  // dynamic shared memory map (after the barrier block)
     ULayer L[UM_MAX_LAYERS];
@@ -134,13 +137,30 @@ __device__ __forceinline__ void store_split4(unsigned char *chunk, int q, int r,
     *reinterpret_cast<uint4 *>(p + PLANE) = lo;
 }
 
+// eight activations of row r -> fp16 hi / lo pairs -> one 16-byte store into each plane of fp16 slab q8 (8 K columns)
+__device__ __forceinline__ void store_split8(unsigned char *chunk, int q8, int r, const float *y) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const __half2 h = __floats2half2_rn(y[2 * p], y[2 * p + 1]);
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn(y[2 * p] - f.x, y[2 * p + 1] - f.y);
+        hi[p] = *reinterpret_cast<const uint32_t *>(&h);
+        lo[p] = *reinterpret_cast<const uint32_t *>(&l);
+    }
+    unsigned char *p = chunk + (uint32_t)q8 * SLAB + (uint32_t)r * 16;
+    *reinterpret_cast<uint4 *>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4 *>(p + PLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 // hidden-layer epilogue for W accumulator columns of row r: D -> tanh(D + b) -> next layer's A chunk.  Written in
 // stages over all W values (bias loads first, then every FFMA, every ex2, every rcp ...) so that ptxas sees W independent
 // chains: the first version interleaved four values per 16-byte store and reloaded the bias between stores, which
 // serialised the groups behind possible shared-memory aliasing -- 2000 cycles per 32-column chunk in the event trace
 // against 512 cycles of SFU time.  The accumulator load is issued before the wait for the destination buffer.
 template <int W, bool A_TMEM>
-__device__ __forceinline__ void epi_tanh_chunk(uint32_t taddr, const float *bias_scaled, unsigned char *chunk, int q0, int r,
+__device__ __forceinline__ void epi_tanh_chunk(uint32_t taddr, const float *bias_scaled, float zs, bool next_f16,
+                                               unsigned char *chunk, int q0, int r,
                                                uint32_t a_hi_t, uint32_t a_lo_t, uint32_t free_bar, uint32_t free_parity,
                                                int trace_role, int &utrace_pos) {
     uint32_t v[W];
@@ -161,7 +181,7 @@ __device__ __forceinline__ void epi_tanh_chunk(uint32_t taddr, const float *bias
     // sharing one rcp between two or four activations saves SFU operations but costs 2.5 / 3.25 extra issue slots per
     // activation (multiplies + an overflow clamp) and measured no faster (profiles/r2/policy_umma.md).
 #pragma unroll
-    for (int j = 0; j < W; ++j) t[j] = fmaf(__uint_as_float(v[j]), TWO_LOG2E, t[j]);
+    for (int j = 0; j < W; ++j) t[j] = fmaf(__uint_as_float(v[j]), zs, t[j]);   // zs = 2 log2 e / (the layer's weight scale)
 #pragma unroll
     for (int j = 0; j < W; ++j) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(t[j]));
 #pragma unroll
@@ -189,6 +209,11 @@ __device__ __forceinline__ void epi_tanh_chunk(uint32_t taddr, const float *bias
             for (int c = 0; c + 16 <= W; c += 16) tmem_st16(a_lo_t + c, v + c);
         }
         tmem_wait_st();
+    } else if (next_f16) {
+        // the consumer layer multiplies fp16 pairs: slabs of 8 K columns; q0 counts 4-column slabs of this thread's offset
+#pragma unroll
+        for (int q = 0; q < W / 8; ++q) store_split8(chunk, (q0 >> 1) + q, r, t + 8 * q);
+        fence_proxy_async();
     } else {
 #pragma unroll
         for (int q = 0; q < W / 4; ++q) store_split4(chunk, q0 + q, r, t[4 * q + 0], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
@@ -238,7 +263,8 @@ __device__ __forceinline__ void mma_issue_loop(const UPlan &P, uint32_t s, uint3
         if (grp * slots + (int64_t)s >= tiles) break;
         for (int li = 0; li < n_layers; ++li) {
             const int K = P.L[li].K, N = P.L[li].N;
-            const uint32_t idesc = umma_idesc_tf32(TILE_M, N);
+            const bool f16 = !A_TMEM && P.L[li].f16 != 0;                    // fp16 pairs: k-steps of 16 (2 slabs of 8)
+            const uint32_t idesc = f16 ? umma_idesc_f16(TILE_M, N) : umma_idesc_tf32(TILE_M, N);
             const uint32_t b_lbo16 = (uint32_t)N << 16;                      // (N * 16 B >> 4) in the LBO field
             const uint32_t kstep16 = (uint32_t)N * 4, blo16 = (uint32_t)N * 2;   // N * 64 B and N * 32 B, >> 4
             const uint32_t dcol = slot_t + (ld & 1u) * pong_off;
@@ -253,7 +279,7 @@ __device__ __forceinline__ void mma_issue_loop(const UPlan &P, uint32_t s, uint3
                 // A operand of k-step j: TMEM address or shared-memory descriptor (low word) of the hi plane
                 uint32_t a_hi = A_TMEM ? a_tm + buf * CHUNK_K
                                        : (a_ring16 + ((s << nbuf_log2) + buf) * (CHUNK >> 4)) | a_lbo16;
-                const int ksteps = min(CHUNK_K, K - k0) >> 3;
+                const int ksteps = min(CHUNK_K, K - k0) >> (f16 ? 4 : 3);
                 for (int j = 0; j < ksteps; ++j) {
                     uint32_t stage = 0;
                     if (STREAMED) {
@@ -267,6 +293,11 @@ __device__ __forceinline__ void mma_issue_loop(const UPlan &P, uint32_t s, uint3
                         umma_tf32_ts(dcol, a_hi, b_hi + blo16, desc_hi, idesc, 1u);
                         umma_tf32_ts(dcol, a_hi, b_hi, desc_hi, idesc, 1u);
                         a_hi += 8;                                                                  // 8 columns of K
+                    } else if (f16) {
+                        umma_f16_lohi(1u, dcol, a_hi + (PLANE >> 4), b_hi, desc_hi, idesc, acc);
+                        umma_f16_lohi(1u, dcol, a_hi, b_hi + blo16, desc_hi, idesc, 1u);
+                        umma_f16_lohi(1u, dcol, a_hi, b_hi, desc_hi, idesc, 1u);
+                        a_hi += (2 * SLAB) >> 4;                                                    // 16 columns of K
                     } else {
                         umma_tf32_lohi(1u, dcol, a_hi + (PLANE >> 4), b_hi, desc_hi, idesc, acc);
                         umma_tf32_lohi(1u, dcol, a_hi, b_hi + blo16, desc_hi, idesc, 1u);
@@ -372,7 +403,9 @@ __device__ __forceinline__ void epilogue_loop(const UArgs &a, int64_t n, unsigne
             if (tracer) UTRACE(s, 200 + li);
             const uint32_t dcol = slot_t + (uint32_t)((layers_done & 1) * P.pong_off);
             ++layers_done;
+            const float zs = bias_s[P.zs_off + li];   // accumulator scale: 1 / (weight scale), x 2 log2 e for tanh layers
             if (L.role == 0) {
+                const bool nf16 = !A_TMEM && P.L[li + 1 < P.n_layers ? li + 1 : li].f16 != 0;
                 for (int c0 = 0; c0 < L.N; c0 += CHUNK_K) {
                     const int buf = g & nbuf_mask;
                     const uint32_t fbar = afr + buf * 8, fpar = ((g >> P.nbuf_log2) & 1) ^ 1;
@@ -380,11 +413,11 @@ __device__ __forceinline__ void epilogue_loop(const UArgs &a, int64_t n, unsigne
                     const uint32_t t_hi = a_hi_base + (uint32_t)(buf * CHUNK_K);
                     if (L.N - c0 >= CHUNK_K) {                      // 32 columns: 16 each
                         const int o = 16 * h;
-                        epi_tanh_chunk<16, A_TMEM>(dcol + c0 + o, bias_s + L.b_off + c0 + o, chunk, o / 4, r, t_hi + o,
+                        epi_tanh_chunk<16, A_TMEM>(dcol + c0 + o, bias_s + L.b_off + c0 + o, zs, nf16, chunk, o / 4, r, t_hi + o,
                                                    t_hi + a_lo_off + o, fbar, fpar, tracer ? s : -1, utrace_pos);
                     } else {                                        // 16 columns: 8 each
                         const int o = 8 * h;
-                        epi_tanh_chunk<8, A_TMEM>(dcol + c0 + o, bias_s + L.b_off + c0 + o, chunk, o / 4, r, t_hi + o,
+                        epi_tanh_chunk<8, A_TMEM>(dcol + c0 + o, bias_s + L.b_off + c0 + o, zs, nf16, chunk, o / 4, r, t_hi + o,
                                                   t_hi + a_lo_off + o, fbar, fpar, tracer ? s : -1, utrace_pos);
                     }
                     if (tracer) UTRACE(s, 300 + li);
@@ -401,7 +434,7 @@ __device__ __forceinline__ void epilogue_loop(const UArgs &a, int64_t n, unsigne
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        float m = __uint_as_float(v[j]) + bias_s[L.b_off + j];
+                        float m = fmaf(__uint_as_float(v[j]), zs, bias_s[L.b_off + j]);
                         if (L.out_act == 1) m = fmaxf(m, 0.0f);
                         scr[j * TILE_M] = m;
                     }
@@ -412,7 +445,7 @@ __device__ __forceinline__ void epilogue_loop(const UArgs &a, int64_t n, unsigne
                 uint32_t v[1];
                 tmem_ld<1>(dcol, v);
                 tmem_wait_ld();
-                if (live) __stcs(a.io.value + i, __uint_as_float(v[0]) + bias_s[L.b_off]);
+                if (live) __stcs(a.io.value + i, fmaf(__uint_as_float(v[0]), zs, bias_s[L.b_off]));
                 tc_fence_before();
             }
         }
@@ -489,7 +522,7 @@ policy_umma_kernel(const __grid_constant__ UArgs a, int64_t n) {
                     for (int li = 0; li < P.n_layers; ++li) {
                         const ULayer &L = P.L[li];
                         const uint32_t kstep_bytes = (uint32_t)L.N * 64;
-                        for (int kk = 0; kk < L.K / 8; ++kk, ++h) {
+                        for (int kk = 0; kk < L.K / (L.f16 ? 16 : 8); ++kk, ++h) {
                             const int stage = h & (NSTAGE - 1);
                             mbar_wait(sbase + BarMap::b_empty + stage * 8, ((h / NSTAGE) & 1) ^ 1);
                             const uint32_t bar = sbase + BarMap::b_full + stage * 8;
@@ -517,30 +550,67 @@ struct PackArgs {
     const float *b[UM_MAX_LAYERS];
     unsigned char *image;
     float *bias;
+    int zs_off;
 };
 
-// nn.Linear weights [n_real][k_real] -> the UMMA image (per k-step: hi plane, lo plane; element (n, k) of a plane at
-// (k % 8 / 4) * N * 16 + n * 16 + (k % 4) * 4, zero-padded) and the bias vector (tanh layers: times 2 log2 e)
-__global__ void policy_pack_kernel(const __grid_constant__ PackArgs a) {
+// nn.Linear weights [n_real][k_real] -> the UMMA image, zero-padded, and the bias vector (tanh layers: times 2 log2 e).
+// TF32 layers: per k-step of 8 a hi and a lo plane, element (n, k) of a plane at (k % 8 / 4) * N * 16 + n * 16 + (k % 4) * 4.
+// fp16 layers (L.f16): weights times 2^s, s chosen per layer so that max |w| 2^s lies in [2^13, 2^14); per k-step of 16 a hi
+// and a lo plane of fp16, element (n, k) at (k % 16 / 8) * N * 16 + n * 16 + (k % 8) * 2.  zs[l] = 2^-s (x 2 log2 e for tanh
+// layers) is what the epilogue multiplies the accumulator by.
+__global__ void __launch_bounds__(256) policy_pack_kernel(const __grid_constant__ PackArgs a) {
+    __shared__ float s_max[8];
+    __shared__ int s_exp;
     const int li = blockIdx.y;
     if (li >= a.n_layers) return;
     const ULayer &L = a.L[li];
-    const int total = L.K * L.N;
+    const int total = L.K * L.N, real = a.k_real[li] * L.n_real;
+    int sexp = 0;
+    if (L.f16) {
+        float m = 0.0f;
+        for (int e = threadIdx.x; e < real; e += blockDim.x) m = fmaxf(m, fabsf(__ldg(a.w[li] + e)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) m = fmaxf(m, s_max[w]);
+            int e = 14;
+            if (m > 0.0f && m < 3.0e38f) frexpf(m, &e);      // m = f 2^e, f in [0.5, 1)
+            int sx = 14 - e;
+            s_exp = sx > 100 ? 100 : (sx < -100 ? -100 : sx);
+        }
+        __syncthreads();
+        sexp = s_exp;
+    }
+    const float scale = ldexpf(1.0f, sexp);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int k = e / L.N, nn = e - k * L.N;
         const float w = (nn < L.n_real && k < a.k_real[li]) ? __ldg(a.w[li] + (int64_t)nn * a.k_real[li] + k) : 0.0f;
-        const uint32_t hi = tf32_hi(w);
-        const float lo = w - __uint_as_float(hi);
-        unsigned char *ks = a.image + L.w_off + (uint32_t)(k / 8) * (uint32_t)L.N * 64;
-        const uint32_t in_plane = (uint32_t)((k & 7) >> 2) * (uint32_t)L.N * 16 + (uint32_t)nn * 16 + (uint32_t)(k & 3) * 4;
-        *reinterpret_cast<uint32_t *>(ks + in_plane) = hi;
-        *reinterpret_cast<float *>(ks + (uint32_t)L.N * 32 + in_plane) = lo;
+        if (L.f16) {
+            const float ws = w * scale;
+            const __half hi = __float2half_rn(ws);
+            const __half lo = __float2half_rn(ws - __half2float(hi));
+            unsigned char *ks = a.image + L.w_off + (uint32_t)(k / 16) * (uint32_t)L.N * 64;
+            const uint32_t in_plane = (uint32_t)((k & 15) >> 3) * (uint32_t)L.N * 16 + (uint32_t)nn * 16 + (uint32_t)(k & 7) * 2;
+            *reinterpret_cast<__half *>(ks + in_plane) = hi;
+            *reinterpret_cast<__half *>(ks + (uint32_t)L.N * 32 + in_plane) = lo;
+        } else {
+            const uint32_t hi = tf32_hi(w);
+            const float lo = w - __uint_as_float(hi);
+            unsigned char *ks = a.image + L.w_off + (uint32_t)(k / 8) * (uint32_t)L.N * 64;
+            const uint32_t in_plane = (uint32_t)((k & 7) >> 2) * (uint32_t)L.N * 16 + (uint32_t)nn * 16 + (uint32_t)(k & 3) * 4;
+            *reinterpret_cast<uint32_t *>(ks + in_plane) = hi;
+            *reinterpret_cast<float *>(ks + (uint32_t)L.N * 32 + in_plane) = lo;
+        }
     }
-    if (blockIdx.x == 0)
+    if (blockIdx.x == 0) {
         for (int j = threadIdx.x; j < L.N; j += blockDim.x) {
             const float b = j < L.n_real ? __ldg(a.b[li] + j) : 0.0f;
             a.bias[L.b_off + j] = L.role == 0 ? b * TWO_LOG2E : b;
         }
+        if (threadIdx.x == 0) a.bias[a.zs_off + li] = (L.role == 0 ? TWO_LOG2E : 1.0f) * ldexpf(1.0f, -sexp);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -571,6 +641,16 @@ int add_net(const b200_mlp *m, bool is_actor, UPlan *P, int *k_real, const float
     return B200ENV_OK;
 }
 
+// B200_POLICY_F16_WIDE=0 in the environment keeps the streamed mode on 3xTF32 (A/B runs)
+bool use_f16_streamed() {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char *e = getenv("B200_POLICY_F16_WIDE");
+        enabled = !(e && e[0] == '0');
+    }
+    return enabled != 0;
+}
+
 int build_plan(const b200_mlp *actor, const b200_mlp *critic, UPlan *P, int *k_real, const float **w, const float **b) {
     *P = UPlan{};
     int rc;
@@ -578,6 +658,8 @@ int build_plan(const b200_mlp *actor, const b200_mlp *critic, UPlan *P, int *k_r
     if (critic && (rc = add_net(critic, false, P, k_real, w, b))) return rc;
     P->S = actor ? actor->dims[0] : critic->dims[0];
     P->A = actor ? actor->dims[actor->n_layers] : 0;
+    P->zs_off = P->bias_floats;
+    P->bias_floats += UM_MAX_LAYERS;
     int nmax = 16, kmax = 8;
     for (int l = 0; l < P->n_layers; ++l) {
         nmax = P->L[l].N > nmax ? P->L[l].N : nmax;
@@ -600,6 +682,18 @@ int build_plan(const b200_mlp *actor, const b200_mlp *critic, UPlan *P, int *k_r
         int cols = slots * slot_cols, pow2 = 32;
         while (pow2 < cols) pow2 *= 2;
         if (total > SMEM_LIMIT || pow2 > 512) continue;
+        if (streamed && use_f16_streamed()) {
+            // streamed mode: every layer after a net's first multiplies fp16 pairs -- half the image bytes pulled through the
+            // ring per tile and half the MMAs (kind::f16 covers K = 16); the image offsets are laid out again
+            uint32_t off = 0;
+            for (int l = 0; l < P->n_layers; ++l) {
+                ULayer &L = P->L[l];
+                L.f16 = !L.first;
+                L.w_off = off;
+                off += (uint32_t)L.K * (uint32_t)L.N * (L.f16 ? 4u : 8u);
+            }
+            P->img_bytes = off;
+        }
         P->slots = slots; P->streamed = streamed; P->nbuf_log2 = nbuf_log2; P->a_tmem = a_tmem;
         P->slot_cols = slot_cols; P->pong_off = nmax; P->a_col = 2 * nmax; P->tmem_cols = pow2;
         P->stage_bytes = stage;
@@ -641,6 +735,7 @@ int policy_umma_pack(const b200_mlp *actor, const b200_mlp *critic, void *worksp
     if (!workspace) return B200ENV_ENULL;
     if (bytes < img + (size_t)P.bias_floats * 4 || ((uintptr_t)workspace & 127)) return B200ENV_EPARAMS;
     pa.n_layers = P.n_layers;
+    pa.zs_off = P.zs_off;
     for (int l = 0; l < P.n_layers; ++l) pa.L[l] = P.L[l];
     pa.image = static_cast<unsigned char *>(workspace);
     pa.bias = reinterpret_cast<float *>(pa.image + img);

@@ -188,6 +188,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// SS form, kind::f16 (fp16 operands in shared memory, K = 16 per instruction): same calling convention as umma_tf32_lohi
+__device__ __forceinline__ void umma_f16_lohi(uint32_t leader, uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32,
+                                              uint32_t desc_hi32, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "setp.ne.b32 q, %6, 0;\n\t"
+                 "mov.b64 da, {%1, %3};\n\t"
+                 "mov.b64 db, {%2, %3};\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
 // TS form, kind::f16: A = 16-bit elements packed two per 32-bit TMEM column (lane = row), B from shared memory; K = 16
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo32, uint32_t desc_hi32,
                                             uint32_t idesc, uint32_t accumulate) {
