@@ -23,6 +23,14 @@
 #endif
 #include "uav_common.cuh"
 
+// -DUAV_RESET_NOINLINE: the auto-reset body (Philox draws, trajectory parameters) as an out-of-line call -- A/B switch for
+// the instruction-cache footprint of the step kernels' hot path
+#ifdef UAV_RESET_NOINLINE
+#define UAV_RESET_INLINE __noinline__
+#else
+#define UAV_RESET_INLINE __forceinline__
+#endif
+
 namespace {
 using namespace uavk;
 
@@ -46,7 +54,7 @@ __device__ __forceinline__ int terminal_flag(const P &p, const T *x, double time
 enum { A_S1 = 6, A_K1 = 9, A_K2 = 12, A_GAM = 15, A_LMD = 18, A_AMP = 21, A_PER = 24, A_PHS = 27, A_REF = 30, A_DREF = 33 };
 
 template <typename T, typename I>
-__device__ __forceinline__ void att_reset_state(const P &p, const b200env_io &io, I n, I i, uint64_t seed,
+__device__ UAV_RESET_INLINE void att_reset_state(const P &p, const b200env_io &io, I n, I i, uint64_t seed,
                                                 int64_t off, T *x /* out: 12 states */) {
     const uint32_t ep = io.episode[i];
 #pragma unroll
@@ -239,7 +247,7 @@ enum { P_SIG = 12, P_S1 = 15, P_AREF = 18, P_K1 = 21, P_K2 = 24, P_GAM = 27, P_L
        P_PHS = 41, P_PREF = 45, P_DPREF = 48, P_NEXT_PQR0 = 51 /* layout variant 1 only */ };
 
 template <typename T, typename I>
-__device__ __forceinline__ void pos_reset_state(const P &p, const b200env_io &io, I n, I i, uint64_t seed,
+__device__ UAV_RESET_INLINE void pos_reset_state(const P &p, const b200env_io &io, I n, I i, uint64_t seed,
                                                 int64_t off, T *x) {
     const uint32_t ep = io.episode[i];
 #pragma unroll
