@@ -123,14 +123,21 @@ __device__ __forceinline__ void fwd_layer(const float *__restrict__ H, int ph, c
     for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0f;
-    const float *hp = H + sg * ph, *wp = W + ng * pw;
+    // one base pointer per operand row, hoisted: inside the (unrolled) k loop every load is base + immediate -- the
+    // address arithmetic was 9 % of the kernel's instructions (LEA per LDS, profiles/r2/learn.md)
+    const float *ha[MI], *wa[NJ];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) ha[i] = H + (sg + 32 * i) * ph;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) wa[j] = W + (ng + 8 * j) * pw;
+#pragma unroll 4
     for (int k0 = 0; k0 < K; k0 += 4) {
         float4 a[MI];
 #pragma unroll
-        for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const float4 *>(hp + 32 * i * ph + k0);
+        for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const float4 *>(ha[i] + k0);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            const float4 w = *reinterpret_cast<const float4 *>(wp + 8 * j * pw + k0);
+            const float4 w = *reinterpret_cast<const float4 *>(wa[j] + k0);
 #pragma unroll
             for (int i = 0; i < MI; ++i) {
                 acc[i][j] = fmaf(a[i].x, w.x, acc[i][j]);
@@ -161,12 +168,16 @@ __device__ __forceinline__ void bwd_layer(const float *__restrict__ G, int pg, c
     for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int jv = 0; jv < NV; ++jv) acc[i][jv] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float *gp = G + sg * pg, *wp = W + 4 * ng;
+    const float *wp = W + 4 * ng;
+    const float *ga[MI];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) ga[i] = G + (sg + 32 * i) * pg;
+#pragma unroll 2
     for (int n0 = 0; n0 < N; n0 += 4) {
         float g[MI][4];
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
-            const float4 t = *reinterpret_cast<const float4 *>(gp + 32 * i * pg + n0);
+            const float4 t = *reinterpret_cast<const float4 *>(ga[i] + n0);
             g[i][0] = t.x; g[i][1] = t.y; g[i][2] = t.z; g[i][3] = t.w;
         }
 #pragma unroll
