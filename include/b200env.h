@@ -91,10 +91,11 @@ typedef struct b200env_io {
     int32_t       *flag;       /* [n]                i32     `terminal_flag`                            */
     void          *reset_obs;  /* [obs_dim][n]       dtype   obs the policy sees next: s' or, where an
                                                              auto-reset happened, the reset obs; may be NULL */
-    int32_t       *work;       /* [1 + n]            i32     optional scratch (may be NULL): work[0] counts, work[1..]
-                                                             lists the instances that terminated in this step, so that
-                                                             kernels with an expensive auto-reset (the obstacle-map
-                                                             rejection sampling of B200ENV_UGVO) balance it over the grid */
+    int32_t       *work;       /* [1 + n]            i32     optional scratch (may be NULL; contents undefined after
+                                                             the call): work[0] counts, work[1..] lists the instances
+                                                             that terminated in this step, so that kernels with an
+                                                             expensive auto-reset (the obstacle-map rejection sampling
+                                                             of B200ENV_UGVO) balance it over the grid */
     int32_t        io_dtype;   /* element type of the RL-facing buffers action, dis, obs, next_obs, reward and
                                   reset_obs: B200ENV_F64 (0) = same as `dtype` (default), B200ENV_F32 = float32 even
                                   when dtype is F64.  The RL side of the reference is float32 (actor output

@@ -162,6 +162,15 @@ static void draw2(uint64_t seed, uint64_t gid, uint32_t ep, uint32_t block, doub
     *u0 = ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) * (1.0 / 9007199254740992.0);
     *u1 = ((double)(o[2] >> 5) * 67108864.0 + (double)(o[3] >> 6)) * (1.0 / 9007199254740992.0);
 }
+/* obstacle candidates: one block, the radius from the 22 low bits draw2 discards (csrc/ugvo.cu draw3) */
+static void draw3(uint64_t seed, uint64_t gid, uint32_t ep, uint32_t block, double *u0, double *u1, double *u2) {
+    uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), ep, block}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+    orc_philox_block(ctr, key, o);
+    *u0 = ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) * (1.0 / 9007199254740992.0);
+    *u1 = ((double)(o[2] >> 5) * 67108864.0 + (double)(o[3] >> 6)) * (1.0 / 9007199254740992.0);
+    const uint32_t low = ((o[0] & 31u) << 17) | ((o[1] & 63u) << 11) | ((o[2] & 31u) << 6) | (o[3] & 63u);
+    *u2 = (double)low * (1.0 / 4194304.0);
+}
 static double lerp_u(double lo, double hi, double u) { return fma(hi - lo, u, lo); }
 
 /* reset(random=True) :527-557 + Map.generate_circle_obs_training map.py:152-174 */
@@ -179,10 +188,9 @@ static void reset_env(const P *p, ugvo_t *e, uint64_t seed, uint64_t gid, uint32
     for (int k = 0; k < p->obs_num && k < MAXO; ++k) {
         int placed = 0;
         for (uint32_t c = 0; c < 2048 && !placed; ++c) {
-            const uint32_t blk = 1000u + 2u * (2048u * (uint32_t)k + c);
-            double ur, dummy;
-            draw2(seed, gid, ep, blk, &u0, &u1);
-            draw2(seed, gid, ep, blk + 1, &ur, &dummy);
+            const uint32_t blk = 1000u + 2048u * (uint32_t)k + c;
+            double ur;
+            draw3(seed, gid, ep, blk, &u0, &u1, &ur);
             const double cx = lerp_u(0., p->map_x, u0), cy = lerp_u(0., p->map_y, u1), r = lerp_u(p->r_min, p->r_max, ur);
             int legal = 1; /* map.py:129-139 */
             if (norm2(sx - cx, sy - cy) <= r + p->safety_dis_st) legal = 0;

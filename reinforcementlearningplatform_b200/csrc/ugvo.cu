@@ -140,8 +140,9 @@ __device__ __forceinline__ T cast_ray(const P &p, const Pose<T> &q, int ray, con
         if (Mth<T>::abs(num - rhs) <= (T)(sizeof(T) == 8 ? 1e-15 : 1e-6) * rhs) miss = num / sq > r0;
         // cal_vector_rad(ray, centre - start) > pi / 2  <=>  both vectors non-degenerate and their dot product < 0
         // (dividing by the positive norms and taking acos cannot change the sign; see vector_rad_obtuse)
+        if (miss) continue; // most in-range circles are missed: the obtuse-angle test is only made for the others
         const bool behind = ray_ok && !(dj < (T)1e-4) && (rdx * (x0 - x) + rdy * (y0 - y) < (T)0);
-        if (!miss && !behind) {
+        if (!behind) {
             const T fx = dm2.div(x0 + m * y0 - m * b);
             const T fy = dm2.div(m * x0 + m * m * y0 + b);
             const T rd = norm2(fx - x0, fy - y0);
@@ -194,6 +195,21 @@ __device__ __forceinline__ Draw2 draw2(uint64_t seed, uint64_t gid, uint32_t ep,
     d.u1 = ((double)(g.r[2] >> 5) * 67108864.0 + (double)(g.r[3] >> 6)) * (1.0 / 9007199254740992.0);
     return d;
 }
+// One block per obstacle candidate: the centre takes the 2 x 53 high bits like draw2, the radius the 22 bits draw2 throws
+// away (5 + 6 + 5 + 6 low bits of the four words) -- a U[0, 1) with 2^-22 resolution for a radius drawn from
+// [r_min, r_max].  A candidate used to cost two Philox blocks (220 of its ~330 instructions); the oracle draws the same.
+struct Draw3 { double u0, u1, u2; };
+__device__ __forceinline__ Draw3 draw3(uint64_t seed, uint64_t gid, uint32_t ep, uint32_t block) {
+    Philox g(seed, gid, ep);
+    g.c3 = block;
+    g.block();
+    Draw3 d;
+    d.u0 = ((double)(g.r[0] >> 5) * 67108864.0 + (double)(g.r[1] >> 6)) * (1.0 / 9007199254740992.0);
+    d.u1 = ((double)(g.r[2] >> 5) * 67108864.0 + (double)(g.r[3] >> 6)) * (1.0 / 9007199254740992.0);
+    const uint32_t low = ((g.r[0] & 31u) << 17) | ((g.r[1] & 63u) << 11) | ((g.r[2] & 31u) << 6) | (g.r[3] & 63u);
+    d.u2 = (double)low * (1.0 / 4194304.0);
+    return d;
+}
 __device__ __forceinline__ double lerp_u(double lo, double hi, double u) { return ::fma(hi - lo, u, lo); }
 // dis_two_points(a, b) <= R, i.e. sqrt(dx^2 + dy^2) <= R (map.py:122,131-133), decided on the squares; the square root is
 // only taken when the two sides agree to ~14 digits, so the decision is the reference's in every case
@@ -233,29 +249,50 @@ __device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gi
     ocx = 0.0; ocy = 0.0; orr = 0.0;
     nobs = 0;
     const int want = p.obs_num < MAXO ? p.obs_num : MAXO;
+    // Rounds of 32 * NC candidates, NC per lane (indices 32 NC r + 32 j + lane): the NC Philox blocks and legality chains
+    // of a lane are independent, which shortens the dependent-instruction path of a placement (the reset launch is
+    // latency-bound: ~8 warps per SM alive on average; NC = 2: 0.874 -> 0.819 ms per step at the steady-state reset rate).
+    // The winner is still the lowest legal candidate index, so the map does not depend on NC.
+#ifndef UGVO_CAND_PER_LANE
+#define UGVO_CAND_PER_LANE 2
+#endif
+    constexpr int NC = UGVO_CAND_PER_LANE;
     for (int k = 0; k < want; ++k) {
         bool placed = false;
-        for (int round = 0; round < 64 && !placed; ++round) {
-            const uint32_t c = (uint32_t)(round * 32 + lane);
-            const uint32_t blk = 1000u + 2u * (2048u * (uint32_t)k + c);
-            d = draw2(seed, gid, ep, blk);
-            const Draw2 dr = draw2(seed, gid, ep, blk + 1u);
-            const double cx = lerp_u(0., p.map_x, d.u0), cy = lerp_u(0., p.map_y, d.u1), r = lerp_u(p.r_min, p.r_max, dr.u0);
-            bool legal = true; // map.py:129-139
-            if (within(sx - cx, sy - cy, r + p.safety_dis_st)) legal = false;
-            if (within(tx - cx, ty - cy, r + p.safety_dis_st)) legal = false;
-            for (int q = 0; q < nobs; ++q) { // placed obstacles: broadcast from lane q
-                if (!__any_sync(FULL, legal)) break; // all 32 candidates of this round are already rejected
-                const double qx = __shfl_sync(FULL, ocx, q), qy = __shfl_sync(FULL, ocy, q), qr = __shfl_sync(FULL, orr, q);
-                if (within(qx - cx, qy - cy, qr + r + p.safety_dis_obs)) legal = false;
+        for (int round = 0; round < 64 / NC && !placed; ++round) {
+            const uint32_t blk = 1000u + 2048u * (uint32_t)k + (uint32_t)(round * 32 * NC + lane);
+            double cx[NC], cy[NC], r[NC];
+            bool legal[NC]; // map.py:129-139
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const Draw3 dc = draw3(seed, gid, ep, blk + 32u * (uint32_t)j);
+                cx[j] = lerp_u(0., p.map_x, dc.u0); cy[j] = lerp_u(0., p.map_y, dc.u1); r[j] = lerp_u(p.r_min, p.r_max, dc.u2);
             }
-            const unsigned m = __ballot_sync(FULL, legal);
-            if (m) {
-                const int src = __ffs(m) - 1;
-                const double wx = __shfl_sync(FULL, cx, src), wy = __shfl_sync(FULL, cy, src), wr = __shfl_sync(FULL, r, src);
-                if (lane == nobs) { ocx = wx; ocy = wy; orr = wr; }
-                ++nobs;
-                placed = true;
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+                legal[j] = !within(sx - cx[j], sy - cy[j], r[j] + p.safety_dis_st) &&
+                           !within(tx - cx[j], ty - cy[j], r[j] + p.safety_dis_st);
+            for (int q = 0; q < nobs; ++q) { // placed obstacles: broadcast from lane q
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < NC; ++j) any = any || legal[j];
+                if (!__any_sync(FULL, any)) break; // all candidates of this round are already rejected
+                const double qx = __shfl_sync(FULL, ocx, q), qy = __shfl_sync(FULL, ocy, q), qr = __shfl_sync(FULL, orr, q);
+#pragma unroll
+                for (int j = 0; j < NC; ++j)
+                    if (within(qx - cx[j], qy - cy[j], qr + r[j] + p.safety_dis_obs)) legal[j] = false;
+            }
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const unsigned m = __ballot_sync(FULL, legal[j]);
+                if (m && !placed) {
+                    const int src = __ffs(m) - 1;
+                    const double wx = __shfl_sync(FULL, cx[j], src), wy = __shfl_sync(FULL, cy[j], src);
+                    const double wr = __shfl_sync(FULL, r[j], src);
+                    if (lane == nobs) { ocx = wx; ocy = wy; orr = wr; }
+                    ++nobs;
+                    placed = true;
+                }
             }
         }
         if (!placed) break;
@@ -377,11 +414,24 @@ ugvo_aux_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io 
 //            instances, so the obstacle lists are shared-memory broadcasts) -- every lane casts a ray;
 //   (phase 3, auto-reset of the terminated instances, is a second launch: ugvo_autoreset_kernel)
 // With io.obs == NULL (observation reuse, vec_env.py) only the post-update scan is cast (one scan per step).
-constexpr int G = 64;
-constexpr int TPB = 128;
+#ifndef UGVO_G
+#define UGVO_G 64
+#endif
+#ifndef UGVO_TPB
+#define UGVO_TPB 128
+#endif
+// six resident blocks per SM (80 registers, the 36.7 KB of shared memory per block allow no more): the ray loop is a
+// chain of dependent fp64 operations, and 24 warps hide it better than the 16 of the uncapped 120-register build
+// (0.942 -> 0.863 ms per step of 262,144 instances at the steady-state reset rate, A/B on one box)
+#ifndef UGVO_MINB
+#define UGVO_MINB 6
+#endif
+constexpr int G = UGVO_G;
+constexpr int TPB = UGVO_TPB;
+static_assert(TPB >= G, "phase 1 runs one thread per instance");
 
 template <typename T, bool IO32>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, UGVO_MINB)
 ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags,
                  uint64_t seed, int64_t off) {
     __shared__ T s_o[4][MAXO][G];                 // x0, y0, r0, d of the in-range obstacles, [slot][instance]
@@ -557,18 +607,34 @@ ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io
 // io.work the step kernel appends the terminated instances and the warps of this grid share them evenly; without it
 // every warp scans the `done` flags of its 32-instance groups.
 constexpr int RESET_WARPS = 8;
+#ifndef UGVO_RESET_MINB
+#define UGVO_RESET_MINB 3 // 80 registers, no spills; 3 / 4 / 5 / 6 blocks per SM measured within 1 % of each other
+#endif
 template <typename T, bool IO32>
-__global__ void __launch_bounds__(RESET_WARPS * 32, 4)
+__global__ void __launch_bounds__(RESET_WARPS * 32, UGVO_RESET_MINB)
 ugvo_autoreset_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint64_t seed,
                       int64_t off) {
     __shared__ T s_o[RESET_WARPS][4][MAXO];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t gw = (int64_t)blockIdx.x * RESET_WARPS + w, nw = (int64_t)gridDim.x * RESET_WARPS;
     if (io.work) {
-        // the step kernel appended the terminated instances to io.work[1..]: deal them evenly to all warps of the grid
+        // the step kernel appended the terminated instances to io.work[1..count].  A reset takes between ~15 and ~250
+        // sampling rounds (crowded maps: half of them give up on one obstacle after 64 rounds), so dealing the list out in
+        // equal shares left most warps idle behind the unlucky ones (warps active 12 % of peak under ncu); every warp now
+        // takes the next entry when it is free -- work[0] is the ticket counter, counted down (it ends below zero; the
+        // launcher clears it before every step kernel).
+#ifdef UGVO_STATIC_DEAL
         const int count = io.work[0];
         for (int64_t k = gw; k < count; k += nw) {
             const int64_t ir = io.work[1 + k];
+#else
+        for (;;) {
+            int tk = 0;
+            if (lane == 0) tk = atomicSub(io.work, 1);
+            tk = __shfl_sync(FULL, tk, 0);
+            if (tk <= 0) break;
+            const int64_t ir = io.work[tk];
+#endif
             WarpInst<T> e;
             warp_reset<T>(p, io, n, ir, seed, off, lane, e);
             if (io.reset_obs) warp_observe<T, IO32>(p, n, ir, lane, e, io.reset_obs, s_o[w][0], s_o[w][1], s_o[w][2], s_o[w][3]);
@@ -604,7 +670,7 @@ int launch(int dtype, int64_t n, const void *params, const b200env_io *io, uint3
         if (ar) {
             // enough warps to hold every SM at 4 blocks; with the list they stride over it, without it over the batch
             int64_t rgrid = (n + RESET_WARPS * 32 - 1) / (RESET_WARPS * 32);
-            if (rgrid > 148 * 4) rgrid = 148 * 4;
+            if (rgrid > 148 * UGVO_RESET_MINB) rgrid = 148 * UGVO_RESET_MINB;
             B200_LAUNCH_TIO(ugvo_autoreset_kernel, (unsigned)rgrid, RESET_WARPS * 32, s, p, *io, n, seed, off);
         }
     } else {
