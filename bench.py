@@ -219,7 +219,14 @@ def timed_steps(env, pool, steps, warmup, dist_on, sampler=None, dis_pool=None):
     return ms
 
 
-def timed_e2e(workload, n, steps, warmup, dist_on, seed, device, offset, dtype, chunks=4, io_dtype=None):
+# Shards of the host-buffer path (timed_e2e): shard c's copies overlap shard c+1's kernel.  Measured on one B200 at 1 M
+# instances (tools/e2e_sweep.py): 1 shard 0.76e9, 2 shards 1.30e9, 3 shards 1.29e9, 4 shards 1.21e9, 8 shards 1.07e9
+# env-steps/s against 1.46e9 for the bare copies -- two shards already keep both directions of the link busy, more only add
+# host <-> device hand-overs; CUDA graphs around a shard's step change nothing (the host is not the limit).
+E2E_SHARDS = 2
+
+
+def timed_e2e(workload, n, steps, warmup, dist_on, seed, device, offset, dtype, chunks=E2E_SHARDS, io_dtype=None):
     """Same metric through the public API with HOST buffers.  Every step, for every instance: the actions are copied
     from pinned host memory, the step kernel runs, and policy_state / reward / is_terminal are read back to pinned host
     memory, where the host waits for them before it issues that instance's next action.  The batch is split into
@@ -372,7 +379,7 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def copy_probe(n, A, S, steps, dev, dist_on, chunks=4):
+def copy_probe(n, A, S, steps, dev, dist_on, chunks=E2E_SHARDS):
     """The bytes of one e2e step moved by plain cudaMemcpyAsync (torch copy_ of pinned float32 buffers, one call per
     buffer), no kernel in between, same shard / stream structure: what the host link alone allows at this GPU count."""
     import torch.distributed as dist
@@ -820,9 +827,9 @@ def main():
                                       "h2d_gbs": world * h2d * e_steps / (p_ms * 1e-3) / 1e9,
                                       "d2h_gbs": world * d2h * e_steps / (p_ms * 1e-3) / 1e9,
                                       "what": "the same pinned buffers moved by one cudaMemcpyAsync each (torch copy_), no "
-                                              "kernel in between, same 4 shards / streams"},
+                                              f"kernel in between, same {E2E_SHARDS} shards / streams"},
                        "frac_of_copy_probe": p_ms / e_ms,
-                       "api": "VecEnv.step_soa on 4 shards / 4 streams: pinned host float32 actions in (the reference's "
+                       "api": f"VecEnv.step_soa on {E2E_SHARDS} shards / {E2E_SHARDS} streams: pinned host float32 actions in (the reference's "
                               "actor emits float32), float32 policy_state + reward and u8 is_terminal out every step; "
                               "state and arithmetic stay in the env dtype; the host waits for a shard's result before "
                               "its next action"}
