@@ -100,7 +100,7 @@ WORKLOADS = {
     "uav_pos": dict(n=1 << 20, desc="UavFntsmcParam position tracking, dt=0.02, time_max=10, 8 gains~U(0,5)/step"),
     "uav_att": dict(n=1 << 20, desc="UavFntsmcParam attitude tracking, dt=0.02, time_max=10, 8 gains~U(0,3)/step"),
     "cartpole": dict(n=65536, desc="CartPole (angle+position) RK4 time-loop step, force~U(-8,8)"),
-    "ugvo": dict(n=262144, desc="UGVForwardObstacleAvoidance DPPO2 variant, dt=0.05, 15 circles, 37-ray laser x2 scans/step"),
+    "ugvo": dict(n=262144, desc="UGVForwardObstacleAvoidance DPPO2 variant, dt=0.05, 15 circles, one 37-ray scan per step (the pre-step scan is the previous step's post-step scan)"),
     "soi": dict(n=1 << 20, desc="SecondOrderIntegration (ENV), RK4 step"),
     "fas": dict(n=1 << 20, desc="Flight_Attitude_Simulator (PPO2 variant), RK4 time-loop step"),
     "fas_discrete": dict(n=1 << 20, desc="FlightAttitudeSimulatorDiscrete, 2 RK4 steps/period, force from the discrete action set"),
