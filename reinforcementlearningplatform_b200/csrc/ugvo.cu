@@ -221,7 +221,10 @@ __device__ __forceinline__ bool within(double dx, double dy, double R) {
 
 // reset(random=True) :527-557 + Map.generate_circle_obs_training (map.py:152-174), cooperative over the warp.
 // Outputs (uniform over the warp): start/target/phi0; per-lane obstacle k = lane (cx, cy, r), nobs.
-__device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gid, uint32_t ep, int lane, double &sx,
+// `pl`: 3 * MAXO doubles of shared memory owned by this warp (x, y, r of the obstacles placed so far): the legality loop
+// reads them as broadcasts, UGVO_PLACED_GROUP obstacles per vote (measured: a wash against one shuffle-broadcast and one
+// vote per obstacle -- larger groups lose more to the delayed early exit than they win in latency).
+__device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gid, uint32_t ep, int lane, double *pl, double &sx,
                                           double &sy, double &tx, double &ty, double &phi0, double &ocx, double &ocy,
                                           double &orr, int &nobs) {
     const double lo = p.st_margin, hx = p.map_x - p.st_margin, hy = p.map_y - p.st_margin;
@@ -256,6 +259,9 @@ __device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gi
 #ifndef UGVO_CAND_PER_LANE
 #define UGVO_CAND_PER_LANE 2
 #endif
+#ifndef UGVO_PLACED_GROUP
+#define UGVO_PLACED_GROUP 2 // 1-vote-per-obstacle shuffles 0.766, groups of 2 / 4 / 8 / 15 from shared memory 0.758 / 0.775 / 0.792 / 0.804 ms per step
+#endif
     constexpr int NC = UGVO_CAND_PER_LANE;
     for (int k = 0; k < want; ++k) {
         bool placed = false;
@@ -272,6 +278,7 @@ __device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gi
             for (int j = 0; j < NC; ++j)
                 legal[j] = !within(sx - cx[j], sy - cy[j], r[j] + p.safety_dis_st) &&
                            !within(tx - cx[j], ty - cy[j], r[j] + p.safety_dis_st);
+#ifdef UGVO_SHFL_PLACED
             for (int q = 0; q < nobs; ++q) { // placed obstacles: broadcast from lane q
                 bool any = false;
 #pragma unroll
@@ -282,6 +289,24 @@ __device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gi
                 for (int j = 0; j < NC; ++j)
                     if (within(qx - cx[j], qy - cy[j], qr + r[j] + p.safety_dis_obs)) legal[j] = false;
             }
+#else
+            for (int q0 = 0; q0 < nobs; q0 += UGVO_PLACED_GROUP) { // placed obstacles, a group per vote
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < NC; ++j) any = any || legal[j];
+                if (!__any_sync(FULL, any)) break; // all candidates of this round are already rejected
+#pragma unroll
+                for (int g = 0; g < UGVO_PLACED_GROUP; ++g) {
+                    const int q = q0 + g;
+                    if (q < nobs) {
+                        const double qx = pl[q], qy = pl[MAXO + q], qr = pl[2 * MAXO + q];
+#pragma unroll
+                        for (int j = 0; j < NC; ++j)
+                            if (within(qx - cx[j], qy - cy[j], qr + r[j] + p.safety_dis_obs)) legal[j] = false;
+                    }
+                }
+            }
+#endif
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
                 const unsigned m = __ballot_sync(FULL, legal[j]);
@@ -289,9 +314,10 @@ __device__ __forceinline__ void reset_map(const P &p, uint64_t seed, uint64_t gi
                     const int src = __ffs(m) - 1;
                     const double wx = __shfl_sync(FULL, cx[j], src), wy = __shfl_sync(FULL, cy[j], src);
                     const double wr = __shfl_sync(FULL, r[j], src);
-                    if (lane == nobs) { ocx = wx; ocy = wy; orr = wr; }
+                    if (lane == nobs) { ocx = wx; ocy = wy; orr = wr; pl[nobs] = wx; pl[MAXO + nobs] = wy; pl[2 * MAXO + nobs] = wr; }
                     ++nobs;
                     placed = true;
+                    __syncwarp();
                 }
             }
         }
@@ -346,11 +372,11 @@ __device__ __forceinline__ void warp_load(const b200env_io &io, int64_t n, int64
 // reset(random=True) :527-557 of instance i by one warp; writes the whole persistent state
 template <typename T>
 __device__ __forceinline__ void warp_reset(const P &p, const b200env_io &io, int64_t n, int64_t i, uint64_t seed,
-                                           int64_t off, int lane, WarpInst<T> &e) {
+                                           int64_t off, int lane, double *pl, WarpInst<T> &e) {
     const uint32_t ep = io.episode[i];
     double sx, sy, ttx, tty, phi0, cx, cy, rr;
     int no;
-    reset_map(p, seed, (uint64_t)(off + i), ep, lane, sx, sy, ttx, tty, phi0, cx, cy, rr, no);
+    reset_map(p, seed, (uint64_t)(off + i), ep, lane, pl, sx, sy, ttx, tty, phi0, cx, cy, rr, no);
     e.x = (T)sx; e.y = (T)sy; e.tgx = (T)ttx; e.tgy = (T)tty; e.phi = (T)phi0; e.vel = (T)0; e.omega = (T)0;
     e.ocx = (T)cx; e.ocy = (T)cy; e.orr = (T)rr; e.nobs = no;
     e.time = 0.0;
@@ -395,13 +421,14 @@ __global__ void __launch_bounds__(WARPS * 32)
 ugvo_aux_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint64_t seed,
                 int64_t off, const uint8_t *mask, int mode) {
     __shared__ T s_o[WARPS][4][MAXO];
+    __shared__ double s_pl[WARPS][3 * MAXO];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * WARPS + w;
     if (i >= n) return; // whole warp exits together
     if (mode == 1 && mask && !mask[i]) return;
     WarpInst<T> e;
     warp_load<T>(io, n, i, lane, e);
-    if (mode == 1) warp_reset<T>(p, io, n, i, seed, off, lane, e);
+    if (mode == 1) warp_reset<T>(p, io, n, i, seed, off, lane, s_pl[w], e);
     if (io.next_obs) warp_observe<T, IO32>(p, n, i, lane, e, io.next_obs, s_o[w][0], s_o[w][1], s_o[w][2], s_o[w][3]);
 }
 
@@ -615,6 +642,7 @@ __global__ void __launch_bounds__(RESET_WARPS * 32, UGVO_RESET_MINB)
 ugvo_autoreset_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io io, int64_t n, uint64_t seed,
                       int64_t off) {
     __shared__ T s_o[RESET_WARPS][4][MAXO];
+    __shared__ double s_pl[RESET_WARPS][3 * MAXO];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t gw = (int64_t)blockIdx.x * RESET_WARPS + w, nw = (int64_t)gridDim.x * RESET_WARPS;
     if (io.work) {
@@ -636,7 +664,7 @@ ugvo_autoreset_kernel(const __grid_constant__ P p, const __grid_constant__ b200e
             const int64_t ir = io.work[tk];
 #endif
             WarpInst<T> e;
-            warp_reset<T>(p, io, n, ir, seed, off, lane, e);
+            warp_reset<T>(p, io, n, ir, seed, off, lane, s_pl[w], e);
             if (io.reset_obs) warp_observe<T, IO32>(p, n, ir, lane, e, io.reset_obs, s_o[w][0], s_o[w][1], s_o[w][2], s_o[w][3]);
         }
         return;
@@ -649,7 +677,7 @@ ugvo_autoreset_kernel(const __grid_constant__ P p, const __grid_constant__ b200e
             const int64_t ir = first + (__ffs(todo) - 1);
             todo &= todo - 1;
             WarpInst<T> e;
-            warp_reset<T>(p, io, n, ir, seed, off, lane, e);
+            warp_reset<T>(p, io, n, ir, seed, off, lane, s_pl[w], e);
             if (io.reset_obs) warp_observe<T, IO32>(p, n, ir, lane, e, io.reset_obs, s_o[w][0], s_o[w][1], s_o[w][2], s_o[w][3]);
         }
     }
