@@ -147,10 +147,10 @@ uav_att_step_kernel(const __grid_constant__ P p, const __grid_constant__ UavDeri
         UAV_STS(io.state, n, A_LMD + k, i, lmd[k]);
     }
     // ref_inner(time, A, T, 0, phase), ref_cmd.py:4-22
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        T dd;
-        ref_channel<T>((T)time, rA[k], rT[k], (T)0, rP[k], ref[k], dref[k], dd);
+    {
+        const T zero3[3] = {(T)0, (T)0, (T)0};
+        T dd[3];
+        ref_channels<T, 3>((T)time, rA, rT, zero3, rP, ref, dref, dd);
     }
     Trig<T> t1;
     t1.eval(x[6], x[7], x[8], false);
@@ -342,9 +342,10 @@ __device__ __forceinline__ void uav_pos_step_one(const P &p, const Consts<T> &c,
     }
     // ---- ref_uav(time, A, T, bias, phase), ref_cmd.py:25-43
     T ref[4], dref[4], ddref[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        ref_channel<T>((T)time, rA[k], rT[k], (T)p.ref_bias_a[k], rP[k], ref[k], dref[k], ddref[k]);
+    {
+        const T bias4[4] = {(T)p.ref_bias_a[0], (T)p.ref_bias_a[1], (T)p.ref_bias_a[2], (T)p.ref_bias_a[3]};
+        ref_channels<T, 4>((T)time, rA, rT, bias4, rP, ref, dref, ddref);
+    }
     // ---- pos_control, uav_pos_ctrl.py:302-315 + FNTSMC.py:47-69 (obs = 0)
     T ctrl[3];
     const T kt_m = c.kt_m; // kt / m (uav_pos_ctrl.py:310), constant: the compiler folds it from the kernel arguments

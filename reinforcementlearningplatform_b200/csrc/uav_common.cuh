@@ -292,5 +292,32 @@ __device__ __forceinline__ void ref_channel(T time, T A, T period, T bias, T pha
     ddr = -A * (w * w) * s;
 }
 
+// NCH channels of ref_uav / ref_inner at once.  The training scripts draw ONE period for all channels of a trajectory and
+// use the phases (pi/2, 0, 0, 0) (uav_pos_ctrl.py:404-408, train.py:61-66), so channels 1..3 have the same angular frequency
+// and the same sincos argument as their predecessor: a channel whose (period, phase) equal the previous channel's reuses
+// its w, sin and cos -- the same inputs through the same code give the same bits, so this is not an approximation -- and
+// only distinct channels pay for the quotient and the sincos (two instead of four per step in the bench configuration).
+// The test is per thread; lanes with distinct channels simply take the full path.
+template <typename T, int NCH>
+__device__ __forceinline__ void ref_channels(T time, const T *A, const T *period, const T *bias, const T *phase, T *r,
+                                             T *dr, T *ddr) {
+#ifdef B200_UAV_REF_NO_SHARE
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) ref_channel<T>(time, A[k], period[k], bias[k], phase[k], r[k], dr[k], ddr[k]);
+#else
+    T w = (T)0, s = (T)0, co = (T)1;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        if (k == 0 || period[k] != period[k - 1] || phase[k] != phase[k - 1]) {
+            if (k == 0 || period[k] != period[k - 1]) w = Mth<T>::div((T)(2 * M_PI), period[k]);
+            Mth<T>::sincos(w * time + phase[k], &s, &co);
+        }
+        r[k] = A[k] * s + bias[k];
+        dr[k] = A[k] * w * co;
+        ddr[k] = -A[k] * (w * w) * s;
+    }
+#endif
+}
+
 
 } // namespace uavk
