@@ -12,8 +12,11 @@
 #include "common.cuh"
 #include <type_traits>
 
+#ifndef ENV_MINBLOCKS
+#define ENV_MINBLOCKS 1 // resident blocks per SM the step kernel is compiled for (register cap); set per family file
+#endif
 template <typename T, class E, bool IO32>
-__global__ void __launch_bounds__(B200_BLOCK)
+__global__ void __launch_bounds__(B200_BLOCK, ENV_MINBLOCKS)
 env_step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ b200env_io io, int64_t n,
                 uint32_t flags, uint64_t seed, int64_t off) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,8 +84,10 @@ env_reset_kernel(const __grid_constant__ typename E::P p, const __grid_constant_
 // step only the action row is read and the transition row (s, s', r, done, flag) is written -- no state round trip
 // through HBM and no per-step launch.  Row t of an array lives `stride` elements after row t-1 (time-major rollout
 // buffer, rollout.py).  Same arithmetic as env_step_kernel step by step, including the in-kernel auto-reset.
+// (compiled for the same register cap as env_step_kernel: ptxas' scheduling, and with it its choice of mul + add pairs to
+// contract, follows the cap, and tests/test_rollout_gpu.py demands the same bits from both kernels)
 template <typename T, class E, bool IO32>
-__global__ void __launch_bounds__(B200_BLOCK)
+__global__ void __launch_bounds__(B200_BLOCK, ENV_MINBLOCKS)
 env_rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ b200env_io io,
                    const __grid_constant__ b200env_rollout_spec rs, int64_t n, uint32_t flags, uint64_t seed, int64_t off) {
     typedef typename std::conditional<IO32, float, T>::type TIO;

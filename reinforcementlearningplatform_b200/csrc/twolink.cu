@@ -1,6 +1,9 @@
 // twolink.cu -- K-TLM: batched TwoLinkManipulator step.
 // Replaces environment/RobotManipulator/TwoLinkManipulator.py:186-312 for n instances.  The 2x2 np.linalg.solve of the
 // ODE (:237) is an in-register LU with partial pivoting (dgesv order).
+// (a 64-register cap = eight resident blocks per SM measured 0.0955 -> 0.0892 ms per 1 M instances, but the step kernel and
+// the fused rollout kernel then no longer produce the same low bits of the fp64 state -- ptxas contracts different mul + add
+// pairs under the cap -- and tests/test_rollout_gpu.py demands equal bits: not adopted)
 #include "env_kernel.cuh"
 
 namespace {

@@ -131,7 +131,10 @@ __device__ __forceinline__ void reset_state(const RP &r, const b200env_io &io, i
 }
 
 template <typename T, int V, bool IO32>
-__global__ void __launch_bounds__(B200_BLOCK, 4)
+#ifndef UAVR_MINBLOCKS
+#define UAVR_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(B200_BLOCK, UAVR_MINBLOCKS)
 uavrobust_step_kernel(const __grid_constant__ RP r, const __grid_constant__ UavDerived dv,
                       const __grid_constant__ RobDerived rd, const __grid_constant__ b200env_io io, int64_t n, uint32_t flags, uint64_t seed, int64_t off) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

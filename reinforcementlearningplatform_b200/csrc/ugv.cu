@@ -1,5 +1,9 @@
 // ugv.cu -- K-UGV: batched UGVForward / UGVBidirectional step (unicycle with drag).
 // Replaces environment/UGV/UGVForward.py:217-362 and UGVBidirectional.py:217-367 for n instances.
+// eight resident blocks per SM (64 registers): 0.0493 -> 0.0470 ms per 1 M instances, A/B on one box
+#ifndef ENV_MINBLOCKS
+#define ENV_MINBLOCKS 8
+#endif
 #include "env_kernel.cuh"
 
 namespace {
