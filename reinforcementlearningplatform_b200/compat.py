@@ -92,6 +92,9 @@ class SingleEnv:
     def visualization(self):  # OpenCV drawing is out of scope
         pass
 
+    def show_image(self, iswait: bool = False):  # called once by the UAV train scripts (Pos/train.py:214); no window here
+        pass
+
     # ------------------------------------------------------------------ parity / checkpoint helpers
     def set_state(self, state, time):
         self._env.set_state_buffers(np.asarray(state, dtype=np.float64).reshape(-1, 1), np.asarray([time]))

@@ -76,3 +76,26 @@ def test_single_uav_reset_with_new_controller_params():
     assert env.time == 0.0 and not env.is_terminal and env.next_state.shape == (6,)
     env.step_update(env.generate_action_4_uav())   # no get_param_from_actor: fixed gains (test_pos_tracking_ctrl.py loop)
     assert np.isfinite(env.reward) and env.time == pytest.approx(0.02)
+
+
+@pytest.mark.parametrize("kind", ["pos", "att"])
+def test_single_uav_view_has_every_attribute_the_train_scripts_touch(kind):
+    """`grep -o 'env\\.[A-Za-z_0-9]*'` over PPO2-4-UavFntsmcParamPos/train.py and PPO2-4-UavFntsmcParamAtt/train.py: every name the
+    scripts read or call on `env` / `env_test` resolves on the single-instance view (drawing calls are no-ops)."""
+    import reinforcementlearningplatform_b200 as rlp
+    common = ["action_dim", "action_range", "state_dim", "name", "dt", "time_max", "current_state", "next_state", "reward",
+              "is_terminal", "terminal_flag", "time", "get_param_from_actor", "step_update", "current_state_norm",
+              "next_state_norm", "save_state_norm", "visualization", "show_image"]
+    if kind == "pos":
+        env = rlp.single(rlp.UavPosCtrlRL(n_envs=1, random_trajectory=True))
+        names = common + ["generate_action_4_uav", "reset_uav_pos_ctrl_RL_tracking"]
+    else:
+        env = rlp.single(rlp.UavAttCtrlRL(n_envs=1, random_trajectory=True))
+        names = common + ["att_control", "reset_uav_att_ctrl_RL_tracking", "ref_att_amplitude", "ref_att_period",
+                          "ref_att_bias_phase", "ref_att_bias_a"]
+    for n in names:
+        assert hasattr(env, n), n
+    env.show_image(True)
+    env.visualization()
+    s = env.current_state_norm(np.zeros(env.state_dim), update=False)
+    assert isinstance(s, np.ndarray) and s.dtype == np.float64 and s.shape == (env.state_dim,)
