@@ -20,6 +20,23 @@ import numpy as np
 import torch
 
 
+class _HostNormalization:
+    """``env.current_state_norm`` / ``env.next_state_norm`` as the scalar train loops use them (uav_pos_ctrl_RL.py:36-37,
+    PPO2-4-UavFntsmcParamPos/train.py:291,308): numpy state in, numpy float64 state out -- the loop hands the result to
+    ``agent.choose_action`` and stores it in the learner's numpy ``RolloutBuffer``.  The statistics live in the engine's
+    device ``Normalization`` (one-sample updates follow the reference's Welford recurrence, csrc/norm.cu); ``running_ms`` and
+    everything else is forwarded to it."""
+
+    def __init__(self, norm):
+        self._norm = norm
+
+    def __call__(self, x, update: bool = True):
+        return self._norm(np.asarray(x, dtype=np.float64), update).double().cpu().numpy()
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["_norm"], name)
+
+
 class SingleEnv:
     _OWN = ("_env", "current_state", "next_state", "current_action", "reward", "is_terminal", "terminal_flag", "time",
             "_pending_gains", "_pack")
@@ -40,6 +57,19 @@ class SingleEnv:
 
     def __getattr__(self, name):  # everything else (state_dim, action_dim, action_range, name, dt, timeMax, ...)
         return getattr(self.__dict__["_env"], name)
+
+    # the env's running state normalisers (SecondOrderIntegration.py:76, uav_pos_ctrl_RL.py:36-37) with numpy in / numpy out
+    @property
+    def current_state_norm(self):
+        if "_cur_norm_host" not in self.__dict__:
+            self.__dict__["_cur_norm_host"] = _HostNormalization(self._env.current_state_norm)
+        return self.__dict__["_cur_norm_host"]
+
+    @property
+    def next_state_norm(self):
+        if "_next_norm_host" not in self.__dict__:
+            self.__dict__["_next_norm_host"] = _HostNormalization(self._env.next_state_norm)
+        return self.__dict__["_next_norm_host"]
 
     # ------------------------------------------------------------------ helpers
     def _pull(self, with_obs: bool):
@@ -103,39 +133,11 @@ class SingleEnv:
         self.time = float(time)
 
 
-class _HostNormalization:
-    """``env.current_state_norm`` / ``env.next_state_norm`` as the scalar train loops use them (uav_pos_ctrl_RL.py:36-37,
-    PPO2-4-UavFntsmcParamPos/train.py:291,308): numpy state in, numpy float64 state out -- the loop hands the result to
-    ``agent.choose_action`` and stores it in the learner's numpy ``RolloutBuffer``.  The statistics live in the engine's
-    device ``Normalization`` (one-sample updates follow the reference's Welford recurrence, csrc/norm.cu); ``running_ms`` and
-    everything else is forwarded to it."""
-
-    def __init__(self, norm):
-        self._norm = norm
-
-    def __call__(self, x, update: bool = True):
-        return self._norm(np.asarray(x, dtype=np.float64), update).double().cpu().numpy()
-
-    def __getattr__(self, name):
-        return getattr(self.__dict__["_norm"], name)
-
-
 class SingleUavEnv(SingleEnv):
     """Deferred three-call protocol of the UavFntsmcParam train loops (see module docstring)."""
     _PLACEHOLDER_POS = [float("nan")] * 4   # what generate_action_4_uav() hands back; step_update ignores its values
     _PLACEHOLDER_ATT = np.full(3, np.nan)
 
-    @property
-    def current_state_norm(self):
-        if "_cur_norm_host" not in self.__dict__:
-            self.__dict__["_cur_norm_host"] = _HostNormalization(self._env.current_state_norm)
-        return self.__dict__["_cur_norm_host"]
-
-    @property
-    def next_state_norm(self):
-        if "_next_norm_host" not in self.__dict__:
-            self.__dict__["_next_norm_host"] = _HostNormalization(self._env.next_state_norm)
-        return self.__dict__["_next_norm_host"]
 
     def get_param_from_actor(self, action_from_actor, update_k2: bool = True):
         a = np.array(action_from_actor, dtype=np.float64).reshape(-1)

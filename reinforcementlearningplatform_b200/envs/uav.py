@@ -172,38 +172,6 @@ class _UavBase(VecEnvBase):
         d = None if dis is None else self._as_soa(dis, self._dd)
         self.step_soa(self._zero_action, d)
 
-    @property
-    def current_state_norm(self):
-        """``Normalization(state_dim)`` applied by the train loop to ``current_state`` (uav_pos_ctrl_RL.py:36,
-        PPO2-4-UavFntsmcParamPos/train.py:291); device-resident, see normalization.py."""
-        if getattr(self, "_cur_norm", None) is None:
-            from ..normalization import Normalization
-            self._cur_norm = Normalization(self.state_dim, device=self.device)
-        return self._cur_norm
-
-    @property
-    def next_state_norm(self):
-        if getattr(self, "_next_norm", None) is None:
-            from ..normalization import Normalization
-            self._next_norm = Normalization(self.state_dim, device=self.device)
-        return self._next_norm
-
-    _NORM_COLS = ("cur_n", "cur_mean", "cur_std", "cur_S", "next_n", "next_mean", "next_std", "next_S")
-
-    def save_state_norm(self, path, msg=None):
-        """Same CSV as uav_pos_ctrl_RL.py:208-222 (columns cur_n, cur_mean, cur_std, cur_S, next_n, ...)."""
-        c, x = self.current_state_norm.running_ms, self.next_state_norm.running_ms
-        cols = [c.n * np.ones(self.state_dim), c.mean, c.std, c.S, x.n * np.ones(self.state_dim), x.mean, x.std, x.S]
-        name = path + ('state_norm.csv' if msg is None else 'state_norm_' + msg + '.csv')
-        np.savetxt(name, np.stack(cols, axis=1), delimiter=',', header=','.join(self._NORM_COLS), comments='', fmt='%.17g')
-
-    def load_norm_normalizer_from_file(self, path, file):
-        """uav_pos_ctrl_RL.py:224-233; reads the reference's own ``state_norm.csv`` files."""
-        data = np.atleast_2d(np.genfromtxt(path + file, delimiter=',', skip_header=1))
-        c, x = self.current_state_norm.running_ms, self.next_state_norm.running_ms
-        c.n, c.mean, c.S = data[0, 0], data[:, 1], data[:, 3]
-        x.n, x.mean, x.S = data[0, 4], data[:, 5], data[:, 7]
-
     # reference attribute names
     @property
     def time_max(self):

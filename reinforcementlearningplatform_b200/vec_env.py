@@ -18,6 +18,8 @@ import ctypes as C
 import os
 from typing import Optional
 
+import math
+
 import numpy as np
 import torch
 
@@ -113,6 +115,56 @@ class VecEnvBase:
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ rl_base metadata (algorithm/rl_base.py:5-124)
+    # Descriptive lists the reference keeps next to state_dim / action_dim; the info printers and the PPO / DQN scripts read
+    # them.  Every env of the engine is continuous in state and action unless a subclass says otherwise
+    # (FlightAttitudeSimulatorDiscrete defines action_num / action_space itself).
+    _RL_BASE_LISTS = {"state_num": ("state_dim", math.inf), "state_step": ("state_dim", None), "state_space": ("state_dim", None),
+                      "isStateContinuous": ("state_dim", True), "state_range": ("state_dim", (-math.inf, math.inf)),
+                      "action_num": ("action_dim", math.inf), "action_step": ("action_dim", None),
+                      "action_space": ("action_dim", None), "isActionContinuous": ("action_dim", True)}
+
+    def __getattr__(self, name):  # only reached for names that are not set on the instance or its class
+        spec = VecEnvBase._RL_BASE_LISTS.get(name)
+        if spec is not None:
+            dim = getattr(self, spec[0])
+            return [list(spec[1]) if isinstance(spec[1], tuple) else spec[1] for _ in range(int(dim))]
+        raise AttributeError(f"{type(self).__name__!s} has no attribute {name!r}")
+
+    @property
+    def current_state_norm(self):
+        """``Normalization(state_dim)`` applied by the train loops to ``current_state`` (uav_pos_ctrl_RL.py:36,
+        SecondOrderIntegration.py:76, PPO2-4-UavFntsmcParamPos/train.py:291); device-resident, see normalization.py."""
+        if getattr(self, "_cur_norm", None) is None:
+            from .normalization import Normalization
+            self._cur_norm = Normalization(self.state_dim, device=self.device)
+        return self._cur_norm
+
+    @property
+    def next_state_norm(self):
+        if getattr(self, "_next_norm", None) is None:
+            from .normalization import Normalization
+            self._next_norm = Normalization(self.state_dim, device=self.device)
+        return self._next_norm
+
+    _NORM_COLS = ("cur_n", "cur_mean", "cur_std", "cur_S", "next_n", "next_mean", "next_std", "next_S")
+
+    def save_state_norm(self, path, msg=None):
+        """Same CSV as uav_pos_ctrl_RL.py:208-222 / SecondOrderIntegration.py:354-368 (columns cur_n, cur_mean, cur_std, cur_S,
+        next_n, ...); the PPO2 train scripts of every env call it."""
+        c, x = self.current_state_norm.running_ms, self.next_state_norm.running_ms
+        cols = [c.n * np.ones(self.state_dim), c.mean, c.std, c.S, x.n * np.ones(self.state_dim), x.mean, x.std, x.S]
+        name = path + ('state_norm.csv' if msg is None else 'state_norm_' + msg + '.csv')
+        np.savetxt(name, np.stack(cols, axis=1), delimiter=',', header=','.join(self._NORM_COLS), comments='', fmt='%.17g')
+
+    def load_norm_normalizer_from_file(self, path, file):
+        """uav_pos_ctrl_RL.py:224-233; reads the reference's own ``state_norm.csv`` files."""
+        data = np.atleast_2d(np.genfromtxt(path + file, delimiter=',', skip_header=1))
+        c, x = self.current_state_norm.running_ms, self.next_state_norm.running_ms
+        c.n, c.mean, c.S = data[0, 0], data[:, 1], data[:, 3]
+        x.n, x.mean, x.S = data[0, 4], data[:, 5], data[:, 7]
+
 
     def _io(self, action=None, dis=None, obs=True, reset_obs=True) -> _lib.IO:
         io = _lib.IO()

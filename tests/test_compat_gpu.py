@@ -99,3 +99,30 @@ def test_single_uav_view_has_every_attribute_the_train_scripts_touch(kind):
     env.visualization()
     s = env.current_state_norm(np.zeros(env.state_dim), update=False)
     assert isinstance(s, np.ndarray) and s.dtype == np.float64 and s.shape == (env.state_dim,)
+
+
+@pytest.mark.parametrize("name", ["cartpole", "cartpole_angleonly_ppo2", "fas_ppo2", "soi", "ballbalancer", "twolink",
+                                  "ugv_forward", "ugvo_dppo2", "fas_discrete"])
+def test_single_view_has_every_attribute_the_demo_scripts_touch(name, tmp_path):
+    """Union of `env.<name>` over the reference's DDPG / DQN / PPO / PPO2 / SAC / TD3 train scripts for the non-UAV envs
+    (demonstration/*/*/train.py) plus the descriptive lists of algorithm/rl_base.py:5-124."""
+    import reinforcementlearningplatform_b200 as rlp
+    cls, kw = env_specs()[name]
+    env = rlp.single(cls(n_envs=1, **kw))
+    names = ["action_dim", "action_range", "state_dim", "name", "dt", "current_action", "current_state", "next_state",
+             "is_terminal", "terminal_flag", "reward", "reset", "step_update", "visualization", "save_state_norm",
+             "current_state_norm", "next_state_norm", "action_num", "action_space", "action_step", "state_num", "state_step",
+             "state_space", "state_range", "isStateContinuous", "isActionContinuous", "use_norm"]
+    for n in names:
+        assert hasattr(env, n), (name, n)
+    assert hasattr(env, "timeMax") or hasattr(env, "time_max")
+    assert len(env.action_num) == env.action_dim and len(env.state_range) == env.state_dim
+    if name == "fas_discrete":
+        assert env.action_num[0] == len(env.action_space[0])          # FlightAttitudeSimulatorDiscrete.py:58-59
+    else:
+        assert env.action_num == [np.inf] * env.action_dim and env.isActionContinuous == [True] * env.action_dim
+    env.reset(True)
+    s = env.current_state_norm(env.next_state, update=True)            # PPO-4-*/train.py, PPO2-4-SecondOrderIntegration/train.py
+    assert isinstance(s, np.ndarray) and s.shape == (env.state_dim,)
+    env.save_state_norm(str(tmp_path) + "/")                           # PPO2-4-*/train.py
+    assert (tmp_path / "state_norm.csv").exists()
