@@ -40,6 +40,7 @@ class _UavRobustBase(VecEnvBase):
     STATE_FIELDS = tuple("x y z vx vy vz phi theta psi p q r s1_0 s1_1 s1_2 aref_0 aref_1 aref_2 daref_0 daref_1 daref_2 "
                          "pref_0 pref_1 pref_2 A_0 A_1 A_2 T_0 T_1 T_2 phase_0 phase_1 phase_2".split())
     Q = (1, 0.1, 0.02)
+    msg_print_flag = True  # uav.py:109 (the train scripts switch the terminal prints off; the engine never prints)
 
     def __init__(self, n_envs: int = 1, UAV_param: uav_param = None, att_ctrl_param: fntsmc_param = None, **kw):
         self._up = UAV_param or robust_uav_param()
