@@ -13,8 +13,8 @@
 // range are kept, in np.argsort(centre distance) order; a ray walks that list and stops at the FIRST obstacle it
 // accepts -- the reference's selection rule (note N8: first accepted obstacle in centre-distance order, not the
 // nearest crossing).  Reset / observe and the in-step auto-reset run one warp per instance: warp votes implement the
-// lane-parallel rejection sampling of the obstacle map (32 candidates per round, lowest legal index wins, so the
-// result is identical to trying the candidates one by one).
+// lane-parallel rejection sampling of the obstacle map (64 candidates per round, two per lane; the lowest legal index
+// wins, so the result is identical to trying the candidates one by one).
 #define B200_SOA_INDEX // see common.cuh: the index form is faster for this warp-cooperative kernel
 #include "common.cuh"
 
@@ -631,8 +631,8 @@ ugvo_step_kernel(const __grid_constant__ P p, const __grid_constant__ b200env_io
 // the other, with all 32 lanes (map rejection sampling by ballot, then the 37-ray reset observation).  Kept out of the
 // step kernel because a reset is ~3000 dependent warp instructions: inside the step it left three of the four warps of
 // a block idle behind it (0.60 -> 0.95 ms per step at ~1 reset per block, ncu/bench).  With the optional scratch list
-// io.work the step kernel appends the terminated instances and the warps of this grid share them evenly; without it
-// every warp scans the `done` flags of its 32-instance groups.
+// io.work the step kernel appends the terminated instances and the warps of this grid take them one at a time from a
+// ticket counter; without it every warp scans the `done` flags of its 32-instance groups.
 constexpr int RESET_WARPS = 8;
 #ifndef UGVO_RESET_MINB
 #define UGVO_RESET_MINB 3 // 80 registers, no spills; 3 / 4 / 5 / 6 blocks per SM measured within 1 % of each other
