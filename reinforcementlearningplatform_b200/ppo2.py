@@ -21,6 +21,7 @@ from __future__ import annotations
 import math
 from typing import Optional
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -90,17 +91,24 @@ class VecPPO2:
         env, buf = self.env, self.buffer
         if not env._policy_obs_valid:
             env.reset(True)
-        self._raw_reward_sum.zero_()
+        # Row t of buf.s is the observation the policy acts on at step t: s[0] is copied once, every step then writes its
+        # policy-facing observation straight into the next row (rollout.RolloutBuffer.step, chain_policy_obs).
+        buf.s[0].copy_(env._reset_obs)
+        if self.reward_norm is not None:
+            ms = self.reward_norm.running_ms
+            n0, m0 = float(ms.n), float(np.asarray(ms.mean).reshape(-1)[0])
         for t in range(buf.batch_size):
-            self.policy(env._reset_obs, action=buf.a[t], log_prob=buf.a_lp[t])      # choose_action, PPO2.py:69-76
-            buf.step(env, t, buf.a[t], store_policy_obs=True)                       # step_update + buffer.append
+            self.policy(buf.s[t], action=buf.a[t], log_prob=buf.a_lp[t])            # choose_action, PPO2.py:69-76
+            buf.step(env, t, buf.a[t], chain_policy_obs=True)                       # step_update + buffer.append
             if self.reward_norm is not None:
-                self._raw_reward_sum += buf.r[t].sum(dtype=torch.float64)
                 self.reward_norm.normalize_soa(buf.r[t], out=buf.r[t])              # r = reward_norm(env.reward), :210
         self.total_steps += buf.batch_size * buf.n_envs
         if self.reward_norm is None:
             return float(buf.r.mean())
-        return float(self._raw_reward_sum) / (buf.batch_size * buf.n_envs)
+        # mean raw reward of this rollout from the normaliser's own float64 statistics (n, mean) before and after it (with
+        # a process group they are the group's): no per-step reduction of the reward row
+        n1, m1 = float(ms.n), float(np.asarray(ms.mean).reshape(-1)[0])
+        return (n1 * m1 - n0 * m0) / max(n1 - n0, 1.0)
 
     # ------------------------------------------------------------------ update (PPO2.py:78-170)
     def _log_prob_entropy(self, s, a):

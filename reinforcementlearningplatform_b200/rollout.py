@@ -47,7 +47,8 @@ class RolloutBuffer:
 
     # ------------------------------------------------------------------ filling
     def step(self, env, t: int, action_soa: torch.Tensor, log_prob_soa: Optional[torch.Tensor] = None,
-             dis_soa: Optional[torch.Tensor] = None, store_policy_obs: bool = False) -> None:
+             dis_soa: Optional[torch.Tensor] = None, store_policy_obs: bool = False,
+             chain_policy_obs: bool = False) -> None:
         """``env.step_update(a); buffer.append(s, a, a_lp, r, s_, done, success, t)`` of the train loops (e.g.
         PPO2-4-CartPoleAngleOnly/train.py:193-215) for every instance, in one kernel launch: the step kernel stores
         current_state, next_state, reward, is_terminal and terminal_flag straight into row ``t``.  ``action_soa`` is
@@ -56,6 +57,16 @@ class RolloutBuffer:
             self.a[t].copy_(action_soa)
         if log_prob_soa is not None and self.a_lp is not None:
             self.a_lp[t].copy_(log_prob_soa)
+        if chain_policy_obs:
+            # Row s[t] already IS the observation the policy acted on: the previous step wrote its policy-facing
+            # observation there (the caller copies env.policy_state into s[0] once per rollout), and this step writes its
+            # own into s[t + 1] -- or, for the last row, back into env.policy_state.  No per-step row copy, and the kernels
+            # skip the current_state they would otherwise recompute.
+            nxt = self.s[t + 1] if t + 1 < self.batch_size else env._reset_obs
+            env.step_into(self.a[t], dis_soa, obs=None, next_obs=self.s_[t], reward=self.r[t], done=self.done[t],
+                          flag=self.flag[t], policy_obs=nxt)
+            self.index = t + 1
+            return
         obs_row = self.s[t]
         if store_policy_obs and not (env.reuse_obs and env._policy_obs_valid):
             # Row s[t] = the observation the policy acted on (`s` of PPO2-4-UavFntsmcParamPos/train.py:290-303, the copy

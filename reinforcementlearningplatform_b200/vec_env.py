@@ -308,29 +308,40 @@ class VecEnvBase:
         if rc:
             _lib.check(rc, "b200env_step")
 
-    def step_into(self, action_soa: torch.Tensor, dis_soa: Optional[torch.Tensor] = None, *, obs: torch.Tensor,
-                  next_obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, flag: torch.Tensor) -> None:
+    def step_into(self, action_soa: torch.Tensor, dis_soa: Optional[torch.Tensor] = None, *, obs: Optional[torch.Tensor],
+                  next_obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, flag: torch.Tensor,
+                  policy_obs: Optional[torch.Tensor] = None) -> None:
         """``step_soa`` with the outputs of this step stored into caller-owned tensors (one row of a device-resident
         ``rollout.RolloutBuffer``) instead of the env's own ``current_state / next_state / reward / is_terminal /
-        terminal_flag`` buffers, which are left untouched.  ``policy_state`` is updated as usual.  Shapes:
-        ``obs, next_obs [state_dim, N]``, ``reward [N]`` in ``io_dtype``; ``done [N]`` uint8; ``flag [N]`` int32."""
+        terminal_flag`` buffers, which are left untouched.  Shapes: ``obs, next_obs [state_dim, N]``, ``reward [N]`` in
+        ``io_dtype``; ``done [N]`` uint8; ``flag [N]`` int32.  ``obs=None``: ``current_state`` is not stored (the kernels
+        skip it).  ``policy_obs``: where the observation the policy acts on next (``next_state``, or the reset observation
+        after an auto-reset) is written instead of ``env.policy_state`` -- a collection loop passes the NEXT row of its
+        observation buffer, so that the row is in place when the policy reads it and no copy is made; the caller then owns
+        that chain (``env.policy_state`` is stale until a step writes it again)."""
         io_dt = self.io_dtype
-        for t, shape, dt in ((obs, (self._od, self.n_envs), io_dt), (next_obs, (self._od, self.n_envs), io_dt),
-                             (reward, (self.n_envs,), io_dt), (done, (self.n_envs,), torch.uint8),
-                             (flag, (self.n_envs,), torch.int32)):
+        checks = [(next_obs, (self._od, self.n_envs), io_dt), (reward, (self.n_envs,), io_dt),
+                  (done, (self.n_envs,), torch.uint8), (flag, (self.n_envs,), torch.int32)]
+        if obs is not None:
+            checks.append((obs, (self._od, self.n_envs), io_dt))
+        if policy_obs is not None:
+            checks.append((policy_obs, (self._od, self.n_envs), io_dt))
+        for t, shape, dt in checks:
             if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self._state_raw.device:
                 raise _lib.B200EnvError(f"step_into: expected contiguous {dt} tensor of shape {shape} on {self.device}")
         if action_soa.dtype != io_dt or (dis_soa is not None and dis_soa.dtype != io_dt):
             raise _lib.B200EnvError(f"step_into: action/dis must be {io_dt}")
         with torch.cuda.device(self.device):
             reuse = self.reuse_obs and self._policy_obs_valid
-            if reuse:  # current_state(t) == policy_state(t-1): a row copy instead of a second get_state()
+            if reuse and obs is not None:  # current_state(t) == policy_state(t-1): a row copy instead of a second get_state()
                 obs.copy_(self._reset_obs)
-            io = self._io(action_soa, dis_soa, obs=not reuse)
-            if not reuse:
+            io = self._io(action_soa, dis_soa, obs=False)
+            if not reuse and obs is not None:
                 io.obs = obs.data_ptr()
             io.next_obs, io.reward, io.done, io.flag = next_obs.data_ptr(), reward.data_ptr(), done.data_ptr(), flag.data_ptr()
-            self._policy_obs_valid = True
+            if policy_obs is not None:
+                io.reset_obs = policy_obs.data_ptr()
+            self._policy_obs_valid = policy_obs is None or policy_obs.data_ptr() == self._reset_obs.data_ptr()
             flags = _lib.AUTO_RESET if self.auto_reset else 0
             _lib.check(self._lib.b200env_step(self.ENV_ID, self._dt_code, self.n_envs, C.byref(self._params),
                                               C.sizeof(self._params), C.byref(io), flags, self.seed,

@@ -88,3 +88,33 @@ def test_rollout_collect_equals_step_by_step(name):
     assert torch.equal(e1._state, e2._state) and torch.equal(e1._time, e2._time) and torch.equal(e1._episode, e2._episode)
     assert torch.equal(e1.policy_state, e2.policy_state)
     assert int(b1.done.sum()) > 0 or name in ("uav_att_rand", "twolink", "ballbalancer", "ugv_forward", "soi", "fas_discrete")
+
+
+@pytest.mark.parametrize("name", ["uav_pos", "uav_att_rand", "soi", "ugvo_dppo2", "cartpole"])
+def test_chained_policy_observations_equal_the_copied_ones(name):
+    """RolloutBuffer.step(chain_policy_obs=True) -- every step writes its policy-facing observation straight into the next
+    row of buf.s, current_state is not stored -- fills the buffer with the same bits as the per-step row copy
+    (store_policy_obs=True), and leaves env.policy_state and the persistent state identical."""
+    import torch
+    from reinforcementlearningplatform_b200 import RolloutBuffer
+    cls, kw = env_specs()[name]
+    n, T, seed = 3000, 24, 6
+    mk = lambda: cls(n_envs=n, device="cuda", dtype=torch.float64, io_dtype=torch.float32, seed=seed, auto_reset=True, **kw)
+    e1, e2 = mk(), mk()
+    e1.reset(True)
+    e2.reset(True)
+    b1, b2 = RolloutBuffer(T, e1), RolloutBuffer(T, e2)
+    ar = torch.as_tensor(np.asarray(e1.action_range, dtype=np.float64), device="cuda", dtype=torch.float32)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = ar[:, :1].view(1, -1, 1) + (ar[:, 1:] - ar[:, :1]).view(1, -1, 1) * torch.rand(b1.a.shape, generator=g, device="cuda")
+    b1.a.copy_(a)
+    b2.a.copy_(a)
+    b2.s[0].copy_(e2.policy_state.t())
+    for t in range(T):
+        b1.step(e1, t, b1.a[t], store_policy_obs=True)
+        b2.step(e2, t, b2.a[t], chain_policy_obs=True)
+    torch.cuda.synchronize()
+    for f in ("s", "s_", "r", "done", "flag"):
+        assert torch.equal(getattr(b1, f), getattr(b2, f)), (name, f)
+    assert torch.equal(e1._state, e2._state) and torch.equal(e1._time, e2._time) and torch.equal(e1._episode, e2._episode)
+    assert torch.equal(e1.policy_state, e2.policy_state)
