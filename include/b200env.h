@@ -443,7 +443,13 @@ B200_API int b200_mc_returns(int r_dtype, int64_t T, int64_t N, const void *r, c
  * b200_norm_merge_apply: merges n_batches batch statistics (batch_stats[n_batches][3][dim], e.g. all-gathered over
  *   ranks, merged in index order) into run_in -> run_out (may alias only if y == NULL), then y = (x - mean) / (std +
  *   eps) with the MERGED statistics (y may be x: in-place normalisation).  The merge is Chan's pairwise update written so that a batch of one sample is
- *   bit-identical to the reference's update; update = 0 skips the merge (evaluation: `update=False`). */
+ *   bit-identical to the reference's update; update = 0 skips the merge (evaluation: `update=False`).
+ * b200_norm_rows_prefix: a whole rollout of ONE scalar feature (the reward column, `r = reward_norm(env.reward)` of
+ *   PPO2-4-CartPoleAngleOnly/train.py:210 applied T times) in three launches instead of 2 T: (1) b200_norm_batch_stats with
+ *   dim = rows over the time-major [rows][n] buffer gives every row's batch statistics, (2) this call merges them row after
+ *   row into the running (n, mean, S) -- batch_stats[n_batches][3][rows], each row's batches in index order -- and stores the
+ *   state after every row in cum[3][rows] and the final one in run_out[3], (3) b200_norm_merge_apply with dim = rows,
+ *   run_in = cum and update = 0 normalises row t with the statistics after rows 0..t, as the per-row calls would. */
 B200_API size_t b200_norm_scratch_bytes(int dim);
 B200_API int b200_norm_seq(int dtype, int64_t rows, int dim, const void *x, void *y, double *run, int update, double eps,
                            void *cuda_stream);
@@ -452,6 +458,8 @@ B200_API int b200_norm_batch_stats(int dtype, int64_t n, int dim, const void *x,
 B200_API int b200_norm_merge_apply(int dtype, int64_t n, int dim, const void *x, void *y, const double *batch_stats,
                                    int n_batches, const double *run_in, double *run_out, int update, double eps,
                                    void *cuda_stream);
+B200_API int b200_norm_rows_prefix(int rows, const double *batch_stats, int n_batches, const double *run_in, double *cum,
+                                   double *run_out, void *cuda_stream);
 
 /* ------------------------------------------------------------- batched policy forward */
 

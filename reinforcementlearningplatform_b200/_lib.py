@@ -185,6 +185,8 @@ def load() -> C.CDLL:
     lib.b200_norm_batch_stats.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp]
     lib.b200_norm_merge_apply.restype = i32
     lib.b200_norm_merge_apply.argtypes = [i32, i64, i32, vp, vp, vp, i32, vp, vp, i32, f64, vp]
+    lib.b200_norm_rows_prefix.restype = i32
+    lib.b200_norm_rows_prefix.argtypes = [i32, vp, i32, vp, vp, vp, vp]
     lib.b200_policy_forward.restype = i32
     lib.b200_policy_forward.argtypes = [i64, vp, vp, vp, vp, vp, C.c_float, vp, u64, u64, i64, i32, vp, vp, vp, vp, vp]
     lib.b200_policy_workspace_bytes.restype = sz

@@ -250,6 +250,37 @@ extern "C" B200_API int b200_norm_merge_apply(int dtype, int64_t n, int dim, con
     return b200_check_launch();
 }
 
+// Rows of a time-major [rows][n] buffer of ONE scalar feature (the rewards of a rollout) entering the running statistics
+// row after row: cum[3][rows] = the running (n, mean, S) after rows 0..t have been merged (each row = n_batches batch
+// statistics, e.g. one per rank, in index order), run_out = the state after the last row.  One thread: `rows` dependent
+// merges of a few fp64 operations each.
+__global__ void norm_rows_prefix_kernel(int rows, int n_batches, const double *__restrict__ batch,
+                                        const double *__restrict__ run_in, double *__restrict__ cum,
+                                        double *__restrict__ run_out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Stat s{run_in[0], run_in[1], run_in[2]};
+    for (int t = 0; t < rows; ++t) {
+        for (int b = 0; b < n_batches; ++b) {
+            const double *bs = batch + (int64_t)b * 3 * rows;
+            s = merge(s, bs[t], bs[rows + t], bs[2 * rows + t]);
+        }
+        cum[t] = s.n;
+        cum[rows + t] = s.mean;
+        cum[2 * rows + t] = s.S;
+    }
+    run_out[0] = s.n;
+    run_out[1] = s.mean;
+    run_out[2] = s.S;
+}
+
+extern "C" B200_API int b200_norm_rows_prefix(int rows, const double *batch_stats, int n_batches, const double *run_in,
+                                              double *cum, double *run_out, void *cuda_stream) {
+    if (rows <= 0 || rows > 65535 || n_batches <= 0) return B200ENV_ESIZE;
+    if (!batch_stats || !run_in || !cum || !run_out) return B200ENV_ENULL;
+    norm_rows_prefix_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(rows, n_batches, batch_stats, run_in, cum, run_out);
+    return b200_check_launch();
+}
+
 extern "C" B200_API int b200_norm_seq(int dtype, int64_t rows, int dim, const void *x, void *y, double *run, int update,
                                       double eps, void *cuda_stream) {
     if (rows <= 0 || dim <= 0) return B200ENV_ESIZE;

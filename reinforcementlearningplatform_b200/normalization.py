@@ -152,6 +152,41 @@ class Normalization:
                 self._run, self._run_next = self._run_next, self._run
         return y
 
+    def normalize_rows(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """A whole time-major rollout column ``x [T, N]`` of this (one-dimensional) normaliser's feature -- the rewards of
+        a rollout -- with row t entering the statistics after rows 0..t-1 and normalised with the statistics after row t:
+        what ``T`` calls of ``normalize_soa(x[t], out=x[t])`` do, in three launches (``b200_norm_rows_prefix``).  The
+        batch statistics of a row are summed about the row's first sample instead of the running mean, so the result agrees
+        with the per-row calls to float64 rounding, not bit for bit.  ``out`` may be ``x``."""
+        if self.dim != 1:
+            raise ValueError("normalize_rows: a one-dimensional normaliser (reward scaling)")
+        if not (x.is_cuda and x.is_contiguous() and x.dim() == 2):
+            raise ValueError("normalize_rows: expected a contiguous CUDA [T, N] tensor")
+        T, n = x.shape
+        code = self._code(x)
+        y = torch.empty_like(x) if out is None else out
+        if getattr(self, "_rows_T", None) != T:
+            self._rows_T = T
+            self._rows_batch = torch.zeros(1, 3, T, dtype=torch.float64, device=self.device)
+            self._rows_cum = torch.zeros(3, T, dtype=torch.float64, device=self.device)
+            self._rows_scratch = torch.zeros(self._lib.b200_norm_scratch_bytes(T), dtype=torch.uint8, device=self.device)
+            self._rows_gathered = None
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b200_norm_batch_stats(code, n, T, p(x), None, p(self._rows_batch), p(self._rows_scratch),
+                                                       self._stream()), "b200_norm_batch_stats")
+            nb, batch = 1, self._rows_batch
+            w = self._world()
+            if w > 1:
+                self._rows_gathered = gather_batch_stats(self._rows_batch, self._rows_gathered, self.group)
+                nb, batch = w, self._rows_gathered
+            _lib.check(self._lib.b200_norm_rows_prefix(T, p(batch), nb, p(self._run), p(self._rows_cum), p(self._run_next),
+                                                       self._stream()), "b200_norm_rows_prefix")
+            _lib.check(self._lib.b200_norm_merge_apply(code, n, T, p(x), p(y), None, 0, p(self._rows_cum), None, 0, EPS,
+                                                       self._stream()), "b200_norm_merge_apply")
+            self._run, self._run_next = self._run_next, self._run
+        return y
+
     def __call__(self, x, update: bool = True):
         """Reference call shape: ``x`` is ``[N, dim]`` (or ``[N]`` / a scalar batch for dim == 1); returns the same
         orientation.  ``[dim, N]`` views of the engine's SoA buffers (``env.current_state`` is such a view) are used in

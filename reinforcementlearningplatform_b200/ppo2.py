@@ -100,8 +100,10 @@ class VecPPO2:
         for t in range(buf.batch_size):
             self.policy(buf.s[t], action=buf.a[t], log_prob=buf.a_lp[t])            # choose_action, PPO2.py:69-76
             buf.step(env, t, buf.a[t], chain_policy_obs=True)                       # step_update + buffer.append
-            if self.reward_norm is not None:
-                self.reward_norm.normalize_soa(buf.r[t], out=buf.r[t])              # r = reward_norm(env.reward), :210
+        if self.reward_norm is not None:
+            # r = reward_norm(env.reward) (:210) for the whole column at once: row t enters the statistics after rows < t
+            # and is normalised with the statistics after row t, as the per-step calls did (three launches per rollout)
+            self.reward_norm.normalize_rows(buf.r, out=buf.r)
         self.total_steps += buf.batch_size * buf.n_envs
         if self.reward_norm is None:
             return float(buf.r.mean())

@@ -181,3 +181,36 @@ def test_engine_mc_returns(oracle_lib):
         assert np.array_equal(out.cpu().numpy(), ref)
         out32 = G.mc_returns(torch.from_numpy(r.astype(np.float32)).cuda(), torch.from_numpy(done).cuda(), gamma)
         assert np.array_equal(out32.cpu().numpy(), oracle.mc_returns(r.astype(np.float32).astype(np.float64), done, gamma))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,N", [(16, 4096), (33, 1000), (4, 1)])
+def test_engine_norm_rows_equals_row_by_row(T, N):
+    """normalize_rows over a [T, N] reward column == T calls of normalize_soa(row) (row t enters the statistics after
+    rows < t and is normalised with the statistics after row t), to float64 rounding of the batch sums."""
+    import torch
+    import reinforcementlearningplatform_b200 as rlp
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.randn((T, N), generator=g, device="cuda") * 3.0 - 7.0).float()
+    a, b = rlp.Normalization(1, device="cuda", sync=False), rlp.Normalization(1, device="cuda", sync=False)
+    warm = torch.randn(64, generator=g, device="cuda").float()      # both start from the same non-empty statistics
+    a.normalize_soa(warm.clone())
+    b.normalize_soa(warm.clone())
+    for rep in range(2):                                            # twice: the second rollout continues the first
+        xa, xb = x.clone() + rep, x.clone() + rep
+        for t in range(T):
+            a.normalize_soa(xa[t], out=xa[t])
+        b.normalize_rows(xb, out=xb)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(xb.cpu().numpy(), xa.cpu().numpy(), rtol=2e-6, atol=2e-6)
+        ra, rb = a._run.cpu().numpy(), b._run.cpu().numpy()
+        assert ra[0, 0] == rb[0, 0] == 64 + (rep + 1) * T * N
+        np.testing.assert_allclose(rb, ra, rtol=1e-12)
+    # an empty normaliser: the first row is the first batch (`self.mean = x` branch of the merge)
+    c, d = rlp.Normalization(1, device="cuda", sync=False), rlp.Normalization(1, device="cuda", sync=False)
+    xa, xb = x.clone(), x.clone()
+    for t in range(T):
+        c.normalize_soa(xa[t], out=xa[t])
+    d.normalize_rows(xb, out=xb)
+    np.testing.assert_allclose(xb.cpu().numpy(), xa.cpu().numpy(), rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(d._run.cpu().numpy(), c._run.cpu().numpy(), rtol=1e-12)
