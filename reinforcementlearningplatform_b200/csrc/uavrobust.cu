@@ -69,11 +69,16 @@ __device__ __forceinline__ void observe(const RP &r, const RobDerived &rd, const
             }
         }
     } else {
+        T rA[3], rT[3], rB[3], rP[3], refs[3], drefs[3], ddrefs[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            T ref, dref, dd;
-            ref_channel<T>((T)time, UAV_LDS(io.state, n, R_AMP + k, i), UAV_LDS(io.state, n, R_PER + k, i),
-                           V == 2 ? (T)0 : (T)r.ref_bias_a[k], UAV_LDS(io.state, n, R_PHS + k, i), ref, dref, dd);
+            rA[k] = UAV_LDS(io.state, n, R_AMP + k, i); rT[k] = UAV_LDS(io.state, n, R_PER + k, i);
+            rB[k] = V == 2 ? (T)0 : (T)r.ref_bias_a[k]; rP[k] = UAV_LDS(io.state, n, R_PHS + k, i);
+        }
+        ref_channels<T, 3>((T)time, rA, rT, rB, rP, refs, drefs, ddrefs); // equal (period, phase) share the sincos
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const T ref = refs[k], dref = drefs[k];
             if (V == 2) {
                 e_out[k] = x[6 + k] - ref; de_out[k] = d1[k] - dref;
                 o[k] = qdiv<T>(e_out[k], r.e_att_span[k], rd.r_att[k]) * g;
