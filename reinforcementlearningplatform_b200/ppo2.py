@@ -3,8 +3,9 @@
 The learner of the reference (algorithm/policy_base/Proximal_Policy_Optimization2.py:17-160, Distributed_PPO2.py) with
 the same hyper-parameter dictionary (``ppo_msg``) and the same loss, restructured around N instances on one GPU:
 
-    collect():  policy_state --K-POLICY--> a, log_prob  --step kernel--> s, s_, r, done, flag written straight into the
-                time-major RolloutBuffer; rewards optionally through the running normaliser (K-NORM), T times, no host copy
+    collect():  row t of the buffer's s --K-POLICY--> a, log_prob  --step kernel--> s_, r, done, flag of row t and the
+                policy-facing observation into row t + 1 of s (time-major RolloutBuffer, no copies); after the T steps the
+                reward column goes through the running normaliser (K-NORM) row by row in one pass; no host copy
     learn():    V(s), V(s_) by K-POLICY (critic only) -> K-GAE + global advantage normalisation ->
                 K_epochs x mini-batches of the clipped-surrogate / entropy / value losses (Adam eps 1e-5, grad-norm clip
                 0.5, linear lr decay, as the reference) by K-LEARN (learn.py / csrc/learn.cu: forward + loss + backward
@@ -81,7 +82,6 @@ class VecPPO2:
         self._epoch_key = (int(seed) * 0x9E3779B97F4A7C15 + 0x5851F42D4C957F2D) & (2 ** 64 - 1)
         self.reward_norm = Normalization(1, device=env.device, group=group) if reward_norm else None
         self.total_steps = 0
-        self._raw_reward_sum = torch.zeros((), dtype=torch.float64, device=env.device)
         self._gen = torch.Generator(device=env.device)
         self._gen.manual_seed(seed + 1)
 
