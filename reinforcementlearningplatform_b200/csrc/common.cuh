@@ -33,6 +33,7 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double div(double x, double y) { return x / y; }
     static __device__ __forceinline__ double tanh(double x) { return ::tanh(x); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
+    static __device__ __forceinline__ double log_nonneg(double x) { return ::log(x); }
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
     static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
 #else // fastmath64.cuh: constant-bank coefficients, no special-case ladders, ~1 ulp
@@ -48,6 +49,11 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double div(double x, double y) { return fm64::div(x, y); }
     static __device__ __forceinline__ double tanh(double x) { return fm64::tanh(x); }
     static __device__ __forceinline__ double log(double x) { return fm64::log(x); }
+#ifdef B200_SMC_FULL_LOG
+    static __device__ __forceinline__ double log_nonneg(double x) { return fm64::log(x); }
+#else
+    static __device__ __forceinline__ double log_nonneg(double x) { return fm64::log_nonneg(x); }
+#endif
     static __device__ __forceinline__ double exp(double x) { return fm64::exp(x); }
     static __device__ __forceinline__ double asin(double x) { return fm64::asin(x); }
 #endif
@@ -89,6 +95,7 @@ template <> struct Mth<float> {
     static __device__ __forceinline__ float tanh(float x) { return ::tanhf(x); }
     static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }
     static __device__ __forceinline__ float log(float x) { return ::logf(x); }
+    static __device__ __forceinline__ float log_nonneg(float x) { return ::logf(x); }
     static __device__ __forceinline__ float exp(float x) { return ::expf(x); }
     static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
     static __device__ __forceinline__ float asin(float x) { return ::asinf(x); }

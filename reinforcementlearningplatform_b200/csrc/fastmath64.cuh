@@ -184,6 +184,30 @@ __device__ __forceinline__ double log(double x) {
     return y;
 }
 
+// log of a value that is an absolute value (|e|, |s| of the sliding surfaces): the same evaluation without the two guards
+// a magnitude cannot trigger by being negative.  NaN and +inf arguments give an unspecified finite value here; the callers'
+// expressions carry the argument itself in a linear term, which propagates NaN / inf whatever this returns.
+__device__ __forceinline__ double log_nonneg(double x) {
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int k = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int i = (hi + 0x95f64) & 0x100000;
+    k += i >> 20;
+    const double m = __hiloint2double(hi | (i ^ 0x3ff00000), lo);
+    const double f = m - 1.0;
+    const double s = div(f, 2.0 + f);
+    const double z = s * s;
+    double R = kL[6];
+    R = fma(R, z, kL[5]); R = fma(R, z, kL[4]); R = fma(R, z, kL[3]); R = fma(R, z, kL[2]); R = fma(R, z, kL[1]);
+    R = fma(R, z, kL[0]);
+    R *= z;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    const double y = dk * kR[4] - ((hfsq - (s * (hfsq + R) + dk * kR[5])) - f);
+    return x < 2.2250738585072014e-308 ? -CUDART_INF : y; // zero / subnormal
+}
+
 // tanh, branch-free; ~2e-16 absolute accuracy
 __device__ __forceinline__ double tanh(double x) {
     const double ax = (fabs(x) > 20.0) ? 20.0 : fabs(x); // tanh(20) rounds to 1; NaN stays NaN (comparison false)

@@ -173,7 +173,7 @@ __device__ SMC_INLINE void smc_axis(T e, T de, T k1, T gamma, T alpha, T beta, T
     pa1_de = gamma * alpha * Mth<T>::pow(ae, alpha - (T)1) * de;
     return;
 #endif
-    const T L = Mth<T>::log(ae);
+    const T L = Mth<T>::log_nonneg(ae);
     const T pa1 = pow_from_log<T>(L, alpha - (T)1);
 #ifdef B200_SMC_TWO_EXP
     const T pa = pow_from_log<T>(L, alpha);
@@ -182,7 +182,7 @@ __device__ SMC_INLINE void smc_axis(T e, T de, T k1, T gamma, T alpha, T beta, T
     const T pa = alpha == (T)0 ? (T)1 : ((ae == (T)0 && alpha > (T)0) ? (T)0 : pa_);
 #endif
     const T s = de + k1 * e + gamma * pa * Mth<T>::tanh((T)5 * e);
-    dot_s1 = pow_from_log<T>(Mth<T>::log(Mth<T>::abs(s)), beta) * Mth<T>::tanh((T)5 * s);
+    dot_s1 = pow_from_log<T>(Mth<T>::log_nonneg(Mth<T>::abs(s)), beta) * Mth<T>::tanh((T)5 * s);
     integ += dot_s1 * dt;
     s_out = s + lmd * integ;           // sigma (att) / so (pos)
     pa1_de = gamma * alpha * pa1 * de; // gamma * alpha * |e|^(alpha-1) * de
