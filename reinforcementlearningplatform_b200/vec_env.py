@@ -56,6 +56,10 @@ class VecEnvBase:
         self.host_only = bool(host_only)
         if host_only:  # parameter/attribute mirror only (CPU tests, oracle drivers): no buffers, no launches
             self.n_envs, self.dtype = int(n_envs), dtype
+            try:  # b200env_dims is a host function of the library; without a built library the mirror has no dims
+                _, self.state_dim, self.action_dim, _ = _lib.dims(self.ENV_ID, self.VARIANT)
+            except (OSError, _lib.B200EnvError):
+                pass
             return
         self._lib = _lib.load()  # raises if the CUDA engine is not built
         self.device = torch.device(device)

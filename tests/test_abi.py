@@ -55,3 +55,41 @@ def test_engine_refuses_cpu_device():
     from reinforcementlearningplatform_b200 import _lib
     with pytest.raises(_lib.B200EnvError):
         rlp.CartPole(n_envs=4, device="cpu")
+
+
+def test_host_mirrors_carry_the_rl_base_description(lib):
+    """Without a GPU: the host-only mirror of every env class has the dimensions the library reports (b200env_dims) and the
+    descriptive lists of algorithm/rl_base.py:5-124 with one entry per dimension -- continuous everywhere except the
+    discrete action set of FlightAttitudeSimulatorDiscrete (FlightAttitudeSimulatorDiscrete.py:58-59)."""
+    import math
+    import numpy as np
+    import reinforcementlearningplatform_b200 as rlp
+    from reinforcementlearningplatform_b200 import _lib
+    makers = [lambda: rlp.CartPole(n_envs=1, host_only=True),
+              lambda: rlp.CartPoleAngleOnly(n_envs=1, variant='env', host_only=True),
+              lambda: rlp.CartPoleAngleOnly(n_envs=1, variant='ppo2', host_only=True),
+              lambda: rlp.Flight_Attitude_Simulator(n_envs=1, host_only=True),
+              lambda: rlp.FlightAttitudeSimulatorDiscrete(n_envs=1, host_only=True),
+              lambda: rlp.SecondOrderIntegration(n_envs=1, host_only=True),
+              lambda: rlp.BallBalancer1D(n_envs=1, host_only=True),
+              lambda: rlp.TwoLinkManipulator(n_envs=1, host_only=True),
+              lambda: rlp.UGVForward(n_envs=1, host_only=True),
+              lambda: rlp.UGVBidirectional(n_envs=1, host_only=True),
+              lambda: rlp.UGVForwardObstacleAvoidance(n_envs=1, variant='dppo2', host_only=True),
+              lambda: rlp.UavAttCtrlRL(n_envs=1, host_only=True),
+              lambda: rlp.UavPosCtrlRL(n_envs=1, host_only=True),
+              lambda: rlp.uav_hover(n_envs=1, host_only=True)]
+    for mk in makers:
+        e = mk()
+        _, od, ad, _ = _lib.dims(e.ENV_ID, e.VARIANT)
+        assert (e.state_dim, e.action_dim) == (od, ad), type(e).__name__
+        assert np.asarray(e.action_range, dtype=float).shape == (ad, 2), type(e).__name__
+        assert len(e.state_num) == len(e.state_range) == len(e.isStateContinuous) == od
+        assert len(e.action_num) == len(e.action_space) == ad
+        if isinstance(e, rlp.FlightAttitudeSimulatorDiscrete):
+            assert e.action_num[0] == len(e.action_space[0]) and e.action_num[0] > 1
+        else:
+            assert e.action_num == [math.inf] * ad and e.isActionContinuous == [True] * ad
+        assert isinstance(e.name, str) and hasattr(e, "use_norm")
+        with pytest.raises(AttributeError):
+            e.no_such_attribute
