@@ -1,6 +1,7 @@
 """CPU: the C restatement (oracle/) against the fixtures recorded from the live reference.
 This is the pin of the oracle: the reference ships no golden vectors, so the
 fixtures under tests/golden/ -- outputs of the unmodified reference classes -- are the authority."""
+import numpy as np
 import pytest
 
 from helpers import OracleBackend, load_golden, replay
@@ -99,3 +100,44 @@ def test_time_loop_substep_trace(name, h, both, oracle_lib):
             be.set_state(g["reset_state"][t][lanes], g["reset_time"][t][lanes], lanes)
             prev_time[lanes] = g["reset_time"][t][lanes]
     assert seen == ({10, 11} if both else {10}), seen
+
+
+def test_oracle_ugvo_reset_draws_legal_maps(oracle_lib):
+    """The engine-defined reset of UGVForwardObstacleAvoidance (Philox draws keyed by (seed, instance, episode); one block
+    per obstacle candidate, the radius from the 22 bits the two 53-bit coordinates leave over -- csrc/ugvo.cu draw3,
+    oracle/c/ugvo.c) against the rules of reset() :527-557 and Map.generate_circle_obs_training (map.py:120-174):
+    clearances to start, target and between obstacles, radii in [r_min, r_max], radius resolution 2^-22 of the range;
+    the draws depend on the global instance index only (not on how instances are split over calls)."""
+    import reinforcementlearningplatform_b200 as rlp
+    from oracle import oracle
+    from reinforcementlearningplatform_b200 import _lib
+    host = rlp.UGVForwardObstacleAvoidance(n_envs=1, variant='dppo2', host_only=True)
+    p = host._params
+    sf, od, ad, dd = _lib.dims(_lib.UGVO, host.VARIANT)
+    n = 96
+    orc = oracle.OracleEnv(_lib.UGVO, p, n, sf, od, ad, dd, seed=5)
+    orc.reset()
+    st = orc.state
+    sx, sy, tx, ty, nobs = st[0], st[1], st[5], st[6], st[7].astype(int)
+    assert np.all((sx >= p.st_margin) & (sx <= p.map_x - p.st_margin) & (sy >= p.st_margin) & (sy <= p.map_y - p.st_margin))
+    assert np.all(np.hypot(tx - sx, ty - sy) >= p.safety_dis_st)
+    assert nobs.min() >= 1 and nobs.max() <= p.obs_num and (nobs == p.obs_num).mean() > 0.2
+    levels = set()
+    for i in range(n):
+        c = st[8:8 + 3 * nobs[i], i].reshape(-1, 3)
+        cx, cy, r = c[:, 0], c[:, 1], c[:, 2]
+        assert np.all((r >= p.r_min) & (r <= p.r_max)) and np.all((cx >= 0) & (cx <= p.map_x) & (cy >= 0) & (cy <= p.map_y))
+        assert np.all(np.hypot(cx - sx[i], cy - sy[i]) > r + p.safety_dis_st)
+        assert np.all(np.hypot(cx - tx[i], cy - ty[i]) > r + p.safety_dis_st)
+        d = np.hypot(cx[:, None] - cx[None, :], cy[:, None] - cy[None, :]) + np.eye(len(r)) * 1e9
+        assert np.all(d > r[:, None] + r[None, :] + p.safety_dis_obs)
+        assert np.all(st[8 + 3 * nobs[i]:, i] == 0.0)                       # unused slots are zero
+        u = (r - p.r_min) / (p.r_max - p.r_min) * 4194304.0                    # radius = lerp(r_min, r_max, k / 2^22)
+        assert np.all(np.abs(u - np.round(u)) < 1e-6)
+        levels.update(np.round(u).astype(int).tolist())
+    assert len(levels) > 0.9 * nobs.sum()                                      # the 22 bits are actually used
+    # instance i of an 96-instance call == instance 0 of a call offset by i
+    for i in (0, 17, 95):
+        one = oracle.OracleEnv(_lib.UGVO, p, 1, sf, od, ad, dd, seed=5, env_index_offset=i)
+        one.reset()
+        assert np.array_equal(one.state[:, 0], st[:, i])
